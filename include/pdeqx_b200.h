@@ -1,0 +1,210 @@
+/* pdeqx_b200.h -- C ABI of libpdeqx_b200.so (sm_100a).
+ *
+ * Drop-in boundary for pdequinox's data-parallel hot path. The reference has no
+ * native interface: its boundary is the Python eqx.Module call on one sample
+ * under jax.vmap. These entry points are what an XLA FFI
+ * custom call (jax.ffi.ffi_call inside jax.custom_vjp) binds for each of those
+ * calls; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every tensor argument is a DEVICE pointer to contiguous float32, channels
+ *     first, last spatial axis contiguous: x[B, C, *S] (the reference's
+ *     single-sample (C,*S) convention with the vmap axis in front);
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*): no synchronisation, no allocation; scratch memory is passed in;
+ *   - return value 0 = ok, negative = error (PDEQX_ERR_*); the message of the
+ *     last error on the calling thread is pdeqx_last_error();
+ *   - the library keeps no mutable global state besides plan objects owned by
+ *     the caller. Plans are immutable after creation and may be shared by
+ *     threads/streams of the same device.
+ */
+#ifndef PDEQX_B200_H_
+#define PDEQX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEQX_OK 0
+#define PDEQX_ERR_INVALID_ARGUMENT (-1)
+#define PDEQX_ERR_UNSUPPORTED (-2)
+#define PDEQX_ERR_CUDA (-3)
+#define PDEQX_ERR_WORKSPACE (-4)
+
+#define PDEQX_MAX_DIMS 3
+
+/* activation fused into an epilogue */
+enum pdeqx_activation {
+  PDEQX_ACT_IDENTITY = 0,
+  PDEQX_ACT_RELU = 1,     /* jax.nn.relu  (ClassicResNet/DilatedResNet/ClassicUNet default) */
+  PDEQX_ACT_GELU_TANH = 2 /* jax.nn.gelu(approximate=True) (ClassicFNO default, _classic_fno.py:20) */
+};
+
+/* halo construction; PhysicsConv maps periodic->WRAP, dirichlet->ZEROS,
+ * neumann->REFLECT (pdequinox/conv/_physics_conv.py:92-101); EDGE is
+ * MorePaddingConv's "replicate" (pdequinox/conv/_conv.py:198-200). */
+enum pdeqx_boundary {
+  PDEQX_PAD_ZEROS = 0,
+  PDEQX_PAD_WRAP = 1,
+  PDEQX_PAD_REFLECT = 2,
+  PDEQX_PAD_EDGE = 3
+};
+
+/* arithmetic of the tensor-core stages. The CUDA-core stages are always fp32. */
+enum pdeqx_precision {
+  PDEQX_PREC_FP32 = 0,  /* fp32 parity mode: FFMA or 3xTF32 split; rel-L2 <= 1e-5 */
+  PDEQX_PREC_TF32 = 1   /* single-pass TF32 on tcgen05; rel-L2 <= 2e-3 */
+};
+
+const char* pdeqx_last_error(void);
+/* "major.minor.patch (sm_100a)" */
+const char* pdeqx_version(void);
+/* number of kernels this library has launched on the calling process since load
+ * (bench.py's gpu_launches claim is read from here). */
+uint64_t pdeqx_launch_count(void);
+/* 1 if the tcgen05/TMA fast paths can run on the current device (sm_100). */
+int pdeqx_has_tcgen05(void);
+/* force-disable (0) / enable (1) the tcgen05 fast paths (tests compare both). */
+void pdeqx_set_fast_paths(int enabled);
+
+/* ------------------------------------------------------------------------- *
+ * SpectralConv / ClassicSpectralBlock
+ *   replaces pdequinox/conv/_spectral_conv.py:107-136 (spectral_conv_nd) and
+ *   pdequinox/blocks/_classic_spectral_block.py:72-75 (block __call__)
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t ndim;                    /* 1..3 */
+  int32_t batch;                   /* vmap axis */
+  int32_t c_in, c_out;             /* call-time i / o of the weight (G, o, i, *modes) */
+  int32_t spatial[PDEQX_MAX_DIMS]; /* S */
+  int32_t modes[PDEQX_MAX_DIMS];   /* num_modes per axis */
+  int32_t precision;               /* enum pdeqx_precision */
+} pdeqx_spectral_desc;
+
+typedef struct pdeqx_spectral_plan pdeqx_spectral_plan; /* opaque: twiddle tables on the device */
+
+/* Builds twiddle tables in float64 on the host, rounds to float32, uploads to the
+ * CURRENT device. Synchronous (cudaMalloc + cudaMemcpy); call outside hot loops.
+ * Errors: modes[-1] > S[-1]/2+1 or modes[a] > S[a] (the reference's einsum
+ * shape-errors there). 2*modes[a] > S[a] is accepted with the reference's
+ * "later corner block overwrites" semantics. */
+int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx_spectral_plan** plan);
+void pdeqx_spectral_plan_destroy(pdeqx_spectral_plan* plan);
+/* bytes of scratch the fwd / bwd calls need (max over both) */
+size_t pdeqx_spectral_workspace_bytes(const pdeqx_spectral_plan* plan);
+/* number of floats of the saved tensors: x_hat = [B, c_in, modes...] complex,
+ * z = [B, c_out, S_1..S_{D-1}, m_D] complex (input of the last inverse stage) */
+size_t pdeqx_spectral_xhat_floats(const pdeqx_spectral_plan* plan);
+size_t pdeqx_spectral_z_floats(const pdeqx_spectral_plan* plan);
+
+/* y[B,c_out,*S] = act( irfftn(mix(rfftn(x))) + (bypass_w . x + bypass_b) )
+ *   w_re, w_im : [G, c_out, c_in, *modes] (G = 2^(ndim-1), corner order of
+ *                generate_modes_slices, _spectral_conv.py:73-104)
+ *   bypass_w   : [c_out, c_in] or NULL (plain SpectralConv); bypass_b [c_out] or NULL
+ *   save_xhat, save_z : outputs kept for the backward pass, or NULL (inference)
+ */
+int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* plan, const float* x, const float* w_re,
+                             const float* w_im, const float* bypass_w, const float* bypass_b,
+                             int32_t activation, float* y, float* save_xhat, float* save_z,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* VJP of the call above (what jax.custom_vjp's bwd rule binds).
+ *   gy [B,c_out,*S] cotangent of y; x, saved_xhat, saved_z from the forward.
+ *   Outputs (overwritten, weight grads summed over the batch):
+ *   gx [B,c_in,*S]; gw_re, gw_im [G,c_out,c_in,*modes]; g_bypass_w [c_out,c_in];
+ *   g_bypass_b [c_out] (the last two may be NULL when bypass_w is NULL).
+ *   gx may be NULL (first layer). scratch_full: [B,c_out,*S] floats (g_pre).
+ */
+int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* plan, const float* x, const float* gy,
+                             const float* w_re, const float* w_im, const float* bypass_w,
+                             const float* bypass_b, int32_t activation, const float* saved_xhat,
+                             const float* saved_z, float* gx, float* gw_re, float* gw_im,
+                             float* g_bypass_w, float* g_bypass_b, float* scratch_full,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * PointwiseLinearConv (1x1 conv)
+ *   replaces pdequinox/conv/_pointwise_linear_conv.py:6-53 (eqx.nn.Conv, k=1)
+ * ------------------------------------------------------------------------- */
+/* y[B,c_out,N] = act(w[c_out,c_in] . x[B,c_in,N] + b[c_out] + add[B,c_out,N]); b, add may be NULL */
+int pdeqx_pointwise_fwd(int32_t batch, int32_t c_in, int32_t c_out, int64_t n_pixels, const float* x,
+                        const float* w, const float* b, const float* add, int32_t activation,
+                        float* y, void* stream);
+/* gx = w^T . gy (gx may be NULL); gw[c_out,c_in] = sum_{b,n} gy x^T; gb[c_out] = sum gy (may be NULL).
+ * Outputs are overwritten. */
+int pdeqx_pointwise_bwd(int32_t batch, int32_t c_in, int32_t c_out, int64_t n_pixels, const float* x,
+                        const float* w, const float* gy, float* gx, float* gw, float* gb,
+                        void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * PhysicsConv / MorePaddingConv
+ *   replaces pdequinox/conv/_conv.py:169-219 with the padding of
+ *   pdequinox/conv/_physics_conv.py:11-26; the halo is built in shared memory.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t ndim; /* 1..3 */
+  int32_t batch;
+  int32_t c_in, c_out, groups;
+  int32_t spatial[PDEQX_MAX_DIMS]; /* input S */
+  int32_t kernel[PDEQX_MAX_DIMS];
+  int32_t stride[PDEQX_MAX_DIMS];
+  int32_t dilation[PDEQX_MAX_DIMS];
+  int32_t pad_lo[PDEQX_MAX_DIMS], pad_hi[PDEQX_MAX_DIMS];
+  int32_t boundary; /* enum pdeqx_boundary */
+} pdeqx_conv_desc;
+
+/* output spatial size per axis: floor((s + lo + hi - d(k-1) - 1)/stride) + 1 */
+int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]);
+/* y = act(corr(pad(x), w) + b + residual); w [c_out, c_in/groups, *k]; b [c_out]; b, residual may be NULL */
+int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b,
+                   const float* residual, int32_t activation, float* y, void* stream);
+/* gx = adjoint-of-pad( corr^T(gy, w) ) + add, overwritten; add [B,c_in,*S] may be NULL (it carries
+ * the cotangent of a residual connection into the same pass) */
+int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add,
+                        float* gx, void* stream);
+/* gw[c_out,c_in/groups,*k] = sum_{b,p} gy . pad(x); gb[c_out] = sum gy (may be NULL); overwritten */
+int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, float* gw,
+                          float* gb, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * GroupNorm (eqx.nn.GroupNorm, eps 1e-5, biased variance, per-channel affine)
+ *   call sites: pdequinox/blocks/_dilated_res_block.py:88-99,143-146,
+ *   _classic_double_conv_block.py:75-83, _classic_res_block.py:80-89
+ * ------------------------------------------------------------------------- */
+size_t pdeqx_groupnorm_workspace_bytes(int32_t batch, int32_t channels);
+/* y[B,C,n] = (x - mean_g) * rstd_g * weight[c] + bias[c]; stats [B,groups,2] = (mean, rstd) is an output
+ * kept for the backward pass; weight/bias may be NULL; workspace: pdeqx_groupnorm_workspace_bytes. */
+int pdeqx_groupnorm_fwd(int32_t batch, int32_t channels, int32_t groups, int64_t n, const float* x,
+                        const float* weight, const float* bias, float eps, float* y, float* stats,
+                        void* workspace, void* stream);
+/* gx, gweight[C], gbias[C] (overwritten; the last two may be NULL); scratch: 2*B*C floats */
+int pdeqx_groupnorm_bwd(int32_t batch, int32_t channels, int32_t groups, int64_t n, const float* x,
+                        const float* weight, const float* stats, const float* gy, float* gx,
+                        float* gweight, float* gbias, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Elementwise pieces of the block / training step
+ * ------------------------------------------------------------------------- */
+/* gx = gy * act'(pre) (gelu'/relu' evaluated on the PRE-activation) */
+int pdeqx_activation_bwd(int64_t n, const float* pre, const float* gy, int32_t activation, float* gx,
+                         void* stream);
+/* y = act(x) */
+int pdeqx_activation_fwd(int64_t n, const float* x, int32_t activation, float* y, void* stream);
+/* out = a + b (residual joins that cannot be fused into an epilogue); out may alias a or b */
+int pdeqx_add(int64_t n, const float* a, const float* b, float* out, void* stream);
+/* loss[0] = mean((pred-target)^2) (jnp.mean over all elements, README.md:74-76);
+ * gpred = grad_scale * 2/n * (pred-target) (may be NULL). partials: >= 1024 floats scratch. */
+int pdeqx_mse_loss(int64_t n, const float* pred, const float* target, float grad_scale, float* loss,
+                   float* gpred, float* partials, void* stream);
+/* optax.adam update on a flat arena: g is first multiplied by grad_scale (1/world_size).
+ * step is the 1-based update count (bias correction). */
+int pdeqx_adam_step(int64_t n, float* param, const float* grad, float* mu, float* nu, float lr,
+                    float b1, float b2, float eps, int32_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEQX_B200_H_ */

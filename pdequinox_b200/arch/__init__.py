@@ -1,0 +1,5 @@
+from ._classic_fno import ClassicFNO
+from ._classic_res_net import ClassicResNet
+from ._dilated_res_net import DilatedResNet
+
+__all__ = ["ClassicFNO", "ClassicResNet", "DilatedResNet"]

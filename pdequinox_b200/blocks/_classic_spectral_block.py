@@ -1,0 +1,48 @@
+"""ClassicSpectralBlock: activation(spectral_conv(x) + by_pass_conv(x)) as ONE fused call
+(reference: pdequinox/blocks/_classic_spectral_block.py:10-131)."""
+from .. import nn, random as jr
+from ..conv import PointwiseLinearConv, SpectralConv
+from ._base_block import Block, BlockFactory
+
+
+class ClassicSpectralBlock(Block):
+    _fields = ("spectral_conv", "by_pass_conv", "activation")
+
+    def __init__(self, num_spatial_dims, in_channels, out_channels, *, activation=nn.gelu, num_modes=8,
+                 use_bias=True, zero_bias_init=False, key):
+        self.num_spatial_dims = num_spatial_dims
+        k_1, k_2 = jr.split(key)
+        self.spectral_conv = SpectralConv(num_spatial_dims=num_spatial_dims, in_channels=in_channels,
+                                          out_channels=out_channels, num_modes=num_modes, key=k_1)
+        self.by_pass_conv = PointwiseLinearConv(num_spatial_dims=num_spatial_dims, in_channels=in_channels,
+                                                out_channels=out_channels, use_bias=use_bias,
+                                                zero_bias_init=zero_bias_init, key=k_2)
+        self.activation = activation
+
+    @property
+    def receptive_field(self):
+        return self.spectral_conv.receptive_field
+
+    def _fwd(self, x, tape):
+        act = nn.activation_code(self.activation)
+        y, saved = self.spectral_conv.apply(x, tape, bypass=self.by_pass_conv, act=act, save=tape is not None)
+        if tape is not None:
+            tape.push((x, saved))
+        return y
+
+    def _bwd(self, gy, tape, need_gx=True):
+        x, saved = tape.pop()
+        return self.spectral_conv.apply_bwd(x, gy, saved, tape, bypass=self.by_pass_conv,
+                                            act=nn.activation_code(self.activation), need_gx=need_gx)
+
+
+class ClassicSpectralBlockFactory(BlockFactory):
+    def __init__(self, *, num_modes=8, use_bias: bool = True, zero_bias_init: bool = False):
+        self.num_modes = num_modes
+        self.use_bias = use_bias
+        self.zero_bias_init = zero_bias_init
+
+    def __call__(self, num_spatial_dims, in_channels, out_channels, *, activation, boundary_mode, key):
+        return ClassicSpectralBlock(num_spatial_dims=num_spatial_dims, in_channels=in_channels,
+                                    out_channels=out_channels, num_modes=self.num_modes, activation=activation,
+                                    key=key, use_bias=self.use_bias, zero_bias_init=self.zero_bias_init)

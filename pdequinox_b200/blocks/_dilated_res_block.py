@@ -1,0 +1,114 @@
+"""DilatedResBlock: per dilation rate norm -> conv -> act, then + bypass
+(reference: pdequinox/blocks/_dilated_res_block.py:18-158)."""
+from .. import _lib, nn, random as jr
+from ..conv import PhysicsConv, PointwiseLinearConv
+from ..nn import Identity
+from ._base_block import Block, BlockFactory
+
+
+class DilatedResBlock(Block):
+    _fields = ("norm_layers", "conv_layers", "activation", "bypass_conv", "bypass_norm")
+
+    def __init__(self, num_spatial_dims, in_channels, out_channels, *, activation=nn.relu, kernel_size=3,
+                 dilation_rates=(1, 2, 4, 8, 4, 2, 1), use_norm=True, num_groups=1, use_bias=True,
+                 zero_bias_init=False, boundary_mode, key):
+        self.num_spatial_dims = num_spatial_dims
+
+        def conv_constructor(i, o, d, b, k):
+            return PhysicsConv(num_spatial_dims=num_spatial_dims, in_channels=i, out_channels=o,
+                               kernel_size=kernel_size, stride=1, dilation=d, boundary_mode=boundary_mode,
+                               use_bias=b, zero_bias_init=zero_bias_init, key=k)
+
+        if use_norm:
+            norm_layers = [nn.GroupNorm(groups=num_groups, channels=in_channels)]
+            for _ in dilation_rates[1:]:
+                norm_layers.append(nn.GroupNorm(groups=num_groups, channels=out_channels))
+            self.norm_layers = tuple(norm_layers)
+        else:
+            self.norm_layers = tuple(Identity() for _ in dilation_rates)
+        key, *keys = jr.split(key, len(dilation_rates) + 1)  # _dilated_res_block.py:103
+        conv_layers = [conv_constructor(in_channels, out_channels, dilation_rates[0], use_bias, keys[0])]
+        for d, k in zip(dilation_rates[1:], keys[1:]):
+            conv_layers.append(conv_constructor(out_channels, out_channels, d, use_bias, k))
+        self.conv_layers = tuple(conv_layers)
+        self.activation = activation
+        if out_channels != in_channels:
+            self.bypass_norm = nn.GroupNorm(groups=num_groups, channels=in_channels) if use_norm else Identity()
+            bypass_conv_key, _ = jr.split(key)
+            self.bypass_conv = PointwiseLinearConv(num_spatial_dims=num_spatial_dims, in_channels=in_channels,
+                                                   out_channels=out_channels, use_bias=use_bias,
+                                                   zero_bias_init=zero_bias_init, key=bypass_conv_key)
+        else:
+            self.bypass_conv = Identity()
+            self.bypass_norm = Identity()
+
+    @property
+    def receptive_field(self):
+        from .._utils import sum_receptive_fields
+        return sum_receptive_fields(tuple(c.receptive_field for c in self.conv_layers))
+
+    def _fwd(self, x, tape):
+        act = nn.activation_code(self.activation)
+        fuse = act in (_lib.ACT_RELU, _lib.ACT_IDENTITY)
+        identity_skip = isinstance(self.bypass_conv, Identity)
+        skip = x if identity_skip else self.bypass_conv._fwd(self.bypass_norm._fwd(x, tape), tape)
+        h = x
+        saved = []
+        last = len(self.conv_layers) - 1
+        for j, (norm, conv) in enumerate(zip(self.norm_layers, self.conv_layers)):
+            hn = norm._fwd(h, tape)
+            if fuse:
+                out = conv.apply(hn, tape, act=act, tag="a")
+                saved.append((hn, out, None))
+            else:
+                pre = conv.apply(hn, tape, tag="p")
+                out = nn.apply_activation(pre, act, tape, conv, "a")
+                saved.append((hn, out, pre))
+            h = out
+        y = nn.add(h, skip, tape, self, "y")
+        if tape is not None:
+            tape.push(saved)
+        return y
+
+    def _bwd(self, gy, tape, need_gx=True):
+        act = nn.activation_code(self.activation)
+        saved = tape.pop()
+        identity_skip = isinstance(self.bypass_conv, Identity)
+        g = gy
+        for j in reversed(range(len(self.conv_layers))):
+            hn, out, pre = saved[j]
+            conv, norm = self.conv_layers[j], self.norm_layers[j]
+            ga = nn.activation_bwd(pre if pre is not None else out, g, act, tape, conv, "ga")
+            first = j == 0
+            no_norm = isinstance(norm, Identity)
+            want = need_gx or not first
+            add = gy if (first and identity_skip and no_norm) else None
+            g = conv.apply_bwd(hn, ga, tape, want, tag="gx", add=add)
+            if want and not no_norm:
+                g = norm._bwd(g, tape)
+                if first and identity_skip:
+                    g = nn.add(g, gy, tape, self, "gx")
+        if not identity_skip:
+            gs = self.bypass_norm._bwd(self.bypass_conv._bwd(gy, tape, need_gx), tape) if need_gx else \
+                self.bypass_conv._bwd(gy, tape, False)
+            if need_gx:
+                g = nn.add(g, gs, tape, self, "gx")
+        return g if need_gx else None
+
+
+class DilatedResBlockFactory(BlockFactory):
+    def __init__(self, kernel_size=3, dilation_rates=(1, 2, 4, 8, 4, 2, 1), *, use_norm=True, num_groups=1,
+                 use_bias=True, zero_bias_init=False):
+        self.kernel_size = kernel_size
+        self.dilation_rates = dilation_rates
+        self.use_norm = use_norm
+        self.num_groups = num_groups
+        self.use_bias = use_bias
+        self.zero_bias_init = zero_bias_init
+
+    def __call__(self, num_spatial_dims, in_channels, out_channels, *, activation, boundary_mode, key):
+        return DilatedResBlock(num_spatial_dims, in_channels, out_channels, activation=activation,
+                               kernel_size=self.kernel_size, dilation_rates=self.dilation_rates,
+                               boundary_mode=boundary_mode, key=key, use_norm=self.use_norm,
+                               num_groups=self.num_groups, use_bias=self.use_bias,
+                               zero_bias_init=self.zero_bias_init)

@@ -1,0 +1,128 @@
+"""SpectralConv: FNO spectral convolution as a fused truncated-DFT pipeline.
+
+reference: pdequinox/conv/_spectral_conv.py:10-136 (rfftn -> per-corner complex einsum -> irfftn).
+Only the retained modes are computed (dense twiddle GEMMs); the zero-filled spectrum never exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib, random as jr
+from .._module import Module, default_device, new_buf, precision_code, to_param
+
+
+class _Plan:
+    def __init__(self, desc):
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().pdeqx_spectral_plan_create(desc, C.byref(self.handle)))
+        L = _lib.lib()
+        self.ws_bytes = L.pdeqx_spectral_workspace_bytes(self.handle)
+        self.xhat_floats = L.pdeqx_spectral_xhat_floats(self.handle)
+        self.z_floats = L.pdeqx_spectral_z_floats(self.handle)
+        self.workspace = torch.empty(self.ws_bytes // 4 + 1, dtype=torch.float32, device=default_device())
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().pdeqx_spectral_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_PLANS = {}
+
+
+def get_plan(D, batch, c_in, c_out, spatial, modes):
+    key = (D, batch, c_in, c_out, tuple(spatial), tuple(modes), precision_code(), torch.cuda.current_device())
+    p = _PLANS.get(key)
+    if p is None:
+        d = _lib.SpectralDesc()
+        d.ndim, d.batch, d.c_in, d.c_out = D, batch, c_in, c_out
+        d.spatial = _lib.ivec(spatial, 1)
+        d.modes = _lib.ivec(modes, 1)
+        d.precision = precision_code()
+        p = _PLANS[key] = _Plan(d)
+    return p
+
+
+class SpectralConv(Module):
+    _fields = ("num_spatial_dims", "num_modes", "weights_real", "weights_imag")
+
+    def __init__(self, num_spatial_dims: int, in_channels: int, out_channels: int, num_modes, *, key):
+        if isinstance(num_modes, int):
+            num_modes = (num_modes,) * num_spatial_dims
+        if len(num_modes) != num_spatial_dims:  # _spectral_conv.py:48-49
+            raise ValueError("num_modes must have the same length as num_spatial_dims")
+        self.num_spatial_dims = num_spatial_dims
+        self.num_modes = tuple(int(m) for m in num_modes)
+        # allocation shape (G, in, out, *modes) (_spectral_conv.py:54-58); the call interprets it as (G, o, i, *modes)
+        weight_shape = (2 ** (num_spatial_dims - 1), in_channels, out_channels) + self.num_modes
+        real_key, imag_key = jr.split(key)  # _spectral_conv.py:60
+        scale = 1.0 / (in_channels * out_channels)
+        self.weights_real = to_param(scale * jr.normal(real_key, weight_shape))
+        self.weights_imag = to_param(scale * jr.normal(imag_key, weight_shape))
+
+    @property
+    def receptive_field(self):
+        return ((float("inf"), float("inf")),) * self.num_spatial_dims
+
+    # call-time channel interpretation: `_, o, *_ = weight.shape`, einsum "i...,oi...->o..." (_spectral_conv.py:129-134)
+    @property
+    def call_out_channels(self):
+        return int(self.weights_real.shape[1])
+
+    @property
+    def call_in_channels(self):
+        return int(self.weights_real.shape[2])
+
+    def apply(self, x, tape, *, bypass=None, act=_lib.ACT_IDENTITY, save=False):
+        """y = act(spectral(x) [+ bypass(x)]); returns (y, saved) with saved = (plan, xhat, z) when `save`."""
+        D = self.num_spatial_dims
+        if x.ndim != D + 2:
+            raise ValueError(f"Input to `SpectralConv` needs to have rank {D + 1}, but input has shape {tuple(x.shape[1:])}.")
+        B, ci = x.shape[:2]
+        co = self.call_out_channels
+        if ci != self.call_in_channels:
+            raise ValueError(f"SpectralConv: input has {ci} channels but the weight contracts over {self.call_in_channels}")
+        spatial = tuple(x.shape[2:])
+        plan = get_plan(D, B, ci, co, spatial, self.num_modes)
+        y = new_buf(tape, self, "y", (B, co) + spatial)
+        xhat = z = None
+        if save:
+            xhat = new_buf(tape, self, "xhat", (plan.xhat_floats,))
+            z = new_buf(tape, self, "z", (plan.z_floats,))
+        bw = bypass.weight if bypass is not None else None
+        bb = bypass.bias if bypass is not None else None
+        _lib.check(_lib.lib().pdeqx_spectral_block_fwd(
+            plan.handle, _lib.ptr(x), _lib.ptr(self.weights_real), _lib.ptr(self.weights_imag), _lib.ptr(bw),
+            _lib.ptr(bb), act, _lib.ptr(y), _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(plan.workspace), plan.ws_bytes,
+            _lib.stream()))
+        return y, (plan, xhat, z)
+
+    def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True):
+        plan, xhat, z = saved
+        gx = new_buf(tape, self, "gx", x.shape) if need_gx else None
+        scratch = new_buf(tape, self, "gpre", gy.shape) if act != _lib.ACT_IDENTITY else None
+        bw = bypass.weight if bypass is not None else None
+        bb = bypass.bias if bypass is not None else None
+        gbw = bypass.grad("weight") if bypass is not None else None
+        gbb = bypass.grad("bias") if (bypass is not None and bypass.bias is not None) else None
+        _lib.check(_lib.lib().pdeqx_spectral_block_bwd(
+            plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(self.weights_real), _lib.ptr(self.weights_imag),
+            _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),
+            _lib.ptr(self.grad("weights_real")), _lib.ptr(self.grad("weights_imag")), _lib.ptr(gbw), _lib.ptr(gbb),
+            _lib.ptr(scratch), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))
+        return gx
+
+    def _fwd(self, x, tape):
+        y, saved = self.apply(x, tape, save=tape is not None)
+        if tape is not None:
+            tape.push((x, saved))
+        return y
+
+    def _bwd(self, gy, tape, need_gx=True):
+        x, saved = tape.pop()
+        return self.apply_bwd(x, gy, saved, tape, need_gx=need_gx)

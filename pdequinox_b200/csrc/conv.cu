@@ -1,0 +1,375 @@
+// PhysicsConv / MorePaddingConv: boundary-aware N-D cross-correlation, generic fp32 path.
+//
+//   replaces pdequinox/conv/_conv.py:169-219 (jnp.pad + lax.conv_general_dilated + bias) with the
+//   SAME padding of pdequinox/conv/_physics_conv.py:11-26.
+//
+// The halo is never materialised: every tap computes its source index through the boundary map
+//   ZEROS   (dirichlet) : out-of-range taps contribute 0          (_conv.py:192-194)
+//   WRAP    (periodic)  : q mod s                                 (_conv.py:190, jnp.pad "wrap")
+//   REFLECT (neumann)   : mirror without repeating the edge       (_conv.py:196, jnp.pad "reflect")
+//   EDGE    (replicate) : clamp                                   (_conv.py:199)
+// This file is the any-shape path (1-3 D, stride, dilation, groups, even kernels); the C >= 16
+// 2-D stride-1 case runs on tcgen05 as an implicit GEMM (tc_conv.cu).
+#include "common.cuh"
+#include "conv_plan.h"
+
+namespace pdeqx {
+
+__host__ __device__ __forceinline__ int boundary_map(int q, int s, int mode) {
+  if (q >= 0 && q < s) return q;
+  switch (mode) {
+    case PDEQX_PAD_WRAP: {
+      int r = q % s;
+      return r < 0 ? r + s : r;
+    }
+    case PDEQX_PAD_REFLECT: {
+      if (s == 1) return 0;
+      int period = 2 * (s - 1);
+      int r = q % period;
+      if (r < 0) r += period;
+      return r < s ? r : period - r;
+    }
+    case PDEQX_PAD_EDGE:
+      return q < 0 ? 0 : s - 1;
+    default:
+      return -1;  // zeros
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: one thread per output element, 4 output channels per thread
+// ---------------------------------------------------------------------------------------------
+constexpr int kOPT = 4;
+
+__global__ void __launch_bounds__(256)
+conv_fwd_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                const float* __restrict__ residual, float* __restrict__ y, int act) {
+  const int64_t n_out = g.n_out;
+  const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
+  const int ochunks = (cog + kOPT - 1) / kOPT;  // per group
+  const int64_t total = (int64_t)g.batch * g.groups * ochunks * n_out;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = idx % n_out;
+    int64_t r = idx / n_out;
+    const int oc = (int)(r % ochunks);
+    r /= ochunks;
+    const int grp = (int)(r % g.groups);
+    const int b = (int)(r / g.groups);
+    int po[PDEQX_MAX_DIMS];
+    {
+      int64_t pp = p;
+      for (int a = g.ndim - 1; a >= 0; --a) {
+        po[a] = (int)(pp % g.out[a]);
+        pp /= g.out[a];
+      }
+    }
+    const int o0 = grp * cog + oc * kOPT;
+    const int no = min(kOPT, cog - oc * kOPT);
+    float acc[kOPT];
+#pragma unroll
+    for (int j = 0; j < kOPT; ++j) acc[j] = 0.f;
+    const float* xb = x + ((int64_t)b * g.c_in + (int64_t)grp * cig) * g.n_in;
+    for (int t = 0; t < g.taps; ++t) {
+      int tt = t;
+      int64_t src = 0;
+      bool valid = true;
+      for (int a = g.ndim - 1; a >= 0; --a) {
+        int ta = tt % g.kernel[a];
+        tt /= g.kernel[a];
+        int q = po[a] * g.stride[a] + ta * g.dilation[a] - g.pad_lo[a];
+        int m = boundary_map(q, g.spatial[a], g.boundary);
+        valid = valid && (m >= 0);
+        src += (int64_t)m * g.in_stride[a];
+      }
+      if (!valid) continue;
+      for (int i = 0; i < cig; ++i) {
+        float xv = __ldg(xb + (int64_t)i * g.n_in + src);
+#pragma unroll
+        for (int j = 0; j < kOPT; ++j)
+          if (j < no) acc[j] = fmaf(__ldg(w + ((int64_t)(o0 + j) * cig + i) * g.taps + t), xv, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kOPT; ++j) {
+      if (j >= no) break;
+      int64_t off = ((int64_t)b * g.c_out + o0 + j) * n_out + p;
+      float v = acc[j] + (bias ? __ldg(bias + o0 + j) : 0.f);
+      if (residual) v += __ldg(residual + off);
+      y[off] = apply_act_rt(v, act);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward data: gather over the pre-images of each input position under the boundary map
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPre = 8;
+
+__device__ __forceinline__ int preimages(int n, int s, int lo, int hi, int mode, int* out) {
+  int c = 0;
+  out[c++] = n;
+  if (mode == PDEQX_PAD_ZEROS) return c;
+  for (int q = -lo; q < 0; ++q)
+    if (boundary_map(q, s, mode) == n && c < kMaxPre) out[c++] = q;
+  for (int q = s; q < s + hi; ++q)
+    if (boundary_map(q, s, mode) == n && c < kMaxPre) out[c++] = q;
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ add,
+                     float* __restrict__ gx) {
+  const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
+  const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = idx % g.n_in;
+    int64_t r = idx / g.n_in;
+    const int ci = (int)(r % g.c_in);
+    const int b = (int)(r / g.c_in);
+    const int grp = ci / cig, il = ci % cig;
+    int pre[PDEQX_MAX_DIMS][kMaxPre];
+    int npre[PDEQX_MAX_DIMS] = {1, 1, 1};
+    {
+      int64_t nn = n;
+      for (int a = g.ndim - 1; a >= 0; --a) {
+        int na = (int)(nn % g.spatial[a]);
+        nn /= g.spatial[a];
+        npre[a] = preimages(na, g.spatial[a], g.pad_lo[a], g.pad_hi[a], g.boundary, pre[a]);
+      }
+    }
+    const float* gyb = gy + ((int64_t)b * g.c_out + (int64_t)grp * cog) * g.n_out;
+    const float* wg = w + ((int64_t)grp * cog * cig + il) * g.taps;
+    float acc = 0.f;
+    for (int c0 = 0; c0 < npre[0]; ++c0)
+      for (int c1 = 0; c1 < npre[1]; ++c1)
+        for (int c2 = 0; c2 < npre[2]; ++c2) {
+          const int cc[PDEQX_MAX_DIMS] = {c0, c1, c2};
+          for (int t = 0; t < g.taps; ++t) {
+            int tt = t;
+            int64_t dst = 0;
+            bool valid = true;
+            for (int a = g.ndim - 1; a >= 0; --a) {
+              int ta = tt % g.kernel[a];
+              tt /= g.kernel[a];
+              int num = pre[a][cc[a]] + g.pad_lo[a] - ta * g.dilation[a];
+              if (num < 0 || num % g.stride[a] != 0) { valid = false; break; }
+              int pa = num / g.stride[a];
+              if (pa >= g.out[a]) { valid = false; break; }
+              dst += (int64_t)pa * g.out_stride[a];
+            }
+            if (!valid) continue;
+            for (int o = 0; o < cog; ++o)
+              acc = fmaf(__ldg(wg + (int64_t)o * cig * g.taps + t), __ldg(gyb + (int64_t)o * g.n_out + dst), acc);
+          }
+        }
+    gx[idx] = acc + (add ? __ldg(add + idx) : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward filter: CTA = 16 out-channels x 16 in-channels x one tap, reduction over (batch, pixels)
+// ---------------------------------------------------------------------------------------------
+constexpr int WF_P = 64;
+
+__global__ void __launch_bounds__(256)
+conv_bwd_filter_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw,
+                       float* __restrict__ gb, int o_tiles, int i_tiles, int64_t chunks) {
+  __shared__ float Gs[WF_P][16 + 1];
+  __shared__ float Xs[WF_P][16 + 1];
+  const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
+  int bid = blockIdx.x;
+  const int t = bid % g.taps;
+  bid /= g.taps;
+  const int it = bid % i_tiles;
+  bid /= i_tiles;
+  const int ot = bid % o_tiles;
+  const int grp = bid / o_tiles;
+  const int tid = threadIdx.x;
+  const int ol = tid / 16, il = tid % 16;
+  int tap[PDEQX_MAX_DIMS];
+  {
+    int tt = t;
+    for (int a = g.ndim - 1; a >= 0; --a) {
+      tap[a] = tt % g.kernel[a];
+      tt /= g.kernel[a];
+    }
+  }
+  float acc = 0.f, bsum = 0.f;
+  const int64_t total_chunks = (int64_t)g.batch * chunks;
+  for (int64_t c = blockIdx.y; c < total_chunks; c += gridDim.y) {
+    const int b = (int)(c / chunks);
+    const int64_t p0 = (c % chunks) * WF_P;
+    for (int idx = tid; idx < 16 * WF_P; idx += 256) {
+      const int ch = idx / WF_P, pl = idx % WF_P;
+      const int64_t p = p0 + pl;
+      float gv = 0.f, xv = 0.f;
+      if (p < g.n_out) {
+        const int o = ot * 16 + ch, i = it * 16 + ch;
+        if (o < cog) gv = __ldg(gy + ((int64_t)b * g.c_out + grp * cog + o) * g.n_out + p);
+        if (i < cig) {
+          int64_t pp = p, src = 0;
+          bool valid = true;
+          for (int a = g.ndim - 1; a >= 0; --a) {
+            int pa = (int)(pp % g.out[a]);
+            pp /= g.out[a];
+            int m = boundary_map(pa * g.stride[a] + tap[a] * g.dilation[a] - g.pad_lo[a], g.spatial[a], g.boundary);
+            valid = valid && (m >= 0);
+            src += (int64_t)m * g.in_stride[a];
+          }
+          if (valid) xv = __ldg(x + ((int64_t)b * g.c_in + grp * cig + i) * g.n_in + src);
+        }
+      }
+      Gs[pl][ch] = gv;
+      Xs[pl][ch] = xv;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int k = 0; k < WF_P; ++k) {
+      acc = fmaf(Gs[k][ol], Xs[k][il], acc);
+      if (il == 0) bsum += Gs[k][ol];
+    }
+    __syncthreads();
+  }
+  const int o = ot * 16 + ol, i = it * 16 + il;
+  if (o < cog && i < cig) atomicAdd(gw + ((int64_t)(grp * cog + o) * cig + i) * g.taps + t, acc);
+  if (gb && il == 0 && it == 0 && t == 0 && o < cog) atomicAdd(gb + grp * cog + o, bsum);
+}
+
+int conv_geometry(const pdeqx_conv_desc* d, ConvGeom* out) {
+  PDEQX_CHECK_ARG(d && out, "null argument");
+  PDEQX_CHECK_ARG(d->ndim >= 1 && d->ndim <= PDEQX_MAX_DIMS, "ndim must be 1..3, got %d", d->ndim);
+  PDEQX_CHECK_ARG(d->batch >= 0 && d->c_in >= 1 && d->c_out >= 1 && d->groups >= 1, "bad batch/channels/groups");
+  PDEQX_CHECK_ARG(d->c_in % d->groups == 0, "`in_channels` (=%d) must be divisible by `groups` (=%d).", d->c_in, d->groups);
+  PDEQX_CHECK_ARG(d->c_out % d->groups == 0, "out_channels (=%d) must be divisible by groups (=%d)", d->c_out, d->groups);
+  PDEQX_CHECK_ARG(d->boundary >= PDEQX_PAD_ZEROS && d->boundary <= PDEQX_PAD_EDGE, "unknown boundary %d", d->boundary);
+  ConvGeom g{};
+  g.ndim = d->ndim;
+  g.batch = d->batch;
+  g.c_in = d->c_in;
+  g.c_out = d->c_out;
+  g.groups = d->groups;
+  g.boundary = d->boundary;
+  g.taps = 1;
+  g.n_in = 1;
+  g.n_out = 1;
+  for (int a = 0; a < PDEQX_MAX_DIMS; ++a) {
+    const bool on = a < d->ndim;
+    g.spatial[a] = on ? d->spatial[a] : 1;
+    g.kernel[a] = on ? d->kernel[a] : 1;
+    g.stride[a] = on ? d->stride[a] : 1;
+    g.dilation[a] = on ? d->dilation[a] : 1;
+    g.pad_lo[a] = on ? d->pad_lo[a] : 0;
+    g.pad_hi[a] = on ? d->pad_hi[a] : 0;
+    PDEQX_CHECK_ARG(g.spatial[a] >= 1 && g.kernel[a] >= 1 && g.stride[a] >= 1 && g.dilation[a] >= 1,
+                    "spatial/kernel/stride/dilation must be >= 1 (axis %d)", a);
+    PDEQX_CHECK_ARG(g.pad_lo[a] >= 0 && g.pad_hi[a] >= 0, "negative padding (axis %d)", a);
+    if (d->boundary == PDEQX_PAD_REFLECT && on)
+      PDEQX_CHECK_ARG(g.spatial[a] > 1 || (g.pad_lo[a] == 0 && g.pad_hi[a] == 0),
+                      "reflect padding needs at least 2 points on axis %d", a);
+    const int span = g.spatial[a] + g.pad_lo[a] + g.pad_hi[a] - g.dilation[a] * (g.kernel[a] - 1) - 1;
+    PDEQX_CHECK_ARG(span >= 0, "kernel does not fit the padded input on axis %d", a);
+    g.out[a] = span / g.stride[a] + 1;
+    g.taps *= g.kernel[a];
+    g.n_in *= g.spatial[a];
+    g.n_out *= g.out[a];
+  }
+  for (int a = PDEQX_MAX_DIMS - 1, si = 1, so = 1; a >= 0; --a) {
+    g.in_stride[a] = si;
+    g.out_stride[a] = so;
+    si *= g.spatial[a];
+    so *= g.out[a];
+  }
+  // pre-image multiplicity of the boundary map must fit the gather in the data-gradient kernel
+  // (upper bound per axis: one hit per period of the map inside each halo)
+  g.max_pre = 1;
+  if (d->boundary != PDEQX_PAD_ZEROS) {
+    for (int a = 0; a < d->ndim; ++a) {
+      const int s = g.spatial[a], lo = g.pad_lo[a], hi = g.pad_hi[a];
+      int worst = 1;
+      if (d->boundary == PDEQX_PAD_WRAP) worst = 1 + (lo + s - 1) / s + (hi + s - 1) / s;
+      else if (d->boundary == PDEQX_PAD_REFLECT) {
+        const int per = 2 * (s - 1);  // both +n and -n occur once per period
+        worst = s > 1 ? 1 + 2 * ((lo + per - 1) / per) + 2 * ((hi + per - 1) / per) : 1;
+      }
+      else worst = 1 + (lo > hi ? lo : hi);
+      g.max_pre = worst > g.max_pre ? worst : g.max_pre;
+    }
+  }
+  *out = g;
+  return PDEQX_OK;
+}
+
+static inline int grid_for(int64_t total) {
+  int64_t b = ceil_div(total, 256);
+  const int64_t cap = 148 * 32;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace pdeqx
+
+using namespace pdeqx;
+
+extern "C" int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]) {
+  ConvGeom g;
+  PDEQX_TRY(conv_geometry(d, &g));
+  for (int a = 0; a < PDEQX_MAX_DIMS; ++a) out_spatial[a] = a < d->ndim ? g.out[a] : 1;
+  return PDEQX_OK;
+}
+
+extern "C" int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b,
+                              const float* residual, int32_t activation, float* y, void* stream) {
+  PDEQX_CHECK_ARG(x && w && y, "null argument");
+  PDEQX_CHECK_ARG(activation >= 0 && activation <= 2, "unknown activation %d", activation);
+  ConvGeom g;
+  PDEQX_TRY(conv_geometry(d, &g));
+  if (g.batch == 0) return PDEQX_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tc_conv_available(g)) return tc_conv_fwd(g, x, w, b, residual, activation, y, s);
+  const int cog = g.c_out / g.groups;
+  const int64_t total = (int64_t)g.batch * g.groups * ceil_div(cog, kOPT) * g.n_out;
+  conv_fwd_kernel<<<grid_for(total), 256, 0, s>>>(g, x, w, b, residual, y, activation);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
+extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add, float* gx,
+                                   void* stream) {
+  PDEQX_CHECK_ARG(gy && w && gx, "null argument");
+  ConvGeom g;
+  PDEQX_TRY(conv_geometry(d, &g));
+  if (g.batch == 0) return PDEQX_OK;
+  if (g.max_pre > kMaxPre) {
+    set_error("padding wraps/reflects onto one point %d times (> %d): grid too small for this dilation", g.max_pre, kMaxPre);
+    return PDEQX_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tc_conv_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, s);
+  const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
+  conv_bwd_data_kernel<<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
+extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, float* gw, float* gb,
+                                     void* stream) {
+  PDEQX_CHECK_ARG(x && gy && gw, "null argument");
+  ConvGeom g;
+  PDEQX_TRY(conv_geometry(d, &g));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
+  PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
+  if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
+  if (g.batch == 0) return PDEQX_OK;
+  if (tc_conv_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, s);
+  const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
+  const int64_t chunks = ceil_div(g.n_out, WF_P);
+  const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;
+  PDEQX_CHECK_ARG(gx_blocks < (1ll << 31), "conv_bwd_filter: grid too large");
+  int64_t split = ceil_div(148 * 8, gx_blocks);
+  if (split > (int64_t)g.batch * chunks) split = (int64_t)g.batch * chunks;
+  if (split > 65535) split = 65535;
+  if (split < 1) split = 1;
+  conv_bwd_filter_kernel<<<dim3((unsigned)gx_blocks, (unsigned)split), 256, 0, s>>>(g, x, gy, gw, gb, o_tiles, i_tiles, chunks);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}

@@ -1,0 +1,26 @@
+// Internal: resolved geometry of one PhysicsConv call, shared by conv.cu (any-shape fp32 path)
+// and tc_conv.cu (tcgen05 implicit GEMM).
+#pragma once
+#include "common.cuh"
+
+namespace pdeqx {
+
+struct ConvGeom {
+  int ndim, batch, c_in, c_out, groups, boundary, taps, max_pre;
+  int spatial[PDEQX_MAX_DIMS], out[PDEQX_MAX_DIMS];
+  int kernel[PDEQX_MAX_DIMS], stride[PDEQX_MAX_DIMS], dilation[PDEQX_MAX_DIMS];
+  int pad_lo[PDEQX_MAX_DIMS], pad_hi[PDEQX_MAX_DIMS];
+  int in_stride[PDEQX_MAX_DIMS], out_stride[PDEQX_MAX_DIMS];  // element strides inside one channel
+  int64_t n_in, n_out;                                        // points per channel
+};
+
+int conv_geometry(const pdeqx_conv_desc* d, ConvGeom* out);
+
+// tcgen05 implicit-GEMM path (tc_conv.cu)
+bool tc_conv_available(const ConvGeom& g);
+int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* residual, int act,
+                float* y, cudaStream_t s);
+int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, cudaStream_t s);
+int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, cudaStream_t s);
+
+}  // namespace pdeqx

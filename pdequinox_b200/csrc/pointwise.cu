@@ -1,0 +1,310 @@
+// PointwiseLinearConv (1x1 conv) forward / backward.
+//
+//   replaces pdequinox/conv/_pointwise_linear_conv.py:6-53 (eqx.nn.Conv with kernel_size=1):
+//   y[b,o,n] = sum_i w[o,i] x[b,i,n] + bias[o]
+//
+// Three regimes:
+//   * lifting (c_in tiny) / projection (c_out tiny): streaming kernels, one pass over the big
+//     tensor, float4 loads/stores -- pure HBM-bound (0.5 flop/B);
+//   * c_in, c_out both large: GEMM (CUDA-core fp32 here; the FNO block's bypass runs fused into
+//     the tcgen05 slab kernel instead, see tc_spectral.cu);
+//   * weight gradient: persistent split-K GEMM over all pixels with one atomic flush per CTA.
+#include "common.cuh"
+
+namespace pdeqx {
+
+constexpr int kSmallC = 8;
+
+// ---- few input channels: keep x in registers, loop over outputs ----------------------------
+//  W(o,i) = w[o*w_so + i*w_si]  (lets the backward pass read w transposed)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+pw_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    const float* __restrict__ add, float* __restrict__ y, int cin, int cout, int64_t n,
+                    int w_so, int w_si, int act) {
+  extern __shared__ float sw[];  // [cout][cin] + [cout]
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) sw[i] = w[(i / cin) * w_so + (i % cin) * w_si];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cin * cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int64_t nv = n / VEC;
+  const float* xb = x + (int64_t)b * cin * n;
+  float* yb = y + (int64_t)b * cout * n;
+  const float* ab = add ? add + (int64_t)b * cout * n : nullptr;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    float xr[kSmallC][VEC];
+    for (int i = 0; i < cin; ++i) {
+      if (VEC == 4) {
+        float4 t = __ldg((const float4*)(xb + (int64_t)i * n) + v);
+        xr[i][0] = t.x; xr[i][1 % VEC] = t.y; xr[i][2 % VEC] = t.z; xr[i][3 % VEC] = t.w;
+      } else {
+        xr[i][0] = __ldg(xb + (int64_t)i * n + v);
+      }
+    }
+    for (int o = 0; o < cout; ++o) {
+      float acc[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] = sw[cin * cout + o];
+      for (int i = 0; i < cin; ++i) {
+        float wv = sw[o * cin + i];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(wv, xr[i][e], acc[e]);
+      }
+      if (VEC == 4) {
+        if (ab) {
+          float4 t = __ldg((const float4*)(ab + (int64_t)o * n) + v);
+          acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w;
+        }
+        float4 r = make_float4(apply_act_rt(acc[0], act), apply_act_rt(acc[1 % VEC], act),
+                               apply_act_rt(acc[2 % VEC], act), apply_act_rt(acc[3 % VEC], act));
+        ((float4*)(yb + (int64_t)o * n))[v] = r;
+      } else {
+        if (ab) acc[0] += __ldg(ab + (int64_t)o * n + v);
+        yb[(int64_t)o * n + v] = apply_act_rt(acc[0], act);
+      }
+    }
+  }
+}
+
+// ---- few output channels: accumulate in registers, stream the inputs -----------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+pw_small_cout_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     const float* __restrict__ add, float* __restrict__ y, int cin, int cout, int64_t n,
+                     int w_so, int w_si, int act) {
+  extern __shared__ float sw[];  // [cout][cin] + [cout]
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) sw[i] = w[(i / cin) * w_so + (i % cin) * w_si];
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cin * cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int64_t nv = n / VEC;
+  const float* xb = x + (int64_t)b * cin * n;
+  float* yb = y + (int64_t)b * cout * n;
+  const float* ab = add ? add + (int64_t)b * cout * n : nullptr;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    float acc[kSmallC][VEC];
+    for (int o = 0; o < cout; ++o)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[o][e] = sw[cin * cout + o];
+#pragma unroll 4
+    for (int i = 0; i < cin; ++i) {
+      float xv[VEC];
+      if (VEC == 4) {
+        float4 t = __ldg((const float4*)(xb + (int64_t)i * n) + v);
+        xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
+      } else {
+        xv[0] = __ldg(xb + (int64_t)i * n + v);
+      }
+      for (int o = 0; o < cout; ++o) {
+        float wv = sw[o * cin + i];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[o][e] = fmaf(wv, xv[e], acc[o][e]);
+      }
+    }
+    for (int o = 0; o < cout; ++o) {
+      if (VEC == 4) {
+        if (ab) {
+          float4 t = __ldg((const float4*)(ab + (int64_t)o * n) + v);
+          acc[o][0] += t.x; acc[o][1 % VEC] += t.y; acc[o][2 % VEC] += t.z; acc[o][3 % VEC] += t.w;
+        }
+        ((float4*)(yb + (int64_t)o * n))[v] =
+            make_float4(apply_act_rt(acc[o][0], act), apply_act_rt(acc[o][1 % VEC], act),
+                        apply_act_rt(acc[o][2 % VEC], act), apply_act_rt(acc[o][3 % VEC], act));
+      } else {
+        if (ab) acc[o][0] += __ldg(ab + (int64_t)o * n + v);
+        yb[(int64_t)o * n + v] = apply_act_rt(acc[o][0], act);
+      }
+    }
+  }
+}
+
+// generic W(o,i) strides so that bwd-data can reuse the forward kernels with w^T
+static int pointwise_apply(int batch, int cin, int cout, int64_t n, const float* x, const float* w, int w_so, int w_si,
+                           const float* bias, const float* add, int act, float* y, cudaStream_t s) {
+  if (batch <= 0 || n <= 0) return PDEQX_OK;
+  PDEQX_CHECK_ARG(batch <= 65535, "pointwise: batch %d exceeds grid.y", batch);
+  const bool vec4 = (n % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+                    (!add || (uintptr_t)add % 16 == 0);
+  const int64_t nv = vec4 ? n / 4 : n;
+  const int blocks = (int)(ceil_div(nv, 256) < 2048 ? ceil_div(nv, 256) : 2048);
+  const size_t smem = (size_t)(cin * cout + cout) * sizeof(float);
+  if (cin <= kSmallC && smem <= 48 * 1024) {
+    if (vec4)
+      pw_small_cin_kernel<4><<<dim3(blocks, batch), 256, smem, s>>>(x, w, bias, add, y, cin, cout, n, w_so, w_si, act);
+    else
+      pw_small_cin_kernel<1><<<dim3(blocks, batch), 256, smem, s>>>(x, w, bias, add, y, cin, cout, n, w_so, w_si, act);
+    PDEQX_LAUNCHED();
+    return PDEQX_OK;
+  }
+  if (cout <= kSmallC && smem <= 48 * 1024) {
+    if (vec4)
+      pw_small_cout_kernel<4><<<dim3(blocks, batch), 256, smem, s>>>(x, w, bias, add, y, cin, cout, n, w_so, w_si, act);
+    else
+      pw_small_cout_kernel<1><<<dim3(blocks, batch), 256, smem, s>>>(x, w, bias, add, y, cin, cout, n, w_so, w_si, act);
+    PDEQX_LAUNCHED();
+    return PDEQX_OK;
+  }
+  SgemmArgs a{};
+  a.A = w; a.B = x; a.C = y; a.bias = bias; a.add = add;
+  a.M = cout; a.N = n; a.K = cin;
+  a.lda_m = w_so; a.lda_k = w_si; a.ldb = n; a.ldc = n;
+  a.strideA = 0; a.strideB = (int64_t)cin * n; a.strideC = (int64_t)cout * n;
+  a.batch = batch; a.act = act;
+  return sgemm_batched(a, s);
+}
+
+// ---- weight / bias gradient ----------------------------------------------------------------
+// General case: gw[64x64 tile] += G[o, K-chunk] . X[i, K-chunk]^T, persistent over (b, pixel chunks).
+constexpr int WG_BK = 32;
+__global__ void __launch_bounds__(256)
+pw_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ gw,
+                float* __restrict__ gb, int batch, int cin, int cout, int64_t n, int64_t chunks_per_b) {
+  __shared__ float Gs[WG_BK][64 + 4];
+  __shared__ float Xs[WG_BK][64 + 4];
+  const int tid = threadIdx.x;
+  const int o0 = blockIdx.y * 64, i0 = blockIdx.z * 64;
+  const int ty = tid / 16, tx = tid % 16;  // 4x4 micro tile
+  float acc[4][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int64_t total = (int64_t)batch * chunks_per_b;
+  for (int64_t c = blockIdx.x; c < total; c += gridDim.x) {
+    const int b = (int)(c / chunks_per_b);
+    const int64_t n0 = (c % chunks_per_b) * WG_BK;
+    // load [64 ch][WG_BK px] tiles, transposed into [px][ch]
+    for (int idx = tid; idx < 64 * WG_BK; idx += 256) {
+      int ch = idx / WG_BK, px = idx % WG_BK;
+      int64_t gn = n0 + px;
+      float gv = 0.f, xv = 0.f;
+      if (gn < n) {
+        if (o0 + ch < cout) gv = __ldg(gy + ((int64_t)b * cout + o0 + ch) * n + gn);
+        if (i0 + ch < cin) xv = __ldg(x + ((int64_t)b * cin + i0 + ch) * n + gn);
+      }
+      Gs[px][ch] = gv;
+      Xs[px][ch] = xv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WG_BK; ++k) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Gs[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Xs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      }
+      if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bsum[i] += a[i];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int o = o0 + ty * 4 + i;
+    if (o >= cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ii = i0 + tx * 4 + j;
+      if (ii < cin) atomicAdd(gw + (int64_t)o * cin + ii, acc[i][j]);
+    }
+    if (gb && tx == 0 && blockIdx.z == 0) atomicAdd(gb + o, bsum[i]);
+  }
+}
+
+// Small side (<= kSmallC channels on one of the two sides): one warp per channel of the large side.
+//   big = gy (cout large, cin small)  if big_is_gy, else big = x.
+__global__ void __launch_bounds__(256)
+pw_wgrad_small_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ gw,
+                      float* __restrict__ gb, int cin, int cout, int64_t n, int64_t chunk) {
+  const int b = blockIdx.y;
+  const int64_t n0 = (int64_t)blockIdx.x * chunk;
+  const int64_t n1 = (n0 + chunk < n) ? n0 + chunk : n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const bool big_is_gy = cout >= cin;
+  const int nbig = big_is_gy ? cout : cin, nsmall = big_is_gy ? cin : cout;
+  const float* big = big_is_gy ? gy + (int64_t)b * cout * n : x + (int64_t)b * cin * n;
+  const float* small = big_is_gy ? x + (int64_t)b * cin * n : gy + (int64_t)b * cout * n;
+  for (int c = warp; c < nbig; c += nwarps) {
+    float acc[kSmallC];
+    float bs = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSmallC; ++j) acc[j] = 0.f;
+    for (int64_t q = n0 + lane; q < n1; q += 32) {
+      float v = __ldg(big + (int64_t)c * n + q);
+      bs += v;
+#pragma unroll
+      for (int j = 0; j < kSmallC; ++j)
+        if (j < nsmall) acc[j] = fmaf(v, __ldg(small + (int64_t)j * n + q), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kSmallC; ++j) {
+      if (j >= nsmall) break;
+      float v = acc[j];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) {
+        int o = big_is_gy ? c : j, i = big_is_gy ? j : c;
+        atomicAdd(gw + (int64_t)o * cin + i, v);
+      }
+    }
+    if (gb && big_is_gy) {
+      for (int off = 16; off > 0; off >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, off);
+      if (lane == 0) atomicAdd(gb + c, bs);
+    }
+  }
+  if (gb && !big_is_gy) {  // bias grad over the small (gy) side
+    for (int o = warp; o < cout; o += nwarps) {
+      float bs = 0.f;
+      for (int64_t q = n0 + lane; q < n1; q += 32) bs += __ldg(small + (int64_t)o * n + q);
+      for (int off = 16; off > 0; off >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, off);
+      if (lane == 0) atomicAdd(gb + o, bs);
+    }
+  }
+}
+
+}  // namespace pdeqx
+
+using namespace pdeqx;
+
+extern "C" int pdeqx_pointwise_fwd(int32_t batch, int32_t c_in, int32_t c_out, int64_t n_pixels, const float* x,
+                                   const float* w, const float* b, const float* add, int32_t activation, float* y,
+                                   void* stream) {
+  PDEQX_CHECK_ARG(x && w && y, "null argument");
+  PDEQX_CHECK_ARG(batch >= 0 && c_in >= 1 && c_out >= 1 && n_pixels >= 0, "bad sizes");
+  PDEQX_CHECK_ARG(activation >= 0 && activation <= 2, "unknown activation %d", activation);
+  return pointwise_apply(batch, c_in, c_out, n_pixels, x, w, c_in, 1, b, add, activation, y, (cudaStream_t)stream);
+}
+
+extern "C" int pdeqx_pointwise_bwd(int32_t batch, int32_t c_in, int32_t c_out, int64_t n_pixels, const float* x,
+                                   const float* w, const float* gy, float* gx, float* gw, float* gb, void* stream) {
+  PDEQX_CHECK_ARG(x && w && gy && gw, "null argument");
+  PDEQX_CHECK_ARG(batch >= 0 && c_in >= 1 && c_out >= 1 && n_pixels >= 0, "bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (gx)  // gx[b,i,n] = sum_o w[o,i] gy[b,o,n]: the forward op with W' = w^T (roles of c_in/c_out swapped)
+    PDEQX_TRY(pointwise_apply(batch, c_out, c_in, n_pixels, gy, w, 1, c_in, nullptr, nullptr, PDEQX_ACT_IDENTITY, gx, s));
+  PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)c_in * c_out, s));
+  if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)c_out, s));
+  if (batch == 0 || n_pixels == 0) return PDEQX_OK;
+  if (c_in <= kSmallC || c_out <= kSmallC) {
+    const int64_t chunk = 8192;
+    PDEQX_CHECK_ARG(batch <= 65535, "pointwise_bwd: batch exceeds grid.y");
+    dim3 grid((unsigned)ceil_div(n_pixels, chunk), batch);
+    pw_wgrad_small_kernel<<<grid, 256, 0, s>>>(gy, x, gw, gb, c_in, c_out, n_pixels, chunk);
+    PDEQX_LAUNCHED();
+    return PDEQX_OK;
+  }
+  const int64_t chunks_per_b = ceil_div(n_pixels, WG_BK);
+  const int64_t total = (int64_t)batch * chunks_per_b;
+  const int ot = (int)ceil_div(c_out, 64), it = (int)ceil_div(c_in, 64);
+  int gx_blocks = (int)(total < 148 * 4 ? total : 148 * 4);
+  pw_wgrad_kernel<<<dim3(gx_blocks, ot, it), 256, 0, s>>>(gy, x, gw, gb, batch, c_in, c_out, n_pixels, chunks_per_b);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}

@@ -1,0 +1,377 @@
+// SpectralConv / ClassicSpectralBlock as a truncated-DFT pipeline.
+//
+//   replaces  pdequinox/conv/_spectral_conv.py:107-136   (rfftn -> corner einsum -> irfftn)
+//             pdequinox/blocks/_classic_spectral_block.py:72-75
+//
+// Only the retained modes are ever computed: the forward transform is a chain of
+// GEMMs against twiddle tables (real->complex on the contiguous axis first, which
+// shrinks the data by s_D/(2 m_D), then complex->complex on the remaining axes),
+// followed by the per-mode channel mix and the mirrored inverse chain. The zero
+// filled full spectrum of the reference is never materialised.
+//
+// This file owns the plan (tables) and the stage sequencing; it dispatches each
+// stage to the tcgen05 kernels (tc_spectral.cu) when the shape allows and to the
+// fp32 CUDA-core GEMMs (gemm_generic.cu) otherwise.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "spectral_plan.h"
+
+namespace pdeqx {
+
+static const double kTwoPi = 6.283185307179586476925286766559;
+
+static int64_t kappa(int j, int s, int m) { return j < m ? j : (int64_t)s - 2 * m + j; }
+
+// cos/sin of 2 pi (k n mod s) / s in float64
+static void cs(int64_t k, int64_t n, int64_t s, double* c, double* sn) {
+  int64_t r = (k * n) % s;
+  double ang = kTwoPi * (double)r / (double)s;
+  *c = cos(ang);
+  *sn = sin(ang);
+}
+
+template <class T>
+static int upload(const std::vector<T>& h, T** d) {
+  PDEQX_CUDA(cudaMalloc((void**)d, h.size() * sizeof(T)));
+  PDEQX_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return PDEQX_OK;
+}
+
+}  // namespace pdeqx
+
+using namespace pdeqx;
+
+extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx_spectral_plan** out) {
+  PDEQX_CHECK_ARG(desc && out, "null argument");
+  const int D = desc->ndim;
+  PDEQX_CHECK_ARG(D >= 1 && D <= PDEQX_MAX_DIMS, "ndim must be 1..3, got %d", D);
+  PDEQX_CHECK_ARG(desc->batch >= 1 && desc->c_in >= 1 && desc->c_out >= 1, "batch/channels must be >= 1");
+  for (int a = 0; a < D; ++a) {
+    PDEQX_CHECK_ARG(desc->spatial[a] >= 1 && desc->modes[a] >= 1, "spatial/modes must be >= 1");
+    if (a == D - 1)
+      PDEQX_CHECK_ARG(desc->modes[a] <= desc->spatial[a] / 2 + 1,
+                      "num_modes[%d]=%d exceeds s//2+1=%d on the rfft axis", a, desc->modes[a],
+                      desc->spatial[a] / 2 + 1);
+    else
+      PDEQX_CHECK_ARG(desc->modes[a] <= desc->spatial[a], "num_modes[%d]=%d exceeds axis length %d", a,
+                      desc->modes[a], desc->spatial[a]);
+  }
+  pdeqx_spectral_plan* p = new pdeqx_spectral_plan();
+  p->desc = *desc;
+  p->G = 1 << (D - 1);
+  const int sD = desc->spatial[D - 1], mD = desc->modes[D - 1];
+
+  // ---- last axis (real <-> complex) ----
+  std::vector<float> r2c_f((size_t)sD * 2 * mD), c2r_i((size_t)2 * mD * sD);
+  std::vector<float> r2c_b((size_t)sD * 2 * mD), c2r_b((size_t)2 * mD * sD);
+  for (int k = 0; k < mD; ++k) {
+    double c = 2.0;
+    if (k == 0) c = 1.0;
+    if (sD % 2 == 0 && k == sD / 2) c = 1.0;  // Nyquist bin: pocketfft c2r drops its imaginary part
+    for (int n = 0; n < sD; ++n) {
+      double co, si;
+      cs(k, n, sD, &co, &si);
+      // x_hat = sum_n x e^{-i th}
+      r2c_f[(size_t)n * 2 * mD + 2 * k] = (float)co;
+      r2c_f[(size_t)n * 2 * mD + 2 * k + 1] = (float)(-si);
+      // y = sum_k c/s (zr cos - zi sin)
+      c2r_i[(size_t)(2 * k) * sD + n] = (float)(c / sD * co);
+      c2r_i[(size_t)(2 * k + 1) * sD + n] = (float)(-c / sD * si);
+      // adjoints are the transposes
+      r2c_b[(size_t)n * 2 * mD + 2 * k] = (float)(c / sD * co);
+      r2c_b[(size_t)n * 2 * mD + 2 * k + 1] = (float)(-c / sD * si);
+      c2r_b[(size_t)(2 * k) * sD + n] = (float)co;
+      c2r_b[(size_t)(2 * k + 1) * sD + n] = (float)(-si);
+    }
+  }
+  int rc = PDEQX_OK;
+  if ((rc = upload(r2c_f, &p->t_r2c_fwd)) || (rc = upload(c2r_i, &p->t_c2r_inv)) ||
+      (rc = upload(r2c_b, &p->t_r2c_bwd)) || (rc = upload(c2r_b, &p->t_c2r_bwd))) {
+    pdeqx_spectral_plan_destroy(p);
+    return rc;
+  }
+
+  // ---- other axes (complex <-> complex) ----
+  for (int a = 0; a < D - 1; ++a) {
+    const int s = desc->spatial[a], m = desc->modes[a];
+    std::vector<float2> fwd((size_t)2 * m * s), inv((size_t)s * 2 * m), inv_adj((size_t)2 * m * s),
+        fwd_adj((size_t)s * 2 * m);
+    for (int j = 0; j < 2 * m; ++j) {
+      // overlap (2m > s): the later (high) corner block overwrites the low one in the reference
+      double keep = 1.0;
+      if (j < m) {
+        for (int jj = m; jj < 2 * m; ++jj)
+          if (kappa(jj, s, m) == kappa(j, s, m)) keep = 0.0;
+      }
+      for (int n = 0; n < s; ++n) {
+        double co, si;
+        cs(kappa(j, s, m), n, s, &co, &si);
+        fwd[(size_t)j * s + n] = make_float2((float)co, (float)(-si));
+        fwd_adj[(size_t)n * 2 * m + j] = make_float2((float)co, (float)si);
+        inv[(size_t)n * 2 * m + j] = make_float2((float)(keep * co / s), (float)(keep * si / s));
+        inv_adj[(size_t)j * s + n] = make_float2((float)(keep * co / s), (float)(-keep * si / s));
+      }
+    }
+    if ((rc = upload(fwd, &p->t_fwd[a])) || (rc = upload(inv, &p->t_inv[a])) ||
+        (rc = upload(inv_adj, &p->t_inv_adj[a])) || (rc = upload(fwd_adj, &p->t_fwd_adj[a]))) {
+      pdeqx_spectral_plan_destroy(p);
+      return rc;
+    }
+  }
+
+  // ---- sizes ----
+  int64_t lead = 1;  // prod s_a, a < D-1
+  int64_t J = mD;    // prod 2m_a (a < D-1) * m_D
+  for (int a = 0; a < D - 1; ++a) {
+    lead *= desc->spatial[a];
+    J *= 2 * desc->modes[a];
+  }
+  p->lead = lead;
+  p->J = J;
+  const int64_t cmax = desc->c_in > desc->c_out ? desc->c_in : desc->c_out;
+  // largest intermediate: right after the r2c stage / right before the c2r stage
+  int64_t lead_max = 1;  // with overlapping slices (2m > s) a truncated axis can be longer than the full one
+  for (int a = 0; a < D - 1; ++a) lead_max *= (desc->spatial[a] > 2 * desc->modes[a] ? desc->spatial[a] : 2 * desc->modes[a]);
+  p->stage_floats = 2 * (int64_t)desc->batch * cmax * lead_max * mD;
+  p->mode_floats = (2 * (int64_t)desc->batch * cmax * J + 63) / 64 * 64;
+  p->ws_bytes = (size_t)(2 * p->stage_floats + 2 * p->mode_floats) * sizeof(float) + 256;
+  rc = tc_plan_init(p);  // builds the tcgen05-side operand tables when the shape qualifies
+  if (rc != PDEQX_OK) {
+    pdeqx_spectral_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return PDEQX_OK;
+}
+
+extern "C" void pdeqx_spectral_plan_destroy(pdeqx_spectral_plan* p) {
+  if (!p) return;
+  cudaFree(p->t_r2c_fwd);
+  cudaFree(p->t_c2r_inv);
+  cudaFree(p->t_r2c_bwd);
+  cudaFree(p->t_c2r_bwd);
+  for (int a = 0; a < PDEQX_MAX_DIMS; ++a) {
+    cudaFree(p->t_fwd[a]);
+    cudaFree(p->t_inv[a]);
+    cudaFree(p->t_inv_adj[a]);
+    cudaFree(p->t_fwd_adj[a]);
+  }
+  tc_plan_free(p);
+  delete p;
+}
+
+extern "C" size_t pdeqx_spectral_workspace_bytes(const pdeqx_spectral_plan* p) { return p ? p->ws_bytes : 0; }
+extern "C" size_t pdeqx_spectral_xhat_floats(const pdeqx_spectral_plan* p) {
+  return p ? (size_t)(2 * (int64_t)p->desc.batch * p->desc.c_in * p->J) : 0;
+}
+extern "C" size_t pdeqx_spectral_z_floats(const pdeqx_spectral_plan* p) {
+  if (!p) return 0;
+  return (size_t)(2 * (int64_t)p->desc.batch * p->desc.c_out * p->lead * p->desc.modes[p->desc.ndim - 1]);
+}
+
+namespace pdeqx {
+
+// real [R, s_D] -> complex [R, m_D]
+static int stage_r2c(const pdeqx_spectral_plan* p, const float* x, const float* table, int64_t rows, float* out,
+                     cudaStream_t s) {
+  const int D = p->desc.ndim;
+  const int sD = p->desc.spatial[D - 1], mD = p->desc.modes[D - 1];
+  if (tc_r2c_available(p)) return tc_r2c(p, x, table == p->t_r2c_bwd, rows, out, s);
+  SgemmArgs a{};
+  a.A = x; a.B = table; a.C = out;
+  a.M = rows; a.N = 2 * mD; a.K = sD;
+  a.lda_m = sD; a.lda_k = 1; a.ldb = 2 * mD; a.ldc = 2 * mD;
+  a.batch = 1; a.act = PDEQX_ACT_IDENTITY;
+  return sgemm_batched(a, s);
+}
+
+// complex [R, m_D] -> real [R, s_D]; out = act(result + add)
+static int stage_c2r(const pdeqx_spectral_plan* p, const float* z, const float* table, int64_t rows, const float* add,
+                     int act, float* out, cudaStream_t s) {
+  const int D = p->desc.ndim;
+  const int sD = p->desc.spatial[D - 1], mD = p->desc.modes[D - 1];
+  SgemmArgs a{};
+  a.A = z; a.B = table; a.C = out; a.add = add;
+  a.M = rows; a.N = sD; a.K = 2 * mD;
+  a.lda_m = 2 * mD; a.lda_k = 1; a.ldb = sD; a.ldc = sD;
+  a.batch = 1; a.act = act;
+  return sgemm_batched(a, s);
+}
+
+// One complex stage along axis `a` of a tensor [B*C, n_0.., n_a, .., inner] (complex).
+//   n_in -> n_out through table [n_out x n_in].
+static int stage_c2c(const float2* table, const float* in, float* out, int64_t outer, int n_in, int n_out,
+                     int64_t inner, cudaStream_t s) {
+  return cgemm_shared_a(table, (const float2*)in, (float2*)out, outer, n_out, n_in, inner, s);
+}
+
+// Workspace regions: two big ping-pong buffers for the chain intermediates and two
+// mode-space buffers (x_hat / y_hat in forward, g_yhat / g_xhat in backward).
+struct Regions {
+  float* big[2];
+  float* mode[2];
+};
+
+// x_hat[B, C, J] <- x[B, C, *S]. Intermediates live in r.big[]; src/dst must not alias them.
+static int forward_chain(const pdeqx_spectral_plan* p, const float* x, int C, bool adjoint_of_inverse, float* dst,
+                         const Regions& r, cudaStream_t s) {
+  const pdeqx_spectral_desc& d = p->desc;
+  const int D = d.ndim;
+  const int mD = d.modes[D - 1];
+  const int64_t BC = (int64_t)d.batch * C;
+  const float* tab_last = adjoint_of_inverse ? p->t_r2c_bwd : p->t_r2c_fwd;
+  float* o = (D == 1) ? dst : r.big[0];
+  PDEQX_TRY(stage_r2c(p, x, tab_last, BC * p->lead, o, s));
+  const float* cur = o;
+  int nb = 1;
+  // axes D-2 .. 0; at axis a the leading axes a' < a are still full-size, trailing ones are truncated
+  for (int a = D - 2; a >= 0; --a) {
+    int64_t outer = BC, inner = mD;
+    for (int b = 0; b < a; ++b) outer *= d.spatial[b];
+    for (int b = a + 1; b < D - 1; ++b) inner *= 2 * d.modes[b];
+    float* dstage = (a == 0) ? dst : r.big[nb];
+    const float2* tab = adjoint_of_inverse ? p->t_inv_adj[a] : p->t_fwd[a];
+    PDEQX_TRY(stage_c2c(tab, cur, dstage, outer, d.spatial[a], 2 * d.modes[a], inner, s));
+    cur = dstage;
+    nb ^= 1;
+  }
+  return PDEQX_OK;
+}
+
+// z[B*C*lead, m_D] <- y_hat[B, C, J] (leading-axis inverse stages, D > 1). Intermediates in r.big[0] only.
+static int inverse_chain(const pdeqx_spectral_plan* p, const float* yhat, int C, bool adjoint_of_forward, float* dst,
+                         const Regions& r, cudaStream_t s) {
+  const pdeqx_spectral_desc& d = p->desc;
+  const int D = d.ndim;
+  const int mD = d.modes[D - 1];
+  const int64_t BC = (int64_t)d.batch * C;
+  const float* cur = yhat;
+  for (int a = 0; a < D - 1; ++a) {
+    int64_t outer = BC, inner = mD;
+    for (int b = 0; b < a; ++b) outer *= d.spatial[b];
+    for (int b = a + 1; b < D - 1; ++b) inner *= 2 * d.modes[b];
+    float* dstage = (a == D - 2) ? dst : r.big[0];
+    const float2* tab = adjoint_of_forward ? p->t_fwd_adj[a] : p->t_inv[a];
+    PDEQX_TRY(stage_c2c(tab, cur, dstage, outer, 2 * d.modes[a], d.spatial[a], inner, s));
+    cur = dstage;
+  }
+  return PDEQX_OK;
+}
+
+static int check_ws(const pdeqx_spectral_plan* p, void* ws, size_t ws_bytes) {
+  if (!ws || ws_bytes < p->ws_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", p->ws_bytes, ws_bytes);
+    return PDEQX_ERR_WORKSPACE;
+  }
+  return PDEQX_OK;
+}
+
+static Regions make_regions(const pdeqx_spectral_plan* p, void* ws) {
+  uintptr_t base = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+  Regions r;
+  r.big[0] = (float*)base;
+  r.big[1] = r.big[0] + p->stage_floats;
+  r.mode[0] = r.big[1] + p->stage_floats;
+  r.mode[1] = r.mode[0] + p->mode_floats;
+  return r;
+}
+
+}  // namespace pdeqx
+
+extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const float* x, const float* w_re,
+                                        const float* w_im, const float* bypass_w, const float* bypass_b,
+                                        int32_t act, float* y, float* save_xhat, float* save_z, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(p && x && w_re && w_im && y, "null argument");
+  PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
+  PDEQX_CHECK_ARG(bypass_w || !bypass_b, "bypass_b without bypass_w");
+  PDEQX_TRY(check_ws(p, workspace, workspace_bytes));
+  cudaStream_t s = (cudaStream_t)stream;
+  const pdeqx_spectral_desc& d = p->desc;
+  const int D = d.ndim;
+  const int sD = d.spatial[D - 1];
+  const int64_t n_pix = p->lead * sD;
+  Regions r = make_regions(p, workspace);
+
+  // forward transform -> x_hat [B, c_in, J]
+  float* xhat = save_xhat ? save_xhat : r.mode[0];
+  PDEQX_TRY(forward_chain(p, x, d.c_in, false, xhat, r, s));
+  // channel mix -> y_hat [B, c_out, J] (for D == 1 this already is z)
+  float* yhat = (D == 1 && save_z) ? save_z : r.mode[1];
+  PDEQX_TRY(mode_mix(p, xhat, w_re, w_im, /*transposed_conj=*/false, yhat, s));
+  // leading-axis inverse stages -> z
+  const float* z = yhat;
+  if (D > 1) {
+    float* zbuf = save_z ? save_z : r.big[1];
+    PDEQX_TRY(inverse_chain(p, yhat, d.c_out, false, zbuf, r, s));
+    z = zbuf;
+  }
+  // last stage: c2r (+ bypass + bias + activation)
+  const int64_t rows = (int64_t)d.batch * d.c_out * p->lead;
+  if (tc_slab_available(p, bypass_w != nullptr))
+    return tc_slab(p, x, z, /*table_sel=*/0, bypass_w, /*bypass_transposed=*/false, bypass_b, act, y, s);
+  if (!bypass_w) return stage_c2r(p, z, p->t_c2r_inv, rows, nullptr, act, y, s);
+  PDEQX_TRY(stage_c2r(p, z, p->t_c2r_inv, rows, nullptr, PDEQX_ACT_IDENTITY, y, s));
+  return pdeqx_pointwise_fwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, bypass_b, /*add=*/y, act, y, stream);
+}
+
+extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const float* x, const float* gy,
+                                        const float* w_re, const float* w_im, const float* bypass_w,
+                                        const float* bypass_b, int32_t act, const float* saved_xhat,
+                                        const float* saved_z, float* gx, float* gw_re, float* gw_im,
+                                        float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(p && x && gy && w_re && w_im && saved_xhat && gw_re && gw_im, "null argument");
+  PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
+  PDEQX_CHECK_ARG(!bypass_w || g_bypass_w, "g_bypass_w is required when bypass_w is given");
+  PDEQX_TRY(check_ws(p, workspace, workspace_bytes));
+  cudaStream_t s = (cudaStream_t)stream;
+  const pdeqx_spectral_desc& d = p->desc;
+  const int D = d.ndim;
+  const int sD = d.spatial[D - 1];
+  const int64_t n_pix = p->lead * sD;
+  const int64_t rows_o = (int64_t)d.batch * d.c_out * p->lead;
+  const int64_t rows_i = (int64_t)d.batch * d.c_in * p->lead;
+  Regions r = make_regions(p, workspace);
+
+  // 1. cotangent of the pre-activation
+  const float* gpre = gy;
+  if (act != PDEQX_ACT_IDENTITY) {
+    PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
+    PDEQX_TRY(stage_c2r(p, saved_z, p->t_c2r_inv, rows_o, nullptr, PDEQX_ACT_IDENTITY, scratch_full, s));
+    if (bypass_w)
+      PDEQX_TRY(pdeqx_pointwise_fwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, bypass_b, scratch_full,
+                                    PDEQX_ACT_IDENTITY, scratch_full, stream));
+    PDEQX_TRY(pdeqx_activation_bwd((int64_t)d.batch * d.c_out * n_pix, scratch_full, gy, act, scratch_full, stream));
+    gpre = scratch_full;
+  }
+  // 2. bypass grads (and the bypass part of gx)
+  bool gx_has_bypass = false;
+  if (bypass_w) {
+    PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, gpre, gx, g_bypass_w,
+                                  bypass_b ? g_bypass_b : nullptr, stream));
+    gx_has_bypass = gx != nullptr;
+  }
+  // 3. g_yhat = adjoint of the inverse transform applied to gpre
+  float* ghat = r.mode[0];
+  PDEQX_TRY(forward_chain(p, gpre, d.c_out, /*adjoint_of_inverse=*/true, ghat, r, s));
+  // 4. weight gradient (batch-reduced inside the kernel)
+  PDEQX_TRY(mode_mix_dw(p, ghat, saved_xhat, gw_re, gw_im, s));
+  if (!gx) return PDEQX_OK;
+  // 5. g_xhat = W^H g_yhat
+  float* gxhat = r.mode[1];
+  PDEQX_TRY(mode_mix(p, ghat, w_re, w_im, /*transposed_conj=*/true, gxhat, s));
+  // 6. adjoint of the leading forward stages
+  const float* gx1 = gxhat;
+  if (D > 1) {
+    float* t = r.big[1];
+    PDEQX_TRY(inverse_chain(p, gxhat, d.c_in, /*adjoint_of_forward=*/true, t, r, s));
+    gx1 = t;
+  }
+  // 7. last stage back to real space (+ bypass contribution already in gx)
+  return stage_c2r(p, gx1, p->t_c2r_bwd, rows_i, gx_has_bypass ? gx : nullptr, PDEQX_ACT_IDENTITY, gx, s);
+}

@@ -1,0 +1,48 @@
+// Internal: the spectral plan object and the stage entry points shared between
+// spectral.cu (sequencing), modemix.cu (channel mix) and tc_spectral.cu (tcgen05 stages).
+#pragma once
+#include "common.cuh"
+
+struct pdeqx_spectral_plan {
+  pdeqx_spectral_desc desc;
+  int G = 1;
+  int64_t lead = 1;          // prod of the leading spatial sizes s_0..s_{D-2}
+  int64_t J = 1;             // retained modes per channel: prod(2 m_a, a < D-1) * m_D
+  int64_t stage_floats = 0;  // floats of one chain ping-pong buffer
+  int64_t mode_floats = 0;   // floats of one mode-space buffer
+  size_t ws_bytes = 0;
+  // last axis, real tables (fp32, generated in fp64)
+  float* t_r2c_fwd = nullptr;  // [s_D, 2 m_D]  cos | -sin                (forward)
+  float* t_c2r_inv = nullptr;  // [2 m_D, s_D]  c/s cos ; -c/s sin        (inverse, irfft weights c)
+  float* t_r2c_bwd = nullptr;  // [s_D, 2 m_D]  = t_c2r_inv^T             (adjoint of inverse)
+  float* t_c2r_bwd = nullptr;  // [2 m_D, s_D]  = t_r2c_fwd^T             (adjoint of forward)
+  // leading axes, complex tables
+  float2* t_fwd[PDEQX_MAX_DIMS] = {nullptr, nullptr, nullptr};      // [2m, s]
+  float2* t_inv[PDEQX_MAX_DIMS] = {nullptr, nullptr, nullptr};      // [s, 2m]
+  float2* t_inv_adj[PDEQX_MAX_DIMS] = {nullptr, nullptr, nullptr};  // [2m, s] = conj(t_inv)^T
+  float2* t_fwd_adj[PDEQX_MAX_DIMS] = {nullptr, nullptr, nullptr};  // [s, 2m] = conj(t_fwd)^T
+  // tcgen05 side (tc_spectral.cu); null when the shape does not qualify
+  void* tc = nullptr;
+};
+
+namespace pdeqx {
+
+// out[b,u,p] = sum_v W(u,v,p) in[b,v,p]; transposed_conj: W(u,v) = conj(w[o=v, i=u]) (u over c_in), else
+// W(u,v) = w[o=u, i=v] (u over c_out). in/out are complex-interleaved [B, C, J].
+int mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re, const float* w_im,
+             bool transposed_conj, float* out, cudaStream_t s);
+// gw[g,o,i,loc] = sum_b ghat[b,o,p] conj(xhat[b,i,p])
+int mode_mix_dw(const pdeqx_spectral_plan* p, const float* ghat, const float* xhat, float* gw_re, float* gw_im,
+                cudaStream_t s);
+
+// tcgen05 stages
+int tc_plan_init(pdeqx_spectral_plan* p);
+void tc_plan_free(pdeqx_spectral_plan* p);
+bool tc_r2c_available(const pdeqx_spectral_plan* p);
+int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int64_t rows, float* out, cudaStream_t s);
+bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass);
+// y = act( c2r(z) [table_sel: 0 = inverse, 1 = adjoint-of-forward] + W(.)x + b )
+int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+            bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s);
+
+}  // namespace pdeqx

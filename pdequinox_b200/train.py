@@ -1,0 +1,117 @@
+"""Batch-sharded training step: MSE loss, explicit reverse pass, gradient all-reduce, fused Adam.
+
+The reference has no training code of its own; users write (README.md:74-86)
+    loss = mean((vmap(model)(x) - y)**2); eqx.filter_value_and_grad; optax.adam(3e-4); eqx.apply_updates
+and no multi-device code exists at all. This module is that step for one rank of a
+data-parallel job: parameters, gradients and Adam moments live in flat fp32 arenas in the reference's
+pytree leaf order; each rank runs the forward and reverse pass on its shard of the batch, the gradient
+arena is summed across ranks with ONE NCCL all-reduce over NVLink (torch.distributed is the plumbing),
+and the 1/world_size scaling is fused into the Adam kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._module import Tape, _as_device, default_device
+
+
+class ParameterArena:
+    """Re-homes every parameter of `model` into one flat buffer (16-byte aligned slices, pytree order)
+    and gives every parameter a gradient view in a second flat buffer."""
+
+    def __init__(self, model):
+        self.model = model
+        self.entries = []  # (path, owner, field, offset, numel, shape)
+        off = 0
+        for path, owner, field in model.named_leaves():
+            t = getattr(owner, field)
+            self.entries.append((path, owner, field, off, t.numel(), tuple(t.shape)))
+            off += (t.numel() + 3) // 4 * 4
+        self.size = off
+        dev = default_device()
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        for path, owner, field, o, n, shape in self.entries:
+            view = self.params[o:o + n].view(shape)
+            view.copy_(getattr(owner, field))
+            setattr(owner, field, view)
+            if not hasattr(owner, "_grads"):
+                owner._grads = {}
+            owner._grads[field] = self.grads[o:o + n].view(shape)
+
+    def named_grads(self):
+        return {p: self.grads[o:o + n].view(shape) for p, _, _, o, n, shape in self.entries}
+
+    def named_params(self):
+        return {p: self.params[o:o + n].view(shape) for p, _, _, o, n, shape in self.entries}
+
+    def load(self, named):
+        """Overwrite parameters from a {path: array} mapping (tests: identical weights as the oracle)."""
+        import numpy as np
+        for p, _, _, o, n, shape in self.entries:
+            if p in named:
+                a = torch.from_numpy(np.ascontiguousarray(named[p], dtype=np.float32)).reshape(shape)
+                self.params[o:o + n].view(shape).copy_(a)
+
+
+class TrainStep:
+    """One Adam step on mse(vmap(model)(x), y); `world` = a torch.distributed process group (or None)."""
+
+    def __init__(self, model, lr=3e-4, b1=0.9, b2=0.999, eps=1e-8, process_group=None, distributed=None):
+        self.model = model
+        self.arena = ParameterArena(model)
+        dev = default_device()
+        self.mu = torch.zeros_like(self.arena.params)
+        self.nu = torch.zeros_like(self.arena.params)
+        self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
+        self.count = 0
+        self.tape = Tape()
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.partials = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.pg = process_group
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.distributed = distributed
+        self.world = torch.distributed.get_world_size(process_group) if distributed else 1
+
+    def loss_and_grad(self, x, y):
+        """Local-shard loss (device scalar) and gradients into the arena (not yet reduced)."""
+        x, y = _as_device(x), _as_device(y)
+        tape = self.tape
+        tape.stack.clear()
+        pred = self.model._fwd(x, tape)
+        if pred.shape != y.shape:
+            raise ValueError(f"prediction {tuple(pred.shape)} and target {tuple(y.shape)} differ in shape")
+        gpred = tape.buf(self, "gpred", pred.shape)
+        _lib.check(_lib.lib().pdeqx_mse_loss(pred.numel(), _lib.ptr(pred), _lib.ptr(y), 1.0, _lib.ptr(self.loss),
+                                             _lib.ptr(gpred), _lib.ptr(self.partials), _lib.stream()))
+        self.model._bwd(gpred, tape, False)
+        return self.loss
+
+    def apply_gradients(self):
+        """All-reduce (sum) the gradient arena over the data-parallel group, then Adam with grad/world."""
+        if self.distributed and self.world > 1:
+            torch.distributed.all_reduce(self.arena.grads, group=self.pg)
+            torch.distributed.all_reduce(self.loss, group=self.pg)
+            self.loss.div_(self.world)
+        self.count += 1
+        _lib.check(_lib.lib().pdeqx_adam_step(self.arena.size, _lib.ptr(self.arena.params), _lib.ptr(self.arena.grads),
+                                              _lib.ptr(self.mu), _lib.ptr(self.nu), self.lr, self.b1, self.b2,
+                                              self.eps, self.count, 1.0 / self.world, _lib.stream()))
+
+    def __call__(self, x, y):
+        """x, y: this rank's shard (B_local, C, *S). Returns the (global mean) loss as a device scalar."""
+        self.loss_and_grad(x, y)
+        self.apply_gradients()
+        return self.loss
+
+
+def shard_batch(x, rank, world):
+    """Rank r gets samples [r*B/n, (r+1)*B/n); B must divide evenly so that the mean of
+    the local gradients equals the full-batch gradient."""
+    B = x.shape[0]
+    if B % world != 0:
+        raise ValueError(f"global batch {B} is not divisible by the number of ranks {world}")
+    per = B // world
+    return x[rank * per:(rank + 1) * per]
