@@ -70,6 +70,22 @@ int pdeqx_has_tcgen05(void);
 /* force-disable (0) / enable (1) the tcgen05 fast paths (tests compare both). */
 void pdeqx_set_fast_paths(int enabled);
 
+/* Per-kernel device timing for bench.py's roofline line: while enabled, the launchers of the tagged
+ * kernels bracket each launch with a cudaEvent pair on the launching stream. pdeqx_timing_read
+ * synchronises those events and returns the summed duration and the launch count of one tag. */
+enum pdeqx_kernel_tag {
+  PDEQX_K_SPECTRAL_SLAB = 1, /* last stage of the spectral block: c2r DFT + bypass 1x1 + bias + activation */
+  PDEQX_K_SPECTRAL_R2C = 2,  /* first stage: truncated real-to-complex DFT along the contiguous axis */
+  PDEQX_K_SPECTRAL_MODES = 3,/* leading-axis DFT stages + per-mode channel mix (mode-space kernels) */
+  PDEQX_K_POINTWISE_WGRAD = 4,
+  PDEQX_K_CONV_FWD = 5,
+  PDEQX_K_CONV_BWD_DATA = 6,
+  PDEQX_K_CONV_BWD_FILTER = 7,
+  PDEQX_K_TAG_COUNT = 8
+};
+void pdeqx_timing_enable(int enabled); /* also clears what was recorded */
+int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launches);
+
 /* ------------------------------------------------------------------------- *
  * SpectralConv / ClassicSpectralBlock
  *   replaces pdequinox/conv/_spectral_conv.py:107-136 (spectral_conv_nd) and

@@ -13,6 +13,7 @@ MAX_DIMS = 3
 ACT_IDENTITY, ACT_RELU, ACT_GELU_TANH = 0, 1, 2
 PAD_ZEROS, PAD_WRAP, PAD_REFLECT, PAD_EDGE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32 = 0, 1
+K_SPECTRAL_SLAB, K_SPECTRAL_R2C, K_SPECTRAL_MODES, K_POINTWISE_WGRAD, K_CONV_FWD, K_CONV_BWD_DATA, K_CONV_BWD_FILTER = range(1, 8)
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpdeqx_b200.so")
 
@@ -43,6 +44,8 @@ PROTOTYPES = {
     "pdeqx_launch_count": (C.c_uint64, []),
     "pdeqx_has_tcgen05": (C.c_int, []),
     "pdeqx_set_fast_paths": (None, [C.c_int]),
+    "pdeqx_timing_enable": (None, [C.c_int]),
+    "pdeqx_timing_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pdeqx_spectral_plan_create": (C.c_int, [C.POINTER(SpectralDesc), C.POINTER(_P)]),
     "pdeqx_spectral_plan_destroy": (None, [_P]),
     "pdeqx_spectral_workspace_bytes": (C.c_size_t, [_P]),

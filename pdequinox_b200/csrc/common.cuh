@@ -52,6 +52,15 @@ extern std::atomic<int> g_fast_paths;
     if (rc__ != PDEQX_OK) return rc__; \
   } while (0)
 
+// ---- optional per-kernel timing (core.cu) --------------------------------------------------
+struct TimedScope {
+  int tag;
+  cudaStream_t stream;
+  int slot;
+  TimedScope(int tag, cudaStream_t s);
+  ~TimedScope();
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- activations (device) -------------------------------------------------

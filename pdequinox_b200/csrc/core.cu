@@ -1,6 +1,9 @@
 // Library-wide state: error string, launch counter, fast-path switch, version.
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace pdeqx {
@@ -16,7 +19,62 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- per-kernel timing ---------------------------------------------------------------------
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+struct TimedRec { cudaEvent_t a, b; int tag; };
+static std::vector<TimedRec> g_timed;
+constexpr size_t kMaxTimed = 1 << 16;
+
+TimedScope::TimedScope(int t, cudaStream_t s) : tag(t), stream(s), slot(-1) {
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (g_timed.size() >= kMaxTimed) return;
+  TimedRec r{};
+  r.tag = t;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  slot = (int)g_timed.size();
+  g_timed.push_back(r);
+}
+
+TimedScope::~TimedScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if ((size_t)slot < g_timed.size()) cudaEventRecord(g_timed[slot].b, stream);
+}
+
 }  // namespace pdeqx
+
+extern "C" void pdeqx_timing_enable(int enabled) {
+  using namespace pdeqx;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (auto& r : g_timed) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_timed.clear();
+  g_timing.store(enabled ? 1 : 0);
+}
+
+extern "C" int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launches) {
+  using namespace pdeqx;
+  PDEQX_CHECK_ARG(total_ms && launches, "null argument");
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  double tot = 0.0;
+  int64_t n = 0;
+  for (auto& r : g_timed) {
+    if (r.tag != tag) continue;
+    PDEQX_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    PDEQX_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *launches = n;
+  return PDEQX_OK;
+}
 
 extern "C" const char* pdeqx_last_error(void) { return pdeqx::t_error; }
 extern "C" const char* pdeqx_version(void) { return "0.1.0 (sm_100a)"; }

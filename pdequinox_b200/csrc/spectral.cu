@@ -180,6 +180,7 @@ static int stage_r2c(const pdeqx_spectral_plan* p, const float* x, const float* 
                      cudaStream_t s) {
   const int D = p->desc.ndim;
   const int sD = p->desc.spatial[D - 1], mD = p->desc.modes[D - 1];
+  TimedScope timed(PDEQX_K_SPECTRAL_R2C, s);
   if (tc_r2c_available(p)) return tc_r2c(p, x, table == p->t_r2c_bwd, rows, out, s);
   SgemmArgs a{};
   a.A = x; a.B = table; a.C = out;
@@ -194,6 +195,7 @@ static int stage_c2r(const pdeqx_spectral_plan* p, const float* z, const float* 
                      int act, float* out, cudaStream_t s) {
   const int D = p->desc.ndim;
   const int sD = p->desc.spatial[D - 1], mD = p->desc.modes[D - 1];
+  TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
   SgemmArgs a{};
   a.A = z; a.B = table; a.C = out; a.add = add;
   a.M = rows; a.N = sD; a.K = 2 * mD;
