@@ -115,6 +115,9 @@ size_t pdeqx_spectral_workspace_bytes(const pdeqx_spectral_plan* plan);
  * z = [B, c_out, S_1..S_{D-1}, m_D] complex (input of the last inverse stage) */
 size_t pdeqx_spectral_xhat_floats(const pdeqx_spectral_plan* plan);
 size_t pdeqx_spectral_z_floats(const pdeqx_spectral_plan* plan);
+/* which stages of this plan run on tcgen05 (bit 0: first-stage r2c DFT, bit 1: last-stage slab kernel,
+ * bit 2: bypass weight gradient); 0 in fp32 precision or when the shape does not qualify */
+int pdeqx_spectral_plan_tcgen05_stages(const pdeqx_spectral_plan* plan);
 
 /* y[B,c_out,*S] = act( irfftn(mix(rfftn(x))) + (bypass_w . x + bypass_b) )
  *   w_re, w_im : [G, c_out, c_in, *modes] (G = 2^(ndim-1), corner order of

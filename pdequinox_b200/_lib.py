@@ -51,6 +51,7 @@ PROTOTYPES = {
     "pdeqx_spectral_workspace_bytes": (C.c_size_t, [_P]),
     "pdeqx_spectral_xhat_floats": (C.c_size_t, [_P]),
     "pdeqx_spectral_z_floats": (C.c_size_t, [_P]),
+    "pdeqx_spectral_plan_tcgen05_stages": (C.c_int, [_P]),
     "pdeqx_spectral_block_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_spectral_block_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                            C.c_size_t, _P]),

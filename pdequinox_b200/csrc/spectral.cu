@@ -173,6 +173,8 @@ extern "C" size_t pdeqx_spectral_z_floats(const pdeqx_spectral_plan* p) {
   return (size_t)(2 * (int64_t)p->desc.batch * p->desc.c_out * p->lead * p->desc.modes[p->desc.ndim - 1]);
 }
 
+extern "C" int pdeqx_spectral_plan_tcgen05_stages(const pdeqx_spectral_plan* p) { return p ? tc_stage_mask(p) : 0; }
+
 namespace pdeqx {
 
 // real [R, s_D] -> complex [R, m_D]
@@ -314,8 +316,10 @@ extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const floa
   }
   // last stage: c2r (+ bypass + bias + activation)
   const int64_t rows = (int64_t)d.batch * d.c_out * p->lead;
-  if (tc_slab_available(p, bypass_w != nullptr))
+  if (tc_slab_available(p, bypass_w != nullptr)) {
+    TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     return tc_slab(p, x, z, /*table_sel=*/0, bypass_w, /*bypass_transposed=*/false, bypass_b, act, y, s);
+  }
   if (!bypass_w) return stage_c2r(p, z, p->t_c2r_inv, rows, nullptr, act, y, s);
   PDEQX_TRY(stage_c2r(p, z, p->t_c2r_inv, rows, nullptr, PDEQX_ACT_IDENTITY, y, s));
   return pdeqx_pointwise_fwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, bypass_b, /*add=*/y, act, y, stream);
@@ -340,23 +344,38 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
   const int64_t rows_i = (int64_t)d.batch * d.c_in * p->lead;
   Regions r = make_regions(p, workspace);
 
-  // 1. cotangent of the pre-activation
+  // 1. cotangent of the pre-activation (pre-activation recomputed from the saved z: nothing full-size is kept)
+  const bool fast = tc_slab_available(p, bypass_w != nullptr);
   const float* gpre = gy;
   if (act != PDEQX_ACT_IDENTITY) {
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
-    PDEQX_TRY(stage_c2r(p, saved_z, p->t_c2r_inv, rows_o, nullptr, PDEQX_ACT_IDENTITY, scratch_full, s));
-    if (bypass_w)
-      PDEQX_TRY(pdeqx_pointwise_fwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, bypass_b, scratch_full,
-                                    PDEQX_ACT_IDENTITY, scratch_full, stream));
-    PDEQX_TRY(pdeqx_activation_bwd((int64_t)d.batch * d.c_out * n_pix, scratch_full, gy, act, scratch_full, stream));
+    if (fast) {
+      TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+      PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/1, gy, d.c_in, d.c_out, scratch_full, s));
+    } else {
+      PDEQX_TRY(stage_c2r(p, saved_z, p->t_c2r_inv, rows_o, nullptr, PDEQX_ACT_IDENTITY, scratch_full, s));
+      if (bypass_w)
+        PDEQX_TRY(pdeqx_pointwise_fwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, bypass_b, scratch_full,
+                                      PDEQX_ACT_IDENTITY, scratch_full, stream));
+      PDEQX_TRY(pdeqx_activation_bwd((int64_t)d.batch * d.c_out * n_pix, scratch_full, gy, act, scratch_full, stream));
+    }
     gpre = scratch_full;
   }
-  // 2. bypass grads (and the bypass part of gx)
+  // 2. bypass grads (and the bypass part of gx; on the tcgen05 path that part is fused into step 7)
   bool gx_has_bypass = false;
+  const bool fuse_bypass_gx = fast && bypass_w && gx;
   if (bypass_w) {
-    PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, gpre, gx, g_bypass_w,
-                                  bypass_b ? g_bypass_b : nullptr, stream));
-    gx_has_bypass = gx != nullptr;
+    if (fast && tc_wgrad_available(p, n_pix)) {
+      TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
+      PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));
+      float* gb = bypass_b ? g_bypass_b : nullptr;
+      if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)d.c_out, s));
+      PDEQX_TRY(tc_wgrad(p, gpre, x, n_pix, g_bypass_w, gb, s));
+    } else {
+      PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, gpre, fuse_bypass_gx ? nullptr : gx,
+                                    g_bypass_w, bypass_b ? g_bypass_b : nullptr, stream));
+      gx_has_bypass = gx != nullptr && !fuse_bypass_gx;
+    }
   }
   // 3. g_yhat = adjoint of the inverse transform applied to gpre
   float* ghat = r.mode[0];
@@ -374,6 +393,10 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
     PDEQX_TRY(inverse_chain(p, gxhat, d.c_in, /*adjoint_of_forward=*/true, t, r, s));
     gx1 = t;
   }
-  // 7. last stage back to real space (+ bypass contribution already in gx)
+  // 7. last stage back to real space, plus the bypass contribution W^T gpre
+  if (fast) {
+    TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+    return tc_slab(p, gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, gx, s);
+  }
   return stage_c2r(p, gx1, p->t_c2r_bwd, rows_i, gx_has_bypass ? gx : nullptr, PDEQX_ACT_IDENTITY, gx, s);
 }

@@ -39,10 +39,20 @@ int mode_mix_dw(const pdeqx_spectral_plan* p, const float* ghat, const float* xh
 int tc_plan_init(pdeqx_spectral_plan* p);
 void tc_plan_free(pdeqx_spectral_plan* p);
 bool tc_r2c_available(const pdeqx_spectral_plan* p);
+int tc_stage_mask(const pdeqx_spectral_plan* p);
 int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int64_t rows, float* out, cudaStream_t s);
 bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass);
 // y = act( c2r(z) [table_sel: 0 = inverse, 1 = adjoint-of-forward] + W(.)x + b )
 int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
             bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s);
+
+// general form: explicit channel counts of THIS call, epilogue mode 1 = aux * act'(.) (cotangent of the pre-activation)
+int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+               bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
+               float* y, cudaStream_t s);
+bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);
+// gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller)
+int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb,
+             cudaStream_t s);
 
 }  // namespace pdeqx

@@ -1,14 +1,889 @@
-// tcgen05 stages of the spectral block (placeholder: not yet enabled; the fp32 GEMM stages run).
+// tcgen05 (TF32) stages of the spectral block -- the three kernels that touch the full-size tensors.
+//
+//   tc_r2c   : X1[row, 0:2m]  = sum_w x[row, w] T[w, :]                 (truncated r2c DFT, first stage)
+//   tc_slab  : y[b,o,l,w]     = epi( sum_k Z[b,o,l,k] Tc[k,w] + sum_i W[o,i] x[b,i,l,w] + bias[o] )
+//              (inverse DFT along the contiguous axis + 1x1 bypass + bias + activation, one pass:
+//               x is read once and y written once -- SURVEY.md App. D.1)
+//   tc_wgrad : gW[o,i] = sum_{b,p} g[b,o,p] x[b,i,p],  gb[o] = sum_{b,p} g[b,o,p]   (bypass weight gradient)
+//
+// All three are persistent, warp-specialised kernels: warp 0 = TMA producer, warp 1 = tcgen05.mma
+// issuer (one elected lane), warp 2 = TMEM allocator, warps 4.. = epilogue (tcgen05.ld -> registers ->
+// coalesced global stores). Operand tiles are staged by TMA with the 128-byte swizzle and consumed
+// through shared-memory descriptors; accumulators live in TMEM (double-buffered where the kernel has
+// more than one output tile per CTA). They are HBM-bound by construction (16-36 flop/B, SURVEY.md
+// App. B): the tensor pipe only has to stay under the memory time, which CUDA-core FFMA cannot.
+#include <math.h>
+
+#include <vector>
+
 #include "spectral_plan.h"
+#include "tc_common.cuh"
 
 namespace pdeqx {
-int tc_plan_init(pdeqx_spectral_plan*) { return PDEQX_OK; }
-void tc_plan_free(pdeqx_spectral_plan*) {}
-bool tc_r2c_available(const pdeqx_spectral_plan*) { return false; }
-int tc_r2c(const pdeqx_spectral_plan*, const float*, bool, int64_t, float*, cudaStream_t) { return PDEQX_ERR_UNSUPPORTED; }
-bool tc_slab_available(const pdeqx_spectral_plan*, bool) { return false; }
-int tc_slab(const pdeqx_spectral_plan*, const float*, const float*, int, const float*, bool, const float*, int, float*,
-            cudaStream_t) {
-  return PDEQX_ERR_UNSUPPORTED;
+namespace tc {
+
+// ------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
 }
+
+int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return PDEQX_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle == TM_SW128_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                             : (swizzle == TM_NONE ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu/%llu/%llu, box %u/%u/%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return PDEQX_ERR_CUDA;
+  }
+  return PDEQX_OK;
+}
+
+static float host_round_tf32(float v) {  // round-to-nearest (ties away), like cvt.rna.tf32.f32
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return v;
+  u += 0x1000u;
+  u &= 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+constexpr int kThreadsSlab = 384;   // warps 0-2 roles, warp 3 idle, warps 4-11 epilogue
+constexpr int kThreadsR2c = 256;    // warps 0-2 roles, warp 3 idle, warps 4-7 epilogue
+constexpr int kTmemCols = 256;
+
+// ------------------------------------------------------------------------------------------
+// epilogue math
+// ------------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ __forceinline__ float gelu_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  float t = FAST ? tanh_fast(u) : tanh_accurate(u);
+  return 0.5f * x * (1.0f + t);
+}
+template <bool FAST>
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float x2 = x * x;
+  float u = k0 * (x + k1 * x * x2);
+  float t = FAST ? tanh_fast(u) : tanh_accurate(u);
+  float du = k0 * (1.0f + 3.0f * k1 * x2);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+
+// ==========================================================================================
+// slab kernel
+// ==========================================================================================
+struct SlabParams {
+  int lead, W, wt_per_row, c_in, c_out;
+  int has_bypass, mode, act, round_out;
+  int stages;
+  int64_t units;  // B * lead * wt_per_row
+  const float* bias;
+  const float* aux;  // mode 1: cotangent gy
+  float* y;
+};
+
+// smem carve-up (all tile regions 1024-B aligned)
+struct SlabSmem {
+  uint32_t tab_off, w_off, stage_off, stage_bytes, x_box_bytes, z_off_in_stage, epi_off, epi_buf_bytes, bar_off, total;
+};
+
+static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages) {
+  SlabSmem s{};
+  uint32_t off = 0;
+  s.tab_off = off;
+  off += 128 * 128;  // one [128 w x 32 k] table tile: the grid is a multiple of W/128, so a CTA only ever sees one w-tile
+  (void)W;
+  s.w_off = off;
+  off += bypass ? (uint32_t)((c_in + 31) / 32) * c_out * 128 : 0;
+  s.x_box_bytes = (uint32_t)c_in * 128;
+  s.z_off_in_stage = bypass ? 4 * s.x_box_bytes : 0;
+  s.stage_bytes = s.z_off_in_stage + (uint32_t)c_out * 128;
+  s.stage_bytes = (s.stage_bytes + 1023) & ~1023u;
+  s.stage_off = off;
+  off += s.stage_bytes * stages;
+  // epilogue staging: per half of the output channels, two [c_out/2 x 128 w] fp32 tiles (TMA store source / aux target)
+  s.epi_off = off;
+  s.epi_buf_bytes = (uint32_t)(c_out / 2) * 512;
+  off += 4 * s.epi_buf_bytes;
+  s.bar_off = off;
+  off += 1024;  // barriers, tmem pointer, bias
+  s.total = off + 1024;  // slack for manual 1024-B alignment of the dynamic base
+  return s;
+}
+
+template <bool FAST_MATH>
+__global__ void __launch_bounds__(kThreadsSlab, 1)
+slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z,
+            const __grid_constant__ CUtensorMap tm_tab, const __grid_constant__ CUtensorMap tm_w,
+            const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_aux, SlabParams p, SlabSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* full = bars;                   // [stages]
+  uint64_t* empty = bars + 8;              // [stages]
+  uint64_t* tfull = bars + 16;             // [2]
+  uint64_t* tempty = bars + 18;            // [2]
+  uint64_t* tabfull = bars + 20;           // [1]
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 22);
+  uint64_t* auxfull = bars + 24;           // [2 halves][2 buffers]
+  float* bias_s = (float*)(bars + 28);     // [c_out] (<= 128 floats)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_z);
+    tma_prefetch_desc(&tm_tab);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 8);
+    mbar_init(&tempty[1], 8);
+    mbar_init(tabfull, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&auxfull[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 3) {
+    for (int i = lane; i < p.c_out; i += 32) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_y);
+      tma_prefetch_desc(&tm_aux);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // constant operands: DFT table tiles and the bypass weight chunks
+      const int wchunks = p.has_bypass ? (p.c_in + 31) / 32 : 0;
+      mbar_expect_tx(tabfull, 128 * 128 + (uint32_t)wchunks * p.c_out * 128);
+      tma_load_2d(smem + L.tab_off, &tm_tab, tabfull, 0, (int)(first % p.wt_per_row) * 128);
+      for (int c = 0; c < wchunks; ++c) tma_load_2d(smem + L.w_off + c * p.c_out * 128, &tm_w, tabfull, c * 32, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t u = first; u < p.units; u += stride) {
+        const int wt = (int)(u % p.wt_per_row);
+        const int64_t bl = u / p.wt_per_row;
+        const int l = (int)(bl % p.lead);
+        const int b = (int)(bl / p.lead);
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + L.stage_off + (size_t)s * L.stage_bytes;
+        mbar_expect_tx(&full[s], (p.has_bypass ? 4 * L.x_box_bytes : 0) + (uint32_t)p.c_out * 128);
+        if (p.has_bypass)
+          for (int j = 0; j < 4; ++j)
+            tma_load_3d(st + j * L.x_box_bytes, &tm_x, &full[s], wt * 128 + j * 32, l, b * p.c_in);
+        tma_load_3d(st + L.z_off_in_stage, &tm_z, &full[s], 0, l, b * p.c_out);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_kk = idesc_tf32(128, p.c_out, false, false);
+      const uint32_t idesc_mk = idesc_tf32(128, p.c_out, true, false);
+      mbar_wait(tabfull, 0);
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int64_t u = first; u < p.units; u += stride) {
+        mbar_wait(&tempty[a], aph ^ 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(a * p.c_out);
+        const uint32_t st = smem_u32(smem + L.stage_off + (size_t)s * L.stage_bytes);
+        // spectral part: A = table tile [128 w x 32 k] (K-major), B = Z box [c_out x 32 k] (K-major)
+        const uint32_t ta = smem_u32(smem + L.tab_off);
+        const uint32_t zb = st + L.z_off_in_stage;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_tf32(d, smem_desc_sw128(ta + k * 32, 0, 1024), smem_desc_sw128(zb + k * 32, 0, 1024), idesc_kk, k > 0);
+        // bypass part: A = x slab [128 w x c_in] (MN-major: w contiguous), B = W [c_out x c_in] (K-major)
+        if (p.has_bypass) {
+          const uint32_t wb = smem_u32(smem + L.w_off);
+          const int ksteps = p.c_in / 8;
+          for (int k = 0; k < ksteps; ++k)
+            mma_tf32(d, smem_desc_sw128_atom32(st + k * 1024, L.x_box_bytes, 512),
+                     smem_desc_sw128(wb + (k >> 2) * p.c_out * 128 + (k & 3) * 32, 0, 1024), idesc_mk, true);
+        }
+        mma_commit(&empty[s]);
+        mma_commit(&tfull[a]);
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> smem tile -> TMA store =====================
+    // Two groups of 4 warps (one per half of the output channels). A group owns two [ncol x 128 w] smem
+    // tiles; in mode 1 the cotangent tile is TMA-loaded into the tile first and updated in place.
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;  // which half of the output channels
+    const int ncol = p.c_out / 2;
+    const bool leader = (q == 0 && lane == 0);
+    uint8_t* ebuf0 = smem + L.epi_off + (size_t)half * 2 * L.epi_buf_bytes;
+    uint64_t* afull = auxfull + half * 2;
+    int a = 0, e = 0;
+    uint32_t aph = 0, eph = 0;
+    if (p.mode == 1 && leader && first < p.units) {
+      const int wt = (int)(first % p.wt_per_row);
+      const int64_t bl = first / p.wt_per_row;
+      mbar_expect_tx(&afull[0], L.epi_buf_bytes);
+      tma_load_3d(ebuf0, &tm_aux, &afull[0], wt * 128, (int)(bl % p.lead), (int)(bl / p.lead) * p.c_out + half * ncol);
+    }
+    for (int64_t u = first; u < p.units; u += stride) {
+      const int wt = (int)(u % p.wt_per_row);
+      const int64_t bl = u / p.wt_per_row;
+      const int l = (int)(bl % p.lead);
+      const int b = (int)(bl / p.lead);
+      float* tile = (float*)(ebuf0 + (size_t)e * L.epi_buf_bytes);
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+      if (p.mode == 1) {
+        mbar_wait(&afull[e], eph);
+      } else {
+        // the store that last used this tile (two units ago) must have finished reading it
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1 + half, 128);
+      }
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.c_out + half * ncol);
+      float* col = tile + q * 32 + lane;  // element (o_local, w) at tile[o_local * 128 + w]
+      for (int c0 = 0; c0 < ncol; c0 += 16) {
+        float v[16];
+        tmem_ld16(t0 + c0, v);
+        tmem_ld_wait();
+        if (c0 + 16 >= ncol) {  // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ol = c0 + j;
+          float val = v[j] + bias_s[half * ncol + ol];
+          float r;
+          if (p.mode == 0) {
+            if (p.act == PDEQX_ACT_GELU_TANH) r = gelu_f<FAST_MATH>(val);
+            else if (p.act == PDEQX_ACT_RELU) r = fmaxf(val, 0.f);
+            else r = val;
+          } else {
+            const float g = col[ol * 128];
+            if (p.act == PDEQX_ACT_GELU_TANH) r = g * gelu_grad_f<FAST_MATH>(val);
+            else if (p.act == PDEQX_ACT_RELU) r = val > 0.f ? g : 0.f;
+            else r = g;
+          }
+          if (p.round_out) r = round_tf32(r);
+          col[ol * 128] = r;
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + half, 128);
+      if (leader) {
+        tma_store_3d(&tm_y, tile, wt * 128, l, b * p.c_out + half * ncol);
+        tma_store_commit();
+        if (p.mode == 1) {
+          const int64_t un = u + stride;
+          if (un < p.units) {  // prefetch the next cotangent tile into the other buffer once its last store has drained
+            tma_store_wait_read<1>();
+            const int wtn = (int)(un % p.wt_per_row);
+            const int64_t bln = un / p.wt_per_row;
+            mbar_expect_tx(&afull[e ^ 1], L.epi_buf_bytes);
+            tma_load_3d(ebuf0 + (size_t)(e ^ 1) * L.epi_buf_bytes, &tm_aux, &afull[e ^ 1], wtn * 128, (int)(bln % p.lead),
+                        (int)(bln / p.lead) * p.c_out + half * ncol);
+          }
+        }
+      }
+      if (++a == 2) { a = 0; aph ^= 1; }
+      if (++e == 2) { e = 0; eph ^= 1; }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ==========================================================================================
+// r2c kernel: out[row, 0:n_valid] = sum_k x[row, k] T[k, :]
+// ==========================================================================================
+struct R2cParams {
+  int64_t rows, tiles;
+  int kchunks, n_valid, out_ld, stages, round_out;
+  float* out;
+};
+
+__global__ void __launch_bounds__(kThreadsR2c, 1)
+r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_tab, R2cParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // [table: kchunks x 4 KB][stages x 16 KB][barriers]
+  const uint32_t tab_bytes = (uint32_t)p.kchunks * 32 * 128;
+  uint8_t* stage0 = smem + tab_bytes;
+  uint64_t* bars = (uint64_t*)(stage0 + (size_t)p.stages * 128 * 128);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 16;
+  uint64_t* tfull = bars + 32;
+  uint64_t* tempty = bars + 34;
+  uint64_t* tabfull = bars + 36;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 38);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_tab);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4);
+    mbar_init(&tempty[1], 4);
+    mbar_init(tabfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<64>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(tabfull, tab_bytes);
+      for (int c = 0; c < p.kchunks; ++c) tma_load_2d(smem + c * 32 * 128, &tm_tab, tabfull, c * 32, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t t = first; t < p.tiles; t += stride) {
+        for (int c = 0; c < p.kchunks; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], 128 * 128);
+          tma_load_2d(stage0 + (size_t)s * 128 * 128, &tm_x, &full[s], c * 32, (int)(t * 128));
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, 32, false, false);
+      mbar_wait(tabfull, 0);
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int64_t t = first; t < p.tiles; t += stride) {
+        mbar_wait(&tempty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(a * 32);
+        for (int c = 0; c < p.kchunks; ++c) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t xa = smem_u32(stage0 + (size_t)s * 128 * 128);
+          const uint32_t tb = smem_u32(smem + c * 32 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_tf32(d, smem_desc_sw128(xa + k * 32, 0, 1024), smem_desc_sw128(tb + k * 32, 0, 1024), idesc, (c | k) != 0);
+          mma_commit(&empty[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        mma_commit(&tfull[a]);
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int a = 0;
+    uint32_t aph = 0;
+    for (int64_t t = first; t < p.tiles; t += stride) {
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+      const int64_t row = t * 128 + q * 32 + lane;
+      if (row < p.rows) {
+        float* o = p.out + row * p.out_ld;
+        if (p.round_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        }
+        if (p.n_valid == 32 && (p.out_ld & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *(float4*)(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < p.n_valid) o[j] = v[j];
+        }
+      }
+      if (++a == 2) { a = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+// ==========================================================================================
+// bypass weight gradient: gW[o,i] += sum_p g[o,p] x[i,p], gb[o] += sum_p g[o,p]   (per CTA partial, atomics)
+// ==========================================================================================
+struct WgradParams {
+  int c_out, c_in, chunks_per_b, stages;
+  int64_t units;  // batch * chunks_per_b (chunk = 32 pixels)
+  float* gw;
+  float* gb;
+};
+
+__global__ void __launch_bounds__(kThreadsR2c, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // stage = [g box: c_out x 128 B][x box: c_in x 128 B][ones: 16 x 128 B]; A = 128 rows from the g box on
+  const uint32_t g_bytes = (uint32_t)p.c_out * 128, x_bytes = (uint32_t)p.c_in * 128;
+  const uint32_t stage_bytes = g_bytes + x_bytes + 2048;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes + 16384);  // 16 KB slack: A tile of the last stage
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 16;
+  uint64_t* done = bars + 32;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 34);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  // ones rows (bias-gradient columns) and a defined value everywhere an A/B descriptor can reach
+  for (uint32_t i = threadIdx.x; i < ((uint32_t)S * stage_bytes + 16384) / 4; i += blockDim.x) {
+    const uint32_t in_stage = (i * 4) % stage_bytes;
+    ((float*)smem)[i] = (i * 4 < (uint32_t)S * stage_bytes && in_stage >= g_bytes + x_bytes) ? 1.0f : 0.0f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int N = p.c_in + 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t u = first; u < p.units; u += stride) {
+        const int b = (int)(u / p.chunks_per_b);
+        const int c = (int)(u % p.chunks_per_b);
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], g_bytes + x_bytes);
+        tma_load_2d(st, &tm_g, &full[s], c * 32, b * p.c_out);
+        tma_load_2d(st + g_bytes, &tm_x, &full[s], c * 32, b * p.c_in);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, N, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      bool acc = false;
+      for (int64_t u = first; u < p.units; u += stride) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mma_tf32(tmem_base, smem_desc_sw128(st + k * 32, 0, 1024), smem_desc_sw128(st + g_bytes + k * 32, 0, 1024), idesc,
+                   acc);
+          acc = true;
+        }
+        mma_commit(&empty[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      mma_commit(done);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    if (first < p.units) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int o = q * 32 + lane;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (o < p.c_out) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i = c0 + j;
+            if (i < p.c_in) atomicAdd(p.gw + (int64_t)o * p.c_in + i, v[j]);
+            else if (i == p.c_in && p.gb) atomicAdd(p.gb + o, v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// small prep kernel: rounded (and optionally transposed) copy of the bypass weight
+__global__ void prep_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int co, int ci, int transpose) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= co * ci) return;
+  int o = idx / ci, i = idx % ci;
+  float v = round_tf32(w[idx]);
+  if (transpose) out[i * co + o] = v;
+  else out[idx] = v;
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------
+// plan-side state and launchers
+// ------------------------------------------------------------------------------------------
+struct TcPlan {
+  bool r2c_ok = false, slab_ok = false, wgrad_ok = false;
+  int sms = 148;
+  float* tab_r2c[2] = {nullptr, nullptr};  // [32][s_D]  (n-major rows, K contiguous): forward / adjoint-of-inverse
+  float* tab_c2r[2] = {nullptr, nullptr};  // [s_D][32]  (w rows, K contiguous): inverse / adjoint-of-forward
+  float* w_prep = nullptr;                 // rounded (transposed) bypass weight
+  CUtensorMap tm_tab_r2c[2], tm_tab_c2r[2];
+  int slab_stages = 0;
+};
+
+static TcPlan* tcp(const pdeqx_spectral_plan* p) { return (TcPlan*)p->tc; }
+
+int tc_plan_init(pdeqx_spectral_plan* p) {
+  const pdeqx_spectral_desc& d = p->desc;
+  p->tc = nullptr;
+  if (d.precision != PDEQX_PREC_TF32) return PDEQX_OK;
+  int dev = 0, major = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PDEQX_OK;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (major != 10 || !tc::encode_tiled_fn()) return PDEQX_OK;
+  const int D = d.ndim, sD = d.spatial[D - 1], mD = d.modes[D - 1];
+  if (2 * mD != 32) return PDEQX_OK;  // TODO: pad the retained columns to 32 for other mode counts
+  if (sD % 32 != 0) return PDEQX_OK;
+  TcPlan* t = new TcPlan();
+  t->sms = sms;
+  // tables in tensor-core layout, rounded to tf32 (round-to-nearest: no truncation bias from the constants)
+  std::vector<float> h((size_t)32 * sD);
+  std::vector<float> src((size_t)32 * sD);
+  const float* dev_src_r2c[2] = {p->t_r2c_fwd, p->t_r2c_bwd};  // [s_D][32]
+  const float* dev_src_c2r[2] = {p->t_c2r_inv, p->t_c2r_bwd};  // [32][s_D]
+  int rc = PDEQX_OK;
+  for (int v = 0; v < 2 && rc == PDEQX_OK; ++v) {
+    if (cudaMemcpy(src.data(), dev_src_r2c[v], src.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = PDEQX_ERR_CUDA;
+    for (int n = 0; n < 32; ++n)
+      for (int k = 0; k < sD; ++k) h[(size_t)n * sD + k] = tc::host_round_tf32(src[(size_t)k * 32 + n]);
+    if (cudaMalloc((void**)&t->tab_r2c[v], h.size() * 4) != cudaSuccess ||
+        cudaMemcpy(t->tab_r2c[v], h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = PDEQX_ERR_CUDA;
+    if (cudaMemcpy(src.data(), dev_src_c2r[v], src.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = PDEQX_ERR_CUDA;
+    for (int w = 0; w < sD; ++w)
+      for (int k = 0; k < 32; ++k) h[(size_t)w * 32 + k] = tc::host_round_tf32(src[(size_t)k * sD + w]);
+    if (cudaMalloc((void**)&t->tab_c2r[v], h.size() * 4) != cudaSuccess ||
+        cudaMemcpy(t->tab_c2r[v], h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = PDEQX_ERR_CUDA;
+    if (rc == PDEQX_OK) {
+      uint64_t dims[2] = {(uint64_t)sD, 32};
+      uint64_t str[1] = {(uint64_t)sD * 4};
+      uint32_t box[2] = {32, 32};
+      rc = tc::make_tensor_map(&t->tm_tab_r2c[v], t->tab_r2c[v], 2, dims, str, box);
+    }
+    if (rc == PDEQX_OK && sD % 128 == 0) {
+      uint64_t dims[2] = {32, (uint64_t)sD};
+      uint64_t str[1] = {32 * 4};
+      uint32_t box[2] = {32, 128};
+      rc = tc::make_tensor_map(&t->tm_tab_c2r[v], t->tab_c2r[v], 2, dims, str, box);
+    }
+  }
+  const int cmax = d.c_in > d.c_out ? d.c_in : d.c_out;
+  if (rc == PDEQX_OK && cudaMalloc((void**)&t->w_prep, (size_t)cmax * cmax * 4) != cudaSuccess) rc = PDEQX_ERR_CUDA;
+  if (rc != PDEQX_OK) {
+    set_error("tcgen05 plan setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    p->tc = t;
+    tc_plan_free(p);
+    return rc;
+  }
+  t->r2c_ok = (sD <= 1024);
+  // slab: both directions (c_in <-> c_out) must fit
+  auto ch_ok = [](int ci, int co) { return ci % 8 == 0 && ci >= 8 && ci <= 128 && co % 32 == 0 && co >= 32 && co <= 128; };
+  if (sD % 128 == 0 && ch_ok(d.c_in, d.c_out) && ch_ok(d.c_out, d.c_in)) {
+    int stages = 0;
+    for (int s = 6; s >= 2; --s) {
+      tc::SlabSmem a = tc::slab_smem(sD, d.c_in, d.c_out, true, s), b = tc::slab_smem(sD, d.c_out, d.c_in, true, s);
+      if (a.total <= 227 * 1024 && b.total <= 227 * 1024) { stages = s; break; }
+    }
+    t->slab_stages = stages;
+    t->slab_ok = stages >= 2;
+  }
+  t->wgrad_ok = d.c_in % 16 == 0 && d.c_out % 8 == 0 && d.c_in <= 112 && d.c_out <= 128;
+  p->tc = t;
+  return PDEQX_OK;
+}
+
+void tc_plan_free(pdeqx_spectral_plan* p) {
+  TcPlan* t = tcp(p);
+  if (!t) return;
+  for (int v = 0; v < 2; ++v) {
+    cudaFree(t->tab_r2c[v]);
+    cudaFree(t->tab_c2r[v]);
+  }
+  cudaFree(t->w_prep);
+  delete t;
+  p->tc = nullptr;
+}
+
+int tc_stage_mask(const pdeqx_spectral_plan* p) {
+  TcPlan* t = tcp(p);
+  if (!t || !g_fast_paths.load(std::memory_order_relaxed)) return 0;
+  return (t->r2c_ok ? 1 : 0) | (t->slab_ok ? 2 : 0) | (t->wgrad_ok ? 4 : 0);
+}
+
+bool tc_r2c_available(const pdeqx_spectral_plan* p) {
+  return tcp(p) && tcp(p)->r2c_ok && g_fast_paths.load(std::memory_order_relaxed);
+}
+
+int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int64_t rows, float* out, cudaStream_t s) {
+  TcPlan* t = tcp(p);
+  const int D = p->desc.ndim, sD = p->desc.spatial[D - 1];
+  PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "tc_r2c: pointers must be 16-byte aligned");
+  CUtensorMap tm_x;
+  uint64_t dims[2] = {(uint64_t)sD, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)sD * 4};
+  uint32_t box[2] = {32, 128};
+  PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 2, dims, str, box));
+  tc::R2cParams rp{};
+  rp.rows = rows;
+  rp.tiles = ceil_div(rows, 128);
+  rp.kchunks = sD / 32;
+  rp.n_valid = 32;
+  rp.out_ld = 32;
+  rp.out = out;
+  rp.round_out = 0;
+  const uint32_t tab_bytes = (uint32_t)rp.kchunks * 4096;
+  int stages = (int)((227 * 1024 - 2048 - tab_bytes) / 16384);
+  if (stages > 10) stages = 10;
+  PDEQX_CHECK_ARG(stages >= 2, "tc_r2c: table does not leave room for the pipeline");
+  rp.stages = stages;
+  const size_t smem = tab_bytes + (size_t)stages * 16384 + 1024 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    PDEQX_CUDA(cudaFuncSetAttribute(tc::r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const int grid = (int)(rp.tiles < t->sms ? rp.tiles : t->sms);
+  tc::r2c_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_x, t->tm_tab_r2c[adjoint_table ? 1 : 0], rp);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
+bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass) {
+  (void)has_bypass;
+  return tcp(p) && tcp(p)->slab_ok && g_fast_paths.load(std::memory_order_relaxed);
+}
+
+// y[B, c_o, lead, W] = epi( c2r(z)[table_sel] + Wmat . x + bias ), Wmat = bypass_w (c_o x c_i) or its transpose
+// (bypass_transposed: bypass_w is [c_i_of_this_call... see spectral.cu) ; mode 1: y = aux * act'(.)
+int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+               bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
+               float* y, cudaStream_t s) {
+  TcPlan* t = tcp(p);
+  const pdeqx_spectral_desc& d = p->desc;
+  const int D = d.ndim, sD = d.spatial[D - 1];
+  const int64_t lead = p->lead;
+  PDEQX_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!x || ((uintptr_t)x & 15) == 0),
+                  "tc_slab: pointers must be 16-byte aligned");
+  const bool bypass = bypass_w != nullptr;
+  CUtensorMap tm_x, tm_z, tm_w;
+  {
+    uint64_t dims[3] = {32, (uint64_t)lead, (uint64_t)d.batch * c_out};
+    uint64_t str[2] = {32 * 4, (uint64_t)lead * 32 * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)c_out};
+    PDEQX_TRY(tc::make_tensor_map(&tm_z, z, 3, dims, str, box));
+  }
+  if (bypass) {
+    uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * c_in};
+    uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)c_in};
+    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128_ATOM32));
+    // rounded copy of the weight as [c_out rows][c_in] (K contiguous)
+    const int n = c_in * c_out;
+    // bypass_w is stored [rows_w][cols_w]; not transposed: [c_out][c_in]; transposed: stored [c_in][c_out]
+    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(bypass_w, t->w_prep, bypass_transposed ? c_in : c_out,
+                                                          bypass_transposed ? c_out : c_in, bypass_transposed ? 1 : 0);
+    PDEQX_LAUNCHED();
+    uint64_t wd[2] = {(uint64_t)c_in, (uint64_t)c_out};
+    uint64_t ws[1] = {(uint64_t)c_in * 4};
+    uint32_t wb[2] = {32, (uint32_t)c_out};
+    PDEQX_TRY(tc::make_tensor_map(&tm_w, t->w_prep, 2, wd, ws, wb));
+  } else {
+    tm_x = tm_z;
+    tm_w = tm_z;
+  }
+  CUtensorMap tm_y, tm_aux;
+  {
+    uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * c_out};
+    uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
+    uint32_t box[3] = {128, 1, (uint32_t)(c_out / 2)};
+    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box, tc::TM_NONE));
+    if (mode == 1) {
+      PDEQX_CHECK_ARG(aux && ((uintptr_t)aux & 15) == 0, "tc_slab: aux must be a 16-byte aligned device pointer");
+      PDEQX_TRY(tc::make_tensor_map(&tm_aux, aux, 3, dims, str, box, tc::TM_NONE));
+    } else {
+      tm_aux = tm_y;
+    }
+  }
+  tc::SlabParams sp{};
+  sp.lead = (int)lead;
+  sp.W = sD;
+  sp.wt_per_row = sD / 128;
+  sp.c_in = c_in;
+  sp.c_out = c_out;
+  sp.has_bypass = bypass ? 1 : 0;
+  sp.mode = mode;
+  sp.act = act;
+  sp.round_out = 0;
+  sp.stages = t->slab_stages;
+  sp.units = (int64_t)d.batch * lead * sp.wt_per_row;
+  sp.bias = bypass_b;
+  sp.aux = aux;
+  sp.y = y;
+  tc::SlabSmem L = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages);
+  static bool attr = false;
+  if (!attr) {
+    PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  int grid = (int)(sp.units < t->sms ? sp.units : t->sms);
+  grid = grid / sp.wt_per_row * sp.wt_per_row;  // every CTA keeps one w-tile of the table (units stride by the grid size)
+  PDEQX_CHECK_ARG(grid >= sp.wt_per_row, "tc_slab: grid smaller than the number of w-tiles");
+  tc::slab_kernel<true><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, t->tm_tab_c2r[table_sel], tm_w, tm_y, tm_aux, sp, L);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
+int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+            bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s) {
+  const pdeqx_spectral_desc& d = p->desc;
+  const int c_in = bypass_transposed ? d.c_out : d.c_in, c_out = bypass_transposed ? d.c_in : d.c_out;
+  return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s);
+}
+
+bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix) {
+  return tcp(p) && tcp(p)->wgrad_ok && n_pix % 32 == 0 && g_fast_paths.load(std::memory_order_relaxed);
+}
+
+// gw [c_out, c_in] and gb [c_out] must be zeroed by the caller
+int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb, cudaStream_t s) {
+  TcPlan* t = tcp(p);
+  const pdeqx_spectral_desc& d = p->desc;
+  CUtensorMap tm_g, tm_x;
+  {
+    uint64_t dims[2] = {(uint64_t)n_pix, (uint64_t)d.batch * d.c_out};
+    uint64_t str[1] = {(uint64_t)n_pix * 4};
+    uint32_t box[2] = {32, (uint32_t)d.c_out};
+    PDEQX_TRY(tc::make_tensor_map(&tm_g, g, 2, dims, str, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)n_pix, (uint64_t)d.batch * d.c_in};
+    uint64_t str[1] = {(uint64_t)n_pix * 4};
+    uint32_t box[2] = {32, (uint32_t)d.c_in};
+    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 2, dims, str, box));
+  }
+  tc::WgradParams wp{};
+  wp.c_out = d.c_out;
+  wp.c_in = d.c_in;
+  wp.chunks_per_b = (int)(n_pix / 32);
+  wp.units = (int64_t)d.batch * wp.chunks_per_b;
+  wp.gw = gw;
+  wp.gb = gb;
+  const uint32_t stage_bytes = (uint32_t)(d.c_out + d.c_in) * 128 + 2048;
+  int stages = (int)((227 * 1024 - 16384 - 2048) / stage_bytes);
+  if (stages > 12) stages = 12;
+  wp.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 16384 + 1024 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    PDEQX_CUDA(cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  const int grid = (int)(wp.units < t->sms ? wp.units : t->sms);
+  tc::wgrad_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_g, tm_x, wp);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
 }  // namespace pdeqx

@@ -1,0 +1,121 @@
+"""TF32 mode: the tcgen05 kernels (first-stage r2c DFT, last-stage slab kernel, bypass weight gradient)
+against the float64 oracle, tolerance rel-L2 <= 2e-3 (BASELINE.json north_star, "stated TF32 mode"),
+and against the library's own fp32 path."""
+import numpy as np
+import pytest
+import torch
+
+import pdequinox_b200 as pdeqx
+from pdequinox_b200 import _lib
+from pdequinox_b200.conv._spectral_conv import get_plan
+from pdequinox_b200.train import ParameterArena
+from oracle import conv as oconv, nn as onn, spectral as ospec
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+CASES = [
+    # (D, B, ci, co, spatial, modes)
+    (2, 2, 32, 32, (16, 128), (4, 16)),
+    (2, 1, 64, 64, (8, 256), (4, 16)),
+    (2, 3, 32, 64, (12, 128), (3, 16)),
+    (2, 2, 64, 32, (6, 256), (3, 16)),
+    (1, 4, 32, 32, (128,), (16,)),
+    (3, 1, 32, 32, (4, 6, 128), (2, 3, 16)),
+    (2, 2, 64, 64, (64, 256), (16, 16)),
+]
+
+
+@pytest.mark.parametrize("D,B,ci,co,spatial,modes", CASES)
+@pytest.mark.parametrize("act", ["gelu", "identity", "relu"])
+def test_tf32_spectral_block(cuda, D, B, ci, co, spatial, modes, act):
+    pdeqx.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(11)
+        x = rng.standard_normal((B, ci) + spatial)
+        gy = rng.standard_normal((B, co) + spatial)
+        wr = rng.standard_normal((2 ** (D - 1), co, ci) + modes) / (ci * co)
+        wi = rng.standard_normal((2 ** (D - 1), co, ci) + modes) / (ci * co)
+        bw = rng.uniform(-1, 1, (co, ci) + (1,) * D) / np.sqrt(ci)
+        bb = rng.uniform(-1, 1, (co,) + (1,) * D)
+        f, fg = onn.ACTIVATIONS[act]
+        pre = ospec.spectral_conv_nd(x, wr, wi, modes) + oconv.pointwise_conv(x, bw, bb)
+        ref_y = f(pre)
+        gpre = gy * fg(pre)
+        gx_s, gwr, gwi, _ = ospec.spectral_conv_vjp(x, wr, wi, modes, gpre)
+        gx_b, gbw, gbb = oconv.pointwise_conv_vjp(x, bw, gpre)
+
+        plan = get_plan(D, B, ci, co, spatial, modes)
+        mask = _lib.lib().pdeqx_spectral_plan_tcgen05_stages(plan.handle)
+        assert mask == 7, f"tcgen05 stages not enabled for this shape (mask {mask})"
+
+        blk = pdeqx.ClassicSpectralBlock(D, ci, co, activation=getattr(pdeqx.nn, act), num_modes=modes, key=0)
+        blk.spectral_conv.weights_real, blk.spectral_conv.weights_imag = dev(wr), dev(wi)
+        blk.by_pass_conv.weight, blk.by_pass_conv.bias = dev(bw), dev(bb)
+        arena = ParameterArena(blk)
+        tape = pdeqx._module.Tape()
+        y = blk._fwd(dev(x), tape)
+        torch.cuda.synchronize()
+        assert rel_l2(host(y), ref_y) <= TOL
+        if act == "relu":
+            # relu' is discontinuous: where |pre| is below the TF32 error the mask may legitimately differ from the
+            # float64 oracle's; evaluate the oracle's reverse pass with the mask of the forward pass under test
+            gpre = gy * (host(y) > 0)
+            gx_s, gwr, gwi, _ = ospec.spectral_conv_vjp(x, wr, wi, modes, gpre)
+            gx_b, gbw, gbb = oconv.pointwise_conv_vjp(x, bw, gpre)
+        gx = blk._bwd(dev(gy), tape, True)
+        torch.cuda.synchronize()
+        g = {k: host(v) for k, v in arena.named_grads().items()}
+        assert rel_l2(host(gx), gx_s + gx_b) <= TOL
+        assert rel_l2(g["spectral_conv.weights_real"], gwr) <= TOL
+        assert rel_l2(g["spectral_conv.weights_imag"], gwi) <= TOL
+        assert rel_l2(g["by_pass_conv.weight"], gbw) <= TOL
+        assert rel_l2(g["by_pass_conv.bias"], gbb) <= TOL
+    finally:
+        pdeqx.set_precision("fp32")
+
+
+def test_tf32_plain_spectral_conv(cuda):
+    pdeqx.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(12)
+        x = rng.standard_normal((2, 32, 16, 128))
+        wr = rng.standard_normal((2, 32, 32, 4, 16)) / 1024
+        wi = rng.standard_normal((2, 32, 32, 4, 16)) / 1024
+        conv = pdeqx.SpectralConv(2, 32, 32, (4, 16), key=0)
+        conv.weights_real, conv.weights_imag = dev(wr), dev(wi)
+        y = host(pdeqx.vmap(conv)(dev(x)))
+        assert rel_l2(y, ospec.spectral_conv_nd(x, wr, wi, (4, 16))) <= TOL
+    finally:
+        pdeqx.set_precision("fp32")
+
+
+def test_tf32_fno_train_step(cuda):
+    """Whole ClassicFNO train step in TF32 mode vs the oracle (2 blocks, hidden 32, 64x128 grid)."""
+    from pdequinox_b200.train import TrainStep
+    pdeqx.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(13)
+        model = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=32, num_modes=16, num_blocks=2, key=5)
+        step = TrainStep(model)
+        p = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in step.arena.named_params().items()}
+        x = rng.standard_normal((2, 1, 64, 128))
+        y = rng.standard_normal((2, 1, 64, 128))
+        loss_ref, g_ref = onn.fno_loss_and_grad(p, x, y, (16, 16), 2)
+        loss = step.loss_and_grad(x, y).item()
+        assert abs(loss - loss_ref) <= 5e-3 * abs(loss_ref)
+        g = {k: v.detach().cpu().numpy() for k, v in step.arena.named_grads().items()}
+        for k in g_ref:
+            assert rel_l2(g[k], g_ref[k]) <= 5e-3, k  # chained TF32 stages through 2 blocks and their reverse pass
+    finally:
+        pdeqx.set_precision("fp32")
