@@ -90,19 +90,23 @@ constexpr int kTmemCols = 256;
 // ------------------------------------------------------------------------------------------
 template <bool FAST>
 __device__ __forceinline__ float gelu_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  float t = FAST ? tanh_fast(u) : tanh_accurate(u);
-  return 0.5f * x * (1.0f + t);
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, k01, k0);
+  const float t = FAST ? tanh_fast(u) : tanh_accurate(u);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 template <bool FAST>
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float x2 = x * x;
-  float u = k0 * (x + k1 * x * x2);
-  float t = FAST ? tanh_fast(u) : tanh_accurate(u);
-  float du = k0 * (1.0f + 3.0f * k1 * x2);
-  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, k01, k0);
+  const float t = FAST ? tanh_fast(u) : tanh_accurate(u);
+  const float du = fmaf(x2, 3.0f * k01, k0);
+  const float hx = 0.5f * x;
+  // 0.5 (1 + t) + 0.5 x (1 - t^2) du
+  return fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }
 
 // ==========================================================================================
@@ -147,7 +151,7 @@ static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages) {
   return s;
 }
 
-template <bool FAST_MATH>
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(kThreadsSlab, 1)
 slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z,
             const __grid_constant__ CUtensorMap tm_tab, const __grid_constant__ CUtensorMap tm_w,
@@ -216,7 +220,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int64_t bl = u / p.wt_per_row;
         const int l = (int)(bl % p.lead);
         const int b = (int)(bl / p.lead);
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_backoff(&empty[s], ph ^ 1);
         uint8_t* st = smem + L.stage_off + (size_t)s * L.stage_bytes;
         mbar_expect_tx(&full[s], (p.has_bypass ? 4 * L.x_box_bytes : 0) + (uint32_t)p.c_out * 128);
         if (p.has_bypass)
@@ -235,8 +239,8 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int64_t u = first; u < p.units; u += stride) {
-        mbar_wait(&tempty[a], aph ^ 1);
-        mbar_wait(&full[s], ph);
+        mbar_wait_backoff(&tempty[a], aph ^ 1);
+        mbar_wait_backoff(&full[s], ph);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(a * p.c_out);
         const uint32_t st = smem_u32(smem + L.stage_off + (size_t)s * L.stage_bytes);
@@ -272,7 +276,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     uint64_t* afull = auxfull + half * 2;
     int a = 0, e = 0;
     uint32_t aph = 0, eph = 0;
-    if (p.mode == 1 && leader && first < p.units) {
+    if (MODE == 1 && leader && first < p.units) {
       const int wt = (int)(first % p.wt_per_row);
       const int64_t bl = first / p.wt_per_row;
       mbar_expect_tx(&afull[0], L.epi_buf_bytes);
@@ -286,7 +290,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       float* tile = (float*)(ebuf0 + (size_t)e * L.epi_buf_bytes);
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
-      if (p.mode == 1) {
+      if (MODE == 1) {
         mbar_wait(&afull[e], eph);
       } else {
         // the store that last used this tile (two units ago) must have finished reading it
@@ -294,7 +298,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         named_bar_sync(1 + half, 128);
       }
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.c_out + half * ncol);
-      float* col = tile + q * 32 + lane;  // element (o_local, w) at tile[o_local * 128 + w]
+      const uint32_t col = smem_u32(tile) + (uint32_t)(q * 32 + lane) * 4;  // element (o_local, w) at tile[o_local * 128 + w]
       for (int c0 = 0; c0 < ncol; c0 += 16) {
         float v[16];
         tmem_ld16(t0 + c0, v);
@@ -304,23 +308,25 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
+        float g[16];
+        if (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = ld_shared_f32(col + (uint32_t)(c0 + j) * 512);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int ol = c0 + j;
-          float val = v[j] + bias_s[half * ncol + ol];
+          const float val = v[j] + bias_s[half * ncol + c0 + j];
           float r;
-          if (p.mode == 0) {
-            if (p.act == PDEQX_ACT_GELU_TANH) r = gelu_f<FAST_MATH>(val);
-            else if (p.act == PDEQX_ACT_RELU) r = fmaxf(val, 0.f);
+          if (MODE == 0) {
+            if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_f<true>(val);
+            else if (ACT == PDEQX_ACT_RELU) r = fmaxf(val, 0.f);
             else r = val;
           } else {
-            const float g = col[ol * 128];
-            if (p.act == PDEQX_ACT_GELU_TANH) r = g * gelu_grad_f<FAST_MATH>(val);
-            else if (p.act == PDEQX_ACT_RELU) r = val > 0.f ? g : 0.f;
-            else r = g;
+            if (ACT == PDEQX_ACT_GELU_TANH) r = g[j] * gelu_grad_f<true>(val);
+            else if (ACT == PDEQX_ACT_RELU) r = val > 0.f ? g[j] : 0.f;
+            else r = g[j];
           }
-          if (p.round_out) r = round_tf32(r);
-          col[ol * 128] = r;
+          st_shared_f32(col + (uint32_t)(c0 + j) * 512, r);
         }
       }
       fence_proxy_async();
@@ -328,7 +334,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (leader) {
         tma_store_3d(&tm_y, tile, wt * 128, l, b * p.c_out + half * ncol);
         tma_store_commit();
-        if (p.mode == 1) {
+        if (MODE == 1) {
           const int64_t un = u + stride;
           if (un < p.units) {  // prefetch the next cotangent tile into the other buffer once its last store has drained
             tma_store_wait_read<1>();
@@ -409,7 +415,7 @@ r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       uint32_t ph = 0;
       for (int64_t t = first; t < p.tiles; t += stride) {
         for (int c = 0; c < p.kchunks; ++c) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_backoff(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], 128 * 128);
           tma_load_2d(stage0 + (size_t)s * 128 * 128, &tm_x, &full[s], c * 32, (int)(t * 128));
           if (++s == S) { s = 0; ph ^= 1; }
@@ -423,11 +429,11 @@ r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int64_t t = first; t < p.tiles; t += stride) {
-        mbar_wait(&tempty[a], aph ^ 1);
+        mbar_wait_backoff(&tempty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(a * 32);
         for (int c = 0; c < p.kchunks; ++c) {
-          mbar_wait(&full[s], ph);
+          mbar_wait_backoff(&full[s], ph);
           tc_fence_after();
           const uint32_t xa = smem_u32(stage0 + (size_t)s * 128 * 128);
           const uint32_t tb = smem_u32(smem + c * 32 * 128);
@@ -538,7 +544,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       for (int64_t u = first; u < p.units; u += stride) {
         const int b = (int)(u / p.chunks_per_b);
         const int c = (int)(u % p.chunks_per_b);
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_backoff(&empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_expect_tx(&full[s], g_bytes + x_bytes);
         tma_load_2d(st, &tm_g, &full[s], c * 32, b * p.c_out);
@@ -553,7 +559,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       uint32_t ph = 0;
       bool acc = false;
       for (int64_t u = first; u < p.units; u += stride) {
-        mbar_wait(&full[s], ph);
+        mbar_wait_backoff(&full[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
 #pragma unroll
@@ -822,15 +828,26 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.aux = aux;
   sp.y = y;
   tc::SlabSmem L = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages);
-  static bool attr = false;
-  if (!attr) {
-    PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
   int grid = (int)(sp.units < t->sms ? sp.units : t->sms);
   grid = grid / sp.wt_per_row * sp.wt_per_row;  // every CTA keeps one w-tile of the table (units stride by the grid size)
   PDEQX_CHECK_ARG(grid >= sp.wt_per_row, "tc_slab: grid smaller than the number of w-tiles");
-  tc::slab_kernel<true><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, t->tm_tab_c2r[table_sel], tm_w, tm_y, tm_aux, sp, L);
+  PDEQX_CHECK_ARG(mode == 0 || act != PDEQX_ACT_IDENTITY, "tc_slab: mode 1 needs an activation");
+  const CUtensorMap& tab = t->tm_tab_c2r[table_sel];
+#define PDEQX_SLAB_LAUNCH(M, A)                                                                                        \
+  do {                                                                                                                 \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    tc::slab_kernel<M, A><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L);          \
+  } while (0)
+  if (mode == 0 && act == PDEQX_ACT_IDENTITY) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_IDENTITY);
+  else if (mode == 0 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_RELU);
+  else if (mode == 0) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_GELU_TANH);
+  else if (act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_RELU);
+  else PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_GELU_TANH);
+#undef PDEQX_SLAB_LAUNCH
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
