@@ -219,52 +219,110 @@ pw_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ x, float
   }
 }
 
-// Small side (<= kSmallC channels on one of the two sides): one warp per channel of the large side.
-//   big = gy (cout large, cin small)  if big_is_gy, else big = x.
+// Small side (<= kSmallC channels on one of the two sides; the lifting 1 -> C and projection C -> 1 of every
+// architecture): persistent streaming kernel. A block walks (batch, pixel-chunk) units; the small side's chunk is
+// staged in shared memory, each warp owns a strided set of channels of the big side and keeps their partial sums in
+// registers across ALL its units (float4 loads, 4 in flight per lane), one atomic flush per block at the end.
+constexpr int WS_CHUNK = 1024;     // pixels per unit
+constexpr int WS_MAXCH = 16;       // big-side channels per warp (8 warps -> up to 128 channels)
 __global__ void __launch_bounds__(256)
 pw_wgrad_small_kernel(const float* __restrict__ gy, const float* __restrict__ x, float* __restrict__ gw,
-                      float* __restrict__ gb, int cin, int cout, int64_t n, int64_t chunk) {
-  const int b = blockIdx.y;
-  const int64_t n0 = (int64_t)blockIdx.x * chunk;
-  const int64_t n1 = (n0 + chunk < n) ? n0 + chunk : n;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+                      float* __restrict__ gb, int batch, int cin, int cout, int64_t n) {
+  extern __shared__ float sm_small[];  // [nsmall][WS_CHUNK]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool big_is_gy = cout >= cin;
   const int nbig = big_is_gy ? cout : cin, nsmall = big_is_gy ? cin : cout;
-  const float* big = big_is_gy ? gy + (int64_t)b * cout * n : x + (int64_t)b * cin * n;
-  const float* small = big_is_gy ? x + (int64_t)b * cin * n : gy + (int64_t)b * cout * n;
-  for (int c = warp; c < nbig; c += nwarps) {
-    float acc[kSmallC];
-    float bs = 0.f;
+  const int64_t chunks = (n + WS_CHUNK - 1) / WS_CHUNK;
+  const int64_t units = (int64_t)batch * chunks;
+  float acc[WS_MAXCH][kSmallC];
+  float bsum[WS_MAXCH];
+  float ssum[kSmallC];  // bias gradient over the small side (only when the small side is gy)
 #pragma unroll
-    for (int j = 0; j < kSmallC; ++j) acc[j] = 0.f;
-    for (int64_t q = n0 + lane; q < n1; q += 32) {
-      float v = __ldg(big + (int64_t)c * n + q);
-      bs += v;
+  for (int c = 0; c < WS_MAXCH; ++c) {
+    bsum[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSmallC; ++j) acc[c][j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < kSmallC; ++j) ssum[j] = 0.f;
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int b = (int)(u / chunks);
+    const int64_t p0 = (u % chunks) * WS_CHUNK;
+    const int len = (int)((n - p0) < WS_CHUNK ? (n - p0) : WS_CHUNK);
+    const float* bigp = (big_is_gy ? gy + (int64_t)b * cout * n : x + (int64_t)b * cin * n) + p0;
+    const float* smallp = (big_is_gy ? x + (int64_t)b * cin * n : gy + (int64_t)b * cout * n) + p0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nsmall * WS_CHUNK; idx += blockDim.x) {
+      const int j = idx / WS_CHUNK, q = idx % WS_CHUNK;
+      sm_small[idx] = q < len ? __ldg(smallp + (int64_t)j * n + q) : 0.f;
+    }
+    __syncthreads();
+    const bool vec = (len == WS_CHUNK) && ((n & 3) == 0) && (((uintptr_t)bigp & 15) == 0);
+#pragma unroll
+    for (int ci = 0; ci < WS_MAXCH; ++ci) {
+      const int c = warp + ci * 8;
+      if (c >= nbig) break;
+      const float* row = bigp + (int64_t)c * n;
+      if (vec) {
+        float4 v[WS_CHUNK / 128];
+#pragma unroll
+        for (int t = 0; t < WS_CHUNK / 128; ++t) v[t] = __ldg((const float4*)row + lane + 32 * t);
+#pragma unroll
+        for (int t = 0; t < WS_CHUNK / 128; ++t) {
+          bsum[ci] += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+#pragma unroll
+          for (int j = 0; j < kSmallC; ++j) {
+            if (j < nsmall) {
+              const float4 sv = *(const float4*)(sm_small + j * WS_CHUNK + (lane + 32 * t) * 4);
+              acc[ci][j] = fmaf(v[t].x, sv.x, fmaf(v[t].y, sv.y, fmaf(v[t].z, sv.z, fmaf(v[t].w, sv.w, acc[ci][j]))));
+            }
+          }
+        }
+      } else {
+        for (int q = lane; q < len; q += 32) {
+          const float v = __ldg(row + q);
+          bsum[ci] += v;
+#pragma unroll
+          for (int j = 0; j < kSmallC; ++j)
+            if (j < nsmall) acc[ci][j] = fmaf(v, sm_small[j * WS_CHUNK + q], acc[ci][j]);
+        }
+      }
+    }
+    if (gb && !big_is_gy && warp == 0) {
 #pragma unroll
       for (int j = 0; j < kSmallC; ++j)
-        if (j < nsmall) acc[j] = fmaf(v, __ldg(small + (int64_t)j * n + q), acc[j]);
+        if (j < nsmall)
+          for (int q = lane; q < len; q += 32) ssum[j] += sm_small[j * WS_CHUNK + q];
     }
+  }
+  // flush
+#pragma unroll
+  for (int ci = 0; ci < WS_MAXCH; ++ci) {
+    const int c = warp + ci * 8;
+    if (c >= nbig) break;
 #pragma unroll
     for (int j = 0; j < kSmallC; ++j) {
       if (j >= nsmall) break;
-      float v = acc[j];
+      float v = acc[ci][j];
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       if (lane == 0) {
-        int o = big_is_gy ? c : j, i = big_is_gy ? j : c;
+        const int o = big_is_gy ? c : j, i = big_is_gy ? j : c;
         atomicAdd(gw + (int64_t)o * cin + i, v);
       }
     }
     if (gb && big_is_gy) {
-      for (int off = 16; off > 0; off >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, off);
-      if (lane == 0) atomicAdd(gb + c, bs);
+      float v = bsum[ci];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) atomicAdd(gb + c, v);
     }
   }
-  if (gb && !big_is_gy) {  // bias grad over the small (gy) side
-    for (int o = warp; o < cout; o += nwarps) {
-      float bs = 0.f;
-      for (int64_t q = n0 + lane; q < n1; q += 32) bs += __ldg(small + (int64_t)o * n + q);
-      for (int off = 16; off > 0; off >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, off);
-      if (lane == 0) atomicAdd(gb + o, bs);
+  if (gb && !big_is_gy && warp == 0) {
+#pragma unroll
+    for (int j = 0; j < kSmallC; ++j) {
+      if (j >= nsmall) break;
+      float v = ssum[j];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) atomicAdd(gb + j, v);
     }
   }
 }
@@ -292,11 +350,12 @@ extern "C" int pdeqx_pointwise_bwd(int32_t batch, int32_t c_in, int32_t c_out, i
   PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)c_in * c_out, s));
   if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)c_out, s));
   if (batch == 0 || n_pixels == 0) return PDEQX_OK;
-  if (c_in <= kSmallC || c_out <= kSmallC) {
-    const int64_t chunk = 8192;
-    PDEQX_CHECK_ARG(batch <= 65535, "pointwise_bwd: batch exceeds grid.y");
-    dim3 grid((unsigned)ceil_div(n_pixels, chunk), batch);
-    pw_wgrad_small_kernel<<<grid, 256, 0, s>>>(gy, x, gw, gb, c_in, c_out, n_pixels, chunk);
+  const int nbig = c_out >= c_in ? c_out : c_in, nsmall = c_out >= c_in ? c_in : c_out;
+  if (nsmall <= kSmallC && nbig <= 8 * WS_MAXCH) {
+    const int64_t units = (int64_t)batch * ceil_div(n_pixels, WS_CHUNK);
+    const int grid = (int)(units < 148 ? units : 148);
+    const size_t smem = (size_t)nsmall * WS_CHUNK * sizeof(float);
+    pw_wgrad_small_kernel<<<grid, 256, smem, s>>>(gy, x, gw, gb, batch, c_in, c_out, n_pixels);
     PDEQX_LAUNCHED();
     return PDEQX_OK;
   }
