@@ -307,3 +307,77 @@ def classic_resnet_loss_and_grad(p, x, y, num_blocks, boundary_mode, activation=
     _, gw, gb = oconv.pointwise_conv_vjp(x, p["lifting.weight"], g, "lifting.bias" in p)
     grads["lifting.weight"], grads["lifting.bias"] = gw, gb
     return loss, {k: grads[k] for k in p if grads.get(k) is not None}
+
+
+# ---------------------------------------------------------------------------
+# Generic evaluators over a {path: array} parameter dict (used with the golden fixtures)
+# ---------------------------------------------------------------------------
+
+def _norm(h, p, prefix, D, groups=1):
+    if prefix + "weight" in p:
+        return group_norm(h, p[prefix + "weight"], p[prefix + "bias"], groups, D)
+    return h
+
+
+def res_block_any(x, p, prefix, boundary_mode, activation, D):
+    """ClassicResBlock with optional norms and optional 1x1 bypass (_classic_res_block.py:112-121)."""
+    act = ACTIVATIONS[activation][0]
+    h = oconv.physics_conv(x, p[prefix + "conv_1.weight"], p.get(prefix + "conv_1.bias"), boundary_mode=boundary_mode)
+    h = act(_norm(h, p, prefix + "norm_1.", D))
+    h = oconv.physics_conv(h, p[prefix + "conv_2.weight"], p.get(prefix + "conv_2.bias"), boundary_mode=boundary_mode)
+    h = _norm(h, p, prefix + "norm_2.", D)
+    skip = x
+    if prefix + "bypass_conv.weight" in p:
+        skip = oconv.pointwise_conv(x, p[prefix + "bypass_conv.weight"], p.get(prefix + "bypass_conv.bias"))
+        skip = _norm(skip, p, prefix + "bypass_norm.", D)
+    return act(h + skip)
+
+
+def dilated_block_any(x, p, prefix, boundary_mode, activation, D, rates=(1, 2, 4, 8, 4, 2, 1)):
+    """DilatedResBlock (_dilated_res_block.py:141-151), in == out."""
+    act = ACTIVATIONS[activation][0]
+    h = x
+    for j, d in enumerate(rates):
+        h = _norm(h, p, prefix + f"norm_layers.{j}.", D)
+        h = act(oconv.physics_conv(h, p[prefix + f"conv_layers.{j}.weight"], p.get(prefix + f"conv_layers.{j}.bias"),
+                                   boundary_mode=boundary_mode, dilation=d))
+    return h + x
+
+
+def double_conv_block(x, p, prefix, boundary_mode, activation, D):
+    """ClassicDoubleConvBlock (_classic_double_conv_block.py:87-90)."""
+    act = ACTIVATIONS[activation][0]
+    h = x
+    for c in ("1", "2"):
+        h = oconv.physics_conv(h, p[prefix + f"conv_{c}.weight"], p.get(prefix + f"conv_{c}.bias"), boundary_mode=boundary_mode)
+        h = act(_norm(h, p, prefix + f"norm_{c}.", D))
+    return h
+
+
+def sequential_forward(p, x, block_fn, num_blocks):
+    """Sequential.__call__ (_sequential.py:111-116) with `block_fn(h, prefix)` per block."""
+    h = oconv.pointwise_conv(x, p["lifting.weight"], p.get("lifting.bias"))
+    for i in range(num_blocks):
+        h = block_fn(h, f"blocks.{i}.")
+    return oconv.pointwise_conv(h, p["projection.weight"], p.get("projection.bias"))
+
+
+def unet_forward(p, x, boundary_mode, num_levels, activation="relu"):
+    """Hierarchical.__call__ (_hierarchical.py:251-284) with ClassicUNet's factories (_classic_u_net.py:62-83):
+    double-conv lifting, stride-2 conv down (NOT pooling), double-conv arcs, transposed-conv up, concat((skip, x))."""
+    D = p["projection.weight"].ndim - 2
+    lead = x.ndim - D - 1
+    h = double_conv_block(x, p, "lifting.", boundary_mode, activation, D)
+    skips = []
+    for i in range(num_levels):
+        skips.append(h)
+        h = oconv.physics_conv(h, p[f"down_sampling_blocks.{i}.weight"], p.get(f"down_sampling_blocks.{i}.bias"),
+                               boundary_mode=boundary_mode, stride=2)
+        h = double_conv_block(h, p, f"left_arc_blocks.{i}.0.", boundary_mode, activation, D)
+    for i in reversed(range(num_levels)):
+        skip = skips.pop()
+        h = oconv.physics_conv_transpose(h, p[f"up_sampling_blocks.{i}.weight"], p.get(f"up_sampling_blocks.{i}.bias"),
+                                         boundary_mode=boundary_mode, stride=2, output_padding=1)
+        h = np.concatenate((skip, h), axis=lead)
+        h = double_conv_block(h, p, f"right_arc_blocks.{i}.0.", boundary_mode, activation, D)
+    return oconv.pointwise_conv(h, p["projection.weight"], p.get("projection.bias"))

@@ -55,6 +55,17 @@ class ParameterArena:
                 self.params[o:o + n].view(shape).copy_(a)
 
 
+def allreduce_gradients_(grads, loss, world, group=None):
+    """The one exchange step of the data-parallel path: SUM the flat gradient arena (and the scalar loss) over
+    the ranks. The 1/world scaling of the gradients is left to the Adam kernel (grad_scale); the loss is
+    averaged here. Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    if world > 1:
+        torch.distributed.all_reduce(grads, group=group)
+        torch.distributed.all_reduce(loss, group=group)
+        loss.div_(world)
+    return grads, loss
+
+
 class TrainStep:
     """One Adam step on mse(vmap(model)(x), y); `world` = a torch.distributed process group (or None)."""
 
@@ -91,10 +102,8 @@ class TrainStep:
 
     def apply_gradients(self):
         """All-reduce (sum) the gradient arena over the data-parallel group, then Adam with grad/world."""
-        if self.distributed and self.world > 1:
-            torch.distributed.all_reduce(self.arena.grads, group=self.pg)
-            torch.distributed.all_reduce(self.loss, group=self.pg)
-            self.loss.div_(self.world)
+        if self.distributed:
+            allreduce_gradients_(self.arena.grads, self.loss, self.world, self.pg)
         self.count += 1
         _lib.check(_lib.lib().pdeqx_adam_step(self.arena.size, _lib.ptr(self.arena.params), _lib.ptr(self.arena.grads),
                                               _lib.ptr(self.mu), _lib.ptr(self.nu), self.lr, self.b1, self.b2,
