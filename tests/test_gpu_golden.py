@@ -21,7 +21,8 @@ def build(case, p):
         kw["num_modes"] = tuple(kw["num_modes"])
     if kind == "SpectralConvRaw":
         wr = p["weights_real"]
-        return pdeqx.SpectralConv(wr.ndim - 3, wr.shape[2], wr.shape[1], kw["num_modes"], key=0)
+        # overwritten weights carry the call-time shape (G, o, i, *modes) == an allocation with in=o, out=i
+        return pdeqx.SpectralConv(wr.ndim - 3, wr.shape[1], wr.shape[2], kw["num_modes"], key=0)
     cls = {"SpectralConv": pdeqx.SpectralConv, "PhysicsConv": pdeqx.PhysicsConv, "PointwiseLinearConv": pdeqx.PointwiseLinearConv,
            "ClassicSpectralBlock": pdeqx.blocks.ClassicSpectralBlock, "ClassicResBlock": pdeqx.blocks.ClassicResBlock,
            "DilatedResBlock": pdeqx.blocks.DilatedResBlock, "ClassicFNO": pdeqx.arch.ClassicFNO,
