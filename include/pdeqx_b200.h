@@ -175,6 +175,12 @@ typedef struct {
   int32_t boundary; /* enum pdeqx_boundary */
 } pdeqx_conv_desc;
 
+/* arithmetic of the convolution kernels for the calling process: PDEQX_PREC_FP32 (default; CUDA-core fp32) or
+ * PDEQX_PREC_TF32 (tcgen05 implicit GEMM for the shapes that qualify: 2-D, k = 3, stride 1, W = 128, C = 32 / 64) */
+void pdeqx_set_conv_precision(int32_t precision);
+/* which passes of this convolution run on tcgen05 under the current settings
+ * (bit 0: forward, bit 1: data gradient, bit 2: filter gradient); 0 = CUDA-core fp32 path */
+int pdeqx_conv_tcgen05_passes(const pdeqx_conv_desc* d);
 /* output spatial size per axis: floor((s + lo + hi - d(k-1) - 1)/stride) + 1 */
 int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]);
 /* y = act(corr(pad(x), w) + b + residual); w [c_out, c_in/groups, *k]; b [c_out]; b, residual may be NULL */

@@ -57,6 +57,8 @@ PROTOTYPES = {
                                            C.c_size_t, _P]),
     "pdeqx_pointwise_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_pointwise_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "pdeqx_set_conv_precision": (None, [_I32]),
+    "pdeqx_conv_tcgen05_passes": (C.c_int, [C.POINTER(ConvDesc)]),
     "pdeqx_conv_out_spatial": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
     "pdeqx_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),

@@ -25,6 +25,7 @@ def set_precision(mode: str):
     if mode not in _PRECISION:
         raise ValueError(f"precision must be one of {list(_PRECISION)}, got {mode}")
     _precision = mode
+    _lib.lib().pdeqx_set_conv_precision(_PRECISION[mode])
 
 
 def get_precision() -> str:

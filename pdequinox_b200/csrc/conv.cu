@@ -309,6 +309,12 @@ static inline int grid_for(int64_t total) {
 
 using namespace pdeqx;
 
+extern "C" int pdeqx_conv_tcgen05_passes(const pdeqx_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geometry(d, &g) != PDEQX_OK) return 0;
+  return (tc_conv_available(g) ? 1 : 0) | (tc_conv_bwd_data_available(g) ? 2 : 0) | (tc_conv_bwd_filter_available(g) ? 4 : 0);
+}
+
 extern "C" int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]) {
   ConvGeom g;
   PDEQX_TRY(conv_geometry(d, &g));
@@ -327,6 +333,7 @@ extern "C" int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const fl
   if (tc_conv_available(g)) return tc_conv_fwd(g, x, w, b, residual, activation, y, s);
   const int cog = g.c_out / g.groups;
   const int64_t total = (int64_t)g.batch * g.groups * ceil_div(cog, kOPT) * g.n_out;
+  TimedScope timed(PDEQX_K_CONV_FWD, s);
   conv_fwd_kernel<<<grid_for(total), 256, 0, s>>>(g, x, w, b, residual, y, activation);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
@@ -343,7 +350,7 @@ extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, co
     return PDEQX_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (tc_conv_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, s);
+  if (tc_conv_bwd_data_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, s);
   const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
   conv_bwd_data_kernel<<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
   PDEQX_LAUNCHED();
@@ -360,7 +367,6 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
   if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
   if (g.batch == 0) return PDEQX_OK;
-  if (tc_conv_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, s);
   const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
   const int64_t chunks = ceil_div(g.n_out, WF_P);
   const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;

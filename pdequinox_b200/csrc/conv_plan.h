@@ -18,6 +18,8 @@ int conv_geometry(const pdeqx_conv_desc* d, ConvGeom* out);
 
 // tcgen05 implicit-GEMM path (tc_conv.cu)
 bool tc_conv_available(const ConvGeom& g);
+bool tc_conv_bwd_data_available(const ConvGeom& g);
+bool tc_conv_bwd_filter_available(const ConvGeom& g);
 int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* residual, int act,
                 float* y, cudaStream_t s);
 int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, cudaStream_t s);

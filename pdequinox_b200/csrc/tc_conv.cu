@@ -1,18 +1,512 @@
-// tcgen05 implicit-GEMM path of PhysicsConv (placeholder: not yet enabled; conv.cu's fp32 path runs).
+// PhysicsConv on tcgen05 (TF32): boundary-aware 2-D k x k cross-correlation as an implicit GEMM over image rows.
+//
+//   replaces jnp.pad + lax.conv_general_dilated + bias (pdequinox/conv/_conv.py:169-219) for the hot-path case:
+//   2-D, stride 1, groups 1, odd kernel k (SAME padding p = d (k-1)/2), any dilation d, W == 128, C_i, C_o multiples
+//   of 32 up to 64 -- the ClassicResNet / DilatedResNet layers of BASELINE.json configs[2].
+//
+// One unit = one output row h of one sample for one half of the output channels:
+//     D[w', (tw, o)] = sum_{th, i} x[b, i, rowmap(h + th d - p), w'] * W[o, i, th, tw]      (M = 128, N = k*C_o/2, K = k*C_i)
+//     y[b, o, h, w]  = act( bias[o] + residual + sum_tw D[colmap(w + tw d - p), (tw, o)] )
+//   * the ROW taps are different TMA boxes (any boundary mode is a row-index map; dirichlet rows are skipped);
+//     consecutive units walk rows with stride d, so two of the three input rows of a unit are still resident in a
+//     3-slot shared-memory ring: ONE new row (C_i x 512 B) is fetched per unit;
+//   * the COLUMN taps stay separate accumulator columns and are shifted in the epilogue, where periodic / dirichlet /
+//     neumann is again just an index map (wrap / drop / mirror) -- no padded copy, no halo exchange;
+//   * the x row is the MN-major A operand (pixels contiguous): TMA SWIZZLE_128B_ATOM_32B + UMMA SWIZZLE_128B_BASE32B;
+//     the re-laid-out, tf32-rounded weights of the CTA's channel half stay resident in shared memory (K-major B).
+// The data gradient of periodic / dirichlet convolutions is the same kernel with flipped, transposed weights.
+// At C = 64, k = 3 the layer sits at the TF32 ridge (144 flop/B): tensor time ~ HBM time.
 #include "conv_plan.h"
+#include "tc_common.cuh"
 
 namespace pdeqx {
-bool tc_conv_available(const ConvGeom&) { return false; }
-int tc_conv_fwd(const ConvGeom&, const float*, const float*, const float*, const float*, int, float*, cudaStream_t) {
-  set_error("tc_conv_fwd: not available");
-  return PDEQX_ERR_UNSUPPORTED;
+namespace tc {
+
+constexpr int kConvThreads = 384;  // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue
+constexpr int kConvTmemCols = 256;
+constexpr int kMaxK = 3;
+
+struct ConvParams {
+  int H, W, c_in, c_out, k, d, p, boundary;
+  int batch, seg, segs_per_image;
+  int act, has_residual, has_bias;
+  int64_t items;  // batch * 2 halves * segs_per_image
+  const float* bias;
+};
+
+struct ConvSmem {
+  uint32_t w_off, w_th_bytes, w_chunk_bytes, ring_off, slot_bytes, box_bytes, tile_off, tile_bytes, bar_off, total;
+};
+
+static ConvSmem conv_smem(int c_in, int c_out, int k) {
+  ConvSmem s{};
+  const uint32_t N = (uint32_t)k * (c_out / 2);
+  uint32_t off = 0;
+  s.w_off = off;
+  s.w_chunk_bytes = N * 128;
+  s.w_th_bytes = (uint32_t)((c_in + 31) / 32) * s.w_chunk_bytes;
+  off += (uint32_t)k * s.w_th_bytes;
+  off = (off + 1023) & ~1023u;
+  s.ring_off = off;
+  s.box_bytes = (uint32_t)c_in * 128;
+  s.slot_bytes = 4 * s.box_bytes;
+  off += 3 * s.slot_bytes;
+  s.tile_off = off;
+  s.tile_bytes = (uint32_t)(c_out / 2) * 512;
+  off += 2 * s.tile_bytes;
+  s.bar_off = off;
+  off += 1024;
+  s.total = off + 1024;
+  return s;
 }
-int tc_conv_bwd_data(const ConvGeom&, const float*, const float*, const float*, float*, cudaStream_t) {
-  set_error("tc_conv_bwd_data: not available");
-  return PDEQX_ERR_UNSUPPORTED;
+
+__device__ __forceinline__ int conv_map(int q, int n, int mode) {
+  if (q >= 0 && q < n) return q;
+  if (mode == PDEQX_PAD_WRAP) {
+    int r = q % n;
+    return r < 0 ? r + n : r;
+  }
+  if (mode == PDEQX_PAD_REFLECT) {
+    const int per = 2 * (n - 1);
+    int r = q % per;
+    if (r < 0) r += per;
+    return r < n ? r : per - r;
+  }
+  if (mode == PDEQX_PAD_EDGE) return q < 0 ? 0 : n - 1;
+  return -1;
 }
+
+// Work decomposition. Rows are walked in stride-d chains (r0, r0 + d, r0 + 2d, ...): the three input rows of
+// output row h = r0 + j d are the "virtual" chain rows v = j-1, j, j+1 (actual row = rowmap(r0 + v d)), so consecutive
+// units share two of them. Virtual row v lives in ring slot (v + 1) % 3: a unit loads only v = j+1 (all three at the
+// start of a segment) and hands v = j-1 back after its first tap. The TMA producer, the MMA issuer and the epilogue
+// warps all derive this schedule from the item index alone -- a few integer ops per unit, nothing is communicated.
+//   item = ((b * d + r0) * segs_per_chain + seg) * 2 + half
+struct ConvItem {
+  int b, half, r0, j0, count;
+};
+__device__ __forceinline__ ConvItem conv_item(const ConvParams& p, int64_t item) {
+  ConvItem it;
+  it.half = (int)(item & 1);
+  int64_t r = item >> 1;
+  const int seg = (int)(r % p.segs_per_image);  // segments per chain
+  r /= p.segs_per_image;
+  it.r0 = (int)(r % p.d);
+  it.b = (int)(r / p.d);
+  it.j0 = seg * p.seg;
+  const int len = (p.H - it.r0 + p.d - 1) / p.d;
+  int c = len - it.j0;
+  it.count = c < 0 ? 0 : (c > p.seg ? p.seg : c);
+  return it;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res, ConvParams p, ConvSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* full = bars;         // [3] ring slots
+  uint64_t* empty = bars + 3;    // [3]
+  uint64_t* tfull = bars + 6;    // [2] accumulators
+  uint64_t* tempty = bars + 8;   // [2]
+  uint64_t* wfull = bars + 10;   // weights
+  uint64_t* rfull = bars + 11;   // [2] residual tiles
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 13);
+  float* bias_s = (float*)(bars + 14);  // [c_out/2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NOH = p.c_out / 2, N = 3 * NOH;
+  const int half_of_cta = (int)(blockIdx.x & 1);  // items alternate halves and the grid is even: a CTA keeps its half
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_y);
+    tma_prefetch_desc(&tm_res);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+      mbar_init(&rfull[i], 1);
+    }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kConvTmemCols>(tmem_ptr);
+  if (warp == 3)
+    for (int i = lane; i < NOH; i += 32) bias_s[i] = p.has_bias ? p.bias[half_of_cta * NOH + i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int kchunks = (p.c_in + 31) / 32;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, 3 * L.w_th_bytes);
+      for (int t = 0; t < 3; ++t)
+        for (int c = 0; c < kchunks; ++c)
+          tma_load_2d(smem + L.w_off + t * L.w_th_bytes + c * L.w_chunk_bytes, &tm_w, wfull, c * 32,
+                      (half_of_cta * 3 + t) * N);
+      uint32_t pe = 0, used = 0;  // per-slot parity of the empty barrier / "has been filled before"
+      for (int64_t item = first; item < p.items; item += stride) {
+        const ConvItem it = conv_item(p, item);
+        for (int jj = 0; jj < it.count; ++jj) {
+          const int j = it.j0 + jj;
+          for (int v = (jj == 0 ? j - 1 : j + 1); v <= j + 1; ++v) {
+            const int row = conv_map(it.r0 + v * p.d, p.H, p.boundary);
+            if (row < 0) continue;  // dirichlet: the tap is skipped
+            const int s = (v + 1) % 3;
+            if (used & (1u << s)) {
+              mbar_wait_backoff(&empty[s], (pe >> s) & 1u);
+              pe ^= 1u << s;
+            }
+            used |= 1u << s;
+            uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
+            mbar_expect_tx(&full[s], L.slot_bytes);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_x, &full[s], c * 32, row, it.b * p.c_in);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, N, /*a_mn_major=*/true, /*b_mn_major=*/false);
+      mbar_wait_backoff(wfull, 0);
+      int a = 0;
+      uint32_t aph = 0, pf = 0;
+      const int ksteps = p.c_in / 8;
+      const uint64_t adesc0 = smem_desc_sw128_atom32(smem_u32(smem + L.ring_off), L.box_bytes, 512);
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.w_off), 0, 1024);
+      for (int64_t item = first; item < p.items; item += stride) {
+        const ConvItem it = conv_item(p, item);
+        for (int jj = 0; jj < it.count; ++jj) {
+          const int j = it.j0 + jj;
+          const bool last = jj == it.count - 1;
+          mbar_wait_backoff(&tempty[a], aph ^ 1);
+          tc_fence_after();
+          const uint32_t dcol = tmem_base + (uint32_t)(a * N);
+          bool acc = false;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const int v = j - 1 + t;
+            const int row = conv_map(it.r0 + v * p.d, p.H, p.boundary);
+            if (row < 0) continue;
+            const int s = (v + 1) % 3;
+            if (jj == 0 || t == 2) {  // filled for this unit
+              mbar_wait_backoff(&full[s], (pf >> s) & 1u);
+              pf ^= 1u << s;
+              tc_fence_after();
+            }
+            const uint64_t ad = adesc0 + (uint64_t)((s * L.slot_bytes) >> 4);
+            const uint64_t bd = bdesc0 + (uint64_t)((t * L.w_th_bytes) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+              mma_tf32(dcol, ad + (uint64_t)(k * 64), bd + (uint64_t)(((k >> 2) * L.w_chunk_bytes + (k & 3) * 32) >> 4), idesc, acc);
+              acc = true;
+            }
+            if (t == 0 || last) mma_commit(&empty[s]);  // v = j-1 is never needed again; at a segment end nothing is
+          }
+          mma_commit(&tfull[a]);
+          if (++a == 2) { a = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int og = (warp - 4) >> 2;            // which 16-channel group of the half
+    const int ocnt = NOH / 2;                  // channels per warp (16)
+    const bool leader = (warp == 4 && lane == 0);
+    const int wq = q * 32 + lane;              // this thread's source column w'
+    int a = 0, e = 0;
+    uint32_t aph = 0, eph = 0;
+    for (int64_t item = first; item < p.items; item += stride) {
+      const ConvItem it = conv_item(p, item);
+      const int ch0 = it.b * p.c_out + it.half * NOH;
+      if (p.has_residual && leader && it.count > 0) {  // first residual tile of the item
+        tma_store_wait_read<1>();
+        mbar_expect_tx(&rfull[e], L.tile_bytes);
+        tma_load_3d(smem + L.tile_off + (size_t)e * L.tile_bytes, &tm_res, &rfull[e], 0, it.r0 + it.j0 * p.d, ch0);
+      }
+      for (int jj = 0; jj < it.count; ++jj) {
+        const int h = it.r0 + (it.j0 + jj) * p.d;
+        const uint32_t tile = smem_u32(smem + L.tile_off + (size_t)e * L.tile_bytes);
+        mbar_wait(&tfull[a], aph);
+        tc_fence_after();
+        if (p.has_residual) {
+          mbar_wait(&rfull[e], eph);
+        } else {
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 256);
+        }
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N + og * ocnt);
+        const uint32_t col0 = tile + (uint32_t)(og * ocnt * 128) * 4;
+        // ---- one pass per column tap (centre first); a barrier per pass keeps every tile element owned by exactly
+        //      one thread per pass. Output w reads input column w + s, i.e. source column w' feeds output w' - s. ----
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int tw = pass == 0 ? 1 : (pass == 1 ? 0 : 2);
+          const int s = (tw - 1) * p.d;
+          int wt = wq - s;
+          bool ok = true;
+          if (p.boundary == PDEQX_PAD_WRAP) wt = (wt + p.W) & (p.W - 1);  // W = 128
+          else ok = wt >= 0 && wt < p.W;
+          float v[16];
+          tmem_ld16(t0 + (uint32_t)(tw * NOH), v);
+          tmem_ld_wait();
+          if (pass == 2 && p.boundary != PDEQX_PAD_REFLECT) {  // last read of this accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+          }
+          if (ok) {
+            const uint32_t addr0 = col0 + (uint32_t)wt * 4;
+            if (pass == 0 && !p.has_residual) {
+#pragma unroll
+              for (int jx = 0; jx < 16; ++jx) st_shared_f32(addr0 + jx * 512, v[jx] + bias_s[og * ocnt + jx]);
+            } else {
+              float t[16];
+#pragma unroll
+              for (int jx = 0; jx < 16; ++jx) t[jx] = ld_shared_f32(addr0 + jx * 512);
+#pragma unroll
+              for (int jx = 0; jx < 16; ++jx)
+                st_shared_f32(addr0 + jx * 512, t[jx] + v[jx] + (pass == 0 ? bias_s[og * ocnt + jx] : 0.f));
+            }
+          }
+          named_bar_sync(1, 256);
+        }
+        // ---- mirror passes (neumann): columns reflected at the two edges ----
+        if (p.boundary == PDEQX_PAD_REFLECT) {
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            const int tw = side == 0 ? 0 : 2;
+            const int s = (tw - 1) * p.d;
+            int wt;
+            bool ok;
+            if (s < 0) { wt = -wq - s; ok = wq >= 1 && wt >= 0 && wt < p.W && wt + s < 0; }
+            else { wt = 2 * (p.W - 1) - wq - s; ok = wq <= p.W - 2 && wt >= 0 && wt < p.W && wt + s >= p.W; }
+            float v[16];
+            tmem_ld16(t0 + (uint32_t)(tw * NOH), v);
+            tmem_ld_wait();
+            if (ok) {
+              const uint32_t addr0 = col0 + (uint32_t)wt * 4;
+#pragma unroll
+              for (int jx = 0; jx < 16; ++jx) st_shared_f32(addr0 + jx * 512, ld_shared_f32(addr0 + jx * 512) + v[jx]);
+            }
+            named_bar_sync(1, 256);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+        // ---- activation pass over the thread's own column ----
+        if (ACT != PDEQX_ACT_IDENTITY) {
+          const uint32_t addr0 = col0 + (uint32_t)wq * 4;
+          float t[16];
+#pragma unroll
+          for (int jx = 0; jx < 16; ++jx) t[jx] = ld_shared_f32(addr0 + jx * 512);
+#pragma unroll
+          for (int jx = 0; jx < 16; ++jx)
+            st_shared_f32(addr0 + jx * 512, ACT == PDEQX_ACT_RELU ? fmaxf(t[jx], 0.f) : gelu_tanh(t[jx]));
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        if (leader) {
+          tma_store_3d(&tm_y, (const void*)(smem + L.tile_off + (size_t)e * L.tile_bytes), 0, h, ch0);
+          tma_store_commit();
+        }
+        if (++a == 2) { a = 0; aph ^= 1; }
+        if (++e == 2) { e = 0; eph ^= 1; }
+        if (p.has_residual && leader && jj + 1 < it.count) {  // next residual tile of this item into the other buffer
+          tma_store_wait_read<1>();
+          mbar_expect_tx(&rfull[e], L.tile_bytes);
+          tma_load_3d(smem + L.tile_off + (size_t)e * L.tile_bytes, &tm_res, &rfull[e], 0, h + p.d, ch0);
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kConvTmemCols>(tmem_base);
+  }
+}
+
+// weights -> [half][th][n = tw * NOH + o_local][i], tf32-rounded. flip: data-gradient weights
+// W'[i_as_out][o_as_in][th][tw] = W[o][i][k-1-th][k-1-tw]
+__global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int c_out, int c_in, int k,
+                                         int flip) {
+  // (c_out, c_in) are the channel counts of THIS call (after the swap for the data gradient)
+  const int NOH = c_out / 2;
+  const int total = c_out * c_in * k * k;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int i = idx % c_in;
+    int r = idx / c_in;
+    const int ol = r % NOH;
+    r /= NOH;
+    const int tw = r % k;
+    r /= k;
+    const int th = r % k;
+    const int half = r / k;
+    const int o = half * NOH + ol;
+    float v;
+    if (!flip) v = w[((o * c_in + i) * k + th) * k + tw];
+    else v = w[((i * c_out + o) * k + (k - 1 - th)) * k + (k - 1 - tw)];  // stored [c_in_call = orig out][c_out_call = orig in]
+    out[idx] = round_tf32(v);
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static float* g_wprep[16] = {nullptr};  // per-device scratch for the re-laid-out weights (k*k*64*64 floats max)
+
+// rows per work item: a divisor of H (so that no item has a ragged tail), as close to 32 as possible
+static int conv_segment(int H) {
+  if (H <= 64) return H;
+  for (int s = 64; s >= 8; --s)
+    if (H % s == 0 && s <= 32) return s;
+  for (int s = 64; s >= 8; --s)
+    if (H % s == 0) return s;
+  return 0;
+}
+
+static bool tc_conv_shape_ok(const ConvGeom& g) {
+  if (g.ndim != 2 || g.groups != 1) return false;
+  if (g.stride[0] != 1 || g.stride[1] != 1) return false;
+  if (g.kernel[0] != g.kernel[1] || g.kernel[0] != 3) return false;
+  if (g.dilation[0] != g.dilation[1]) return false;
+  const int d = g.dilation[0], pd = d * (g.kernel[0] - 1) / 2;
+  for (int a = 0; a < 2; ++a)
+    if (g.pad_lo[a] != pd || g.pad_hi[a] != pd) return false;
+  if (g.spatial[1] != 128) return false;
+  if (pd >= g.spatial[0] || pd >= g.spatial[1] - 1) return false;
+  if ((g.c_in != 32 && g.c_in != 64) || g.c_out != 64) return false;
+  if (g.c_in != g.c_out) return false;  // the data gradient swaps the roles; keep both directions on the fast path
+  if (g.boundary == PDEQX_PAD_EDGE) return false;
+  if (3 * (g.c_out / 2) * 2 > tc::kConvTmemCols) return false;
+  return true;
+}
+
+extern std::atomic<int> g_precision_conv;
+std::atomic<int> g_precision_conv{PDEQX_PREC_FP32};
+
+bool tc_conv_available(const ConvGeom& g) {
+  if (!g_fast_paths.load(std::memory_order_relaxed)) return false;
+  if (g_precision_conv.load(std::memory_order_relaxed) != PDEQX_PREC_TF32) return false;
+  if (!tc_conv_shape_ok(g)) return false;
+  if (!pdeqx_has_tcgen05() || !tc::encode_tiled_fn()) return false;
+  return true;
+}
+
+static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, bool flip, const float* bias,
+                            const float* residual, int act, float* y, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  PDEQX_CUDA(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PDEQX_CHECK_ARG(dev < 16, "device index too large");
+  const int c_in = flip ? g.c_out : g.c_in, c_out = flip ? g.c_in : g.c_out;
+  const int k = g.kernel[0];
+  if (!g_wprep[dev]) PDEQX_CUDA(cudaMalloc((void**)&g_wprep[dev], sizeof(float) * 64 * 64 * 9));
+  PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!residual || ((uintptr_t)residual & 15) == 0),
+                  "tc_conv: tensors must be 16-byte aligned");
+  const int total_w = c_out * c_in * k * k;
+  tc::conv_prep_weights_kernel<<<(total_w + 255) / 256, 256, 0, s>>>(w, g_wprep[dev], c_out, c_in, k, flip ? 1 : 0);
+  PDEQX_LAUNCHED();
+  const int H = g.spatial[0], W = g.spatial[1];
+  CUtensorMap tm_x, tm_w, tm_y, tm_res;
+  {
+    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * c_in};
+    uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)c_in};
+    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128_ATOM32));
+  }
+  {
+    const uint32_t N = (uint32_t)k * (c_out / 2);
+    uint64_t dims[2] = {(uint64_t)c_in, (uint64_t)2 * k * N};
+    uint64_t str[1] = {(uint64_t)c_in * 4};
+    uint32_t box[2] = {32, N};
+    PDEQX_TRY(tc::make_tensor_map(&tm_w, g_wprep[dev], 2, dims, str, box, tc::TM_SW128));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * c_out};
+    uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    uint32_t box[3] = {128, 1, (uint32_t)(c_out / 2)};
+    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box, tc::TM_NONE));
+    if (residual) PDEQX_TRY(tc::make_tensor_map(&tm_res, residual, 3, dims, str, box, tc::TM_NONE));
+    else tm_res = tm_y;
+  }
+  tc::ConvParams cp{};
+  cp.H = H; cp.W = W; cp.c_in = c_in; cp.c_out = c_out; cp.k = k; cp.d = g.dilation[0]; cp.p = g.pad_lo[0];
+  cp.boundary = g.boundary;
+  cp.batch = g.batch;
+  const int max_chain = (int)ceil_div(H, cp.d);
+  cp.seg = max_chain < 32 ? max_chain : 32;
+  cp.segs_per_image = (int)ceil_div(max_chain, cp.seg);  // segments per chain
+  cp.act = act;
+  cp.has_residual = residual ? 1 : 0;
+  cp.has_bias = bias ? 1 : 0;
+  cp.bias = bias;
+  cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image * 2;
+  tc::ConvSmem L = tc::conv_smem(c_in, c_out, k);
+  PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv: shared memory budget exceeded (%u bytes)", L.total);
+  int grid = (int)(cp.items < sms ? cp.items : sms);
+  grid &= ~1;  // even: a CTA keeps one channel half (its weights stay resident)
+  PDEQX_CHECK_ARG(grid >= 2, "tc_conv: grid too small");
+#define PDEQX_CONV_LAUNCH(A)                                                                                         \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_rows_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    tc::conv_rows_kernel<A><<<grid, tc::kConvThreads, L.total, s>>>(tm_x, tm_w, tm_y, tm_res, cp, L);                 \
+  } while (0)
+  if (act == PDEQX_ACT_RELU) PDEQX_CONV_LAUNCH(PDEQX_ACT_RELU);
+  else if (act == PDEQX_ACT_GELU_TANH) PDEQX_CONV_LAUNCH(PDEQX_ACT_GELU_TANH);
+  else PDEQX_CONV_LAUNCH(PDEQX_ACT_IDENTITY);
+#undef PDEQX_CONV_LAUNCH
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
+int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* residual, int act,
+                float* y, cudaStream_t s) {
+  TimedScope timed(PDEQX_K_CONV_FWD, s);
+  return conv_rows_launch(g, x, w, false, b, residual, act, y, s);
+}
+
+bool tc_conv_bwd_data_available(const ConvGeom& g) {
+  return tc_conv_available(g) && g.boundary != PDEQX_PAD_REFLECT;  // the adjoint of a reflect pad is a fold, not a conv
+}
+
+int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, cudaStream_t s) {
+  TimedScope timed(PDEQX_K_CONV_BWD_DATA, s);
+  return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, s);
+}
+
+bool tc_conv_bwd_filter_available(const ConvGeom&) { return false; }
+
 int tc_conv_bwd_filter(const ConvGeom&, const float*, const float*, float*, float*, cudaStream_t) {
   set_error("tc_conv_bwd_filter: not available");
   return PDEQX_ERR_UNSUPPORTED;
 }
+
 }  // namespace pdeqx
+
+extern "C" void pdeqx_set_conv_precision(int32_t precision) { pdeqx::g_precision_conv.store(precision); }
