@@ -23,8 +23,11 @@ namespace pdeqx {
 namespace tc {
 
 constexpr int kConvThreads = 384;  // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue
-constexpr int kConvTmemCols = 256;
+constexpr int kConvTmemCols = 512;
+constexpr int kAcc = 4;  // accumulator stages in TMEM (4 x 96 columns): the MMA issuer runs up to 4 units ahead of the epilogue
 constexpr int kMaxK = 3;
+constexpr int kRing = 4;    // input rows resident per CTA: 3 in use + 1 in flight
+constexpr int kMaxDil = 8;  // column taps reach at most 8 columns into the neighbouring warp's columns
 
 struct ConvParams {
   int H, W, c_in, c_out, k, d, p, boundary;
@@ -35,7 +38,7 @@ struct ConvParams {
 };
 
 struct ConvSmem {
-  uint32_t w_off, w_th_bytes, w_chunk_bytes, ring_off, slot_bytes, box_bytes, tile_off, tile_bytes, bar_off, total;
+  uint32_t w_off, w_th_bytes, w_chunk_bytes, ring_off, slot_bytes, box_bytes, tile_off, tile_bytes, xbuf_off, bar_off, total;
 };
 
 static ConvSmem conv_smem(int c_in, int c_out, int k) {
@@ -50,10 +53,12 @@ static ConvSmem conv_smem(int c_in, int c_out, int k) {
   s.ring_off = off;
   s.box_bytes = (uint32_t)c_in * 128;
   s.slot_bytes = 4 * s.box_bytes;
-  off += 3 * s.slot_bytes;
+  off += kRing * s.slot_bytes;
   s.tile_off = off;
   s.tile_bytes = (uint32_t)(c_out / 2) * 512;
-  off += 2 * s.tile_bytes;
+  off += s.tile_bytes;  // one output / residual tile (the ring needs the rest of the 227 KB)
+  s.xbuf_off = off;     // edge-column exchange: [2 taps][8 warps][16 channels][kMaxDil] floats
+  off += 2 * 8 * 16 * kMaxDil * 4;
   s.bar_off = off;
   off += 1024;
   s.total = off + 1024;
@@ -107,14 +112,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + L.bar_off);
-  uint64_t* full = bars;         // [3] ring slots
-  uint64_t* empty = bars + 3;    // [3]
-  uint64_t* tfull = bars + 6;    // [2] accumulators
-  uint64_t* tempty = bars + 8;   // [2]
-  uint64_t* wfull = bars + 10;   // weights
-  uint64_t* rfull = bars + 11;   // [2] residual tiles
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 13);
-  float* bias_s = (float*)(bars + 14);  // [c_out/2]
+  uint64_t* full = bars;         // [kRing] ring slots
+  uint64_t* empty = bars + 4;    // [kRing]
+  uint64_t* tfull = bars + 8;    // [kAcc] accumulators
+  uint64_t* tempty = bars + 12;  // [kAcc]
+  uint64_t* wfull = bars + 16;   // weights
+  uint64_t* rfull = bars + 17;   // residual tile
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 19);
+  float* bias_s = (float*)(bars + 20);  // [c_out/2]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NOH = p.c_out / 2, N = 3 * NOH;
@@ -127,15 +132,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     tma_prefetch_desc(&tm_res);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kRing; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);
-      mbar_init(&rfull[i], 1);
     }
+    mbar_init(rfull, 1);
     mbar_init(wfull, 1);
     fence_barrier_init();
   }
@@ -160,65 +165,85 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       uint32_t pe = 0, used = 0;  // per-slot parity of the empty barrier / "has been filled before"
       for (int64_t item = first; item < p.items; item += stride) {
         const ConvItem it = conv_item(p, item);
-        for (int jj = 0; jj < it.count; ++jj) {
-          const int j = it.j0 + jj;
-          for (int v = (jj == 0 ? j - 1 : j + 1); v <= j + 1; ++v) {
-            const int row = conv_map(it.r0 + v * p.d, p.H, p.boundary);
-            if (row < 0) continue;  // dirichlet: the tap is skipped
-            const int s = (v + 1) % 3;
-            if (used & (1u << s)) {
-              mbar_wait_backoff(&empty[s], (pe >> s) & 1u);
-              pe ^= 1u << s;
-            }
-            used |= 1u << s;
-            uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
-            mbar_expect_tx(&full[s], L.slot_bytes);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_x, &full[s], c * 32, row, it.b * p.c_in);
+        if (it.count == 0) continue;
+        // chain rows j0-1 .. j0+count of this segment, in order; runs ahead as far as the ring allows
+        for (int v = it.j0 - 1; v <= it.j0 + it.count; ++v) {
+          const int row = conv_map(it.r0 + v * p.d, p.H, p.boundary);
+          if (row < 0) continue;  // dirichlet: the tap is skipped
+          const int s = (v + 1) & (kRing - 1);
+          if (used & (1u << s)) {
+            mbar_wait_backoff(&empty[s], (pe >> s) & 1u);
+            pe ^= 1u << s;
           }
+          used |= 1u << s;
+          uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
+          mbar_expect_tx(&full[s], L.slot_bytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_x, &full[s], c * 32, row, it.b * p.c_in);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ONE thread issues every tcgen05.mma of the CTA, so its instruction stream is the critical path once the
+    // memory side keeps up: descriptors are (constant high word, low word = base + offset), the k loop is unrolled,
+    // and row validity needs no division.
+    // The whole warp runs the loop convergently (so the descriptor arithmetic stays warp-uniform) and one elected
+    // lane issues the tcgen05 instructions.
+    {
       const uint32_t idesc = idesc_tf32(128, N, /*a_mn_major=*/true, /*b_mn_major=*/false);
-      mbar_wait_backoff(wfull, 0);
+      mbar_wait(wfull, 0);
       int a = 0;
       uint32_t aph = 0, pf = 0;
-      const int ksteps = p.c_in / 8;
       const uint64_t adesc0 = smem_desc_sw128_atom32(smem_u32(smem + L.ring_off), L.box_bytes, 512);
       const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.w_off), 0, 1024);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t slot16 = L.slot_bytes >> 4, wth16 = L.w_th_bytes >> 4, chunk16 = L.w_chunk_bytes >> 4;
+      const bool zeros = p.boundary == PDEQX_PAD_ZEROS;
       for (int64_t item = first; item < p.items; item += stride) {
         const ConvItem it = conv_item(p, item);
         for (int jj = 0; jj < it.count; ++jj) {
           const int j = it.j0 + jj;
           const bool last = jj == it.count - 1;
-          mbar_wait_backoff(&tempty[a], aph ^ 1);
+          const int h = it.r0 + j * p.d;
+          mbar_wait(&tempty[a], aph ^ 1);
           tc_fence_after();
           const uint32_t dcol = tmem_base + (uint32_t)(a * N);
-          bool acc = false;
+          uint32_t acc = 0;
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
-            const int v = j - 1 + t;
-            const int row = conv_map(it.r0 + v * p.d, p.H, p.boundary);
-            if (row < 0) continue;
-            const int s = (v + 1) % 3;
-            if (jj == 0 || t == 2) {  // filled for this unit
-              mbar_wait_backoff(&full[s], (pf >> s) & 1u);
+            if (zeros && ((t == 0 && h - p.d < 0) || (t == 2 && h + p.d >= p.H))) continue;  // dirichlet row tap
+            const int s = (j + t) & (kRing - 1);  // slot of chain row v = j - 1 + t
+            if (jj == 0 || t == 2) {              // first use of this row
+              mbar_wait(&full[s], (pf >> s) & 1u);
               pf ^= 1u << s;
               tc_fence_after();
             }
-            const uint64_t ad = adesc0 + (uint64_t)((s * L.slot_bytes) >> 4);
-            const uint64_t bd = bdesc0 + (uint64_t)((t * L.w_th_bytes) >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              mma_tf32(dcol, ad + (uint64_t)(k * 64), bd + (uint64_t)(((k >> 2) * L.w_chunk_bytes + (k & 3) * 32) >> 4), idesc, acc);
-              acc = true;
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * slot16;
+            const uint32_t b_lo = b_lo0 + (uint32_t)t * wth16;
+            if (elect_one()) {
+            if (p.c_in == 64) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                mma_tf32_lohi(dcol, a_lo + k * 64, a_hi, b_lo + (k >> 2) * chunk16 + (k & 3) * 2, b_hi, idesc, acc);
+                acc = 1;
+              }
+            } else {
+              const int ks = p.c_in / 8;
+              for (int k = 0; k < ks; ++k) {
+                mma_tf32_lohi(dcol, a_lo + k * 64, a_hi, b_lo + (k >> 2) * chunk16 + (k & 3) * 2, b_hi, idesc, acc);
+                acc = 1;
+              }
             }
             if (t == 0 || last) mma_commit(&empty[s]);  // v = j-1 is never needed again; at a segment end nothing is
+            }
+            acc = 1;
+            __syncwarp();
           }
-          mma_commit(&tfull[a]);
-          if (++a == 2) { a = 0; aph ^= 1; }
+          if (elect_one()) mma_commit(&tfull[a]);
+          __syncwarp();
+          if (++a == kAcc) { a = 0; aph ^= 1; }
         }
       }
     }
@@ -229,109 +254,100 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int ocnt = NOH / 2;                  // channels per warp (16)
     const bool leader = (warp == 4 && lane == 0);
     const int wq = q * 32 + lane;              // this thread's source column w'
-    int a = 0, e = 0;
+    int a = 0;
     uint32_t aph = 0, eph = 0;
+    // per-thread constants of the column gather: output column wq reads D_0 at colmap(wq - d) and D_2 at colmap(wq + d)
+    const int c0 = conv_map(wq - p.d, p.W, p.boundary), c2 = conv_map(wq + p.d, p.W, p.boundary);
+    const bool use0 = c0 >= 0, use2 = c2 >= 0;
+    const bool in0 = use0 && (c0 >> 5) == q, in2 = use2 && (c2 >> 5) == q;
+    const int l0 = c0 & 31, l2 = c2 & 31;
+    float bias_r[16];
+#pragma unroll
+    for (int jx = 0; jx < 16; ++jx) bias_r[jx] = bias_s[og * ocnt + jx];
     for (int64_t item = first; item < p.items; item += stride) {
       const ConvItem it = conv_item(p, item);
       const int ch0 = it.b * p.c_out + it.half * NOH;
       if (p.has_residual && leader && it.count > 0) {  // first residual tile of the item
-        tma_store_wait_read<1>();
-        mbar_expect_tx(&rfull[e], L.tile_bytes);
-        tma_load_3d(smem + L.tile_off + (size_t)e * L.tile_bytes, &tm_res, &rfull[e], 0, it.r0 + it.j0 * p.d, ch0);
+        tma_store_wait_read<0>();
+        mbar_expect_tx(rfull, L.tile_bytes);
+        tma_load_3d(smem + L.tile_off, &tm_res, rfull, 0, it.r0 + it.j0 * p.d, ch0);
       }
       for (int jj = 0; jj < it.count; ++jj) {
         const int h = it.r0 + (it.j0 + jj) * p.d;
-        const uint32_t tile = smem_u32(smem + L.tile_off + (size_t)e * L.tile_bytes);
+        const uint32_t tile = smem_u32(smem + L.tile_off);
         mbar_wait(&tfull[a], aph);
         tc_fence_after();
-        if (p.has_residual) {
-          mbar_wait(&rfull[e], eph);
-        } else {
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 256);
-        }
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N + og * ocnt);
-        const uint32_t col0 = tile + (uint32_t)(og * ocnt * 128) * 4;
-        // ---- one pass per column tap (centre first); a barrier per pass keeps every tile element owned by exactly
-        //      one thread per pass. Output w reads input column w + s, i.e. source column w' feeds output w' - s. ----
+        // the three column taps of this thread's SOURCE column w' = wq (16 channels each), then the accumulator is free
+        float v0[16], v1[16], v2[16];
+        tmem_ld16(t0, v0);
+        tmem_ld16(t0 + (uint32_t)NOH, v1);
+        tmem_ld16(t0 + (uint32_t)(2 * NOH), v2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
+        // Output column w gathers D_0[colmap(w - d)] + D_1[w] + D_2[colmap(w + d)]. Sources inside the warp's own 32 columns
+        // come by shuffle; the d columns next to a warp edge (and the wrapped ones) go through a small exchange buffer.
+        const int d = p.d;
+        float* xb = (float*)(smem + L.xbuf_off);
+        float* xb0 = xb + ((0 * 8 + (og * 4 + q)) * 16) * kMaxDil;  // my last d lanes of D_0
+        float* xb2 = xb + ((1 * 8 + (og * 4 + q)) * 16) * kMaxDil;  // my first d lanes of D_2
+        if (lane >= 32 - d) {
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const int tw = pass == 0 ? 1 : (pass == 1 ? 0 : 2);
-          const int s = (tw - 1) * p.d;
-          int wt = wq - s;
-          bool ok = true;
-          if (p.boundary == PDEQX_PAD_WRAP) wt = (wt + p.W) & (p.W - 1);  // W = 128
-          else ok = wt >= 0 && wt < p.W;
-          float v[16];
-          tmem_ld16(t0 + (uint32_t)(tw * NOH), v);
-          tmem_ld_wait();
-          if (pass == 2 && p.boundary != PDEQX_PAD_REFLECT) {  // last read of this accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
-          }
-          if (ok) {
-            const uint32_t addr0 = col0 + (uint32_t)wt * 4;
-            if (pass == 0 && !p.has_residual) {
-#pragma unroll
-              for (int jx = 0; jx < 16; ++jx) st_shared_f32(addr0 + jx * 512, v[jx] + bias_s[og * ocnt + jx]);
-            } else {
-              float t[16];
-#pragma unroll
-              for (int jx = 0; jx < 16; ++jx) t[jx] = ld_shared_f32(addr0 + jx * 512);
-#pragma unroll
-              for (int jx = 0; jx < 16; ++jx)
-                st_shared_f32(addr0 + jx * 512, t[jx] + v[jx] + (pass == 0 ? bias_s[og * ocnt + jx] : 0.f));
-            }
-          }
-          named_bar_sync(1, 256);
+          for (int jx = 0; jx < 16; ++jx) xb0[jx * kMaxDil + lane - (32 - d)] = v0[jx];
         }
-        // ---- mirror passes (neumann): columns reflected at the two edges ----
-        if (p.boundary == PDEQX_PAD_REFLECT) {
+        if (lane < d) {
 #pragma unroll
-          for (int side = 0; side < 2; ++side) {
-            const int tw = side == 0 ? 0 : 2;
-            const int s = (tw - 1) * p.d;
-            int wt;
-            bool ok;
-            if (s < 0) { wt = -wq - s; ok = wq >= 1 && wt >= 0 && wt < p.W && wt + s < 0; }
-            else { wt = 2 * (p.W - 1) - wq - s; ok = wq <= p.W - 2 && wt >= 0 && wt < p.W && wt + s >= p.W; }
-            float v[16];
-            tmem_ld16(t0 + (uint32_t)(tw * NOH), v);
-            tmem_ld_wait();
-            if (ok) {
-              const uint32_t addr0 = col0 + (uint32_t)wt * 4;
-#pragma unroll
-              for (int jx = 0; jx < 16; ++jx) st_shared_f32(addr0 + jx * 512, ld_shared_f32(addr0 + jx * 512) + v[jx]);
-            }
-            named_bar_sync(1, 256);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[a]);
+          for (int jx = 0; jx < 16; ++jx) xb2[jx * kMaxDil + lane] = v2[jx];
         }
-        // ---- activation pass over the thread's own column ----
-        if (ACT != PDEQX_ACT_IDENTITY) {
-          const uint32_t addr0 = col0 + (uint32_t)wq * 4;
-          float t[16];
+        if (p.has_residual) {
+          mbar_wait(rfull, eph);
+          eph ^= 1;
+        } else {
+          if (leader) tma_store_wait_read<0>();  // the previous unit's store has drained the tile
+        }
+        named_bar_sync(1, 256);
+        // branch-free gather: every lane loads a (valid) exchange-buffer address and selects
+        const uint32_t xbs = smem_u32(xb);
+        const uint32_t far0 = xbs + (uint32_t)(((0 * 8 + (og * 4 + (use0 && !in0 ? (c0 >> 5) : q))) * 16) * kMaxDil +
+                                               (use0 && !in0 ? (c0 & 31) - (32 - d) : 0)) * 4;
+        const uint32_t far2 = xbs + (uint32_t)(((1 * 8 + (og * 4 + (use2 && !in2 ? (c2 >> 5) : q))) * 16) * kMaxDil +
+                                               (use2 && !in2 ? (c2 & 31) : 0)) * 4;
+        const uint32_t addr0 = tile + (uint32_t)((og * ocnt) * 128 + wq) * 4;
+        float f0[16], f2[16], res[16];
 #pragma unroll
-          for (int jx = 0; jx < 16; ++jx) t[jx] = ld_shared_f32(addr0 + jx * 512);
+        for (int jx = 0; jx < 16; ++jx) {
+          f0[jx] = ld_shared_f32(far0 + jx * kMaxDil * 4);
+          f2[jx] = ld_shared_f32(far2 + jx * kMaxDil * 4);
+        }
+        if (p.has_residual) {
 #pragma unroll
-          for (int jx = 0; jx < 16; ++jx)
-            st_shared_f32(addr0 + jx * 512, ACT == PDEQX_ACT_RELU ? fmaxf(t[jx], 0.f) : gelu_tanh(t[jx]));
+          for (int jx = 0; jx < 16; ++jx) res[jx] = ld_shared_f32(addr0 + jx * 512);
+        }
+#pragma unroll
+        for (int jx = 0; jx < 16; ++jx) {
+          const float s0 = __shfl_sync(0xffffffffu, v0[jx], l0);
+          const float s2 = __shfl_sync(0xffffffffu, v2[jx], l2);
+          float r = v1[jx] + bias_r[jx];
+          r += use0 ? (in0 ? s0 : f0[jx]) : 0.f;
+          r += use2 ? (in2 ? s2 : f2[jx]) : 0.f;
+          if (p.has_residual) r += res[jx];
+          if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
+          else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
+          st_shared_f32(addr0 + jx * 512, r);
         }
         fence_proxy_async();
         named_bar_sync(1, 256);
         if (leader) {
-          tma_store_3d(&tm_y, (const void*)(smem + L.tile_off + (size_t)e * L.tile_bytes), 0, h, ch0);
+          tma_store_3d(&tm_y, (const void*)(smem + L.tile_off), 0, h, ch0);
           tma_store_commit();
         }
-        if (++a == 2) { a = 0; aph ^= 1; }
-        if (++e == 2) { e = 0; eph ^= 1; }
-        if (p.has_residual && leader && jj + 1 < it.count) {  // next residual tile of this item into the other buffer
-          tma_store_wait_read<1>();
-          mbar_expect_tx(&rfull[e], L.tile_bytes);
-          tma_load_3d(smem + L.tile_off + (size_t)e * L.tile_bytes, &tm_res, &rfull[e], 0, h + p.d, ch0);
+        if (++a == kAcc) { a = 0; aph ^= 1; }
+        if (p.has_residual && leader && jj + 1 < it.count) {  // next residual tile once the store has read this one
+          tma_store_wait_read<0>();
+          mbar_expect_tx(rfull, L.tile_bytes);
+          tma_load_3d(smem + L.tile_off, &tm_res, rfull, 0, h + p.d, ch0);
         }
       }
     }
@@ -395,11 +411,11 @@ static bool tc_conv_shape_ok(const ConvGeom& g) {
   for (int a = 0; a < 2; ++a)
     if (g.pad_lo[a] != pd || g.pad_hi[a] != pd) return false;
   if (g.spatial[1] != 128) return false;
-  if (pd >= g.spatial[0] || pd >= g.spatial[1] - 1) return false;
+  if (pd >= g.spatial[0] || d > tc::kMaxDil) return false;
   if ((g.c_in != 32 && g.c_in != 64) || g.c_out != 64) return false;
   if (g.c_in != g.c_out) return false;  // the data gradient swaps the roles; keep both directions on the fast path
   if (g.boundary == PDEQX_PAD_EDGE) return false;
-  if (3 * (g.c_out / 2) * 2 > tc::kConvTmemCols) return false;
+  if (3 * (g.c_out / 2) * tc::kAcc > tc::kConvTmemCols) return false;
   return true;
 }
 

@@ -239,8 +239,8 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int64_t u = first; u < p.units; u += stride) {
-        mbar_wait_backoff(&tempty[a], aph ^ 1);
-        mbar_wait_backoff(&full[s], ph);
+        mbar_wait(&tempty[a], aph ^ 1);
+        mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(a * p.c_out);
         const uint32_t st = smem_u32(smem + L.stage_off + (size_t)s * L.stage_bytes);
@@ -429,11 +429,11 @@ r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int64_t t = first; t < p.tiles; t += stride) {
-        mbar_wait_backoff(&tempty[a], aph ^ 1);
+        mbar_wait(&tempty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(a * 32);
         for (int c = 0; c < p.kchunks; ++c) {
-          mbar_wait_backoff(&full[s], ph);
+          mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t xa = smem_u32(stage0 + (size_t)s * 128 * 128);
           const uint32_t tb = smem_u32(smem + c * 32 * 128);
@@ -559,7 +559,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       uint32_t ph = 0;
       bool acc = false;
       for (int64_t u = first; u < p.units; u += stride) {
-        mbar_wait_backoff(&full[s], ph);
+        mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
 #pragma unroll
