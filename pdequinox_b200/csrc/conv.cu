@@ -116,6 +116,9 @@ __device__ __forceinline__ int preimages(int n, int s, int lo, int hi, int mode,
   return c;
 }
 
+// MIRROR_ONLY: only the contributions that reach an input point through a wrapped / reflected halo position, ADDED to gx
+// (the tcgen05 path computes the zero-extended part; see tc_conv_bwd_data for neumann)
+template <bool MIRROR_ONLY>
 __global__ void __launch_bounds__(256)
 conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ add,
                      float* __restrict__ gx) {
@@ -137,12 +140,14 @@ conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __re
         npre[a] = preimages(na, g.spatial[a], g.pad_lo[a], g.pad_hi[a], g.boundary, pre[a]);
       }
     }
+    if (MIRROR_ONLY && npre[0] * npre[1] * npre[2] == 1) continue;
     const float* gyb = gy + ((int64_t)b * g.c_out + (int64_t)grp * cog) * g.n_out;
     const float* wg = w + ((int64_t)grp * cog * cig + il) * g.taps;
     float acc = 0.f;
     for (int c0 = 0; c0 < npre[0]; ++c0)
       for (int c1 = 0; c1 < npre[1]; ++c1)
         for (int c2 = 0; c2 < npre[2]; ++c2) {
+          if (MIRROR_ONLY && c0 + c1 + c2 == 0) continue;  // the direct position is the zero-extended part
           const int cc[PDEQX_MAX_DIMS] = {c0, c1, c2};
           for (int t = 0; t < g.taps; ++t) {
             int tt = t;
@@ -162,7 +167,8 @@ conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __re
               acc = fmaf(__ldg(wg + (int64_t)o * cig * g.taps + t), __ldg(gyb + (int64_t)o * g.n_out + dst), acc);
           }
         }
-    gx[idx] = acc + (add ? __ldg(add + idx) : 0.f);
+    if (MIRROR_ONLY) gx[idx] += acc;
+    else gx[idx] = acc + (add ? __ldg(add + idx) : 0.f);
   }
 }
 
@@ -305,6 +311,13 @@ static inline int grid_for(int64_t total) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w, float* gx, cudaStream_t s) {
+  const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
+  conv_bwd_data_kernel<true><<<grid_for(total), 256, 0, s>>>(g, gy, w, nullptr, gx);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
 }  // namespace pdeqx
 
 using namespace pdeqx;
@@ -352,7 +365,7 @@ extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, co
   cudaStream_t s = (cudaStream_t)stream;
   if (tc_conv_bwd_data_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, s);
   const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
-  conv_bwd_data_kernel<<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
+  conv_bwd_data_kernel<false><<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
@@ -367,6 +380,7 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
   if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
   if (g.batch == 0) return PDEQX_OK;
+  if (tc_conv_bwd_filter_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, s);
   const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
   const int64_t chunks = ceil_div(g.n_out, WF_P);
   const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;

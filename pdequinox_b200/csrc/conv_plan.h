@@ -16,6 +16,9 @@ struct ConvGeom {
 
 int conv_geometry(const pdeqx_conv_desc* d, ConvGeom* out);
 
+// gx += the part of the data gradient that arrives through wrapped / reflected halo positions (conv.cu, CUDA cores)
+int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w, float* gx, cudaStream_t s);
+
 // tcgen05 implicit-GEMM path (tc_conv.cu)
 bool tc_conv_available(const ConvGeom& g);
 bool tc_conv_bwd_data_available(const ConvGeom& g);

@@ -32,6 +32,7 @@ int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ bool elect_one() {
+  __syncwarp();  // elect.sync needs the whole warp converged (wait loops before it may exit lane by lane)
   uint32_t pred = 0;
   asm volatile(
       "{\n\t.reg .pred P;\n\t.reg .b32 R;\n\t"

@@ -385,6 +385,354 @@ __global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __r
   }
 }
 
+// ==========================================================================================
+// Filter gradient on tcgen05:  gW[o,i,th,tw] = sum_{b,h,w} gy[b,o,h,w] * x[b,i,rowmap(h+(th-1)d), colmap(w+(tw-1)d)]
+// ==========================================================================================
+// Unit = one row (b, h); the contraction runs over the 128 columns of the row (K = w).
+//   A (M = 128): column-SHIFTED copies of the gy row, stacked: group 1 = [shift for tw=0 (64 o) ; shift for tw=2 (64 o)],
+//                group 2 = [centre (64 o) ; don't-care]. A shifted copy is just a TMA box whose start column is moved by
+//                -s; out-of-range columns are zero-filled, i.e. this kernel computes the zero-extended ("dirichlet in w")
+//                part for every boundary mode -- the d wrapped / mirrored edge columns of periodic / neumann are added by
+//                conv_wgrad_edge_kernel on CUDA cores.
+//   B (N = 64):  the three x rows rowmap(h + (th-1) d) (K-major), from the same 3-row ring as the forward kernel.
+//   D: 6 accumulators of 64 columns (2 groups x 3 row taps) that live in TMEM for the CTA's whole life; each CTA flushes
+//      its partial sum to a scratch slab once, a second kernel reduces the slabs into gW (deterministic, no atomics).
+struct WgParams {
+  int H, W, c, d, boundary;
+  int seg, segs_per_chain;
+  int64_t items;  // batch * d * segs_per_chain
+  float* scratch;  // [grid][3 tw][3 th][c i][c o]
+  int col_shift;   // TMA column shift of the two outer taps (0 when pre-shifted copies are used)
+};
+
+struct WgSmem {
+  uint32_t gy_off, gy_chunk_bytes, ring_off, slot_bytes, box_bytes, bar_off, total;
+};
+constexpr int kWgRing = 4;   // x rows resident (3 in use + 1 in flight)
+constexpr int kWgGyStages = 3;  // 32-column chunks of shifted gy copies in flight (4 chunks per row rotate through them)
+
+static WgSmem wg_smem(int c) {
+  WgSmem s{};
+  uint32_t off = 0;
+  s.box_bytes = (uint32_t)c * 128;          // [c rows][32 w]
+  s.gy_off = off;
+  s.gy_chunk_bytes = 3 * s.box_bytes;       // [shift tw=0][shift tw=2][centre]
+  off += kWgGyStages * s.gy_chunk_bytes + s.box_bytes;  // + tail so that the last centre box has a (don't-care) upper half
+  s.ring_off = off;
+  s.slot_bytes = 4 * s.box_bytes;
+  off += kWgRing * s.slot_bytes;
+  s.bar_off = off;
+  off += 1024;
+  s.total = off + 1024;
+  return s;
+}
+
+struct WgItem {
+  int b, r0, j0, count;
+};
+__device__ __forceinline__ WgItem wg_item(const WgParams& p, int64_t item) {
+  WgItem it;
+  int64_t r = item;
+  const int seg = (int)(r % p.segs_per_chain);
+  r /= p.segs_per_chain;
+  it.r0 = (int)(r % p.d);
+  it.b = (int)(r / p.d);
+  it.j0 = seg * p.seg;
+  const int len = (p.H - it.r0 + p.d - 1) / p.d;
+  int c = len - it.j0;
+  it.count = c < 0 ? 0 : (c > p.seg ? p.seg : c);
+  return it;
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_gy0,
+                  const __grid_constant__ CUtensorMap tm_gy2, const __grid_constant__ CUtensorMap tm_x, WgParams p, WgSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* gyfull = bars;        // [kWgGyStages] chunk stages of shifted gy copies
+  uint64_t* gyempty = bars + 4;   // [kWgGyStages]
+  uint64_t* xfull = bars + 8;     // [kWgRing]
+  uint64_t* xempty = bars + 12;   // [kWgRing]
+  uint64_t* done = bars + 16;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 17);
+  uint32_t* inited_s = (uint32_t*)(bars + 18);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.c;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_gy);
+    tma_prefetch_desc(&tm_gy0);
+    tma_prefetch_desc(&tm_gy2);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&gyfull[i], 1);
+      mbar_init(&gyempty[i], 1);
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
+    mbar_init(done, 1);
+    *inited_s = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  // the don't-care upper half of the last centre box must at least be finite
+  for (uint32_t i = threadIdx.x; i < L.box_bytes / 4; i += blockDim.x)
+    ((float*)(smem + L.gy_off + kWgGyStages * L.gy_chunk_bytes))[i] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const bool zeros = p.boundary == PDEQX_PAD_ZEROS;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t pe = 0, used = 0, gpe = 0, gused = 0;
+      int gs = 0;  // gy chunk stage of the next chunk (global rotation over all chunks of all units)
+      for (int64_t item = first; item < p.items; item += stride) {
+        const WgItem it = wg_item(p, item);
+        int v_next = it.j0 - 1;  // next chain row of x to fetch
+        for (int jj = 0; jj < it.count; ++jj) {
+          const int j = it.j0 + jj;
+          const int h = it.r0 + j * p.d;
+          // x rows up to v = j + 2 (one row ahead of what this unit needs)
+          const int v_hi = (j + 2 <= it.j0 + it.count) ? j + 2 : it.j0 + it.count;
+          for (; v_next <= v_hi; ++v_next) {
+            const int row = conv_map(it.r0 + v_next * p.d, p.H, p.boundary);
+            if (row < 0) continue;
+            const int s = (v_next + 1) & (kWgRing - 1);
+            if (used & (1u << s)) {
+              mbar_wait_backoff(&xempty[s], (pe >> s) & 1u);
+              pe ^= 1u << s;
+            }
+            used |= 1u << s;
+            uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
+            mbar_expect_tx(&xfull[s], L.slot_bytes);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_x, &xfull[s], c * 32, row, it.b * C);
+          }
+          // the gy row of this unit: per 32-column chunk the two shifted copies and the centre copy
+          for (int c = 0; c < 4; ++c) {
+            if (gused & (1u << gs)) {
+              mbar_wait_backoff(&gyempty[gs], (gpe >> gs) & 1u);
+              gpe ^= 1u << gs;
+            }
+            gused |= 1u << gs;
+            uint8_t* dst = smem + L.gy_off + (size_t)gs * L.gy_chunk_bytes;
+            mbar_expect_tx(&gyfull[gs], L.gy_chunk_bytes);
+            // tap tw reads x column w + s, s = (tw - 1) d: substitute w' = w + s  =>  A_tw[o, w'] = gy[o, w' - s]
+            // (TMA needs 16-byte aligned box columns: for d % 4 != 0 the shifted copies come from pre-shifted tensors)
+            tma_load_3d(dst, &tm_gy0, &gyfull[gs], c * 32 + p.col_shift, h, it.b * C);                // tw = 0 (s = -d)
+            tma_load_3d(dst + L.box_bytes, &tm_gy2, &gyfull[gs], c * 32 - p.col_shift, h, it.b * C);  // tw = 2 (s = +d)
+            tma_load_3d(dst + 2 * L.box_bytes, &tm_gy, &gyfull[gs], c * 32, h, it.b * C);        // tw = 1
+            if (++gs == kWgGyStages) gs = 0;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
+    const uint32_t idesc = idesc_tf32(128, C, false, false);
+    const uint64_t adesc0 = smem_desc_sw128(smem_u32(smem + L.gy_off), 0, 1024);
+    const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.ring_off), 0, 1024);
+    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+    const uint32_t gchunk16 = L.gy_chunk_bytes >> 4, box16 = L.box_bytes >> 4, slot16 = L.slot_bytes >> 4;
+    uint32_t pf = 0, gpf = 0, inited = 0;
+    int gs = 0;
+    bool any = false;
+    for (int64_t item = first; item < p.items; item += stride) {
+      const WgItem it = wg_item(p, item);
+      for (int jj = 0; jj < it.count; ++jj) {
+        const int j = it.j0 + jj;
+        const bool last = jj == it.count - 1;
+        const int h = it.r0 + j * p.d;
+        bool valid[3];
+        valid[0] = !(zeros && h - p.d < 0);
+        valid[1] = true;
+        valid[2] = !(zeros && h + p.d >= p.H);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          if (!valid[t]) continue;
+          if (jj == 0 || t == 2) {  // first use of chain row v = j - 1 + t
+            const int s = (j + t) & (kWgRing - 1);
+            mbar_wait(&xfull[s], (pf >> s) & 1u);
+            pf ^= 1u << s;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(&gyfull[gs], (gpf >> gs) & 1u);
+          gpf ^= 1u << gs;
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              if (!valid[t]) continue;
+              const int s = (j + t) & (kWgRing - 1);
+              const uint32_t b_lo = b_lo0 + (uint32_t)s * slot16 + (uint32_t)c * box16;
+              const uint32_t a1 = a_lo0 + (uint32_t)gs * gchunk16;  // [shift tw=0 ; shift tw=2]
+              const uint32_t a2 = a1 + 2 * box16;                  // [centre ; don't-care]
+              const uint32_t d1 = tmem_base + (uint32_t)(t * C), d2 = tmem_base + (uint32_t)((3 + t) * C);
+              const uint32_t acc = (inited >> t) & 1u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_tf32_lohi(d1, a1 + k * 2, a_hi, b_lo + k * 2, b_hi, idesc, (c | k) ? 1u : acc);
+                mma_tf32_lohi(d2, a2 + k * 2, a_hi, b_lo + k * 2, b_hi, idesc, (c | k) ? 1u : acc);
+              }
+            }
+            mma_commit(&gyempty[gs]);
+            if (c == 3) {  // rows: v = j-1 is never needed again; at a segment end nothing is
+#pragma unroll
+              for (int t = 0; t < 3; ++t)
+                if (valid[t] && (t == 0 || last)) mma_commit(&xempty[(j + t) & (kWgRing - 1)]);
+            }
+          }
+          __syncwarp();
+          if (++gs == kWgGyStages) gs = 0;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (valid[t]) inited |= 1u << t;
+        any = true;
+      }
+    }
+    if (elect_one()) {
+      *inited_s = inited;
+      mma_commit(done);
+    }
+    __syncwarp();
+    (void)any;
+  } else if (warp >= 4) {
+    // ===================== flush: TMEM -> scratch[cta][tw][th][i][o] =====================
+    const int q = warp & 3;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const uint32_t inited = *(volatile uint32_t*)inited_s;
+    float* out = p.scratch + (size_t)blockIdx.x * 9 * C * C;
+    // lanes 0..63 of group 1 = tap tw 0, lanes 64..127 = tap tw 2; lanes 0..63 of group 2 = tap tw 1
+    const int o = (q & 1) * 32 + lane;
+    for (int g = 0; g < 2; ++g) {
+      if (g == 1 && q >= 2) break;
+      const int tw = g == 0 ? (q < 2 ? 0 : 2) : 1;
+      for (int t = 0; t < 3; ++t) {
+        for (int c0 = 0; c0 < C; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 3 + t) * C + c0), v);
+          tmem_ld_wait();
+          if (o < C) {
+#pragma unroll
+            for (int jx = 0; jx < 16; ++jx)
+              out[((size_t)(tw * 3 + t) * C + c0 + jx) * C + o] = ((inited >> t) & 1u) ? v[jx] : 0.f;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Column-shifted, zero-extended copies of gy for the two outer column taps when d is not a multiple of 4:
+//   out0[.., w'] = gy[.., w' + d]   (tap tw = 0),   out2[.., w'] = gy[.., w' - d]   (tap tw = 2),   0 outside the row.
+__global__ void __launch_bounds__(256)
+conv_shift_rows_kernel(const float* __restrict__ gy, float* __restrict__ out0, float* __restrict__ out2, int64_t rows, int W, int d) {
+  const int64_t total = rows * W;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % W);
+    out0[idx] = (w + d < W) ? __ldg(gy + idx + d) : 0.f;
+    out2[idx] = (w - d >= 0) ? __ldg(gy + idx - d) : 0.f;
+  }
+}
+
+// gw[o][i][th][tw] = sum_cta scratch[cta][tw][th][i][o]   (+ what the edge kernel adds afterwards)
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gw, int nslabs, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [tw][th][i][o]
+  const int total = 9 * C * C;
+  if (idx >= total) return;
+  float acc = 0.f;
+  for (int s = 0; s < nslabs; ++s) acc += scratch[(size_t)s * total + idx];
+  const int o = idx % C;
+  int r = idx / C;
+  const int i = r % C;
+  r /= C;
+  const int th = r % 3, tw = r / 3;
+  gw[((o * C + i) * 3 + th) * 3 + tw] = acc;
+}
+
+// The wrapped (periodic) / mirrored (neumann) edge columns of the two outer column taps, which the zero-extended tensor-core
+// pass leaves out:  gW[o,i,th,tw] += sum_{b,h} sum_{w : w+s outside [0,W)} gy[b,o,h,w] x[b,i,rowmap(h+(th-1)d), colmap(w+s)].
+// grid (row blocks, 6 = 3 row taps x 2 sides); 256 threads, thread = (o, 16 input channels); d <= 8 columns per side.
+__global__ void __launch_bounds__(256)
+conv_wgrad_edge_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw, int B, int C, int H,
+                       int W, int d, int boundary) {
+  __shared__ float gs[64][kMaxDil + 1];
+  __shared__ float xs[64][kMaxDil + 1];
+  const int th = blockIdx.y % 3, side = blockIdx.y / 3;  // side 0: tap tw = 0 (s = -d, left edge), side 1: tw = 2
+  const int tw = side == 0 ? 0 : 2;
+  const int s = (tw - 1) * d;
+  const int tid = threadIdx.x;
+  const int o = tid & 63, ig = tid >> 6;  // 4 groups of 16 input channels
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  const int64_t rows = (int64_t)B * H;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = (int)(r / H), h = (int)(r % H);
+    const int hr = conv_map(h + (th - 1) * d, H, boundary);
+    __syncthreads();
+    for (int idx = tid; idx < 64 * d; idx += 256) {
+      const int ch = idx / d, e = idx % d;
+      const int w = side == 0 ? e : W - d + e;  // the d output columns whose tap falls outside the row
+      const int wc = conv_map(w + s, W, boundary);
+      gs[ch][e] = ch < C ? __ldg(gy + (((int64_t)b * C + ch) * H + h) * W + w) : 0.f;
+      xs[ch][e] = (ch < C && hr >= 0 && wc >= 0) ? __ldg(x + (((int64_t)b * C + ch) * H + hr) * W + wc) : 0.f;
+    }
+    __syncthreads();
+    for (int e = 0; e < d; ++e) {
+      const float g = gs[o][e];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = fmaf(g, xs[ig * 16 + k][e], acc[k]);
+    }
+  }
+  if (o < C) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int i = ig * 16 + k;
+      if (i < C) atomicAdd(gw + ((o * C + i) * 3 + th) * 3 + tw, acc[k]);
+    }
+  }
+}
+
+// gb[o] = sum_{b,h,w} gy[b,o,h,w]: one block per (b, o) plane chunk, atomics on C addresses
+__global__ void __launch_bounds__(256)
+conv_bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ gb, int C, int64_t n) {
+  const int64_t plane = blockIdx.x;  // b * C + o
+  const float4* src = (const float4*)(gy + plane * n);
+  float acc = 0.f;
+  for (int64_t v = threadIdx.x; v < n / 4; v += blockDim.x) {
+    const float4 t = __ldg(src + v);
+    acc += (t.x + t.y) + (t.z + t.w);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(gb + (int)(plane % C), t);
+  }
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------
@@ -507,20 +855,88 @@ int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* 
   return conv_rows_launch(g, x, w, false, b, residual, act, y, s);
 }
 
-bool tc_conv_bwd_data_available(const ConvGeom& g) {
-  return tc_conv_available(g) && g.boundary != PDEQX_PAD_REFLECT;  // the adjoint of a reflect pad is a fold, not a conv
-}
+bool tc_conv_bwd_data_available(const ConvGeom& g) { return tc_conv_available(g); }
 
 int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, cudaStream_t s) {
   TimedScope timed(PDEQX_K_CONV_BWD_DATA, s);
-  return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, s);
+  if (g.boundary != PDEQX_PAD_REFLECT) return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, s);
+  // neumann: the adjoint of a reflect pad is a FOLD, not a convolution. The zero-extended part is the same implicit GEMM
+  // (dirichlet data gradient); what arrives through mirrored halo positions only touches a frame of width d and is added
+  // by the CUDA-core gather.
+  ConvGeom z = g;
+  z.boundary = PDEQX_PAD_ZEROS;
+  PDEQX_TRY(conv_rows_launch(z, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, s));
+  return conv_bwd_data_mirror_part(g, gy, w, gx, s);
 }
 
-bool tc_conv_bwd_filter_available(const ConvGeom&) { return false; }
+static float* g_wg_scratch[16] = {nullptr};
+static float* g_wg_shift[16] = {nullptr};   // per-device pre-shifted gy copies (2 x activation size), grown on demand
+static size_t g_wg_shift_floats[16] = {0};  // per-device [148][9][64][64] partial filter gradients
 
-int tc_conv_bwd_filter(const ConvGeom&, const float*, const float*, float*, float*, cudaStream_t) {
-  set_error("tc_conv_bwd_filter: not available");
-  return PDEQX_ERR_UNSUPPORTED;
+bool tc_conv_bwd_filter_available(const ConvGeom& g) { return tc_conv_available(g) && g.c_in == 64; }
+
+// gw, gb zeroed by the caller (conv.cu)
+int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, cudaStream_t s) {
+  TimedScope timed(PDEQX_K_CONV_BWD_FILTER, s);
+  int dev = 0, sms = 148;
+  PDEQX_CUDA(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PDEQX_CHECK_ARG(dev < 16 && sms <= 160, "unexpected device");
+  const int C = g.c_in, H = g.spatial[0], W = g.spatial[1], d = g.dilation[0];
+  if (!g_wg_scratch[dev]) PDEQX_CUDA(cudaMalloc((void**)&g_wg_scratch[dev], sizeof(float) * 160 * 9 * 64 * 64));
+  PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)gy & 15) == 0, "tc_conv: tensors must be 16-byte aligned");
+  CUtensorMap tm_gy, tm_gy0, tm_gy2, tm_x;
+  const bool preshift = (d % 4) != 0;
+  const size_t n_act = (size_t)g.batch * C * H * W;
+  if (preshift) {  // TMA box columns must be 16-byte aligned: materialise the two shifted copies once
+    if (g_wg_shift_floats[dev] < 2 * n_act) {
+      if (g_wg_shift[dev]) PDEQX_CUDA(cudaFree(g_wg_shift[dev]));
+      g_wg_shift[dev] = nullptr;
+      g_wg_shift_floats[dev] = 0;
+      PDEQX_CUDA(cudaMalloc((void**)&g_wg_shift[dev], sizeof(float) * 2 * n_act));
+      g_wg_shift_floats[dev] = 2 * n_act;
+    }
+    tc::conv_shift_rows_kernel<<<148 * 16, 256, 0, s>>>(gy, g_wg_shift[dev], g_wg_shift[dev] + n_act, (int64_t)g.batch * C * H, W, d);
+    PDEQX_LAUNCHED();
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * C};
+    uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)C};
+    PDEQX_TRY(tc::make_tensor_map(&tm_gy, gy, 3, dims, str, box, tc::TM_SW128));
+    PDEQX_TRY(tc::make_tensor_map(&tm_gy0, preshift ? g_wg_shift[dev] : gy, 3, dims, str, box, tc::TM_SW128));
+    PDEQX_TRY(tc::make_tensor_map(&tm_gy2, preshift ? g_wg_shift[dev] + n_act : gy, 3, dims, str, box, tc::TM_SW128));
+    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128));
+  }
+  tc::WgParams wp{};
+  wp.H = H; wp.W = W; wp.c = C; wp.d = d; wp.boundary = g.boundary;
+  const int max_chain = (int)ceil_div(H, d);
+  wp.seg = max_chain < 32 ? max_chain : 32;
+  wp.segs_per_chain = (int)ceil_div(max_chain, wp.seg);
+  wp.items = (int64_t)g.batch * d * wp.segs_per_chain;
+  wp.scratch = g_wg_scratch[dev];
+  wp.col_shift = preshift ? 0 : d;
+  tc::WgSmem L = tc::wg_smem(C);
+  PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
+  const int grid = (int)(wp.items < sms ? wp.items : sms);
+  static bool attr = false;
+  if (!attr) {
+    PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  tc::conv_wgrad_kernel<<<grid, 256, L.total, s>>>(tm_gy, tm_gy0, tm_gy2, tm_x, wp, L);
+  PDEQX_LAUNCHED();
+  tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C);
+  PDEQX_LAUNCHED();
+  if (g.boundary == PDEQX_PAD_WRAP || g.boundary == PDEQX_PAD_REFLECT) {
+    tc::conv_wgrad_edge_kernel<<<dim3(148 * 2, 6), 256, 0, s>>>(x, gy, gw, g.batch, C, H, W, d, g.boundary);
+    PDEQX_LAUNCHED();
+  }
+  if (gb) {
+    tc::conv_bias_grad_kernel<<<g.batch * C, 256, 0, s>>>(gy, gb, C, (int64_t)H * W);
+    PDEQX_LAUNCHED();
+  }
+  return PDEQX_OK;
 }
 
 }  // namespace pdeqx

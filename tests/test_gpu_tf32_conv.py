@@ -44,8 +44,7 @@ def test_tf32_conv_fwd_bwd(mode, C, H, d, B):
     desc, _ = conv._desc(dev(x))
     passes = _lib.lib().pdeqx_conv_tcgen05_passes(desc)
     if C == 64:
-        assert passes & 1, "forward is not on the tcgen05 path"
-        assert bool(passes & 2) == (mode != "neumann")  # the adjoint of a reflect pad is a fold: fp32 path
+        assert passes == 7, f"tcgen05 passes {passes}"
     else:
         assert passes == 0  # C = 32 runs the fp32 path (also under set_precision("tf32"))
     # plain
