@@ -258,6 +258,29 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": slab_bytes, "avg_launch_us": avg_s * 1e6,
                     "launches_timed": slab_n.value, "share_of_step": slab_ms.value / ms, "traffic": None}
 
+    # ---- PhysicsConv roofline (BASELINE.json configs[2] layer: 3x3, 64 -> 64, 128x128, batch 128, periodic) ----
+    physics = None
+    if world == 1:
+        conv = pdeqx.PhysicsConv(2, 64, 64, 3, key=1, boundary_mode="periodic")
+        xc = torch.randn(128, 64, 128, 128, device="cuda")
+        yc = torch.empty_like(xc)
+        desc, _ = conv._desc(xc)
+
+        def conv_fwd():
+            _lib.check(L.pdeqx_conv_fwd(desc, _lib.ptr(xc), _lib.ptr(conv.weight), _lib.ptr(conv.bias), None, _lib.ACT_RELU,
+                                        _lib.ptr(yc), _lib.stream()))
+        for _ in range(3):
+            conv_fwd()
+        reps = 10
+        ms_c = timed(conv_fwd, reps) / reps
+        conv_bytes = 4 * 128 * (64 + 64) * 128 * 128 + 4 * 64 * (64 * 9 + 1)
+        physics = {"bound": "hbm (at the TF32 ridge: 144 flop/B)", "kernel": "PhysicsConv 3x3 64->64 fwd + bias + relu, 128x128, batch 128, periodic",
+                   "achieved": conv_bytes / (ms_c * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": conv_bytes / (ms_c * 1e-3) / 1e9 / hbm_peak, "avg_launch_us": ms_c * 1e3,
+                   "tflops": 2 * 64 * 64 * 9 * 128 * 128 * 128 / (ms_c * 1e-3) / 1e12,
+                   "tcgen05_passes": int(L.pdeqx_conv_tcgen05_passes(desc))}
+        del xc, yc
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, dt, cores = cpu_train_step_rate(args.cpu_sample, 2, 1)
@@ -279,6 +302,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "physics_conv": physics,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
