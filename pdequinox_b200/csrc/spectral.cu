@@ -140,6 +140,7 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
   p->mode_floats = (2 * (int64_t)desc->batch * cmax * J + 63) / 64 * 64;
   p->ws_bytes = (size_t)(2 * p->stage_floats + 2 * p->mode_floats) * sizeof(float) + 256;
   rc = tc_plan_init(p);  // builds the tcgen05-side operand tables when the shape qualifies
+  if (rc == PDEQX_OK) rc = tc_c2c_plan_init(p);
   if (rc != PDEQX_OK) {
     pdeqx_spectral_plan_destroy(p);
     return rc;
@@ -161,6 +162,7 @@ extern "C" void pdeqx_spectral_plan_destroy(pdeqx_spectral_plan* p) {
     cudaFree(p->t_fwd_adj[a]);
   }
   tc_plan_free(p);
+  tc_c2c_plan_free(p);
   delete p;
 }
 
@@ -208,8 +210,10 @@ static int stage_c2r(const pdeqx_spectral_plan* p, const float* z, const float* 
 
 // One complex stage along axis `a` of a tensor [B*C, n_0.., n_a, .., inner] (complex).
 //   n_in -> n_out through table [n_out x n_in].
-static int stage_c2c(const float2* table, const float* in, float* out, int64_t outer, int n_in, int n_out,
-                     int64_t inner, cudaStream_t s) {
+static int stage_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float2* table, const float* in, float* out,
+                     int64_t outer, int n_in, int n_out, int64_t inner, cudaStream_t s) {
+  TimedScope timed(PDEQX_K_SPECTRAL_MODES, s);
+  if (tc_c2c_available(p, axis, kind, inner)) return tc_c2c(p, axis, kind, in, out, outer, inner, s);
   return cgemm_shared_a(table, (const float2*)in, (float2*)out, outer, n_out, n_in, inner, s);
 }
 
@@ -239,7 +243,7 @@ static int forward_chain(const pdeqx_spectral_plan* p, const float* x, int C, bo
     for (int b = a + 1; b < D - 1; ++b) inner *= 2 * d.modes[b];
     float* dstage = (a == 0) ? dst : r.big[nb];
     const float2* tab = adjoint_of_inverse ? p->t_inv_adj[a] : p->t_fwd[a];
-    PDEQX_TRY(stage_c2c(tab, cur, dstage, outer, d.spatial[a], 2 * d.modes[a], inner, s));
+    PDEQX_TRY(stage_c2c(p, a, adjoint_of_inverse ? 2 : 0, tab, cur, dstage, outer, d.spatial[a], 2 * d.modes[a], inner, s));
     cur = dstage;
     nb ^= 1;
   }
@@ -260,7 +264,7 @@ static int inverse_chain(const pdeqx_spectral_plan* p, const float* yhat, int C,
     for (int b = a + 1; b < D - 1; ++b) inner *= 2 * d.modes[b];
     float* dstage = (a == D - 2) ? dst : r.big[0];
     const float2* tab = adjoint_of_forward ? p->t_fwd_adj[a] : p->t_inv[a];
-    PDEQX_TRY(stage_c2c(tab, cur, dstage, outer, 2 * d.modes[a], d.spatial[a], inner, s));
+    PDEQX_TRY(stage_c2c(p, a, adjoint_of_forward ? 3 : 1, tab, cur, dstage, outer, 2 * d.modes[a], d.spatial[a], inner, s));
     cur = dstage;
   }
   return PDEQX_OK;

@@ -23,6 +23,8 @@ struct pdeqx_spectral_plan {
   float2* t_fwd_adj[PDEQX_MAX_DIMS] = {nullptr, nullptr, nullptr};  // [s, 2m] = conj(t_fwd)^T
   // tcgen05 side (tc_spectral.cu); null when the shape does not qualify
   void* tc = nullptr;
+  // tcgen05 leading-axis stages (tc_c2c.cu)
+  void* tc_c2c = nullptr;
 };
 
 namespace pdeqx {
@@ -46,6 +48,12 @@ bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass);
 int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
             bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s);
 
+// leading-axis complex DFT stages on tcgen05 (tc_c2c.cu). kind: 0 forward, 1 inverse, 2 adjoint-of-inverse, 3 adjoint-of-forward
+int tc_c2c_plan_init(pdeqx_spectral_plan* p);
+void tc_c2c_plan_free(pdeqx_spectral_plan* p);
+bool tc_c2c_available(const pdeqx_spectral_plan* p, int axis, int kind, int64_t inner_complex);
+int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, float* out, int64_t outer, int64_t inner_complex,
+           cudaStream_t s);
 // general form: explicit channel counts of THIS call, epilogue mode 1 = aux * act'(.) (cotangent of the pre-activation)
 int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,

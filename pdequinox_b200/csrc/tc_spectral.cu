@@ -124,10 +124,10 @@ struct SlabParams {
 
 // smem carve-up (all tile regions 1024-B aligned)
 struct SlabSmem {
-  uint32_t tab_off, w_off, stage_off, stage_bytes, x_box_bytes, z_off_in_stage, epi_off, epi_buf_bytes, bar_off, total;
+  uint32_t tab_off, w_off, stage_off, stage_bytes, x_box_bytes, z_off_in_stage, epi_off, epi_buf_bytes, epi_bufs, bar_off, total;
 };
 
-static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages) {
+static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, int epi_bufs = 2) {
   SlabSmem s{};
   uint32_t off = 0;
   s.tab_off = off;
@@ -144,7 +144,8 @@ static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages) {
   // epilogue staging: per half of the output channels, two [c_out/2 x 128 w] fp32 tiles (TMA store source / aux target)
   s.epi_off = off;
   s.epi_buf_bytes = (uint32_t)(c_out / 2) * 512;
-  off += 4 * s.epi_buf_bytes;
+  off += 2 * (uint32_t)epi_bufs * s.epi_buf_bytes;
+  s.epi_bufs = (uint32_t)epi_bufs;
   s.bar_off = off;
   off += 1024;  // barriers, tmem pointer, bias
   s.total = off + 1024;  // slack for manual 1024-B alignment of the dynamic base
@@ -165,8 +166,8 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint64_t* tempty = bars + 18;            // [2]
   uint64_t* tabfull = bars + 20;           // [1]
   uint32_t* tmem_ptr = (uint32_t*)(bars + 22);
-  uint64_t* auxfull = bars + 24;           // [2 halves][2 buffers]
-  float* bias_s = (float*)(bars + 28);     // [c_out] (<= 128 floats)
+  uint64_t* auxfull = bars + 24;           // [2 halves][up to 3 buffers]
+  float* bias_s = (float*)(bars + 30);     // [c_out] (<= 128 floats)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -187,7 +188,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     mbar_init(&tempty[0], 8);
     mbar_init(&tempty[1], 8);
     mbar_init(tabfull, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&auxfull[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&auxfull[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -272,15 +273,21 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int half = (warp - 4) >> 2;  // which half of the output channels
     const int ncol = p.c_out / 2;
     const bool leader = (q == 0 && lane == 0);
-    uint8_t* ebuf0 = smem + L.epi_off + (size_t)half * 2 * L.epi_buf_bytes;
-    uint64_t* afull = auxfull + half * 2;
+    const int NB = (int)L.epi_bufs;  // 2 (MODE 0) or 3 (MODE 1: the cotangent tile is prefetched two units ahead)
+    uint8_t* ebuf0 = smem + L.epi_off + (size_t)half * NB * L.epi_buf_bytes;
+    uint64_t* afull = auxfull + half * 3;
     int a = 0, e = 0;
     uint32_t aph = 0, eph = 0;
-    if (MODE == 1 && leader && first < p.units) {
-      const int wt = (int)(first % p.wt_per_row);
-      const int64_t bl = first / p.wt_per_row;
-      mbar_expect_tx(&afull[0], L.epi_buf_bytes);
-      tma_load_3d(ebuf0, &tm_aux, &afull[0], wt * 128, (int)(bl % p.lead), (int)(bl / p.lead) * p.c_out + half * ncol);
+    auto load_aux = [&](int64_t un, int buf) {
+      const int wtn = (int)(un % p.wt_per_row);
+      const int64_t bln = un / p.wt_per_row;
+      mbar_expect_tx(&afull[buf], L.epi_buf_bytes);
+      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], wtn * 128, (int)(bln % p.lead),
+                  (int)(bln / p.lead) * p.c_out + half * ncol);
+    };
+    if (MODE == 1 && leader) {
+      if (first < p.units) load_aux(first, 0);
+      if (first + stride < p.units) load_aux(first + stride, 1);
     }
     for (int64_t u = first; u < p.units; u += stride) {
       const int wt = (int)(u % p.wt_per_row);
@@ -335,19 +342,15 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         tma_store_3d(&tm_y, tile, wt * 128, l, b * p.c_out + half * ncol);
         tma_store_commit();
         if (MODE == 1) {
-          const int64_t un = u + stride;
-          if (un < p.units) {  // prefetch the next cotangent tile into the other buffer once its last store has drained
+          const int64_t un = u + 2 * stride;
+          if (un < p.units) {  // cotangent tile two units ahead, into the buffer whose store (previous unit) has drained
             tma_store_wait_read<1>();
-            const int wtn = (int)(un % p.wt_per_row);
-            const int64_t bln = un / p.wt_per_row;
-            mbar_expect_tx(&afull[e ^ 1], L.epi_buf_bytes);
-            tma_load_3d(ebuf0 + (size_t)(e ^ 1) * L.epi_buf_bytes, &tm_aux, &afull[e ^ 1], wtn * 128, (int)(bln % p.lead),
-                        (int)(bln / p.lead) * p.c_out + half * ncol);
+            load_aux(un, e == 0 ? NB - 1 : e - 1);
           }
         }
       }
       if (++a == 2) { a = 0; aph ^= 1; }
-      if (++e == 2) { e = 0; eph ^= 1; }
+      if (++e == NB) { e = 0; eph ^= 1; }
     }
     if (leader) tma_store_wait_all();
   }
@@ -827,7 +830,17 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.bias = bypass_b;
   sp.aux = aux;
   sp.y = y;
-  tc::SlabSmem L = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages);
+  int epi_bufs = 2;
+  if (mode == 1) {  // trade one load stage for a third epilogue tile (cotangent prefetch distance 2)
+    tc::SlabSmem t3 = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages - 1, 3);
+    if (sp.stages > 2 && t3.total <= 227 * 1024) {
+      epi_bufs = 3;
+      sp.stages -= 1;
+    } else if (tc::slab_smem(sD, c_in, c_out, bypass, sp.stages, 3).total <= 227 * 1024) {
+      epi_bufs = 3;
+    }
+  }
+  tc::SlabSmem L = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages, epi_bufs);
   int grid = (int)(sp.units < t->sms ? sp.units : t->sms);
   grid = grid / sp.wt_per_row * sp.wt_per_row;  // every CTA keeps one w-tile of the table (units stride by the grid size)
   PDEQX_CHECK_ARG(grid >= sp.wt_per_row, "tc_slab: grid smaller than the number of w-tiles");
