@@ -23,7 +23,8 @@ namespace pdeqx {
 namespace tc {
 
 struct C2cParams {
-  int n_in, n_out, N;       // N = 2 n_out accumulator columns
+  int n_in, n_out, N;       // N = 2 n_part accumulator columns per unit
+  int n_part, parts;        // output rows per unit; units per block group (n_out = n_part * parts)
   int kchunk, kchunks;      // rows per TMA stage, stages per unit
   int q_per_outer;          // 32-float chunks per row
   int stages, acc_stages;
@@ -32,13 +33,13 @@ struct C2cParams {
   float* out;
 };
 
-constexpr int kC2cThreads = 256;
+constexpr int kC2cThreads = 384;  // warps 0-2 roles, 4-11 epilogue (two warps per TMEM lane quarter)
 
 __global__ void __launch_bounds__(kC2cThreads, 1)
 c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_tab, C2cParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t tab_chunk_bytes = (uint32_t)p.N * 128;               // [N rows][32 k]
+  const uint32_t tab_chunk_bytes = (uint32_t)(2 * p.n_out) * 128;     // [2 n_out rows][32 k]
   const uint32_t tab_bytes = (uint32_t)(p.n_in / 32) * tab_chunk_bytes;
   const uint32_t box_bytes = (uint32_t)p.kchunk * 128;                 // [kchunk rows][32 floats]
   const uint32_t stage_bytes = 4 * box_bytes;
@@ -63,7 +64,7 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     mbar_init(tabfull, 1);
     fence_barrier_init();
@@ -80,7 +81,7 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     if (lane == 0) {
       mbar_expect_tx(tabfull, tab_bytes);
       for (int c = 0; c < p.n_in / 32; ++c)
-        for (int nb = 0; nb < p.N; nb += 256)
+        for (int nb = 0; nb < 2 * p.n_out; nb += 256)
           tma_load_2d(smem + (size_t)c * tab_chunk_bytes + (size_t)nb * 128, &tm_tab, tabfull, c * 32, nb);
       int s = 0;
       uint32_t ph = 0;
@@ -91,7 +92,7 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
           mbar_expect_tx(&full[s], stage_bytes);
 #pragma unroll
           for (int mb = 0; mb < 4; ++mb) {
-            const int64_t id = u * 4 + mb;  // blocks past the end are out of bounds: zero-filled, never stored
+            const int64_t id = (u / p.parts) * 4 + mb;  // blocks past the end are out of bounds: zero-filled, never stored
             const int outer = (int)(id / p.q_per_outer), q = (int)(id % p.q_per_outer);
             tma_load_3d(dst + mb * box_bytes, &tm_in, &full[s], q * 32, kc * p.kchunk, outer);
           }
@@ -101,9 +102,10 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp convergent, one elected lane issues) =====================
-    const int nmma = (p.N + 255) / 256;                 // MMAs per k-step (N <= 256 per instruction)
-    const int ncols = p.N < 256 ? p.N : 256;
-    const uint32_t idesc = idesc_tf32(128, ncols, /*a_mn_major=*/true, /*b_mn_major=*/false);
+    // one MMA with N = 2 n_out when a unit covers every output row ([Re T ; Im T] rows are contiguous), else two MMAs
+    // (Re rows of the part, Im rows of the part) with N = n_part each
+    const bool single = p.parts == 1;
+    const uint32_t idesc = idesc_tf32(128, single ? p.N : p.n_part, /*a_mn_major=*/true, /*b_mn_major=*/false);
     const uint64_t adesc0 = smem_desc_sw128_atom32(smem_u32(stage0), box_bytes, 512);
     const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem), 0, 1024);
     const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
@@ -114,6 +116,8 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     int s = 0, a = 0;
     uint32_t ph = 0, aph = 0;
     for (int64_t u = first; u < p.units; u += stride) {
+      const int part = (int)(u % p.parts);
+      const uint32_t re16 = (uint32_t)(part * p.n_part) * 8, im16 = (uint32_t)(p.n_out + part * p.n_part) * 8;  // rows * 128 B / 16
       mbar_wait(&tempty[a], aph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(a * p.N);
@@ -125,9 +129,9 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
           for (int ks = 0; ks < ksteps; ++ks) {
             const int kg = kc * ksteps + ks;  // global k-step: table chunk kg >> 2, 32-byte slice kg & 3
             const uint32_t b_lo = b_lo0 + (uint32_t)(kg >> 2) * tchunk16 + (uint32_t)(kg & 3) * 2;
-            for (int nb = 0; nb < nmma; ++nb)
-              mma_tf32_lohi(d0 + (uint32_t)(nb * 256), a_lo + (uint32_t)ks * 64, a_hi, b_lo + (uint32_t)nb * (256 * 128 / 16), b_hi,
-                            idesc, (kc | ks) ? 1u : 0u);
+            const uint32_t acc = (kc | ks) ? 1u : 0u;
+            mma_tf32_lohi(d0, a_lo + (uint32_t)ks * 64, a_hi, b_lo + re16, b_hi, idesc, acc);
+            if (!single) mma_tf32_lohi(d0 + (uint32_t)p.n_part, a_lo + (uint32_t)ks * 64, a_hi, b_lo + im16, b_hi, idesc, acc);
           }
           mma_commit(&empty[s]);
           if (kc == p.kchunks - 1) mma_commit(&tfull[a]);
@@ -139,24 +143,28 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ===================== epilogue: combine re/im parts, store rows =====================
-    const int q4 = warp & 3;  // which of the unit's four blocks (= TMEM lane quarter)
+    const int q4 = warp & 3;            // which of the unit's four blocks (= TMEM lane quarter)
+    const int rh = (warp - 4) >> 2;     // which half of the unit's output rows
+    const int rows_w = p.n_part / 2;    // rows per warp
     int a = 0;
     uint32_t aph = 0;
     for (int64_t u = first; u < p.units; u += stride) {
-      const int64_t id = u * 4 + q4;
+      const int part = (int)(u % p.parts);
+      const int64_t id = (u / p.parts) * 4 + q4;
       const bool live = id < p.blocks;
       const int64_t outer = id / p.q_per_outer;
       const int q = (int)(id % p.q_per_outer);
-      float* dst = p.out + outer * (int64_t)p.n_out * p.inner_f + (int64_t)q * 32 + lane;
+      const int row0 = part * p.n_part + rh * rows_w;
+      float* dst = p.out + (outer * (int64_t)p.n_out + row0) * p.inner_f + (int64_t)q * 32 + lane;
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.N);
-      for (int r0 = 0; r0 < p.n_out; r0 += 16) {
+      const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.N + rh * rows_w);
+      for (int r0 = 0; r0 < rows_w; r0 += 16) {
         float pr[16], qi[16];
         tmem_ld16(t0 + (uint32_t)r0, pr);
-        tmem_ld16(t0 + (uint32_t)(p.n_out + r0), qi);
+        tmem_ld16(t0 + (uint32_t)(p.n_part + r0), qi);
         tmem_ld_wait();
-        if (r0 + 16 >= p.n_out) {
+        if (r0 + 16 >= rows_w) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
@@ -226,7 +234,7 @@ int tc_c2c_plan_init(pdeqx_spectral_plan* p) {
       tb.n_in = n_in[k];
       tb.n_out = n_out[k];
       // shape limits of the kernel: K chunks of 32, N = 2 n_out <= 512 accumulator columns, 16-column epilogue steps
-      if (n_in[k] % 32 != 0 || n_out[k] % 16 != 0 || 2 * n_out[k] > 512 || (2 * n_out[k] > 256 && (2 * n_out[k]) % 256 != 0)) continue;
+      if (n_in[k] % 32 != 0 || n_out[k] % 32 != 0 || (2 * n_out[k] > 256 && (2 * n_out[k]) % 256 != 0)) continue;
       if ((size_t)2 * n_out[k] * n_in[k] * 4 > 96 * 1024) continue;  // table must stay resident in shared memory
       std::vector<float2> h((size_t)n_out[k] * n_in[k]);
       if (cudaMemcpy(h.data(), src[k], h.size() * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) continue;
@@ -273,16 +281,18 @@ int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, fl
   tc::C2cParams cp{};
   cp.n_in = tb.n_in;
   cp.n_out = tb.n_out;
-  cp.N = 2 * tb.n_out;
+  cp.parts = (2 * tb.n_out > 256) ? (2 * tb.n_out) / 256 : 1;
+  cp.n_part = tb.n_out / cp.parts;
+  cp.N = 2 * cp.n_part;
   cp.kchunk = tb.n_in >= 64 && tb.n_in % 64 == 0 ? 64 : 32;
   cp.kchunks = tb.n_in / cp.kchunk;
   cp.inner_f = 2 * inner_complex;
   cp.q_per_outer = (int)(cp.inner_f / 32);
   cp.blocks = outer * cp.q_per_outer;
-  cp.units = ceil_div(cp.blocks, 4);
-  cp.acc_stages = (2 * cp.N <= 512) ? 2 : 1;
+  cp.units = ceil_div(cp.blocks, 4) * cp.parts;
+  cp.acc_stages = 2;
   cp.out = out;
-  const uint32_t tab_bytes = (uint32_t)cp.N * tb.n_in * 4;
+  const uint32_t tab_bytes = (uint32_t)(2 * tb.n_out) * tb.n_in * 4;
   const uint32_t stage_bytes = 4 * (uint32_t)cp.kchunk * 128;
   int stages = (int)((227 * 1024 - 2048 - tab_bytes) / stage_bytes);
   if (stages > 6) stages = 6;
