@@ -141,6 +141,128 @@ mode_mix_dw_kernel(const float2* __restrict__ ghat, const float2* __restrict__ x
   }
 }
 
+
+// ---- tiled path: per-mode complex GEMM  C[m,n,p] = sum_k A(m,k,p) * B(n,k,p)^(conj) -------------------------------
+// One CTA owns PT consecutive retained modes (one run along the contiguous mode axis, so the corner g and the weight
+// offset are affine in the mode), 64 rows m and NT columns n; operands are staged through shared memory in K chunks,
+// each thread keeps an 8 x 4 complex accumulator tile for one mode. The three uses differ only in where the operands
+// live: mode-space arrays are complex-interleaved [row, J], weights are planar (re / im arrays) in the reference
+// layout (G, o, i, *m).
+//   mix    : M = b, N = u = o, K = v = i, B = w[o=n, i=k]            (planar), C interleaved
+//   mix^H  : M = b, N = u = i, K = v = o, B = conj(w[o=k, i=n])      (planar), C interleaved
+//   dW     : M = o, N = i,     K = b,     B = conj(xhat[b=k, i=n])   (interleaved), C planar
+struct TiledArgs {
+  const float2* a;   // interleaved
+  int64_t a_sm, a_sk;  // strides (in float2) over m and k
+  const float2* b2;  // interleaved B (dW)
+  const float* br;   // planar B (mix)
+  const float* bi;
+  int64_t b_sn, b_sk;  // strides (float2 for interleaved / floats for planar) over n and k
+  float2* c2;        // interleaved C (mix)
+  float* cr;         // planar C (dW)
+  float* ci;
+  int64_t c_sm, c_sn;
+  int M, N, K;
+  int64_t J;
+  int64_t w_corner;  // O * I * mprod: weight floats per corner
+  ModeMap mm;
+};
+
+constexpr int TM_MT = 64, TM_KC = 8;
+
+template <int PT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
+__global__ void __launch_bounds__(256, 2)
+mode_gemm_tiled_kernel(TiledArgs t) {
+  constexpr int NQ = 32 / PT;   // n-quads per warp-row group ... threads = PT * 8 * NQ
+  constexpr int NT = 4 * NQ;    // columns per CTA
+  __shared__ float2 As[TM_KC][TM_MT][PT];
+  __shared__ float2 Bs[TM_KC][NT][PT];
+  const int tid = threadIdx.x;
+  const int pm = tid % PT, mq = (tid / PT) % 8, nq = tid / (PT * 8);
+  const int64_t p0 = (int64_t)blockIdx.x * PT;
+  const int m0 = blockIdx.y * TM_MT, n0 = blockIdx.z * NT;
+  int g;
+  int64_t loc;
+  mode_to_weight(t.mm, p0, g, loc);
+  const int64_t woff = (int64_t)g * t.w_corner + loc;  // planar operands: offset of mode p0 inside an (o,i) plane
+  float2 acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
+
+  for (int k0 = 0; k0 < t.K; k0 += TM_KC) {
+    // A chunk: [KC][MT][PT] float2, PT contiguous in global memory
+    for (int idx = tid; idx < TM_KC * TM_MT * PT; idx += 256) {
+      const int q = idx % PT, m = (idx / PT) % TM_MT, k = idx / (PT * TM_MT);
+      float2 v = make_float2(0.f, 0.f);
+      if (m0 + m < t.M && k0 + k < t.K) v = __ldg(t.a + (int64_t)(m0 + m) * t.a_sm + (int64_t)(k0 + k) * t.a_sk + p0 + q);
+      As[k][m][q] = v;
+    }
+    for (int idx = tid; idx < TM_KC * NT * PT; idx += 256) {
+      const int q = idx % PT, n = (idx / PT) % NT, k = idx / (PT * NT);
+      float2 v = make_float2(0.f, 0.f);
+      if (n0 + n < t.N && k0 + k < t.K) {
+        if (B_PLANAR) {
+          const int64_t off = (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + woff + q;
+          v = make_float2(__ldg(t.br + off), __ldg(t.bi + off));
+        } else {
+          v = __ldg(t.b2 + (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + p0 + q);
+        }
+        if (CONJ_B) v.y = -v.y;
+      }
+      Bs[k][n][q] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TM_KC; ++k) {
+      float2 a[8], b[4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = As[k][mq + 8 * r][pm];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = Bs[k][nq * 4 + c][pm];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc[r][c].x = fmaf(a[r].x, b[c].x, fmaf(-a[r].y, b[c].y, acc[r][c].x));
+          acc[r][c].y = fmaf(a[r].x, b[c].y, fmaf(a[r].y, b[c].x, acc[r][c].y));
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int m = m0 + mq + 8 * r;
+    if (m >= t.M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + nq * 4 + c;
+      if (n >= t.N) continue;
+      if (C_PLANAR) {
+        const int64_t off = (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + woff + pm;
+        t.cr[off] = acc[r][c].x;
+        t.ci[off] = acc[r][c].y;
+      } else {
+        t.c2[(int64_t)m * t.c_sm + (int64_t)n * t.c_sn + p0 + pm] = acc[r][c];
+      }
+    }
+  }
+}
+
+template <bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
+static bool launch_tiled(const TiledArgs& t, cudaStream_t s) {
+  const int mD = t.mm.m[t.mm.D - 1];
+  const int pt = (mD % 8 == 0) ? 8 : (mD % 4 == 0) ? 4 : 0;
+  if (!pt) return false;
+  const int nt = 4 * (32 / pt);
+  dim3 grid((unsigned)(t.J / pt), (unsigned)ceil_div(t.M, TM_MT), (unsigned)ceil_div(t.N, nt));
+  if (grid.y > 65535 || grid.z > 65535) return false;
+  if (pt == 8) mode_gemm_tiled_kernel<8, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t);
+  else mode_gemm_tiled_kernel<4, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t);
+  return true;
+}
+
 static ModeMap make_map(const pdeqx_spectral_plan* p) {
   ModeMap mm;
   mm.D = p->desc.ndim;
@@ -157,6 +279,19 @@ int mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re, c
   const pdeqx_spectral_desc& d = p->desc;
   const int O = d.c_out, I = d.c_in;
   const int U = transposed_conj ? I : O, V = transposed_conj ? O : I;
+  {
+    TiledArgs t{};
+    t.mm = make_map(p);
+    t.a = (const float2*)in; t.a_sm = (int64_t)V * p->J; t.a_sk = p->J;
+    t.br = w_re; t.bi = w_im;
+    // W(u,v): plain -> w[o=u, i=v]; transposed_conj -> conj(w[o=v, i=u])
+    t.b_sn = transposed_conj ? t.mm.mprod : (int64_t)I * t.mm.mprod;
+    t.b_sk = transposed_conj ? (int64_t)I * t.mm.mprod : t.mm.mprod;
+    t.c2 = (float2*)out; t.c_sm = (int64_t)U * p->J; t.c_sn = p->J;
+    t.M = d.batch; t.N = U; t.K = V; t.J = p->J; t.w_corner = (int64_t)O * I * t.mm.mprod;
+    const bool ok = transposed_conj ? launch_tiled<true, false, true>(t, s) : launch_tiled<true, false, false>(t, s);
+    if (ok) { PDEQX_LAUNCHED(); return PDEQX_OK; }
+  }
   dim3 grid((unsigned)ceil_div(p->J, 16), (unsigned)ceil_div(d.batch, 16), (unsigned)ceil_div(U, 16));
   PDEQX_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "mode_mix: grid too large");
   ModeMap mm = make_map(p);
@@ -171,6 +306,15 @@ int mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re, c
 int mode_mix_dw(const pdeqx_spectral_plan* p, const float* ghat, const float* xhat, float* gw_re, float* gw_im,
                 cudaStream_t s) {
   const pdeqx_spectral_desc& d = p->desc;
+  {
+    TiledArgs t{};
+    t.mm = make_map(p);
+    t.a = (const float2*)ghat; t.a_sm = p->J; t.a_sk = (int64_t)d.c_out * p->J;
+    t.b2 = (const float2*)xhat; t.b_sn = p->J; t.b_sk = (int64_t)d.c_in * p->J;
+    t.cr = gw_re; t.ci = gw_im; t.c_sm = (int64_t)d.c_in * t.mm.mprod; t.c_sn = t.mm.mprod;
+    t.M = d.c_out; t.N = d.c_in; t.K = d.batch; t.J = p->J; t.w_corner = (int64_t)d.c_out * d.c_in * t.mm.mprod;
+    if (launch_tiled<false, true, true>(t, s)) { PDEQX_LAUNCHED(); return PDEQX_OK; }
+  }
   dim3 grid((unsigned)ceil_div(p->J, 16), (unsigned)ceil_div(d.c_out, 16), (unsigned)ceil_div(d.c_in, 16));
   PDEQX_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "mode_mix_dw: grid too large");
   mode_mix_dw_kernel<<<grid, 256, 0, s>>>((const float2*)ghat, (const float2*)xhat, gw_re, gw_im, d.batch, p->J,

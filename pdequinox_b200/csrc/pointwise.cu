@@ -327,6 +327,65 @@ pw_wgrad_small_kernel(const float* __restrict__ gy, const float* __restrict__ x,
   }
 }
 
+
+// One channel on the small side (the lifting 1 -> C and projection C -> 1 of every architecture in the reference):
+// pure streaming. blockIdx.y selects a group of WC_CG big-side channels; a thread keeps one float4 of the small side in
+// registers and issues the WC_CG row loads of its 4 pixels back to back (16 x 16 B in flight per thread), accumulating
+// per-channel dot products (and channel sums for the bias) across all its units; one block reduction + atomic flush.
+constexpr int WC_CG = 16;
+template <bool BIG_IS_GY>
+__global__ void __launch_bounds__(256, 2)
+pw_wgrad_c1_kernel(const float* __restrict__ big, const float* __restrict__ small_, float* __restrict__ gw,
+                   float* __restrict__ gb, int batch, int nbig, int64_t n) {
+  __shared__ float red[8][2 * WC_CG + 1];
+  const int c0 = blockIdx.y * WC_CG;
+  const int64_t chunks = n / 1024;  // the launcher guarantees n % 1024 == 0
+  const int64_t units = (int64_t)batch * chunks;
+  float acc[WC_CG], bs[WC_CG], ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < WC_CG; ++c) acc[c] = bs[c] = 0.f;
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int b = (int)(u / chunks);
+    const int64_t p = (u % chunks) * 1024 + threadIdx.x * 4;
+    const float4 sv = __ldg((const float4*)(small_ + (int64_t)b * n + p));
+    const float* row = big + ((int64_t)b * nbig + c0) * n + p;
+    float4 v[WC_CG];
+#pragma unroll
+    for (int c = 0; c < WC_CG; ++c) v[c] = (c0 + c < nbig) ? __ldg((const float4*)(row + (int64_t)c * n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < WC_CG; ++c) {
+      acc[c] = fmaf(v[c].x, sv.x, fmaf(v[c].y, sv.y, fmaf(v[c].z, sv.z, fmaf(v[c].w, sv.w, acc[c]))));
+      if (BIG_IS_GY) bs[c] += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+    }
+    if (!BIG_IS_GY) ss += (sv.x + sv.y) + (sv.z + sv.w);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < WC_CG; ++c) {
+    float a = acc[c], s2 = bs[c];
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (BIG_IS_GY) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) { red[warp][c] = a; red[warp][WC_CG + c] = s2; }
+  }
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  if (lane == 0) red[warp][2 * WC_CG] = ss;
+  __syncthreads();
+  if (threadIdx.x < 2 * WC_CG + 1) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int c = threadIdx.x % WC_CG;
+    if (threadIdx.x < WC_CG) {
+      if (c0 + c < nbig) atomicAdd(gw + c0 + c, t);  // gw is [nbig] either way: (C_o,1) or (1,C_i)
+    } else if (threadIdx.x < 2 * WC_CG) {
+      if (BIG_IS_GY && gb && c0 + c < nbig) atomicAdd(gb + c0 + c, t);
+    } else if (!BIG_IS_GY && gb && blockIdx.y == 0) {
+      atomicAdd(gb, t);
+    }
+  }
+}
+
 }  // namespace pdeqx
 
 using namespace pdeqx;
@@ -351,6 +410,18 @@ extern "C" int pdeqx_pointwise_bwd(int32_t batch, int32_t c_in, int32_t c_out, i
   if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)c_out, s));
   if (batch == 0 || n_pixels == 0) return PDEQX_OK;
   const int nbig = c_out >= c_in ? c_out : c_in, nsmall = c_out >= c_in ? c_in : c_out;
+  if (nsmall == 1 && n_pixels % 1024 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)gy % 16 == 0) {
+    const bool big_is_gy = c_out >= c_in;
+    const int64_t units = (int64_t)batch * (n_pixels / 1024);
+    const int groups = (int)ceil_div(nbig, WC_CG);
+    int per_group = (148 * 2 + groups - 1) / groups;  // 2 resident CTAs per SM over all channel groups
+    if (per_group > units) per_group = (int)units;
+    dim3 grid(per_group, groups);
+    if (big_is_gy) pw_wgrad_c1_kernel<true><<<grid, 256, 0, s>>>(gy, x, gw, gb, batch, nbig, n_pixels);
+    else pw_wgrad_c1_kernel<false><<<grid, 256, 0, s>>>(x, gy, gw, gb, batch, nbig, n_pixels);
+    PDEQX_LAUNCHED();
+    return PDEQX_OK;
+  }
   if (nsmall <= kSmallC && nbig <= 8 * WS_MAXCH) {
     const int64_t units = (int64_t)batch * ceil_div(n_pixels, WS_CHUNK);
     const int grid = (int)(units < 148 ? units : 148);
