@@ -195,6 +195,43 @@ int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float*
                           float* gb, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * PhysicsConvTranspose / MorePaddingConvTranspose (ClassicUNet up-sampling)
+ *   replaces pdequinox/conv/_conv.py:378-471 with the SAME padding of
+ *   pdequinox/conv/_physics_conv.py:219-232. Reference-specific semantics: the
+ *   weight [c_out, c_in/groups, *k] is used as is (no flip, no in/out swap) in
+ *   a stride-1 correlation over the boundary-padded, stride-dilated input.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t ndim; /* 1..3 */
+  int32_t batch;
+  int32_t c_in, c_out, groups;
+  int32_t spatial[PDEQX_MAX_DIMS]; /* input S */
+  int32_t kernel[PDEQX_MAX_DIMS];
+  int32_t stride[PDEQX_MAX_DIMS];  /* up-sampling factor (lhs dilation) */
+  int32_t dilation[PDEQX_MAX_DIMS];
+  int32_t pad_lo[PDEQX_MAX_DIMS], pad_hi[PDEQX_MAX_DIMS]; /* the module's `padding` */
+  int32_t output_padding[PDEQX_MAX_DIMS];
+  int32_t boundary; /* enum pdeqx_boundary */
+} pdeqx_convT_desc;
+int pdeqx_convT_out_spatial(const pdeqx_convT_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]);
+/* y[B,c_out,*S_out] = corr(dilate(pad(x)), w) + b; b may be NULL */
+int pdeqx_convT_fwd(const pdeqx_convT_desc* d, const float* x, const float* w, const float* b, float* y,
+                    void* stream);
+/* gx[B,c_in,*S] (overwritten) */
+int pdeqx_convT_bwd_data(const pdeqx_convT_desc* d, const float* gy, const float* w, float* gx,
+                         void* stream);
+/* gw[c_out,c_in/groups,*k], gb[c_out] (may be NULL); overwritten */
+int pdeqx_convT_bwd_filter(const pdeqx_convT_desc* d, const float* x, const float* gy, float* gw,
+                           float* gb, void* stream);
+
+/* Skip connection of Hierarchical.__call__ (pdequinox/_hierarchical.py:275):
+ * out[B, c_a + c_b, n] = concatenate((a, b), channel axis), and its adjoint. */
+int pdeqx_concat_channels(int32_t batch, int32_t c_a, int32_t c_b, int64_t n, const float* a,
+                          const float* b, float* out, void* stream);
+int pdeqx_split_channels(int32_t batch, int32_t c_a, int32_t c_b, int64_t n, const float* g, float* ga,
+                         float* gb, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * GroupNorm (eqx.nn.GroupNorm, eps 1e-5, biased variance, per-channel affine)
  *   call sites: pdequinox/blocks/_dilated_res_block.py:88-99,143-146,
  *   _classic_double_conv_block.py:75-83, _classic_res_block.py:80-89

@@ -234,21 +234,22 @@ def more_padding_conv_transpose(x, weight, bias, *, stride, padding, output_padd
     st = _ntuple(stride, D)
     rd = _ntuple(dilation, D)
     op = _ntuple(output_padding, D)
-    padding_t = tuple(
+    padding = tuple(tuple(pp) for pp in padding)
+    padding_t = tuple(  # _conv.py:411-416
         (d * (kk - 1) - p0, d * (kk - 1) - p1 + o)
         for (p0, p1), kk, o, d in zip(padding, k, op, rd)
     )
     if padding_mode != "zeros":
-        pre_dilation_padding = tuple(
-            (math.ceil(p_l / s), math.ceil(p_r / s)) for (p_l, p_r), s in zip(padding_t, st)
+        pre_dilation_padding = tuple(  # _conv.py:420-426: ceil(transpose_padding / stride)
+            ((p_l + (s - 1)) // s, (p_r + (s - 1)) // s) for (p_l, p_r), s in zip(padding_t, st)
         )
-        post = tuple(
-            (p_l - pd_l * s, p_r - pd_r * s)
-            for (p_l, p_r), (pd_l, pd_r), s in zip(padding_t, pre_dilation_padding, st)
+        post = tuple(  # _conv.py:428-436: from the module's own `padding`, NOT the transpose padding
+            (p_l - pd_l * s, p_r - pd_r * s + o)
+            for (p_l, p_r), (pd_l, pd_r), s, o in zip(padding, pre_dilation_padding, st, op)
         )
         x = pad_boundary(x, pre_dilation_padding, padding_mode, D)
     else:
-        post = padding_t
+        post = tuple((p_l, p_r + o) for (p_l, p_r), o in zip(padding, op))  # _conv.py:448-455
     y = conv_general_dilated(x, weight, (1,) * D, post, st, rd, groups)
     if bias is not None:
         y = y + bias.reshape((-1,) + (1,) * D).astype(y.dtype)

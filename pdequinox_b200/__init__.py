@@ -5,10 +5,12 @@ reference; all arithmetic runs in libpdeqx_b200.so (hand-written CUDA). There is
 from . import arch, blocks, conv, nn, random, train  # noqa: F401
 from ._module import (count_parameters, get_precision, set_precision, tree_leaves, tree_paths, vmap,  # noqa: F401
                       Module)
+from ._hierarchical import Hierarchical  # noqa: F401
 from ._sequential import Sequential  # noqa: F401
 from ._utils import sum_receptive_fields  # noqa: F401
-from .arch import ClassicFNO, ClassicResNet, DilatedResNet  # noqa: F401
+from .arch import ClassicFNO, ClassicResNet, ClassicUNet, DilatedResNet  # noqa: F401
 from .blocks import *  # noqa: F401,F403
-from .conv import MorePaddingConv, PhysicsConv, PointwiseLinearConv, SpectralConv  # noqa: F401
+from .conv import (MorePaddingConv, MorePaddingConvTranspose, PhysicsConv, PhysicsConvTranspose,  # noqa: F401
+                   PointwiseLinearConv, SpectralConv)
 
 __version__ = "0.1.0"

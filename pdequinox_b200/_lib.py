@@ -34,6 +34,14 @@ class ConvDesc(C.Structure):
                 ("pad_lo", C.c_int32 * MAX_DIMS), ("pad_hi", C.c_int32 * MAX_DIMS), ("boundary", C.c_int32)]
 
 
+class ConvTDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("batch", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32),
+                ("groups", C.c_int32), ("spatial", C.c_int32 * MAX_DIMS), ("kernel", C.c_int32 * MAX_DIMS),
+                ("stride", C.c_int32 * MAX_DIMS), ("dilation", C.c_int32 * MAX_DIMS),
+                ("pad_lo", C.c_int32 * MAX_DIMS), ("pad_hi", C.c_int32 * MAX_DIMS),
+                ("output_padding", C.c_int32 * MAX_DIMS), ("boundary", C.c_int32)]
+
+
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 
@@ -63,6 +71,12 @@ PROTOTYPES = {
     "pdeqx_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "pdeqx_conv_bwd_filter": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
+    "pdeqx_convT_out_spatial": (C.c_int, [C.POINTER(ConvTDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
+    "pdeqx_convT_fwd": (C.c_int, [C.POINTER(ConvTDesc), _P, _P, _P, _P, _P]),
+    "pdeqx_convT_bwd_data": (C.c_int, [C.POINTER(ConvTDesc), _P, _P, _P, _P]),
+    "pdeqx_convT_bwd_filter": (C.c_int, [C.POINTER(ConvTDesc), _P, _P, _P, _P, _P]),
+    "pdeqx_concat_channels": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P]),
+    "pdeqx_split_channels": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P]),
     "pdeqx_groupnorm_workspace_bytes": (C.c_size_t, [_I32, _I32]),
     "pdeqx_groupnorm_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _F, _P, _P, _P, _P]),
     "pdeqx_groupnorm_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

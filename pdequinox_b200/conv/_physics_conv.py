@@ -133,3 +133,103 @@ class PhysicsConv(MorePaddingConv):
                          groups=groups, use_bias=use_bias, padding_mode=padding_mode, key=key, **kwargs)
         if use_bias and zero_bias_init:  # _physics_conv.py:117-118
             self.bias = to_param(np.zeros(tuple(self.bias.shape), np.float32))
+
+
+class MorePaddingConvTranspose(Module):
+    """General N-D transposed convolution with the reference's semantics (_conv.py:233-471): the weight
+    (C_out, C_in/groups, *k) is used as is in a stride-1 correlation over the boundary-padded, stride-dilated input."""
+    _fields = ("weight", "bias")
+
+    def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, padding=0,
+                 padding_mode="zeros", output_padding=0, dilation=1, groups=1, use_bias=True, *, key, **kwargs):
+        self.num_spatial_dims = num_spatial_dims
+        self.kernel_size = _ntuple(kernel_size, num_spatial_dims, "kernel_size")
+        self.stride = _ntuple(stride, num_spatial_dims, "stride")
+        self.output_padding = _ntuple(output_padding, num_spatial_dims, "output_padding")
+        self.dilation = _ntuple(dilation, num_spatial_dims, "dilation")
+        if self.output_padding >= self.stride and any(o >= s for o, s in zip(self.output_padding, self.stride)):
+            raise ValueError("Must have `output_padding < stride` (elementwise).")  # _conv.py:333-335
+        if isinstance(padding, int):
+            self.padding = tuple((padding, padding) for _ in range(num_spatial_dims))
+        elif isinstance(padding, (tuple, list)) and len(padding) == num_spatial_dims:
+            self.padding = tuple((p, p) if isinstance(p, int) else tuple(p) for p in padding)
+        else:  # _conv.py:365-369
+            raise ValueError(f"`padding` must either be an int or tuple of length {num_spatial_dims} containing ints or tuples of length 2.")
+        if padding_mode not in _PADDING_MODES:
+            raise ValueError("`padding_mode` must be one of ['zeros', 'reflect', 'replicate', 'circular']")
+        self.padding_mode = padding_mode
+        self.in_channels, self.out_channels, self.groups, self.use_bias = in_channels, out_channels, groups, use_bias
+        wkey, bkey = jr.split(key, 2)  # _conv.py:321
+        cig = in_channels // groups
+        lim = 1.0 / math.sqrt(cig * math.prod(self.kernel_size))  # _conv.py:337-352
+        self.weight = to_param(jr.uniform(wkey, (out_channels, cig) + self.kernel_size, -lim, lim))
+        self.bias = to_param(jr.uniform(bkey, (out_channels,) + (1,) * num_spatial_dims, -lim, lim)) if use_bias else None
+
+    @property
+    def receptive_field(self):  # _conv.py:473-482
+        return tuple((float(((k - 1) // 2) * d), float((k // 2) * d)) for k, d in zip(self.kernel_size, self.dilation))
+
+    def _desc(self, x):
+        D = self.num_spatial_dims
+        if x.ndim != D + 2:
+            raise ValueError(f"Input to `ConvTranspose` needs to have rank {D + 1}, but input has shape {tuple(x.shape[1:])}.")
+        if x.shape[1] != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[1]}")
+        d = _lib.ConvTDesc()
+        d.ndim, d.batch, d.c_in, d.c_out, d.groups = D, x.shape[0], self.in_channels, self.out_channels, self.groups
+        d.spatial = _lib.ivec(x.shape[2:], 1)
+        d.kernel = _lib.ivec(self.kernel_size, 1)
+        d.stride = _lib.ivec(self.stride, 1)
+        d.dilation = _lib.ivec(self.dilation, 1)
+        d.pad_lo = _lib.ivec([p[0] for p in self.padding], 0)
+        d.pad_hi = _lib.ivec([p[1] for p in self.padding], 0)
+        d.output_padding = _lib.ivec(self.output_padding, 0)
+        d.boundary = _PADDING_MODES[self.padding_mode]
+        out = (_lib.C.c_int32 * _lib.MAX_DIMS)()
+        _lib.check(_lib.lib().pdeqx_convT_out_spatial(d, out))
+        return d, tuple(out[a] for a in range(D))
+
+    def _fwd(self, x, tape):
+        d, out_sp = self._desc(x)
+        y = new_buf(tape, self, "y", (x.shape[0], self.out_channels) + out_sp)
+        _lib.check(_lib.lib().pdeqx_convT_fwd(d, _lib.ptr(x), _lib.ptr(self.weight), _lib.ptr(self.bias), _lib.ptr(y),
+                                              _lib.stream()))
+        if tape is not None:
+            tape.push(x)
+        return y
+
+    def _bwd(self, gy, tape, need_gx=True):
+        x = tape.pop()
+        d, _ = self._desc(x)
+        L = _lib.lib()
+        gb = self.grad("bias") if self.bias is not None else None
+        _lib.check(L.pdeqx_convT_bwd_filter(d, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(self.grad("weight")), _lib.ptr(gb),
+                                            _lib.stream()))
+        if not need_gx:
+            return None
+        gx = new_buf(tape, self, "gx", x.shape)
+        _lib.check(L.pdeqx_convT_bwd_data(d, _lib.ptr(gy), _lib.ptr(self.weight), _lib.ptr(gx), _lib.stream()))
+        return gx
+
+
+class PhysicsConvTranspose(MorePaddingConvTranspose):
+    """_physics_conv.py:121-236."""
+
+    def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, output_padding=0, dilation=1,
+                 groups=1, use_bias=True, *, key, boundary_mode, zero_bias_init=False, **kwargs):
+        self.boundary_mode = boundary_mode.lower()
+        if self.boundary_mode == "periodic":
+            padding_mode = "circular"
+        elif self.boundary_mode == "dirichlet":
+            padding_mode = "zeros"
+        elif self.boundary_mode == "neumann":
+            padding_mode = "reflect"
+        else:  # _physics_conv.py:211-215
+            raise ValueError(f"Only 'periodic', 'dirichlet', 'neumann' boundary modes are supported, got {boundary_mode}")
+        super().__init__(num_spatial_dims=num_spatial_dims, in_channels=in_channels, out_channels=out_channels,
+                         kernel_size=kernel_size, stride=stride,
+                         padding=compute_same_padding(num_spatial_dims, kernel_size, dilation),
+                         padding_mode=padding_mode, output_padding=output_padding, dilation=dilation, groups=groups,
+                         use_bias=use_bias, key=key, **kwargs)
+        if use_bias and zero_bias_init:  # _physics_conv.py:233-234
+            self.bias = to_param(np.zeros(tuple(self.bias.shape), np.float32))

@@ -154,6 +154,36 @@ for mode in ("periodic", "dirichlet", "neumann"):
 kw = dict(num_spatial_dims=1, in_channels=1, out_channels=1, hidden_channels=4, num_levels=2, boundary_mode="dirichlet")
 record("arch_unet_1d_dirichlet", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=key), rng.standard_normal((1, 32)))
 
+# ---- round-1 widening: UNet path (appended after the original cases so that their random streams are unchanged) ----
+i = 4
+for D, ci, co, spatial, k, stride, op, dil in [(1, 2, 2, (8,), 4, 2, 1, 1), (1, 2, 3, (10,), 5, 2, 1, 1), (2, 2, 3, (6, 6), 3, 2, 0, 1),
+                                               (1, 2, 2, (9,), 3, 2, 1, 2), (1, 3, 2, (12,), 2, 3, 2, 1), (2, 2, 2, (5, 6), (3, 4), (2, 1), (1, 0), 1)]:
+    for mode in ("periodic", "dirichlet", "neumann"):
+        kw = dict(num_spatial_dims=D, in_channels=ci, out_channels=co, kernel_size=k, stride=stride, output_padding=op,
+                  dilation=dil, boundary_mode=mode)
+        m = ref.conv.PhysicsConvTranspose(**kw, key=key)
+        record(f"convT_{i}_{mode}", "PhysicsConvTranspose", kw, m, rng.standard_normal((ci,) + spatial))
+    i += 1
+for mode in ("periodic", "dirichlet", "neumann"):
+    for use_norm in (False, True):
+        kw = dict(num_spatial_dims=2, in_channels=3, out_channels=4, boundary_mode=mode, use_norm=use_norm)
+        record(f"block_double_{mode}_{int(use_norm)}", "ClassicDoubleConvBlock", kw,
+               ref.blocks.ClassicDoubleConvBlock(**kw, key=key), rng.standard_normal((3, 9, 10)), {"activation": "relu"})
+    kw = dict(num_spatial_dims=1, in_channels=3, out_channels=3, boundary_mode=mode)
+    record(f"block_down_{mode}", "LinearConvDownBlock", kw, ref.blocks.LinearConvDownBlock(**kw, key=key), rng.standard_normal((3, 16)))
+    kw = dict(num_spatial_dims=1, in_channels=4, out_channels=2, boundary_mode=mode)
+    record(f"block_up_{mode}", "LinearConvUpBlock", kw, ref.blocks.LinearConvUpBlock(**kw, key=key), rng.standard_normal((4, 8)))
+for mode in ("periodic", "neumann"):
+    kw = dict(num_spatial_dims=1, in_channels=1, out_channels=1, hidden_channels=4, num_levels=2, boundary_mode=mode)
+    record(f"arch_unet_1d_{mode}", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=key), rng.standard_normal((1, 32)))
+for mode in ("periodic", "dirichlet", "neumann"):
+    kw = dict(num_spatial_dims=2, in_channels=2, out_channels=1, hidden_channels=4, num_levels=2, boundary_mode=mode)
+    record(f"arch_unet_2d_{mode}", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=key), rng.standard_normal((2, 16, 12)))
+kw = dict(num_spatial_dims=1, in_channels=1, out_channels=1, boundary_mode="dirichlet")  # BASELINE.json configs[1]: README defaults
+record("arch_unet_1d_readme", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=key), rng.standard_normal((1, 64)))
+kw = dict(num_spatial_dims=1, in_channels=1, out_channels=1, hidden_channels=4, num_levels=1, use_norm=False, boundary_mode="dirichlet")
+record("arch_unet_1d_nonorm", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=key), rng.standard_normal((1, 16)))
+
 # ---- parameter counts computed by the reference's own count_parameters ----
 counts = {}
 for nm, ctor in [("ClassicFNO", ref.arch.ClassicFNO), ("ClassicResNet", ref.arch.ClassicResNet),

@@ -35,7 +35,8 @@ def oracle_eval(case, x, p):
                                dilation=kw["dilation"], groups=kw["groups"])
     elif kind == "PhysicsConvTranspose":
         y = oconv.physics_conv_transpose(xb, p["weight"], p.get("bias"), boundary_mode=kw["boundary_mode"],
-                                         stride=kw["stride"], output_padding=kw["output_padding"])
+                                         stride=kw["stride"], output_padding=kw["output_padding"],
+                                         dilation=kw.get("dilation", 1))
     elif kind == "PointwiseLinearConv":
         y = oconv.pointwise_conv(xb, p["weight"], p.get("bias"))
     elif kind == "ClassicSpectralBlock":
@@ -59,7 +60,14 @@ def oracle_eval(case, x, p):
         y = onn.sequential_forward(p, xb, lambda h, pre: onn.dilated_block_any(h, p, pre, kw["boundary_mode"], "relu", D),
                                    kw.get("num_blocks", 2))
     elif kind == "ClassicUNet":
-        y = onn.unet_forward(p, xb, kw["boundary_mode"], kw["num_levels"])
+        y = onn.unet_forward(p, xb, kw["boundary_mode"], kw.get("num_levels", 4))
+    elif kind == "ClassicDoubleConvBlock":
+        y = onn.double_conv_block(xb, p, "", kw["boundary_mode"], case["activation"], kw["num_spatial_dims"])
+    elif kind == "LinearConvDownBlock":
+        y = oconv.physics_conv(xb, p["weight"], p.get("bias"), boundary_mode=kw["boundary_mode"], stride=2)
+    elif kind == "LinearConvUpBlock":
+        y = oconv.physics_conv_transpose(xb, p["weight"], p.get("bias"), boundary_mode=kw["boundary_mode"], stride=2,
+                                         output_padding=1)
     else:
         raise KeyError(kind)
     return y[0]

@@ -11,7 +11,8 @@ from conftest import rel_l2
 pytestmark = pytest.mark.gpu
 
 SUPPORTED = {"SpectralConv", "SpectralConvRaw", "PhysicsConv", "PointwiseLinearConv", "ClassicSpectralBlock",
-             "ClassicResBlock", "DilatedResBlock", "ClassicFNO", "ClassicResNet", "DilatedResNet"}
+             "ClassicResBlock", "DilatedResBlock", "ClassicFNO", "ClassicResNet", "DilatedResNet", "PhysicsConvTranspose",
+             "ClassicDoubleConvBlock", "LinearConvDownBlock", "LinearConvUpBlock", "ClassicUNet"}
 CASES = [c for c in gc.CASES if c["kind"] in SUPPORTED]
 
 
@@ -26,11 +27,15 @@ def build(case, p):
     cls = {"SpectralConv": pdeqx.SpectralConv, "PhysicsConv": pdeqx.PhysicsConv, "PointwiseLinearConv": pdeqx.PointwiseLinearConv,
            "ClassicSpectralBlock": pdeqx.blocks.ClassicSpectralBlock, "ClassicResBlock": pdeqx.blocks.ClassicResBlock,
            "DilatedResBlock": pdeqx.blocks.DilatedResBlock, "ClassicFNO": pdeqx.arch.ClassicFNO,
-           "ClassicResNet": pdeqx.arch.ClassicResNet, "DilatedResNet": pdeqx.arch.DilatedResNet}[kind]
+           "ClassicResNet": pdeqx.arch.ClassicResNet, "DilatedResNet": pdeqx.arch.DilatedResNet,
+           "PhysicsConvTranspose": pdeqx.PhysicsConvTranspose, "ClassicDoubleConvBlock": pdeqx.blocks.ClassicDoubleConvBlock,
+           "LinearConvDownBlock": pdeqx.blocks.LinearConvDownBlock, "LinearConvUpBlock": pdeqx.blocks.LinearConvUpBlock,
+           "ClassicUNet": pdeqx.arch.ClassicUNet}[kind]
     if isinstance(kw.get("kernel_size"), list):
         kw["kernel_size"] = tuple(kw["kernel_size"])
-    if isinstance(kw.get("stride"), list):
-        kw["stride"] = tuple(kw["stride"])
+    for name in ("stride", "output_padding"):
+        if isinstance(kw.get(name), list):
+            kw[name] = tuple(kw[name])
     return cls(**kw, key=0)
 
 

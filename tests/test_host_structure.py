@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_shared_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "pdeqx_b200.h")).read()
-    declared = set(re.findall(r"\b(pdeqx_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(pdeqx_[A-Za-z0-9_]+)\s*\(", header))
     assert len(declared) >= 25
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in sorted(declared):
@@ -43,6 +43,10 @@ def test_no_cpu_fallback_without_cuda():
     (lambda: pdeqx.ClassicFNO(2, 1, 1, hidden_channels=64, num_modes=16, key=0), 16794049),   # BASELINE configs[3]
     (lambda: pdeqx.ClassicResNet(2, 1, 1, hidden_channels=64, key=0), 443329),                # BASELINE configs[2]
     (lambda: pdeqx.DilatedResNet(2, 1, 1, hidden_channels=64, key=0), 518977),
+    (lambda: pdeqx.ClassicUNet(1, 1, 1, key=0), 789089),           # README defaults (SURVEY.md 8d cfg 2)
+    (lambda: pdeqx.ClassicUNet(1, 1, 1, hidden_channels=32, num_levels=2, boundary_mode="dirichlet", key=0), 189633),  # train_unet_as_poisson_solver.ipynb:225-235
+    (lambda: pdeqx.ClassicUNet(2, 1, 1, key=0), 2357441),
+    (lambda: pdeqx.ClassicUNet(3, 1, 1, key=0), 7062497),
 ])
 def test_parameter_counts_match_reference(ctor, expect):
     assert pdeqx.count_parameters(ctor()) == expect
@@ -77,6 +81,28 @@ def test_leaf_order_matches_reference_pytree():
     assert pdeqx.tree_paths(r)[2:10] == [
         "blocks.0.conv_1.weight", "blocks.0.conv_1.bias", "blocks.0.norm_1.weight", "blocks.0.norm_1.bias",
         "blocks.0.conv_2.weight", "blocks.0.conv_2.bias", "blocks.0.norm_2.weight", "blocks.0.norm_2.bias"]
+
+
+def test_unet_leaf_order_and_shared_arc_keys():
+    m = pdeqx.ClassicUNet(1, 1, 1, hidden_channels=4, num_levels=2, key=0)
+    paths = pdeqx.tree_paths(m)
+    # dataclass-field order of Hierarchical (_hierarchical.py:21-30): lifting, down, left, up, right, projection
+    first = [p.split(".")[0] for p in paths]
+    order = [k for i, k in enumerate(first) if i == 0 or first[i - 1] != k]
+    assert order == ["lifting", "down_sampling_blocks", "left_arc_blocks", "up_sampling_blocks", "right_arc_blocks",
+                     "projection"]
+    assert "left_arc_blocks.1.0.conv_2.weight" in paths and "right_arc_blocks.0.0.norm_1.bias" in paths
+    assert tuple(m.up_sampling_blocks[1].weight.shape) == (8, 16, 3)       # fan_out -> fan_out // 2, weight (C_out, C_in, k)
+    assert tuple(m.right_arc_blocks[1][0].conv_1.weight.shape) == (8, 16, 3)  # concat(skip 8, up 8) -> 8
+    assert m.down_sampling_blocks[0].stride == (2,) and m.up_sampling_blocks[0].output_padding == (1,)
+    # every block of one arc is built from the same key (_hierarchical.py:196,208): identical initial weights
+    h = pdeqx.Hierarchical(1, 1, 1, hidden_channels=4, num_levels=1, num_blocks=3, activation=pdeqx.nn.relu, key=0,
+                           boundary_mode="periodic")
+    a, b = h.left_arc_blocks[0][1], h.left_arc_blocks[0][2]
+    assert bool((a.conv_1.weight == b.conv_1.weight).all())
+    assert pdeqx.ClassicUNet(1, 1, 1, key=0).receptive_field == tuple(pdeqx.ClassicUNet(1, 1, 1, key=1).receptive_field)
+    with pytest.raises(ValueError):  # _physics_conv.py:211-215
+        pdeqx.PhysicsConvTranspose(1, 1, 1, 3, key=0, boundary_mode="robin")
 
 
 def test_constructor_signatures_and_errors():
