@@ -13,6 +13,7 @@
 // stage to the tcgen05 kernels (tc_spectral.cu) when the shape allows and to the
 // fp32 CUDA-core GEMMs (gemm_generic.cu) otherwise.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -226,14 +227,14 @@ struct Regions {
 
 // x_hat[B, C, J] <- x[B, C, *S]. Intermediates live in r.big[]; src/dst must not alias them.
 static int forward_chain(const pdeqx_spectral_plan* p, const float* x, int C, bool adjoint_of_inverse, float* dst,
-                         const Regions& r, cudaStream_t s) {
+                         const Regions& r, cudaStream_t s, bool r2c_done = false) {
   const pdeqx_spectral_desc& d = p->desc;
   const int D = d.ndim;
   const int mD = d.modes[D - 1];
   const int64_t BC = (int64_t)d.batch * C;
   const float* tab_last = adjoint_of_inverse ? p->t_r2c_bwd : p->t_r2c_fwd;
   float* o = (D == 1) ? dst : r.big[0];
-  PDEQX_TRY(stage_r2c(p, x, tab_last, BC * p->lead, o, s));
+  if (!r2c_done) PDEQX_TRY(stage_r2c(p, x, tab_last, BC * p->lead, o, s));  // else: the caller already filled `o`
   const float* cur = o;
   int nb = 1;
   // axes D-2 .. 0; at axis a the leading axes a' < a are still full-size, trailing ones are truncated
@@ -268,6 +269,19 @@ static int inverse_chain(const pdeqx_spectral_plan* p, const float* yhat, int C,
     cur = dstage;
   }
   return PDEQX_OK;
+}
+
+// Samples per chunk of the L2-blocked front of the backward pass (0 = unchunked; experiment knob PDEQX_BWD_CHUNK).
+static int bwd_chunk_samples(const pdeqx_spectral_plan* p, int64_t n_pix) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("PDEQX_BWD_CHUNK");
+    env = e ? atoi(e) : -1;
+  }
+  (void)n_pix;
+  // Measured on B200 (configs[3], B = 64): 1.71 ms unchunked vs 1.87 / 2.08 / 2.48 / 3.13 ms at 16 / 8 / 4 / 2 samples per
+  // chunk -- the fixed cost of three persistent-kernel launches per chunk outweighs the L2 hits, so the default is off.
+  return env > 0 && env < p->desc.batch ? env : 0;
 }
 
 static int check_ws(const pdeqx_spectral_plan* p, void* ws, size_t ws_bytes) {
@@ -348,9 +362,41 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
   const int64_t rows_i = (int64_t)d.batch * d.c_in * p->lead;
   Regions r = make_regions(p, workspace);
 
-  // 1. cotangent of the pre-activation (pre-activation recomputed from the saved z: nothing full-size is kept)
   const bool fast = tc_slab_available(p, bypass_w != nullptr);
   const float* gpre = gy;
+  bool gx_has_bypass = false;
+  const bool fuse_bypass_gx = fast && bypass_w && gx;
+  bool r2c_done = false;
+  const int chunk = bwd_chunk_samples(p, n_pix);
+  if (fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
+    // Steps 1-3a in sample chunks small enough for the 126 MB L2: the cotangent chunk written by the slab kernel is
+    // still L2-resident when the bypass weight gradient and the first DFT stage read it back, and so is most of x.
+    PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
+    const int mD = d.modes[D - 1];
+    float* x1 = (D == 1) ? r.mode[0] : r.big[0];
+    float* gb = bypass_b ? g_bypass_b : nullptr;
+    PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));
+    if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)d.c_out, s));
+    for (int b0 = 0; b0 < d.batch; b0 += chunk) {
+      pdeqx_spectral_plan pc = *p;  // shallow copy: same tables, fewer samples
+      pc.desc.batch = d.batch - b0 < chunk ? d.batch - b0 : chunk;
+      const int64_t off_o = (int64_t)b0 * d.c_out * n_pix, off_i = (int64_t)b0 * d.c_in * n_pix;
+      const int64_t off_z = (int64_t)b0 * d.c_out * p->lead * 2 * mD;
+      {
+        TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+        PDEQX_TRY(tc_slab_ex(&pc, x + off_i, saved_z + off_z, 0, bypass_w, false, bypass_b, act, /*mode=*/1, gy + off_o,
+                             d.c_in, d.c_out, scratch_full + off_o, s));
+      }
+      {
+        TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
+        PDEQX_TRY(tc_wgrad(&pc, scratch_full + off_o, x + off_i, n_pix, g_bypass_w, gb, s));
+      }
+      PDEQX_TRY(stage_r2c(p, scratch_full + off_o, p->t_r2c_bwd, (int64_t)pc.desc.batch * d.c_out * p->lead, x1 + off_z, s));
+    }
+    gpre = scratch_full;
+    r2c_done = true;
+  } else {
+  // 1. cotangent of the pre-activation (pre-activation recomputed from the saved z: nothing full-size is kept)
   if (act != PDEQX_ACT_IDENTITY) {
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
     if (fast) {
@@ -366,8 +412,6 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
     gpre = scratch_full;
   }
   // 2. bypass grads (and the bypass part of gx; on the tcgen05 path that part is fused into step 7)
-  bool gx_has_bypass = false;
-  const bool fuse_bypass_gx = fast && bypass_w && gx;
   if (bypass_w) {
     if (fast && tc_wgrad_available(p, n_pix)) {
       TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
@@ -381,9 +425,10 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
       gx_has_bypass = gx != nullptr && !fuse_bypass_gx;
     }
   }
+  }
   // 3. g_yhat = adjoint of the inverse transform applied to gpre
   float* ghat = r.mode[0];
-  PDEQX_TRY(forward_chain(p, gpre, d.c_out, /*adjoint_of_inverse=*/true, ghat, r, s));
+  PDEQX_TRY(forward_chain(p, gpre, d.c_out, /*adjoint_of_inverse=*/true, ghat, r, s, r2c_done));
   // 4. weight gradient (batch-reduced inside the kernel)
   PDEQX_TRY(mode_mix_dw(p, ghat, saved_xhat, gw_re, gw_im, s));
   if (!gx) return PDEQX_OK;
