@@ -35,6 +35,19 @@ static void cs(int64_t k, int64_t n, int64_t s, double* c, double* sn) {
   *sn = sin(ang);
 }
 
+// Where the first stage of the adjoint-of-inverse transform of the reverse pass runs (PDEQX_FUSE_R2C):
+//   1 (default) = inside the bypass weight-gradient kernel, which streams the same cotangent tile (-131 us per block at
+//   configs[3]); 0 = its own kernel. A third variant (inside the epilogue of the slab kernel that produces the cotangent,
+//   as per-w-tile partial sums) was measured slower (+159 us in the slab kernel for -190 us) and removed.
+static int fuse_r2c_mode() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PDEQX_FUSE_R2C");
+    env = e ? atoi(e) : 1;
+  }
+  return env;
+}
+
 template <class T>
 static int upload(const std::vector<T>& h, T** d) {
   PDEQX_CUDA(cudaMalloc((void**)d, h.size() * sizeof(T)));
@@ -226,6 +239,7 @@ struct Regions {
 };
 
 // x_hat[B, C, J] <- x[B, C, *S]. Intermediates live in r.big[]; src/dst must not alias them.
+// r2c_done: the first stage was already computed into the chain's first buffer (fused into another pass over x).
 static int forward_chain(const pdeqx_spectral_plan* p, const float* x, int C, bool adjoint_of_inverse, float* dst,
                          const Regions& r, cudaStream_t s, bool r2c_done = false) {
   const pdeqx_spectral_desc& d = p->desc;
@@ -418,7 +432,13 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
       PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));
       float* gb = bypass_b ? g_bypass_b : nullptr;
       if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)d.c_out, s));
-      PDEQX_TRY(tc_wgrad(p, gpre, x, n_pix, g_bypass_w, gb, s));
+      // step 3a rides along: the kernel that streams gpre for the weight gradient also applies the first DFT stage
+      float* x1 = nullptr;
+      if (fuse_r2c_mode() == 1 && tc_wgrad_r2c_available(p)) {
+        x1 = (D == 1) ? r.mode[0] : r.big[0];
+        r2c_done = true;
+      }
+      PDEQX_TRY(tc_wgrad(p, gpre, x, n_pix, g_bypass_w, gb, s, x1));
     } else {
       PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, gpre, fuse_bypass_gx ? nullptr : gx,
                                     g_bypass_w, bypass_b ? g_bypass_b : nullptr, stream));

@@ -61,6 +61,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);
 // gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller)
 int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb,
-             cudaStream_t s);
+             cudaStream_t s, float* x1_out = nullptr);
+bool tc_wgrad_r2c_available(const pdeqx_spectral_plan* p);
 
 }  // namespace pdeqx

@@ -13,6 +13,7 @@
 // more than one output tile per CTA). They are HBM-bound by construction (16-36 flop/B, SURVEY.md
 // App. B): the tensor pipe only has to stay under the memory time, which CUDA-core FFMA cannot.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -125,6 +126,7 @@ struct SlabParams {
 // smem carve-up (all tile regions 1024-B aligned)
 struct SlabSmem {
   uint32_t tab_off, w_off, stage_off, stage_bytes, x_box_bytes, z_off_in_stage, epi_off, epi_buf_bytes, epi_bufs, bar_off, total;
+  uint32_t chunk_bytes;
 };
 
 static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, int epi_bufs = 2) {
@@ -141,10 +143,12 @@ static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, i
   s.stage_bytes = (s.stage_bytes + 1023) & ~1023u;
   s.stage_off = off;
   off += s.stage_bytes * stages;
-  // epilogue staging: per half of the output channels, two [c_out/2 x 128 w] fp32 tiles (TMA store source / aux target)
+  // epilogue staging: `epi_bufs` output tiles [c_out x 128 w] fp32 (TMA store source / aux target), each stored as four
+  // SWIZZLE_128B chunks [c_out rows x 32 w]: every epilogue warp owns one 128-byte-row box per half (its own TMA box)
   s.epi_off = off;
-  s.epi_buf_bytes = (uint32_t)(c_out / 2) * 512;
-  off += 2 * (uint32_t)epi_bufs * s.epi_buf_bytes;
+  s.chunk_bytes = (uint32_t)c_out * 128;
+  s.epi_buf_bytes = 4 * s.chunk_bytes;
+  off += (uint32_t)epi_bufs * s.epi_buf_bytes;
   s.epi_bufs = (uint32_t)epi_bufs;
   s.bar_off = off;
   off += 1024;  // barriers, tmem pointer, bias
@@ -166,8 +170,8 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint64_t* tempty = bars + 18;            // [2]
   uint64_t* tabfull = bars + 20;           // [1]
   uint32_t* tmem_ptr = (uint32_t*)(bars + 22);
-  uint64_t* auxfull = bars + 24;           // [2 halves][up to 3 buffers]
-  float* bias_s = (float*)(bars + 30);     // [c_out] (<= 128 floats)
+  uint64_t* auxfull = bars + 24;           // [8 epilogue warps][3 buffers] cotangent chunk landed (MODE 1)
+  float* bias_s = (float*)(bars + 48);     // [c_out] (<= 128 floats)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -188,7 +192,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     mbar_init(&tempty[0], 8);
     mbar_init(&tempty[1], 8);
     mbar_init(tabfull, 1);
-    for (int i = 0; i < 6; ++i) mbar_init(&auxfull[i], 1);
+    for (int i = 0; i < 24; ++i) mbar_init(&auxfull[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -267,25 +271,26 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> smem tile -> TMA store =====================
-    // Two groups of 4 warps (one per half of the output channels). A group owns two [ncol x 128 w] smem
-    // tiles; in mode 1 the cotangent tile is TMA-loaded into the tile first and updated in place.
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    // Eight autonomous warps: warp (half, q) owns the [c_out/2 channels x 32 w] piece of the output tile that its TMEM
+    // lane quarter produces -- one swizzled 128-byte-row box. It fills the piece, stores it with its own TMA store and
+    // (mode 1) prefetches its own piece of the cotangent tile two units ahead: no CTA-level barrier in the loop.
+    // The tile [c_out x 128 w] is laid out as four SWIZZLE_128B chunks [c_out rows x 32 w].
+    const int q = warp & 3;            // TMEM lane quarter this warp may read = 32-w chunk of the tile
     const int half = (warp - 4) >> 2;  // which half of the output channels
     const int ncol = p.c_out / 2;
-    const bool leader = (q == 0 && lane == 0);
-    const int NB = (int)L.epi_bufs;  // 2 (MODE 0) or 3 (MODE 1: the cotangent tile is prefetched two units ahead)
-    uint8_t* ebuf0 = smem + L.epi_off + (size_t)half * NB * L.epi_buf_bytes;
-    uint64_t* afull = auxfull + half * 3;
+    const int NB = (int)L.epi_bufs;  // 2 (MODE 0) or 3 (MODE 1: the cotangent piece is prefetched two units ahead)
+    uint8_t* ebuf0 = smem + L.epi_off + (size_t)q * L.chunk_bytes + (size_t)half * ncol * 128;  // this warp's piece in buffer 0
+    uint64_t* afull = auxfull + (half * 4 + q) * 3;
     int a = 0, e = 0;
     uint32_t aph = 0, eph = 0;
     auto load_aux = [&](int64_t un, int buf) {
       const int wtn = (int)(un % p.wt_per_row);
       const int64_t bln = un / p.wt_per_row;
-      mbar_expect_tx(&afull[buf], L.epi_buf_bytes);
-      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], wtn * 128, (int)(bln % p.lead),
+      mbar_expect_tx(&afull[buf], (uint32_t)ncol * 128);
+      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], wtn * 128 + q * 32, (int)(bln % p.lead),
                   (int)(bln / p.lead) * p.c_out + half * ncol);
     };
-    if (MODE == 1 && leader) {
+    if (MODE == 1 && lane == 0) {
       if (first < p.units) load_aux(first, 0);
       if (first + stride < p.units) load_aux(first + stride, 1);
     }
@@ -294,18 +299,20 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int64_t bl = u / p.wt_per_row;
       const int l = (int)(bl % p.lead);
       const int b = (int)(bl / p.lead);
-      float* tile = (float*)(ebuf0 + (size_t)e * L.epi_buf_bytes);
+      uint8_t* piece = ebuf0 + (size_t)e * L.epi_buf_bytes;
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
       if (MODE == 1) {
         mbar_wait(&afull[e], eph);
       } else {
-        // the store that last used this tile (two units ago) must have finished reading it
-        if (leader) tma_store_wait_read<1>();
-        named_bar_sync(1 + half, 128);
+        // this warp's store that last used the piece (NB units ago) must have finished reading it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
       }
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.c_out + half * ncol);
-      const uint32_t col = smem_u32(tile) + (uint32_t)(q * 32 + lane) * 4;  // element (o_local, w) at tile[o_local * 128 + w]
+      // element (o_local, w = 32 q + lane): row o_local of the piece, 16-byte units XOR-swizzled by (row & 7)
+      const uint32_t col = smem_u32(piece);
+      const uint32_t lane_b = (uint32_t)lane * 4;
       for (int c0 = 0; c0 < ncol; c0 += 16) {
         float v[16];
         tmem_ld16(t0 + c0, v);
@@ -318,7 +325,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         float g[16];
         if (MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = ld_shared_f32(col + (uint32_t)(c0 + j) * 512);
+          for (int j = 0; j < 16; ++j) g[j] = ld_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)));
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -333,17 +340,17 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             else if (ACT == PDEQX_ACT_RELU) r = val > 0.f ? g[j] : 0.f;
             else r = g[j];
           }
-          st_shared_f32(col + (uint32_t)(c0 + j) * 512, r);
+          st_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
         }
       }
       fence_proxy_async();
-      named_bar_sync(1 + half, 128);
-      if (leader) {
-        tma_store_3d(&tm_y, tile, wt * 128, l, b * p.c_out + half * ncol);
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tm_y, piece, wt * 128 + q * 32, l, b * p.c_out + half * ncol);
         tma_store_commit();
         if (MODE == 1) {
           const int64_t un = u + 2 * stride;
-          if (un < p.units) {  // cotangent tile two units ahead, into the buffer whose store (previous unit) has drained
+          if (un < p.units) {  // cotangent piece two units ahead, into the buffer whose store (previous unit) has drained
             tma_store_wait_read<1>();
             load_aux(un, e == 0 ? NB - 1 : e - 1);
           }
@@ -352,7 +359,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (++a == 2) { a = 0; aph ^= 1; }
       if (++e == NB) { e = 0; eph ^= 1; }
     }
-    if (leader) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -494,29 +501,40 @@ r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
 // bypass weight gradient: gW[o,i] += sum_p g[o,p] x[i,p], gb[o] += sum_p g[o,p]   (per CTA partial, atomics)
 // ==========================================================================================
 struct WgradParams {
-  int c_out, c_in, chunks_per_b, stages;
-  int64_t units;  // batch * chunks_per_b (chunk = 32 pixels)
+  int c_out, c_in, chunks_per_row, lead, stages;
+  int64_t rows;  // batch * lead image rows; a unit = one row = chunks_per_row stages of 32 pixels
   float* gw;
   float* gb;
+  // fused first stage of the adjoint-of-inverse DFT of g (optional): x1[(b * c_out + o) * lead + l][0:32] = sum_w g[b,o,l,w] T[w,:]
+  float* x1;
 };
 
 __global__ void __launch_bounds__(kThreadsR2c, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, WgradParams p) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
+             const __grid_constant__ CUtensorMap tm_tab, WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  // stage = [g box: c_out x 128 B][x box: c_in x 128 B][ones: 16 x 128 B]; A = 128 rows from the g box on
+  // [r2c table: chunks_per_row x 4 KB (fused only)] [stages] ; stage = [g box: c_out x 128 B][x box: c_in x 128 B][ones: 16 x 128 B];
+  // A = 128 rows from the g box on
+  const bool fused = p.x1 != nullptr;
+  const uint32_t tab_bytes = fused ? (uint32_t)p.chunks_per_row * 4096 : 0;
+  uint8_t* stage0 = smem + tab_bytes;
   const uint32_t g_bytes = (uint32_t)p.c_out * 128, x_bytes = (uint32_t)p.c_in * 128;
   const uint32_t stage_bytes = g_bytes + x_bytes + 2048;
-  uint64_t* bars = (uint64_t*)(smem + (size_t)p.stages * stage_bytes + 16384);  // 16 KB slack: A tile of the last stage
+  uint64_t* bars = (uint64_t*)(stage0 + (size_t)p.stages * stage_bytes + 16384);  // 16 KB slack: A tile of the last stage
   uint64_t* full = bars;
   uint64_t* empty = bars + 16;
   uint64_t* done = bars + 32;
+  uint64_t* tabfull = bars + 33;
   uint32_t* tmem_ptr = (uint32_t*)(bars + 34);
+  uint64_t* x1full = bars + 36;   // [2]
+  uint64_t* x1empty = bars + 38;  // [2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_g);
     tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_tab);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -524,13 +542,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       mbar_init(&empty[i], 1);
     }
     mbar_init(done, 1);
+    mbar_init(tabfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x1full[i], 1);
+      mbar_init(&x1empty[i], 2);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
   // ones rows (bias-gradient columns) and a defined value everywhere an A/B descriptor can reach
   for (uint32_t i = threadIdx.x; i < ((uint32_t)S * stage_bytes + 16384) / 4; i += blockDim.x) {
     const uint32_t in_stage = (i * 4) % stage_bytes;
-    ((float*)smem)[i] = (i * 4 < (uint32_t)S * stage_bytes && in_stage >= g_bytes + x_bytes) ? 1.0f : 0.0f;
+    ((float*)stage0)[i] = (i * 4 < (uint32_t)S * stage_bytes && in_stage >= g_bytes + x_bytes) ? 1.0f : 0.0f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -539,46 +562,93 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
   const int64_t first = blockIdx.x, stride = gridDim.x;
   const int N = p.c_in + 16;
+  const int W = p.chunks_per_row * 32;
 
   if (warp == 0) {
     if (lane == 0) {
+      if (fused) {
+        mbar_expect_tx(tabfull, tab_bytes);
+        for (int c = 0; c < p.chunks_per_row; ++c) tma_load_2d(smem + c * 4096, &tm_tab, tabfull, c * 32, 0);
+      }
       int s = 0;
       uint32_t ph = 0;
-      for (int64_t u = first; u < p.units; u += stride) {
-        const int b = (int)(u / p.chunks_per_b);
-        const int c = (int)(u % p.chunks_per_b);
-        mbar_wait_backoff(&empty[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full[s], g_bytes + x_bytes);
-        tma_load_2d(st, &tm_g, &full[s], c * 32, b * p.c_out);
-        tma_load_2d(st + g_bytes, &tm_x, &full[s], c * 32, b * p.c_in);
-        if (++s == S) { s = 0; ph ^= 1; }
+      for (int64_t r = first; r < p.rows; r += stride) {
+        const int b = (int)(r / p.lead);
+        const int l = (int)(r % p.lead);
+        for (int c = 0; c < p.chunks_per_row; ++c) {
+          mbar_wait_backoff(&empty[s], ph ^ 1);
+          uint8_t* st = stage0 + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full[s], g_bytes + x_bytes);
+          tma_load_2d(st, &tm_g, &full[s], l * W + c * 32, b * p.c_out);
+          tma_load_2d(st + g_bytes, &tm_x, &full[s], l * W + c * 32, b * p.c_in);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(128, N, false, false);
-      int s = 0;
+      const uint32_t idesc2 = idesc_tf32(128, 32, false, false);
+      if (fused) mbar_wait(tabfull, 0);
+      int s = 0, it = 0;
       uint32_t ph = 0;
       bool acc = false;
-      for (int64_t u = first; u < p.units; u += stride) {
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          mma_tf32(tmem_base, smem_desc_sw128(st + k * 32, 0, 1024), smem_desc_sw128(st + g_bytes + k * 32, 0, 1024), idesc,
-                   acc);
-          acc = true;
+      for (int64_t r = first; r < p.rows; r += stride, ++it) {
+        const int a2 = it & 1;
+        if (fused) {
+          mbar_wait(&x1empty[a2], (((uint32_t)it >> 1) & 1) ^ 1);
+          tc_fence_after();
         }
-        mma_commit(&empty[s]);
-        if (++s == S) { s = 0; ph ^= 1; }
+        const uint32_t d2 = tmem_base + 128u + (uint32_t)(a2 * 32);
+        for (int c = 0; c < p.chunks_per_row; ++c) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_tf32(tmem_base, smem_desc_sw128(st + k * 32, 0, 1024), smem_desc_sw128(st + g_bytes + k * 32, 0, 1024), idesc,
+                     acc);
+            acc = true;
+          }
+          if (fused) {
+            // same A rows (g rows 0..c_out-1 are the ones kept), B = table chunk [32 k x 32 w] of this pixel chunk
+            const uint32_t tb = smem_u32(smem + c * 4096);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_tf32(d2, smem_desc_sw128(st + k * 32, 0, 1024), smem_desc_sw128(tb + k * 32, 0, 1024), idesc2, (c | k) != 0);
+          }
+          mma_commit(&empty[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        if (fused) mma_commit(&x1full[a2]);
       }
       mma_commit(done);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    if (first < p.units) {
+    if (fused && q < 2) {
+      // drain the r2c accumulator of every row: TMEM lane = A row = output channel o (q < 2: rows 0..63 hold g)
+      int it = 0;
+      for (int64_t r = first; r < p.rows; r += stride, ++it) {
+        const int a2 = it & 1;
+        mbar_wait(&x1full[a2], ((uint32_t)it >> 1) & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(a2 * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&x1empty[a2]);
+        const int o = q * 32 + lane;
+        if (o < p.c_out) {
+          const int64_t row = ((r / p.lead) * p.c_out + o) * p.lead + r % p.lead;
+          float4* dst = (float4*)(p.x1 + row * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+    if (first < p.rows) {
       mbar_wait(done, 0);
       tc_fence_after();
       const int o = q * 32 + lane;
@@ -690,13 +760,12 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
   // slab: both directions (c_in <-> c_out) must fit
   auto ch_ok = [](int ci, int co) { return ci % 8 == 0 && ci >= 8 && ci <= 128 && co % 32 == 0 && co >= 32 && co <= 128; };
   if (sD % 128 == 0 && ch_ok(d.c_in, d.c_out) && ch_ok(d.c_out, d.c_in)) {
-    int stages = 0;
-    for (int s = 6; s >= 2; --s) {
-      tc::SlabSmem a = tc::slab_smem(sD, d.c_in, d.c_out, true, s), b = tc::slab_smem(sD, d.c_out, d.c_in, true, s);
-      if (a.total <= 227 * 1024 && b.total <= 227 * 1024) { stages = s; break; }
-    }
-    t->slab_stages = stages;
-    t->slab_ok = stages >= 2;
+    // every variant the block uses must fit two load stages: forward / data-gradient (2 tiles) and the
+    // pre-activation-cotangent pass (3 tiles)
+    t->slab_ok = tc::slab_smem(sD, d.c_in, d.c_out, true, 2, 2).total <= 227 * 1024 &&
+                 tc::slab_smem(sD, d.c_out, d.c_in, true, 2, 2).total <= 227 * 1024 &&
+                 tc::slab_smem(sD, d.c_in, d.c_out, true, 2, 3).total <= 227 * 1024;
+    t->slab_stages = 2;
   }
   t->wgrad_ok = d.c_in % 16 == 0 && d.c_out % 8 == 0 && d.c_in <= 112 && d.c_out <= 128;
   p->tc = t;
@@ -806,11 +875,11 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   {
     uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * c_out};
     uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
-    uint32_t box[3] = {128, 1, (uint32_t)(c_out / 2)};
-    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box, tc::TM_NONE));
+    uint32_t box[3] = {32, 1, (uint32_t)(c_out / 2)};
+    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box));
     if (mode == 1) {
       PDEQX_CHECK_ARG(aux && ((uintptr_t)aux & 15) == 0, "tc_slab: aux must be a 16-byte aligned device pointer");
-      PDEQX_TRY(tc::make_tensor_map(&tm_aux, aux, 3, dims, str, box, tc::TM_NONE));
+      PDEQX_TRY(tc::make_tensor_map(&tm_aux, aux, 3, dims, str, box));
     } else {
       tm_aux = tm_y;
     }
@@ -825,21 +894,17 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.mode = mode;
   sp.act = act;
   sp.round_out = 0;
-  sp.stages = t->slab_stages;
   sp.units = (int64_t)d.batch * lead * sp.wt_per_row;
   sp.bias = bypass_b;
   sp.aux = aux;
   sp.y = y;
-  int epi_bufs = 2;
-  if (mode == 1) {  // trade one load stage for a third epilogue tile (cotangent prefetch distance 2)
-    tc::SlabSmem t3 = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages - 1, 3);
-    if (sp.stages > 2 && t3.total <= 227 * 1024) {
-      epi_bufs = 3;
-      sp.stages -= 1;
-    } else if (tc::slab_smem(sD, c_in, c_out, bypass, sp.stages, 3).total <= 227 * 1024) {
-      epi_bufs = 3;
-    }
-  }
+  // mode 1 keeps three epilogue tiles (cotangent prefetch distance 2); the load pipeline gets what is left
+  const int epi_bufs = mode == 1 ? 3 : 2;
+  int stages = 0;
+  for (int st = 6; st >= 2; --st)
+    if (tc::slab_smem(sD, c_in, c_out, bypass, st, epi_bufs).total <= 227 * 1024) { stages = st; break; }
+  PDEQX_CHECK_ARG(stages >= 2, "tc_slab: shared memory does not fit two load stages (c_in %d, c_out %d)", c_in, c_out);
+  sp.stages = stages;
   tc::SlabSmem L = tc::slab_smem(sD, c_in, c_out, bypass, sp.stages, epi_bufs);
   int grid = (int)(sp.units < t->sms ? sp.units : t->sms);
   grid = grid / sp.wt_per_row * sp.wt_per_row;  // every CTA keeps one w-tile of the table (units stride by the grid size)
@@ -875,11 +940,21 @@ int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int ta
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix) {
   return tcp(p) && tcp(p)->wgrad_ok && n_pix % 32 == 0 && g_fast_paths.load(std::memory_order_relaxed);
 }
+bool tc_wgrad_r2c_available(const pdeqx_spectral_plan* p) {
+  const pdeqx_spectral_desc& d = p->desc;
+  return tcp(p) && tcp(p)->wgrad_ok && tcp(p)->r2c_ok && d.c_out <= 64 && d.spatial[d.ndim - 1] <= 1024 &&
+         g_fast_paths.load(std::memory_order_relaxed);
+}
 
-// gw [c_out, c_in] and gb [c_out] must be zeroed by the caller
-int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb, cudaStream_t s) {
+// gw [c_out, c_in] and gb [c_out] must be zeroed by the caller. x1_out (optional): the first stage of the
+// adjoint-of-inverse DFT of g, [B * c_out * lead][32] -- the same pass over g that feeds the weight gradient
+int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb, cudaStream_t s,
+             float* x1_out) {
   TcPlan* t = tcp(p);
   const pdeqx_spectral_desc& d = p->desc;
+  const int sD = d.spatial[d.ndim - 1];
+  PDEQX_CHECK_ARG(n_pix == p->lead * sD, "tc_wgrad: n_pix does not match the plan");
+  PDEQX_CHECK_ARG(!x1_out || (d.c_out <= 64 && d.modes[d.ndim - 1] == 16 && t->r2c_ok), "tc_wgrad: fused r2c needs c_out <= 64, 16 modes");
   CUtensorMap tm_g, tm_x;
   {
     uint64_t dims[2] = {(uint64_t)n_pix, (uint64_t)d.batch * d.c_out};
@@ -896,22 +971,26 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   tc::WgradParams wp{};
   wp.c_out = d.c_out;
   wp.c_in = d.c_in;
-  wp.chunks_per_b = (int)(n_pix / 32);
-  wp.units = (int64_t)d.batch * wp.chunks_per_b;
+  wp.chunks_per_row = sD / 32;
+  wp.lead = (int)p->lead;
+  wp.rows = (int64_t)d.batch * p->lead;
   wp.gw = gw;
   wp.gb = gb;
+  wp.x1 = x1_out;
+  const uint32_t tab_bytes = x1_out ? (uint32_t)wp.chunks_per_row * 4096 : 0;
   const uint32_t stage_bytes = (uint32_t)(d.c_out + d.c_in) * 128 + 2048;
-  int stages = (int)((227 * 1024 - 16384 - 2048) / stage_bytes);
+  int stages = (int)((227 * 1024 - 16384 - 2048 - (int)tab_bytes) / (int)stage_bytes);
   if (stages > 12) stages = 12;
+  PDEQX_CHECK_ARG(stages >= 2, "tc_wgrad: shared memory does not fit two stages");
   wp.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 16384 + 1024 + 1024;
+  const size_t smem = tab_bytes + (size_t)stages * stage_bytes + 16384 + 1024 + 1024;
   static bool attr = false;
   if (!attr) {
     PDEQX_CUDA(cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  const int grid = (int)(wp.units < t->sms ? wp.units : t->sms);
-  tc::wgrad_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_g, tm_x, wp);
+  const int grid = (int)(wp.rows < t->sms ? wp.rows : t->sms);
+  tc::wgrad_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_g, tm_x, t->tm_tab_r2c[1], wp);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }

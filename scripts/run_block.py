@@ -31,3 +31,19 @@ gx = blk._bwd(gy, tape, True)
 e1.record()
 torch.cuda.synchronize()
 print(f"block fwd {t_f:.3f} ms, bwd {e0.elapsed_time(e1):.3f} ms (B={B}, {prec})")
+# per-kernel device timing of one more forward + reverse pass
+from pdequinox_b200 import _lib
+L = _lib.lib()
+L.pdeqx_timing_enable(1)
+tape.stack.clear()
+y = blk._fwd(x, tape)
+gx = blk._bwd(gy, tape, True)
+torch.cuda.synchronize()
+names = {1: "slab", 2: "r2c", 3: "modes(c2c)", 4: "wgrad"}
+out = []
+for tag, nm in names.items():
+    ms, n = _lib.C.c_double(), _lib.C.c_int64()
+    L.pdeqx_timing_read(tag, _lib.C.byref(ms), _lib.C.byref(n))
+    out.append(f"{nm} {ms.value * 1e3:.0f} us/{n.value}")
+L.pdeqx_timing_enable(0)
+print("   " + ", ".join(out))

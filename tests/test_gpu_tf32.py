@@ -32,7 +32,9 @@ CASES = [
     (2, 2, 64, 32, (6, 256), (3, 16)),
     (1, 4, 32, 32, (128,), (16,)),
     (3, 1, 32, 32, (4, 6, 128), (2, 3, 16)),
-    (2, 2, 64, 64, (64, 256), (16, 16)),
+    (2, 2, 64, 64, (64, 256), (16, 16)),   # fused first DFT stage in the slab kernel (two w-tile partial sums)
+    (2, 3, 64, 64, (32, 128), (8, 16)),    # ... one w-tile
+    (2, 1, 64, 64, (96, 384), (16, 16)),   # ... three w-tiles, odd number of units per CTA
 ]
 
 
