@@ -29,10 +29,24 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug output goes to stderr
+# (NCCL's version banner is a bare printf): file descriptor 1 is pointed at stderr for the whole process and the result
+# line is written to a private duplicate of the original stdout.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 WORKLOAD = "ClassicFNO 2D periodic, 256x256 grid, hidden 64, 16 modes/axis, 4 blocks, global batch 64 (BASELINE.json configs[3])"
 GRID, HIDDEN, MODES, BLOCKS, GLOBAL_BATCH = 256, 64, 16, 4, 64
 METRIC = "ClassicFNO 2D 256^2 train samples/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the three slab-kernel variants at B = 64 from the ncu capture
+# in profiles/ (mean of fwd 2.229e9, cotangent 3.318e9, data-gradient 2.246e9 bytes); None until a capture exists
+SLAB_TRAFFIC = None
 
 
 def parse():
@@ -43,37 +57,62 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PDEQX_PRECISION", "tf32"), choices=["tf32", "fp32"])
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
-    ap.add_argument("--cpu-sample", type=int, default=2, help="samples per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="samples (= host threads) per CPU-baseline step; 0 = all cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-allreduce", action="store_true", help="bucketed all-reduce on a side stream during the reverse pass")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's train step (NumPy; pocketfft + BLAS on the host cores)
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_rate(sample, steps, warmup):
+def cpu_workers():
+    """Host threads of the CPU arm: one sample per thread (the path shards by sample), bounded by memory (~4 GB each)."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        import psutil
+        cores = min(cores, max(1, int(psutil.virtual_memory().available // (4 << 30))))
+    except Exception:
+        pass
+    return max(1, min(cores, 32))
+
+
+def cpu_train_step_rate(workers, steps, warmup):
+    """One train step of the oracle port on `workers` samples, one sample per host thread (NumPy's pocketfft, einsum and
+    BLAS calls release the GIL; BLAS itself is pinned to one thread per call), gradients averaged, one Adam update."""
     import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import nn as onn
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
     rng = np.random.default_rng(0)
     p = onn.init_fno(rng, 2, 1, 1, hidden_channels=HIDDEN, num_modes=MODES, num_blocks=BLOCKS)
     state = onn.adam_init(p)
-    x = rng.standard_normal((sample, 1, GRID, GRID)).astype(np.float32)
-    y = rng.standard_normal((sample, 1, GRID, GRID)).astype(np.float32)
+    x = rng.standard_normal((workers, 1, GRID, GRID)).astype(np.float32)
+    y = rng.standard_normal((workers, 1, GRID, GRID)).astype(np.float32)
+
+    def one(i):
+        return onn.fno_loss_and_grad(p, x[i:i + 1], y[i:i + 1], (MODES, MODES), BLOCKS)
+
     times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        _, g = onn.fno_loss_and_grad(p, x, y, (MODES, MODES), BLOCKS)
-        g = {k: v.reshape(p[k].shape) for k, v in g.items()}
-        p, state = onn.adam_step(p, g, state)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
-    dt = sum(times) / len(times)
+    limiter = threadpool_limits(limits=1) if (threadpool_limits and workers > 1) else None
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        cores = len(os.sched_getaffinity(0))
-    return sample / dt, dt, cores
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                results = list(pool.map(one, range(workers)))
+                g = {k: sum(r[1][k] for r in results).reshape(p[k].shape) / workers for k in results[0][1]}
+                p, state = onn.adam_step(p, g, state)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits() if hasattr(limiter, "restore_original_limits") else None
+    dt = sum(times) / len(times)
+    return workers / dt, dt, workers
 
 
 def run_reference(args):
@@ -82,10 +121,11 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 3))
     warmup = 1 if args.warmup > 0 else 0
-    rate, dt, cores = cpu_train_step_rate(args.cpu_sample, steps, warmup)
-    sample = (f"{args.cpu_sample} of the {args.global_batch} samples per step, {steps} timed steps; NumPy port of the "
-              "reference train step (rfftn/einsum/irfftn forward, analytic reverse pass, Adam); jax/equinox are not "
-              "installable in this image so the reference itself cannot run")
+    workers = args.cpu_sample if args.cpu_sample > 0 else cpu_workers()
+    rate, dt, cores = cpu_train_step_rate(workers, steps, warmup)
+    sample = (f"{workers} of the {args.global_batch} samples per step (one per host thread), {steps} timed steps of {dt:.1f} s; "
+              "NumPy port of the reference train step (rfftn/einsum/irfftn forward, analytic reverse pass, Adam); "
+              "jax/equinox are not installable in this image so the reference itself cannot run")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -95,7 +135,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -150,6 +190,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def shutdown(world, graphed):
+    """Tear down in an order that cannot hang: captured graphs that contain NCCL kernels are released before the
+    communicator, and a watchdog ends the process if the communicator teardown itself blocks (the result line has
+    already been printed and flushed by then)."""
+    import torch
+    import torch.distributed as dist
+    if graphed is not None:
+        graphed.graph.reset()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            os._exit(0)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -175,7 +235,7 @@ def run_ours(args):
     pdeqx.set_precision(args.precision)
 
     model = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=HIDDEN, num_modes=MODES, num_blocks=BLOCKS, key=0)
-    step = TrainStep(model, lr=3e-4)
+    step = TrainStep(model, lr=3e-4, overlap=args.overlap_allreduce)
     rng = np.random.default_rng(1234)  # same global batch on every rank, sharded by sample
     xg = rng.standard_normal((args.global_batch, 1, GRID, GRID), dtype=np.float32)
     yg = rng.standard_normal((args.global_batch, 1, GRID, GRID), dtype=np.float32)
@@ -201,30 +261,49 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident arm ----
+    # ---- warm-up (eager), then capture the whole step (forward, reverse pass, all-reduce, Adam) into one CUDA graph ----
     for _ in range(max(args.warmup, 3)):
         step(xd, yd)
+    torch.cuda.synchronize()
+    launches0 = L.pdeqx_launch_count()
+    step(xd, yd)
+    launches_per_step = L.pdeqx_launch_count() - launches0
+    graphed = None
+    if not args.no_graph:
+        try:
+            from pdequinox_b200.train import GraphedTrainStep
+            graphed = GraphedTrainStep(step, xd, yd, warmup=1)
+        except Exception as exc:  # capture is an optimisation of the launch path, never a different computation
+            print(f"# CUDA-graph capture failed ({type(exc).__name__}: {exc}); timing the eager launch path", file=sys.stderr)
+            graphed = None
+    run_step = (lambda: graphed()) if graphed is not None else (lambda: step(xd, yd))
+    for _ in range(2):
+        run_step()
+
+    # ---- device-resident arm ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = L.pdeqx_launch_count()
-    L.pdeqx_timing_enable(1)
-    ms = timed(lambda: step(xd, yd), args.steps)
-    launches = L.pdeqx_launch_count() - launches0
-    slab_ms, slab_n = _lib.C.c_double(), _lib.C.c_int64()
-    _lib.check(L.pdeqx_timing_read(_lib.K_SPECTRAL_SLAB, _lib.C.byref(slab_ms), _lib.C.byref(slab_n)))
-    L.pdeqx_timing_enable(0)
+    ms = timed(run_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
     value = args.global_batch * args.steps / (ms * 1e-3)
 
     # ---- end-to-end arm: host buffers in, loss out, every step ----
     xin, yin = torch.empty_like(xd), torch.empty_like(yd)
     loss_host = torch.zeros(1).pin_memory()
 
+    if graphed is not None:
+        graphed.prefetch(xh, yh)  # input pipeline primed: every step below issues the copy of the batch after it
+
     def e2e_step():
-        xin.copy_(xh, non_blocking=True)
-        yin.copy_(yh, non_blocking=True)
-        loss = step(xin, yin)
+        if graphed is not None:
+            loss = graphed()              # consumes the staged batch (waits for its host -> device copy), one graph launch
+            graphed.prefetch(xh, yh)      # next batch: pinned host -> device on the copy stream, under this step's kernels
+        else:
+            xin.copy_(xh, non_blocking=True)
+            yin.copy_(yh, non_blocking=True)
+            loss = step(xin, yin)
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller owns the loss value before the next step
 
@@ -233,9 +312,16 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = args.global_batch * args.steps / (ms_e2e * 1e-3)
 
+    # ---- per-kernel durations: the same steps launched eagerly, each tagged launch bracketed by CUDA events on its stream ----
+    probe_steps = min(args.steps, 3)
+    L.pdeqx_timing_enable(1)
+    ms_probe = timed(lambda: step(xd, yd), probe_steps)
+    slab_ms, slab_n = _lib.C.c_double(), _lib.C.c_int64()
+    _lib.check(L.pdeqx_timing_read(_lib.K_SPECTRAL_SLAB, _lib.C.byref(slab_ms), _lib.C.byref(slab_n)))
+    L.pdeqx_timing_enable(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(world, graphed)
         return
 
     # ---- roofline of the dominant kernel (read x once + write y once [+ saved z]) ----
@@ -246,17 +332,24 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     n_pix = GRID * GRID
-    # per launch: x [B,C,N] read, y [B,C,N] written, z [B,C,H,2m] read, tables + bypass weights (negligible)
-    slab_bytes = 4 * per * HIDDEN * (2 * n_pix + GRID * 2 * MODES) + 4 * (HIDDEN * HIDDEN + HIDDEN + 2 * MODES * GRID)
+    # the slab kernel runs three times per block: forward (read x, z; write y), cotangent of the pre-activation (read x, z,
+    # gy; write g) and data gradient (read g, z'; write gx); z = [B,C,H,2m]; tables + bypass weights are negligible
+    small = 4 * (HIDDEN * HIDDEN + HIDDEN + 2 * MODES * GRID)
+    bytes_2 = 4 * per * HIDDEN * (2 * n_pix + GRID * 2 * MODES) + small
+    bytes_3 = 4 * per * HIDDEN * (3 * n_pix + GRID * 2 * MODES) + small
+    slab_bytes = (2 * bytes_2 + bytes_3) / 3.0  # mean over the launches timed (equal numbers of the three variants)
     roofline = None
     if slab_n.value > 0:
         avg_s = slab_ms.value * 1e-3 / slab_n.value
         achieved = slab_bytes / avg_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "spectral block last stage (c2r DFT + 1x1 bypass + bias + gelu)",
+        roofline = {"bound": "hbm", "kernel": "tc::slab_kernel, spectral block last stage (c2r DFT + 1x1 bypass + bias + gelu / gelu' / adjoint), "
+                              "mean over its three uses per block",
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": slab_bytes, "avg_launch_us": avg_s * 1e6,
-                    "launches_timed": slab_n.value, "share_of_step": slab_ms.value / ms, "traffic": None}
+                    "launches_timed": slab_n.value, "share_of_step": slab_ms.value / ms_probe,
+                    "timed_in": f"{probe_steps} eagerly launched steps after the graph-replayed region (events cannot bracket "
+                                "kernels inside a graph replay); share_of_step is relative to that pass", "traffic": SLAB_TRAFFIC}
 
     # ---- PhysicsConv roofline (BASELINE.json configs[2] layer: 3x3, 64 -> 64, 128x128, batch 128, periodic) ----
     physics = None
@@ -283,10 +376,11 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, dt, cores = cpu_train_step_rate(args.cpu_sample, 2, 1)
+        workers = args.cpu_sample if args.cpu_sample > 0 else cpu_workers()
+        rate, dt, cores = cpu_train_step_rate(workers, 2, 1)
         cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_sample} of the {args.global_batch} samples per step, 2 timed steps ({dt:.1f} s each); "
-                         "NumPy port of the reference train step (jax/equinox not installable here)"}
+               "sample": f"{workers} of the {args.global_batch} samples per step (one per host thread), 2 timed steps "
+                         f"({dt:.1f} s each); NumPy port of the reference train step (jax/equinox not installable here)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -295,6 +389,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": args.global_batch, "per_gpu_batch": per,
                    "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of the 67.2 MB gradient arena per step)",
+                   "launch": "one CUDA graph replay per step" if graphed is not None else "eager kernel launches",
                    "precision": args.precision,
                    "l2": "inputs larger than L2: every activation tensor is %.0f MB per rank" % (per * HIDDEN * n_pix * 4 / 1e6)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
@@ -305,9 +400,8 @@ def run_ours(args):
         "physics_conv": physics,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
+    shutdown(world, graphed)
 
 
 if __name__ == "__main__":

@@ -265,6 +265,11 @@ int pdeqx_mse_loss(int64_t n, const float* pred, const float* target, float grad
  * step is the 1-based update count (bias correction). */
 int pdeqx_adam_step(int64_t n, float* param, const float* grad, float* mu, float* nu, float lr,
                     float b1, float b2, float eps, int32_t step, float grad_scale, void* stream);
+/* Same update with the step count kept ON THE DEVICE, so that a captured CUDA graph of the whole train
+ * step can be replayed: state[0] holds the update count (int32 bit pattern, start at 0) and is
+ * incremented by the call; state[1..2] receive the bias corrections. state: 4 floats. */
+int pdeqx_adam_step_dev(int64_t n, float* param, const float* grad, float* mu, float* nu, float lr,
+                        float b1, float b2, float eps, float* state, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

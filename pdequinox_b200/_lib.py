@@ -85,6 +85,7 @@ PROTOTYPES = {
     "pdeqx_activation_bwd": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),
     "pdeqx_mse_loss": (C.c_int, [_I64, _P, _P, _F, _P, _P, _P, _P]),
     "pdeqx_adam_step": (C.c_int, [_I64, _P, _P, _P, _P, _F, _F, _F, _F, _I32, _F, _P]),
+    "pdeqx_adam_step_dev": (C.c_int, [_I64, _P, _P, _P, _P, _F, _F, _F, _F, _P, _F, _P]),
 }
 
 _lib = None

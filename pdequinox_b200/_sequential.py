@@ -41,10 +41,17 @@ class Sequential(Module):
         return self.projection._fwd(x, tape)
 
     def _bwd(self, gy, tape, need_gx=False):
+        # `_grad_ready_hook(prefix)` (set by the data-parallel train step) is told as soon as every gradient under a
+        # pytree prefix is final, so that its all-reduce can start while the rest of the reverse pass still runs
+        hook = getattr(self, "_grad_ready_hook", None) or (lambda prefix: None)
         g = self.projection._bwd(gy, tape, True)
-        for block in reversed(self.blocks):
-            g = block._bwd(g, tape, True)
-        return self.lifting._bwd(g, tape, need_gx)
+        hook("projection.")
+        for i in reversed(range(len(self.blocks))):
+            g = self.blocks[i]._bwd(g, tape, True)
+            hook(f"blocks.{i}.")
+        gx = self.lifting._bwd(g, tape, need_gx)
+        hook("lifting.")
+        return gx
 
     @property
     def receptive_field(self):

@@ -85,7 +85,12 @@ mse_final_kernel(const float* __restrict__ partials, int nparts, double inv_n, f
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
-            int64_t n, float lr, float b1, float b2, float eps, float inv_c1, float inv_c2, float gscale) {
+            int64_t n, float lr, float b1, float b2, float eps, float inv_c1, float inv_c2, float gscale,
+            const float* __restrict__ corr) {
+  if (corr) {  // bias corrections of the device-side step counter (CUDA-graph replays)
+    inv_c1 = corr[1];
+    inv_c2 = corr[2];
+  }
   const int64_t nv = n / 4;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
     float4 pv = ((float4*)p)[v], gv = __ldg((const float4*)g + v), mv = ((float4*)mu)[v], vv = ((float4*)nu)[v];
@@ -169,7 +174,29 @@ extern "C" int pdeqx_adam_step(int64_t n, float* param, const float* grad, float
   if (n == 0) return PDEQX_OK;
   const double c1 = 1.0 - pow((double)b1, (double)step), c2 = 1.0 - pow((double)b2, (double)step);
   adam_kernel<<<stream_blocks(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(param, grad, mu, nu, n, lr, b1, b2, eps,
-                                                                         (float)(1.0 / c1), (float)(1.0 / c2), grad_scale);
+                                                                         (float)(1.0 / c1), (float)(1.0 / c2), grad_scale, nullptr);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
+// state[0] = update count (int32 bits), state[1] = 1 / (1 - b1^t), state[2] = 1 / (1 - b2^t)
+__global__ void adam_tick_kernel(float* state, float b1, float b2) {
+  const int t = __float_as_int(state[0]) + 1;
+  state[0] = __int_as_float(t);
+  state[1] = (float)(1.0 / (1.0 - pow((double)b1, (double)t)));
+  state[2] = (float)(1.0 / (1.0 - pow((double)b2, (double)t)));
+}
+
+extern "C" int pdeqx_adam_step_dev(int64_t n, float* param, const float* grad, float* mu, float* nu, float lr, float b1,
+                                   float b2, float eps, float* state, float grad_scale, void* stream) {
+  PDEQX_CHECK_ARG(n >= 0 && state && (n == 0 || (param && grad && mu && nu)), "bad arguments");
+  PDEQX_CHECK_ARG(aligned16(param) && aligned16(grad) && aligned16(mu) && aligned16(nu),
+                  "arena pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, s>>>(state, b1, b2);
+  PDEQX_LAUNCHED();
+  if (n == 0) return PDEQX_OK;
+  adam_kernel<<<stream_blocks(n / 4 + 1), 256, 0, s>>>(param, grad, mu, nu, n, lr, b1, b2, eps, 1.f, 1.f, grad_scale, state);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }

@@ -168,13 +168,14 @@ struct TiledArgs {
   ModeMap mm;
 };
 
-constexpr int TM_MT = 64, TM_KC = 8;
+constexpr int TM_KC = 8;  // K chunk; a CTA covers 8 * RT rows (RT = rows per thread: small batches shrink the tile)
 
-template <int PT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
+template <int PT, int RT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 __global__ void __launch_bounds__(256, 2)
 mode_gemm_tiled_kernel(TiledArgs t) {
   constexpr int NQ = 32 / PT;   // n-quads per warp-row group ... threads = PT * 8 * NQ
   constexpr int NT = 4 * NQ;    // columns per CTA
+  constexpr int TM_MT = 8 * RT; // rows per CTA
   __shared__ float2 As[TM_KC][TM_MT][PT];
   __shared__ float2 Bs[TM_KC][NT][PT];
   const int tid = threadIdx.x;
@@ -185,9 +186,9 @@ mode_gemm_tiled_kernel(TiledArgs t) {
   int64_t loc;
   mode_to_weight(t.mm, p0, g, loc);
   const int64_t woff = (int64_t)g * t.w_corner + loc;  // planar operands: offset of mode p0 inside an (o,i) plane
-  float2 acc[8][4];
+  float2 acc[RT][4];
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+  for (int r = 0; r < RT; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
 
@@ -216,13 +217,13 @@ mode_gemm_tiled_kernel(TiledArgs t) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TM_KC; ++k) {
-      float2 a[8], b[4];
+      float2 a[RT], b[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) a[r] = As[k][mq + 8 * r][pm];
+      for (int r = 0; r < RT; ++r) a[r] = As[k][mq + 8 * r][pm];
 #pragma unroll
       for (int c = 0; c < 4; ++c) b[c] = Bs[k][nq * 4 + c][pm];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int r = 0; r < RT; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           acc[r][c].x = fmaf(a[r].x, b[c].x, fmaf(-a[r].y, b[c].y, acc[r][c].x));
@@ -232,7 +233,7 @@ mode_gemm_tiled_kernel(TiledArgs t) {
     __syncthreads();
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
+  for (int r = 0; r < RT; ++r) {
     const int m = m0 + mq + 8 * r;
     if (m >= t.M) continue;
 #pragma unroll
@@ -250,17 +251,29 @@ mode_gemm_tiled_kernel(TiledArgs t) {
   }
 }
 
+template <int PT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
+static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
+  // rows per thread: the smallest power of two whose 8 * RT-row tile covers M (at most 64 rows per CTA)
+  int rt = 1;
+  while (rt < 8 && 8 * rt < t.M) rt *= 2;
+  const int nt = 4 * (32 / PT);
+  dim3 grid((unsigned)(t.J / PT), (unsigned)ceil_div(t.M, 8 * rt), (unsigned)ceil_div(t.N, nt));
+  if (grid.y > 65535 || grid.z > 65535) return false;
+  switch (rt) {
+    case 1: mode_gemm_tiled_kernel<PT, 1, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
+    case 2: mode_gemm_tiled_kernel<PT, 2, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
+    case 4: mode_gemm_tiled_kernel<PT, 4, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
+    default: mode_gemm_tiled_kernel<PT, 8, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
+  }
+  return true;
+}
+
 template <bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 static bool launch_tiled(const TiledArgs& t, cudaStream_t s) {
   const int mD = t.mm.m[t.mm.D - 1];
-  const int pt = (mD % 8 == 0) ? 8 : (mD % 4 == 0) ? 4 : 0;
-  if (!pt) return false;
-  const int nt = 4 * (32 / pt);
-  dim3 grid((unsigned)(t.J / pt), (unsigned)ceil_div(t.M, TM_MT), (unsigned)ceil_div(t.N, nt));
-  if (grid.y > 65535 || grid.z > 65535) return false;
-  if (pt == 8) mode_gemm_tiled_kernel<8, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t);
-  else mode_gemm_tiled_kernel<4, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t);
-  return true;
+  if (mD % 8 == 0) return launch_tiled_pt<8, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
+  if (mD % 4 == 0) return launch_tiled_pt<4, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
+  return false;
 }
 
 static ModeMap make_map(const pdeqx_spectral_plan* p) {

@@ -1,2 +1,5 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_tf32_n2.json 2> gpurun_out/bench_tf32_n2.err
-head -c 900 gpurun_out/bench_tf32_n2.json; echo; tail -3 gpurun_out/bench_tf32_n2.err
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_tf32_n2.json 2> gpurun_out/bench_tf32_n2.err
+echo "rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_tf32_n2.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['launch'])"
+OVERLAP=0 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29516 scripts/dp_parity.py 2>&1 | grep -E "dp_parity|Error|error" | head -5
+timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_tf32.py tests/test_gpu_models.py -q -x --timeout 200 2>&1 | tail -2

@@ -79,3 +79,33 @@ def test_dilated_resnet_forward_matches_oracle(cuda):
     # the reverse pass runs and produces finite gradients of the right shapes
     step.loss_and_grad(x, rng.standard_normal(x.shape))
     assert torch.isfinite(step.arena.grads).all()
+
+
+def test_graph_replayed_train_steps_equal_eager_steps(cuda):
+    """GraphedTrainStep replays the captured launch sequence: after the same number of updates on the same batches the
+    parameters must equal those of the eagerly launched steps (same kernels, same order; only the atomically reduced
+    bypass gradients may differ in summation order)."""
+    from pdequinox_b200.train import GraphedTrainStep
+    pdeqx.set_precision("fp32")
+    rng = np.random.default_rng(31)
+    xs = [torch.from_numpy(rng.standard_normal((4, 1, 32, 32))).float().cuda() for _ in range(3)]
+    ys = [torch.from_numpy(rng.standard_normal((4, 1, 32, 32))).float().cuda() for _ in range(3)]
+
+    def make():
+        return TrainStep(pdeqx.ClassicFNO(2, 1, 1, hidden_channels=8, num_modes=4, num_blocks=2, key=9), lr=1e-2)
+
+    eager = make()
+    losses_e = [eager(x, y).item() for x, y in zip(xs, ys)]
+    other = make()
+    snapshot = other.arena.params.clone()
+    graphed = GraphedTrainStep(other, xs[0], ys[0], warmup=2)
+    # warm-up and capture ran real updates: rewind the optimiser state, then replay the three batches
+    with torch.no_grad():
+        other.arena.params.copy_(snapshot)
+        other.mu.zero_()
+        other.nu.zero_()
+        other.adam_state.zero_()
+    losses_g = [graphed(x, y).item() for x, y in zip(xs, ys)]
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= 1e-5 * abs(a)
+    assert rel_l2(other.arena.params.cpu().numpy(), eager.arena.params.cpu().numpy()) <= 1e-5

@@ -156,3 +156,16 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
                 assert "oracle/" not in src and "oracle." not in src.replace("oracle.md", ""), f"{f} references the oracle"
+
+
+def test_gradient_buckets_tile_the_arena():
+    """The overlapped exchange all-reduces one contiguous arena range per finished pytree prefix (projection, blocks in
+    reverse, lifting): the ranges must tile the flat gradient arena exactly, or a gradient would stay un-reduced."""
+    from pdequinox_b200.train import TrainStep
+    m = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=8, num_modes=4, num_blocks=3, key=0)
+    st = TrainStep(m, distributed=False)
+    ranges = sorted(st._prefix_range(p) for p in ["projection.", "blocks.2.", "blocks.1.", "blocks.0.", "lifting."])
+    assert ranges[0][0] == 0 and ranges[-1][1] == st.arena.size
+    for (a0, a1), (b0, b1) in zip(ranges[:-1], ranges[1:]):
+        assert a1 == b0
+    assert st._prefix_range("no_such_prefix.") == (None, None)
