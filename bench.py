@@ -44,9 +44,10 @@ def emit(line):
 WORKLOAD = "ClassicFNO 2D periodic, 256x256 grid, hidden 64, 16 modes/axis, 4 blocks, global batch 64 (BASELINE.json configs[3])"
 GRID, HIDDEN, MODES, BLOCKS, GLOBAL_BATCH = 256, 64, 16, 4, 64
 METRIC = "ClassicFNO 2D 256^2 train samples/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the three slab-kernel variants at B = 64 from the ncu capture
-# in profiles/ (mean of fwd 2.229e9, cotangent 3.318e9, data-gradient 2.246e9 bytes); None until a capture exists
-SLAB_TRAFFIC = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of tc::slab_kernel at B = 64 per GPU, from the `ncu --set full`
+# capture summarised in profiles/r1_block_ncu.md: forward 2.233e9, cotangent pass 3.322e9, data gradient 2.255e9 bytes;
+# the mean over the three uses (as `achieved` averages them). Algorithmic mean: 2.640e9 -> no re-reads.
+SLAB_TRAFFIC_B64 = (2.233e9 + 3.322e9 + 2.255e9) / 3.0
 
 
 def parse():
@@ -349,7 +350,10 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": slab_bytes, "avg_launch_us": avg_s * 1e6,
                     "launches_timed": slab_n.value, "share_of_step": slab_ms.value / ms_probe,
                     "timed_in": f"{probe_steps} eagerly launched steps after the graph-replayed region (events cannot bracket "
-                                "kernels inside a graph replay); share_of_step is relative to that pass", "traffic": SLAB_TRAFFIC}
+                                "kernels inside a graph replay); share_of_step is relative to that pass",
+                    "traffic": SLAB_TRAFFIC_B64 * per / 64.0,
+                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum at 64 samples per GPU "
+                                      "(profiles/r1_block_ncu.md), scaled by this run's samples per GPU"}
 
     # ---- PhysicsConv roofline (BASELINE.json configs[2] layer: 3x3, 64 -> 64, 128x128, batch 128, periodic) ----
     physics = None
