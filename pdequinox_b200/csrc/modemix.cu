@@ -14,26 +14,31 @@ namespace pdeqx {
 
 struct ModeMap {
   int D;
-  int m[PDEQX_MAX_DIMS];
+  int m[PDEQX_MAX_DIMS];   // the reference's mode counts (weight layout)
+  int nd[PDEQX_MAX_DIMS];  // data layout: rows per leading axis (>= 2 m_a), modes on the last axis (>= m_{D-1}); the
+                           // excess positions are padding that carries zeros (spectral_plan.h)
   int64_t mprod;  // prod m_a
 };
 
-// p -> (g, loc): corner index and offset inside the corner's (m_0..m_{D-1}) block
-__device__ __forceinline__ void mode_to_weight(const ModeMap& mm, int64_t p, int& g, int64_t& loc) {
+// p -> (g, loc): corner index and offset inside the corner's (m_0..m_{D-1}) block; false for a padding position
+__device__ __forceinline__ bool mode_to_weight(const ModeMap& mm, int64_t p, int& g, int64_t& loc) {
   const int D = mm.D;
-  int64_t k = p % mm.m[D - 1];
-  int64_t rest = p / mm.m[D - 1];
+  int64_t k = p % mm.nd[D - 1];
+  int64_t rest = p / mm.nd[D - 1];
+  bool valid = k < mm.m[D - 1];
   g = 0;
   loc = k;
   int64_t stride = mm.m[D - 1];
   for (int a = D - 2; a >= 0; --a) {
-    int j = (int)(rest % (2 * mm.m[a]));
-    rest /= 2 * mm.m[a];
+    int j = (int)(rest % mm.nd[a]);
+    rest /= mm.nd[a];
+    valid = valid && j < 2 * mm.m[a];
     int hi = j >= mm.m[a];
     g |= hi << a;
     loc += (int64_t)(j - hi * mm.m[a]) * stride;
     stride *= mm.m[a];
   }
+  return valid;
 }
 
 // out[b,u,p] = sum_v W(u,v,p) * in[b,v,p]
@@ -49,14 +54,14 @@ mode_mix_kernel(const float2* __restrict__ in, const float* __restrict__ wr, con
   if (p >= J) return;
   int g;
   int64_t loc;
-  mode_to_weight(mm, p, g, loc);
+  const bool valid = mode_to_weight(mm, p, g, loc);
   float2 acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
   const int64_t wbase = (int64_t)g * O * I * mm.mprod + loc;
-  for (int v = 0; v < V; ++v) {
+  for (int v = 0; v < (valid ? V : 0); ++v) {  // padding positions: zeros out
     float2 x[4];
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
@@ -126,7 +131,7 @@ mode_mix_dw_kernel(const float2* __restrict__ ghat, const float2* __restrict__ x
   }
   int g;
   int64_t loc;
-  mode_to_weight(mm, p, g, loc);
+  if (!mode_to_weight(mm, p, g, loc)) return;  // padding position: no weight slot
   const int64_t wbase = (int64_t)g * O * I * mm.mprod + loc;
 #pragma unroll
   for (int oo = 0; oo < 4; ++oo) {
@@ -184,7 +189,7 @@ mode_gemm_tiled_kernel(TiledArgs t) {
   const int m0 = blockIdx.y * TM_MT, n0 = blockIdx.z * NT;
   int g;
   int64_t loc;
-  mode_to_weight(t.mm, p0, g, loc);
+  const bool valid = mode_to_weight(t.mm, p0, g, loc);  // a tile is all data or all padding (PT divides both mode counts)
   const int64_t woff = (int64_t)g * t.w_corner + loc;  // planar operands: offset of mode p0 inside an (o,i) plane
   float2 acc[RT][4];
 #pragma unroll
@@ -192,7 +197,7 @@ mode_gemm_tiled_kernel(TiledArgs t) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
 
-  for (int k0 = 0; k0 < t.K; k0 += TM_KC) {
+  for (int k0 = 0; k0 < (valid ? t.K : 0); k0 += TM_KC) {  // padding tile: interleaved outputs get zeros, planar ones nothing
     // A chunk: [KC][MT][PT] float2, PT contiguous in global memory
     for (int idx = tid; idx < TM_KC * TM_MT * PT; idx += 256) {
       const int q = idx % PT, m = (idx / PT) % TM_MT, k = idx / (PT * TM_MT);
@@ -241,6 +246,7 @@ mode_gemm_tiled_kernel(TiledArgs t) {
       const int n = n0 + nq * 4 + c;
       if (n >= t.N) continue;
       if (C_PLANAR) {
+        if (!valid) continue;
         const int64_t off = (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + woff + pm;
         t.cr[off] = acc[r][c].x;
         t.ci[off] = acc[r][c].y;
@@ -270,9 +276,9 @@ static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
 
 template <bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 static bool launch_tiled(const TiledArgs& t, cudaStream_t s) {
-  const int mD = t.mm.m[t.mm.D - 1];
-  if (mD % 8 == 0) return launch_tiled_pt<8, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
-  if (mD % 4 == 0) return launch_tiled_pt<4, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
+  const int mD = t.mm.m[t.mm.D - 1], nD = t.mm.nd[t.mm.D - 1];
+  if (mD % 8 == 0 && nD % 8 == 0) return launch_tiled_pt<8, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
+  if (mD % 4 == 0 && nD % 4 == 0) return launch_tiled_pt<4, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
   return false;
 }
 
@@ -282,6 +288,7 @@ static ModeMap make_map(const pdeqx_spectral_plan* p) {
   mm.mprod = 1;
   for (int a = 0; a < PDEQX_MAX_DIMS; ++a) {
     mm.m[a] = a < mm.D ? p->desc.modes[a] : 1;
+    mm.nd[a] = a < mm.D - 1 ? p->n2[a] : (a == mm.D - 1 ? p->mlast : 1);
     if (a < mm.D) mm.mprod *= p->desc.modes[a];
   }
   return mm;

@@ -79,9 +79,21 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
   p->G = 1 << (D - 1);
   const int sD = desc->spatial[D - 1], mD = desc->modes[D - 1];
 
+  // ---- padded mode geometry (DATA layout only; weights keep the reference's mode counts) ----
+  // The tcgen05 stages want 32 real accumulator columns on the contiguous axis (16 complex modes) and multiples of 32
+  // retained rows on the leading axes. Smaller mode counts (configs[4]: 12) are padded with zero table rows / columns:
+  // the padded modes carry exact zeros through every stage and the channel mix skips them.
+  const bool tf32 = desc->precision == PDEQX_PREC_TF32;
+  const int mP = (tf32 && mD < 16 && mD % 4 == 0 && sD % 32 == 0) ? 16 : mD;
+  p->mlast = mP;
+  for (int a = 0; a < PDEQX_MAX_DIMS; ++a) {
+    p->n2[a] = a < D - 1 ? 2 * desc->modes[a] : 1;
+    if (a < D - 1 && tf32 && mP == 16 && p->n2[a] % 32 != 0 && desc->spatial[a] % 32 == 0) p->n2[a] = (p->n2[a] + 31) / 32 * 32;
+  }
+
   // ---- last axis (real <-> complex) ----
-  std::vector<float> r2c_f((size_t)sD * 2 * mD), c2r_i((size_t)2 * mD * sD);
-  std::vector<float> r2c_b((size_t)sD * 2 * mD), c2r_b((size_t)2 * mD * sD);
+  std::vector<float> r2c_f((size_t)sD * 2 * mP, 0.f), c2r_i((size_t)2 * mP * sD, 0.f);
+  std::vector<float> r2c_b((size_t)sD * 2 * mP, 0.f), c2r_b((size_t)2 * mP * sD, 0.f);
   for (int k = 0; k < mD; ++k) {
     double c = 2.0;
     if (k == 0) c = 1.0;
@@ -90,14 +102,14 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
       double co, si;
       cs(k, n, sD, &co, &si);
       // x_hat = sum_n x e^{-i th}
-      r2c_f[(size_t)n * 2 * mD + 2 * k] = (float)co;
-      r2c_f[(size_t)n * 2 * mD + 2 * k + 1] = (float)(-si);
+      r2c_f[(size_t)n * 2 * mP + 2 * k] = (float)co;
+      r2c_f[(size_t)n * 2 * mP + 2 * k + 1] = (float)(-si);
       // y = sum_k c/s (zr cos - zi sin)
       c2r_i[(size_t)(2 * k) * sD + n] = (float)(c / sD * co);
       c2r_i[(size_t)(2 * k + 1) * sD + n] = (float)(-c / sD * si);
       // adjoints are the transposes
-      r2c_b[(size_t)n * 2 * mD + 2 * k] = (float)(c / sD * co);
-      r2c_b[(size_t)n * 2 * mD + 2 * k + 1] = (float)(-c / sD * si);
+      r2c_b[(size_t)n * 2 * mP + 2 * k] = (float)(c / sD * co);
+      r2c_b[(size_t)n * 2 * mP + 2 * k + 1] = (float)(-c / sD * si);
       c2r_b[(size_t)(2 * k) * sD + n] = (float)co;
       c2r_b[(size_t)(2 * k + 1) * sD + n] = (float)(-si);
     }
@@ -111,9 +123,10 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
 
   // ---- other axes (complex <-> complex) ----
   for (int a = 0; a < D - 1; ++a) {
-    const int s = desc->spatial[a], m = desc->modes[a];
-    std::vector<float2> fwd((size_t)2 * m * s), inv((size_t)s * 2 * m), inv_adj((size_t)2 * m * s),
-        fwd_adj((size_t)s * 2 * m);
+    const int s = desc->spatial[a], m = desc->modes[a], np2 = p->n2[a];  // np2 >= 2m rows / columns, the extra ones zero
+    const float2 zero2 = make_float2(0.f, 0.f);
+    std::vector<float2> fwd((size_t)np2 * s, zero2), inv((size_t)s * np2, zero2), inv_adj((size_t)np2 * s, zero2),
+        fwd_adj((size_t)s * np2, zero2);
     for (int j = 0; j < 2 * m; ++j) {
       // overlap (2m > s): the later (high) corner block overwrites the low one in the reference
       double keep = 1.0;
@@ -125,8 +138,8 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
         double co, si;
         cs(kappa(j, s, m), n, s, &co, &si);
         fwd[(size_t)j * s + n] = make_float2((float)co, (float)(-si));
-        fwd_adj[(size_t)n * 2 * m + j] = make_float2((float)co, (float)si);
-        inv[(size_t)n * 2 * m + j] = make_float2((float)(keep * co / s), (float)(keep * si / s));
+        fwd_adj[(size_t)n * np2 + j] = make_float2((float)co, (float)si);
+        inv[(size_t)n * np2 + j] = make_float2((float)(keep * co / s), (float)(keep * si / s));
         inv_adj[(size_t)j * s + n] = make_float2((float)(keep * co / s), (float)(-keep * si / s));
       }
     }
@@ -139,18 +152,18 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
 
   // ---- sizes ----
   int64_t lead = 1;  // prod s_a, a < D-1
-  int64_t J = mD;    // prod 2m_a (a < D-1) * m_D
+  int64_t J = mP;    // (padded) retained modes per channel: prod n2_a (a < D-1) * m_D
   for (int a = 0; a < D - 1; ++a) {
     lead *= desc->spatial[a];
-    J *= 2 * desc->modes[a];
+    J *= p->n2[a];
   }
   p->lead = lead;
   p->J = J;
   const int64_t cmax = desc->c_in > desc->c_out ? desc->c_in : desc->c_out;
   // largest intermediate: right after the r2c stage / right before the c2r stage
   int64_t lead_max = 1;  // with overlapping slices (2m > s) a truncated axis can be longer than the full one
-  for (int a = 0; a < D - 1; ++a) lead_max *= (desc->spatial[a] > 2 * desc->modes[a] ? desc->spatial[a] : 2 * desc->modes[a]);
-  p->stage_floats = 2 * (int64_t)desc->batch * cmax * lead_max * mD;
+  for (int a = 0; a < D - 1; ++a) lead_max *= (desc->spatial[a] > p->n2[a] ? desc->spatial[a] : p->n2[a]);
+  p->stage_floats = 2 * (int64_t)desc->batch * cmax * lead_max * mP;
   p->mode_floats = (2 * (int64_t)desc->batch * cmax * J + 63) / 64 * 64;
   p->ws_bytes = (size_t)(2 * p->stage_floats + 2 * p->mode_floats) * sizeof(float) + 256;
   rc = tc_plan_init(p);  // builds the tcgen05-side operand tables when the shape qualifies
@@ -186,7 +199,7 @@ extern "C" size_t pdeqx_spectral_xhat_floats(const pdeqx_spectral_plan* p) {
 }
 extern "C" size_t pdeqx_spectral_z_floats(const pdeqx_spectral_plan* p) {
   if (!p) return 0;
-  return (size_t)(2 * (int64_t)p->desc.batch * p->desc.c_out * p->lead * p->desc.modes[p->desc.ndim - 1]);
+  return (size_t)(2 * (int64_t)p->desc.batch * p->desc.c_out * p->lead * p->mlast);
 }
 
 extern "C" int pdeqx_spectral_plan_tcgen05_stages(const pdeqx_spectral_plan* p) { return p ? tc_stage_mask(p) : 0; }
@@ -197,7 +210,7 @@ namespace pdeqx {
 static int stage_r2c(const pdeqx_spectral_plan* p, const float* x, const float* table, int64_t rows, float* out,
                      cudaStream_t s) {
   const int D = p->desc.ndim;
-  const int sD = p->desc.spatial[D - 1], mD = p->desc.modes[D - 1];
+  const int sD = p->desc.spatial[D - 1], mD = p->mlast;
   TimedScope timed(PDEQX_K_SPECTRAL_R2C, s);
   if (tc_r2c_available(p)) return tc_r2c(p, x, table == p->t_r2c_bwd, rows, out, s);
   SgemmArgs a{};
@@ -212,7 +225,7 @@ static int stage_r2c(const pdeqx_spectral_plan* p, const float* x, const float* 
 static int stage_c2r(const pdeqx_spectral_plan* p, const float* z, const float* table, int64_t rows, const float* add,
                      int act, float* out, cudaStream_t s) {
   const int D = p->desc.ndim;
-  const int sD = p->desc.spatial[D - 1], mD = p->desc.modes[D - 1];
+  const int sD = p->desc.spatial[D - 1], mD = p->mlast;
   TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
   SgemmArgs a{};
   a.A = z; a.B = table; a.C = out; a.add = add;
@@ -227,7 +240,10 @@ static int stage_c2r(const pdeqx_spectral_plan* p, const float* z, const float* 
 static int stage_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float2* table, const float* in, float* out,
                      int64_t outer, int n_in, int n_out, int64_t inner, cudaStream_t s) {
   TimedScope timed(PDEQX_K_SPECTRAL_MODES, s);
-  if (tc_c2c_available(p, axis, kind, inner)) return tc_c2c(p, axis, kind, in, out, outer, inner, s);
+  // forward-type stages (kinds 0, 2) walk the axes downwards and end in the fp32 channel mix; inverse-type stages (1, 3)
+  // end in the tcgen05 slab kernel: every output that another tensor-core stage will read is rounded to tf32 here
+  const bool feeds_tc = (kind == 0 || kind == 2) ? axis > 0 : true;
+  if (tc_c2c_available(p, axis, kind, inner)) return tc_c2c(p, axis, kind, in, out, outer, inner, s, feeds_tc);
   return cgemm_shared_a(table, (const float2*)in, (float2*)out, outer, n_out, n_in, inner, s);
 }
 
@@ -244,7 +260,7 @@ static int forward_chain(const pdeqx_spectral_plan* p, const float* x, int C, bo
                          const Regions& r, cudaStream_t s, bool r2c_done = false) {
   const pdeqx_spectral_desc& d = p->desc;
   const int D = d.ndim;
-  const int mD = d.modes[D - 1];
+  const int mD = p->mlast;
   const int64_t BC = (int64_t)d.batch * C;
   const float* tab_last = adjoint_of_inverse ? p->t_r2c_bwd : p->t_r2c_fwd;
   float* o = (D == 1) ? dst : r.big[0];
@@ -255,10 +271,10 @@ static int forward_chain(const pdeqx_spectral_plan* p, const float* x, int C, bo
   for (int a = D - 2; a >= 0; --a) {
     int64_t outer = BC, inner = mD;
     for (int b = 0; b < a; ++b) outer *= d.spatial[b];
-    for (int b = a + 1; b < D - 1; ++b) inner *= 2 * d.modes[b];
+    for (int b = a + 1; b < D - 1; ++b) inner *= p->n2[b];
     float* dstage = (a == 0) ? dst : r.big[nb];
     const float2* tab = adjoint_of_inverse ? p->t_inv_adj[a] : p->t_fwd[a];
-    PDEQX_TRY(stage_c2c(p, a, adjoint_of_inverse ? 2 : 0, tab, cur, dstage, outer, d.spatial[a], 2 * d.modes[a], inner, s));
+    PDEQX_TRY(stage_c2c(p, a, adjoint_of_inverse ? 2 : 0, tab, cur, dstage, outer, d.spatial[a], p->n2[a], inner, s));
     cur = dstage;
     nb ^= 1;
   }
@@ -270,16 +286,16 @@ static int inverse_chain(const pdeqx_spectral_plan* p, const float* yhat, int C,
                          const Regions& r, cudaStream_t s) {
   const pdeqx_spectral_desc& d = p->desc;
   const int D = d.ndim;
-  const int mD = d.modes[D - 1];
+  const int mD = p->mlast;
   const int64_t BC = (int64_t)d.batch * C;
   const float* cur = yhat;
   for (int a = 0; a < D - 1; ++a) {
     int64_t outer = BC, inner = mD;
     for (int b = 0; b < a; ++b) outer *= d.spatial[b];
-    for (int b = a + 1; b < D - 1; ++b) inner *= 2 * d.modes[b];
+    for (int b = a + 1; b < D - 1; ++b) inner *= p->n2[b];
     float* dstage = (a == D - 2) ? dst : r.big[0];
     const float2* tab = adjoint_of_forward ? p->t_fwd_adj[a] : p->t_inv[a];
-    PDEQX_TRY(stage_c2c(p, a, adjoint_of_forward ? 3 : 1, tab, cur, dstage, outer, 2 * d.modes[a], d.spatial[a], inner, s));
+    PDEQX_TRY(stage_c2c(p, a, adjoint_of_forward ? 3 : 1, tab, cur, dstage, outer, p->n2[a], d.spatial[a], inner, s));
     cur = dstage;
   }
   return PDEQX_OK;
@@ -386,7 +402,7 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
     // Steps 1-3a in sample chunks small enough for the 126 MB L2: the cotangent chunk written by the slab kernel is
     // still L2-resident when the bypass weight gradient and the first DFT stage read it back, and so is most of x.
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
-    const int mD = d.modes[D - 1];
+    const int mD = p->mlast;
     float* x1 = (D == 1) ? r.mode[0] : r.big[0];
     float* gb = bypass_b ? g_bypass_b : nullptr;
     PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));

@@ -7,7 +7,9 @@ struct pdeqx_spectral_plan {
   pdeqx_spectral_desc desc;
   int G = 1;
   int64_t lead = 1;          // prod of the leading spatial sizes s_0..s_{D-2}
-  int64_t J = 1;             // retained modes per channel: prod(2 m_a, a < D-1) * m_D
+  int mlast = 1;             // mode count of the DATA layout on the contiguous axis (>= modes[D-1]; padded modes are zero)
+  int n2[PDEQX_MAX_DIMS] = {1, 1, 1};  // retained rows of the data layout on each leading axis (>= 2 m_a)
+  int64_t J = 1;             // retained (padded) modes per channel: prod(n2_a, a < D-1) * mlast
   int64_t stage_floats = 0;  // floats of one chain ping-pong buffer
   int64_t mode_floats = 0;   // floats of one mode-space buffer
   size_t ws_bytes = 0;
@@ -52,8 +54,10 @@ int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int ta
 int tc_c2c_plan_init(pdeqx_spectral_plan* p);
 void tc_c2c_plan_free(pdeqx_spectral_plan* p);
 bool tc_c2c_available(const pdeqx_spectral_plan* p, int axis, int kind, int64_t inner_complex);
+// round_out: the result feeds another tcgen05 (tf32) stage -- round it to tf32 (nearest) here instead of letting that
+// stage truncate the operand
 int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, float* out, int64_t outer, int64_t inner_complex,
-           cudaStream_t s);
+           cudaStream_t s, bool round_out = false);
 // general form: explicit channel counts of THIS call, epilogue mode 1 = aux * act'(.) (cotangent of the pre-activation)
 int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,

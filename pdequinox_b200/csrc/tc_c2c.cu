@@ -28,6 +28,7 @@ struct C2cParams {
   int kchunk, kchunks;      // rows per TMA stage, stages per unit
   int q_per_outer;          // 32-float chunks per row
   int stages, acc_stages;
+  int round_out;            // round the outputs to tf32 (nearest): the consumer is another tcgen05 stage, which would truncate
   int64_t blocks, units;    // M-blocks (outer x chunk), units of 4 blocks
   int64_t inner_f;          // floats per row
   float* out;
@@ -172,7 +173,8 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float other = __shfl_xor_sync(0xffffffffu, qi[j], 1);
-          const float v = (lane & 1) ? pr[j] + other : pr[j] - other;
+          float v = (lane & 1) ? pr[j] + other : pr[j] - other;
+          if (p.round_out) v = round_tf32(v);
           if (live) dst[(int64_t)(r0 + j) * p.inner_f] = v;
         }
       }
@@ -226,7 +228,7 @@ int tc_c2c_plan_init(pdeqx_spectral_plan* p) {
   TcC2cPlan* t = new TcC2cPlan();
   t->sms = sms;
   for (int a = 0; a < d.ndim - 1; ++a) {
-    const int s = d.spatial[a], m2 = 2 * d.modes[a];
+    const int s = d.spatial[a], m2 = p->n2[a];
     const float2* src[4] = {p->t_fwd[a], p->t_inv[a], p->t_inv_adj[a], p->t_fwd_adj[a]};
     const int n_out[4] = {m2, s, m2, s}, n_in[4] = {s, m2, s, m2};
     for (int k = 0; k < 4; ++k) {
@@ -273,7 +275,7 @@ bool tc_c2c_available(const pdeqx_spectral_plan* p, int axis, int kind, int64_t 
 }
 
 int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, float* out, int64_t outer, int64_t inner_complex,
-           cudaStream_t s) {
+           cudaStream_t s, bool round_out) {
   TcC2cPlan* t = (TcC2cPlan*)p->tc_c2c;
   const C2cTable& tb = t->t[axis][kind];
   PDEQX_CHECK_ARG(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "tc_c2c: pointers must be 16-byte aligned");
@@ -291,6 +293,7 @@ int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, fl
   cp.blocks = outer * cp.q_per_outer;
   cp.units = ceil_div(cp.blocks, 4) * cp.parts;
   cp.acc_stages = 2;
+  cp.round_out = round_out ? 1 : 0;
   cp.out = out;
   const uint32_t tab_bytes = (uint32_t)(2 * tb.n_out) * tb.n_in * 4;
   const uint32_t stage_bytes = 4 * (uint32_t)cp.kchunk * 128;

@@ -115,6 +115,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // ==========================================================================================
 struct SlabParams {
   int lead, W, wt_per_row, c_in, c_out;
+  int rpu;  // image rows per 128-pixel unit: 1 for W >= 128 (W / 128 units per row), 128 / W for narrower grids
   int has_bypass, mode, act, round_out;
   int stages;
   int64_t units;  // B * lead * wt_per_row
@@ -132,14 +133,16 @@ struct SlabSmem {
 static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, int epi_bufs = 2) {
   SlabSmem s{};
   uint32_t off = 0;
+  const uint32_t rpu = W >= 128 ? 1 : 128 / W;
   s.tab_off = off;
-  off += 128 * 128;  // one [128 w x 32 k] table tile: the grid is a multiple of W/128, so a CTA only ever sees one w-tile
-  (void)W;
+  // W >= 128: one [128 w x 32 k] table tile (the grid is a multiple of W/128, so a CTA only ever sees one w-tile);
+  // W < 128: the unit spans rpu rows and the table is block diagonal, one [128 pixels x 32 k] tile per row of the unit
+  off += rpu * 128 * 128;
   s.w_off = off;
   off += bypass ? (uint32_t)((c_in + 31) / 32) * c_out * 128 : 0;
   s.x_box_bytes = (uint32_t)c_in * 128;
   s.z_off_in_stage = bypass ? 4 * s.x_box_bytes : 0;
-  s.stage_bytes = s.z_off_in_stage + (uint32_t)c_out * 128;
+  s.stage_bytes = s.z_off_in_stage + rpu * (uint32_t)c_out * 128;
   s.stage_bytes = (s.stage_bytes + 1023) & ~1023u;
   s.stage_off = off;
   off += s.stage_bytes * stages;
@@ -215,23 +218,28 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     if (lane == 0) {
       // constant operands: DFT table tiles and the bypass weight chunks
       const int wchunks = p.has_bypass ? (p.c_in + 31) / 32 : 0;
-      mbar_expect_tx(tabfull, 128 * 128 + (uint32_t)wchunks * p.c_out * 128);
-      tma_load_2d(smem + L.tab_off, &tm_tab, tabfull, 0, (int)(first % p.wt_per_row) * 128);
+      mbar_expect_tx(tabfull, (uint32_t)p.rpu * 128 * 128 + (uint32_t)wchunks * p.c_out * 128);
+      for (int c = 0; c < p.rpu; ++c)
+        tma_load_2d(smem + L.tab_off + c * 128 * 128, &tm_tab, tabfull, 0, ((int)(first % p.wt_per_row) + c) * 128);
       for (int c = 0; c < wchunks; ++c) tma_load_2d(smem + L.w_off + c * p.c_out * 128, &tm_w, tabfull, c * 32, 0);
       int s = 0;
       uint32_t ph = 0;
       for (int64_t u = first; u < p.units; u += stride) {
         const int wt = (int)(u % p.wt_per_row);
         const int64_t bl = u / p.wt_per_row;
-        const int l = (int)(bl % p.lead);
-        const int b = (int)(bl / p.lead);
+        const int lu = p.lead / p.rpu;
+        const int l = (int)(bl % lu) * p.rpu;  // first image row of the unit
+        const int b = (int)(bl / lu);
         mbar_wait_backoff(&empty[s], ph ^ 1);
         uint8_t* st = smem + L.stage_off + (size_t)s * L.stage_bytes;
-        mbar_expect_tx(&full[s], (p.has_bypass ? 4 * L.x_box_bytes : 0) + (uint32_t)p.c_out * 128);
+        mbar_expect_tx(&full[s], (p.has_bypass ? 4 * L.x_box_bytes : 0) + (uint32_t)p.rpu * p.c_out * 128);
         if (p.has_bypass)
-          for (int j = 0; j < 4; ++j)
-            tma_load_3d(st + j * L.x_box_bytes, &tm_x, &full[s], wt * 128 + j * 32, l, b * p.c_in);
-        tma_load_3d(st + L.z_off_in_stage, &tm_z, &full[s], 0, l, b * p.c_out);
+          for (int j = 0; j < 4; ++j) {
+            const int px = wt * 128 + j * 32;  // pixel offset inside the unit's row group
+            tma_load_3d(st + j * L.x_box_bytes, &tm_x, &full[s], px % p.W, l + px / p.W, b * p.c_in);
+          }
+        for (int c = 0; c < p.rpu; ++c)
+          tma_load_3d(st + L.z_off_in_stage + c * p.c_out * 128, &tm_z, &full[s], 0, l + c, b * p.c_out);
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
@@ -252,9 +260,11 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         // spectral part: A = table tile [128 w x 32 k] (K-major), B = Z box [c_out x 32 k] (K-major)
         const uint32_t ta = smem_u32(smem + L.tab_off);
         const uint32_t zb = st + L.z_off_in_stage;
+        for (int c = 0; c < p.rpu; ++c)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_tf32(d, smem_desc_sw128(ta + k * 32, 0, 1024), smem_desc_sw128(zb + k * 32, 0, 1024), idesc_kk, k > 0);
+          for (int k = 0; k < 4; ++k)
+            mma_tf32(d, smem_desc_sw128(ta + c * 128 * 128 + k * 32, 0, 1024),
+                     smem_desc_sw128(zb + c * p.c_out * 128 + k * 32, 0, 1024), idesc_kk, (c | k) != 0);
         // bypass part: A = x slab [128 w x c_in] (MN-major: w contiguous), B = W [c_out x c_in] (K-major)
         if (p.has_bypass) {
           const uint32_t wb = smem_u32(smem + L.w_off);
@@ -284,21 +294,23 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     int a = 0, e = 0;
     uint32_t aph = 0, eph = 0;
     auto load_aux = [&](int64_t un, int buf) {
-      const int wtn = (int)(un % p.wt_per_row);
+      const int pxn = (int)(un % p.wt_per_row) * 128 + q * 32;
       const int64_t bln = un / p.wt_per_row;
+      const int lu = p.lead / p.rpu;
       mbar_expect_tx(&afull[buf], (uint32_t)ncol * 128);
-      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], wtn * 128 + q * 32, (int)(bln % p.lead),
-                  (int)(bln / p.lead) * p.c_out + half * ncol);
+      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], pxn % p.W, (int)(bln % lu) * p.rpu + pxn / p.W,
+                  (int)(bln / lu) * p.c_out + half * ncol);
     };
     if (MODE == 1 && lane == 0) {
       if (first < p.units) load_aux(first, 0);
       if (first + stride < p.units) load_aux(first + stride, 1);
     }
     for (int64_t u = first; u < p.units; u += stride) {
-      const int wt = (int)(u % p.wt_per_row);
+      const int px = (int)(u % p.wt_per_row) * 128 + q * 32;  // this warp's pixels inside the unit's row group
       const int64_t bl = u / p.wt_per_row;
-      const int l = (int)(bl % p.lead);
-      const int b = (int)(bl / p.lead);
+      const int lu = p.lead / p.rpu;
+      const int l = (int)(bl % lu) * p.rpu + px / p.W;
+      const int b = (int)(bl / lu);
       uint8_t* piece = ebuf0 + (size_t)e * L.epi_buf_bytes;
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
@@ -346,7 +358,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&tm_y, piece, wt * 128 + q * 32, l, b * p.c_out + half * ncol);
+        tma_store_3d(&tm_y, piece, px % p.W, l, b * p.c_out + half * ncol);
         tma_store_commit();
         if (MODE == 1) {
           const int64_t un = u + 2 * stride;
@@ -507,6 +519,7 @@ struct WgradParams {
   float* gb;
   // fused first stage of the adjoint-of-inverse DFT of g (optional): x1[(b * c_out + o) * lead + l][0:32] = sum_w g[b,o,l,w] T[w,:]
   float* x1;
+  int round_x1;  // x1 feeds a tcgen05 c2c stage (D >= 2): round to tf32 here
 };
 
 __global__ void __launch_bounds__(kThreadsR2c, 1)
@@ -643,6 +656,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
         if (o < p.c_out) {
           const int64_t row = ((r / p.lead) * p.c_out + o) * p.lead + r % p.lead;
           float4* dst = (float4*)(p.x1 + row * 32);
+          if (p.round_x1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -711,8 +728,8 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (major != 10 || !tc::encode_tiled_fn()) return PDEQX_OK;
-  const int D = d.ndim, sD = d.spatial[D - 1], mD = d.modes[D - 1];
-  if (2 * mD != 32) return PDEQX_OK;  // TODO: pad the retained columns to 32 for other mode counts
+  const int D = d.ndim, sD = d.spatial[D - 1], mD = p->mlast;
+  if (2 * mD != 32) return PDEQX_OK;  // 16 (padded) modes on the contiguous axis = 32 accumulator columns
   if (sD % 32 != 0) return PDEQX_OK;
   TcPlan* t = new TcPlan();
   t->sms = sms;
@@ -730,10 +747,22 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
         cudaMemcpy(t->tab_r2c[v], h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
       rc = PDEQX_ERR_CUDA;
     if (cudaMemcpy(src.data(), dev_src_c2r[v], src.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = PDEQX_ERR_CUDA;
-    for (int w = 0; w < sD; ++w)
-      for (int k = 0; k < 32; ++k) h[(size_t)w * 32 + k] = tc::host_round_tf32(src[(size_t)k * sD + w]);
-    if (cudaMalloc((void**)&t->tab_c2r[v], h.size() * 4) != cudaSuccess ||
-        cudaMemcpy(t->tab_c2r[v], h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+    // W >= 128: [s_D rows][32 k]. W < 128 (128 % W == 0): the slab unit spans rpu = 128 / W image rows; tile c (of rpu)
+    // is [128 pixels][32 k] with the table in the rows of image row c and zeros elsewhere (block-diagonal operand).
+    const int rpu = sD >= 128 ? 1 : (128 % sD == 0 ? 128 / sD : 0);
+    std::vector<float> hc((size_t)(sD >= 128 ? sD : rpu * 128) * 32, 0.f);
+    if (sD >= 128) {
+      for (int w = 0; w < sD; ++w)
+        for (int k = 0; k < 32; ++k) hc[(size_t)w * 32 + k] = tc::host_round_tf32(src[(size_t)k * sD + w]);
+    } else {
+      for (int c = 0; c < rpu; ++c)
+        for (int w = 0; w < sD; ++w)
+          for (int k = 0; k < 32; ++k)
+            hc[((size_t)c * 128 + (size_t)c * sD + w) * 32 + k] = tc::host_round_tf32(src[(size_t)k * sD + w]);
+    }
+    if (hc.empty()) hc.resize(32, 0.f);
+    if (cudaMalloc((void**)&t->tab_c2r[v], hc.size() * 4) != cudaSuccess ||
+        cudaMemcpy(t->tab_c2r[v], hc.data(), hc.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
       rc = PDEQX_ERR_CUDA;
     if (rc == PDEQX_OK) {
       uint64_t dims[2] = {(uint64_t)sD, 32};
@@ -741,8 +770,8 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
       uint32_t box[2] = {32, 32};
       rc = tc::make_tensor_map(&t->tm_tab_r2c[v], t->tab_r2c[v], 2, dims, str, box);
     }
-    if (rc == PDEQX_OK && sD % 128 == 0) {
-      uint64_t dims[2] = {32, (uint64_t)sD};
+    if (rc == PDEQX_OK && (sD % 128 == 0 || rpu > 0)) {
+      uint64_t dims[2] = {32, (uint64_t)(sD >= 128 ? sD : rpu * 128)};
       uint64_t str[1] = {32 * 4};
       uint32_t box[2] = {32, 128};
       rc = tc::make_tensor_map(&t->tm_tab_c2r[v], t->tab_c2r[v], 2, dims, str, box);
@@ -759,7 +788,8 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
   t->r2c_ok = (sD <= 1024);
   // slab: both directions (c_in <-> c_out) must fit
   auto ch_ok = [](int ci, int co) { return ci % 8 == 0 && ci >= 8 && ci <= 128 && co % 32 == 0 && co >= 32 && co <= 128; };
-  if (sD % 128 == 0 && ch_ok(d.c_in, d.c_out) && ch_ok(d.c_out, d.c_in)) {
+  const bool w_ok = sD % 128 == 0 || (sD >= 32 && sD < 128 && 128 % sD == 0 && p->lead % (128 / sD) == 0);
+  if (w_ok && ch_ok(d.c_in, d.c_out) && ch_ok(d.c_out, d.c_in)) {
     // every variant the block uses must fit two load stages: forward / data-gradient (2 tiles) and the
     // pre-activation-cotangent pass (3 tiles)
     t->slab_ok = tc::slab_smem(sD, d.c_in, d.c_out, true, 2, 2).total <= 227 * 1024 &&
@@ -810,7 +840,7 @@ int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int
   rp.n_valid = 32;
   rp.out_ld = 32;
   rp.out = out;
-  rp.round_out = 0;
+  rp.round_out = D >= 2 ? 1 : 0;  // the next stage is a tcgen05 c2c stage (it would truncate); D == 1 feeds the fp32 channel mix
   const uint32_t tab_bytes = (uint32_t)rp.kchunks * 4096;
   int stages = (int)((227 * 1024 - 2048 - tab_bytes) / 16384);
   if (stages > 10) stages = 10;
@@ -887,14 +917,15 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   tc::SlabParams sp{};
   sp.lead = (int)lead;
   sp.W = sD;
-  sp.wt_per_row = sD / 128;
+  sp.rpu = sD >= 128 ? 1 : 128 / sD;
+  sp.wt_per_row = sD >= 128 ? sD / 128 : 1;
   sp.c_in = c_in;
   sp.c_out = c_out;
   sp.has_bypass = bypass ? 1 : 0;
   sp.mode = mode;
   sp.act = act;
   sp.round_out = 0;
-  sp.units = (int64_t)d.batch * lead * sp.wt_per_row;
+  sp.units = (int64_t)d.batch * (lead / sp.rpu) * sp.wt_per_row;
   sp.bias = bypass_b;
   sp.aux = aux;
   sp.y = y;
@@ -954,7 +985,7 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   const pdeqx_spectral_desc& d = p->desc;
   const int sD = d.spatial[d.ndim - 1];
   PDEQX_CHECK_ARG(n_pix == p->lead * sD, "tc_wgrad: n_pix does not match the plan");
-  PDEQX_CHECK_ARG(!x1_out || (d.c_out <= 64 && d.modes[d.ndim - 1] == 16 && t->r2c_ok), "tc_wgrad: fused r2c needs c_out <= 64, 16 modes");
+  PDEQX_CHECK_ARG(!x1_out || (d.c_out <= 64 && p->mlast == 16 && t->r2c_ok), "tc_wgrad: fused r2c needs c_out <= 64, 16 modes");
   CUtensorMap tm_g, tm_x;
   {
     uint64_t dims[2] = {(uint64_t)n_pix, (uint64_t)d.batch * d.c_out};
@@ -977,6 +1008,7 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   wp.gw = gw;
   wp.gb = gb;
   wp.x1 = x1_out;
+  wp.round_x1 = d.ndim >= 2 ? 1 : 0;
   const uint32_t tab_bytes = x1_out ? (uint32_t)wp.chunks_per_row * 4096 : 0;
   const uint32_t stage_bytes = (uint32_t)(d.c_out + d.c_in) * 128 + 2048;
   int stages = (int)((227 * 1024 - 16384 - 2048 - (int)tab_bytes) / (int)stage_bytes);

@@ -32,9 +32,14 @@ CASES = [
     (2, 2, 64, 32, (6, 256), (3, 16)),
     (1, 4, 32, 32, (128,), (16,)),
     (3, 1, 32, 32, (4, 6, 128), (2, 3, 16)),
-    (2, 2, 64, 64, (64, 256), (16, 16)),   # fused first DFT stage in the slab kernel (two w-tile partial sums)
-    (2, 3, 64, 64, (32, 128), (8, 16)),    # ... one w-tile
-    (2, 1, 64, 64, (96, 384), (16, 16)),   # ... three w-tiles, odd number of units per CTA
+    (2, 2, 64, 64, (64, 256), (16, 16)),
+    (2, 3, 64, 64, (32, 128), (8, 16)),
+    (2, 1, 64, 64, (96, 384), (16, 16)),   # three w-tiles, odd number of units per CTA
+    # mode counts other than 16 are zero-padded in the data layout; grids narrower than 128 put several rows in a slab unit
+    (3, 2, 32, 32, (32, 32, 64), (12, 12, 12)),  # BASELINE configs[4] geometry scaled down: 12 modes, W = 64
+    (2, 2, 32, 32, (64, 64), (12, 12)),
+    (2, 2, 64, 64, (64, 128), (8, 12)),
+    (2, 3, 32, 32, (32, 32), (4, 8)),            # W = 32: four rows per unit
 ]
 
 
