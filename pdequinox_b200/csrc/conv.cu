@@ -118,15 +118,55 @@ __device__ __forceinline__ int preimages(int n, int s, int lo, int hi, int mode,
 
 // MIRROR_ONLY: only the contributions that reach an input point through a wrapped / reflected halo position, ADDED to gx
 // (the tcgen05 path computes the zero-extended part; see tc_conv_bwd_data for neumann)
+// (2-D only) the points of one channel plane within `band` of an edge, enumerated as top rows, bottom rows, then the left and
+// right columns of the rows in between: only these can be reached through a mirrored / wrapped halo position
+struct Frame2d {
+  int band_h, band_w;  // band widths along axis 0 / axis 1 (clipped so that the bands do not overlap)
+  int64_t count;       // points per channel plane
+};
+__host__ __device__ __forceinline__ Frame2d frame2d(const ConvGeom& g) {
+  Frame2d f;
+  const int H = g.spatial[0], W = g.spatial[1];
+  const int bh = g.pad_lo[0] > g.pad_hi[0] ? g.pad_lo[0] : g.pad_hi[0], bw = g.pad_lo[1] > g.pad_hi[1] ? g.pad_lo[1] : g.pad_hi[1];
+  f.band_h = 2 * (bh + 1) >= H ? (H + 1) / 2 : bh + 1;  // reflect reaches index `pad`, wrap index pad - 1
+  f.band_w = 2 * (bw + 1) >= W ? (W + 1) / 2 : bw + 1;
+  const int mid_h = H - 2 * f.band_h > 0 ? H - 2 * f.band_h : 0;
+  const int top = H - mid_h;  // rows covered entirely
+  const int side = W - 2 * f.band_w > 0 ? 2 * f.band_w : W;
+  f.count = (int64_t)top * W + (int64_t)mid_h * side;
+  return f;
+}
+__device__ __forceinline__ int64_t frame2d_point(const ConvGeom& g, const Frame2d& f, int64_t k) {
+  const int H = g.spatial[0], W = g.spatial[1];
+  const int mid_h = H - 2 * f.band_h > 0 ? H - 2 * f.band_h : 0;
+  const int top = H - mid_h;
+  if (k < (int64_t)top * W) {  // full rows: the first band_h rows, then the last ones
+    const int r = (int)(k / W), c = (int)(k % W);
+    const int h = r < f.band_h ? r : r + mid_h;
+    return (int64_t)h * W + c;
+  }
+  k -= (int64_t)top * W;
+  const int side = W - 2 * f.band_w > 0 ? 2 * f.band_w : W;
+  const int r = (int)(k / side), c = (int)(k % side);
+  const int wcol = (side == W || c < f.band_w) ? c : W - side + c;
+  return (int64_t)(f.band_h + r) * W + wcol;
+}
+
 template <bool MIRROR_ONLY>
 __global__ void __launch_bounds__(256)
 conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ add,
                      float* __restrict__ gx) {
   const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
-  const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t n = idx % g.n_in;
-    int64_t r = idx / g.n_in;
+  const bool framed = MIRROR_ONLY && g.ndim == 2;  // walk only the frame of every plane
+  Frame2d fr{};
+  if (framed) fr = frame2d(g);
+  const int64_t per_plane = framed ? fr.count : g.n_in;
+  const int64_t total = (int64_t)g.batch * g.c_in * per_plane;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = it % per_plane;
+    int64_t r = it / per_plane;
+    if (framed) n = frame2d_point(g, fr, n);
+    const int64_t idx = r * g.n_in + n;
     const int ci = (int)(r % g.c_in);
     const int b = (int)(r / g.c_in);
     const int grp = ci / cig, il = ci % cig;
@@ -312,7 +352,7 @@ static inline int grid_for(int64_t total) {
 }
 
 int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w, float* gx, cudaStream_t s) {
-  const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
+  const int64_t total = (int64_t)g.batch * g.c_in * (g.ndim == 2 ? frame2d(g).count : g.n_in);
   conv_bwd_data_kernel<true><<<grid_for(total), 256, 0, s>>>(g, gy, w, nullptr, gx);
   PDEQX_LAUNCHED();
   return PDEQX_OK;

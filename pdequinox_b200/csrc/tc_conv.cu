@@ -390,10 +390,11 @@ __global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __r
 // ==========================================================================================
 // Unit = one row (b, h); the contraction runs over the 128 columns of the row (K = w).
 //   A (M = 128): column-SHIFTED copies of the gy row, stacked: group 1 = [shift for tw=0 (64 o) ; shift for tw=2 (64 o)],
-//                group 2 = [centre (64 o) ; don't-care]. A shifted copy is just a TMA box whose start column is moved by
-//                -s; out-of-range columns are zero-filled, i.e. this kernel computes the zero-extended ("dirichlet in w")
-//                part for every boundary mode -- the d wrapped / mirrored edge columns of periodic / neumann are added by
-//                conv_wgrad_edge_kernel on CUDA cores.
+//                group 2 = [centre (64 o) ; don't-care]. For d % 4 == 0 a shifted copy is just a TMA box whose start
+//                column is moved by -s (out-of-range columns zero-filled: the zero-extended, "dirichlet in w" part; the d
+//                wrapped / mirrored edge columns of periodic / neumann are added by conv_wgrad_edge_kernel). An unaligned
+//                box column faults, so for the other dilations the two shifted operands are materialised once by
+//                conv_shift_rows_kernel -- with the halo contributions already folded in, for every boundary mode.
 //   B (N = 64):  the three x rows rowmap(h + (th-1) d) (K-major), from the same 3-row ring as the forward kernel.
 //   D: 6 accumulators of 64 columns (2 groups x 3 row taps) that live in TMEM for the CTA's whole life; each CTA flushes
 //      its partial sum to a scratch slab once, a second kernel reduces the slabs into gW (deterministic, no atomics).
@@ -641,15 +642,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_consta
   }
 }
 
-// Column-shifted, zero-extended copies of gy for the two outer column taps when d is not a multiple of 4:
-//   out0[.., w'] = gy[.., w' + d]   (tap tw = 0),   out2[.., w'] = gy[.., w' - d]   (tap tw = 2),   0 outside the row.
+// Column-shifted copies of gy for the two outer column taps when d is not a multiple of 4 (an unaligned TMA box column
+// faults): A_tw[.., w'] = sum over the output columns w whose tap reads x column w' = colmap(w + s), s = (tw - 1) d:
+//   the direct one, w = w' - s, plus -- periodic / neumann -- the columns that reach w' through the wrapped / mirrored halo.
+// With these operands the tensor-core pass is the complete filter gradient for every boundary mode (no edge pass).
 __global__ void __launch_bounds__(256)
-conv_shift_rows_kernel(const float* __restrict__ gy, float* __restrict__ out0, float* __restrict__ out2, int64_t rows, int W, int d) {
+conv_shift_rows_kernel(const float* __restrict__ gy, float* __restrict__ out0, float* __restrict__ out2, int64_t rows, int W, int d,
+                       int boundary) {
   const int64_t total = rows * W;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(idx % W);
-    out0[idx] = (w + d < W) ? __ldg(gy + idx + d) : 0.f;
-    out2[idx] = (w - d >= 0) ? __ldg(gy + idx - d) : 0.f;
+    const float* row = gy + (idx - w);
+    float a0 = (w + d < W) ? __ldg(row + w + d) : 0.f;   // tw = 0: s = -d, direct source column w + d
+    float a2 = (w - d >= 0) ? __ldg(row + w - d) : 0.f;  // tw = 2: s = +d, direct source column w - d
+    if (boundary != PDEQX_PAD_ZEROS && (w <= d || w >= W - 1 - d)) {
+      for (int e = 0; e < d; ++e) {
+        if (conv_map(e - d, W, boundary) == w) a0 += __ldg(row + e);                  // left halo of tap 0
+        if (conv_map(W - d + e + d, W, boundary) == w) a2 += __ldg(row + W - d + e);  // right halo of tap 2
+      }
+    }
+    out0[idx] = a0;
+    out2[idx] = a2;
   }
 }
 
@@ -896,7 +909,8 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
       PDEQX_CUDA(cudaMalloc((void**)&g_wg_shift[dev], sizeof(float) * 2 * n_act));
       g_wg_shift_floats[dev] = 2 * n_act;
     }
-    tc::conv_shift_rows_kernel<<<148 * 16, 256, 0, s>>>(gy, g_wg_shift[dev], g_wg_shift[dev] + n_act, (int64_t)g.batch * C * H, W, d);
+    tc::conv_shift_rows_kernel<<<148 * 16, 256, 0, s>>>(gy, g_wg_shift[dev], g_wg_shift[dev] + n_act, (int64_t)g.batch * C * H, W, d,
+                                                        g.boundary);
     PDEQX_LAUNCHED();
   }
   {
@@ -928,7 +942,7 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
   PDEQX_LAUNCHED();
   tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C);
   PDEQX_LAUNCHED();
-  if (g.boundary == PDEQX_PAD_WRAP || g.boundary == PDEQX_PAD_REFLECT) {
+  if (!preshift && (g.boundary == PDEQX_PAD_WRAP || g.boundary == PDEQX_PAD_REFLECT)) {  // (pre-shifted operands carry the halo)
     tc::conv_wgrad_edge_kernel<<<dim3(148 * 2, 6), 256, 0, s>>>(x, gy, gw, g.batch, C, H, W, d, g.boundary);
     PDEQX_LAUNCHED();
   }
