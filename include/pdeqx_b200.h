@@ -144,6 +144,24 @@ int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* plan, const float* x, co
                              float* g_bypass_w, float* g_bypass_b, float* scratch_full,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same VJP with the two ends of an architecture folded in (both optional, both need
+ * pdeqx_spectral_block_rank1_ok(plan, has_bypass, activation) == 1: tcgen05 slab kernel + fused activation):
+ *  - gy_w != NULL: RANK-ONE cotangent gy_full[b,o,pixel] = gy_w[o] * gy[b,pixel] -- what reaches the last spectral block
+ *    through the C -> 1 pointwise projection (pdequinox/arch/_classic_fno.py:78-83; the data gradient of
+ *    pdequinox/conv/_pointwise_linear_conv.py:37-49 is exactly this outer product). gy is then [B,*S]; the full-size
+ *    cotangent is never written or read, the kernel forms it in its epilogue.
+ *  - lift_u != NULL (gx must be NULL): the block's input was produced from the single-channel field lift_u [B,*S] by the
+ *    1 -> c_in pointwise lifting (pdequinox/arch/_classic_fno.py:71-76); instead of storing gx the last kernel
+ *    accumulates that lifting's gradients lift_gw[i] = sum gx[b,i,pixel] lift_u[b,pixel], lift_gb[i] = sum gx (may be
+ *    NULL). Outputs are overwritten. */
+int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* plan, int32_t has_bypass, int32_t activation);
+int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* plan, const float* x, const float* gy, const float* gy_w,
+                                const float* lift_u, float* lift_gw, float* lift_gb, const float* w_re,
+                                const float* w_im, const float* bypass_w, const float* bypass_b,
+                                int32_t activation, const float* saved_xhat, const float* saved_z, float* gx,
+                                float* gw_re, float* gw_im, float* g_bypass_w, float* g_bypass_b,
+                                float* scratch_full, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * PointwiseLinearConv (1x1 conv)
  *   replaces pdequinox/conv/_pointwise_linear_conv.py:6-53 (eqx.nn.Conv, k=1)

@@ -3,6 +3,7 @@ from . import random as jr
 from ._module import Module
 from ._utils import sum_receptive_fields
 from .blocks import ClassicResBlockFactory, LinearChannelAdjustBlockFactory
+from .conv import PointwiseLinearConv
 
 
 class Sequential(Module):
@@ -44,11 +45,47 @@ class Sequential(Module):
         # `_grad_ready_hook(prefix)` (set by the data-parallel train step) is told as soon as every gradient under a
         # pytree prefix is final, so that its all-reduce can start while the rest of the reverse pass still runs
         hook = getattr(self, "_grad_ready_hook", None) or (lambda prefix: None)
-        g = self.projection._bwd(gy, tape, True)
-        hook("projection.")
-        for i in reversed(range(len(self.blocks))):
-            g = self.blocks[i]._bwd(g, tape, True)
+        nb = len(self.blocks)
+        first, last = self.blocks[0], self.blocks[-1]
+        # Both ends of the architecture are pointwise and single-channel on the outside (1 -> C lifting, C -> 1 projection):
+        #  * the projection's data gradient is the outer product weight[o] * gy[b, pixel]; the last spectral block takes the
+        #    two factors and forms the cotangent inside its kernel instead of reading a materialised full-size tensor;
+        #  * the lifting's parameter gradients are reductions of the first block's input gradient against the input field;
+        #    the first block's last kernel accumulates them instead of writing that gradient out.
+        # Both need the block's tcgen05 path (`rank1_ok`); otherwise the plain chain below runs.
+        fold_proj = fold_lift = False
+        x_proj = tape.pop()  # what the projection saved (pushed back below)
+        if hasattr(last, "rank1_ok") and last.rank1_ok(tape):
+            fold_proj = isinstance(self.projection, PointwiseLinearConv) and self.projection.out_channels == 1
+            # the first block's forward record sits below the later blocks' records: same plan family, ask the block itself
+            fold_lift = (isinstance(self.lifting, PointwiseLinearConv) and self.lifting.in_channels == 1 and not need_gx
+                         and hasattr(first, "rank1_ok"))
+        tape.push(x_proj)
+        if fold_proj:
+            self.projection._bwd(gy, tape, False)  # weight / bias gradients only
+            hook("projection.")
+        else:
+            g = self.projection._bwd(gy, tape, True)
+            hook("projection.")
+        for i in reversed(range(nb)):
+            kw = {}
+            if fold_proj and i == nb - 1:
+                kw["gy_w"] = self.projection.weight
+                g = gy
+            if fold_lift and i == 0 and self.blocks[0].rank1_ok(tape):
+                u = tape.stack[-2]  # the lifting's saved input, right below the first block's record
+                lw = self.lifting.grad("weight")
+                lb = self.lifting.grad("bias") if self.lifting.bias is not None else None
+                kw["lift"] = (u, lw, lb)
+            if kw:
+                g = self.blocks[i]._bwd_ex(g, tape, True, **kw)
+            else:
+                g = self.blocks[i]._bwd(g, tape, True)
             hook(f"blocks.{i}.")
+            if "lift" in kw:
+                tape.pop()  # the lifting's record: its gradients were just written by the block's kernel
+                hook("lifting.")
+                return None
         gx = self.lifting._bwd(g, tape, need_gx)
         hook("lifting.")
         return gx

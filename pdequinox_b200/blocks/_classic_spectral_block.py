@@ -35,6 +35,22 @@ class ClassicSpectralBlock(Block):
         return self.spectral_conv.apply_bwd(x, gy, saved, tape, bypass=self.by_pass_conv,
                                             act=nn.activation_code(self.activation), need_gx=need_gx)
 
+    # ---- rank-one cotangent (the block sits right before a C -> 1 pointwise projection) ----
+    def rank1_ok(self, tape):
+        """True if the reverse pass of the forward call on top of `tape` can take its cotangent as gy_w[o] * gy1[b, pixel]."""
+        from .. import _lib
+        if not tape.stack:
+            return False
+        _, saved = tape.stack[-1]
+        return bool(_lib.lib().pdeqx_spectral_block_rank1_ok(saved[0].handle, 1, nn.activation_code(self.activation)))
+
+    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None):
+        """gy_w: `gy` is the single-channel factor of a rank-one cotangent; lift = (u, gw, gb): accumulate the gradients of
+        the 1 -> C lifting that produced this block's input from `u` instead of returning the input gradient."""
+        x, saved = tape.pop()
+        return self.spectral_conv.apply_bwd(x, gy, saved, tape, bypass=self.by_pass_conv,
+                                            act=nn.activation_code(self.activation), need_gx=need_gx, gy_w=gy_w, lift=lift)
+
 
 class ClassicSpectralBlockFactory(BlockFactory):
     def __init__(self, *, num_modes=8, use_bias: bool = True, zero_bias_init: bool = False):

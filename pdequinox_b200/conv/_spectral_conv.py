@@ -102,14 +102,30 @@ class SpectralConv(Module):
             _lib.stream()))
         return y, (plan, xhat, z)
 
-    def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True):
+    def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True, gy_w=None, lift=None):
+        """VJP. With `gy_w` the cotangent is rank one: gy_w[o] * gy[b, 0, *S] (what a C -> 1 pointwise projection sends
+        back); it is then formed inside the kernel instead of being materialised. With `lift = (u, gw, gb)` the input
+        gradient is not stored: the gradients gw, gb of the 1 -> C pointwise lifting that made x from the field u are
+        accumulated instead (pdeqx_spectral_block_bwd_ex)."""
         plan, xhat, z = saved
-        gx = new_buf(tape, self, "gx", x.shape) if need_gx else None
-        scratch = new_buf(tape, self, "gpre", gy.shape) if act != _lib.ACT_IDENTITY else None
+        gx = new_buf(tape, self, "gx", x.shape) if (need_gx and lift is None) else None
+        full = (x.shape[0], self.call_out_channels) + tuple(x.shape[2:])
+        scratch = new_buf(tape, self, "gpre", full) if act != _lib.ACT_IDENTITY else None
         bw = bypass.weight if bypass is not None else None
         bb = bypass.bias if bypass is not None else None
         gbw = bypass.grad("weight") if bypass is not None else None
         gbb = bypass.grad("bias") if (bypass is not None and bypass.bias is not None) else None
+        if gy_w is not None or lift is not None:
+            u, lgw, lgb = lift if lift is not None else (None, None, None)
+            if lift is not None:
+                gx = None
+            _lib.check(_lib.lib().pdeqx_spectral_block_bwd_ex(
+                plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(gy_w), _lib.ptr(u), _lib.ptr(lgw), _lib.ptr(lgb),
+                _lib.ptr(self.weights_real),
+                _lib.ptr(self.weights_imag), _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),
+                _lib.ptr(self.grad("weights_real")), _lib.ptr(self.grad("weights_imag")), _lib.ptr(gbw), _lib.ptr(gbb),
+                _lib.ptr(scratch), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))
+            return gx
         _lib.check(_lib.lib().pdeqx_spectral_block_bwd(
             plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(self.weights_real), _lib.ptr(self.weights_imag),
             _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),

@@ -373,12 +373,16 @@ extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const floa
   return pdeqx_pointwise_fwd(d.batch, d.c_in, d.c_out, n_pix, x, bypass_w, bypass_b, /*add=*/y, act, y, stream);
 }
 
-extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const float* x, const float* gy,
-                                        const float* w_re, const float* w_im, const float* bypass_w,
-                                        const float* bypass_b, int32_t act, const float* saved_xhat,
-                                        const float* saved_z, float* gx, float* gw_re, float* gw_im,
-                                        float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+// gy_w != null: the cotangent is rank one, gy[b,o,pixel] = gy_w[o] * gy[b,pixel] (gy then holds the single-channel factor)
+// lift_u != null: gx is not produced; the block's input came from the single-channel field lift_u through a 1 -> c_in
+// pointwise lifting, whose gradients lift_gw[i] = sum gx[b,i,pixel] lift_u[b,pixel], lift_gb[i] = sum gx[b,i,pixel] are
+// accumulated by the last kernel instead
+static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x, const float* gy, const float* gy_w,
+                                   const float* lift_u, float* lift_gw, float* lift_gb, const float* w_re, const float* w_im, const float* bypass_w,
+                                   const float* bypass_b, int32_t act, const float* saved_xhat,
+                                   const float* saved_z, float* gx, float* gw_re, float* gw_im,
+                                   float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(p && x && gy && w_re && w_im && saved_xhat && gw_re && gw_im, "null argument");
   PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
   PDEQX_CHECK_ARG(!bypass_w || g_bypass_w, "g_bypass_w is required when bypass_w is given");
@@ -398,7 +402,9 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
   const bool fuse_bypass_gx = fast && bypass_w && gx;
   bool r2c_done = false;
   const int chunk = bwd_chunk_samples(p, n_pix);
-  if (fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
+  PDEQX_CHECK_ARG(!gy_w || (fast && act != PDEQX_ACT_IDENTITY),
+                  "a rank-1 cotangent needs the tcgen05 slab kernel and a fused activation (pdeqx_spectral_block_rank1_ok)");
+  if (!gy_w && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
     // Steps 1-3a in sample chunks small enough for the 126 MB L2: the cotangent chunk written by the slab kernel is
     // still L2-resident when the bypass weight gradient and the first DFT stage read it back, and so is most of x.
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
@@ -431,7 +437,9 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
     if (fast) {
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-      PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/1, gy, d.c_in, d.c_out, scratch_full, s));
+      // mode 2: the cotangent tile is formed in the epilogue from its two factors instead of being read from HBM
+      PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/gy_w ? 2 : 1, gy, d.c_in, d.c_out, scratch_full, s,
+                           gy_w));
     } else {
       PDEQX_TRY(stage_c2r(p, saved_z, p->t_c2r_inv, rows_o, nullptr, PDEQX_ACT_IDENTITY, scratch_full, s));
       if (bypass_w)
@@ -467,7 +475,8 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
   PDEQX_TRY(forward_chain(p, gpre, d.c_out, /*adjoint_of_inverse=*/true, ghat, r, s, r2c_done));
   // 4. weight gradient (batch-reduced inside the kernel)
   PDEQX_TRY(mode_mix_dw(p, ghat, saved_xhat, gw_re, gw_im, s));
-  if (!gx) return PDEQX_OK;
+  PDEQX_CHECK_ARG(!lift_u || (fast && bypass_w), "the fused lifting gradients need the tcgen05 slab kernel (pdeqx_spectral_block_rank1_ok)");
+  if (!gx && !lift_u) return PDEQX_OK;
   // 5. g_xhat = W^H g_yhat
   float* gxhat = r.mode[1];
   PDEQX_TRY(mode_mix(p, ghat, w_re, w_im, /*transposed_conj=*/true, gxhat, s));
@@ -479,9 +488,43 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
     gx1 = t;
   }
   // 7. last stage back to real space, plus the bypass contribution W^T gpre
+  if (fast && lift_u) {
+    TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+    PDEQX_CUDA(cudaMemsetAsync(lift_gw, 0, sizeof(float) * (size_t)d.c_in, s));
+    if (lift_gb) PDEQX_CUDA(cudaMemsetAsync(lift_gb, 0, sizeof(float) * (size_t)d.c_in, s));
+    return tc_slab_ex(p, gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, /*mode=*/3,
+                      lift_u, d.c_out, d.c_in, nullptr, s, nullptr, lift_gw, lift_gb);
+  }
   if (fast) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     return tc_slab(p, gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, gx, s);
   }
   return stage_c2r(p, gx1, p->t_c2r_bwd, rows_i, gx_has_bypass ? gx : nullptr, PDEQX_ACT_IDENTITY, gx, s);
+}
+
+extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const float* x, const float* gy,
+                                        const float* w_re, const float* w_im, const float* bypass_w,
+                                        const float* bypass_b, int32_t act, const float* saved_xhat,
+                                        const float* saved_z, float* gx, float* gw_re, float* gw_im,
+                                        float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return spectral_block_bwd_impl(p, x, gy, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, saved_xhat, saved_z, gx, gw_re, gw_im,
+                                 g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* p, int32_t has_bypass, int32_t act) {
+  return p && act != PDEQX_ACT_IDENTITY && tc_slab_available(p, has_bypass != 0) ? 1 : 0;
+}
+
+extern "C" int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* p, const float* x, const float* gy,
+                                           const float* gy_w, const float* lift_u, float* lift_gw, float* lift_gb,
+                                           const float* w_re, const float* w_im, const float* bypass_w,
+                                           const float* bypass_b, int32_t act, const float* saved_xhat,
+                                           const float* saved_z, float* gx, float* gw_re, float* gw_im,
+                                           float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(!lift_u || (lift_gw && !gx), "lift_u needs lift_gw and replaces gx");
+  return spectral_block_bwd_impl(p, x, gy, gy_w, lift_u, lift_gw, lift_gb, w_re, w_im, bypass_w, bypass_b, act, saved_xhat,
+                                 saved_z, gx, gw_re, gw_im, g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes,
+                                 stream);
 }

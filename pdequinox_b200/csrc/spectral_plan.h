@@ -58,10 +58,12 @@ bool tc_c2c_available(const pdeqx_spectral_plan* p, int axis, int kind, int64_t 
 // stage truncate the operand
 int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, float* out, int64_t outer, int64_t inner_complex,
            cudaStream_t s, bool round_out = false);
-// general form: explicit channel counts of THIS call, epilogue mode 1 = aux * act'(.) (cotangent of the pre-activation)
+// general form: explicit channel counts of THIS call, epilogue mode 1 = aux * act'(.) (cotangent of the pre-activation),
+// mode 2 = the same with a rank-1 cotangent aux_w[o] * aux[b, pixel] (behind a C -> 1 pointwise projection),
+// mode 3 = nothing stored: red_w[o] += sum result * aux[b, pixel], red_b[o] += sum result (in front of a 1 -> C lifting)
 int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
-               float* y, cudaStream_t s);
+               float* y, cudaStream_t s, const float* aux_w = nullptr, float* red_w = nullptr, float* red_b = nullptr);
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);
 // gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller)
 int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb,

@@ -82,7 +82,7 @@ static float host_round_tf32(float v) {  // round-to-nearest (ties away), like c
   return r;
 }
 
-constexpr int kThreadsSlab = 384;   // warps 0-2 roles, warp 3 idle, warps 4-11 epilogue
+constexpr int kThreadsSlab = 640;   // warps 0-2 roles, warp 3 idle, warps 4-19 epilogue (4 per TMEM lane quarter)
 constexpr int kThreadsR2c = 256;    // warps 0-2 roles, warp 3 idle, warps 4-7 epilogue
 constexpr int kTmemCols = 256;
 
@@ -115,12 +115,16 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // ==========================================================================================
 struct SlabParams {
   int lead, W, wt_per_row, c_in, c_out;
+  int parts;  // epilogue warps per TMEM lane quarter: each owns c_out / parts channels (4, or 2 when c_out < 64)
   int rpu;  // image rows per 128-pixel unit: 1 for W >= 128 (W / 128 units per row), 128 / W for narrower grids
   int has_bypass, mode, act, round_out;
   int stages;
   int64_t units;  // B * lead * wt_per_row
   const float* bias;
-  const float* aux;  // mode 1: cotangent gy
+  const float* aux;  // mode 1: cotangent gy [B, c_out, lead, W]; mode 2: its single-channel factor gy1 [B, lead, W]
+  float* red_w;        // mode 3: out[o] += sum_{b,pixel} result[b,o,pixel] * aux[b,pixel]   (aux = single-channel field)
+  float* red_b;        // mode 3: out[o] += sum_{b,pixel} result[b,o,pixel]                 (may be null)
+  const float* aux_w;  // mode 2: the per-channel factor, gy[b,o,p] = aux_w[o] * gy1[b,p] (cotangent behind a C -> 1 projection)
   float* y;
 };
 
@@ -147,14 +151,14 @@ static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, i
   s.stage_off = off;
   off += s.stage_bytes * stages;
   // epilogue staging: `epi_bufs` output tiles [c_out x 128 w] fp32 (TMA store source / aux target), each stored as four
-  // SWIZZLE_128B chunks [c_out rows x 32 w]: every epilogue warp owns one 128-byte-row box per half (its own TMA box)
+  // SWIZZLE_128B chunks [c_out rows x 32 w]: every epilogue warp owns one 128-byte-row box per part (its own TMA box)
   s.epi_off = off;
   s.chunk_bytes = (uint32_t)c_out * 128;
   s.epi_buf_bytes = 4 * s.chunk_bytes;
   off += (uint32_t)epi_bufs * s.epi_buf_bytes;
   s.epi_bufs = (uint32_t)epi_bufs;
   s.bar_off = off;
-  off += 1024;  // barriers, tmem pointer, bias
+  off += 2048;  // barriers, tmem pointer, bias, rank-1 cotangent factor
   s.total = off + 1024;  // slack for manual 1024-B alignment of the dynamic base
   return s;
 }
@@ -173,8 +177,9 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint64_t* tempty = bars + 18;            // [2]
   uint64_t* tabfull = bars + 20;           // [1]
   uint32_t* tmem_ptr = (uint32_t*)(bars + 22);
-  uint64_t* auxfull = bars + 24;           // [8 epilogue warps][3 buffers] cotangent chunk landed (MODE 1)
-  float* bias_s = (float*)(bars + 48);     // [c_out] (<= 128 floats)
+  uint64_t* auxfull = bars + 24;           // [16 epilogue warps][3 buffers] cotangent chunk landed (MODE 1)
+  float* bias_s = (float*)(bars + 72);     // [c_out] (<= 128 floats)
+  float* auxw_s = bias_s + 128;            // [c_out] per-channel factor of a rank-1 cotangent (MODE 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -192,15 +197,18 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8);
-    mbar_init(&tempty[1], 8);
+    mbar_init(&tempty[0], 4 * p.parts);
+    mbar_init(&tempty[1], 4 * p.parts);
     mbar_init(tabfull, 1);
-    for (int i = 0; i < 24; ++i) mbar_init(&auxfull[i], 1);
+    for (int i = 0; i < 48; ++i) mbar_init(&auxfull[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
   if (warp == 3) {
-    for (int i = lane; i < p.c_out; i += 32) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = lane; i < p.c_out; i += 32) {
+      bias_s[i] = p.bias ? p.bias[i] : 0.f;
+      auxw_s[i] = (MODE == 2 && p.aux_w) ? p.aux_w[i] : 0.f;
+    }
     if (lane == 0) {
       tma_prefetch_desc(&tm_y);
       tma_prefetch_desc(&tm_aux);
@@ -279,18 +287,19 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         if (++a == 2) { a = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < p.parts) {
     // ===================== epilogue: TMEM -> registers -> smem tile -> TMA store =====================
-    // Eight autonomous warps: warp (half, q) owns the [c_out/2 channels x 32 w] piece of the output tile that its TMEM
+    // The kernel is bound by the latency of this stage (TMEM load -> activation math -> shared store), not by its issue
+    // rate, so it gets 16 warps. Autonomous warps: warp (part, q) owns the [c_out/parts channels x 32 w] piece of the output tile that its TMEM
     // lane quarter produces -- one swizzled 128-byte-row box. It fills the piece, stores it with its own TMA store and
     // (mode 1) prefetches its own piece of the cotangent tile two units ahead: no CTA-level barrier in the loop.
     // The tile [c_out x 128 w] is laid out as four SWIZZLE_128B chunks [c_out rows x 32 w].
     const int q = warp & 3;            // TMEM lane quarter this warp may read = 32-w chunk of the tile
-    const int half = (warp - 4) >> 2;  // which half of the output channels
-    const int ncol = p.c_out / 2;
+    const int part = (warp - 4) >> 2;  // which slice of the output channels
+    const int ncol = p.c_out / p.parts;
     const int NB = (int)L.epi_bufs;  // 2 (MODE 0) or 3 (MODE 1: the cotangent piece is prefetched two units ahead)
-    uint8_t* ebuf0 = smem + L.epi_off + (size_t)q * L.chunk_bytes + (size_t)half * ncol * 128;  // this warp's piece in buffer 0
-    uint64_t* afull = auxfull + (half * 4 + q) * 3;
+    uint8_t* ebuf0 = smem + L.epi_off + (size_t)q * L.chunk_bytes + (size_t)part * ncol * 128;  // this warp's piece in buffer 0
+    uint64_t* afull = auxfull + (part * 4 + q) * 3;
     int a = 0, e = 0;
     uint32_t aph = 0, eph = 0;
     auto load_aux = [&](int64_t un, int buf) {
@@ -299,8 +308,13 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int lu = p.lead / p.rpu;
       mbar_expect_tx(&afull[buf], (uint32_t)ncol * 128);
       tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], pxn % p.W, (int)(bln % lu) * p.rpu + pxn / p.W,
-                  (int)(bln / lu) * p.c_out + half * ncol);
+                  (int)(bln / lu) * p.c_out + part * ncol);
     };
+    float racc_w[2][16], racc_b[2][16];  // MODE 3 only (dead otherwise); c_out / parts <= 32 channels per warp
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) racc_w[ci][j] = racc_b[ci][j] = 0.f;
     if (MODE == 1 && lane == 0) {
       if (first < p.units) load_aux(first, 0);
       if (first + stride < p.units) load_aux(first + stride, 1);
@@ -314,14 +328,44 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       uint8_t* piece = ebuf0 + (size_t)e * L.epi_buf_bytes;
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
+      float sv = 0.f;  // MODE 2: this lane's pixel of the single-channel cotangent factor
       if (MODE == 1) {
         mbar_wait(&afull[e], eph);
       } else {
+        if (MODE == 2 || MODE == 3) sv = __ldg(p.aux + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane);
         // this warp's store that last used the piece (NB units ago) must have finished reading it
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        if (MODE != 3) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
       }
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.c_out + half * ncol);
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.c_out + part * ncol);
+      if (MODE == 3) {
+        // nothing is stored: the result only feeds the gradients of the 1 -> C pointwise lifting that produced this
+        // block's input from the single-channel field `aux` -- per-channel dot products kept in registers across units
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = ci * 16;
+          if (c0 < ncol) {
+            float v[16];
+            tmem_ld16(t0 + c0, v);
+            tmem_ld_wait();
+            if (c0 + 16 >= ncol) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[a]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float r = v[j] + bias_s[part * ncol + c0 + j];
+              racc_w[ci][j] = fmaf(r, sv, racc_w[ci][j]);
+              racc_b[ci][j] += r;
+            }
+          }
+        }
+        if (++a == 2) { a = 0; aph ^= 1; }
+        continue;
+      }
       // element (o_local, w = 32 q + lane): row o_local of the piece, 16-byte units XOR-swizzled by (row & 7)
       const uint32_t col = smem_u32(piece);
       const uint32_t lane_b = (uint32_t)lane * 4;
@@ -338,10 +382,13 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         if (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) g[j] = ld_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)));
+        } else if (MODE == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = auxw_s[part * ncol + c0 + j] * sv;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float val = v[j] + bias_s[half * ncol + c0 + j];
+          const float val = v[j] + bias_s[part * ncol + c0 + j];
           float r;
           if (MODE == 0) {
             if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_f<true>(val);
@@ -358,7 +405,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&tm_y, piece, px % p.W, l, b * p.c_out + half * ncol);
+        tma_store_3d(&tm_y, piece, px % p.W, l, b * p.c_out + part * ncol);
         tma_store_commit();
         if (MODE == 1) {
           const int64_t un = u + 2 * stride;
@@ -370,6 +417,26 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
       if (++a == 2) { a = 0; aph ^= 1; }
       if (++e == NB) { e = 0; eph ^= 1; }
+    }
+    if (MODE == 3) {
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        if (ci * 16 < ncol) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float vw = racc_w[ci][j], vb = racc_b[ci][j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              vw += __shfl_xor_sync(0xffffffffu, vw, off);
+              vb += __shfl_xor_sync(0xffffffffu, vb, off);
+            }
+            if (lane == 0) {
+              atomicAdd(p.red_w + part * ncol + ci * 16 + j, vw);
+              if (p.red_b) atomicAdd(p.red_b + part * ncol + ci * 16 + j, vb);
+            }
+          }
+        }
+      }
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -867,11 +934,14 @@ bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass) {
 // (bypass_transposed: bypass_w is [c_i_of_this_call... see spectral.cu) ; mode 1: y = aux * act'(.)
 int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
-               float* y, cudaStream_t s) {
+               float* y, cudaStream_t s, const float* aux_w, float* red_w, float* red_b) {
   TcPlan* t = tcp(p);
   const pdeqx_spectral_desc& d = p->desc;
   const int D = d.ndim, sD = d.spatial[D - 1];
   const int64_t lead = p->lead;
+  PDEQX_CHECK_ARG(mode != 2 || (aux && aux_w), "tc_slab: mode 2 needs the cotangent factors");
+  PDEQX_CHECK_ARG(mode != 3 || (aux && red_w && act == PDEQX_ACT_IDENTITY), "tc_slab: mode 3 needs the field, an output and no activation");
+  if (mode == 3) y = red_w;  // (no tile is stored; the tensor map below only needs a valid 16-byte aligned base)
   PDEQX_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!x || ((uintptr_t)x & 15) == 0),
                   "tc_slab: pointers must be 16-byte aligned");
   const bool bypass = bypass_w != nullptr;
@@ -905,7 +975,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   {
     uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * c_out};
     uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)(c_out / 2)};
+    uint32_t box[3] = {32, 1, (uint32_t)(c_out / (c_out >= 64 ? 4 : 2))};  // one epilogue warp's piece
     PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box));
     if (mode == 1) {
       PDEQX_CHECK_ARG(aux && ((uintptr_t)aux & 15) == 0, "tc_slab: aux must be a 16-byte aligned device pointer");
@@ -917,6 +987,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   tc::SlabParams sp{};
   sp.lead = (int)lead;
   sp.W = sD;
+  sp.parts = c_out >= 64 ? 4 : 2;
   sp.rpu = sD >= 128 ? 1 : 128 / sD;
   sp.wt_per_row = sD >= 128 ? sD / 128 : 1;
   sp.c_in = c_in;
@@ -928,6 +999,9 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.units = (int64_t)d.batch * (lead / sp.rpu) * sp.wt_per_row;
   sp.bias = bypass_b;
   sp.aux = aux;
+  sp.aux_w = aux_w;
+  sp.red_w = red_w;
+  sp.red_b = red_b;
   sp.y = y;
   // mode 1 keeps three epilogue tiles (cotangent prefetch distance 2); the load pipeline gets what is left
   const int epi_bufs = mode == 1 ? 3 : 2;
@@ -940,7 +1014,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   int grid = (int)(sp.units < t->sms ? sp.units : t->sms);
   grid = grid / sp.wt_per_row * sp.wt_per_row;  // every CTA keeps one w-tile of the table (units stride by the grid size)
   PDEQX_CHECK_ARG(grid >= sp.wt_per_row, "tc_slab: grid smaller than the number of w-tiles");
-  PDEQX_CHECK_ARG(mode == 0 || act != PDEQX_ACT_IDENTITY, "tc_slab: mode 1 needs an activation");
+  PDEQX_CHECK_ARG(mode == 0 || mode == 3 || act != PDEQX_ACT_IDENTITY, "tc_slab: modes 1 and 2 need an activation");
   const CUtensorMap& tab = t->tm_tab_c2r[table_sel];
 #define PDEQX_SLAB_LAUNCH(M, A)                                                                                        \
   do {                                                                                                                 \
@@ -951,11 +1025,14 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
     }                                                                                                                  \
     tc::slab_kernel<M, A><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L);          \
   } while (0)
-  if (mode == 0 && act == PDEQX_ACT_IDENTITY) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_IDENTITY);
+  if (mode == 3) PDEQX_SLAB_LAUNCH(3, PDEQX_ACT_IDENTITY);
+  else if (mode == 0 && act == PDEQX_ACT_IDENTITY) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_IDENTITY);
   else if (mode == 0 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_RELU);
   else if (mode == 0) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_GELU_TANH);
-  else if (act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_RELU);
-  else PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_GELU_TANH);
+  else if (mode == 1 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_RELU);
+  else if (mode == 1) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_GELU_TANH);
+  else if (act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_RELU);
+  else PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_GELU_TANH);
 #undef PDEQX_SLAB_LAUNCH
   PDEQX_LAUNCHED();
   return PDEQX_OK;
@@ -965,7 +1042,7 @@ int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int ta
             bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s) {
   const pdeqx_spectral_desc& d = p->desc;
   const int c_in = bypass_transposed ? d.c_out : d.c_in, c_out = bypass_transposed ? d.c_in : d.c_out;
-  return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s);
+  return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s, nullptr, nullptr, nullptr);
 }
 
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix) {

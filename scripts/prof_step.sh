@@ -1,2 +1,2 @@
-python bench.py --steps 3 --warmup 3 --precision tf32 --no-cpu-baseline > gpurun_out/bench_tf32_v3.json 2> gpurun_out/bench_tf32_v3.err && ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 200 --csv --log-file gpurun_out/step_launches.csv python bench.py --steps 3 --warmup 3 --precision tf32 --no-cpu-baseline > /dev/null 2>&1
-head -c 400 gpurun_out/bench_tf32_v3.json; echo
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain_bench.log 2>&1 &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 240 --csv --log-file gpurun_out/r1_step_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > /dev/null 2>&1

@@ -107,18 +107,29 @@ def test_tf32_plain_spectral_conv(cuda):
         pdeqx.set_precision("fp32")
 
 
-def test_tf32_fno_train_step(cuda):
-    """Whole ClassicFNO train step in TF32 mode vs the oracle (2 blocks, hidden 32, 64x128 grid)."""
+@pytest.mark.parametrize("D,spatial,hidden,modes,blocks", [
+    (2, (64, 128), 32, 16, 2),   # projection folded into the last block (rank-one cotangent), lifting into the first
+    (2, (32, 128), 64, 16, 1),   # one block: both folds in the same reverse pass
+    (2, (64, 64), 32, 12, 3),    # padded modes, two rows per slab unit
+    (3, (32, 32, 64), 32, 12, 2),
+])
+def test_tf32_fno_train_step(cuda, D, spatial, hidden, modes, blocks):
+    """Whole ClassicFNO train step in TF32 mode vs the oracle."""
     from pdequinox_b200.train import TrainStep
     pdeqx.set_precision("tf32")
     try:
         rng = np.random.default_rng(13)
-        model = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=32, num_modes=16, num_blocks=2, key=5)
+        model = pdeqx.ClassicFNO(D, 1, 1, hidden_channels=hidden, num_modes=modes, num_blocks=blocks, key=5)
         step = TrainStep(model)
+        # non-zero lifting / projection biases so that every folded gradient is exercised
+        with torch.no_grad():
+            named = step.arena.named_params()
+            named["lifting.bias"].add_(0.3)
+            named["projection.bias"].add_(-0.2)
         p = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in step.arena.named_params().items()}
-        x = rng.standard_normal((2, 1, 64, 128))
-        y = rng.standard_normal((2, 1, 64, 128))
-        loss_ref, g_ref = onn.fno_loss_and_grad(p, x, y, (16, 16), 2)
+        x = rng.standard_normal((2, 1) + spatial)
+        y = rng.standard_normal((2, 1) + spatial)
+        loss_ref, g_ref = onn.fno_loss_and_grad(p, x, y, (modes,) * D, blocks)
         loss = step.loss_and_grad(x, y).item()
         assert abs(loss - loss_ref) <= 5e-3 * abs(loss_ref)
         g = {k: v.detach().cpu().numpy() for k, v in step.arena.named_grads().items()}
