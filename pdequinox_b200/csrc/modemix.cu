@@ -175,14 +175,26 @@ struct TiledArgs {
 
 constexpr int TM_KC = 8;  // K chunk; a CTA covers 8 * RT rows (RT = rows per thread: small batches shrink the tile)
 
+// cp.async (LDGSTS) with zero fill: `bytes` of 4 or 8 are copied when `pred`, else the destination is zero-filled
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int src_bytes = pred ? BYTES : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(gsrc), "n"(BYTES), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int PT, int RT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 __global__ void __launch_bounds__(256, 2)
 mode_gemm_tiled_kernel(TiledArgs t) {
   constexpr int NQ = 32 / PT;   // n-quads per warp-row group ... threads = PT * 8 * NQ
   constexpr int NT = 4 * NQ;    // columns per CTA
   constexpr int TM_MT = 8 * RT; // rows per CTA
-  __shared__ float2 As[TM_KC][TM_MT][PT];
-  __shared__ float2 Bs[TM_KC][NT][PT];
+  constexpr int A_ELEMS = TM_KC * TM_MT * PT, B_ELEMS = TM_KC * NT * PT;
+  // two stages of [A chunk: KC x MT x PT][B chunk: KC x NT x PT] float2, filled by cp.async one K chunk ahead of the math
+  extern __shared__ float2 tile_smem[];
   const int tid = threadIdx.x;
   const int pm = tid % PT, mq = (tid / PT) % 8, nq = tid / (PT * 8);
   const int64_t p0 = (int64_t)blockIdx.x * PT;
@@ -197,45 +209,62 @@ mode_gemm_tiled_kernel(TiledArgs t) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
 
-  for (int k0 = 0; k0 < (valid ? t.K : 0); k0 += TM_KC) {  // padding tile: interleaved outputs get zeros, planar ones nothing
+  auto issue = [&](int k0, int stage) {
+    float2* As = tile_smem + (size_t)stage * (A_ELEMS + B_ELEMS);
+    float2* Bs = As + A_ELEMS;
     // A chunk: [KC][MT][PT] float2, PT contiguous in global memory
-    for (int idx = tid; idx < TM_KC * TM_MT * PT; idx += 256) {
+    for (int idx = tid; idx < A_ELEMS; idx += 256) {
       const int q = idx % PT, m = (idx / PT) % TM_MT, k = idx / (PT * TM_MT);
-      float2 v = make_float2(0.f, 0.f);
-      if (m0 + m < t.M && k0 + k < t.K) v = __ldg(t.a + (int64_t)(m0 + m) * t.a_sm + (int64_t)(k0 + k) * t.a_sk + p0 + q);
-      As[k][m][q] = v;
+      const bool ok = m0 + m < t.M && k0 + k < t.K;
+      const float2* src = ok ? t.a + (int64_t)(m0 + m) * t.a_sm + (int64_t)(k0 + k) * t.a_sk + p0 + q : t.a;
+      cp_async_zfill<8>(As + idx, src, ok);
     }
-    for (int idx = tid; idx < TM_KC * NT * PT; idx += 256) {
+    for (int idx = tid; idx < B_ELEMS; idx += 256) {
       const int q = idx % PT, n = (idx / PT) % NT, k = idx / (PT * NT);
-      float2 v = make_float2(0.f, 0.f);
-      if (n0 + n < t.N && k0 + k < t.K) {
-        if (B_PLANAR) {
-          const int64_t off = (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + woff + q;
-          v = make_float2(__ldg(t.br + off), __ldg(t.bi + off));
-        } else {
-          v = __ldg(t.b2 + (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + p0 + q);
-        }
-        if (CONJ_B) v.y = -v.y;
+      const bool ok = n0 + n < t.N && k0 + k < t.K;
+      if (B_PLANAR) {
+        const int64_t off = ok ? (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + woff + q : 0;
+        cp_async_zfill<4>(&Bs[idx].x, t.br + off, ok);
+        cp_async_zfill<4>(&Bs[idx].y, t.bi + off, ok);
+      } else {
+        const float2* src = ok ? t.b2 + (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + p0 + q : t.b2;
+        cp_async_zfill<8>(Bs + idx, src, ok);
       }
-      Bs[k][n][q] = v;
+    }
+    cp_async_commit();
+  };
+
+  const int nchunks = valid ? (t.K + TM_KC - 1) / TM_KC : 0;  // padding tile: interleaved outputs get zeros, planar ones nothing
+  if (nchunks > 0) issue(0, 0);
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) {
+      issue((c + 1) * TM_KC, (c + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const float2* As = tile_smem + (size_t)(c & 1) * (A_ELEMS + B_ELEMS);
+    const float2* Bs = As + A_ELEMS;
 #pragma unroll
     for (int k = 0; k < TM_KC; ++k) {
       float2 a[RT], b[4];
 #pragma unroll
-      for (int r = 0; r < RT; ++r) a[r] = As[k][mq + 8 * r][pm];
+      for (int r = 0; r < RT; ++r) a[r] = As[(k * TM_MT + mq + 8 * r) * PT + pm];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) b[c] = Bs[k][nq * 4 + c][pm];
+      for (int cc = 0; cc < 4; ++cc) {
+        b[cc] = Bs[(k * NT + nq * 4 + cc) * PT + pm];
+        if (CONJ_B) b[cc].y = -b[cc].y;
+      }
 #pragma unroll
       for (int r = 0; r < RT; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          acc[r][c].x = fmaf(a[r].x, b[c].x, fmaf(-a[r].y, b[c].y, acc[r][c].x));
-          acc[r][c].y = fmaf(a[r].x, b[c].y, fmaf(a[r].y, b[c].x, acc[r][c].y));
+        for (int cc = 0; cc < 4; ++cc) {
+          acc[r][cc].x = fmaf(a[r].x, b[cc].x, fmaf(-a[r].y, b[cc].y, acc[r][cc].x));
+          acc[r][cc].y = fmaf(a[r].x, b[cc].y, fmaf(a[r].y, b[cc].x, acc[r][cc].y));
         }
     }
-    __syncthreads();
+    __syncthreads();  // the stage is refilled by the prefetch of the next iteration
   }
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
@@ -265,12 +294,24 @@ static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
   const int nt = 4 * (32 / PT);
   dim3 grid((unsigned)(t.J / PT), (unsigned)ceil_div(t.M, 8 * rt), (unsigned)ceil_div(t.N, nt));
   if (grid.y > 65535 || grid.z > 65535) return false;
+#define PDEQX_MODE_GEMM(RT_)                                                                                            \
+  do {                                                                                                                 \
+    const size_t smem = (size_t)2 * TM_KC * (8 * RT_ + nt) * PT * sizeof(float2);                                      \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      cudaFuncSetAttribute(mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B>,                                \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                                    \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, smem, s>>>(t);                            \
+  } while (0)
   switch (rt) {
-    case 1: mode_gemm_tiled_kernel<PT, 1, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
-    case 2: mode_gemm_tiled_kernel<PT, 2, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
-    case 4: mode_gemm_tiled_kernel<PT, 4, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
-    default: mode_gemm_tiled_kernel<PT, 8, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, 0, s>>>(t); break;
+    case 1: PDEQX_MODE_GEMM(1); break;
+    case 2: PDEQX_MODE_GEMM(2); break;
+    case 4: PDEQX_MODE_GEMM(4); break;
+    default: PDEQX_MODE_GEMM(8); break;
   }
+#undef PDEQX_MODE_GEMM
   return true;
 }
 

@@ -419,6 +419,9 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (++e == NB) { e = 0; eph ^= 1; }
     }
     if (MODE == 3) {
+      // warp-level reduction over the 32 pixels, then the four lane-quarter warps of a channel slice are combined in
+      // shared memory (the output tiles are idle in this mode): ONE atomic per channel and CTA
+      float* red_s = (float*)(smem + L.epi_off);  // [2 (w, b)][4 q][c_out]
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         if (ci * 16 < ncol) {
@@ -431,10 +434,24 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               vb += __shfl_xor_sync(0xffffffffu, vb, off);
             }
             if (lane == 0) {
-              atomicAdd(p.red_w + part * ncol + ci * 16 + j, vw);
-              if (p.red_b) atomicAdd(p.red_b + part * ncol + ci * 16 + j, vb);
+              red_s[(0 * 4 + q) * p.c_out + part * ncol + ci * 16 + j] = vw;
+              red_s[(1 * 4 + q) * p.c_out + part * ncol + ci * 16 + j] = vb;
             }
           }
+        }
+      }
+      named_bar_sync(1, 128 * p.parts);
+      if (q == 0) {
+        for (int c = lane; c < ncol; c += 32) {
+          const int ch = part * ncol + c;
+          float vw = 0.f, vb = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            vw += red_s[(0 * 4 + qq) * p.c_out + ch];
+            vb += red_s[(1 * 4 + qq) * p.c_out + ch];
+          }
+          atomicAdd(p.red_w + ch, vw);
+          if (p.red_b) atomicAdd(p.red_b + ch, vb);
         }
       }
     }
