@@ -83,25 +83,40 @@ pw_small_cout_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   const float* ab = add ? add + (int64_t)b * cout * n : nullptr;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
     float acc[kSmallC][VEC];
-    for (int o = 0; o < cout; ++o)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) acc[o][e] = sw[cin * cout + o];
-#pragma unroll 4
-    for (int i = 0; i < cin; ++i) {
-      float xv[VEC];
-      if (VEC == 4) {
-        float4 t = __ldg((const float4*)(xb + (int64_t)i * n) + v);
-        xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
-      } else {
-        xv[0] = __ldg(xb + (int64_t)i * n + v);
+    for (int o = 0; o < kSmallC; ++o)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[o][e] = o < cout ? sw[cin * cout + o] : 0.f;
+    // 16 channel rows in flight per thread: the kernel is a pure stream over x (one 16-byte load per channel and thread)
+    for (int i0 = 0; i0 < cin; i0 += 16) {
+      float xv[16][VEC];
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) {
+        const int i = i0 + ii < cin ? i0 + ii : cin - 1;
+        if (VEC == 4) {
+          float4 t = __ldg((const float4*)(xb + (int64_t)i * n) + v);
+          xv[ii][0] = t.x; xv[ii][1 % VEC] = t.y; xv[ii][2 % VEC] = t.z; xv[ii][3 % VEC] = t.w;
+        } else {
+          xv[ii][0] = __ldg(xb + (int64_t)i * n + v);
+        }
       }
-      for (int o = 0; o < cout; ++o) {
-        float wv = sw[o * cin + i];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[o][e] = fmaf(wv, xv[e], acc[o][e]);
+      for (int ii = 0; ii < 16; ++ii) {
+        if (i0 + ii < cin) {
+#pragma unroll
+          for (int o = 0; o < kSmallC; ++o) {  // static register indices: `cout` only predicates
+            if (o < cout) {
+              float wv = sw[o * cin + i0 + ii];
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) acc[o][e] = fmaf(wv, xv[ii][e], acc[o][e]);
+            }
+          }
+        }
       }
     }
-    for (int o = 0; o < cout; ++o) {
+#pragma unroll
+    for (int o = 0; o < kSmallC; ++o) {
+      if (o >= cout) break;
       if (VEC == 4) {
         if (ab) {
           float4 t = __ldg((const float4*)(ab + (int64_t)o * n) + v);

@@ -686,10 +686,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(128, N, false, false);
       const uint32_t idesc2 = idesc_tf32(128, 32, false, false);
+      // The issuing thread is the critical resource of this kernel (8 MMAs per 16 KB stage): descriptors are built once,
+      // per MMA only the 14-bit start-address field moves (>> 4 units: +2 per 32-byte K step)
+      const uint64_t d0 = smem_desc_sw128(smem_u32(stage0), 0, 1024);
+      const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+      const uint32_t stage16 = stage_bytes >> 4, g16 = g_bytes >> 4;
+      const uint32_t tab_lo0 = (uint32_t)smem_desc_sw128(smem_u32(smem), 0, 1024);
       if (fused) mbar_wait(tabfull, 0);
       int s = 0, it = 0;
       uint32_t ph = 0;
-      bool acc = false;
+      uint32_t acc = 0;
       for (int64_t r = first; r < p.rows; r += stride, ++it) {
         const int a2 = it & 1;
         if (fused) {
@@ -700,19 +706,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
         for (int c = 0; c < p.chunks_per_row; ++c) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
+          const uint32_t a_lo = lo0 + (uint32_t)s * stage16;  // A: 128 rows from the g box on
+          const uint32_t b_lo = a_lo + g16;                   // B: x box (+ ones rows)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            mma_tf32(tmem_base, smem_desc_sw128(st + k * 32, 0, 1024), smem_desc_sw128(st + g_bytes + k * 32, 0, 1024), idesc,
-                     acc);
-            acc = true;
+            mma_tf32_lohi(tmem_base, a_lo + k * 2, hi, b_lo + k * 2, hi, idesc, acc);
+            acc = 1;
           }
           if (fused) {
             // same A rows (g rows 0..c_out-1 are the ones kept), B = table chunk [32 k x 32 w] of this pixel chunk
-            const uint32_t tb = smem_u32(smem + c * 4096);
+            const uint32_t t_lo = tab_lo0 + (uint32_t)c * (4096 >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_tf32(d2, smem_desc_sw128(st + k * 32, 0, 1024), smem_desc_sw128(tb + k * 32, 0, 1024), idesc2, (c | k) != 0);
+            for (int k = 0; k < 4; ++k) mma_tf32_lohi(d2, a_lo + k * 2, hi, t_lo + k * 2, hi, idesc2, (c | k) ? 1u : 0u);
           }
           mma_commit(&empty[s]);
           if (++s == S) { s = 0; ph ^= 1; }
