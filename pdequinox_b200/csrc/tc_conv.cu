@@ -22,7 +22,8 @@
 namespace pdeqx {
 namespace tc {
 
-constexpr int kConvThreads = 384;  // warps 0-2: TMA / MMA / TMEM alloc; warps 4-11: epilogue
+constexpr int kConvThreads = 640;  // warps 0-2: TMA / MMA / TMEM alloc; warps 4-19: epilogue (4 per TMEM lane quarter)
+constexpr int kConvOcnt = 8;       // output channels per epilogue warp (NOH = 32 channels per CTA / 4 warps per quarter)
 constexpr int kConvTmemCols = 512;
 constexpr int kAcc = 4;  // accumulator stages in TMEM (4 x 96 columns): the MMA issuer runs up to 4 units ahead of the epilogue
 constexpr int kMaxK = 3;
@@ -57,8 +58,8 @@ static ConvSmem conv_smem(int c_in, int c_out, int k) {
   s.tile_off = off;
   s.tile_bytes = (uint32_t)(c_out / 2) * 512;
   off += s.tile_bytes;  // one output / residual tile (the ring needs the rest of the 227 KB)
-  s.xbuf_off = off;     // edge-column exchange: [2 taps][8 warps][16 channels][kMaxDil] floats
-  off += 2 * 8 * 16 * kMaxDil * 4;
+  s.xbuf_off = off;     // edge-column exchange: [2 taps][16 warps][8 channels][kMaxDil] floats
+  off += 2 * 16 * 8 * kMaxDil * 4;
   s.bar_off = off;
   off += 1024;
   s.total = off + 1024;
@@ -120,6 +121,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   uint64_t* rfull = bars + 17;   // residual tile
   uint32_t* tmem_ptr = (uint32_t*)(bars + 19);
   float* bias_s = (float*)(bars + 20);  // [c_out/2]
+  uint64_t* rfull_w = bars + 40;        // [16 epilogue warps] residual piece landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NOH = p.c_out / 2, N = 3 * NOH;
@@ -138,10 +140,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], 16);
     }
     mbar_init(rfull, 1);
     mbar_init(wfull, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&rfull_w[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kConvTmemCols>(tmem_ptr);
@@ -249,84 +252,95 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // This stage is latency bound (TMEM load -> neighbour exchange -> shared store), so it gets 16 warps: warp (og, q)
+    // owns 8 output channels x the 32 columns of TMEM lane quarter q. Its output piece is its own swizzled 1 KB TMA box
+    // (stored, and for a residual pre-loaded, by the warp itself); the only cross-warp step is the exchange of the d edge
+    // columns between the four lane-quarter warps of one channel group (one 128-thread named barrier).
     const int q = warp & 3;
-    const int og = (warp - 4) >> 2;            // which 16-channel group of the half
-    const int ocnt = NOH / 2;                  // channels per warp (16)
-    const bool leader = (warp == 4 && lane == 0);
+    const int og = (warp - 4) >> 2;            // which 8-channel group of the half
+    constexpr int ocnt = kConvOcnt;            // channels per warp
+    const int wid = og * 4 + q;                // epilogue warp index 0..15
     const int wq = q * 32 + lane;              // this thread's source column w'
     int a = 0;
-    uint32_t aph = 0, eph = 0;
+    uint32_t aph = 0, eph = 0, par = 0;
     // per-thread constants of the column gather: output column wq reads D_0 at colmap(wq - d) and D_2 at colmap(wq + d)
     const int c0 = conv_map(wq - p.d, p.W, p.boundary), c2 = conv_map(wq + p.d, p.W, p.boundary);
     const bool use0 = c0 >= 0, use2 = c2 >= 0;
     const bool in0 = use0 && (c0 >> 5) == q, in2 = use2 && (c2 >> 5) == q;
     const int l0 = c0 & 31, l2 = c2 & 31;
-    float bias_r[16];
+    const int d = p.d;
+    // the exchange slots are double-buffered by unit parity when d <= 4 (two halves of the kMaxDil entries): one barrier
+    // per unit; wider dilations keep a second barrier that protects the buffer against the next unit's writes
+    const bool dbuf = d <= kMaxDil / 2;
+    float bias_r[ocnt];
 #pragma unroll
-    for (int jx = 0; jx < 16; ++jx) bias_r[jx] = bias_s[og * ocnt + jx];
+    for (int jx = 0; jx < ocnt; ++jx) bias_r[jx] = bias_s[og * ocnt + jx];
+    uint8_t* piece_p = smem + L.tile_off + (size_t)wid * 1024;  // [8 channels][32 w] fp32, 128-byte rows, SWIZZLE_128B
+    const uint32_t piece = smem_u32(piece_p);
+    const uint32_t lane_b = (uint32_t)lane * 4;
+    float* xb = (float*)(smem + L.xbuf_off);
+    const uint32_t xbs = smem_u32(xb);
     for (int64_t item = first; item < p.items; item += stride) {
       const ConvItem it = conv_item(p, item);
-      const int ch0 = it.b * p.c_out + it.half * NOH;
-      if (p.has_residual && leader && it.count > 0) {  // first residual tile of the item
+      const int ch0 = it.b * p.c_out + it.half * NOH + og * ocnt;
+      if (p.has_residual && lane == 0 && it.count > 0) {  // first residual piece of the item
         tma_store_wait_read<0>();
-        mbar_expect_tx(rfull, L.tile_bytes);
-        tma_load_3d(smem + L.tile_off, &tm_res, rfull, 0, it.r0 + it.j0 * p.d, ch0);
+        mbar_expect_tx(&rfull_w[wid], 1024);
+        tma_load_3d(piece_p, &tm_res, &rfull_w[wid], q * 32, it.r0 + it.j0 * p.d, ch0);
       }
       for (int jj = 0; jj < it.count; ++jj) {
         const int h = it.r0 + (it.j0 + jj) * p.d;
-        const uint32_t tile = smem_u32(smem + L.tile_off);
         mbar_wait(&tfull[a], aph);
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N + og * ocnt);
-        // the three column taps of this thread's SOURCE column w' = wq (16 channels each), then the accumulator is free
-        float v0[16], v1[16], v2[16];
-        tmem_ld16(t0, v0);
-        tmem_ld16(t0 + (uint32_t)NOH, v1);
-        tmem_ld16(t0 + (uint32_t)(2 * NOH), v2);
+        // the three column taps of this thread's SOURCE column w' = wq (8 channels each), then the accumulator is free
+        float v0[ocnt], v1[ocnt], v2[ocnt];
+        tmem_ld8(t0, v0);
+        tmem_ld8(t0 + (uint32_t)NOH, v1);
+        tmem_ld8(t0 + (uint32_t)(2 * NOH), v2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[a]);
         // Output column w gathers D_0[colmap(w - d)] + D_1[w] + D_2[colmap(w + d)]. Sources inside the warp's own 32 columns
         // come by shuffle; the d columns next to a warp edge (and the wrapped ones) go through a small exchange buffer.
-        const int d = p.d;
-        float* xb = (float*)(smem + L.xbuf_off);
-        float* xb0 = xb + ((0 * 8 + (og * 4 + q)) * 16) * kMaxDil;  // my last d lanes of D_0
-        float* xb2 = xb + ((1 * 8 + (og * 4 + q)) * 16) * kMaxDil;  // my first d lanes of D_2
+        const int xo = dbuf ? (int)par * (kMaxDil / 2) : 0;
+        float* xb0 = xb + ((0 * 16 + wid) * ocnt) * kMaxDil + xo;  // my last d lanes of D_0
+        float* xb2 = xb + ((1 * 16 + wid) * ocnt) * kMaxDil + xo;  // my first d lanes of D_2
         if (lane >= 32 - d) {
 #pragma unroll
-          for (int jx = 0; jx < 16; ++jx) xb0[jx * kMaxDil + lane - (32 - d)] = v0[jx];
+          for (int jx = 0; jx < ocnt; ++jx) xb0[jx * kMaxDil + lane - (32 - d)] = v0[jx];
         }
         if (lane < d) {
 #pragma unroll
-          for (int jx = 0; jx < 16; ++jx) xb2[jx * kMaxDil + lane] = v2[jx];
+          for (int jx = 0; jx < ocnt; ++jx) xb2[jx * kMaxDil + lane] = v2[jx];
         }
         if (p.has_residual) {
-          mbar_wait(rfull, eph);
+          mbar_wait(&rfull_w[wid], eph);
           eph ^= 1;
         } else {
-          if (leader) tma_store_wait_read<0>();  // the previous unit's store has drained the tile
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has drained its piece
+          __syncwarp();
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + og, 128);
         // branch-free gather: every lane loads a (valid) exchange-buffer address and selects
-        const uint32_t xbs = smem_u32(xb);
-        const uint32_t far0 = xbs + (uint32_t)(((0 * 8 + (og * 4 + (use0 && !in0 ? (c0 >> 5) : q))) * 16) * kMaxDil +
+        const uint32_t far0 = xbs + (uint32_t)(((0 * 16 + (og * 4 + (use0 && !in0 ? (c0 >> 5) : q))) * ocnt) * kMaxDil + xo +
                                                (use0 && !in0 ? (c0 & 31) - (32 - d) : 0)) * 4;
-        const uint32_t far2 = xbs + (uint32_t)(((1 * 8 + (og * 4 + (use2 && !in2 ? (c2 >> 5) : q))) * 16) * kMaxDil +
+        const uint32_t far2 = xbs + (uint32_t)(((1 * 16 + (og * 4 + (use2 && !in2 ? (c2 >> 5) : q))) * ocnt) * kMaxDil + xo +
                                                (use2 && !in2 ? (c2 & 31) : 0)) * 4;
-        const uint32_t addr0 = tile + (uint32_t)((og * ocnt) * 128 + wq) * 4;
-        float f0[16], f2[16], res[16];
+        float f0[ocnt], f2[ocnt], res[ocnt];
 #pragma unroll
-        for (int jx = 0; jx < 16; ++jx) {
+        for (int jx = 0; jx < ocnt; ++jx) {
           f0[jx] = ld_shared_f32(far0 + jx * kMaxDil * 4);
           f2[jx] = ld_shared_f32(far2 + jx * kMaxDil * 4);
         }
         if (p.has_residual) {
 #pragma unroll
-          for (int jx = 0; jx < 16; ++jx) res[jx] = ld_shared_f32(addr0 + jx * 512);
+          for (int jx = 0; jx < ocnt; ++jx) res[jx] = ld_shared_f32(piece + (uint32_t)jx * 128 + (lane_b ^ ((uint32_t)jx << 4)));
         }
+        if (!dbuf) named_bar_sync(1 + og, 128);  // everyone has read the exchange slots before the next unit overwrites them
 #pragma unroll
-        for (int jx = 0; jx < 16; ++jx) {
+        for (int jx = 0; jx < ocnt; ++jx) {
           const float s0 = __shfl_sync(0xffffffffu, v0[jx], l0);
           const float s2 = __shfl_sync(0xffffffffu, v2[jx], l2);
           float r = v1[jx] + bias_r[jx];
@@ -335,23 +349,24 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (p.has_residual) r += res[jx];
           if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
           else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
-          st_shared_f32(addr0 + jx * 512, r);
+          st_shared_f32(piece + (uint32_t)jx * 128 + (lane_b ^ ((uint32_t)jx << 4)), r);
         }
         fence_proxy_async();
-        named_bar_sync(1, 256);
-        if (leader) {
-          tma_store_3d(&tm_y, (const void*)(smem + L.tile_off), 0, h, ch0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tm_y, (const void*)piece_p, q * 32, h, ch0);
           tma_store_commit();
+          if (p.has_residual && jj + 1 < it.count) {  // next residual piece once the store has read this one
+            tma_store_wait_read<0>();
+            mbar_expect_tx(&rfull_w[wid], 1024);
+            tma_load_3d(piece_p, &tm_res, &rfull_w[wid], q * 32, h + p.d, ch0);
+          }
         }
+        par ^= 1;
         if (++a == kAcc) { a = 0; aph ^= 1; }
-        if (p.has_residual && leader && jj + 1 < it.count) {  // next residual tile once the store has read this one
-          tma_store_wait_read<0>();
-          mbar_expect_tx(rfull, L.tile_bytes);
-          tma_load_3d(smem + L.tile_off, &tm_res, rfull, 0, h + p.d, ch0);
-        }
       }
     }
-    if (leader) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -823,9 +838,9 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   {
     uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * c_out};
     uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
-    uint32_t box[3] = {128, 1, (uint32_t)(c_out / 2)};
-    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box, tc::TM_NONE));
-    if (residual) PDEQX_TRY(tc::make_tensor_map(&tm_res, residual, 3, dims, str, box, tc::TM_NONE));
+    uint32_t box[3] = {32, 1, (uint32_t)tc::kConvOcnt};  // one epilogue warp's piece
+    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box, tc::TM_SW128));
+    if (residual) PDEQX_TRY(tc::make_tensor_map(&tm_res, residual, 3, dims, str, box, tc::TM_SW128));
     else tm_res = tm_y;
   }
   tc::ConvParams cp{};
