@@ -92,7 +92,8 @@ convT_fwd_kernel(ConvTGeom g, const float* __restrict__ x, const float* __restri
         src += (int64_t)m * g.in_stride[a];
       }
       if (!valid) continue;
-      for (int i = 0; i < cig; ++i) {
+#pragma unroll 8
+      for (int i = 0; i < cig; ++i) {  // independent loads in flight: the small-tensor regime is latency bound
         const float xv = __ldg(xb + (int64_t)i * g.n_in + src);
 #pragma unroll
         for (int j = 0; j < kCtOPT; ++j)
@@ -161,6 +162,7 @@ convT_bwd_data_kernel(ConvTGeom g, const float* __restrict__ gy, const float* __
               dst += (int64_t)q * g.out_stride[a];
             }
             if (!valid) continue;
+#pragma unroll 8
             for (int o = 0; o < cog; ++o)
               acc = fmaf(__ldg(wg + (int64_t)o * cig * g.taps + t), __ldg(gyb + (int64_t)o * g.n_out + dst), acc);
           }

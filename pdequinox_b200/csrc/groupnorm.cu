@@ -48,16 +48,22 @@ gn_channel_stats_kernel(const float* __restrict__ x, double* __restrict__ partia
   }
 }
 
-// stats[(b*G + g)*2 + {0,1}] = mean, rstd
+// stats[(b*G + g)*2 + {0,1}] = mean, rstd; one warp per (sample, group), lanes split the group's channels
 __global__ void gn_finalize_kernel(const double* __restrict__ partial, float* __restrict__ stats, int BG, int cpg,
                                    int64_t n, float eps) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= BG) return;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < cpg; ++c) {
+  for (int c = lane; c < cpg; c += 32) {
     s += partial[((int64_t)i * cpg + c) * 2];
     q += partial[((int64_t)i * cpg + c) * 2 + 1];
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+  if (lane != 0) return;
   const double cnt = (double)cpg * (double)n;
   const double mean = s / cnt;
   double var = q / cnt - mean * mean;
@@ -124,12 +130,31 @@ gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gy, c
                     int cpg, int G, int64_t n) {
   const int bc = blockIdx.x, b = bc / C, c = bc % C, g = c / cpg;
   const float mean = stats[2 * (b * G + g)], rstd = stats[2 * (b * G + g) + 1];
+  // group sums of the per-channel partials: the block's threads split the group's channels (a serial loop per thread over
+  // up to 256 channels made this kernel 56 us on 131 KB tensors), then a two-level shuffle / shared-memory reduction
+  __shared__ float red1[8], red2[8];
   float s1 = 0.f, s2 = 0.f;
-  for (int cc = 0; cc < cpg; ++cc) {
+  for (int cc = threadIdx.x; cc < cpg; cc += blockDim.x) {
     const int ch = g * cpg + cc;
     const float wv = w ? __ldg(w + ch) : 1.f;
     s1 = fmaf(wv, scratch[((int64_t)b * C + ch) * 2], s1);
     s2 = fmaf(wv, scratch[((int64_t)b * C + ch) * 2 + 1], s2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red1[threadIdx.x >> 5] = s1;
+    red2[threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  s1 = s2 = 0.f;
+#pragma unroll
+  for (int wv2 = 0; wv2 < 8; ++wv2) {
+    s1 += red1[wv2];
+    s2 += red2[wv2];
   }
   const float inv = 1.f / ((float)cpg * (float)n);
   s1 *= inv;
@@ -186,7 +211,7 @@ extern "C" int pdeqx_groupnorm_fwd(int32_t batch, int32_t channels, int32_t grou
   double* partial = (double*)workspace;
   gn_channel_stats_kernel<<<BC, 256, 0, s>>>(x, partial, n);
   PDEQX_LAUNCHED();
-  gn_finalize_kernel<<<(int)ceil_div(BG, 128), 128, 0, s>>>(partial, stats, BG, cpg, n, eps);
+  gn_finalize_kernel<<<(int)ceil_div(BG, 4), 128, 0, s>>>(partial, stats, BG, cpg, n, eps);
   PDEQX_LAUNCHED();
   gn_apply_kernel<<<dim3(BC, chunks_for(n, BC)), 256, 0, s>>>(x, stats, weight, bias, y, channels, cpg, groups, n);
   PDEQX_LAUNCHED();
