@@ -106,6 +106,10 @@ conv_fwd_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxPre = 8;
 
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 __device__ __forceinline__ int preimages(int n, int s, int lo, int hi, int mode, int* out) {
   int c = 0;
   out[c++] = n;
@@ -211,6 +215,81 @@ conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __re
         }
     if (MIRROR_ONLY) gx[idx] += acc;
     else gx[idx] = acc + (add ? __ldg(add + idx) : 0.f);
+  }
+}
+
+
+// Mirror / wrap part of the data gradient for the 2-D, groups == 1, c_in == c_out == 64 case with the whole filter
+// resident in shared memory (the tcgen05 path: 64 x 64 x 9 fp32 = 147 KB). Persistent blocks of 32 warps; ONE WARP per
+// frame point (32 points in flight per SM hide the load latency; lanes own channels c and c + 32). For its point a warp
+// enumerates the (pre-image, tap) pairs that hit an output position, first fetches gy[b, o, position] of every pair into
+// its own shared-memory slab -- all of the point's global loads in flight together -- then contracts them with the filter
+// (conflict-free filter reads, broadcast gy reads). Only __syncwarp between the phases.
+//   gx[b,ci,n] += sum over the non-direct pre-images q of n under the boundary map, taps t, out channels o:
+//                 w[o,ci,t] * gy[b,o,(q + pad - t d) / stride]
+constexpr int kMirPairs = 8;    // pairs staged per batch
+constexpr int kMirWarps = 32;
+__global__ void __launch_bounds__(kMirWarps * 32)
+conv_bwd_data_mirror2d_kernel(ConvGeom g, const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ gx) {
+  extern __shared__ float ws[];  // [taps][64 o][64 ci], then [warps][kMirPairs][64 o]
+  constexpr int CH = 64;
+  const int taps = g.taps;
+  float* gys = ws + (size_t)taps * CH * CH;
+  for (int idx = threadIdx.x; idx < taps * CH * CH; idx += blockDim.x) {
+    const int i = idx % CH, o = (idx / CH) % CH, t = idx / (CH * CH);
+    ws[idx] = __ldg(w + ((int64_t)o * CH + i) * taps + t);
+  }
+  __syncthreads();
+  const Frame2d fr = frame2d(g);
+  const int warp = threadIdx.x >> 5, c = threadIdx.x & 31;
+  float* mine = gys + (size_t)warp * kMirPairs * CH;
+  const int64_t total = (int64_t)g.batch * fr.count;
+  for (int64_t pt = (int64_t)blockIdx.x * kMirWarps + warp; pt < total; pt += (int64_t)gridDim.x * kMirWarps) {
+    const int b = (int)(pt / fr.count);
+    const int64_t n = frame2d_point(g, fr, pt % fr.count);
+    int pre[2][kMaxPre];
+    int npre[2];
+    npre[1] = preimages((int)(n % g.spatial[1]), g.spatial[1], g.pad_lo[1], g.pad_hi[1], g.boundary, pre[1]);
+    npre[0] = preimages((int)(n / g.spatial[1]), g.spatial[0], g.pad_lo[0], g.pad_hi[0], g.boundary, pre[0]);
+    if (npre[0] * npre[1] == 1) continue;
+    const float* gyc = gy + ((int64_t)b * CH + c) * g.n_out;  // this lane's output channels c, c + 32 in the fetch phase
+    float* gxp = gx + ((int64_t)b * CH + c) * g.n_in + n;
+    const float old0 = gxp[0], old1 = gxp[(int64_t)32 * g.n_in];  // (in flight while the pairs are processed)
+    float acc0 = 0.f, acc1 = 0.f;
+    const int npairs_all = npre[0] * npre[1] * taps;  // pair index k = (c0 * npre[1] + c1) * taps + t
+    int k = taps;                                       // skip (c0, c1) = (0, 0): the direct position
+    while (k < npairs_all) {
+      // ---- fetch phase: up to kMirPairs valid pairs ----
+      int tl[kMirPairs];
+      int cnt = 0;
+      for (; k < npairs_all && cnt < kMirPairs; ++k) {
+        const int t = k % taps, cc = k / taps, c1 = cc % npre[1], c0 = cc / npre[1];
+        const int t0 = t / g.kernel[1], t1 = t % g.kernel[1];
+        const int num0 = pre[0][c0] + g.pad_lo[0] - t0 * g.dilation[0], num1 = pre[1][c1] + g.pad_lo[1] - t1 * g.dilation[1];
+        if (num0 < 0 || num1 < 0 || num0 % g.stride[0] != 0 || num1 % g.stride[1] != 0) continue;
+        const int p0 = num0 / g.stride[0], p1 = num1 / g.stride[1];
+        if (p0 >= g.out[0] || p1 >= g.out[1]) continue;
+        const float* src = gyc + (int64_t)p0 * g.out_stride[0] + p1;
+        mine[cnt * CH + c] = __ldg(src);
+        mine[cnt * CH + c + 32] = __ldg(src + (int64_t)32 * g.n_out);
+        tl[cnt++] = t;
+      }
+      __syncwarp();
+      // ---- contraction phase ----
+      for (int j = 0; j < cnt; ++j) {
+        const float* wt = ws + (size_t)tl[j] * CH * CH + c;
+        const float* gv = mine + j * CH;
+#pragma unroll 16
+        for (int o = 0; o < CH; ++o) {
+          const float gvo = gv[o];
+          acc0 = fmaf(wt[o * CH], gvo, acc0);
+          acc1 = fmaf(wt[o * CH + 32], gvo, acc1);
+        }
+      }
+      __syncwarp();
+    }
+    gxp[0] = old0 + acc0;
+    gxp[(int64_t)32 * g.n_in] = old1 + acc1;
   }
 }
 
@@ -354,6 +433,17 @@ static inline int grid_for(int64_t total) {
 }
 
 int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w, float* gx, cudaStream_t s) {
+  const size_t wbytes = sizeof(float) * ((size_t)g.taps * g.c_out * g.c_in + kMirWarps * kMirPairs * 64);
+  if (g.ndim == 2 && g.groups == 1 && g.c_in == 64 && g.c_out == 64 && wbytes <= 220 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      PDEQX_CUDA(cudaFuncSetAttribute(conv_bwd_data_mirror2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr = true;
+    }
+    conv_bwd_data_mirror2d_kernel<<<148, kMirWarps * 32, wbytes, s>>>(g, gy, w, gx);
+    PDEQX_LAUNCHED();
+    return PDEQX_OK;
+  }
   const int64_t total = (int64_t)g.batch * g.c_in * (g.ndim == 2 ? frame2d(g).count : g.n_in);
   conv_bwd_data_kernel<true><<<grid_for(total), 256, 0, s>>>(g, gy, w, nullptr, gx);
   PDEQX_LAUNCHED();
