@@ -156,7 +156,11 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       const int64_t outer = id / p.q_per_outer;
       const int q = (int)(id % p.q_per_outer);
       const int row0 = part * p.n_part + rh * rows_w;
-      float* dst = p.out + (outer * (int64_t)p.n_out + row0) * p.inner_f + (int64_t)q * 32 + lane;
+      // (warp-uniform) output pointer of this lane's column; consecutive output rows are inner_f floats apart -- the
+      // per-row address is a pointer increment, not a 64-bit multiply
+      float* rowp = p.out + (outer * (int64_t)p.n_out + row0) * p.inner_f + (int64_t)q * 32 + lane;
+      const int64_t rstride = p.inner_f;
+      const bool odd = lane & 1;
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * p.N + rh * rows_w);
@@ -170,12 +174,15 @@ c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
+        if (live) {  // warp-uniform: the whole 32-float block is inside the tensor or not
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float other = __shfl_xor_sync(0xffffffffu, qi[j], 1);
-          float v = (lane & 1) ? pr[j] + other : pr[j] - other;
-          if (p.round_out) v = round_tf32(v);
-          if (live) dst[(int64_t)(r0 + j) * p.inner_f] = v;
+          for (int j = 0; j < 16; ++j) {
+            const float other = __shfl_xor_sync(0xffffffffu, qi[j], 1);
+            float v = odd ? pr[j] + other : pr[j] - other;
+            if (p.round_out) v = round_tf32(v);
+            *rowp = v;
+            rowp += rstride;
+          }
         }
       }
       if (++a == AS) { a = 0; aph ^= 1; }
