@@ -606,6 +606,8 @@ struct WgradParams {
   int round_x1;  // x1 feeds a tcgen05 c2c stage (D >= 2): round to tf32 here
 };
 
+constexpr int kWgGroup = 4;  // image rows whose first-DFT-stage results share one accumulator tile (one drain per group)
+
 __global__ void __launch_bounds__(kThreadsR2c, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_tab, WgradParams p) {
@@ -646,7 +648,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);  // 128 (gW | gb) + 2 x kWgGroup x 32 (first-DFT-stage tiles)
   // ones rows (bias-gradient columns) and a defined value everywhere an A/B descriptor can reach
   for (uint32_t i = threadIdx.x; i < ((uint32_t)S * stage_bytes + 16384) / 4; i += blockDim.x) {
     const uint32_t in_stage = (i * 4) % stage_bytes;
@@ -658,6 +660,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t groups = (p.rows + kWgGroup - 1) / kWgGroup;  // a CTA walks groups of kWgGroup consecutive image rows
   const int N = p.c_in + 16;
   const int W = p.chunks_per_row * 32;
 
@@ -669,16 +672,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       }
       int s = 0;
       uint32_t ph = 0;
-      for (int64_t r = first; r < p.rows; r += stride) {
-        const int b = (int)(r / p.lead);
-        const int l = (int)(r % p.lead);
-        for (int c = 0; c < p.chunks_per_row; ++c) {
-          mbar_wait_backoff(&empty[s], ph ^ 1);
-          uint8_t* st = stage0 + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full[s], g_bytes + x_bytes);
-          tma_load_2d(st, &tm_g, &full[s], l * W + c * 32, b * p.c_out);
-          tma_load_2d(st + g_bytes, &tm_x, &full[s], l * W + c * 32, b * p.c_in);
-          if (++s == S) { s = 0; ph ^= 1; }
+      for (int64_t gi = first; gi < groups; gi += stride) {
+        for (int rr = 0; rr < kWgGroup; ++rr) {
+          const int64_t r = gi * kWgGroup + rr;
+          if (r >= p.rows) break;
+          const int b = (int)(r / p.lead);
+          const int l = (int)(r % p.lead);
+          for (int c = 0; c < p.chunks_per_row; ++c) {
+            mbar_wait_backoff(&empty[s], ph ^ 1);
+            uint8_t* st = stage0 + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], g_bytes + x_bytes);
+            tma_load_2d(st, &tm_g, &full[s], l * W + c * 32, b * p.c_out);
+            tma_load_2d(st + g_bytes, &tm_x, &full[s], l * W + c * 32, b * p.c_in);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -696,13 +703,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       int s = 0, it = 0;
       uint32_t ph = 0;
       uint32_t acc = 0;
-      for (int64_t r = first; r < p.rows; r += stride, ++it) {
+      for (int64_t gi = first; gi < groups; gi += stride, ++it) {
         const int a2 = it & 1;
         if (fused) {
           mbar_wait(&x1empty[a2], (((uint32_t)it >> 1) & 1) ^ 1);
           tc_fence_after();
         }
-        const uint32_t d2 = tmem_base + 128u + (uint32_t)(a2 * 32);
+       for (int rr = 0; rr < kWgGroup; ++rr) {
+        if (gi * kWgGroup + rr >= p.rows) break;
+        // the rows of a group land in consecutive 32-column slices of one accumulator tile: ONE drain per group
+        const uint32_t d2 = tmem_base + 128u + (uint32_t)(a2 * kWgGroup * 32 + rr * 32);
         for (int c = 0; c < p.chunks_per_row; ++c) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -722,6 +732,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
           mma_commit(&empty[s]);
           if (++s == S) { s = 0; ph ^= 1; }
         }
+       }
         if (fused) mma_commit(&x1full[a2]);
       }
       mma_commit(done);
@@ -731,30 +742,39 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
     if (fused && q < 2) {
       // drain the r2c accumulator of every row: TMEM lane = A row = output channel o (q < 2: rows 0..63 hold g)
       int it = 0;
-      for (int64_t r = first; r < p.rows; r += stride, ++it) {
+      const int o = q * 32 + lane;
+      for (int64_t gi = first; gi < groups; gi += stride, ++it) {
         const int a2 = it & 1;
         mbar_wait(&x1full[a2], ((uint32_t)it >> 1) & 1);
         tc_fence_after();
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(a2 * 32), v);
+        // all rows of the group are loaded before the single wait: one TMEM round trip per group instead of per row
+        float v[kWgGroup][32];
+#pragma unroll
+        for (int rr = 0; rr < kWgGroup; ++rr)
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(a2 * kWgGroup * 32 + rr * 32), v[rr]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&x1empty[a2]);
-        const int o = q * 32 + lane;
         if (o < p.c_out) {
-          const int64_t row = ((r / p.lead) * p.c_out + o) * p.lead + r % p.lead;
-          float4* dst = (float4*)(p.x1 + row * 32);
-          if (p.round_x1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          for (int rr = 0; rr < kWgGroup; ++rr) {
+            const int64_t r = gi * kWgGroup + rr;
+            if (r < p.rows) {
+              const int64_t row = ((r / p.lead) * p.c_out + o) * p.lead + r % p.lead;
+              float4* dst = (float4*)(p.x1 + row * 32);
+              if (p.round_x1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[rr][j] = round_tf32(v[rr][j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[rr][4 * j], v[rr][4 * j + 1], v[rr][4 * j + 2], v[rr][4 * j + 3]);
+            }
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
     }
-    if (first < p.rows) {
+    if (first < groups) {
       mbar_wait(done, 0);
       tc_fence_after();
       const int o = q * 32 + lane;
@@ -777,7 +797,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -1120,7 +1140,8 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
     PDEQX_CUDA(cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  const int grid = (int)(wp.rows < t->sms ? wp.rows : t->sms);
+  const int64_t wgroups = ceil_div(wp.rows, tc::kWgGroup);
+  const int grid = (int)(wgroups < t->sms ? wgroups : t->sms);
   tc::wgrad_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_g, tm_x, t->tm_tab_r2c[1], wp);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
