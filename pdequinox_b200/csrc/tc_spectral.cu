@@ -115,7 +115,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // ==========================================================================================
 struct SlabParams {
   int lead, W, wt_per_row, c_in, c_out;
-  int parts;  // epilogue warps per TMEM lane quarter: each owns c_out / parts channels (4, or 2 when c_out < 64)
+  int parts;  // epilogue warps per TMEM lane quarter: each owns c_out / parts channels (8, 16 or 32)
   int rpu;  // image rows per 128-pixel unit: 1 for W >= 128 (W / 128 units per row), 128 / W for narrower grids
   int has_bypass, mode, act, round_out;
   int stages;
@@ -259,27 +259,31 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       mbar_wait(tabfull, 0);
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
+      const uint64_t kk0 = smem_desc_sw128(0, 0, 1024);                       // K-major operands (address field added below)
+      const uint64_t mk0 = smem_desc_sw128_atom32(0, L.x_box_bytes, 512);     // MN-major x slab
+      const uint32_t kk_hi = (uint32_t)(kk0 >> 32), kk_lo = (uint32_t)kk0, mk_hi = (uint32_t)(mk0 >> 32), mk_lo = (uint32_t)mk0;
+      const uint32_t tab_lo = kk_lo + (smem_u32(smem + L.tab_off) >> 4), w_lo = kk_lo + (smem_u32(smem + L.w_off) >> 4);
+      const uint32_t st16_0 = smem_u32(smem + L.stage_off) >> 4, stage16 = L.stage_bytes >> 4, z16 = L.z_off_in_stage >> 4;
+      const uint32_t cbox16 = (uint32_t)p.c_out * 128 >> 4;
       for (int64_t u = first; u < p.units; u += stride) {
         mbar_wait(&tempty[a], aph ^ 1);
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(a * p.c_out);
-        const uint32_t st = smem_u32(smem + L.stage_off + (size_t)s * L.stage_bytes);
+        // descriptors: constant high words, low word = 14-bit start address (>> 4); per MMA only integer adds
+        const uint32_t st16 = st16_0 + (uint32_t)s * stage16;
         // spectral part: A = table tile [128 w x 32 k] (K-major), B = Z box [c_out x 32 k] (K-major)
-        const uint32_t ta = smem_u32(smem + L.tab_off);
-        const uint32_t zb = st + L.z_off_in_stage;
         for (int c = 0; c < p.rpu; ++c)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            mma_tf32(d, smem_desc_sw128(ta + c * 128 * 128 + k * 32, 0, 1024),
-                     smem_desc_sw128(zb + c * p.c_out * 128 + k * 32, 0, 1024), idesc_kk, (c | k) != 0);
+            mma_tf32_lohi(d, tab_lo + (uint32_t)c * (128 * 128 >> 4) + k * 2, kk_hi,
+                          kk_lo + st16 + z16 + (uint32_t)c * cbox16 + k * 2, kk_hi, idesc_kk, (c | k) ? 1u : 0u);
         // bypass part: A = x slab [128 w x c_in] (MN-major: w contiguous), B = W [c_out x c_in] (K-major)
         if (p.has_bypass) {
-          const uint32_t wb = smem_u32(smem + L.w_off);
           const int ksteps = p.c_in / 8;
           for (int k = 0; k < ksteps; ++k)
-            mma_tf32(d, smem_desc_sw128_atom32(st + k * 1024, L.x_box_bytes, 512),
-                     smem_desc_sw128(wb + (k >> 2) * p.c_out * 128 + (k & 3) * 32, 0, 1024), idesc_mk, true);
+            mma_tf32_lohi(d, mk_lo + st16 + (uint32_t)k * (1024 >> 4), mk_hi, w_lo + (uint32_t)(k >> 2) * cbox16 + (k & 3) * 2, kk_hi,
+                          idesc_mk, 1u);
         }
         mma_commit(&empty[s]);
         mma_commit(&tfull[a]);
@@ -297,6 +301,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int q = warp & 3;            // TMEM lane quarter this warp may read = 32-w chunk of the tile
     const int part = (warp - 4) >> 2;  // which slice of the output channels
     const int ncol = p.c_out / p.parts;
+    const int nc = ncol < 16 ? ncol : 16;  // valid columns of a 16-column TMEM load (8 when c_out = 32)
     const int NB = (int)L.epi_bufs;  // 2 (MODE 0) or 3 (MODE 1: the cotangent piece is prefetched two units ahead)
     uint8_t* ebuf0 = smem + L.epi_off + (size_t)q * L.chunk_bytes + (size_t)part * ncol * 128;  // this warp's piece in buffer 0
     uint64_t* afull = auxfull + (part * 4 + q) * 3;
@@ -357,9 +362,11 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float r = v[j] + bias_s[part * ncol + c0 + j];
-              racc_w[ci][j] = fmaf(r, sv, racc_w[ci][j]);
-              racc_b[ci][j] += r;
+              if (j < nc) {
+                const float r = v[j] + bias_s[part * ncol + c0 + j];
+                racc_w[ci][j] = fmaf(r, sv, racc_w[ci][j]);
+                racc_b[ci][j] += r;
+              }
             }
           }
         }
@@ -381,13 +388,14 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         float g[16];
         if (MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = ld_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)));
+          for (int j = 0; j < 16; ++j) g[j] = j < nc ? ld_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4))) : 0.f;
         } else if (MODE == 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = auxw_s[part * ncol + c0 + j] * sv;
+          for (int j = 0; j < 16; ++j) g[j] = j < nc ? auxw_s[part * ncol + c0 + j] * sv : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
+          if (j >= nc) break;
           const float val = v[j] + bias_s[part * ncol + c0 + j];
           float r;
           if (MODE == 0) {
@@ -427,6 +435,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         if (ci * 16 < ncol) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
+            if (j >= nc) break;
             float vw = racc_w[ci][j], vb = racc_b[ci][j];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -1017,7 +1026,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   {
     uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * c_out};
     uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)(c_out / (c_out >= 64 ? 4 : 2))};  // one epilogue warp's piece
+    uint32_t box[3] = {32, 1, (uint32_t)(c_out / 4)};  // one epilogue warp's piece
     PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box));
     if (mode == 1) {
       PDEQX_CHECK_ARG(aux && ((uintptr_t)aux & 15) == 0, "tc_slab: aux must be a 16-byte aligned device pointer");
@@ -1029,7 +1038,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   tc::SlabParams sp{};
   sp.lead = (int)lead;
   sp.W = sD;
-  sp.parts = c_out >= 64 ? 4 : 2;
+  sp.parts = 4;  // c_out is a multiple of 32: 8, 16 or 32 channels per epilogue warp
   sp.rpu = sD >= 128 ? 1 : 128 / sD;
   sp.wt_per_row = sD >= 128 ? sD / 128 : 1;
   sp.c_in = c_in;
