@@ -130,6 +130,17 @@ int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* plan, const float* x, co
                              int32_t activation, float* y, float* save_xhat, float* save_z,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same forward pass for a block whose input is the pointwise 1 -> c_in lifting x[b,i,pixel] = lift_w[i] *
+ * lift_u[b,pixel] + lift_b[i] of a single-channel field (pdequinox/arch/_classic_fno.py:71-76 in front of the first
+ * ClassicSpectralBlock): x is never written. The first DFT stage of x is the lifting of the first stage of lift_u (the
+ * transform is linear) and the bypass term is rank one, (bypass_w . lift_w)[o] * lift_u + const[o], added in the last
+ * kernel's epilogue. Needs pdeqx_spectral_block_rank1_ok(plan, 1, activation) == 1 and ndim >= 2; bypass_w required. */
+int pdeqx_spectral_block_fwd_lifted(const pdeqx_spectral_plan* plan, const float* lift_u, const float* lift_w,
+                                    const float* lift_b, const float* w_re, const float* w_im,
+                                    const float* bypass_w, const float* bypass_b, int32_t activation, float* y,
+                                    float* save_xhat, float* save_z, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+
 /* VJP of the call above (what jax.custom_vjp's bwd rule binds).
  *   gy [B,c_out,*S] cotangent of y; x, saved_xhat, saved_z from the forward.
  *   Outputs (overwritten, weight grads summed over the batch):
@@ -153,10 +164,13 @@ int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* plan, const float* x, co
  *  - lift_u != NULL (gx must be NULL): the block's input was produced from the single-channel field lift_u [B,*S] by the
  *    1 -> c_in pointwise lifting (pdequinox/arch/_classic_fno.py:71-76); instead of storing gx the last kernel
  *    accumulates that lifting's gradients lift_gw[i] = sum gx[b,i,pixel] lift_u[b,pixel], lift_gb[i] = sum gx (may be
- *    NULL). Outputs are overwritten. */
+ *    NULL). Outputs are overwritten. If additionally x == NULL the forward pass ran through
+ *    pdeqx_spectral_block_fwd_lifted: the lifted input lift_w[i] * lift_u + lift_b[i] (lift_b may be NULL) was never
+ *    materialised and the reverse pass works from lift_u, lift_w, lift_b alone. */
 int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* plan, int32_t has_bypass, int32_t activation);
 int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* plan, const float* x, const float* gy, const float* gy_w,
-                                const float* lift_u, float* lift_gw, float* lift_gb, const float* w_re,
+                                const float* lift_u, float* lift_gw, float* lift_gb, const float* lift_w,
+                                const float* lift_b, const float* w_re,
                                 const float* w_im, const float* bypass_w, const float* bypass_b,
                                 int32_t activation, const float* saved_xhat, const float* saved_z, float* gx,
                                 float* gw_re, float* gw_im, float* g_bypass_w, float* g_bypass_b,

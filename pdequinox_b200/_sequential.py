@@ -36,8 +36,20 @@ class Sequential(Module):
                                              boundary_mode=boundary_mode, key=key)
 
     def _fwd(self, x, tape):
-        x = self.lifting._fwd(x, tape)
-        for block in self.blocks:
+        first = self.blocks[0]
+        # a 1 -> C pointwise lifting in front of a spectral block is folded into that block (the lifted tensor is never
+        # written; see ClassicSpectralBlock._fwd_lifted). Only inside a training step's tape with no input gradient wanted
+        # downstream of it: the matching reverse pass accumulates the lifting's gradients instead of an input gradient.
+        fold = (tape is not None and getattr(tape, "fold_lifting", False) and isinstance(self.lifting, PointwiseLinearConv)
+                and self.lifting.in_channels == 1 and hasattr(first, "lifted_ok") and first.lifted_ok(x))
+        if fold:
+            tape.push(x)  # stands for the lifting's record (its input)
+            x = first._fwd_lifted(x, self.lifting, tape)
+            rest = self.blocks[1:]
+        else:
+            x = self.lifting._fwd(x, tape)
+            rest = self.blocks
+        for block in rest:
             x = block._fwd(x, tape)
         return self.projection._fwd(x, tape)
 
@@ -72,11 +84,14 @@ class Sequential(Module):
             if fold_proj and i == nb - 1:
                 kw["gy_w"] = self.projection.weight
                 g = gy
-            if fold_lift and i == 0 and self.blocks[0].rank1_ok(tape):
+            lifted_fwd = i == 0 and tape.stack[-1][0] is None  # the forward pass folded the lifting in: it must be unfolded here
+            if i == 0 and (lifted_fwd or (fold_lift and self.blocks[0].rank1_ok(tape))):
                 u = tape.stack[-2]  # the lifting's saved input, right below the first block's record
                 lw = self.lifting.grad("weight")
                 lb = self.lifting.grad("bias") if self.lifting.bias is not None else None
                 kw["lift"] = (u, lw, lb)
+                if lifted_fwd:
+                    kw["lifted"] = (self.lifting.weight, self.lifting.bias)
             if kw:
                 g = self.blocks[i]._bwd_ex(g, tape, True, **kw)
             else:

@@ -44,12 +44,25 @@ class ClassicSpectralBlock(Block):
         _, saved = tape.stack[-1]
         return bool(_lib.lib().pdeqx_spectral_block_rank1_ok(saved[0].handle, 1, nn.activation_code(self.activation)))
 
-    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None):
+    def lifted_ok(self, u):
+        return self.spectral_conv.lifted_ok(u, nn.activation_code(self.activation))
+
+    def _fwd_lifted(self, u, lifting, tape):
+        """Forward pass on the input lifting(u) (a 1 -> C PointwiseLinearConv) without materialising it."""
+        act = nn.activation_code(self.activation)
+        y, saved = self.spectral_conv.apply_lifted(u, lifting.weight, lifting.bias, tape, bypass=self.by_pass_conv, act=act,
+                                                   save=tape is not None)
+        if tape is not None:
+            tape.push((None, saved))  # x = None marks the lifted forward pass
+        return y
+
+    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None, lifted=None):
         """gy_w: `gy` is the single-channel factor of a rank-one cotangent; lift = (u, gw, gb): accumulate the gradients of
         the 1 -> C lifting that produced this block's input from `u` instead of returning the input gradient."""
         x, saved = tape.pop()
         return self.spectral_conv.apply_bwd(x, gy, saved, tape, bypass=self.by_pass_conv,
-                                            act=nn.activation_code(self.activation), need_gx=need_gx, gy_w=gy_w, lift=lift)
+                                            act=nn.activation_code(self.activation), need_gx=need_gx, gy_w=gy_w, lift=lift,
+                                            lifted=lifted if x is None else None)
 
 
 class ClassicSpectralBlockFactory(BlockFactory):

@@ -102,14 +102,45 @@ class SpectralConv(Module):
             _lib.stream()))
         return y, (plan, xhat, z)
 
-    def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True, gy_w=None, lift=None):
+    def apply_lifted(self, u, lift_w, lift_b, tape, *, bypass, act, save=False):
+        """y = act(spectral(x) + bypass(x)) for x = lift_w[i] * u + lift_b[i] (a pointwise 1 -> C lifting of the single-channel
+        field u [B, 1, *S]) WITHOUT materialising x (pdeqx_spectral_block_fwd_lifted). Returns (y, saved)."""
+        D = self.num_spatial_dims
+        B = u.shape[0]
+        ci, co = self.call_in_channels, self.call_out_channels
+        spatial = tuple(u.shape[2:])
+        plan = get_plan(D, B, ci, co, spatial, self.num_modes)
+        y = new_buf(tape, self, "y", (B, co) + spatial)
+        xhat = z = None
+        if save:
+            xhat = new_buf(tape, self, "xhat", (plan.xhat_floats,))
+            z = new_buf(tape, self, "z", (plan.z_floats,))
+        _lib.check(_lib.lib().pdeqx_spectral_block_fwd_lifted(
+            plan.handle, _lib.ptr(u), _lib.ptr(lift_w), _lib.ptr(lift_b), _lib.ptr(self.weights_real),
+            _lib.ptr(self.weights_imag), _lib.ptr(bypass.weight), _lib.ptr(bypass.bias), act, _lib.ptr(y), _lib.ptr(xhat),
+            _lib.ptr(z), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))
+        return y, (plan, xhat, z)
+
+    def lifted_ok(self, u, act):
+        """True if `apply_lifted` can run for a field of this shape (tcgen05 path, at least 2 spatial dims)."""
+        D = self.num_spatial_dims
+        if D < 2 or not u.is_cuda or act == _lib.ACT_IDENTITY:
+            return False
+        plan = get_plan(D, u.shape[0], self.call_in_channels, self.call_out_channels, tuple(u.shape[2:]), self.num_modes)
+        L = _lib.lib()
+        return bool(L.pdeqx_spectral_block_rank1_ok(plan.handle, 1, act)) and (L.pdeqx_spectral_plan_tcgen05_stages(plan.handle) & 1) == 1
+
+    def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True, gy_w=None, lift=None,
+                  lifted=None):
         """VJP. With `gy_w` the cotangent is rank one: gy_w[o] * gy[b, 0, *S] (what a C -> 1 pointwise projection sends
         back); it is then formed inside the kernel instead of being materialised. With `lift = (u, gw, gb)` the input
         gradient is not stored: the gradients gw, gb of the 1 -> C pointwise lifting that made x from the field u are
-        accumulated instead (pdeqx_spectral_block_bwd_ex)."""
+        accumulated instead (pdeqx_spectral_block_bwd_ex). With `lifted = (lift_w, lift_b)` the forward pass was
+        `apply_lifted`: x is None and the reverse pass works from u alone."""
         plan, xhat, z = saved
+        ref = x if x is not None else lift[0]
         gx = new_buf(tape, self, "gx", x.shape) if (need_gx and lift is None) else None
-        full = (x.shape[0], self.call_out_channels) + tuple(x.shape[2:])
+        full = (ref.shape[0], self.call_out_channels) + tuple(ref.shape[2:])
         scratch = new_buf(tape, self, "gpre", full) if act != _lib.ACT_IDENTITY else None
         bw = bypass.weight if bypass is not None else None
         bb = bypass.bias if bypass is not None else None
@@ -119,9 +150,10 @@ class SpectralConv(Module):
             u, lgw, lgb = lift if lift is not None else (None, None, None)
             if lift is not None:
                 gx = None
+            lw, lb = lifted if lifted is not None else (None, None)
             _lib.check(_lib.lib().pdeqx_spectral_block_bwd_ex(
                 plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(gy_w), _lib.ptr(u), _lib.ptr(lgw), _lib.ptr(lgb),
-                _lib.ptr(self.weights_real),
+                _lib.ptr(lw), _lib.ptr(lb), _lib.ptr(self.weights_real),
                 _lib.ptr(self.weights_imag), _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),
                 _lib.ptr(self.grad("weights_real")), _lib.ptr(self.grad("weights_imag")), _lib.ptr(gbw), _lib.ptr(gbb),
                 _lib.ptr(scratch), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))

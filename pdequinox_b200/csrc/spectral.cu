@@ -166,6 +166,7 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
   p->stage_floats = 2 * (int64_t)desc->batch * cmax * lead_max * mP;
   p->mode_floats = (2 * (int64_t)desc->batch * cmax * J + 63) / 64 * 64;
   p->ws_bytes = (size_t)(2 * p->stage_floats + 2 * p->mode_floats) * sizeof(float) + 256;
+  if (cudaMalloc((void**)&p->lift_scratch, sizeof(float) * 4 * 128) != cudaSuccess) p->lift_scratch = nullptr;
   rc = tc_plan_init(p);  // builds the tcgen05-side operand tables when the shape qualifies
   if (rc == PDEQX_OK) rc = tc_c2c_plan_init(p);
   if (rc != PDEQX_OK) {
@@ -188,6 +189,7 @@ extern "C" void pdeqx_spectral_plan_destroy(pdeqx_spectral_plan* p) {
     cudaFree(p->t_inv_adj[a]);
     cudaFree(p->t_fwd_adj[a]);
   }
+  cudaFree(p->lift_scratch);
   tc_plan_free(p);
   tc_c2c_plan_free(p);
   delete p;
@@ -245,6 +247,63 @@ static int stage_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const flo
   const bool feeds_tc = (kind == 0 || kind == 2) ? axis > 0 : true;
   if (tc_c2c_available(p, axis, kind, inner)) return tc_c2c(p, axis, kind, in, out, outer, inner, s, feeds_tc);
   return cgemm_shared_a(table, (const float2*)in, (float2*)out, outer, n_out, n_in, inner, s);
+}
+
+
+__device__ __forceinline__ float to_tf32(float v) {  // round to nearest, as the tcgen05 stages expect from their producers
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// ---- a pointwise 1 -> C lifting in front of the block, folded in (the lifted tensor x = w (x) u + b never exists) ----
+// a[o] = sum_i Wb[o,i] wl[i];  c[o] = sum_i Wb[o,i] bl[i] + bb[o]: the bypass of the lifted input is a[o] u[pixel] + c[o]
+__global__ void lift_fold_bypass_kernel(const float* __restrict__ wb, const float* __restrict__ bb, const float* __restrict__ wl,
+                                        const float* __restrict__ bl, int co, int ci, float* __restrict__ a, float* __restrict__ c) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= co) return;
+  float sa = 0.f, sc = bb ? bb[o] : 0.f;
+  for (int i = 0; i < ci; ++i) {
+    const float w = wb[(int64_t)o * ci + i];
+    sa = fmaf(w, wl[i], sa);
+    if (bl) sc = fmaf(w, bl[i], sc);
+  }
+  a[o] = sa;
+  c[o] = sc;
+}
+// first DFT stage of the lifted input from the first DFT stage U1 of the field (the transform is linear):
+//   X1[(b C + o) lead + l][k] = wl[o] U1[b lead + l][k] + [k == 0] bl[o] s_D     (sum_w cos(0) = s_D; every other column sums to 0)
+__global__ void __launch_bounds__(256)
+lift_x1_kernel(const float4* __restrict__ u1, const float* __restrict__ wl, const float* __restrict__ bl, float sD, int C, int64_t lead,
+               int64_t total4, int round, float4* __restrict__ x1) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k4 = (int)(idx & 7);          // float4 index inside the 32-float row
+    const int64_t row = idx >> 3;            // (b C + o) lead + l
+    const int64_t l = row % lead;
+    const int64_t bo = row / lead;
+    const int o = (int)(bo % C);
+    const int64_t b = bo / C;
+    float4 v = __ldg(u1 + ((b * lead + l) << 3) + k4);
+    const float w = wl[o];
+    v.x *= w; v.y *= w; v.z *= w; v.w *= w;
+    if (k4 == 0 && bl) v.x = fmaf(bl[o], sD, v.x);
+    if (round) {
+      v.x = to_tf32(v.x);
+      v.y = to_tf32(v.y);
+      v.z = to_tf32(v.z);
+      v.w = to_tf32(v.w);
+    }
+    x1[idx] = v;
+  }
+}
+// bypass gradients from the two reductions s1[o] = sum g u, s0[o] = sum g:  gW[o,i] = s1[o] wl[i] + s0[o] bl[i];  gb[o] = s0[o]
+__global__ void lift_unfold_wgrad_kernel(const float* __restrict__ s1, const float* __restrict__ s0, const float* __restrict__ wl,
+                                         const float* __restrict__ bl, int co, int ci, float* __restrict__ gw, float* __restrict__ gb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= co * ci) return;
+  const int o = idx / ci, i = idx % ci;
+  gw[idx] = s1[o] * wl[i] + (bl ? s0[o] * bl[i] : 0.f);
+  if (gb && i == 0) gb[o] = s0[o];
 }
 
 // Workspace regions: two big ping-pong buffers for the chain intermediates and two
@@ -334,11 +393,15 @@ static Regions make_regions(const pdeqx_spectral_plan* p, void* ws) {
 
 }  // namespace pdeqx
 
-extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const float* x, const float* w_re,
-                                        const float* w_im, const float* bypass_w, const float* bypass_b,
-                                        int32_t act, float* y, float* save_xhat, float* save_z, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
-  PDEQX_CHECK_ARG(p && x && w_re && w_im && y, "null argument");
+// lift_u != null: the block's input is the pointwise lifting lift_w[i] * lift_u[b, pixel] + lift_b[i] of a single-channel
+// field and is never materialised (x is ignored): its first DFT stage is the lifting of the field's first stage, and its
+// bypass term is rank one, folded into the last kernel's epilogue
+static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x, const float* lift_u, const float* lift_w,
+                                   const float* lift_b, const float* w_re,
+                                   const float* w_im, const float* bypass_w, const float* bypass_b,
+                                   int32_t act, float* y, float* save_xhat, float* save_z, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(p && (x || lift_u) && w_re && w_im && y, "null argument");
   PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
   PDEQX_CHECK_ARG(bypass_w || !bypass_b, "bypass_b without bypass_w");
   PDEQX_TRY(check_ws(p, workspace, workspace_bytes));
@@ -351,7 +414,22 @@ extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const floa
 
   // forward transform -> x_hat [B, c_in, J]
   float* xhat = save_xhat ? save_xhat : r.mode[0];
-  PDEQX_TRY(forward_chain(p, x, d.c_in, false, xhat, r, s));
+  const bool lifted = lift_u != nullptr;
+  if (lifted) {
+    PDEQX_CHECK_ARG(lift_w && bypass_w && D >= 2 && p->lift_scratch && d.c_in <= 128 && d.c_out <= 128 &&
+                        tc_slab_available(p, true) && tc_r2c_available(p) && p->mlast == 16,
+                    "the lifted forward pass needs the tcgen05 path (pdeqx_spectral_block_rank1_ok) and a bypass");
+    // first stage of the single-channel field, then its lifting (the DFT is linear; the bias only feeds column k = 0)
+    float* u1 = r.big[1];
+    PDEQX_TRY(stage_r2c(p, lift_u, p->t_r2c_fwd, (int64_t)d.batch * p->lead, u1, s));
+    const int64_t total4 = (int64_t)d.batch * d.c_in * p->lead * 8;
+    const int blocks = (int)(ceil_div(total4, 256) < 148 * 16 ? ceil_div(total4, 256) : 148 * 16);
+    lift_x1_kernel<<<blocks, 256, 0, s>>>((const float4*)u1, lift_w, lift_b, (float)sD, d.c_in, p->lead, total4, 1, (float4*)r.big[0]);
+    PDEQX_LAUNCHED();
+    PDEQX_TRY(forward_chain(p, nullptr, d.c_in, false, xhat, r, s, /*r2c_done=*/true));
+  } else {
+    PDEQX_TRY(forward_chain(p, x, d.c_in, false, xhat, r, s));
+  }
   // channel mix -> y_hat [B, c_out, J] (for D == 1 this already is z)
   float* yhat = (D == 1 && save_z) ? save_z : r.mode[1];
   PDEQX_TRY(mode_mix(p, xhat, w_re, w_im, /*transposed_conj=*/false, yhat, s));
@@ -364,6 +442,15 @@ extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const floa
   }
   // last stage: c2r (+ bypass + bias + activation)
   const int64_t rows = (int64_t)d.batch * d.c_out * p->lead;
+  if (lifted) {
+    float* fa = p->lift_scratch;       // a[o]: per-channel factor of the rank-one bypass
+    float* fc = p->lift_scratch + 128;  // c[o]: its constant part (+ bypass bias)
+    lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
+    PDEQX_LAUNCHED();
+    TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+    return tc_slab_ex(p, nullptr, z, /*table_sel=*/0, nullptr, false, fc, act, /*mode=*/0, nullptr, d.c_in, d.c_out, y, s, nullptr,
+                      nullptr, nullptr, lift_u, fa);
+  }
   if (tc_slab_available(p, bypass_w != nullptr)) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     return tc_slab(p, x, z, /*table_sel=*/0, bypass_w, /*bypass_transposed=*/false, bypass_b, act, y, s);
@@ -374,18 +461,41 @@ extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const floa
 }
 
 // gy_w != null: the cotangent is rank one, gy[b,o,pixel] = gy_w[o] * gy[b,pixel] (gy then holds the single-channel factor)
+extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const float* x, const float* w_re,
+                                        const float* w_im, const float* bypass_w, const float* bypass_b,
+                                        int32_t act, float* y, float* save_xhat, float* save_z, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(x, "null argument");
+  return spectral_block_fwd_impl(p, x, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, y, save_xhat, save_z,
+                                 workspace, workspace_bytes, stream);
+}
+
+extern "C" int pdeqx_spectral_block_fwd_lifted(const pdeqx_spectral_plan* p, const float* lift_u, const float* lift_w,
+                                               const float* lift_b, const float* w_re, const float* w_im,
+                                               const float* bypass_w, const float* bypass_b, int32_t act, float* y,
+                                               float* save_xhat, float* save_z, void* workspace, size_t workspace_bytes,
+                                               void* stream) {
+  PDEQX_CHECK_ARG(lift_u && lift_w, "null argument");
+  return spectral_block_fwd_impl(p, nullptr, lift_u, lift_w, lift_b, w_re, w_im, bypass_w, bypass_b, act, y, save_xhat,
+                                 save_z, workspace, workspace_bytes, stream);
+}
+
 // lift_u != null: gx is not produced; the block's input came from the single-channel field lift_u through a 1 -> c_in
 // pointwise lifting, whose gradients lift_gw[i] = sum gx[b,i,pixel] lift_u[b,pixel], lift_gb[i] = sum gx[b,i,pixel] are
 // accumulated by the last kernel instead
 static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x, const float* gy, const float* gy_w,
-                                   const float* lift_u, float* lift_gw, float* lift_gb, const float* w_re, const float* w_im, const float* bypass_w,
+                                   const float* lift_u, float* lift_gw, float* lift_gb, const float* lift_w,
+                                   const float* lift_b, const float* w_re, const float* w_im, const float* bypass_w,
                                    const float* bypass_b, int32_t act, const float* saved_xhat,
                                    const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                    float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  PDEQX_CHECK_ARG(p && x && gy && w_re && w_im && saved_xhat && gw_re && gw_im, "null argument");
+  PDEQX_CHECK_ARG(p && (x || (lift_u && lift_w)) && gy && w_re && w_im && saved_xhat && gw_re && gw_im, "null argument");
   PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
   PDEQX_CHECK_ARG(!bypass_w || g_bypass_w, "g_bypass_w is required when bypass_w is given");
+  // x == null: the block's input lift_w (x) lift_u + lift_b was never materialised (forward ran through
+  // pdeqx_spectral_block_fwd_lifted); every place that reads x below works from the single-channel field instead
+  const bool lifted = x == nullptr;
   PDEQX_TRY(check_ws(p, workspace, workspace_bytes));
   cudaStream_t s = (cudaStream_t)stream;
   const pdeqx_spectral_desc& d = p->desc;
@@ -402,9 +512,11 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   const bool fuse_bypass_gx = fast && bypass_w && gx;
   bool r2c_done = false;
   const int chunk = bwd_chunk_samples(p, n_pix);
+  PDEQX_CHECK_ARG(!lifted || (fast && act != PDEQX_ACT_IDENTITY && bypass_w && p->lift_scratch && lift_gw),
+                  "the lifted reverse pass needs the tcgen05 slab kernel, a fused activation and a bypass");
   PDEQX_CHECK_ARG(!gy_w || (fast && act != PDEQX_ACT_IDENTITY),
                   "a rank-1 cotangent needs the tcgen05 slab kernel and a fused activation (pdeqx_spectral_block_rank1_ok)");
-  if (!gy_w && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
+  if (!gy_w && !lifted && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
     // Steps 1-3a in sample chunks small enough for the 126 MB L2: the cotangent chunk written by the slab kernel is
     // still L2-resident when the bypass weight gradient and the first DFT stage read it back, and so is most of x.
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
@@ -435,7 +547,15 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   // 1. cotangent of the pre-activation (pre-activation recomputed from the saved z: nothing full-size is kept)
   if (act != PDEQX_ACT_IDENTITY) {
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
-    if (fast) {
+    if (lifted) {
+      float* fa = p->lift_scratch;
+      float* fc = p->lift_scratch + 128;
+      lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
+      PDEQX_LAUNCHED();
+      TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+      PDEQX_TRY(tc_slab_ex(p, nullptr, saved_z, 0, nullptr, false, fc, act, /*mode=*/gy_w ? 2 : 1, gy, d.c_in, d.c_out, scratch_full, s,
+                           gy_w, nullptr, nullptr, lift_u, fa));
+    } else if (fast) {
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
       // mode 2: the cotangent tile is formed in the epilogue from its two factors instead of being read from HBM
       PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/gy_w ? 2 : 1, gy, d.c_in, d.c_out, scratch_full, s,
@@ -450,7 +570,16 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
     gpre = scratch_full;
   }
   // 2. bypass grads (and the bypass part of gx; on the tcgen05 path that part is fused into step 7)
-  if (bypass_w) {
+  if (bypass_w && lifted) {
+    // gW_byp[o,i] = sum g[o,p] x[i,p] with x = lift_w (x) u + lift_b: two reductions over g (one pass), then an outer product
+    float* s1 = p->lift_scratch + 256;
+    float* s0 = p->lift_scratch + 384;
+    TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
+    PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, 1, d.c_out, n_pix, lift_u, lift_w, gpre, nullptr, s1, s0, stream));
+    lift_unfold_wgrad_kernel<<<(d.c_out * d.c_in + 255) / 256, 256, 0, s>>>(s1, s0, lift_w, lift_b, d.c_out, d.c_in, g_bypass_w,
+                                                                         bypass_b ? g_bypass_b : nullptr);
+    PDEQX_LAUNCHED();
+  } else if (bypass_w) {
     if (fast && tc_wgrad_available(p, n_pix)) {
       TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
       PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));
@@ -508,7 +637,7 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
                                         const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                         float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                         size_t workspace_bytes, void* stream) {
-  return spectral_block_bwd_impl(p, x, gy, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, saved_xhat, saved_z, gx, gw_re, gw_im,
+  return spectral_block_bwd_impl(p, x, gy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, saved_xhat, saved_z, gx, gw_re, gw_im,
                                  g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes, stream);
 }
 
@@ -518,13 +647,14 @@ extern "C" int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* p, int32
 
 extern "C" int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* p, const float* x, const float* gy,
                                            const float* gy_w, const float* lift_u, float* lift_gw, float* lift_gb,
+                                           const float* lift_w, const float* lift_b,
                                            const float* w_re, const float* w_im, const float* bypass_w,
                                            const float* bypass_b, int32_t act, const float* saved_xhat,
                                            const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                            float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                            size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(!lift_u || (lift_gw && !gx), "lift_u needs lift_gw and replaces gx");
-  return spectral_block_bwd_impl(p, x, gy, gy_w, lift_u, lift_gw, lift_gb, w_re, w_im, bypass_w, bypass_b, act, saved_xhat,
+  return spectral_block_bwd_impl(p, x, gy, gy_w, lift_u, lift_gw, lift_gb, lift_w, lift_b, w_re, w_im, bypass_w, bypass_b, act, saved_xhat,
                                  saved_z, gx, gw_re, gw_im, g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes,
                                  stream);
 }

@@ -13,6 +13,7 @@ struct pdeqx_spectral_plan {
   int64_t stage_floats = 0;  // floats of one chain ping-pong buffer
   int64_t mode_floats = 0;   // floats of one mode-space buffer
   size_t ws_bytes = 0;
+  float* lift_scratch = nullptr;  // 4 x 128 floats: folded factors of a pointwise lifting in front of the block
   // last axis, real tables (fp32, generated in fp64)
   float* t_r2c_fwd = nullptr;  // [s_D, 2 m_D]  cos | -sin                (forward)
   float* t_c2r_inv = nullptr;  // [2 m_D, s_D]  c/s cos ; -c/s sin        (inverse, irfft weights c)
@@ -60,10 +61,12 @@ int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, fl
            cudaStream_t s, bool round_out = false);
 // general form: explicit channel counts of THIS call, epilogue mode 1 = aux * act'(.) (cotangent of the pre-activation),
 // mode 2 = the same with a rank-1 cotangent aux_w[o] * aux[b, pixel] (behind a C -> 1 pointwise projection),
+// byp_u / byp_a (modes 0-2, bypass_w == null): rank-one bypass byp_a[o] * byp_u[b, pixel] added before the activation;
 // mode 3 = nothing stored: red_w[o] += sum result * aux[b, pixel], red_b[o] += sum result (in front of a 1 -> C lifting)
 int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
-               float* y, cudaStream_t s, const float* aux_w = nullptr, float* red_w = nullptr, float* red_b = nullptr);
+               float* y, cudaStream_t s, const float* aux_w = nullptr, float* red_w = nullptr, float* red_b = nullptr,
+               const float* byp_u = nullptr, const float* byp_a = nullptr);
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);
 // gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller)
 int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb,

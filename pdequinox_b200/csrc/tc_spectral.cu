@@ -124,6 +124,8 @@ struct SlabParams {
   const float* aux;  // mode 1: cotangent gy [B, c_out, lead, W]; mode 2: its single-channel factor gy1 [B, lead, W]
   float* red_w;        // mode 3: out[o] += sum_{b,pixel} result[b,o,pixel] * aux[b,pixel]   (aux = single-channel field)
   float* red_b;        // mode 3: out[o] += sum_{b,pixel} result[b,o,pixel]                 (may be null)
+  const float* byp_u;  // BYP1: the bypass term is rank one, byp_a[o] * byp_u[b, pixel] (the block's input is a pointwise 1 -> C
+  const float* byp_a;  //       lifting of the single-channel field byp_u; its constant part is folded into `bias`)
   const float* aux_w;  // mode 2: the per-channel factor, gy[b,o,p] = aux_w[o] * gy1[b,p] (cotangent behind a C -> 1 projection)
   float* y;
 };
@@ -158,12 +160,12 @@ static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, i
   off += (uint32_t)epi_bufs * s.epi_buf_bytes;
   s.epi_bufs = (uint32_t)epi_bufs;
   s.bar_off = off;
-  off += 2048;  // barriers, tmem pointer, bias, rank-1 cotangent factor
+  off += 3072;  // barriers, tmem pointer, bias, rank-1 cotangent factor, rank-1 bypass factor
   s.total = off + 1024;  // slack for manual 1024-B alignment of the dynamic base
   return s;
 }
 
-template <int MODE, int ACT>
+template <int MODE, int ACT, bool BYP1>
 __global__ void __launch_bounds__(kThreadsSlab, 1)
 slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z,
             const __grid_constant__ CUtensorMap tm_tab, const __grid_constant__ CUtensorMap tm_w,
@@ -180,6 +182,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint64_t* auxfull = bars + 24;           // [16 epilogue warps][3 buffers] cotangent chunk landed (MODE 1)
   float* bias_s = (float*)(bars + 72);     // [c_out] (<= 128 floats)
   float* auxw_s = bias_s + 128;            // [c_out] per-channel factor of a rank-1 cotangent (MODE 2)
+  float* bypa_s = auxw_s + 128;            // [c_out] per-channel factor of a rank-1 bypass (BYP1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -208,6 +211,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     for (int i = lane; i < p.c_out; i += 32) {
       bias_s[i] = p.bias ? p.bias[i] : 0.f;
       auxw_s[i] = (MODE == 2 && p.aux_w) ? p.aux_w[i] : 0.f;
+      bypa_s[i] = (BYP1 && p.byp_a) ? p.byp_a[i] : 0.f;
     }
     if (lane == 0) {
       tma_prefetch_desc(&tm_y);
@@ -334,6 +338,8 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
       float sv = 0.f;  // MODE 2: this lane's pixel of the single-channel cotangent factor
+      float su = 0.f;  // BYP1: this lane's pixel of the single-channel field behind the lifting
+      if (BYP1) su = __ldg(p.byp_u + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane);
       if (MODE == 1) {
         mbar_wait(&afull[e], eph);
       } else {
@@ -396,7 +402,8 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (j >= nc) break;
-          const float val = v[j] + bias_s[part * ncol + c0 + j];
+          float val = v[j] + bias_s[part * ncol + c0 + j];
+          if (BYP1) val = fmaf(bypa_s[part * ncol + c0 + j], su, val);
           float r;
           if (MODE == 0) {
             if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_f<true>(val);
@@ -985,7 +992,7 @@ bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass) {
 // (bypass_transposed: bypass_w is [c_i_of_this_call... see spectral.cu) ; mode 1: y = aux * act'(.)
 int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
-               float* y, cudaStream_t s, const float* aux_w, float* red_w, float* red_b) {
+               float* y, cudaStream_t s, const float* aux_w, float* red_w, float* red_b, const float* byp_u, const float* byp_a) {
   TcPlan* t = tcp(p);
   const pdeqx_spectral_desc& d = p->desc;
   const int D = d.ndim, sD = d.spatial[D - 1];
@@ -1051,6 +1058,8 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.bias = bypass_b;
   sp.aux = aux;
   sp.aux_w = aux_w;
+  sp.byp_u = byp_u;
+  sp.byp_a = byp_a;
   sp.red_w = red_w;
   sp.red_b = red_b;
   sp.y = y;
@@ -1067,16 +1076,23 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   PDEQX_CHECK_ARG(grid >= sp.wt_per_row, "tc_slab: grid smaller than the number of w-tiles");
   PDEQX_CHECK_ARG(mode == 0 || mode == 3 || act != PDEQX_ACT_IDENTITY, "tc_slab: modes 1 and 2 need an activation");
   const CUtensorMap& tab = t->tm_tab_c2r[table_sel];
-#define PDEQX_SLAB_LAUNCH(M, A)                                                                                        \
-  do {                                                                                                                 \
-    static bool attr = false;                                                                                          \
-    if (!attr) {                                                                                                       \
-      PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<M, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                                     \
-    }                                                                                                                  \
-    tc::slab_kernel<M, A><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L);          \
+  const bool byp1 = byp_u != nullptr;
+  PDEQX_CHECK_ARG(!byp1 || (byp_a && !bypass && mode <= 2), "tc_slab: a rank-one bypass replaces the bypass weight (modes 0-2)");
+#define PDEQX_SLAB_LAUNCH_B(M, A, B1)                                                                                     \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<M, A, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    tc::slab_kernel<M, A, B1><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L);         \
   } while (0)
-  if (mode == 3) PDEQX_SLAB_LAUNCH(3, PDEQX_ACT_IDENTITY);
+#define PDEQX_SLAB_LAUNCH(M, A)                 \
+  do {                                          \
+    if (byp1) PDEQX_SLAB_LAUNCH_B(M, A, true);  \
+    else PDEQX_SLAB_LAUNCH_B(M, A, false);      \
+  } while (0)
+  if (mode == 3) PDEQX_SLAB_LAUNCH_B(3, PDEQX_ACT_IDENTITY, false);
   else if (mode == 0 && act == PDEQX_ACT_IDENTITY) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_IDENTITY);
   else if (mode == 0 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_RELU);
   else if (mode == 0) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_GELU_TANH);
@@ -1084,6 +1100,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   else if (mode == 1) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_GELU_TANH);
   else if (act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_RELU);
   else PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_GELU_TANH);
+#undef PDEQX_SLAB_LAUNCH_B
 #undef PDEQX_SLAB_LAUNCH
   PDEQX_LAUNCHED();
   return PDEQX_OK;
@@ -1093,7 +1110,7 @@ int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int ta
             bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s) {
   const pdeqx_spectral_desc& d = p->desc;
   const int c_in = bypass_transposed ? d.c_out : d.c_in, c_out = bypass_transposed ? d.c_in : d.c_out;
-  return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s, nullptr, nullptr, nullptr);
+  return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix) {

@@ -122,6 +122,7 @@ class TrainStep:
         x, y = _as_device(x), _as_device(y)
         tape = self.tape
         tape.stack.clear()
+        tape.fold_lifting = True  # no gradient w.r.t. the network input is taken: a pointwise lifting may be folded away
         self._reduced = []
         pred = self.model._fwd(x, tape)
         if pred.shape != y.shape:
