@@ -130,16 +130,21 @@ int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* plan, const float* x, co
                              int32_t activation, float* y, float* save_xhat, float* save_z,
                              void* workspace, size_t workspace_bytes, void* stream);
 
-/* The same forward pass for a block whose input is the pointwise 1 -> c_in lifting x[b,i,pixel] = lift_w[i] *
- * lift_u[b,pixel] + lift_b[i] of a single-channel field (pdequinox/arch/_classic_fno.py:71-76 in front of the first
- * ClassicSpectralBlock): x is never written. The first DFT stage of x is the lifting of the first stage of lift_u (the
- * transform is linear) and the bypass term is rank one, (bypass_w . lift_w)[o] * lift_u + const[o], added in the last
- * kernel's epilogue. Needs pdeqx_spectral_block_rank1_ok(plan, 1, activation) == 1 and ndim >= 2; bypass_w required. */
-int pdeqx_spectral_block_fwd_lifted(const pdeqx_spectral_plan* plan, const float* lift_u, const float* lift_w,
-                                    const float* lift_b, const float* w_re, const float* w_im,
-                                    const float* bypass_w, const float* bypass_b, int32_t activation, float* y,
-                                    float* save_xhat, float* save_z, void* workspace, size_t workspace_bytes,
-                                    void* stream);
+/* The same forward pass with the two pointwise ends of an architecture folded in (both optional; both need
+ * pdeqx_spectral_block_rank1_ok(plan, 1, activation) == 1, ndim >= 2 and a bypass):
+ *  - lift_u != NULL (then x must be NULL): the block's input is the pointwise 1 -> c_in lifting x[b,i,pixel] = lift_w[i] *
+ *    lift_u[b,pixel] + lift_b[i] of a single-channel field (pdequinox/arch/_classic_fno.py:71-76 in front of the first
+ *    ClassicSpectralBlock) and is never written: its first DFT stage is the lifting of the first stage of lift_u (the
+ *    transform is linear) and the bypass term is rank one, (bypass_w . lift_w)[o] * lift_u + const[o], added in the last
+ *    kernel's epilogue.
+ *  - proj_out != NULL (then y may be NULL): the block's output only feeds the pointwise C -> 1 projection
+ *    (pdequinox/arch/_classic_fno.py:78-83): proj_out[b,pixel] = sum_o proj_w[o] y[b,o,pixel] + proj_b[0] is reduced in
+ *    the last kernel's epilogue and y is never written. */
+int pdeqx_spectral_block_fwd_ex(const pdeqx_spectral_plan* plan, const float* x, const float* lift_u,
+                                const float* lift_w, const float* lift_b, const float* proj_w, const float* proj_b,
+                                float* proj_out, const float* w_re, const float* w_im, const float* bypass_w,
+                                const float* bypass_b, int32_t activation, float* y, float* save_xhat, float* save_z,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* VJP of the call above (what jax.custom_vjp's bwd rule binds).
  *   gy [B,c_out,*S] cotangent of y; x, saved_xhat, saved_z from the forward.
@@ -165,12 +170,15 @@ int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* plan, const float* x, co
  *    1 -> c_in pointwise lifting (pdequinox/arch/_classic_fno.py:71-76); instead of storing gx the last kernel
  *    accumulates that lifting's gradients lift_gw[i] = sum gx[b,i,pixel] lift_u[b,pixel], lift_gb[i] = sum gx (may be
  *    NULL). Outputs are overwritten. If additionally x == NULL the forward pass ran through
- *    pdeqx_spectral_block_fwd_lifted: the lifted input lift_w[i] * lift_u + lift_b[i] (lift_b may be NULL) was never
- *    materialised and the reverse pass works from lift_u, lift_w, lift_b alone. */
+ *    pdeqx_spectral_block_fwd_ex with a lifted input: lift_w[i] * lift_u + lift_b[i] (lift_b may be NULL) was never
+ *    materialised and the reverse pass works from lift_u, lift_w, lift_b alone.
+ *  - proj_gw != NULL (needs gy_w): the forward pass projected the block's output without storing it
+ *    (pdeqx_spectral_block_fwd_ex with proj_out); the projection's weight gradient proj_gw[o] = sum_{b,pixel}
+ *    act(pre)[b,o,pixel] * gy[b,pixel] is accumulated from the activation recomputed in the cotangent pass. */
 int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* plan, int32_t has_bypass, int32_t activation);
 int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* plan, const float* x, const float* gy, const float* gy_w,
                                 const float* lift_u, float* lift_gw, float* lift_gb, const float* lift_w,
-                                const float* lift_b, const float* w_re,
+                                const float* lift_b, float* proj_gw, const float* w_re,
                                 const float* w_im, const float* bypass_w, const float* bypass_b,
                                 int32_t activation, const float* saved_xhat, const float* saved_z, float* gx,
                                 float* gw_re, float* gw_im, float* g_bypass_w, float* g_bypass_b,

@@ -64,9 +64,9 @@ PROTOTYPES = {
     "pdeqx_spectral_block_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                            C.c_size_t, _P]),
     "pdeqx_spectral_block_rank1_ok": (C.c_int, [_P, _I32, _I32]),
-    "pdeqx_spectral_block_bwd_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
+    "pdeqx_spectral_block_bwd_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P, C.c_size_t, _P]),
-    "pdeqx_spectral_block_fwd_lifted": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_spectral_block_fwd_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_pointwise_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_pointwise_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "pdeqx_set_conv_precision": (None, [_I32]),

@@ -36,21 +36,33 @@ class Sequential(Module):
                                              boundary_mode=boundary_mode, key=key)
 
     def _fwd(self, x, tape):
-        first = self.blocks[0]
-        # a 1 -> C pointwise lifting in front of a spectral block is folded into that block (the lifted tensor is never
-        # written; see ClassicSpectralBlock._fwd_lifted). Only inside a training step's tape with no input gradient wanted
-        # downstream of it: the matching reverse pass accumulates the lifting's gradients instead of an input gradient.
-        fold = (tape is not None and getattr(tape, "fold_lifting", False) and isinstance(self.lifting, PointwiseLinearConv)
+        first, last = self.blocks[0], self.blocks[-1]
+        # Inside a training step's tape (no gradient w.r.t. the network input wanted) both pointwise ends of the architecture
+        # are folded into the spectral blocks next to them, so that neither full-size tensor is ever written:
+        #  * a 1 -> C lifting in front of the first block (ClassicSpectralBlock._fwd_ex(lifting=...));
+        #  * a C -> 1 projection behind the last block (…(proj=...)): reduced in that block's last kernel.
+        # The matching reverse pass accumulates the lifting's / projection's gradients inside the blocks' kernels.
+        folding = tape is not None and getattr(tape, "fold_lifting", False)
+        fold = (folding and isinstance(self.lifting, PointwiseLinearConv)
                 and self.lifting.in_channels == 1 and hasattr(first, "lifted_ok") and first.lifted_ok(x))
+        fold_proj = (folding and isinstance(self.projection, PointwiseLinearConv) and self.projection.out_channels == 1
+                     and self.projection.in_channels == getattr(last, "out_channels", self.projection.in_channels)
+                     and hasattr(last, "projected_ok") and last.projected_ok(x))
+        nb = len(self.blocks)
         if fold:
             tape.push(x)  # stands for the lifting's record (its input)
-            x = first._fwd_lifted(x, self.lifting, tape)
-            rest = self.blocks[1:]
         else:
             x = self.lifting._fwd(x, tape)
-            rest = self.blocks
-        for block in rest:
-            x = block._fwd(x, tape)
+        for i, block in enumerate(self.blocks):
+            kw = {}
+            if fold and i == 0:
+                kw["lifting"] = self.lifting
+            if fold_proj and i == nb - 1:
+                kw["proj"] = self.projection
+            x = block._fwd_ex(x, tape, **kw) if kw else block._fwd(x, tape)
+        if fold_proj:
+            tape.push(None)  # the projection's record: its input was never written
+            return x
         return self.projection._fwd(x, tape)
 
     def _bwd(self, gy, tape, need_gx=False):
@@ -66,23 +78,31 @@ class Sequential(Module):
         #    the first block's last kernel accumulates them instead of writing that gradient out.
         # Both need the block's tcgen05 path (`rank1_ok`); otherwise the plain chain below runs.
         fold_proj = fold_lift = False
-        x_proj = tape.pop()  # what the projection saved (pushed back below)
+        x_proj = tape.pop()  # what the projection saved (pushed back below); None: the forward pass folded it away
+        projected_fwd = x_proj is None
         if hasattr(last, "rank1_ok") and last.rank1_ok(tape):
             fold_proj = isinstance(self.projection, PointwiseLinearConv) and self.projection.out_channels == 1
             # the first block's forward record sits below the later blocks' records: same plan family, ask the block itself
             fold_lift = (isinstance(self.lifting, PointwiseLinearConv) and self.lifting.in_channels == 1 and not need_gx
                          and hasattr(first, "rank1_ok"))
-        tape.push(x_proj)
-        if fold_proj:
-            self.projection._bwd(gy, tape, False)  # weight / bias gradients only
-            hook("projection.")
+        if projected_fwd:
+            if not fold_proj:
+                raise RuntimeError("the projected forward pass needs the rank-one reverse pass of the last block")
+            # bias gradient = sum of the cotangent; the weight gradient comes out of the last block's cotangent kernel
+            self.projection.bias_grad_only(gy, tape)
         else:
-            g = self.projection._bwd(gy, tape, True)
+            tape.push(x_proj)
+            if fold_proj:
+                self.projection._bwd(gy, tape, False)  # weight / bias gradients only
+            else:
+                g = self.projection._bwd(gy, tape, True)
             hook("projection.")
         for i in reversed(range(nb)):
             kw = {}
             if fold_proj and i == nb - 1:
                 kw["gy_w"] = self.projection.weight
+                if projected_fwd:
+                    kw["proj_gw"] = self.projection.grad("weight")
                 g = gy
             lifted_fwd = i == 0 and tape.stack[-1][0] is None  # the forward pass folded the lifting in: it must be unfolded here
             if i == 0 and (lifted_fwd or (fold_lift and self.blocks[0].rank1_ok(tape))):
@@ -96,6 +116,8 @@ class Sequential(Module):
                 g = self.blocks[i]._bwd_ex(g, tape, True, **kw)
             else:
                 g = self.blocks[i]._bwd(g, tape, True)
+            if projected_fwd and i == nb - 1:
+                hook("projection.")
             hook(f"blocks.{i}.")
             if "lift" in kw:
                 tape.pop()  # the lifting's record: its gradients were just written by the block's kernel

@@ -47,22 +47,32 @@ class ClassicSpectralBlock(Block):
     def lifted_ok(self, u):
         return self.spectral_conv.lifted_ok(u, nn.activation_code(self.activation))
 
-    def _fwd_lifted(self, u, lifting, tape):
-        """Forward pass on the input lifting(u) (a 1 -> C PointwiseLinearConv) without materialising it."""
+    def projected_ok(self, x):
+        return self.spectral_conv.projected_ok(x, nn.activation_code(self.activation))
+
+    def _fwd_ex(self, x, tape, lifting=None, proj=None):
+        """Forward pass with the architecture's pointwise ends folded in: `lifting` (a 1 -> C PointwiseLinearConv; `x` is then
+        its single-channel input and the lifted tensor is never materialised) and / or `proj` (a C -> 1 PointwiseLinearConv
+        behind this block: the projected field is returned and this block's output is never written)."""
         act = nn.activation_code(self.activation)
-        y, saved = self.spectral_conv.apply_lifted(u, lifting.weight, lifting.bias, tape, bypass=self.by_pass_conv, act=act,
-                                                   save=tape is not None)
+        y, saved = self.spectral_conv.apply_ex(x, tape, bypass=self.by_pass_conv, act=act, save=tape is not None,
+                                               lifting=(lifting.weight, lifting.bias) if lifting is not None else None,
+                                               proj=(proj.weight, proj.bias) if proj is not None else None)
         if tape is not None:
-            tape.push((None, saved))  # x = None marks the lifted forward pass
+            tape.push((None if lifting is not None else x, saved))  # x = None marks the lifted forward pass
         return y
 
-    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None, lifted=None):
+    def _fwd_lifted(self, u, lifting, tape):
+        return self._fwd_ex(u, tape, lifting=lifting)
+
+    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None, lifted=None, proj_gw=None):
         """gy_w: `gy` is the single-channel factor of a rank-one cotangent; lift = (u, gw, gb): accumulate the gradients of
-        the 1 -> C lifting that produced this block's input from `u` instead of returning the input gradient."""
+        the 1 -> C lifting that produced this block's input from `u` instead of returning the input gradient; proj_gw: the
+        forward pass was projected (`_fwd_ex(proj=...)`): also accumulate the projection's weight gradient."""
         x, saved = tape.pop()
         return self.spectral_conv.apply_bwd(x, gy, saved, tape, bypass=self.by_pass_conv,
                                             act=nn.activation_code(self.activation), need_gx=need_gx, gy_w=gy_w, lift=lift,
-                                            lifted=lifted if x is None else None)
+                                            lifted=lifted if x is None else None, proj_gw=proj_gw)
 
 
 class ClassicSpectralBlockFactory(BlockFactory):

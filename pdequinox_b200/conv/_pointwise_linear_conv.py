@@ -58,6 +58,19 @@ class PointwiseLinearConv(Module):
                                                   _lib.ptr(self.grad("weight")), _lib.ptr(gb), _lib.stream()))
         return gx
 
+    def bias_grad_only(self, gy, tape):
+        """Reverse pass of a C -> 1 projection whose input was never stored (folded into the producing spectral block, which
+        also accumulates the weight gradient): only the bias gradient sum_{b,pixel} gy is formed here."""
+        if self.out_channels != 1:
+            raise ValueError("bias_grad_only is the reverse pass of a C -> 1 projection")
+        if self.bias is None:
+            return
+        B = gy.shape[0]
+        n = int(np.prod(gy.shape[2:]))
+        junk = new_buf(tape, self, "gw1", (1,))
+        _lib.check(_lib.lib().pdeqx_pointwise_bwd(B, 1, 1, n, _lib.ptr(gy), _lib.ptr(self.weight), _lib.ptr(gy), None,
+                                                  _lib.ptr(junk), _lib.ptr(self.grad("bias")), _lib.stream()))
+
     def _fwd(self, x, tape):
         y = self.apply(x, tape)
         if tape is not None:

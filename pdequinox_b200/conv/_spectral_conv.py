@@ -102,24 +102,47 @@ class SpectralConv(Module):
             _lib.stream()))
         return y, (plan, xhat, z)
 
-    def apply_lifted(self, u, lift_w, lift_b, tape, *, bypass, act, save=False):
-        """y = act(spectral(x) + bypass(x)) for x = lift_w[i] * u + lift_b[i] (a pointwise 1 -> C lifting of the single-channel
-        field u [B, 1, *S]) WITHOUT materialising x (pdeqx_spectral_block_fwd_lifted). Returns (y, saved)."""
+    def apply_ex(self, x, tape, *, bypass, act, save=False, lifting=None, proj=None):
+        """The block's forward pass with the pointwise ends of the architecture folded in (pdeqx_spectral_block_fwd_ex).
+        `lifting = (lift_w, lift_b)`: `x` is the single-channel field u [B, 1, *S] and the block's input is the 1 -> C
+        lifting lift_w[i] * u + lift_b[i], never materialised. `proj = (proj_w, proj_b)`: the block's output only feeds a
+        C -> 1 pointwise projection; the projected field [B, 1, *S] is returned and the block's output is never written.
+        Returns (y or projected field, saved)."""
         D = self.num_spatial_dims
-        B = u.shape[0]
+        B = x.shape[0]
         ci, co = self.call_in_channels, self.call_out_channels
-        spatial = tuple(u.shape[2:])
+        spatial = tuple(x.shape[2:])
         plan = get_plan(D, B, ci, co, spatial, self.num_modes)
-        y = new_buf(tape, self, "y", (B, co) + spatial)
+        y = out = None
+        if proj is None:
+            y = new_buf(tape, self, "y", (B, co) + spatial)
+        else:
+            out = new_buf(tape, self, "proj", (B, 1) + spatial)
         xhat = z = None
         if save:
             xhat = new_buf(tape, self, "xhat", (plan.xhat_floats,))
             z = new_buf(tape, self, "z", (plan.z_floats,))
-        _lib.check(_lib.lib().pdeqx_spectral_block_fwd_lifted(
-            plan.handle, _lib.ptr(u), _lib.ptr(lift_w), _lib.ptr(lift_b), _lib.ptr(self.weights_real),
+        lw, lb = lifting if lifting is not None else (None, None)
+        pw, pb = proj if proj is not None else (None, None)
+        _lib.check(_lib.lib().pdeqx_spectral_block_fwd_ex(
+            plan.handle, _lib.ptr(None if lifting is not None else x), _lib.ptr(x if lifting is not None else None),
+            _lib.ptr(lw), _lib.ptr(lb), _lib.ptr(pw), _lib.ptr(pb), _lib.ptr(out), _lib.ptr(self.weights_real),
             _lib.ptr(self.weights_imag), _lib.ptr(bypass.weight), _lib.ptr(bypass.bias), act, _lib.ptr(y), _lib.ptr(xhat),
             _lib.ptr(z), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))
-        return y, (plan, xhat, z)
+        return (out if proj is not None else y), (plan, xhat, z)
+
+    def apply_lifted(self, u, lift_w, lift_b, tape, *, bypass, act, save=False):
+        """`apply_ex` with only the lifting folded in."""
+        return self.apply_ex(u, tape, bypass=bypass, act=act, save=save, lifting=(lift_w, lift_b))
+
+    def projected_ok(self, x, act):
+        """True if `apply_ex(..., proj=...)` can run for a batch / grid of this shape (tcgen05 slab path with a rank-one
+        cotangent in the reverse pass, at least 2 spatial dims, at most 64 output channels)."""
+        D = self.num_spatial_dims
+        if D < 2 or not x.is_cuda or act == _lib.ACT_IDENTITY or self.call_out_channels > 64:
+            return False
+        plan = get_plan(D, x.shape[0], self.call_in_channels, self.call_out_channels, tuple(x.shape[2:]), self.num_modes)
+        return bool(_lib.lib().pdeqx_spectral_block_rank1_ok(plan.handle, 1, act))
 
     def lifted_ok(self, u, act):
         """True if `apply_lifted` can run for a field of this shape (tcgen05 path, at least 2 spatial dims)."""
@@ -131,12 +154,13 @@ class SpectralConv(Module):
         return bool(L.pdeqx_spectral_block_rank1_ok(plan.handle, 1, act)) and (L.pdeqx_spectral_plan_tcgen05_stages(plan.handle) & 1) == 1
 
     def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True, gy_w=None, lift=None,
-                  lifted=None):
+                  lifted=None, proj_gw=None):
         """VJP. With `gy_w` the cotangent is rank one: gy_w[o] * gy[b, 0, *S] (what a C -> 1 pointwise projection sends
         back); it is then formed inside the kernel instead of being materialised. With `lift = (u, gw, gb)` the input
         gradient is not stored: the gradients gw, gb of the 1 -> C pointwise lifting that made x from the field u are
         accumulated instead (pdeqx_spectral_block_bwd_ex). With `lifted = (lift_w, lift_b)` the forward pass was
-        `apply_lifted`: x is None and the reverse pass works from u alone."""
+        `apply_lifted`: x is None and the reverse pass works from u alone. With `proj_gw` (needs `gy_w`) the forward pass was
+        `apply_ex(..., proj=...)`: the projection's weight gradient is accumulated into it from the recomputed activation."""
         plan, xhat, z = saved
         ref = x if x is not None else lift[0]
         gx = new_buf(tape, self, "gx", x.shape) if (need_gx and lift is None) else None
@@ -153,7 +177,7 @@ class SpectralConv(Module):
             lw, lb = lifted if lifted is not None else (None, None)
             _lib.check(_lib.lib().pdeqx_spectral_block_bwd_ex(
                 plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(gy_w), _lib.ptr(u), _lib.ptr(lgw), _lib.ptr(lgb),
-                _lib.ptr(lw), _lib.ptr(lb), _lib.ptr(self.weights_real),
+                _lib.ptr(lw), _lib.ptr(lb), _lib.ptr(proj_gw), _lib.ptr(self.weights_real),
                 _lib.ptr(self.weights_imag), _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),
                 _lib.ptr(self.grad("weights_real")), _lib.ptr(self.grad("weights_imag")), _lib.ptr(gbw), _lib.ptr(gbb),
                 _lib.ptr(scratch), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))

@@ -256,6 +256,11 @@ __device__ __forceinline__ float to_tf32(float v) {  // round to nearest, as the
   return __uint_as_float(r);
 }
 
+__global__ void fill_kernel(float* __restrict__ out, int64_t n, const float* __restrict__ value) {
+  const float v = value ? value[0] : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
 // ---- a pointwise 1 -> C lifting in front of the block, folded in (the lifted tensor x = w (x) u + b never exists) ----
 // a[o] = sum_i Wb[o,i] wl[i];  c[o] = sum_i Wb[o,i] bl[i] + bb[o]: the bypass of the lifted input is a[o] u[pixel] + c[o]
 __global__ void lift_fold_bypass_kernel(const float* __restrict__ wb, const float* __restrict__ bb, const float* __restrict__ wl,
@@ -396,12 +401,15 @@ static Regions make_regions(const pdeqx_spectral_plan* p, void* ws) {
 // lift_u != null: the block's input is the pointwise lifting lift_w[i] * lift_u[b, pixel] + lift_b[i] of a single-channel
 // field and is never materialised (x is ignored): its first DFT stage is the lifting of the field's first stage, and its
 // bypass term is rank one, folded into the last kernel's epilogue
+// proj_out != null: the block's output only feeds a pointwise C -> 1 projection out[b,pixel] = sum_o proj_w[o] y[b,o,pixel] +
+// proj_b; it is reduced in the last kernel's epilogue and y is never written (y may be null)
 static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x, const float* lift_u, const float* lift_w,
-                                   const float* lift_b, const float* w_re,
+                                   const float* lift_b, const float* proj_w, const float* proj_b, float* proj_out,
+                                   const float* w_re,
                                    const float* w_im, const float* bypass_w, const float* bypass_b,
                                    int32_t act, float* y, float* save_xhat, float* save_z, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  PDEQX_CHECK_ARG(p && (x || lift_u) && w_re && w_im && y, "null argument");
+  PDEQX_CHECK_ARG(p && (x || lift_u) && w_re && w_im && (y || proj_out), "null argument");
   PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
   PDEQX_CHECK_ARG(bypass_w || !bypass_b, "bypass_b without bypass_w");
   PDEQX_TRY(check_ws(p, workspace, workspace_bytes));
@@ -442,14 +450,26 @@ static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x,
   }
   // last stage: c2r (+ bypass + bias + activation)
   const int64_t rows = (int64_t)d.batch * d.c_out * p->lead;
+  const bool projected = proj_out != nullptr;
+  if (projected) {
+    PDEQX_CHECK_ARG(proj_w && bypass_w && tc_slab_available(p, true),
+                    "the projected forward pass needs the tcgen05 path (pdeqx_spectral_block_rank1_ok) and a bypass");
+    const int64_t n1 = (int64_t)d.batch * n_pix;
+    fill_kernel<<<(int)(ceil_div(n1, 1024) < 148 * 8 ? ceil_div(n1, 1024) : 148 * 8), 256, 0, s>>>(proj_out, n1, proj_b);
+    PDEQX_LAUNCHED();
+  }
   if (lifted) {
     float* fa = p->lift_scratch;       // a[o]: per-channel factor of the rank-one bypass
     float* fc = p->lift_scratch + 128;  // c[o]: its constant part (+ bypass bias)
     lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
     PDEQX_LAUNCHED();
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-    return tc_slab_ex(p, nullptr, z, /*table_sel=*/0, nullptr, false, fc, act, /*mode=*/0, nullptr, d.c_in, d.c_out, y, s, nullptr,
-                      nullptr, nullptr, lift_u, fa);
+    return tc_slab_ex(p, nullptr, z, /*table_sel=*/0, nullptr, false, fc, act, /*mode=*/projected ? 4 : 0, nullptr, d.c_in, d.c_out,
+                      projected ? proj_out : y, s, projected ? proj_w : nullptr, nullptr, nullptr, lift_u, fa);
+  }
+  if (projected) {
+    TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+    return tc_slab_ex(p, x, z, /*table_sel=*/0, bypass_w, false, bypass_b, act, /*mode=*/4, nullptr, d.c_in, d.c_out, proj_out, s, proj_w);
   }
   if (tc_slab_available(p, bypass_w != nullptr)) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
@@ -466,18 +486,20 @@ extern "C" int pdeqx_spectral_block_fwd(const pdeqx_spectral_plan* p, const floa
                                         int32_t act, float* y, float* save_xhat, float* save_z, void* workspace,
                                         size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(x, "null argument");
-  return spectral_block_fwd_impl(p, x, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, y, save_xhat, save_z,
-                                 workspace, workspace_bytes, stream);
+  return spectral_block_fwd_impl(p, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, y,
+                                 save_xhat, save_z, workspace, workspace_bytes, stream);
 }
 
-extern "C" int pdeqx_spectral_block_fwd_lifted(const pdeqx_spectral_plan* p, const float* lift_u, const float* lift_w,
-                                               const float* lift_b, const float* w_re, const float* w_im,
-                                               const float* bypass_w, const float* bypass_b, int32_t act, float* y,
-                                               float* save_xhat, float* save_z, void* workspace, size_t workspace_bytes,
-                                               void* stream) {
-  PDEQX_CHECK_ARG(lift_u && lift_w, "null argument");
-  return spectral_block_fwd_impl(p, nullptr, lift_u, lift_w, lift_b, w_re, w_im, bypass_w, bypass_b, act, y, save_xhat,
-                                 save_z, workspace, workspace_bytes, stream);
+extern "C" int pdeqx_spectral_block_fwd_ex(const pdeqx_spectral_plan* p, const float* x, const float* lift_u,
+                                           const float* lift_w, const float* lift_b, const float* proj_w,
+                                           const float* proj_b, float* proj_out, const float* w_re, const float* w_im,
+                                           const float* bypass_w, const float* bypass_b, int32_t act, float* y,
+                                           float* save_xhat, float* save_z, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  PDEQX_CHECK_ARG((x != nullptr) != (lift_u != nullptr), "give either x or the lifted field");
+  PDEQX_CHECK_ARG(!lift_u || lift_w, "null argument");
+  return spectral_block_fwd_impl(p, x, lift_u, lift_w, lift_b, proj_w, proj_b, proj_out, w_re, w_im, bypass_w, bypass_b, act, y,
+                                 save_xhat, save_z, workspace, workspace_bytes, stream);
 }
 
 // lift_u != null: gx is not produced; the block's input came from the single-channel field lift_u through a 1 -> c_in
@@ -485,7 +507,7 @@ extern "C" int pdeqx_spectral_block_fwd_lifted(const pdeqx_spectral_plan* p, con
 // accumulated by the last kernel instead
 static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x, const float* gy, const float* gy_w,
                                    const float* lift_u, float* lift_gw, float* lift_gb, const float* lift_w,
-                                   const float* lift_b, const float* w_re, const float* w_im, const float* bypass_w,
+                                   const float* lift_b, float* proj_gw, const float* w_re, const float* w_im, const float* bypass_w,
                                    const float* bypass_b, int32_t act, const float* saved_xhat,
                                    const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                    float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
@@ -514,6 +536,8 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   const int chunk = bwd_chunk_samples(p, n_pix);
   PDEQX_CHECK_ARG(!lifted || (fast && act != PDEQX_ACT_IDENTITY && bypass_w && p->lift_scratch && lift_gw),
                   "the lifted reverse pass needs the tcgen05 slab kernel, a fused activation and a bypass");
+  PDEQX_CHECK_ARG(!proj_gw || (gy_w && d.c_out <= 64), "proj_gw needs the rank-one cotangent (gy_w) and c_out <= 64");
+  if (proj_gw) PDEQX_CUDA(cudaMemsetAsync(proj_gw, 0, sizeof(float) * (size_t)d.c_out, s));
   PDEQX_CHECK_ARG(!gy_w || (fast && act != PDEQX_ACT_IDENTITY),
                   "a rank-1 cotangent needs the tcgen05 slab kernel and a fused activation (pdeqx_spectral_block_rank1_ok)");
   if (!gy_w && !lifted && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
@@ -553,13 +577,15 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
       lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
       PDEQX_LAUNCHED();
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-      PDEQX_TRY(tc_slab_ex(p, nullptr, saved_z, 0, nullptr, false, fc, act, /*mode=*/gy_w ? 2 : 1, gy, d.c_in, d.c_out, scratch_full, s,
-                           gy_w, nullptr, nullptr, lift_u, fa));
+      PDEQX_TRY(tc_slab_ex(p, nullptr, saved_z, 0, nullptr, false, fc, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
+                           scratch_full, s, gy_w, proj_gw, nullptr, lift_u, fa));
     } else if (fast) {
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
       // mode 2: the cotangent tile is formed in the epilogue from its two factors instead of being read from HBM
-      PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/gy_w ? 2 : 1, gy, d.c_in, d.c_out, scratch_full, s,
-                           gy_w));
+      // mode 5: ... and the projection's weight gradient is accumulated from the recomputed activation (the block's output
+      // was never stored by the projected forward pass)
+      PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
+                           scratch_full, s, gy_w, proj_gw));
     } else {
       PDEQX_TRY(stage_c2r(p, saved_z, p->t_c2r_inv, rows_o, nullptr, PDEQX_ACT_IDENTITY, scratch_full, s));
       if (bypass_w)
@@ -637,7 +663,7 @@ extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const floa
                                         const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                         float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                         size_t workspace_bytes, void* stream) {
-  return spectral_block_bwd_impl(p, x, gy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, saved_xhat, saved_z, gx, gw_re, gw_im,
+  return spectral_block_bwd_impl(p, x, gy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, saved_xhat, saved_z, gx, gw_re, gw_im,
                                  g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes, stream);
 }
 
@@ -647,14 +673,15 @@ extern "C" int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* p, int32
 
 extern "C" int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* p, const float* x, const float* gy,
                                            const float* gy_w, const float* lift_u, float* lift_gw, float* lift_gb,
-                                           const float* lift_w, const float* lift_b,
+                                           const float* lift_w, const float* lift_b, float* proj_gw,
                                            const float* w_re, const float* w_im, const float* bypass_w,
                                            const float* bypass_b, int32_t act, const float* saved_xhat,
                                            const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                            float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                            size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(!lift_u || (lift_gw && !gx), "lift_u needs lift_gw and replaces gx");
-  return spectral_block_bwd_impl(p, x, gy, gy_w, lift_u, lift_gw, lift_gb, lift_w, lift_b, w_re, w_im, bypass_w, bypass_b, act, saved_xhat,
+  return spectral_block_bwd_impl(p, x, gy, gy_w, lift_u, lift_gw, lift_gb, lift_w, lift_b, proj_gw, w_re, w_im, bypass_w, bypass_b, act,
+                                 saved_xhat,
                                  saved_z, gx, gw_re, gw_im, g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes,
                                  stream);
 }

@@ -110,6 +110,18 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }
 
+// gelu(x) and gelu'(x) from one tanh
+__device__ __forceinline__ void gelu_both_f(float x, float& y, float& dy) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, k01, k0);
+  const float t = tanh_fast(u);
+  const float du = fmaf(x2, 3.0f * k01, k0);
+  const float hx = 0.5f * x;
+  y = fmaf(hx, t, hx);
+  dy = fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+}
+
 // ==========================================================================================
 // slab kernel
 // ==========================================================================================
@@ -210,7 +222,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   if (warp == 3) {
     for (int i = lane; i < p.c_out; i += 32) {
       bias_s[i] = p.bias ? p.bias[i] : 0.f;
-      auxw_s[i] = (MODE == 2 && p.aux_w) ? p.aux_w[i] : 0.f;
+      auxw_s[i] = ((MODE == 2 || MODE == 4 || MODE == 5) && p.aux_w) ? p.aux_w[i] : 0.f;
       bypa_s[i] = (BYP1 && p.byp_a) ? p.byp_a[i] : 0.f;
     }
     if (lane == 0) {
@@ -343,9 +355,9 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (MODE == 1) {
         mbar_wait(&afull[e], eph);
       } else {
-        if (MODE == 2 || MODE == 3) sv = __ldg(p.aux + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane);
+        if (MODE == 2 || MODE == 3 || MODE == 5) sv = __ldg(p.aux + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane);
         // this warp's store that last used the piece (NB units ago) must have finished reading it
-        if (MODE != 3) {
+        if (MODE != 3 && MODE != 4) {
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
         }
@@ -381,6 +393,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
       // element (o_local, w = 32 q + lane): row o_local of the piece, 16-byte units XOR-swizzled by (row & 7)
       const uint32_t col = smem_u32(piece);
+      float pacc = 0.f;  // MODE 4: projected value of this lane's pixel over this warp's channels
       const uint32_t lane_b = (uint32_t)lane * 4;
       for (int c0 = 0; c0 < ncol; c0 += 16) {
         float v[16];
@@ -395,7 +408,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         if (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) g[j] = j < nc ? ld_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4))) : 0.f;
-        } else if (MODE == 2) {
+        } else if (MODE == 2 || MODE == 5) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) g[j] = j < nc ? auxw_s[part * ncol + c0 + j] * sv : 0.f;
         }
@@ -405,10 +418,22 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           float val = v[j] + bias_s[part * ncol + c0 + j];
           if (BYP1) val = fmaf(bypa_s[part * ncol + c0 + j], su, val);
           float r;
-          if (MODE == 0) {
+          if (MODE == 0 || MODE == 4) {
             if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_f<true>(val);
             else if (ACT == PDEQX_ACT_RELU) r = fmaxf(val, 0.f);
             else r = val;
+            if (MODE == 4) {  // the activated value only feeds the C -> 1 projection: nothing is stored
+              pacc = fmaf(auxw_s[part * ncol + c0 + j], r, pacc);
+              continue;
+            }
+          } else if (MODE == 5) {
+            // rank-one cotangent AND the projection's weight gradient sum_pixels act(pre)[o] * gy1 (the activated output was
+            // never stored: it is recomputed here from the same pre-activation; ncol <= 16 in this mode)
+            float yv, dy;
+            if (ACT == PDEQX_ACT_GELU_TANH) gelu_both_f(val, yv, dy);
+            else { yv = fmaxf(val, 0.f); dy = val > 0.f ? 1.f : 0.f; }
+            r = g[j] * dy;
+            racc_w[0][j] = fmaf(yv, sv, racc_w[0][j]);
           } else {
             if (ACT == PDEQX_ACT_GELU_TANH) r = g[j] * gelu_grad_f<true>(val);
             else if (ACT == PDEQX_ACT_RELU) r = val > 0.f ? g[j] : 0.f;
@@ -416,6 +441,11 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           }
           st_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
         }
+      }
+      if (MODE == 4) {  // this warp's channel slice of the projected pixel: the slices meet in the output by atomic adds
+        atomicAdd(p.y + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane, pacc);
+        if (++a == 2) { a = 0; aph ^= 1; }
+        continue;
       }
       fence_proxy_async();
       __syncwarp();
@@ -433,10 +463,15 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (++a == 2) { a = 0; aph ^= 1; }
       if (++e == NB) { e = 0; eph ^= 1; }
     }
-    if (MODE == 3) {
+    if (MODE == 3 || MODE == 5) {
       // warp-level reduction over the 32 pixels, then the four lane-quarter warps of a channel slice are combined in
       // shared memory (the output tiles are idle in this mode): ONE atomic per channel and CTA
       float* red_s = (float*)(smem + L.epi_off);  // [2 (w, b)][4 q][c_out]
+      if (MODE == 5) {  // the tiles were in use here: every warp's stores must have read them before they are reused
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        named_bar_sync(1, 128 * p.parts);
+      }
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         if (ci * 16 < ncol) {
@@ -999,7 +1034,10 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   const int64_t lead = p->lead;
   PDEQX_CHECK_ARG(mode != 2 || (aux && aux_w), "tc_slab: mode 2 needs the cotangent factors");
   PDEQX_CHECK_ARG(mode != 3 || (aux && red_w && act == PDEQX_ACT_IDENTITY), "tc_slab: mode 3 needs the field, an output and no activation");
-  if (mode == 3) y = red_w;  // (no tile is stored; the tensor map below only needs a valid 16-byte aligned base)
+  PDEQX_CHECK_ARG(mode != 4 || (y && aux_w), "tc_slab: mode 4 needs the projection weight and the output field");
+  PDEQX_CHECK_ARG(mode != 5 || (aux && aux_w && red_w && c_out <= 64), "tc_slab: mode 5 needs the cotangent factors, an output and c_out <= 64");
+  float* y_field = y;  // modes 3 / 4 store no tile: the tile tensor map is a placeholder
+  if (mode == 3) y = red_w;
   PDEQX_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!x || ((uintptr_t)x & 15) == 0),
                   "tc_slab: pointers must be 16-byte aligned");
   const bool bypass = bypass_w != nullptr;
@@ -1034,7 +1072,8 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
     uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * c_out};
     uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
     uint32_t box[3] = {32, 1, (uint32_t)(c_out / 4)};  // one epilogue warp's piece
-    PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box));
+    if (mode == 4) tm_y = tm_z;  // (never used)
+    else PDEQX_TRY(tc::make_tensor_map(&tm_y, y, 3, dims, str, box));
     if (mode == 1) {
       PDEQX_CHECK_ARG(aux && ((uintptr_t)aux & 15) == 0, "tc_slab: aux must be a 16-byte aligned device pointer");
       PDEQX_TRY(tc::make_tensor_map(&tm_aux, aux, 3, dims, str, box));
@@ -1062,7 +1101,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.byp_a = byp_a;
   sp.red_w = red_w;
   sp.red_b = red_b;
-  sp.y = y;
+  sp.y = mode == 4 ? y_field : y;
   // mode 1 keeps three epilogue tiles (cotangent prefetch distance 2); the load pipeline gets what is left
   const int epi_bufs = mode == 1 ? 3 : 2;
   int stages = 0;
@@ -1074,10 +1113,10 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   int grid = (int)(sp.units < t->sms ? sp.units : t->sms);
   grid = grid / sp.wt_per_row * sp.wt_per_row;  // every CTA keeps one w-tile of the table (units stride by the grid size)
   PDEQX_CHECK_ARG(grid >= sp.wt_per_row, "tc_slab: grid smaller than the number of w-tiles");
-  PDEQX_CHECK_ARG(mode == 0 || mode == 3 || act != PDEQX_ACT_IDENTITY, "tc_slab: modes 1 and 2 need an activation");
+  PDEQX_CHECK_ARG(mode == 0 || mode == 3 || mode == 4 || act != PDEQX_ACT_IDENTITY, "tc_slab: modes 1, 2 and 5 need an activation");
   const CUtensorMap& tab = t->tm_tab_c2r[table_sel];
   const bool byp1 = byp_u != nullptr;
-  PDEQX_CHECK_ARG(!byp1 || (byp_a && !bypass && mode <= 2), "tc_slab: a rank-one bypass replaces the bypass weight (modes 0-2)");
+  PDEQX_CHECK_ARG(!byp1 || (byp_a && !bypass && mode != 3), "tc_slab: a rank-one bypass replaces the bypass weight");
 #define PDEQX_SLAB_LAUNCH_B(M, A, B1)                                                                                     \
   do {                                                                                                                    \
     static bool attr = false;                                                                                             \
@@ -1098,8 +1137,13 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   else if (mode == 0) PDEQX_SLAB_LAUNCH(0, PDEQX_ACT_GELU_TANH);
   else if (mode == 1 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_RELU);
   else if (mode == 1) PDEQX_SLAB_LAUNCH(1, PDEQX_ACT_GELU_TANH);
-  else if (act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_RELU);
-  else PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_GELU_TANH);
+  else if (mode == 2 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_RELU);
+  else if (mode == 2) PDEQX_SLAB_LAUNCH(2, PDEQX_ACT_GELU_TANH);
+  else if (mode == 4 && act == PDEQX_ACT_IDENTITY) PDEQX_SLAB_LAUNCH(4, PDEQX_ACT_IDENTITY);
+  else if (mode == 4 && act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(4, PDEQX_ACT_RELU);
+  else if (mode == 4) PDEQX_SLAB_LAUNCH(4, PDEQX_ACT_GELU_TANH);
+  else if (act == PDEQX_ACT_RELU) PDEQX_SLAB_LAUNCH(5, PDEQX_ACT_RELU);
+  else PDEQX_SLAB_LAUNCH(5, PDEQX_ACT_GELU_TANH);
 #undef PDEQX_SLAB_LAUNCH_B
 #undef PDEQX_SLAB_LAUNCH
   PDEQX_LAUNCHED();

@@ -137,3 +137,36 @@ def test_tf32_fno_train_step(cuda, D, spatial, hidden, modes, blocks):
             assert rel_l2(g[k], g_ref[k]) <= 5e-3, k  # chained TF32 stages through 2 blocks and their reverse pass
     finally:
         pdeqx.set_precision("fp32")
+
+
+@pytest.mark.parametrize("spatial,hidden,blocks,act", [
+    ((64, 128), 32, 2, "gelu"),
+    ((32, 256), 64, 1, "relu"),   # one block: lifting and projection folded into the same forward call
+    ((128, 128), 64, 3, "gelu"),
+])
+def test_tf32_folded_forward_equals_plain_forward(cuda, spatial, hidden, blocks, act):
+    """The training-tape forward pass (1 -> C lifting and C -> 1 projection folded into the first / last spectral block:
+    neither full-size tensor is written) gives the same prediction as the plain layer-by-layer forward pass and as the
+    oracle (pdequinox/arch/_classic_fno.py:71-83 around pdequinox/blocks/_classic_spectral_block.py:72-75)."""
+    from pdequinox_b200._module import Tape
+    from pdequinox_b200 import nn as pnn
+    pdeqx.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(21)
+        model = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=hidden, num_modes=16, num_blocks=blocks,
+                                 activation=getattr(pnn, act), key=9)
+        with torch.no_grad():
+            model.lifting.bias.add_(0.25)
+            model.projection.bias.add_(-0.4)
+        x = rng.standard_normal((3, 1) + spatial)
+        plain = host(model._fwd(dev(x), None))
+        tape = Tape()
+        tape.fold_lifting = True
+        folded = host(model._fwd(dev(x), tape))
+        assert tape.stack[-1] is None, "the projection was not folded into the last block"
+        assert rel_l2(folded, plain) <= 2e-4
+        p = {k: host(getattr(o, f)).astype(np.float64) for k, o, f in model.named_leaves()}
+        ref = onn.fno_forward(p, x, (16, 16), blocks, activation=act)
+        assert rel_l2(folded, ref) <= TOL
+    finally:
+        pdeqx.set_precision("fp32")
