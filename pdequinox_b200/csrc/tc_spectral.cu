@@ -169,7 +169,7 @@ static SlabSmem slab_smem(int W, int c_in, int c_out, bool bypass, int stages, i
   s.epi_off = off;
   s.chunk_bytes = (uint32_t)c_out * 128;
   s.epi_buf_bytes = 4 * s.chunk_bytes;
-  off += (uint32_t)epi_bufs * s.epi_buf_bytes;
+  off += epi_bufs > 0 ? (uint32_t)epi_bufs * s.epi_buf_bytes : 4096u;  // (modes 3 / 4 store no tile: 4 KB for the final reduction)
   s.epi_bufs = (uint32_t)epi_bufs;
   s.bar_off = off;
   off += 3072;  // barriers, tmem pointer, bias, rank-1 cotangent factor, rank-1 bypass factor
@@ -340,6 +340,21 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (first < p.units) load_aux(first, 0);
       if (first + stride < p.units) load_aux(first + stride, 1);
     }
+    // single-channel fields read per pixel (the rank-one factors): loaded ONE UNIT AHEAD -- this stage is latency bound and a
+    // dependent global load at the top of every unit would sit on its critical path
+    constexpr bool kUsesAux1 = MODE == 2 || MODE == 3 || MODE == 5;
+    auto field_index = [&](int64_t un) -> int64_t {
+      const int pxn = (int)(un % p.wt_per_row) * 128 + q * 32;
+      const int64_t bln = un / p.wt_per_row;
+      const int lun = p.lead / p.rpu;
+      return ((bln / lun) * p.lead + (int)(bln % lun) * p.rpu + pxn / p.W) * p.W + (pxn % p.W) + lane;
+    };
+    float sv_next = 0.f, su_next = 0.f;
+    if (first < p.units) {
+      const int64_t fi = field_index(first);
+      if (kUsesAux1) sv_next = __ldg(p.aux + fi);
+      if (BYP1) su_next = __ldg(p.byp_u + fi);
+    }
     for (int64_t u = first; u < p.units; u += stride) {
       const int px = (int)(u % p.wt_per_row) * 128 + q * 32;  // this warp's pixels inside the unit's row group
       const int64_t bl = u / p.wt_per_row;
@@ -347,15 +362,18 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int l = (int)(bl % lu) * p.rpu + px / p.W;
       const int b = (int)(bl / lu);
       uint8_t* piece = ebuf0 + (size_t)e * L.epi_buf_bytes;
+      const float sv = sv_next;  // MODE 2 / 3 / 5: this lane's pixel of the single-channel cotangent factor / field
+      const float su = su_next;  // BYP1: this lane's pixel of the single-channel field behind the lifting
+      if ((kUsesAux1 || BYP1) && u + stride < p.units) {
+        const int64_t fi = field_index(u + stride);
+        if (kUsesAux1) sv_next = __ldg(p.aux + fi);
+        if (BYP1) su_next = __ldg(p.byp_u + fi);
+      }
       mbar_wait(&tfull[a], aph);
       tc_fence_after();
-      float sv = 0.f;  // MODE 2: this lane's pixel of the single-channel cotangent factor
-      float su = 0.f;  // BYP1: this lane's pixel of the single-channel field behind the lifting
-      if (BYP1) su = __ldg(p.byp_u + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane);
       if (MODE == 1) {
         mbar_wait(&afull[e], eph);
       } else {
-        if (MODE == 2 || MODE == 3 || MODE == 5) sv = __ldg(p.aux + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane);
         // this warp's store that last used the piece (NB units ago) must have finished reading it
         if (MODE != 3 && MODE != 4) {
           if (lane == 0) tma_store_wait_read<1>();
@@ -1102,8 +1120,9 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   sp.red_w = red_w;
   sp.red_b = red_b;
   sp.y = mode == 4 ? y_field : y;
-  // mode 1 keeps three epilogue tiles (cotangent prefetch distance 2); the load pipeline gets what is left
-  const int epi_bufs = mode == 1 ? 3 : 2;
+  // mode 1 keeps three epilogue tiles (cotangent prefetch distance 2), modes 3 / 4 store no tile and keep none; the load
+  // pipeline gets what is left
+  const int epi_bufs = mode == 1 ? 3 : (mode == 3 || mode == 4) ? 0 : 2;
   int stages = 0;
   for (int st = 6; st >= 2; --st)
     if (tc::slab_smem(sD, c_in, c_out, bypass, st, epi_bufs).total <= 227 * 1024) { stages = st; break; }
