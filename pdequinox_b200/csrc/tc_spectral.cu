@@ -323,13 +323,28 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     uint64_t* afull = auxfull + (part * 4 + q) * 3;
     int a = 0, e = 0;
     uint32_t aph = 0, eph = 0;
-    auto load_aux = [&](int64_t un, int buf) {
-      const int pxn = (int)(un % p.wt_per_row) * 128 + q * 32;
-      const int64_t bln = un / p.wt_per_row;
-      const int lu = p.lead / p.rpu;
+    // Unit coordinates advance incrementally (units stride by the grid size, a multiple of wt_per_row, so a CTA keeps its
+    // w-tile and (row group, sample) move by a constant): this stage is bound by its instruction count and 64-bit
+    // divisions per unit cost as much as the activation math.
+    const int lu = p.lead / p.rpu;
+    const int px = (int)(first % p.wt_per_row) * 128 + q * 32;  // this warp's pixels inside the unit's row group
+    const int pxw = px % p.W, l_off = px / p.W;
+    const int64_t dbl = stride / p.wt_per_row;
+    const int adv_b = (int)(dbl / lu), adv_l = (int)(dbl % lu);
+    struct Coord { int li, b; };
+    auto advance = [&](Coord& c) {
+      c.li += adv_l;
+      c.b += adv_b;
+      if (c.li >= lu) { c.li -= lu; ++c.b; }
+    };
+    Coord cur{(int)((first / p.wt_per_row) % lu), (int)((first / p.wt_per_row) / lu)};
+    Coord nxt = cur;  // coordinates one unit ahead (rank-one field prefetch)
+    advance(nxt);
+    Coord nx2 = nxt;  // two units ahead (MODE 1: cotangent piece prefetch)
+    advance(nx2);
+    auto load_aux = [&](const Coord& c, int buf) {
       mbar_expect_tx(&afull[buf], (uint32_t)ncol * 128);
-      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], pxn % p.W, (int)(bln % lu) * p.rpu + pxn / p.W,
-                  (int)(bln / lu) * p.c_out + part * ncol);
+      tma_load_3d(ebuf0 + (size_t)buf * L.epi_buf_bytes, &tm_aux, &afull[buf], pxw, c.li * p.rpu + l_off, c.b * p.c_out + part * ncol);
     };
     float racc_w[2][16], racc_b[2][16];  // MODE 3 only (dead otherwise); c_out / parts <= 32 channels per warp
 #pragma unroll
@@ -337,35 +352,29 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 16; ++j) racc_w[ci][j] = racc_b[ci][j] = 0.f;
     if (MODE == 1 && lane == 0) {
-      if (first < p.units) load_aux(first, 0);
-      if (first + stride < p.units) load_aux(first + stride, 1);
+      if (first < p.units) load_aux(cur, 0);
+      if (first + stride < p.units) load_aux(nxt, 1);
     }
     // single-channel fields read per pixel (the rank-one factors): loaded ONE UNIT AHEAD -- this stage is latency bound and a
     // dependent global load at the top of every unit would sit on its critical path
     constexpr bool kUsesAux1 = MODE == 2 || MODE == 3 || MODE == 5;
-    auto field_index = [&](int64_t un) -> int64_t {
-      const int pxn = (int)(un % p.wt_per_row) * 128 + q * 32;
-      const int64_t bln = un / p.wt_per_row;
-      const int lun = p.lead / p.rpu;
-      return ((bln / lun) * p.lead + (int)(bln % lun) * p.rpu + pxn / p.W) * p.W + (pxn % p.W) + lane;
+    auto field_index = [&](const Coord& c) -> int64_t {
+      return ((int64_t)c.b * p.lead + c.li * p.rpu + l_off) * p.W + pxw + lane;
     };
     float sv_next = 0.f, su_next = 0.f;
     if (first < p.units) {
-      const int64_t fi = field_index(first);
+      const int64_t fi = field_index(cur);
       if (kUsesAux1) sv_next = __ldg(p.aux + fi);
       if (BYP1) su_next = __ldg(p.byp_u + fi);
     }
-    for (int64_t u = first; u < p.units; u += stride) {
-      const int px = (int)(u % p.wt_per_row) * 128 + q * 32;  // this warp's pixels inside the unit's row group
-      const int64_t bl = u / p.wt_per_row;
-      const int lu = p.lead / p.rpu;
-      const int l = (int)(bl % lu) * p.rpu + px / p.W;
-      const int b = (int)(bl / lu);
+    for (int64_t u = first; u < p.units; u += stride, cur = nxt, nxt = nx2, advance(nx2)) {
+      const int l = cur.li * p.rpu + l_off;
+      const int b = cur.b;
       uint8_t* piece = ebuf0 + (size_t)e * L.epi_buf_bytes;
       const float sv = sv_next;  // MODE 2 / 3 / 5: this lane's pixel of the single-channel cotangent factor / field
       const float su = su_next;  // BYP1: this lane's pixel of the single-channel field behind the lifting
       if ((kUsesAux1 || BYP1) && u + stride < p.units) {
-        const int64_t fi = field_index(u + stride);
+        const int64_t fi = field_index(nxt);
         if (kUsesAux1) sv_next = __ldg(p.aux + fi);
         if (BYP1) su_next = __ldg(p.byp_u + fi);
       }
@@ -461,20 +470,20 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         }
       }
       if (MODE == 4) {  // this warp's channel slice of the projected pixel: the slices meet in the output by atomic adds
-        atomicAdd(p.y + ((int64_t)b * p.lead + l) * p.W + (px % p.W) + lane, pacc);
+        atomicAdd(p.y + ((int64_t)b * p.lead + l) * p.W + pxw + lane, pacc);
         if (++a == 2) { a = 0; aph ^= 1; }
         continue;
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&tm_y, piece, px % p.W, l, b * p.c_out + part * ncol);
+        tma_store_3d(&tm_y, piece, pxw, l, b * p.c_out + part * ncol);
         tma_store_commit();
         if (MODE == 1) {
           const int64_t un = u + 2 * stride;
           if (un < p.units) {  // cotangent piece two units ahead, into the buffer whose store (previous unit) has drained
             tma_store_wait_read<1>();
-            load_aux(un, e == 0 ? NB - 1 : e - 1);
+            load_aux(nx2, e == 0 ? NB - 1 : e - 1);
           }
         }
       }
