@@ -18,6 +18,8 @@
 #include <vector>
 
 #include "spectral_plan.h"
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace pdeqx {
@@ -318,6 +320,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const int part = (warp - 4) >> 2;  // which slice of the output channels
     const int ncol = p.c_out / p.parts;
     const int nc = ncol < 16 ? ncol : 16;  // valid columns of a 16-column TMEM load (8 when c_out = 32)
+    const uint32_t bias_sa = smem_u32(bias_s), auxw_sa = smem_u32(auxw_s), bypa_sa = smem_u32(bypa_s);
     const int NB = (int)L.epi_bufs;  // 2 (MODE 0) or 3 (MODE 1: the cotangent piece is prefetched two units ahead)
     uint8_t* ebuf0 = smem + L.epi_off + (size_t)q * L.chunk_bytes + (size_t)part * ncol * 128;  // this warp's piece in buffer 0
     uint64_t* afull = auxfull + (part * 4 + q) * 3;
@@ -422,7 +425,10 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const uint32_t col = smem_u32(piece);
       float pacc = 0.f;  // MODE 4: projected value of this lane's pixel over this warp's channels
       const uint32_t lane_b = (uint32_t)lane * 4;
-      for (int c0 = 0; c0 < ncol; c0 += 16) {
+      // one 16-column TMEM load of which NC (8 or 16, compile time: the element loop is straight-line code, so the
+      // independent activation chains of a chunk overlap) columns are this warp's channels
+      auto chunk = [&](int c0, auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;
         float v[16];
         tmem_ld16(t0 + c0, v);
         tmem_ld_wait();
@@ -431,26 +437,35 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
-        float g[16];
+        // per-channel constants of this chunk (shared-space vector loads)
+        const uint32_t cidx = (uint32_t)(part * ncol + c0) * 4;
+        float bias_c[NC], bypa_c[NC], auxw_c[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j += 4) {
+          ld_shared_const_v4(bias_sa + cidx + j * 4, bias_c + j);
+          if (BYP1) ld_shared_const_v4(bypa_sa + cidx + j * 4, bypa_c + j);
+          if (MODE == 2 || MODE == 4 || MODE == 5) ld_shared_const_v4(auxw_sa + cidx + j * 4, auxw_c + j);
+        }
+        const uint32_t row0 = col + (uint32_t)c0 * 128;
+        float g[NC];
         if (MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = j < nc ? ld_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4))) : 0.f;
+          for (int j = 0; j < NC; ++j) g[j] = ld_shared_f32(row0 + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)));
         } else if (MODE == 2 || MODE == 5) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) g[j] = j < nc ? auxw_s[part * ncol + c0 + j] * sv : 0.f;
+          for (int j = 0; j < NC; ++j) g[j] = auxw_c[j] * sv;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (j >= nc) break;
-          float val = v[j] + bias_s[part * ncol + c0 + j];
-          if (BYP1) val = fmaf(bypa_s[part * ncol + c0 + j], su, val);
+        for (int j = 0; j < NC; ++j) {
+          float val = v[j] + bias_c[j];
+          if (BYP1) val = fmaf(bypa_c[j], su, val);
           float r;
           if (MODE == 0 || MODE == 4) {
             if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_f<true>(val);
             else if (ACT == PDEQX_ACT_RELU) r = fmaxf(val, 0.f);
             else r = val;
             if (MODE == 4) {  // the activated value only feeds the C -> 1 projection: nothing is stored
-              pacc = fmaf(auxw_s[part * ncol + c0 + j], r, pacc);
+              pacc = fmaf(auxw_c[j], r, pacc);
               continue;
             }
           } else if (MODE == 5) {
@@ -466,8 +481,16 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             else if (ACT == PDEQX_ACT_RELU) r = val > 0.f ? g[j] : 0.f;
             else r = g[j];
           }
-          st_shared_f32(col + (uint32_t)(c0 + j) * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
+          st_shared_f32(row0 + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
         }
+      };
+      if (nc == 16) {
+        for (int c0 = 0; c0 < ncol; c0 += 16) {
+          if (c0 + 16 <= ncol) chunk(c0, std::integral_constant<int, 16>{});
+          else chunk(c0, std::integral_constant<int, 8>{});  // 24 channels per warp (c_out = 96): the tail chunk has 8
+        }
+      } else {
+        chunk(0, std::integral_constant<int, 8>{});
       }
       if (MODE == 4) {  // this warp's channel slice of the projected pixel: the slices meet in the output by atomic adds
         atomicAdd(p.y + ((int64_t)b * p.lead + l) * p.W + pxw + lane, pacc);
