@@ -221,6 +221,10 @@ void pdeqx_set_conv_precision(int32_t precision);
 /* which passes of this convolution run on tcgen05 under the current settings
  * (bit 0: forward, bit 1: data gradient, bit 2: filter gradient); 0 = CUDA-core fp32 path */
 int pdeqx_conv_tcgen05_passes(const pdeqx_conv_desc* d);
+/* how many forward / data-gradient launches of this process took the CTA-pair kernel (tcgen05 cta_group::2: two CTAs of one
+ * TPC share one N = 192 MMA, each holding half of the filter): the C = 64 shapes whose row chains split into equal segments.
+ * A diagnostic for tests and profiles; the one-CTA kernel covers the rest. */
+int64_t pdeqx_conv_pair_launches(void);
 /* output spatial size per axis: floor((s + lo + hi - d(k-1) - 1)/stride) + 1 */
 int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]);
 /* y = act(corr(pad(x), w) + b + residual); w [c_out, c_in/groups, *k]; b [c_out]; b, residual may be NULL */

@@ -15,7 +15,7 @@ PAD_ZEROS, PAD_WRAP, PAD_REFLECT, PAD_EDGE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32 = 0, 1
 K_SPECTRAL_SLAB, K_SPECTRAL_R2C, K_SPECTRAL_MODES, K_POINTWISE_WGRAD, K_CONV_FWD, K_CONV_BWD_DATA, K_CONV_BWD_FILTER = range(1, 8)
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpdeqx_b200.so")
+LIB_PATH = os.environ.get("PDEQX_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpdeqx_b200.so")
 
 
 class PdeqxError(RuntimeError):
@@ -71,6 +71,7 @@ PROTOTYPES = {
     "pdeqx_pointwise_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "pdeqx_set_conv_precision": (None, [_I32]),
     "pdeqx_conv_tcgen05_passes": (C.c_int, [C.POINTER(ConvDesc)]),
+    "pdeqx_conv_pair_launches": (C.c_int64, []),
     "pdeqx_conv_out_spatial": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
     "pdeqx_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),

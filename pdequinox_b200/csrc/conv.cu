@@ -454,6 +454,9 @@ int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w
 
 using namespace pdeqx;
 
+namespace pdeqx { int64_t tc_conv_pair_launches(); }
+extern "C" int64_t pdeqx_conv_pair_launches(void) { return pdeqx::tc_conv_pair_launches(); }
+
 extern "C" int pdeqx_conv_tcgen05_passes(const pdeqx_conv_desc* d) {
   ConvGeom g;
   if (conv_geometry(d, &g) != PDEQX_OK) return 0;

@@ -36,6 +36,8 @@ struct ConvParams {
   int act, has_residual, has_bias;
   int64_t items;  // batch * 2 halves * segs_per_image
   const float* bias;
+  float* y;          // pair kernel: output / residual as plain pointers (its epilogue stores from registers)
+  const float* res;
 };
 
 struct ConvSmem {
@@ -58,8 +60,8 @@ static ConvSmem conv_smem(int c_in, int c_out, int k) {
   s.tile_off = off;
   s.tile_bytes = (uint32_t)(c_out / 2) * 512;
   off += s.tile_bytes;  // one output / residual tile (the ring needs the rest of the 227 KB)
-  s.xbuf_off = off;     // edge-column exchange: [2 taps][16 warps][8 channels][kMaxDil] floats
-  off += 2 * 16 * 8 * kMaxDil * 4;
+  s.xbuf_off = off;     // edge-column exchange: [2 taps][16 warps][kMaxDil columns][8 channels] floats
+  off += 2 * 16 * 8 * kMaxDil * 4 + 64;  // (+ one all-zero column slot: the source of dropped dirichlet taps, pair kernel)
   s.bar_off = off;
   off += 1024;
   s.total = off + 1024;
@@ -280,6 +282,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const uint32_t lane_b = (uint32_t)lane * 4;
     float* xb = (float*)(smem + L.xbuf_off);
     const uint32_t xbs = smem_u32(xb);
+    // where this lane's out-of-warp sources sit in the exchange buffer (own slot 0 if it has none: the value is not used)
+    const uint32_t far0_base = xbs + (((0 * 16 + (uint32_t)(og * 4 + (use0 && !in0 ? (c0 >> 5) : q))) * kMaxDil +
+                                       (uint32_t)(use0 && !in0 ? (c0 & 31) - (32 - d) : 0)) * ocnt) * 4;
+    const uint32_t far2_base = xbs + (((1 * 16 + (uint32_t)(og * 4 + (use2 && !in2 ? (c2 >> 5) : q))) * kMaxDil +
+                                       (uint32_t)(use2 && !in2 ? (c2 & 31) : 0)) * ocnt) * 4;
     for (int64_t item = first; item < p.items; item += stride) {
       const ConvItem it = conv_item(p, item);
       const int ch0 = it.b * p.c_out + it.half * NOH + og * ocnt;
@@ -304,16 +311,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         if (lane == 0) mbar_arrive(&tempty[a]);
         // Output column w gathers D_0[colmap(w - d)] + D_1[w] + D_2[colmap(w + d)]. Sources inside the warp's own 32 columns
         // come by shuffle; the d columns next to a warp edge (and the wrapped ones) go through a small exchange buffer.
-        const int xo = dbuf ? (int)par * (kMaxDil / 2) : 0;
-        float* xb0 = xb + ((0 * 16 + wid) * ocnt) * kMaxDil + xo;  // my last d lanes of D_0
-        float* xb2 = xb + ((1 * 16 + wid) * ocnt) * kMaxDil + xo;  // my first d lanes of D_2
-        if (lane >= 32 - d) {
-#pragma unroll
-          for (int jx = 0; jx < ocnt; ++jx) xb0[jx * kMaxDil + lane - (32 - d)] = v0[jx];
+        // Exchange layout [tap][warp][column slot][8 channels]: a column's 8 channels are 32 contiguous bytes, so an edge lane
+        // writes / a neighbour reads them with two 128-bit accesses (the shared-memory pipe is shared with the tensor core's
+        // operand fetch, which alone takes half of it: 16 scalar loads + 16 scalar stores per unit and warp were as much again)
+        const uint32_t xo = dbuf ? par * (kMaxDil / 2) : 0u;
+        if (lane >= 32 - d) {  // my last d columns of D_0
+          const uint32_t a0 = xbs + (((0 * 16 + (uint32_t)wid) * kMaxDil + xo + (uint32_t)(lane - (32 - d))) * ocnt) * 4;
+          st_shared_v4(a0, v0);
+          st_shared_v4(a0 + 16, v0 + 4);
         }
-        if (lane < d) {
-#pragma unroll
-          for (int jx = 0; jx < ocnt; ++jx) xb2[jx * kMaxDil + lane] = v2[jx];
+        if (lane < d) {  // my first d columns of D_2
+          const uint32_t a2 = xbs + (((1 * 16 + (uint32_t)wid) * kMaxDil + xo + (uint32_t)lane) * ocnt) * 4;
+          st_shared_v4(a2, v2);
+          st_shared_v4(a2 + 16, v2 + 4);
         }
         if (p.has_residual) {
           mbar_wait(&rfull_w[wid], eph);
@@ -324,16 +334,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
         named_bar_sync(1 + og, 128);
         // branch-free gather: every lane loads a (valid) exchange-buffer address and selects
-        const uint32_t far0 = xbs + (uint32_t)(((0 * 16 + (og * 4 + (use0 && !in0 ? (c0 >> 5) : q))) * ocnt) * kMaxDil + xo +
-                                               (use0 && !in0 ? (c0 & 31) - (32 - d) : 0)) * 4;
-        const uint32_t far2 = xbs + (uint32_t)(((1 * 16 + (og * 4 + (use2 && !in2 ? (c2 >> 5) : q))) * ocnt) * kMaxDil + xo +
-                                               (use2 && !in2 ? (c2 & 31) : 0)) * 4;
+        const uint32_t far0 = far0_base + xo * (ocnt * 4), far2 = far2_base + xo * (ocnt * 4);
         float f0[ocnt], f2[ocnt], res[ocnt];
-#pragma unroll
-        for (int jx = 0; jx < ocnt; ++jx) {
-          f0[jx] = ld_shared_f32(far0 + jx * kMaxDil * 4);
-          f2[jx] = ld_shared_f32(far2 + jx * kMaxDil * 4);
-        }
+        ld_shared_v4(far0, f0);
+        ld_shared_v4(far0 + 16, f0 + 4);
+        ld_shared_v4(far2, f2);
+        ld_shared_v4(far2 + 16, f2 + 4);
         if (p.has_residual) {
 #pragma unroll
           for (int jx = 0; jx < ocnt; ++jx) res[jx] = ld_shared_f32(piece + (uint32_t)jx * 128 + (lane_b ^ ((uint32_t)jx << 4)));
@@ -373,6 +379,280 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<kConvTmemCols>(tmem_base);
+  }
+}
+
+// ==========================================================================================
+// CTA-pair variant (cta_group::2): the same implicit GEMM with ALL output channels per unit.
+// ==========================================================================================
+// The one-CTA kernel above keeps one half of the filter (73 KB) next to the 4-row input ring, so a unit is N = 96 wide:
+// per loaded row it has only 24 x 56 cycles of tensor work, with ONE 32 KB row in flight per SM -- it is bound by the
+// latency of that single outstanding row (Little: 148 x 32 KB / ~1.2 us = 3.9 TB/s of operand traffic, which it needs
+// twice because both channel halves read every x row). Here two CTAs of one TPC form a pair: each keeps ITS half of the
+// filter and ITS OWN image rows (M = 256 = 128 pixels of each CTA's row), and one tcgen05.mma.cta_group::2 of N = 192
+// reads the filter halves from both shared memories. Per loaded row a CTA now has 24 x 96 cycles of tensor work, every x
+// row is fetched once, and the same 4-slot ring covers the load latency twice over.
+//   * both CTAs load their own rows / filter half with cta_group::2 TMA loads that count on the LEADER's barriers;
+//   * the leader's elected lane issues every MMA and commits (multicast) to the ring / accumulator barriers of both CTAs;
+//   * the epilogue warps of both CTAs drain their own TMEM (16 warps x 2 passes of 8 channels), store straight from
+//     registers (a warp-wide store per channel is one 128-byte line) and release the accumulator on the leader's barrier;
+//   * dirichlet row taps are zero rows (out-of-range TMA coordinate) instead of skipped MMAs: the two CTAs work on
+//     different rows and must issue the same instruction stream.
+constexpr int kAcc2 = 2;  // accumulator stages: 2 x 192 columns
+
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res, ConvParams p, ConvSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* full = bars;         // [kRing] ring slots (the leader's count both CTAs' bytes)
+  uint64_t* empty = bars + 4;    // [kRing]
+  uint64_t* tfull = bars + 8;    // [kAcc2] accumulators
+  uint64_t* tempty = bars + 12;  // [kAcc2] (the leader's: 16 epilogue warps of each CTA)
+  uint64_t* wfull = bars + 16;   // weights (the leader's)
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 19);
+  float* bias_s = (float*)(bars + 20);  // [c_out = 64]
+  uint64_t* xbar = bars + 56;           // [4 channel groups][2] edge columns of a pass are in the exchange buffer
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NOH = p.c_out / 2, NH = 3 * NOH, N = 2 * NH;  // 32, 96 (per CTA), 192 (per MMA)
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_y);
+    tma_prefetch_desc(&tm_res);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kAcc2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 32);
+    }
+    mbar_init(wfull, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&xbar[i], 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<kConvTmemCols>(tmem_ptr);
+  if (warp == 3) {
+    for (int i = lane; i < p.c_out; i += 32) bias_s[i] = p.has_bias ? p.bias[i] : 0.f;
+    if (lane < 16) ((float*)(smem + L.xbuf_off + 2 * 16 * 8 * kMaxDil * 4))[lane] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  // pair q of the grid takes item pairs q, q + pairs, ...; the CTA of rank r works on item 2 * pair_index + r
+  const int64_t first = (int64_t)(blockIdx.x >> 1) * 2 + rank, stride = (int64_t)(gridDim.x >> 1) * 2;
+  const int kchunks = (p.c_in + 31) / 32;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      if (rank == 0) mbar_expect_tx(wfull, 2 * 3 * L.w_th_bytes);
+      for (int t = 0; t < 3; ++t)
+        for (int c = 0; c < kchunks; ++c)
+          tma_load_2d_pair(smem + L.w_off + t * L.w_th_bytes + c * L.w_chunk_bytes, &tm_w, wfull, c * 32, ((int)rank * 3 + t) * NH);
+      uint32_t pe = 0, used = 0;
+      for (int64_t item = first; item < p.items; item += stride) {
+        const ConvItem it = conv_item(p, item * 2);
+        // the count + 2 chain rows of the item, in order; slots are numbered from the item's first row so that both CTAs of
+        // the pair (different segments) walk the ring identically
+        for (int i = 0; i <= it.count + 1; ++i) {
+          const int row = conv_map(it.r0 + (it.j0 - 1 + i) * p.d, p.H, p.boundary);  // -1 (dirichlet halo): out of range = zeros
+          const int s = i & (kRing - 1);
+          if (used & (1u << s)) {
+            mbar_wait_backoff(&empty[s], (pe >> s) & 1u);
+            pe ^= 1u << s;
+          }
+          used |= 1u << s;
+          uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * L.slot_bytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_3d_pair(dst + c * L.box_bytes, &tm_x, &full[s], c * 32, row, it.b * p.c_in);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      const uint32_t idesc = idesc_tf32(256, N, /*a_mn_major=*/true, /*b_mn_major=*/false);
+      mbar_wait(wfull, 0);
+      int a = 0;
+      uint32_t aph = 0, pf = 0;
+      const uint64_t adesc0 = smem_desc_sw128_atom32(smem_u32(smem + L.ring_off), L.box_bytes, 512);
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.w_off), 0, 1024);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
+      const uint32_t slot16 = L.slot_bytes >> 4, wth16 = L.w_th_bytes >> 4, chunk16 = L.w_chunk_bytes >> 4;
+      const int ks = p.c_in / 8;
+      for (int64_t item = first; item < p.items; item += stride) {
+        const ConvItem it = conv_item(p, item * 2);
+        for (int jj = 0; jj < it.count; ++jj) {
+          const bool last = jj == it.count - 1;
+          mbar_wait(&tempty[a], aph ^ 1);
+          tc_fence_after();
+          const uint32_t dcol = tmem_base + (uint32_t)(a * N);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const int s = (jj + t) & (kRing - 1);  // slot of the item's row jj + t (= chain row j - 1 + t)
+            if (jj == 0 || t == 2) {               // first use of this row
+              mbar_wait(&full[s], (pf >> s) & 1u);
+              pf ^= 1u << s;
+              tc_fence_after();
+            }
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * slot16;
+            const uint32_t b_lo = b_lo0 + (uint32_t)t * wth16;
+            if (elect_one()) {
+              for (int k = 0; k < ks; ++k)
+                mma_tf32_lohi_pair(dcol, a_lo + k * 64, a_hi, b_lo + (k >> 2) * chunk16 + (k & 3) * 2, b_hi, idesc, (t | k) ? 1u : 0u);
+              if (t == 0 || last) mma_commit_pair(&empty[s]);  // v = j-1 is never needed again; at a segment end nothing is
+            }
+            __syncwarp();
+          }
+          if (elect_one()) mma_commit_pair(&tfull[a]);
+          __syncwarp();
+          if (++a == kAcc2) { a = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own rows) =====================
+    // warp (og, q) owns 16 output channels x the 32 columns of TMEM lane quarter q, drained in two passes of 8 channels;
+    // a pass is the one-CTA kernel's unit epilogue (neighbour exchange, 1 KB swizzled piece, own TMA store).
+    const int q = warp & 3;
+    const int og = (warp - 4) >> 2;
+    constexpr int ocnt = kConvOcnt;
+    const int wid = og * 4 + q;
+    const int wq = q * 32 + lane;
+    int a = 0;
+    uint32_t aph = 0, par = 0;
+    const int c0 = conv_map(wq - p.d, p.W, p.boundary), c2 = conv_map(wq + p.d, p.W, p.boundary);
+    const bool use0 = c0 >= 0, use2 = c2 >= 0;
+    const bool in0 = use0 && (c0 >> 5) == q, in2 = use2 && (c2 >> 5) == q;
+    const int l0 = c0 & 31, l2 = c2 & 31;
+    const int d = p.d;
+    const bool dbuf = d <= kMaxDil / 2;
+    const int64_t plane = (int64_t)p.H * p.W;
+    const uint32_t xbs = smem_u32(smem + L.xbuf_off);
+    // where this lane's out-of-warp sources sit in the exchange buffer: a neighbour's slot, the all-zero slot for a dropped
+    // (dirichlet) tap, or -- value unused -- the own slot 0 if the source is inside the warp (it comes by shuffle)
+    const uint32_t zero_slot = xbs + 2 * 16 * 8 * kMaxDil * 4;
+    const uint32_t far0_base = !use0 ? zero_slot
+                                     : xbs + (((0 * 16 + (uint32_t)(og * 4 + (!in0 ? (c0 >> 5) : q))) * kMaxDil +
+                                               (uint32_t)(!in0 ? (c0 & 31) - (32 - d) : 0)) * ocnt) * 4;
+    const uint32_t far2_base = !use2 ? zero_slot
+                                     : xbs + (((1 * 16 + (uint32_t)(og * 4 + (!in2 ? (c2 >> 5) : q))) * kMaxDil +
+                                               (uint32_t)(!in2 ? (c2 & 31) : 0)) * ocnt) * 4;
+    const uint32_t xo_b = dbuf ? (kMaxDil / 2) * (ocnt * 4) : 0u;  // byte offset of the second exchange buffer half
+    const uint32_t xo0_b = use0 ? xo_b : 0u, xo2_b = use2 ? xo_b : 0u;  // (the zero slot has no second half)
+    const uint32_t bias_sa = smem_u32(bias_s);
+    uint32_t xph = 0;
+    for (int64_t item = first; item < p.items; item += stride) {
+      const ConvItem it = conv_item(p, item * 2);
+      const int chb = it.b * p.c_out + og * 2 * ocnt;  // first of this warp's 16 channels
+      for (int jj = 0; jj < it.count; ++jj) {
+        const int h = it.r0 + (it.j0 + jj) * p.d;
+        mbar_wait(&tfull[a], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+          const int cg = og * 2 + ps;  // 8-channel group 0..7: filter half cg >> 2, group cg & 3 inside the half
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N + (cg >> 2) * NH + (cg & 3) * ocnt);
+          // this lane's 8 output elements: pixel (h, wq) of 8 consecutive channel planes; a warp-wide store per channel is one
+          // full 128-byte line, so the pass needs no staging tile, no async-proxy fence and no wait on an earlier TMA store
+          const int64_t off0 = (((int64_t)chb + ps * ocnt) * p.H + h) * p.W + wq;
+          float res[ocnt];
+          if (p.has_residual) {
+#pragma unroll
+            for (int jx = 0; jx < ocnt; ++jx) res[jx] = __ldg(p.res + off0 + (int64_t)jx * plane);
+          }
+          float v0[ocnt], v1[ocnt], v2[ocnt];
+          tmem_ld8(t0, v0);
+          tmem_ld8(t0 + (uint32_t)NOH, v1);
+          tmem_ld8(t0 + (uint32_t)(2 * NOH), v2);
+          tmem_ld_wait();
+          if (ps == 1) {  // last read of this accumulator: hand it back to the leader's MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[a]);
+          }
+#if defined(PDEQX_CONV_DIAG) && PDEQX_CONV_DIAG < 3  // timing experiments only: 1 = no neighbour exchange, 2 = no stores either
+          {
+#if PDEQX_CONV_DIAG == 1
+#pragma unroll
+            for (int jx = 0; jx < ocnt; ++jx) p.y[off0 + (int64_t)jx * plane] = v0[jx] + v1[jx] + v2[jx];
+#else
+            if (v0[0] + v1[1] + v2[2] == 123.456f) p.y[off0] = 0.f;
+#endif
+            par ^= 1;
+            continue;
+          }
+#endif
+          const uint32_t xo = dbuf ? par * (kMaxDil / 2) : 0u;
+          if (lane >= 32 - d) {
+            const uint32_t a0 = xbs + (((0 * 16 + (uint32_t)wid) * kMaxDil + xo + (uint32_t)(lane - (32 - d))) * ocnt) * 4;
+            st_shared_v4(a0, v0);
+            st_shared_v4(a0 + 16, v0 + 4);
+          }
+          if (lane < d) {
+            const uint32_t a2 = xbs + (((1 * 16 + (uint32_t)wid) * kMaxDil + xo + (uint32_t)lane) * ocnt) * 4;
+            st_shared_v4(a2, v2);
+            st_shared_v4(a2 + 16, v2 + 4);
+          }
+          // the edge columns are published on an mbarrier (one arrive per warp) and the wait comes after the work that does
+          // not need them -- in-warp shifts and the centre tap -- so the exchange latency hides behind it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xbar[og * 2 + (int)par]);
+          float bias_r[ocnt], acc[ocnt], s0[ocnt], s2[ocnt];
+          ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4), bias_r);
+          ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4) + 16, bias_r + 4);
+#pragma unroll
+          for (int jx = 0; jx < ocnt; ++jx) {
+            s0[jx] = __shfl_sync(0xffffffffu, v0[jx], l0);
+            s2[jx] = __shfl_sync(0xffffffffu, v2[jx], l2);
+            acc[jx] = v1[jx] + bias_r[jx];
+            if (p.has_residual) acc[jx] += res[jx];
+          }
+          mbar_wait(&xbar[og * 2 + (int)par], (xph >> par) & 1u);
+          xph ^= 1u << par;
+          const uint32_t far0 = far0_base + (par ? xo0_b : 0u), far2 = far2_base + (par ? xo2_b : 0u);
+          float f0[ocnt], f2[ocnt];
+          ld_shared_v4(far0, f0);
+          ld_shared_v4(far0 + 16, f0 + 4);
+          ld_shared_v4(far2, f2);
+          ld_shared_v4(far2 + 16, f2 + 4);
+          if (!dbuf) named_bar_sync(1 + og, 128);
+#pragma unroll
+          for (int jx = 0; jx < ocnt; ++jx) {
+            float r = acc[jx] + (in0 ? s0[jx] : f0[jx]) + (in2 ? s2[jx] : f2[jx]);
+            if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
+            else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
+#if defined(PDEQX_CONV_DIAG) && PDEQX_CONV_DIAG == 3  // timing experiment: full epilogue arithmetic, no stores
+            if (r == 123.456f) p.y[off0] = r;
+#else
+            p.y[off0 + (int64_t)jx * plane] = r;
+#endif
+          }
+          par ^= 1;
+        }
+        if (++a == kAcc2) { a = 0; aph ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // every MMA, remote arrive and TMEM read of the pair is done before either CTA lets go
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<kConvTmemCols>(tmem_base);
   }
 }
 
@@ -806,6 +1086,9 @@ bool tc_conv_available(const ConvGeom& g) {
   return true;
 }
 
+static std::atomic<int64_t> g_pair_launches{0};
+int64_t tc_conv_pair_launches() { return g_pair_launches.load(std::memory_order_relaxed); }
+
 static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, bool flip, const float* bias,
                             const float* residual, int act, float* y, cudaStream_t s) {
   int dev = 0, sms = 148;
@@ -854,9 +1137,49 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   cp.has_residual = residual ? 1 : 0;
   cp.has_bias = bias ? 1 : 0;
   cp.bias = bias;
+  cp.y = y;
+  cp.res = residual;
   cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image * 2;
   tc::ConvSmem L = tc::conv_smem(c_in, c_out, k);
   PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv: shared memory budget exceeded (%u bytes)", L.total);
+  // CTA-pair kernel (cta_group::2, all 64 output channels per unit): needs chains of equal length cut into equal segments
+  // (both CTAs of a pair issue the same schedule) and an even number of items
+  static const bool pair_enabled = [] { const char* e = getenv("PDEQX_CONV_PAIR"); return !(e && e[0] == '0'); }();
+  if (pair_enabled && c_in == 64 && c_out == 64 && H % cp.d == 0 && sms >= 2) {
+    const int chain = H / cp.d, pairs = sms / 2;
+    int best_seg = 0;
+    int64_t best_cost = 0;
+    for (int seg = 4; seg <= 64 && seg <= chain; ++seg) {
+      if (chain % seg) continue;
+      const int64_t items2 = (int64_t)g.batch * cp.d * (chain / seg);
+      if (items2 & 1) continue;
+      const int64_t rounds = ceil_div(items2 / 2, (int64_t)pairs);
+      const int64_t cost = rounds * (seg + 2);  // rows a CTA walks, the two halo rows of every segment included
+      if (!best_seg || cost < best_cost) { best_seg = seg; best_cost = cost; }
+    }
+    if (best_seg) {
+      cp.seg = best_seg;
+      cp.segs_per_image = chain / best_seg;
+      cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image;
+      int grid2 = (int)(cp.items < sms ? cp.items : sms) & ~1;
+#define PDEQX_CONV_PAIR_LAUNCH(A)                                                                                         \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_rows_pair_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    tc::conv_rows_pair_kernel<A><<<grid2, tc::kConvThreads, L.total, s>>>(tm_x, tm_w, tm_y, tm_res, cp, L);               \
+  } while (0)
+      if (act == PDEQX_ACT_RELU) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_RELU);
+      else if (act == PDEQX_ACT_GELU_TANH) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_GELU_TANH);
+      else PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_IDENTITY);
+#undef PDEQX_CONV_PAIR_LAUNCH
+      PDEQX_LAUNCHED();
+      g_pair_launches.fetch_add(1, std::memory_order_relaxed);
+      return PDEQX_OK;
+    }
+  }
   int grid = (int)(cp.items < sms ? cp.items : sms);
   grid &= ~1;  // even: a CTA keeps one channel half (its weights stay resident)
   PDEQX_CHECK_ARG(grid >= 2, "tc_conv: grid too small");

@@ -49,7 +49,10 @@ def test_tf32_conv_fwd_bwd(mode, C, H, d, B):
         assert passes == 0  # C = 32 runs the fp32 path (also under set_precision("tf32"))
     # plain
     ref = oconv.physics_conv(x, w, b, boundary_mode=mode, dilation=d)
+    pair0 = _lib.lib().pdeqx_conv_pair_launches()
     y = conv.apply(dev(x), None)
+    # the CTA-pair kernel (cta_group::2) takes every C = 64 shape whose row chains split into equal segments
+    assert (_lib.lib().pdeqx_conv_pair_launches() > pair0) == (C == 64 and H % d == 0)
     torch.cuda.synchronize()
     assert rel_l2(host(y), ref) <= TOL
     # fused residual + relu epilogue
