@@ -44,10 +44,10 @@ def emit(line):
 WORKLOAD = "ClassicFNO 2D periodic, 256x256 grid, hidden 64, 16 modes/axis, 4 blocks, global batch 64 (BASELINE.json configs[3])"
 GRID, HIDDEN, MODES, BLOCKS, GLOBAL_BATCH = 256, 64, 16, 4, 64
 METRIC = "ClassicFNO 2D 256^2 train samples/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of tc::slab_kernel at B = 64 per GPU, from the `ncu --set full`
-# capture summarised in profiles/r1_block_ncu.md: forward 2.233e9, cotangent pass 3.322e9, data gradient 2.255e9 bytes;
-# the mean over the three uses (as `achieved` averages them). Algorithmic mean: 2.640e9 -> no re-reads.
-SLAB_TRAFFIC_B64 = (2.233e9 + 3.322e9 + 2.255e9) / 3.0
+# dram__bytes_read.sum + dram__bytes_write.sum of tc::slab_kernel at B = 64 per GPU, summed over the 12 launches of one train
+# step (profiles/r1_slab_traffic.csv: forward 6.86 GB, cotangent passes 11.13 GB, data gradients 7.95 GB) and averaged per launch,
+# as `achieved` averages them. Algorithmic mean: 2.199e9 -> no re-reads (part of z is still in L2).
+SLAB_TRAFFIC_B64 = 25.93e9 / 12.0
 
 
 def parse():
@@ -218,6 +218,7 @@ def run_ours(args):
     import pdequinox_b200 as pdeqx
     from pdequinox_b200 import _lib
     from pdequinox_b200.train import TrainStep
+    from pdequinox_b200.conv._spectral_conv import get_plan
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -334,17 +335,29 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     n_pix = GRID * GRID
     # the slab kernel runs three times per block: forward (read x, z; write y), cotangent of the pre-activation (read x, z,
-    # gy; write g) and data gradient (read g, z'; write gx); z = [B,C,H,2m]; tables + bypass weights are negligible
+    # gy; write g) and data gradient (read g, z'; write gx) = 7 full-size tensor passes per block; z = [B,C,H,2m]; tables +
+    # bypass weights are negligible. The folded ends of the network remove passes: the lifted first block never reads its
+    # input (forward, cotangent) nor writes its input gradient; the last block's cotangent is rank one (gy is a single
+    # channel) and, projected, its forward pass writes a single channel.
+    act_code = pdeqx.nn.activation_code(model.blocks[0].activation)
+    lifted = bool(model.blocks[0].lifted_ok(xd))
+    rank1 = bool(L.pdeqx_spectral_block_rank1_ok(get_plan(2, per, HIDDEN, HIDDEN, (GRID, GRID), (MODES, MODES)).handle, 1, act_code))
+    projected = bool(model.blocks[-1].projected_ok(xd))
+    tensor_passes = 7 * BLOCKS - (3 if lifted else 0) - (1 if rank1 else 0) - (1 if projected else 0)
+    slab_launches = 3 * BLOCKS
     small = 4 * (HIDDEN * HIDDEN + HIDDEN + 2 * MODES * GRID)
-    bytes_2 = 4 * per * HIDDEN * (2 * n_pix + GRID * 2 * MODES) + small
-    bytes_3 = 4 * per * HIDDEN * (3 * n_pix + GRID * 2 * MODES) + small
-    slab_bytes = (2 * bytes_2 + bytes_3) / 3.0  # mean over the launches timed (equal numbers of the three variants)
+    one_tensor = 4 * per * HIDDEN * n_pix
+    z_bytes = 4 * per * HIDDEN * GRID * 2 * MODES
+    field = 4 * per * n_pix  # single-channel fields read by the folded variants
+    n_fields = (3 if lifted else 0) + (1 if rank1 else 0) + (1 if projected else 0)
+    slab_bytes = (tensor_passes * one_tensor + n_fields * field) / slab_launches + z_bytes + small  # mean over a step's launches
     roofline = None
     if slab_n.value > 0:
         avg_s = slab_ms.value * 1e-3 / slab_n.value
         achieved = slab_bytes / avg_s / 1e9
         roofline = {"bound": "hbm", "kernel": "tc::slab_kernel, spectral block last stage (c2r DFT + 1x1 bypass + bias + gelu / gelu' / adjoint), "
-                              "mean over its three uses per block",
+                              "mean over its %d launches per step (%d full-size tensor passes: lifting %s, projection %s)"
+                              % (slab_launches, tensor_passes, "folded" if lifted else "separate", "folded" if projected else "separate"),
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_launch": slab_bytes, "avg_launch_us": avg_s * 1e6,
@@ -352,8 +365,8 @@ def run_ours(args):
                     "timed_in": f"{probe_steps} eagerly launched steps after the graph-replayed region (events cannot bracket "
                                 "kernels inside a graph replay); share_of_step is relative to that pass",
                     "traffic": SLAB_TRAFFIC_B64 * per / 64.0,
-                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum at 64 samples per GPU "
-                                      "(profiles/r1_block_ncu.md), scaled by this run's samples per GPU"}
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 12 launches of one step at 64 samples "
+                                      "per GPU (profiles/r1_slab_traffic.csv), scaled by this run's samples per GPU"}
 
     # ---- PhysicsConv roofline (BASELINE.json configs[2] layer: 3x3, 64 -> 64, 128x128, batch 128, periodic) ----
     physics = None
