@@ -937,6 +937,317 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Filter gradient with the column-shifted operands built IN SHARED MEMORY (any dilation, any boundary mode).
+// ------------------------------------------------------------------------------------------
+// The kernel above needs the shifted copies of the gy row as TMA boxes, and a box column that is not 16-byte aligned
+// faults -- so for d % 4 != 0 it reads two pre-shifted tensors that a separate pass had to write (3 extra passes over
+// an activation-sized tensor). Here the gy row is loaded ONCE (raw, double buffered), and thirteen shifter warps
+// write the two shifted copies of every 32-column chunk into a two-stage operand buffer -- with the wrapped / mirrored
+// halo columns of periodic / neumann already folded in -- while the tensor core works on the previous chunk. The centre tap
+// reads the raw row directly. HBM traffic: x and gy once.
+struct WgsSmem {
+  uint32_t raw_off, sh_off, ring_off, slot_bytes, box_bytes, bar_off, total;
+};
+constexpr int kWgsThreads = 512;
+constexpr int kWgsShifters = kWgsThreads / 32 - 3;  // warps 3..15
+
+static WgsSmem wgs_smem(int c) {
+  WgsSmem s{};
+  uint32_t off = 0;
+  s.box_bytes = (uint32_t)c * 128;  // [c rows][32 w]
+  s.raw_off = off;                  // 2 raw gy rows of 4 boxes; the box after a centre box is its (don't-care) upper half
+  off += 2 * 4 * s.box_bytes;
+  s.sh_off = off;                   // 2 stages of [shift tw=0 box][shift tw=2 box]
+  off += 2 * 2 * s.box_bytes;
+  s.ring_off = off;
+  s.slot_bytes = 4 * s.box_bytes;
+  off += kWgRing * s.slot_bytes;
+  s.bar_off = off;
+  off += 1024;
+  s.total = off + 1024;
+  return s;
+}
+
+// element (row r, column w) of a gy row held as four SWIZZLE_128B boxes [c rows][32 w]
+__device__ __forceinline__ uint32_t wgs_elem_addr(uint32_t row_base, uint32_t box_bytes, int r, int w) {
+  return row_base + (uint32_t)(w >> 5) * box_bytes + (uint32_t)r * 128 + ((((uint32_t)(w & 31) >> 2) ^ ((uint32_t)r & 7)) << 4) +
+         ((uint32_t)w & 3) * 4;
+}
+
+__global__ void __launch_bounds__(kWgsThreads, 1)
+conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_x, WgParams p, WgsSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* rawfull = bars;       // [2] raw gy rows
+  uint64_t* rawempty = bars + 2;  // [2]
+  uint64_t* shfull = bars + 4;    // [2] shifted-operand stages (one arrive per shifter warp)
+  uint64_t* shempty = bars + 6;   // [2]
+  uint64_t* xfull = bars + 8;     // [kWgRing]
+  uint64_t* xempty = bars + 12;   // [kWgRing]
+  uint64_t* done = bars + 16;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 17);
+  uint32_t* inited_s = (uint32_t*)(bars + 18);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.c, W = p.W, d = p.d;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_gy);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&rawfull[i], 1);
+      mbar_init(&rawempty[i], 1);
+      mbar_init(&shfull[i], kWgsShifters);
+      mbar_init(&shempty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+    }
+    mbar_init(done, 1);
+    *inited_s = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  // everything a don't-care operand half can reach must at least be finite
+  for (uint32_t i = threadIdx.x; i < (L.ring_off - L.raw_off) / 4; i += blockDim.x) ((float*)(smem + L.raw_off))[i] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const bool zeros = p.boundary == PDEQX_PAD_ZEROS;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t pe = 0, used = 0, rpe = 0, rused = 0;
+      int rb = 0;
+      for (int64_t item = first; item < p.items; item += stride) {
+        const WgItem it = wg_item(p, item);
+        int v_next = it.j0 - 1;  // next chain row of x to fetch
+        for (int jj = 0; jj < it.count; ++jj) {
+          const int j = it.j0 + jj;
+          const int h = it.r0 + j * p.d;
+          const int v_hi = (j + 2 <= it.j0 + it.count) ? j + 2 : it.j0 + it.count;
+          for (; v_next <= v_hi; ++v_next) {
+            const int row = conv_map(it.r0 + v_next * p.d, p.H, p.boundary);
+            if (row < 0) continue;
+            const int s = (v_next + 1) & (kWgRing - 1);
+            if (used & (1u << s)) {
+              mbar_wait_backoff(&xempty[s], (pe >> s) & 1u);
+              pe ^= 1u << s;
+            }
+            used |= 1u << s;
+            uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
+            mbar_expect_tx(&xfull[s], L.slot_bytes);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_x, &xfull[s], c * 32, row, it.b * C);
+          }
+          // the raw gy row of this unit
+          if (rused & (1u << rb)) {
+            mbar_wait_backoff(&rawempty[rb], (rpe >> rb) & 1u);
+            rpe ^= 1u << rb;
+          }
+          rused |= 1u << rb;
+          uint8_t* dst = smem + L.raw_off + (size_t)rb * 4 * L.box_bytes;
+          mbar_expect_tx(&rawfull[rb], 4 * L.box_bytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_gy, &rawfull[rb], c * 32, h, it.b * C);
+          rb ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
+    const uint32_t idesc = idesc_tf32(128, C, false, false);
+    const uint64_t adesc0 = smem_desc_sw128(smem_u32(smem + L.sh_off), 0, 1024);
+    const uint64_t rdesc0 = smem_desc_sw128(smem_u32(smem + L.raw_off), 0, 1024);
+    const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.ring_off), 0, 1024);
+    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)adesc0, r_lo0 = (uint32_t)rdesc0, b_lo0 = (uint32_t)bdesc0;
+    const uint32_t box16 = L.box_bytes >> 4, slot16 = L.slot_bytes >> 4;
+    uint32_t pf = 0, spf = 0, rpf = 0, inited = 0;
+    int st = 0, rb = 0;
+    for (int64_t item = first; item < p.items; item += stride) {
+      const WgItem it = wg_item(p, item);
+      for (int jj = 0; jj < it.count; ++jj) {
+        const int j = it.j0 + jj;
+        const bool last = jj == it.count - 1;
+        const int h = it.r0 + j * p.d;
+        bool valid[3];
+        valid[0] = !(zeros && h - p.d < 0);
+        valid[1] = true;
+        valid[2] = !(zeros && h + p.d >= p.H);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          if (!valid[t]) continue;
+          if (jj == 0 || t == 2) {  // first use of chain row v = j - 1 + t
+            const int s = (j + t) & (kWgRing - 1);
+            mbar_wait(&xfull[s], (pf >> s) & 1u);
+            pf ^= 1u << s;
+          }
+        }
+        mbar_wait(&rawfull[rb], (rpf >> rb) & 1u);
+        rpf ^= 1u << rb;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(&shfull[st], (spf >> st) & 1u);
+          spf ^= 1u << st;
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              if (!valid[t]) continue;
+              const int s = (j + t) & (kWgRing - 1);
+              const uint32_t b_lo = b_lo0 + (uint32_t)s * slot16 + (uint32_t)c * box16;
+              const uint32_t a1 = a_lo0 + (uint32_t)st * 2 * box16;               // [shift tw=0 ; shift tw=2]
+              const uint32_t a2 = r_lo0 + (uint32_t)(rb * 4 + c) * box16;         // [centre ; don't-care]
+              const uint32_t d1 = tmem_base + (uint32_t)(t * C), d2 = tmem_base + (uint32_t)((3 + t) * C);
+              const uint32_t acc = (inited >> t) & 1u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_tf32_lohi(d1, a1 + k * 2, a_hi, b_lo + k * 2, b_hi, idesc, (c | k) ? 1u : acc);
+                mma_tf32_lohi(d2, a2 + k * 2, a_hi, b_lo + k * 2, b_hi, idesc, (c | k) ? 1u : acc);
+              }
+            }
+            mma_commit(&shempty[st]);
+            if (c == 3) {
+              mma_commit(&rawempty[rb]);  // (the shifters are done with a raw row before its last chunk can be consumed)
+#pragma unroll
+              for (int t = 0; t < 3; ++t)
+                if (valid[t] && (t == 0 || last)) mma_commit(&xempty[(j + t) & (kWgRing - 1)]);
+            }
+          }
+          __syncwarp();
+          st ^= 1;
+        }
+        rb ^= 1;
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (valid[t]) inited |= 1u << t;
+      }
+    }
+    if (elect_one()) {
+      *inited_s = inited;
+      mma_commit(done);
+    }
+    __syncwarp();
+  } else if (warp >= 3) {
+    // ===================== shifters: raw gy row -> [shift tw=0 | shift tw=2] operand chunks =====================
+    //   A_0[o, w'] = gy[o, w' + d] (+ the halo columns that reach x column w' through the boundary map), A_2[o, w'] = gy[o, w' - d] (...)
+    // -- exactly what conv_shift_rows_kernel writes to HBM for the kernel above. One thread = one 16-byte unit (4 columns) of one
+    // channel row; interior units are two 128-bit loads + a funnel, the d columns next to each edge take the scalar path.
+    const int tid = (warp - 3) * 32 + lane;
+    const uint32_t raw0 = smem_u32(smem + L.raw_off), sh0 = smem_u32(smem + L.sh_off);
+    uint32_t rpf = 0, spe = 0, sused = 0;
+    int st = 0, rb = 0;
+    const int dm = d & 3;
+    for (int64_t item = first; item < p.items; item += stride) {
+      const WgItem it = wg_item(p, item);
+      for (int jj = 0; jj < it.count; ++jj) {
+        mbar_wait(&rawfull[rb], (rpf >> rb) & 1u);
+        rpf ^= 1u << rb;
+        const uint32_t rbase = raw0 + (uint32_t)rb * 4 * L.box_bytes;
+        for (int c = 0; c < 4; ++c) {
+          if (sused & (1u << st)) {
+            mbar_wait(&shempty[st], (spe >> st) & 1u);
+            spe ^= 1u << st;
+          }
+          sused |= 1u << st;
+          const uint32_t sbase = sh0 + (uint32_t)st * 2 * L.box_bytes;
+          // units of this chunk: 2 taps x C rows x 8 sixteen-byte units
+#ifndef PDEQX_WG_DIAG  // (timing experiment: no shifter work)
+          for (int u = tid; u < 2 * C * 8; u += kWgsShifters * 32) {
+            const int tap = u >> 9;  // (C = 64) 0: tw = 0 (source column w' + d), 1: tw = 2 (source column w' - d); warp-uniform
+            const int r = (u >> 3) & 63, cu = u & 7;
+            const int w0 = c * 32 + cu * 4;  // first of the unit's four columns w'
+            const int sh = tap == 0 ? d : -d;
+            float o4[4];
+            const int src0 = w0 + sh;
+            // periodic: the operand is the circular shift of the row (direct part + wrapped halo), every unit takes the fast path;
+            // dirichlet / neumann: units whose sources leave the row or that receive mirrored halo columns take the scalar path
+            const bool wrap = p.boundary == PDEQX_PAD_WRAP;
+            const bool interior = wrap || (src0 >= 0 && src0 + 3 < W && (zeros || (w0 > d && w0 + 3 < W - 1 - d)));
+            if (interior) {
+              // source columns src0 .. src0 + 3 = units ub and ub + 1 of the row's 32, offset dm (tap 0) or 4 - dm (tap 2)
+              const int off = tap == 0 ? dm : ((4 - dm) & 3);
+              const int ub = ((src0 - off) >> 2) & 31;
+              float lo[4], hi[4];
+              ld_shared_v4(wgs_elem_addr(rbase, L.box_bytes, r, ub * 4), lo);
+              if (off) {
+                ld_shared_v4(wgs_elem_addr(rbase, L.box_bytes, r, ((ub + 1) & 31) * 4), hi);
+                if (off == 1) { o4[0] = lo[1]; o4[1] = lo[2]; o4[2] = lo[3]; o4[3] = hi[0]; }
+                else if (off == 2) { o4[0] = lo[2]; o4[1] = lo[3]; o4[2] = hi[0]; o4[3] = hi[1]; }
+                else { o4[0] = lo[3]; o4[1] = hi[0]; o4[2] = hi[1]; o4[3] = hi[2]; }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o4[i] = lo[i];
+              }
+            } else {
+              // zero-extended direct source + (neumann) the one mirrored halo column that maps onto x column w:
+              //   tap 0: conv_map(e - d) = d - e = w  ->  gy[d - w] for 1 <= w <= d;   tap 2: conv_map(W + e) = W - 2 - e = w  ->
+              //   gy[2W - 2 - d - w] for W - 1 - d <= w <= W - 2   (what conv_shift_rows_kernel's search loop finds)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int w = w0 + i, src = w + sh;
+                float a = (src >= 0 && src < W) ? ld_shared_f32(wgs_elem_addr(rbase, L.box_bytes, r, src)) : 0.f;
+                if (!zeros) {
+                  const int hs = tap == 0 ? d - w : 2 * W - 2 - d - w;
+                  const bool has = tap == 0 ? (w >= 1 && w <= d) : (w >= W - 1 - d && w <= W - 2);
+                  if (has) a += ld_shared_f32(wgs_elem_addr(rbase, L.box_bytes, r, hs));
+                }
+                o4[i] = a;
+              }
+            }
+            st_shared_v4(sbase + (uint32_t)tap * L.box_bytes + (uint32_t)r * 128 + (((uint32_t)cu ^ ((uint32_t)r & 7)) << 4), o4);
+          }
+#endif
+          fence_proxy_async();  // the tensor core reads what this thread wrote through the async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&shfull[st]);
+          st ^= 1;
+        }
+        rb ^= 1;
+      }
+    }
+    if (warp >= 4 && warp < 8) {
+      // ===================== flush: TMEM -> scratch[cta][tw][th][i][o] =====================
+      const int q = warp & 3;
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const uint32_t inited = *(volatile uint32_t*)inited_s;
+      float* out = p.scratch + (size_t)blockIdx.x * 9 * C * C;
+      const int o = (q & 1) * 32 + lane;
+      for (int g = 0; g < 2; ++g) {
+        if (g == 1 && q >= 2) break;
+        const int tw = g == 0 ? (q < 2 ? 0 : 2) : 1;
+        for (int t = 0; t < 3; ++t) {
+          for (int c0 = 0; c0 < C; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 3 + t) * C + c0), v);
+            tmem_ld_wait();
+            if (o < C) {
+#pragma unroll
+              for (int jx = 0; jx < 16; ++jx)
+                out[((size_t)(tw * 3 + t) * C + c0 + jx) * C + o] = ((inited >> t) & 1u) ? v[jx] : 0.f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Column-shifted copies of gy for the two outer column taps when d is not a multiple of 4 (an unaligned TMA box column
 // faults): A_tw[.., w'] = sum over the output columns w whose tap reads x column w' = colmap(w + s), s = (tw - 1) d:
 //   the direct one, w = w' - s, plus -- periodic / neumann -- the columns that reach w' through the wrapped / mirrored halo.
@@ -1237,6 +1548,39 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
   if (!g_wg_scratch[dev]) PDEQX_CUDA(cudaMalloc((void**)&g_wg_scratch[dev], sizeof(float) * 160 * 9 * 64 * 64));
   PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)gy & 15) == 0, "tc_conv: tensors must be 16-byte aligned");
   CUtensorMap tm_gy, tm_gy0, tm_gy2, tm_x;
+  static const bool smem_shift = [] { const char* e = getenv("PDEQX_WG_SMEM_SHIFT"); return !(e && e[0] == '0'); }();
+  if (smem_shift && C == 64) {
+    // the shifted operands (halo folded in) are built in shared memory by the kernel itself: x and gy are read once
+    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * C};
+    uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)C};
+    PDEQX_TRY(tc::make_tensor_map(&tm_gy, gy, 3, dims, str, box, tc::TM_SW128));
+    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128));
+    tc::WgParams wp{};
+    wp.H = H; wp.W = W; wp.c = C; wp.d = d; wp.boundary = g.boundary;
+    const int max_chain = (int)ceil_div(H, d);
+    wp.seg = max_chain < 32 ? max_chain : 32;
+    wp.segs_per_chain = (int)ceil_div(max_chain, wp.seg);
+    wp.items = (int64_t)g.batch * d * wp.segs_per_chain;
+    wp.scratch = g_wg_scratch[dev];
+    tc::WgsSmem L = tc::wgs_smem(C);
+    PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
+    const int grid = (int)(wp.items < sms ? wp.items : sms);
+    static bool attr2 = false;
+    if (!attr2) {
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr2 = true;
+    }
+    tc::conv_wgrad_shift_kernel<<<grid, tc::kWgsThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
+    PDEQX_LAUNCHED();
+    tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C);
+    PDEQX_LAUNCHED();
+    if (gb) {
+      tc::conv_bias_grad_kernel<<<g.batch * C, 256, 0, s>>>(gy, gb, C, (int64_t)H * W);
+      PDEQX_LAUNCHED();
+    }
+    return PDEQX_OK;
+  }
   const bool preshift = (d % 4) != 0;
   const size_t n_act = (size_t)g.batch * C * H * W;
   if (preshift) {  // TMA box columns must be 16-byte aligned: materialise the two shifted copies once
