@@ -186,7 +186,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int PT, int RT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
+// NS = cp.async stages: small batches (RT <= 2: a few samples per GPU) have almost no math per K chunk, so the kernel is a
+// stream over the weights and needs more chunks in flight than the two that suffice when the FFMA work covers the loads
+template <int PT, int RT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B, int NS = (RT == 1 ? 4 : (RT == 2 ? 3 : 2))>
 __global__ void __launch_bounds__(256, 2)
 mode_gemm_tiled_kernel(TiledArgs t) {
   constexpr int NQ = 32 / PT;   // n-quads per warp-row group ... threads = PT * 8 * NQ
@@ -235,16 +237,17 @@ mode_gemm_tiled_kernel(TiledArgs t) {
   };
 
   const int nchunks = valid ? (t.K + TM_KC - 1) / TM_KC : 0;  // padding tile: interleaved outputs get zeros, planar ones nothing
-  if (nchunks > 0) issue(0, 0);
+  // NS - 1 chunks in flight ahead of the math; one commit group per iteration (possibly empty) keeps the wait count constant
+  for (int c = 0; c < NS - 1; ++c) {
+    if (c < nchunks) issue(c * TM_KC, c);
+    else cp_async_commit();
+  }
   for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) {
-      issue((c + 1) * TM_KC, (c + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    if (c + NS - 1 < nchunks) issue((c + NS - 1) * TM_KC, (c + NS - 1) % NS);
+    else cp_async_commit();
+    cp_async_wait<NS - 1>();
     __syncthreads();
-    const float2* As = tile_smem + (size_t)(c & 1) * (A_ELEMS + B_ELEMS);
+    const float2* As = tile_smem + (size_t)(c % NS) * (A_ELEMS + B_ELEMS);
     const float2* Bs = As + A_ELEMS;
 #pragma unroll
     for (int k = 0; k < TM_KC; ++k) {
@@ -296,7 +299,7 @@ static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
   if (grid.y > 65535 || grid.z > 65535) return false;
 #define PDEQX_MODE_GEMM(RT_)                                                                                            \
   do {                                                                                                                 \
-    const size_t smem = (size_t)2 * TM_KC * (8 * RT_ + nt) * PT * sizeof(float2);                                      \
+    const size_t smem = (size_t)(RT_ == 1 ? 4 : (RT_ == 2 ? 3 : 2)) * TM_KC * (8 * RT_ + nt) * PT * sizeof(float2);    \
     static bool attr = false;                                                                                          \
     if (!attr) {                                                                                                       \
       cudaFuncSetAttribute(mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B>,                                \
@@ -318,6 +321,9 @@ static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
 template <bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 static bool launch_tiled(const TiledArgs& t, cudaStream_t s) {
   const int mD = t.mm.m[t.mm.D - 1], nD = t.mm.nd[t.mm.D - 1];
+  // few rows (a small per-GPU batch): the kernel streams the weights, so 16 consecutive modes per tile (64-byte runs of a
+  // weight plane instead of 32-byte ones) matter more than the column reuse of the wider tile
+  if (mD % 16 == 0 && nD % 16 == 0 && t.M <= 16) return launch_tiled_pt<16, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
   if (mD % 8 == 0 && nD % 8 == 0) return launch_tiled_pt<8, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
   if (mD % 4 == 0 && nD % 4 == 0) return launch_tiled_pt<4, B_PLANAR, C_PLANAR, CONJ_B>(t, s);
   return false;
