@@ -879,16 +879,24 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
       mbar_wait(done, 0);
       tc_fence_after();
       const int o = q * 32 + lane;
+      const bool vec_ok = (p.c_in & 3) == 0 && ((uintptr_t)p.gw & 15) == 0;
       for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
         if (o < p.c_out) {
+          if (c0 + 16 <= p.c_in && vec_ok) {
+            // 128-bit reductions: 148 CTAs add into the same c_out x c_in words, a quarter of the L2 atomic operations
+            float4* dst = (float4*)(p.gw + (int64_t)o * p.c_in + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int i = c0 + j;
-            if (i < p.c_in) atomicAdd(p.gw + (int64_t)o * p.c_in + i, v[j]);
-            else if (i == p.c_in && p.gb) atomicAdd(p.gb + o, v[j]);
+            for (int j = 0; j < 4; ++j) atomicAdd(dst + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int i = c0 + j;
+              if (i < p.c_in) atomicAdd(p.gw + (int64_t)o * p.c_in + i, v[j]);
+              else if (i == p.c_in && p.gb) atomicAdd(p.gb + o, v[j]);
+            }
           }
         }
       }
