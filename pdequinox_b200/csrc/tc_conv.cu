@@ -1277,8 +1277,15 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, floa
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [tw][th][i][o]
   const int total = 9 * C * C;
   if (idx >= total) return;
-  float acc = 0.f;
-  for (int s = 0; s < nslabs; ++s) acc += scratch[(size_t)s * total + idx];
+  // eight independent partial sums: the 148 slab reads of a thread are otherwise one latency-bound dependent chain
+  float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int s = 0;
+  for (; s + 8 <= nslabs; s += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[j] += __ldg(scratch + (size_t)(s + j) * total + idx);
+  }
+  for (; s < nslabs; ++s) part[0] += __ldg(scratch + (size_t)s * total + idx);
+  const float acc = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
   const int o = idx % C;
   int r = idx / C;
   const int i = r % C;
