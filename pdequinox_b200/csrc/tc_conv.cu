@@ -624,11 +624,18 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           mbar_wait(&xbar[og * 2 + (int)par], (xph >> par) & 1u);
           xph ^= 1u << par;
           const uint32_t far0 = far0_base + (par ? xo0_b : 0u), far2 = far2_base + (par ? xo2_b : 0u);
+          // only the d lanes next to a warp edge (and dropped taps: the zero slot) read the exchange buffer: the shared-memory
+          // pipe is shared with the tensor core's operand fetch, which is what bounds this kernel
           float f0[ocnt], f2[ocnt];
-          ld_shared_v4(far0, f0);
-          ld_shared_v4(far0 + 16, f0 + 4);
-          ld_shared_v4(far2, f2);
-          ld_shared_v4(far2 + 16, f2 + 4);
+          if (!in0) {
+            ld_shared_v4(far0, f0);
+            ld_shared_v4(far0 + 16, f0 + 4);
+          }
+          if (!in2) {
+            ld_shared_v4(far2, f2);
+            ld_shared_v4(far2 + 16, f2 + 4);
+          }
+          __syncwarp();
           if (!dbuf) named_bar_sync(1 + og, 128);
 #pragma unroll
           for (int jx = 0; jx < ocnt; ++jx) {
