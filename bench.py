@@ -394,9 +394,9 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         workers = args.cpu_sample if args.cpu_sample > 0 else cpu_workers()
-        rate, dt, cores = cpu_train_step_rate(workers, 2, 1)
+        rate, dt, cores = cpu_train_step_rate(workers, 5, 1)  # ~12 s of CPU work on a 16-core host
         cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"{workers} of the {args.global_batch} samples per step (one per host thread), 2 timed steps "
+               "sample": f"{workers} of the {args.global_batch} samples per step (one per host thread), 5 timed steps "
                          f"({dt:.1f} s each); NumPy port of the reference train step (jax/equinox not installable here)"}
 
     line = {
