@@ -46,3 +46,8 @@ def normal(key, shape):
 
 def uniform(key, shape, minval=0.0, maxval=1.0):
     return _as_key(key).generator().uniform(minval, maxval, shape).astype(np.float32)
+
+
+def permutation(key, n: int):
+    """A random permutation of range(n) (the reference shuffles an epoch with jax.random.permutation, _utils.py:110)."""
+    return _as_key(key).generator().permutation(int(n))
