@@ -344,6 +344,33 @@ def dilated_block_any(x, p, prefix, boundary_mode, activation, D, rates=(1, 2, 4
     return h + x
 
 
+def modern_block_any(x, p, prefix, boundary_mode, activation, D):
+    """ModernResBlock (_modern_res_block.py:133-140): pre-activation ordering, norm -> act -> conv twice, plus the bypass
+    (1x1 conv of the normalised input when the channel counts differ, else the identity)."""
+    act = ACTIVATIONS[activation][0]
+    h = oconv.physics_conv(act(_norm(x, p, prefix + "norm_1.", D)), p[prefix + "conv_1.weight"], p.get(prefix + "conv_1.bias"),
+                           boundary_mode=boundary_mode)
+    h = oconv.physics_conv(act(_norm(h, p, prefix + "norm_2.", D)), p[prefix + "conv_2.weight"], p.get(prefix + "conv_2.bias"),
+                           boundary_mode=boundary_mode)
+    skip = x
+    if prefix + "bypass_conv.weight" in p:
+        skip = oconv.pointwise_conv(_norm(x, p, prefix + "bypass_norm.", D), p[prefix + "bypass_conv.weight"],
+                                    p.get(prefix + "bypass_conv.bias"))
+    return h + skip
+
+
+def conv_net_forward(p, x, boundary_mode, activation="relu", final_activation="identity"):
+    """ConvNet.__call__ (_conv_net.py:111-114): activation after every layer but the last, final_activation after it."""
+    n = 0
+    while f"layers.{n}.weight" in p:
+        n += 1
+    h = x
+    for j in range(n):
+        h = oconv.physics_conv(h, p[f"layers.{j}.weight"], p.get(f"layers.{j}.bias"), boundary_mode=boundary_mode)
+        h = ACTIVATIONS[activation if j < n - 1 else final_activation][0](h)
+    return h
+
+
 def double_conv_block(x, p, prefix, boundary_mode, activation, D):
     """ClassicDoubleConvBlock (_classic_double_conv_block.py:87-90)."""
     act = ACTIVATIONS[activation][0]

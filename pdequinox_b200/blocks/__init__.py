@@ -6,8 +6,10 @@ from ._dilated_res_block import DilatedResBlock, DilatedResBlockFactory
 from ._linear_channel_adjust_block import LinearChannelAdjustBlock, LinearChannelAdjustBlockFactory
 from ._linear_conv_down_block import LinearConvDownBlock, LinearConvDownBlockFactory
 from ._linear_conv_up_block import LinearConvUpBlock, LinearConvUpBlockFactory
+from ._modern_res_block import ModernResBlock, ModernResBlockFactory
 
 __all__ = ["Block", "BlockFactory", "ClassicDoubleConvBlock", "ClassicDoubleConvBlockFactory", "ClassicResBlock",
            "ClassicResBlockFactory", "ClassicSpectralBlock", "ClassicSpectralBlockFactory", "DilatedResBlock",
            "DilatedResBlockFactory", "LinearChannelAdjustBlock", "LinearChannelAdjustBlockFactory",
-           "LinearConvDownBlock", "LinearConvDownBlockFactory", "LinearConvUpBlock", "LinearConvUpBlockFactory"]
+           "LinearConvDownBlock", "LinearConvDownBlockFactory", "LinearConvUpBlock", "LinearConvUpBlockFactory",
+           "ModernResBlock", "ModernResBlockFactory"]

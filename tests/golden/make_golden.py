@@ -184,10 +184,30 @@ record("arch_unet_1d_readme", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=
 kw = dict(num_spatial_dims=1, in_channels=1, out_channels=1, hidden_channels=4, num_levels=1, use_norm=False, boundary_mode="dirichlet")
 record("arch_unet_1d_nonorm", "ClassicUNet", kw, ref.arch.ClassicUNet(**kw, key=key), rng.standard_normal((1, 16)))
 
+# ---- the pre-activation ResNet and the plain ConvNet (appended: earlier random streams unchanged) ----
+for mode in ("periodic", "dirichlet", "neumann"):
+    for use_norm in (False, True):
+        kw = dict(num_spatial_dims=2, in_channels=4, out_channels=4, boundary_mode=mode, use_norm=use_norm)
+        record(f"block_modern_{mode}_{int(use_norm)}", "ModernResBlock", kw, ref.blocks.ModernResBlock(**kw, key=key),
+               rng.standard_normal((4, 9, 10)), {"activation": "relu"})
+    kw = dict(num_spatial_dims=2, in_channels=1, out_channels=1, hidden_channels=6, num_blocks=2, boundary_mode=mode)
+    record(f"arch_modern_{mode}", "ModernResNet", kw, ref.arch.ModernResNet(**kw, key=key), rng.standard_normal((1, 12, 10)))
+    kw = dict(num_spatial_dims=2, in_channels=2, out_channels=1, hidden_channels=5, depth=3, boundary_mode=mode)
+    record(f"arch_convnet_{mode}", "ConvNet", kw, ref.arch.ConvNet(**kw, key=key), rng.standard_normal((2, 11, 9)))
+for use_norm in (False, True):
+    kw = dict(num_spatial_dims=1, in_channels=3, out_channels=5, boundary_mode="periodic", use_norm=use_norm)
+    record(f"block_modern_in_ne_out_{int(use_norm)}", "ModernResBlock", kw, ref.blocks.ModernResBlock(**kw, key=key),
+           rng.standard_normal((3, 12)), {"activation": "relu"})
+kw = dict(num_spatial_dims=1, in_channels=1, out_channels=2, depth=0, boundary_mode="dirichlet")
+record("arch_convnet_depth0", "ConvNet", kw, ref.arch.ConvNet(**kw, key=key), rng.standard_normal((1, 16)))
+kw = dict(num_spatial_dims=3, in_channels=1, out_channels=1, hidden_channels=3, depth=2, boundary_mode="periodic")
+record("arch_convnet_3d", "ConvNet", kw, ref.arch.ConvNet(**kw, key=key), rng.standard_normal((1, 6, 5, 7)))
+
 # ---- parameter counts computed by the reference's own count_parameters ----
 counts = {}
 for nm, ctor in [("ClassicFNO", ref.arch.ClassicFNO), ("ClassicResNet", ref.arch.ClassicResNet),
-                 ("DilatedResNet", ref.arch.DilatedResNet), ("ClassicUNet", ref.arch.ClassicUNet)]:
+                 ("DilatedResNet", ref.arch.DilatedResNet), ("ClassicUNet", ref.arch.ClassicUNet),
+                 ("ModernResNet", ref.arch.ModernResNet), ("ConvNet", ref.arch.ConvNet)]:
     for D in (1, 2, 3):
         counts[f"{nm}_{D}d"] = int(ref.count_parameters(ctor(D, 1, 1, key=key)))
 counts["ClassicFNO_2d_h64_m16"] = int(ref.count_parameters(ref.arch.ClassicFNO(2, 1, 1, hidden_channels=64, num_modes=16, key=key)))

@@ -59,6 +59,14 @@ def oracle_eval(case, x, p):
         D = kw["num_spatial_dims"]
         y = onn.sequential_forward(p, xb, lambda h, pre: onn.dilated_block_any(h, p, pre, kw["boundary_mode"], "relu", D),
                                    kw.get("num_blocks", 2))
+    elif kind == "ModernResBlock":
+        y = onn.modern_block_any(xb, p, "", kw["boundary_mode"], case["activation"], kw["num_spatial_dims"])
+    elif kind == "ModernResNet":
+        D = kw["num_spatial_dims"]
+        y = onn.sequential_forward(p, xb, lambda h, pre: onn.modern_block_any(h, p, pre, kw["boundary_mode"], "relu", D),
+                                   kw.get("num_blocks", 6))
+    elif kind == "ConvNet":
+        y = onn.conv_net_forward(p, xb, kw["boundary_mode"])
     elif kind == "ClassicUNet":
         y = onn.unet_forward(p, xb, kw["boundary_mode"], kw.get("num_levels", 4))
     elif kind == "ClassicDoubleConvBlock":

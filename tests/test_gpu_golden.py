@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 SUPPORTED = {"SpectralConv", "SpectralConvRaw", "PhysicsConv", "PointwiseLinearConv", "ClassicSpectralBlock",
              "ClassicResBlock", "DilatedResBlock", "ClassicFNO", "ClassicResNet", "DilatedResNet", "PhysicsConvTranspose",
-             "ClassicDoubleConvBlock", "LinearConvDownBlock", "LinearConvUpBlock", "ClassicUNet"}
+             "ClassicDoubleConvBlock", "LinearConvDownBlock", "LinearConvUpBlock", "ClassicUNet", "ModernResBlock",
+             "ModernResNet", "ConvNet"}
 CASES = [c for c in gc.CASES if c["kind"] in SUPPORTED]
 
 
@@ -30,7 +31,8 @@ def build(case, p):
            "ClassicResNet": pdeqx.arch.ClassicResNet, "DilatedResNet": pdeqx.arch.DilatedResNet,
            "PhysicsConvTranspose": pdeqx.PhysicsConvTranspose, "ClassicDoubleConvBlock": pdeqx.blocks.ClassicDoubleConvBlock,
            "LinearConvDownBlock": pdeqx.blocks.LinearConvDownBlock, "LinearConvUpBlock": pdeqx.blocks.LinearConvUpBlock,
-           "ClassicUNet": pdeqx.arch.ClassicUNet}[kind]
+           "ClassicUNet": pdeqx.arch.ClassicUNet, "ModernResBlock": pdeqx.blocks.ModernResBlock,
+           "ModernResNet": pdeqx.arch.ModernResNet, "ConvNet": pdeqx.arch.ConvNet}[kind]
     if isinstance(kw.get("kernel_size"), list):
         kw["kernel_size"] = tuple(kw["kernel_size"])
     for name in ("stride", "output_padding"):
