@@ -408,3 +408,27 @@ def unet_forward(p, x, boundary_mode, num_levels, activation="relu"):
         h = np.concatenate((skip, h), axis=lead)
         h = double_conv_block(h, p, f"right_arc_blocks.{i}.0.", boundary_mode, activation, D)
     return oconv.pointwise_conv(h, p["projection.weight"], p.get("projection.bias"))
+
+
+def modern_unet_forward(p, x, boundary_mode, num_levels, num_blocks=2, activation="relu"):
+    """Hierarchical.__call__ (_hierarchical.py:251-284) with ModernUNet's factories (_modern_u_net.py:78-98): pre-activation
+    ResNet blocks as lifting and arcs (num_blocks per level and arc), stride-2 conv down, transposed-conv up,
+    concat((skip, x)), 1x1 projection."""
+    D = p["projection.weight"].ndim - 2
+    lead = x.ndim - D - 1
+    h = modern_block_any(x, p, "lifting.", boundary_mode, activation, D)
+    skips = []
+    for i in range(num_levels):
+        skips.append(h)
+        h = oconv.physics_conv(h, p[f"down_sampling_blocks.{i}.weight"], p.get(f"down_sampling_blocks.{i}.bias"),
+                               boundary_mode=boundary_mode, stride=2)
+        for j in range(num_blocks):
+            h = modern_block_any(h, p, f"left_arc_blocks.{i}.{j}.", boundary_mode, activation, D)
+    for i in reversed(range(num_levels)):
+        skip = skips.pop()
+        h = oconv.physics_conv_transpose(h, p[f"up_sampling_blocks.{i}.weight"], p.get(f"up_sampling_blocks.{i}.bias"),
+                                         boundary_mode=boundary_mode, stride=2, output_padding=1)
+        h = np.concatenate((skip, h), axis=lead)
+        for j in range(num_blocks):
+            h = modern_block_any(h, p, f"right_arc_blocks.{i}.{j}.", boundary_mode, activation, D)
+    return oconv.pointwise_conv(h, p["projection.weight"], p.get("projection.bias"))

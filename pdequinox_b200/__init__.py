@@ -8,7 +8,8 @@ from ._module import (count_parameters, get_precision, set_precision, tree_leave
 from ._hierarchical import Hierarchical  # noqa: F401
 from ._sequential import Sequential  # noqa: F401
 from ._utils import cycling_dataloader, dataloader, sum_receptive_fields  # noqa: F401
-from .arch import ClassicFNO, ClassicResNet, ClassicUNet, ConvNet, DilatedResNet, ModernResNet  # noqa: F401
+from .arch import (ClassicFNO, ClassicResNet, ClassicUNet, ConvNet, DilatedResNet, ModernResNet,  # noqa: F401
+                   ModernUNet)
 from .blocks import *  # noqa: F401,F403
 from .conv import (MorePaddingConv, MorePaddingConvTranspose, PhysicsConv, PhysicsConvTranspose,  # noqa: F401
                    PointwiseLinearConv, SpectralConv)

@@ -203,11 +203,21 @@ record("arch_convnet_depth0", "ConvNet", kw, ref.arch.ConvNet(**kw, key=key), rn
 kw = dict(num_spatial_dims=3, in_channels=1, out_channels=1, hidden_channels=3, depth=2, boundary_mode="periodic")
 record("arch_convnet_3d", "ConvNet", kw, ref.arch.ConvNet(**kw, key=key), rng.standard_normal((1, 6, 5, 7)))
 
+for mode in ("periodic", "dirichlet", "neumann"):
+    kw = dict(num_spatial_dims=1, in_channels=1, out_channels=1, hidden_channels=4, num_levels=2, boundary_mode=mode)
+    record(f"arch_modern_unet_1d_{mode}", "ModernUNet", kw, ref.arch.ModernUNet(**kw, key=key), rng.standard_normal((1, 32)))
+    kw = dict(num_spatial_dims=2, in_channels=3, out_channels=4, boundary_mode=mode)
+    record(f"block_linear_{mode}", "LinearConvBlock", kw, ref.blocks.LinearConvBlock(**kw, key=key), rng.standard_normal((3, 7, 9)))
+kw = dict(num_spatial_dims=2, in_channels=2, out_channels=1, hidden_channels=4, num_levels=2, num_blocks=1, use_norm=False,
+          channel_multipliers=[2, 3], boundary_mode="periodic")
+record("arch_modern_unet_2d_multipliers", "ModernUNet", kw, ref.arch.ModernUNet(**kw, key=key), rng.standard_normal((2, 16, 12)))
+
 # ---- parameter counts computed by the reference's own count_parameters ----
 counts = {}
 for nm, ctor in [("ClassicFNO", ref.arch.ClassicFNO), ("ClassicResNet", ref.arch.ClassicResNet),
                  ("DilatedResNet", ref.arch.DilatedResNet), ("ClassicUNet", ref.arch.ClassicUNet),
-                 ("ModernResNet", ref.arch.ModernResNet), ("ConvNet", ref.arch.ConvNet)]:
+                 ("ModernResNet", ref.arch.ModernResNet), ("ConvNet", ref.arch.ConvNet),
+                 ("ModernUNet", ref.arch.ModernUNet)]:
     for D in (1, 2, 3):
         counts[f"{nm}_{D}d"] = int(ref.count_parameters(ctor(D, 1, 1, key=key)))
 counts["ClassicFNO_2d_h64_m16"] = int(ref.count_parameters(ref.arch.ClassicFNO(2, 1, 1, hidden_channels=64, num_modes=16, key=key)))

@@ -65,6 +65,10 @@ def oracle_eval(case, x, p):
         D = kw["num_spatial_dims"]
         y = onn.sequential_forward(p, xb, lambda h, pre: onn.modern_block_any(h, p, pre, kw["boundary_mode"], "relu", D),
                                    kw.get("num_blocks", 6))
+    elif kind == "ModernUNet":
+        y = onn.modern_unet_forward(p, xb, kw["boundary_mode"], kw.get("num_levels", 4), kw.get("num_blocks", 2))
+    elif kind == "LinearConvBlock":
+        y = oconv.physics_conv(xb, p["weight"], p.get("bias"), boundary_mode=kw["boundary_mode"])
     elif kind == "ConvNet":
         y = onn.conv_net_forward(p, xb, kw["boundary_mode"])
     elif kind == "ClassicUNet":

@@ -17,8 +17,6 @@ def test_oracle_reproduces_reference_outputs(case):
 def test_parameter_counts_from_the_reference_itself():
     import pdequinox_b200 as pdeqx
     for name, n in gc.PARAMETER_COUNTS.items():
-        if name.startswith("ClassicUNet"):
-            continue  # ClassicUNet: next tier
         if name == "ClassicFNO_2d_h64_m16":
             m = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=64, num_modes=16, key=0)
         else:

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 SUPPORTED = {"SpectralConv", "SpectralConvRaw", "PhysicsConv", "PointwiseLinearConv", "ClassicSpectralBlock",
              "ClassicResBlock", "DilatedResBlock", "ClassicFNO", "ClassicResNet", "DilatedResNet", "PhysicsConvTranspose",
              "ClassicDoubleConvBlock", "LinearConvDownBlock", "LinearConvUpBlock", "ClassicUNet", "ModernResBlock",
-             "ModernResNet", "ConvNet"}
+             "ModernResNet", "ConvNet", "ModernUNet", "LinearConvBlock"}
 CASES = [c for c in gc.CASES if c["kind"] in SUPPORTED]
 
 
@@ -32,10 +32,11 @@ def build(case, p):
            "PhysicsConvTranspose": pdeqx.PhysicsConvTranspose, "ClassicDoubleConvBlock": pdeqx.blocks.ClassicDoubleConvBlock,
            "LinearConvDownBlock": pdeqx.blocks.LinearConvDownBlock, "LinearConvUpBlock": pdeqx.blocks.LinearConvUpBlock,
            "ClassicUNet": pdeqx.arch.ClassicUNet, "ModernResBlock": pdeqx.blocks.ModernResBlock,
-           "ModernResNet": pdeqx.arch.ModernResNet, "ConvNet": pdeqx.arch.ConvNet}[kind]
+           "ModernResNet": pdeqx.arch.ModernResNet, "ConvNet": pdeqx.arch.ConvNet, "ModernUNet": pdeqx.arch.ModernUNet,
+           "LinearConvBlock": pdeqx.blocks.LinearConvBlock}[kind]
     if isinstance(kw.get("kernel_size"), list):
         kw["kernel_size"] = tuple(kw["kernel_size"])
-    for name in ("stride", "output_padding"):
+    for name in ("stride", "output_padding", "channel_multipliers"):
         if isinstance(kw.get(name), list):
             kw[name] = tuple(kw[name])
     return cls(**kw, key=0)

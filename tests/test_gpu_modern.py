@@ -92,3 +92,13 @@ def test_conv_net_gelu_hidden_and_relu_final(cuda):
     model = pdeqx.ConvNet(1, 1, 1, hidden_channels=3, depth=2, activation=pdeqx.nn.gelu, final_activation=pdeqx.nn.relu,
                           boundary_mode="periodic", key=1)
     _check_train_step(model, lambda q, x: onn.conv_net_forward(q, x, "periodic", "gelu", "relu"), 2, 1, 1, (16,), 34)
+
+
+@pytest.mark.parametrize("D,spatial,mode,use_norm,levels,blocks", [
+    (1, (32,), "dirichlet", True, 2, 2), (1, (16,), "periodic", False, 1, 1), (2, (8, 12), "neumann", True, 2, 1)])
+def test_modern_unet_train_step_matches_oracle(cuda, D, spatial, mode, use_norm, levels, blocks):
+    """Hierarchical with pre-activation ResNet arcs (pdequinox/arch/_modern_u_net.py:78-98): forward and every gradient."""
+    pdeqx.set_precision("fp32")
+    model = pdeqx.ModernUNet(D, 1, 1, hidden_channels=4, num_levels=levels, num_blocks=blocks, use_norm=use_norm,
+                             boundary_mode=mode, key=8)
+    _check_train_step(model, lambda q, x: onn.modern_unet_forward(q, x, mode, levels, blocks), 2, 1, 1, spatial, 35)
