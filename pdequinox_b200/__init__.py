@@ -2,7 +2,7 @@
 PhysicsConv / PointwiseLinearConv, the FNO / ResNet blocks and architectures built from them, and a
 batch-sharded Adam training step. Same constructors, call convention and parameter pytree as the
 reference; all arithmetic runs in libpdeqx_b200.so (hand-written CUDA). There is no CPU fallback."""
-from . import arch, blocks, conv, nn, random, train  # noqa: F401
+from . import arch, blocks, conv, nn, random, sample_data, train  # noqa: F401
 from ._module import (count_parameters, get_precision, set_precision, tree_leaves, tree_paths, vmap,  # noqa: F401
                       Module)
 from ._hierarchical import Hierarchical  # noqa: F401
