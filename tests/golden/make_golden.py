@@ -38,9 +38,21 @@ def named_leaves(obj, prefix=""):
         for i, o in enumerate(obj):
             out.update(named_leaves(o, f"{prefix}{i}."))
     elif hasattr(obj, "__dict__") and not isinstance(obj, type):
-        for k, v in vars(obj).items():
-            out.update(named_leaves(v, f"{prefix}{k}."))
+        for k in field_order(obj):
+            out.update(named_leaves(vars(obj)[k], f"{prefix}{k}."))
     return out
+
+
+def field_order(obj):
+    """Attribute names in dataclass-FIELD order (class annotations, base classes first): the order in which equinox flattens a
+    Module, i.e. the reference's leaf order -- not the order in which __init__ happens to assign them."""
+    names = []
+    for cls in reversed(type(obj).__mro__):
+        for k in getattr(cls, "__annotations__", {}):
+            if k not in names:
+                names.append(k)
+    have = vars(obj)
+    return [k for k in names if k in have] + [k for k in have if k not in names]
 
 
 def randomise(obj):
