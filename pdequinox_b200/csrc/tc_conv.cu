@@ -1413,6 +1413,7 @@ bool tc_conv_available(const ConvGeom& g) {
 }
 
 static std::atomic<int64_t> g_pair_launches{0};
+static std::atomic<bool> g_pair_unavailable{false};
 int64_t tc_conv_pair_launches() { return g_pair_launches.load(std::memory_order_relaxed); }
 
 static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, bool flip, const float* bias,
@@ -1471,7 +1472,8 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   // CTA-pair kernel (cta_group::2, all 64 output channels per unit): needs chains of equal length cut into equal segments
   // (both CTAs of a pair issue the same schedule) and an even number of items
   static const bool pair_enabled = [] { const char* e = getenv("PDEQX_CONV_PAIR"); return !(e && e[0] == '0'); }();
-  if (pair_enabled && c_in == 64 && c_out == 64 && H % cp.d == 0 && sms >= 2) {
+  const tc::ConvParams cp_one_cta = cp;
+  if (pair_enabled && !g_pair_unavailable.load(std::memory_order_relaxed) && c_in == 64 && c_out == 64 && H % cp.d == 0 && sms >= 2) {
     const int chain = H / cp.d, pairs = sms / 2;
     int best_seg = 0;
     int64_t best_cost = 0;
@@ -1501,9 +1503,16 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
       else if (act == PDEQX_ACT_GELU_TANH) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_GELU_TANH);
       else PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_IDENTITY);
 #undef PDEQX_CONV_PAIR_LAUNCH
-      PDEQX_LAUNCHED();
-      g_pair_launches.fetch_add(1, std::memory_order_relaxed);
-      return PDEQX_OK;
+      // A device that cannot co-schedule the two-CTA cluster with 227 KB each (a partitioned GPU, an odd SM count) rejects
+      // the launch synchronously: remember that and take the one-CTA kernel from now on instead of failing the call.
+      const cudaError_t pair_err = cudaGetLastError();
+      if (pair_err == cudaSuccess) {
+        ::pdeqx::g_launches.fetch_add(1, std::memory_order_relaxed);
+        g_pair_launches.fetch_add(1, std::memory_order_relaxed);
+        return PDEQX_OK;
+      }
+      g_pair_unavailable.store(true, std::memory_order_relaxed);
+      cp = cp_one_cta;
     }
   }
   int grid = (int)(cp.items < sms ? cp.items : sms);
