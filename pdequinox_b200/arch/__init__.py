@@ -1,9 +1,10 @@
-from ._classic_fno import ClassicFNO
-from ._classic_res_net import ClassicResNet
-from ._classic_u_net import ClassicUNet
-from ._conv_net import ConvNet
-from ._dilated_res_net import DilatedResNet
-from ._modern_res_net import ModernResNet
-from ._modern_u_net import ModernUNet
+"""Architectures (reference package: pdequinox/arch): Sequential- and Hierarchical-based networks plus the plain ConvNet."""
+import importlib
 
-__all__ = ["ClassicFNO", "ClassicResNet", "ClassicUNet", "ConvNet", "DilatedResNet", "ModernResNet", "ModernUNet"]
+_ARCHS = {"ClassicFNO": "_classic_fno", "ClassicResNet": "_classic_res_net", "ClassicUNet": "_classic_u_net",
+          "ConvNet": "_conv_net", "DilatedResNet": "_dilated_res_net", "ModernResNet": "_modern_res_net",
+          "ModernUNet": "_modern_u_net"}
+__all__ = sorted(_ARCHS)
+for _name, _module in _ARCHS.items():
+    globals()[_name] = getattr(importlib.import_module(f"{__name__}.{_module}"), _name)
+del _name, _module

@@ -1,16 +1,20 @@
-from ._base_block import Block, BlockFactory
-from ._classic_double_conv_block import ClassicDoubleConvBlock, ClassicDoubleConvBlockFactory
-from ._classic_res_block import ClassicResBlock, ClassicResBlockFactory
-from ._classic_spectral_block import ClassicSpectralBlock, ClassicSpectralBlockFactory
-from ._dilated_res_block import DilatedResBlock, DilatedResBlockFactory
-from ._linear_channel_adjust_block import LinearChannelAdjustBlock, LinearChannelAdjustBlockFactory
-from ._linear_conv_block import LinearConvBlock, LinearConvBlockFactory
-from ._linear_conv_down_block import LinearConvDownBlock, LinearConvDownBlockFactory
-from ._linear_conv_up_block import LinearConvUpBlock, LinearConvUpBlockFactory
-from ._modern_res_block import ModernResBlock, ModernResBlockFactory
+"""Blocks and their factories (reference package: pdequinox/blocks). Every block class `X` comes with `XFactory`."""
+from . import (_base_block, _classic_double_conv_block, _classic_res_block, _classic_spectral_block, _dilated_res_block,
+               _linear_blocks, _modern_res_block)
 
-__all__ = ["Block", "BlockFactory", "ClassicDoubleConvBlock", "ClassicDoubleConvBlockFactory", "ClassicResBlock",
-           "ClassicResBlockFactory", "ClassicSpectralBlock", "ClassicSpectralBlockFactory", "DilatedResBlock",
-           "DilatedResBlockFactory", "LinearChannelAdjustBlock", "LinearChannelAdjustBlockFactory",
-           "LinearConvBlock", "LinearConvBlockFactory", "LinearConvDownBlock", "LinearConvDownBlockFactory", "LinearConvUpBlock", "LinearConvUpBlockFactory",
-           "ModernResBlock", "ModernResBlockFactory"]
+_BLOCKS = {
+    _classic_double_conv_block: ["ClassicDoubleConvBlock"],
+    _classic_res_block: ["ClassicResBlock"],
+    _classic_spectral_block: ["ClassicSpectralBlock"],
+    _dilated_res_block: ["DilatedResBlock"],
+    _linear_blocks: ["LinearChannelAdjustBlock", "LinearConvBlock", "LinearConvDownBlock", "LinearConvUpBlock"],
+    _modern_res_block: ["ModernResBlock"],
+}
+__all__ = ["Block", "BlockFactory"]
+Block, BlockFactory = _base_block.Block, _base_block.BlockFactory
+for _module, _names in _BLOCKS.items():
+    for _name in _names:
+        for _export in (_name, _name + "Factory"):
+            globals()[_export] = getattr(_module, _export)
+            __all__.append(_export)
+del _module, _names, _name, _export
