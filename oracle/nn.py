@@ -277,8 +277,9 @@ def group_norm_vjp(x, weight, groups, D, gy, eps=1e-5):
     return gx.reshape(x.shape).astype(x.dtype), gw.astype(x.dtype), gb.astype(x.dtype)
 
 
-def classic_resnet_loss_and_grad(p, x, y, num_blocks, boundary_mode, activation="relu"):
-    """mse(classic_resnet(x), y) and its gradient (use_norm=False, in==out channels)."""
+def classic_resnet_loss_and_grad(p, x, y, num_blocks, boundary_mode, activation="relu", relu_masks=None):
+    """mse(classic_resnet(x), y) and its gradient (use_norm=False, in==out channels).
+    `relu_masks` (optional, {(block, 0 | 1): bool array}): evaluate act' with the given masks (see dilated_resnet_loss_and_grad)."""
     act, act_grad = ACTIVATIONS[activation]
     grads = {}
     h = oconv.pointwise_conv(x, p["lifting.weight"], p.get("lifting.bias"))
@@ -297,13 +298,90 @@ def classic_resnet_loss_and_grad(p, x, y, num_blocks, boundary_mode, activation=
     grads["projection.weight"], grads["projection.bias"] = gw, gb
     for i in reversed(range(num_blocks)):
         hin, pre1, a1, pre2 = saved[i]
-        g2 = g * act_grad(pre2)
+        g2 = g * (relu_masks[(i, 1)].astype(pre2.dtype) if relu_masks is not None else act_grad(pre2))
         ga1, gw2, gb2 = oconv.physics_conv_vjp(a1, p[f"blocks.{i}.conv_2.weight"], g2, boundary_mode=boundary_mode)
-        g1 = ga1 * act_grad(pre1)
+        g1 = ga1 * (relu_masks[(i, 0)].astype(pre1.dtype) if relu_masks is not None else act_grad(pre1))
         gh, gw1, gb1 = oconv.physics_conv_vjp(hin, p[f"blocks.{i}.conv_1.weight"], g1, boundary_mode=boundary_mode)
         grads[f"blocks.{i}.conv_1.weight"], grads[f"blocks.{i}.conv_1.bias"] = gw1, gb1
         grads[f"blocks.{i}.conv_2.weight"], grads[f"blocks.{i}.conv_2.bias"] = gw2, gb2
         g = gh + g2
+    _, gw, gb = oconv.pointwise_conv_vjp(x, p["lifting.weight"], g, "lifting.bias" in p)
+    grads["lifting.weight"], grads["lifting.bias"] = gw, gb
+    return loss, {k: grads[k] for k in p if grads.get(k) is not None}
+
+
+def init_dilated_resnet(rng, D, in_channels, out_channels, *, hidden_channels=32, num_blocks=2, kernel_size=3,
+                        dilation_rates=(1, 2, 4, 8, 4, 2, 1), use_norm=True, dtype=np.float32):
+    """Leaf order of DilatedResNet (Sequential of DilatedResBlock: norm_layers[*], conv_layers[*]; App. C)."""
+    p = {}
+    p["lifting.weight"], p["lifting.bias"] = oconv.init_conv_weights(rng, D, in_channels, hidden_channels, 1, dtype=dtype)
+    for i in range(num_blocks):
+        if use_norm:
+            for j in range(len(dilation_rates)):
+                p[f"blocks.{i}.norm_layers.{j}.weight"] = np.ones(hidden_channels, dtype)
+                p[f"blocks.{i}.norm_layers.{j}.bias"] = np.zeros(hidden_channels, dtype)
+        for j in range(len(dilation_rates)):
+            w, b = oconv.init_conv_weights(rng, D, hidden_channels, hidden_channels, kernel_size, dtype=dtype)
+            p[f"blocks.{i}.conv_layers.{j}.weight"], p[f"blocks.{i}.conv_layers.{j}.bias"] = w, b
+    p["projection.weight"], p["projection.bias"] = oconv.init_conv_weights(rng, D, hidden_channels, out_channels, 1, dtype=dtype)
+    return p
+
+
+def dilated_resnet_forward(p, x, num_blocks, boundary_mode, dilation_rates=(1, 2, 4, 8, 4, 2, 1), activation="relu"):
+    D = p["lifting.weight"].ndim - 2
+    use_norm = "blocks.0.norm_layers.0.weight" in p
+    h = oconv.pointwise_conv(x, p["lifting.weight"], p.get("lifting.bias"))
+    for i in range(num_blocks):
+        h = dilated_res_block(h, p, f"blocks.{i}.", boundary_mode, dilation_rates, activation, use_norm, D)
+    return oconv.pointwise_conv(h, p["projection.weight"], p.get("projection.bias"))
+
+
+def dilated_resnet_loss_and_grad(p, x, y, num_blocks, boundary_mode, dilation_rates=(1, 2, 4, 8, 4, 2, 1), activation="relu",
+                                 relu_masks=None):
+    """mse(dilated_resnet(x), y) and its gradient: DilatedResBlock (_dilated_res_block.py:141-151, in == out) is per rate
+    norm -> conv -> act, then + x; analytic reverse mode through group_norm_vjp / physics_conv_vjp.
+    `relu_masks` (optional, {(block, layer): bool array}): evaluate act' with the given masks instead of the oracle's own
+    pre-activation signs (used to compare against a reduced-precision forward pass whose masks may legitimately differ
+    where |pre| is below that precision's error)."""
+    act, act_grad = ACTIVATIONS[activation]
+    D = p["lifting.weight"].ndim - 2
+    use_norm = "blocks.0.norm_layers.0.weight" in p
+    grads = {}
+    h = oconv.pointwise_conv(x, p["lifting.weight"], p.get("lifting.bias"))
+    saved = []
+    for i in range(num_blocks):
+        layers = []
+        hin = h
+        for j, d in enumerate(dilation_rates):
+            pre_n = h
+            if use_norm:
+                h = group_norm(h, p[f"blocks.{i}.norm_layers.{j}.weight"], p[f"blocks.{i}.norm_layers.{j}.bias"], 1, D)
+            hn = h
+            pre = oconv.physics_conv(hn, p[f"blocks.{i}.conv_layers.{j}.weight"], p.get(f"blocks.{i}.conv_layers.{j}.bias"),
+                                     boundary_mode=boundary_mode, dilation=d)
+            h = act(pre)
+            layers.append((pre_n, hn, pre))
+        h = h + hin
+        saved.append(layers)
+    pred = oconv.pointwise_conv(h, p["projection.weight"], p.get("projection.bias"))
+    diff = pred - y
+    loss = float(np.mean(diff.astype(np.float64) ** 2))
+    g = ((2.0 / diff.size) * diff).astype(x.dtype)
+    g, gw, gb = oconv.pointwise_conv_vjp(h, p["projection.weight"], g, "projection.bias" in p)
+    grads["projection.weight"], grads["projection.bias"] = gw, gb
+    for i in reversed(range(num_blocks)):
+        gskip = g
+        for j in reversed(range(len(dilation_rates))):
+            pre_n, hn, pre = saved[i][j]
+            mask = relu_masks[(i, j)].astype(pre.dtype) if relu_masks is not None else act_grad(pre)
+            gpre = g * mask
+            g, gwc, gbc = oconv.physics_conv_vjp(hn, p[f"blocks.{i}.conv_layers.{j}.weight"], gpre, boundary_mode=boundary_mode,
+                                                dilation=dilation_rates[j])
+            grads[f"blocks.{i}.conv_layers.{j}.weight"], grads[f"blocks.{i}.conv_layers.{j}.bias"] = gwc, gbc
+            if use_norm:
+                g, gnw, gnb = group_norm_vjp(pre_n, p[f"blocks.{i}.norm_layers.{j}.weight"], 1, D, g)
+                grads[f"blocks.{i}.norm_layers.{j}.weight"], grads[f"blocks.{i}.norm_layers.{j}.bias"] = gnw, gnb
+        g = g + gskip
     _, gw, gb = oconv.pointwise_conv_vjp(x, p["lifting.weight"], g, "lifting.bias" in p)
     grads["lifting.weight"], grads["lifting.bias"] = gw, gb
     return loss, {k: grads[k] for k in p if grads.get(k) is not None}

@@ -90,6 +90,11 @@ class Hierarchical(Module):
                                          reversed(self.right_arc_blocks)):
             skip = skips.pop()
             x = up._fwd(x, tape)
+            if skip.shape[0] != x.shape[0] or tuple(skip.shape[2:]) != tuple(x.shape[2:]):
+                # the reference raises from jnp.concatenate (_hierarchical.py:272-275) when a custom up-sampling factory
+                # does not restore the skip's grid
+                raise ValueError(f"Cannot concatenate the skip connection {tuple(skip.shape)} with the up-sampled "
+                                 f"tensor {tuple(x.shape)}: all dimensions but the channel axis must match")
             B, ca, cb = skip.shape[0], skip.shape[1], x.shape[1]
             n = skip[0, 0].numel()
             cat = new_buf(tape, self, f"cat{level}", (B, ca + cb) + tuple(skip.shape[2:]))

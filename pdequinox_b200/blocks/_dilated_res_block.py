@@ -81,7 +81,9 @@ class DilatedResBlock(Block):
             ga = nn.activation_bwd(pre if pre is not None else out, g, act, tape, conv, "ga")
             first = j == 0
             no_norm = isinstance(norm, Identity)
-            want = need_gx or not first
+            # a GroupNorm in front of the conv has parameters of its own: their gradients need the conv's input gradient
+            # even when the caller does not want the block's (and the norm's tape record must be popped either way)
+            want = need_gx or not first or not no_norm
             add = gy if (first and identity_skip and no_norm) else None
             g = conv.apply_bwd(hn, ga, tape, want, tag="gx", add=add)
             if want and not no_norm:
@@ -89,8 +91,10 @@ class DilatedResBlock(Block):
                 if first and identity_skip:
                     g = nn.add(g, gy, tape, self, "gx")
         if not identity_skip:
-            gs = self.bypass_norm._bwd(self.bypass_conv._bwd(gy, tape, need_gx), tape) if need_gx else \
-                self.bypass_conv._bwd(gy, tape, False)
+            skip_norm = isinstance(self.bypass_norm, Identity)
+            gs = self.bypass_conv._bwd(gy, tape, need_gx or not skip_norm)
+            if not skip_norm:
+                gs = self.bypass_norm._bwd(gs, tape)
             if need_gx:
                 g = nn.add(g, gs, tape, self, "gx")
         return g if need_gx else None

@@ -37,7 +37,7 @@ class MorePaddingConv(Module):
     _fields = ("weight", "bias")
 
     def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, padding=0,
-                 padding_mode="zeros", dilation=1, groups=1, use_bias=True, *, key, **kwargs):
+                 padding_mode="zeros", dilation=1, groups=1, use_bias=True, *, key):
         self.num_spatial_dims = num_spatial_dims
         self.kernel_size = _ntuple(kernel_size, num_spatial_dims, "kernel_size")
         self.stride = _ntuple(stride, num_spatial_dims, "stride")
@@ -117,7 +117,7 @@ class PhysicsConv(MorePaddingConv):
     """_physics_conv.py:29-118."""
 
     def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, dilation=1, groups=1,
-                 use_bias=True, *, key, boundary_mode, zero_bias_init=False, **kwargs):
+                 use_bias=True, *, key, boundary_mode, zero_bias_init=False):
         self.boundary_mode = boundary_mode.lower()
         if self.boundary_mode == "periodic":
             padding_mode = "circular"
@@ -130,7 +130,7 @@ class PhysicsConv(MorePaddingConv):
         super().__init__(num_spatial_dims=num_spatial_dims, in_channels=in_channels, out_channels=out_channels,
                          kernel_size=kernel_size, stride=stride,
                          padding=compute_same_padding(num_spatial_dims, kernel_size, dilation), dilation=dilation,
-                         groups=groups, use_bias=use_bias, padding_mode=padding_mode, key=key, **kwargs)
+                         groups=groups, use_bias=use_bias, padding_mode=padding_mode, key=key)
         if use_bias and zero_bias_init:  # _physics_conv.py:117-118
             self.bias = to_param(np.zeros(tuple(self.bias.shape), np.float32))
 
@@ -141,7 +141,7 @@ class MorePaddingConvTranspose(Module):
     _fields = ("weight", "bias")
 
     def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, padding=0,
-                 padding_mode="zeros", output_padding=0, dilation=1, groups=1, use_bias=True, *, key, **kwargs):
+                 padding_mode="zeros", output_padding=0, dilation=1, groups=1, use_bias=True, *, key):
         self.num_spatial_dims = num_spatial_dims
         self.kernel_size = _ntuple(kernel_size, num_spatial_dims, "kernel_size")
         self.stride = _ntuple(stride, num_spatial_dims, "stride")
@@ -216,7 +216,7 @@ class PhysicsConvTranspose(MorePaddingConvTranspose):
     """_physics_conv.py:121-236."""
 
     def __init__(self, num_spatial_dims, in_channels, out_channels, kernel_size, stride=1, output_padding=0, dilation=1,
-                 groups=1, use_bias=True, *, key, boundary_mode, zero_bias_init=False, **kwargs):
+                 groups=1, use_bias=True, *, key, boundary_mode, zero_bias_init=False):
         self.boundary_mode = boundary_mode.lower()
         if self.boundary_mode == "periodic":
             padding_mode = "circular"
@@ -230,6 +230,6 @@ class PhysicsConvTranspose(MorePaddingConvTranspose):
                          kernel_size=kernel_size, stride=stride,
                          padding=compute_same_padding(num_spatial_dims, kernel_size, dilation),
                          padding_mode=padding_mode, output_padding=output_padding, dilation=dilation, groups=groups,
-                         use_bias=use_bias, key=key, **kwargs)
+                         use_bias=use_bias, key=key)
         if use_bias and zero_bias_init:  # _physics_conv.py:233-234
             self.bias = to_param(np.zeros(tuple(self.bias.shape), np.float32))

@@ -165,12 +165,17 @@ class GraphedTrainStep:
     """The whole train step (forward, reverse pass, gradient all-reduce, Adam) captured ONCE into a CUDA graph and
     replayed: ~100 kernel launches and their host-side descriptor work collapse into one graph launch, which is what
     keeps small per-GPU batches (8 samples per GPU at 8 GPUs) from being launch-bound. Inputs are copied into static
-    device buffers; every intermediate lives in the step's persistent tape buffers, so replays allocate nothing."""
+    device buffers; every intermediate lives in the step's persistent tape buffers, so replays allocate nothing.
+
+    Construction is free of side effects on the optimisation: the `warmup` eager steps that allocate the tape buffers
+    before the capture run on the example batch, and the parameters, Adam moments, the device-side update counter and
+    `step.count` are rewound to their values at entry afterwards (capturing itself executes nothing)."""
 
     def __init__(self, step: "TrainStep", x_example, y_example, warmup=3):
         self.step = step
         self.x = _as_device(x_example).clone()
         self.y = _as_device(y_example).clone()
+        entry = (step.arena.params.clone(), step.mu.clone(), step.nu.clone(), step.adam_state.clone(), step.count)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up on a side stream: allocates every tape buffer, sets kernel attributes
@@ -181,6 +186,11 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             step(self.x, self.y)
+        step.arena.params.copy_(entry[0])
+        step.mu.copy_(entry[1])
+        step.nu.copy_(entry[2])
+        step.adam_state.copy_(entry[3])
+        step.count = entry[4]
         self.loss = step.loss
         # input pipeline: the NEXT batch is copied host -> device on a side stream while the current step runs
         self._copy_stream = torch.cuda.Stream()

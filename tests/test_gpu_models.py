@@ -99,12 +99,9 @@ def test_graph_replayed_train_steps_equal_eager_steps(cuda):
     other = make()
     snapshot = other.arena.params.clone()
     graphed = GraphedTrainStep(other, xs[0], ys[0], warmup=2)
-    # warm-up and capture ran real updates: rewind the optimiser state, then replay the three batches
-    with torch.no_grad():
-        other.arena.params.copy_(snapshot)
-        other.mu.zero_()
-        other.nu.zero_()
-        other.adam_state.zero_()
+    # construction (warm-up steps + capture) must leave the optimisation where it was
+    assert torch.equal(other.arena.params, snapshot) and other.count == 0
+    assert not other.mu.any() and not other.nu.any() and not other.adam_state.any()
     losses_g = [graphed(x, y).item() for x, y in zip(xs, ys)]
     for a, b in zip(losses_e, losses_g):
         assert abs(a - b) <= 1e-5 * abs(a)

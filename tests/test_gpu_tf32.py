@@ -131,10 +131,10 @@ def test_tf32_fno_train_step(cuda, D, spatial, hidden, modes, blocks):
         y = rng.standard_normal((2, 1) + spatial)
         loss_ref, g_ref = onn.fno_loss_and_grad(p, x, y, (modes,) * D, blocks)
         loss = step.loss_and_grad(x, y).item()
-        assert abs(loss - loss_ref) <= 5e-3 * abs(loss_ref)
+        assert abs(loss - loss_ref) <= TOL * abs(loss_ref)
         g = {k: v.detach().cpu().numpy() for k, v in step.arena.named_grads().items()}
         for k in g_ref:
-            assert rel_l2(g[k], g_ref[k]) <= 5e-3, k  # chained TF32 stages through 2 blocks and their reverse pass
+            assert rel_l2(g[k], g_ref[k]) <= TOL, k  # whole-model bar = the north star's 2e-3, chained stages included
     finally:
         pdeqx.set_precision("fp32")
 

@@ -79,7 +79,18 @@ def test_tf32_resnet_train_step(cuda):
     x = rng.standard_normal((2, 1, 32, 128))
     y = rng.standard_normal((2, 1, 32, 128))
     pred = host(pdeqx.vmap(model)(dev(x)))
-    assert rel_l2(pred, onn.classic_resnet_forward(p, x, 2, "periodic")) <= 3e-3
-    loss_ref, g_ref = onn.classic_resnet_loss_and_grad(p, x, y, 2, "periodic")
+    assert rel_l2(pred, onn.classic_resnet_forward(p, x, 2, "periodic")) <= TOL
     loss = step.loss_and_grad(x, y).item()
-    assert abs(loss - loss_ref) <= 5e-3 * abs(loss_ref)
+    # relu' is discontinuous: the oracle's reverse pass uses the relu masks of the forward pass under test
+    from pdequinox_b200._module import Tape
+    tape = Tape()
+    model._fwd(dev(x), tape)
+    masks = {}
+    for i, (_, h, p1, yy, p2) in enumerate(r for r in tape.stack if isinstance(r, tuple) and len(r) == 5):
+        masks[(i, 0)] = host(h if p1 is None else p1) > 0
+        masks[(i, 1)] = host(yy if p2 is None else p2) > 0
+    loss_ref, g_ref = onn.classic_resnet_loss_and_grad(p, x, y, 2, "periodic", relu_masks=masks)
+    assert abs(loss - loss_ref) <= TOL * abs(loss_ref)
+    g = {k: host(v) for k, v in step.arena.named_grads().items()}
+    for k in g_ref:
+        assert rel_l2(g[k], g_ref[k]) <= TOL, k

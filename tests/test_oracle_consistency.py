@@ -103,3 +103,31 @@ def test_fno_and_resnet_loss_gradients_finite_differences():
             num = (onn.mse_loss(onn.classic_resnet_forward(qp, x, 2, mode), y)
                    - onn.mse_loss(onn.classic_resnet_forward(qm, x, 2, mode), y)) / 2e-6
             assert num == pytest.approx(float(np.sum(g[key].reshape(d.shape) * d)), rel=2e-5, abs=1e-9), (mode, key)
+
+
+@pytest.mark.parametrize("mode", ["periodic", "dirichlet", "neumann"])
+def test_dilated_resnet_loss_gradients_finite_differences(mode):
+    """The analytic reverse pass of the DilatedResNet oracle (GroupNorm -> dilated conv -> act per rate, + skip) against central
+    differences of its own float64 loss along a random direction in every leaf; its forward pass is pinned by the golden
+    vectors generated from the reference's source (arch_dilated_resnet_* cases)."""
+    rng = np.random.default_rng(6)
+    rates = (1, 2, 1)
+    p = {k: v.astype(np.float64) for k, v in
+         onn.init_dilated_resnet(rng, 2, 1, 1, hidden_channels=3, num_blocks=2, dilation_rates=rates).items()}
+    for k in p:  # non-trivial affine parameters
+        if "norm_layers" in k:
+            p[k] = p[k] + 0.3 * rng.standard_normal(p[k].shape)
+    x, y = rng.standard_normal((2, 1, 8, 6)), rng.standard_normal((2, 1, 8, 6))
+    loss, g = onn.dilated_resnet_loss_and_grad(p, x, y, 2, mode, rates, activation="gelu")
+    assert loss == pytest.approx(onn.mse_loss(onn.dilated_resnet_forward(p, x, 2, mode, rates, "gelu"), y))
+    assert list(g) == list(p)
+    # the golden-pinned evaluator (tests/golden_cases.py: arch_dilated_* cases) and this forward pass are the same function
+    golden_path = onn.sequential_forward(p, x, lambda h, pre: onn.dilated_block_any(h, p, pre, mode, "gelu", 2, rates), 2)
+    np.testing.assert_allclose(onn.dilated_resnet_forward(p, x, 2, mode, rates, "gelu"), golden_path, rtol=0, atol=1e-13)
+    for key in p:
+        d = rng.standard_normal(p[key].shape)
+        pp, pm = dict(p), dict(p)
+        pp[key], pm[key] = p[key] + 1e-6 * d, p[key] - 1e-6 * d
+        num = (onn.mse_loss(onn.dilated_resnet_forward(pp, x, 2, mode, rates, "gelu"), y)
+               - onn.mse_loss(onn.dilated_resnet_forward(pm, x, 2, mode, rates, "gelu"), y)) / 2e-6
+        assert num == pytest.approx(float(np.sum(g[key].reshape(d.shape) * d)), rel=2e-5, abs=1e-9), key
