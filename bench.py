@@ -41,13 +41,67 @@ os.dup2(2, 1)
 def emit(line):
     os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
-WORKLOAD = "ClassicFNO 2D periodic, 256x256 grid, hidden 64, 16 modes/axis, 4 blocks, global batch 64 (BASELINE.json configs[3])"
-GRID, HIDDEN, MODES, BLOCKS, GLOBAL_BATCH = 256, 64, 16, 4, 64
-METRIC = "ClassicFNO 2D 256^2 train samples/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of tc::slab_kernel at B = 64 per GPU, summed over the 12 launches of one train
-# step (profiles/r1_slab_traffic.csv: forward 6.86 GB, cotangent passes 11.13 GB, data gradients 7.95 GB) and averaged per launch,
-# as `achieved` averages them. Algorithmic mean: 2.199e9 -> no re-reads (part of z is still in L2).
-SLAB_TRAFFIC_B64 = 25.93e9 / 12.0
+# The workloads: BASELINE.json configs[3] (the metric's configuration, default) and configs[4] (--config fno3d).
+CONFIGS = {
+    "fno2d": dict(workload="ClassicFNO 2D periodic, 256x256 grid, hidden 64, 16 modes/axis, 4 blocks, global batch 64 (BASELINE.json configs[3])",
+                  metric="ClassicFNO 2D 256^2 train samples/s", ndim=2, grid=256, hidden=64, modes=16, blocks=4, global_batch=64),
+    "fno3d": dict(workload="ClassicFNO 3D periodic, 64x64x64 grid, hidden 32, 12 modes/axis, 4 blocks, global batch 32 (BASELINE.json configs[4])",
+                  metric="ClassicFNO 3D 64^3 train samples/s", ndim=3, grid=64, hidden=32, modes=12, blocks=4, global_batch=32),
+}
+L2_NOTE = ("GPU arm: inputs larger than L2, no flush between steps (every activation tensor of a step is >= 134 MB per rank "
+           "at every rank count up to 8; L2 is 126 MB)")
+
+
+def config_block(args):
+    """`config` of the JSON line: identical in both arms (the reference arm runs on the GPU arm's configuration)."""
+    return {"workload": args.cfg["workload"], "global_batch": args.global_batch, "l2": L2_NOTE}
+
+
+TRAFFIC_CSV = os.path.join(ROOT, "profiles", "slab_traffic.csv")
+
+
+def kernel_source_sha():
+    """sha256 over the kernel sources (csrc/ + the public header): an ncu capture under profiles/ is only quoted by the
+    bench line if it was taken from exactly these sources (there is no .git on the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "pdequinox_b200", "csrc")
+    files = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(ROOT, "include", "pdeqx_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_slab_traffic(config, per_gpu_batch):
+    """(bytes per slab launch, note) from profiles/slab_traffic.csv -- dram__bytes_read.sum + dram__bytes_write.sum of every
+    tc::slab_kernel launch of ONE train step, captured by `scripts/profile_step.sh traffic` -- or (None, why) when the
+    capture does not belong to this build / workload. The file starts with `# key=value` lines: source_sha, config,
+    per_gpu_batch."""
+    import csv
+    try:
+        lines = open(TRAFFIC_CSV).read().splitlines()
+    except OSError:
+        return None, "no capture: profiles/slab_traffic.csv is absent"
+    meta = dict(ln[1:].strip().split("=", 1) for ln in lines if ln.startswith("#") and "=" in ln)
+    if meta.get("source_sha") != kernel_source_sha():
+        return None, f"stale capture: taken from kernel sources {meta.get('source_sha')}, this build is {kernel_source_sha()}"
+    if meta.get("config") != config or int(meta.get("per_gpu_batch", -1)) != per_gpu_batch:
+        return None, f"capture is for {meta.get('config')} at {meta.get('per_gpu_batch')} samples per GPU"
+    rows = list(csv.reader(ln for ln in lines if ln.startswith('"')))
+    head = rows[0]
+    ki, mi, vi = head.index("Kernel Name"), head.index("Metric Name"), head.index("Metric Value")
+    ii = head.index("ID")
+    total, ids = 0.0, set()
+    for r in rows[1:]:
+        if "slab_kernel" in r[ki] and r[mi] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(r[vi].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[r[head.index("Metric Unit")]]
+            ids.add(r[ii])
+    if not ids:
+        return None, "capture holds no slab_kernel launch"
+    return total / len(ids), (f"ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the {len(ids)} slab_kernel launches of one "
+                              f"train step (profiles/slab_traffic.csv, kernel sources {meta['source_sha']})")
 
 
 def parse():
@@ -57,12 +111,17 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PDEQX_PRECISION", "tf32"), choices=["tf32", "fp32"])
-    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--config", default="fno2d", choices=sorted(CONFIGS), help="fno2d = BASELINE.json configs[3] (the metric), fno3d = configs[4]")
+    ap.add_argument("--global-batch", type=int, default=0, help="0 = the configuration's own global batch")
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples (= host threads) per CPU-baseline step; 0 = all cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-allreduce", action="store_true", help="bucketed all-reduce on a side stream during the reverse pass")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.cfg = CONFIGS[a.config]
+    if a.global_batch <= 0:
+        a.global_batch = a.cfg["global_batch"]
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -79,9 +138,10 @@ def cpu_workers():
     return max(1, min(cores, 32))
 
 
-def cpu_train_step_rate(workers, steps, warmup):
-    """One train step of the oracle port on `workers` samples, one sample per host thread (NumPy's pocketfft, einsum and
-    BLAS calls release the GIL; BLAS itself is pinned to one thread per call), gradients averaged, one Adam update."""
+def cpu_train_step_rate(cfg, samples, workers, steps, warmup):
+    """Train steps of the oracle port on `samples` samples each, in waves of `workers` host threads, one sample per thread
+    (NumPy's pocketfft, einsum and BLAS calls release the GIL; BLAS itself is pinned to one thread per call), gradients
+    averaged over the samples, one Adam update per step. Returns (samples/s, seconds per step)."""
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     from oracle import nn as onn
@@ -89,14 +149,16 @@ def cpu_train_step_rate(workers, steps, warmup):
         from threadpoolctl import threadpool_limits
     except Exception:
         threadpool_limits = None
+    D, grid, modes, blocks = cfg["ndim"], cfg["grid"], cfg["modes"], cfg["blocks"]
     rng = np.random.default_rng(0)
-    p = onn.init_fno(rng, 2, 1, 1, hidden_channels=HIDDEN, num_modes=MODES, num_blocks=BLOCKS)
+    p = onn.init_fno(rng, D, 1, 1, hidden_channels=cfg["hidden"], num_modes=modes, num_blocks=blocks)
     state = onn.adam_init(p)
-    x = rng.standard_normal((workers, 1, GRID, GRID)).astype(np.float32)
-    y = rng.standard_normal((workers, 1, GRID, GRID)).astype(np.float32)
+    shape = (samples, 1) + (grid,) * D
+    x = rng.standard_normal(shape).astype(np.float32)
+    y = rng.standard_normal(shape).astype(np.float32)
 
     def one(i):
-        return onn.fno_loss_and_grad(p, x[i:i + 1], y[i:i + 1], (MODES, MODES), BLOCKS)
+        return onn.fno_loss_and_grad(p, x[i:i + 1], y[i:i + 1], (modes,) * D, blocks)
 
     times = []
     limiter = threadpool_limits(limits=1) if (threadpool_limits and workers > 1) else None
@@ -104,35 +166,54 @@ def cpu_train_step_rate(workers, steps, warmup):
         with ThreadPoolExecutor(max_workers=workers) as pool:
             for it in range(warmup + steps):
                 t0 = time.perf_counter()
-                results = list(pool.map(one, range(workers)))
-                g = {k: sum(r[1][k] for r in results).reshape(p[k].shape) / workers for k in results[0][1]}
+                acc = None
+                for w0 in range(0, samples, workers):  # one wave = one sample per host thread; summed as it completes
+                    for _, g in pool.map(one, range(w0, min(w0 + workers, samples))):
+                        acc = dict(g) if acc is None else {k: acc[k] + g[k] for k in acc}
+                g = {k: acc[k].reshape(p[k].shape) / samples for k in acc}
                 p, state = onn.adam_step(p, g, state)
                 if it >= warmup:
                     times.append(time.perf_counter() - t0)
     finally:
-        if limiter is not None:
-            limiter.restore_original_limits() if hasattr(limiter, "restore_original_limits") else None
+        if limiter is not None and hasattr(limiter, "restore_original_limits"):
+            limiter.restore_original_limits()
     dt = sum(times) / len(times)
-    return workers / dt, dt, workers
+    return samples / dt, dt
+
+
+# seconds of host work one sample of a train step costs on one thread (measured on the round-1 GPU box: 16 samples on 16
+# threads per 1.9-2.0 s step); only used to size the bounded sample of the reference arm before anything is timed
+CPU_SECONDS_PER_SAMPLE = {"fno2d": 2.0, "fno3d": 6.0}
+REFERENCE_BUDGET_S = 270.0
 
 
 def run_reference(args):
+    """--impl reference: the CPU port of the reference's train step on this box's host cores, on the configuration,
+    --steps and --warmup of the GPU arm. A step covers the full global batch whenever (steps + warmup) such steps fit
+    REFERENCE_BUDGET_S of host time; otherwise the largest whole number of waves that does (stated in `sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warmup = 1 if args.warmup > 0 else 0
+    cfg = args.cfg
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     workers = args.cpu_sample if args.cpu_sample > 0 else cpu_workers()
-    rate, dt, cores = cpu_train_step_rate(workers, steps, warmup)
-    sample = (f"{workers} of the {args.global_batch} samples per step (one per host thread), {steps} timed steps of {dt:.1f} s; "
-              "NumPy port of the reference train step (rfftn/einsum/irfftn forward, analytic reverse pass, Adam); "
-              "jax/equinox are not installable in this image so the reference itself cannot run")
+    workers = min(workers, args.global_batch)
+    wave_s = CPU_SECONDS_PER_SAMPLE[args.config]
+    waves_full = -(-args.global_batch // workers)
+    waves = max(1, min(waves_full, int(REFERENCE_BUDGET_S / ((steps + warmup) * wave_s))))
+    samples = min(args.global_batch, waves * workers)
+    rate, dt = cpu_train_step_rate(cfg, samples, workers, steps, warmup)
+    sample = (f"{samples} of the {args.global_batch} samples per step in {waves} wave(s) of {workers} host threads (one sample per "
+              f"thread), {steps} timed steps of {dt:.1f} s after {warmup} warm-up; NumPy port of the reference train step "
+              "(rfftn/einsum/irfftn forward, analytic reverse pass, Adam); jax/equinox are not installable in this image so the "
+              "reference itself cannot run")
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "timing": "host perf_counter, CPU only"},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_block(args),
+        "details": {"timing": "host perf_counter, CPU only"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -218,7 +299,6 @@ def run_ours(args):
     import pdequinox_b200 as pdeqx
     from pdequinox_b200 import _lib
     from pdequinox_b200.train import TrainStep
-    from pdequinox_b200.conv._spectral_conv import get_plan
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,11 +316,14 @@ def run_ours(args):
     L = _lib.lib()
     pdeqx.set_precision(args.precision)
 
-    model = pdeqx.ClassicFNO(2, 1, 1, hidden_channels=HIDDEN, num_modes=MODES, num_blocks=BLOCKS, key=0)
+    cfg = args.cfg
+    D, GRID, HIDDEN, MODES, BLOCKS = cfg["ndim"], cfg["grid"], cfg["hidden"], cfg["modes"], cfg["blocks"]
+    spatial = (GRID,) * D
+    model = pdeqx.ClassicFNO(D, 1, 1, hidden_channels=HIDDEN, num_modes=MODES, num_blocks=BLOCKS, key=0)
     step = TrainStep(model, lr=3e-4, overlap=args.overlap_allreduce)
     rng = np.random.default_rng(1234)  # same global batch on every rank, sharded by sample
-    xg = rng.standard_normal((args.global_batch, 1, GRID, GRID), dtype=np.float32)
-    yg = rng.standard_normal((args.global_batch, 1, GRID, GRID), dtype=np.float32)
+    xg = rng.standard_normal((args.global_batch, 1) + spatial, dtype=np.float32)
+    yg = rng.standard_normal((args.global_batch, 1) + spatial, dtype=np.float32)
     xh = torch.from_numpy(xg[rank * per:(rank + 1) * per]).pin_memory()
     yh = torch.from_numpy(yg[rank * per:(rank + 1) * per]).pin_memory()
     xd, yd = xh.cuda(), yh.cuda()
@@ -318,55 +401,88 @@ def run_ours(args):
     probe_steps = min(args.steps, 3)
     L.pdeqx_timing_enable(1)
     ms_probe = timed(lambda: step(xd, yd), probe_steps)
-    slab_ms, slab_n = _lib.C.c_double(), _lib.C.c_int64()
-    _lib.check(L.pdeqx_timing_read(_lib.K_SPECTRAL_SLAB, _lib.C.byref(slab_ms), _lib.C.byref(slab_n)))
+    slab_ms, slab_n, slab_bytes_total = _lib.C.c_double(), _lib.C.c_int64(), _lib.C.c_double()
+    _lib.check(L.pdeqx_timing_read_ex(_lib.K_SPECTRAL_SLAB, _lib.C.byref(slab_ms), _lib.C.byref(slab_n), _lib.C.byref(slab_bytes_total)))
     L.pdeqx_timing_enable(0)
 
     if rank != 0:
         shutdown(world, graphed)
         return
 
-    # ---- roofline of the dominant kernel (read x once + write y once [+ saved z]) ----
+    # ---- roofline of the dominant kernel ----
+    # tc::slab_kernel = the last stage of every pass over a spectral block (forward, pre-activation cotangent, data gradient).
+    # Its launcher states the ALGORITHMIC bytes of each launch -- every tensor the launch reads or writes, once (SURVEY.md 8d:
+    # x in, y out, plus the saved z / the cotangent where the variant has them; the folded ends of the network read or write a
+    # single-channel field instead) -- and the library brackets every launch with CUDA events on its stream.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    n_pix = GRID * GRID
-    # the slab kernel runs three times per block: forward (read x, z; write y), cotangent of the pre-activation (read x, z,
-    # gy; write g) and data gradient (read g, z'; write gx) = 7 full-size tensor passes per block; z = [B,C,H,2m]; tables +
-    # bypass weights are negligible. The folded ends of the network remove passes: the lifted first block never reads its
-    # input (forward, cotangent) nor writes its input gradient; the last block's cotangent is rank one (gy is a single
-    # channel) and, projected, its forward pass writes a single channel.
-    act_code = pdeqx.nn.activation_code(model.blocks[0].activation)
-    lifted = bool(model.blocks[0].lifted_ok(xd))
-    rank1 = bool(L.pdeqx_spectral_block_rank1_ok(get_plan(2, per, HIDDEN, HIDDEN, (GRID, GRID), (MODES, MODES)).handle, 1, act_code))
-    projected = bool(model.blocks[-1].projected_ok(xd))
-    tensor_passes = 7 * BLOCKS - (3 if lifted else 0) - (1 if rank1 else 0) - (1 if projected else 0)
-    slab_launches = 3 * BLOCKS
-    small = 4 * (HIDDEN * HIDDEN + HIDDEN + 2 * MODES * GRID)
-    one_tensor = 4 * per * HIDDEN * n_pix
-    z_bytes = 4 * per * HIDDEN * GRID * 2 * MODES
-    field = 4 * per * n_pix  # single-channel fields read by the folded variants
-    n_fields = (3 if lifted else 0) + (1 if rank1 else 0) + (1 if projected else 0)
-    slab_bytes = (tensor_passes * one_tensor + n_fields * field) / slab_launches + z_bytes + small  # mean over a step's launches
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    n_pix = GRID ** D
     roofline = None
     if slab_n.value > 0:
         avg_s = slab_ms.value * 1e-3 / slab_n.value
+        slab_bytes = slab_bytes_total.value / slab_n.value
         achieved = slab_bytes / avg_s / 1e9
+        traffic, traffic_note = measured_slab_traffic(args.config, per)
         roofline = {"bound": "hbm", "kernel": "tc::slab_kernel, spectral block last stage (c2r DFT + 1x1 bypass + bias + gelu / gelu' / adjoint), "
-                              "mean over its %d launches per step (%d full-size tensor passes: lifting %s, projection %s)"
-                              % (slab_launches, tensor_passes, "folded" if lifted else "separate", "folded" if projected else "separate"),
+                              "mean over its %d launches per step" % (slab_n.value // probe_steps),
                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "peak_source": peak_source,
                     "algorithmic_bytes_per_launch": slab_bytes, "avg_launch_us": avg_s * 1e6,
                     "launches_timed": slab_n.value, "share_of_step": slab_ms.value / ms_probe,
                     "timed_in": f"{probe_steps} eagerly launched steps after the graph-replayed region (events cannot bracket "
                                 "kernels inside a graph replay); share_of_step is relative to that pass",
-                    "traffic": SLAB_TRAFFIC_B64 * per / 64.0,
-                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the 12 launches of one step at 64 samples "
-                                      "per GPU (profiles/r1_slab_traffic.csv), scaled by this run's samples per GPU"}
+                    "traffic": traffic, "traffic_source": traffic_note}
+
+    # ---- op-level roofline: one whole ClassicSpectralBlock (hidden -> hidden, this configuration's grid and per-GPU batch),
+    # forward and reverse pass, every kernel of the op (r2c, leading-axis DFTs, channel mix, slab; cotangent, weight
+    # gradients, adjoint chain, data gradient) inside the CUDA-event bracket, against SURVEY.md 8(d)'s algorithmic bytes:
+    #   forward: read x, write y, read the complex weights;  reverse: read gy, write gx, read w, write gw (+ saved modes)
+    spectral_block = None
+    if world == 1:
+        from pdequinox_b200.train import ParameterArena
+        blk = pdeqx.ClassicSpectralBlock(D, HIDDEN, HIDDEN, activation=model.blocks[0].activation, num_modes=MODES, key=2)
+        ParameterArena(blk)
+        xb = torch.randn((per, HIDDEN) + spatial, device="cuda")
+        gyb = torch.randn((per, HIDDEN) + spatial, device="cuda")
+        tape = pdeqx._module.Tape()
+
+        reps, ms_f, ms_b = 5, 0.0, 0.0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for it in range(2 + reps):
+            tape.stack.clear()
+            ev[0].record()
+            blk._fwd(xb, tape)
+            ev[1].record()
+            blk._bwd(gyb, tape, True)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ms_f += ev[0].elapsed_time(ev[1]) / reps
+                ms_b += ev[1].elapsed_time(ev[2]) / reps
+        G = 2 ** (D - 1)
+        w_bytes = 8 * G * HIDDEN * HIDDEN * MODES ** D
+        act_bytes = 4 * per * (HIDDEN + HIDDEN) * n_pix
+        modes_saved = 8 * per * HIDDEN * G * MODES ** D
+        fwd_bytes = act_bytes + w_bytes + 4 * HIDDEN * (HIDDEN + 1)
+        bwd_bytes = act_bytes + 2 * w_bytes + modes_saved
+        spectral_block = {
+            "op": f"ClassicSpectralBlock {HIDDEN}->{HIDDEN}, grid {'x'.join(map(str, spatial))}, {MODES} modes/axis, batch {per} (spectral conv + "
+                  "1x1 bypass + bias + activation as one op; every kernel of the op inside the bracket)",
+            "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_source,
+            "fwd": {"us": ms_f * 1e3, "algorithmic_bytes": fwd_bytes, "achieved": fwd_bytes / (ms_f * 1e-3) / 1e9,
+                    "frac": fwd_bytes / (ms_f * 1e-3) / 1e9 / hbm_peak},
+            "bwd": {"us": ms_b * 1e3, "algorithmic_bytes": bwd_bytes, "achieved": bwd_bytes / (ms_b * 1e-3) / 1e9,
+                    "frac": bwd_bytes / (ms_b * 1e-3) / 1e9 / hbm_peak,
+                    "note": "SURVEY.md 8(d) counts gy in + gx out only; the reverse pass also has to read x (bypass weight gradient, "
+                            "recomputed pre-activation): with that tensor the floor is 1.5x these bytes"},
+        }
+        del xb, gyb, tape, blk
+        torch.cuda.empty_cache()
 
     # ---- PhysicsConv roofline (BASELINE.json configs[2] layer: 3x3, 64 -> 64, 128x128, batch 128, periodic) ----
     physics = None
@@ -381,7 +497,7 @@ def run_ours(args):
                                         _lib.ptr(yc), _lib.stream()))
         for _ in range(3):
             conv_fwd()
-        reps = 10
+        reps = 100  # ~25 ms back to back: long enough for the clocks to settle under this kernel
         ms_c = timed(conv_fwd, reps) / reps
         conv_bytes = 4 * 128 * (64 + 64) * 128 * 128 + 4 * 64 * (64 * 9 + 1)
         physics = {"bound": "hbm (at the TF32 ridge: 144 flop/B)", "kernel": "PhysicsConv 3x3 64->64 fwd + bias + relu, 128x128, batch 128, periodic",
@@ -394,26 +510,29 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         workers = args.cpu_sample if args.cpu_sample > 0 else cpu_workers()
-        rate, dt, cores = cpu_train_step_rate(workers, 5, 1)  # ~12 s of CPU work on a 16-core host
-        cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+        workers = min(workers, args.global_batch)
+        rate, dt = cpu_train_step_rate(cfg, workers, workers, 5, 1)  # ~12 s of CPU work on a 16-core host
+        cpu = {"value": rate, "unit": "samples/s", "cores": workers, "kind": "port",
                "sample": f"{workers} of the {args.global_batch} samples per step (one per host thread), 5 timed steps "
                          f"({dt:.1f} s each); NumPy port of the reference train step (jax/equinox not installable here)"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": cfg["metric"], "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "tf32 (fp32 accumulate, fp32 storage)" if args.precision == "tf32" else "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": args.global_batch, "per_gpu_batch": per,
-                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of the 67.2 MB gradient arena per step)",
+        "config": config_block(args),
+        "details": {"per_gpu_batch": per,
+                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of the %.1f MB gradient arena per step)" % (step.arena.size * 4 / 1e6),
                    "launch": "one CUDA graph replay per step" if graphed is not None else "eager kernel launches",
                    "precision": args.precision,
-                   "l2": "inputs larger than L2: every activation tensor is %.0f MB per rank" % (per * HIDDEN * n_pix * 4 / 1e6)},
+                   "activation_tensor_mb_per_rank": per * HIDDEN * n_pix * 4 / 1e6},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4) * world, "d2h_bytes_per_step": 4 * world},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "spectral_block": spectral_block,
         "physics_conv": physics,
         "cpu_baseline": cpu,
     }

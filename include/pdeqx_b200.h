@@ -85,6 +85,9 @@ enum pdeqx_kernel_tag {
 };
 void pdeqx_timing_enable(int enabled); /* also clears what was recorded */
 int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launches);
+/* same, plus the ALGORITHMIC bytes of those launches as stated by their launchers (every tensor the launch reads or
+ * writes, counted once: SURVEY.md 8d) -- the numerator of bench.py's roofline.achieved. May be NULL. */
+int pdeqx_timing_read_ex(int32_t tag, double* total_ms, int64_t* launches, double* algorithmic_bytes);
 
 /* ------------------------------------------------------------------------- *
  * SpectralConv / ClassicSpectralBlock

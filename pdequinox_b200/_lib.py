@@ -54,6 +54,7 @@ PROTOTYPES = {
     "pdeqx_set_fast_paths": (None, [C.c_int]),
     "pdeqx_timing_enable": (None, [C.c_int]),
     "pdeqx_timing_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "pdeqx_timing_read_ex": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "pdeqx_spectral_plan_create": (C.c_int, [C.POINTER(SpectralDesc), C.POINTER(_P)]),
     "pdeqx_spectral_plan_destroy": (None, [_P]),
     "pdeqx_spectral_workspace_bytes": (C.c_size_t, [_P]),

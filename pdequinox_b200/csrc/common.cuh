@@ -57,9 +57,15 @@ struct TimedScope {
   int tag;
   cudaStream_t stream;
   int slot;
+  double bytes;       // algorithmic bytes of the launches inside the scope (reported by the launchers, see timed_bytes)
+  TimedScope* outer;  // enclosing scope of the calling thread
   TimedScope(int tag, cudaStream_t s);
   ~TimedScope();
 };
+// A launcher states the ALGORITHMIC bytes of the launch it just enqueued (the tensors it reads and writes once each --
+// SURVEY.md 8d -- not what the hardware moved): credited to the innermost timed scope of the calling thread, no-op
+// when timing is off. bench.py divides these by the scope's event time for its roofline line.
+void timed_bytes(double bytes);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -22,11 +22,13 @@ void set_error(const char* fmt, ...) {
 // ---- per-kernel timing ---------------------------------------------------------------------
 static std::atomic<int> g_timing{0};
 static std::mutex g_timing_mu;
-struct TimedRec { cudaEvent_t a, b; int tag; };
+struct TimedRec { cudaEvent_t a, b; int tag; double bytes; };
+static thread_local TimedScope* t_scope = nullptr;
 static std::vector<TimedRec> g_timed;
 constexpr size_t kMaxTimed = 1 << 16;
 
-TimedScope::TimedScope(int t, cudaStream_t s) : tag(t), stream(s), slot(-1) {
+TimedScope::TimedScope(int t, cudaStream_t s) : tag(t), stream(s), slot(-1), bytes(0.0), outer(t_scope) {
+  t_scope = this;
   if (!g_timing.load(std::memory_order_relaxed)) return;
   std::lock_guard<std::mutex> lk(g_timing_mu);
   if (g_timed.size() >= kMaxTimed) return;
@@ -39,9 +41,17 @@ TimedScope::TimedScope(int t, cudaStream_t s) : tag(t), stream(s), slot(-1) {
 }
 
 TimedScope::~TimedScope() {
+  t_scope = outer;
   if (slot < 0) return;
   std::lock_guard<std::mutex> lk(g_timing_mu);
-  if ((size_t)slot < g_timed.size()) cudaEventRecord(g_timed[slot].b, stream);
+  if ((size_t)slot < g_timed.size()) {
+    cudaEventRecord(g_timed[slot].b, stream);
+    g_timed[slot].bytes = bytes;
+  }
+}
+
+void timed_bytes(double b) {
+  if (t_scope && t_scope->slot >= 0) t_scope->bytes += b;
 }
 
 }  // namespace pdeqx
@@ -57,11 +67,11 @@ extern "C" void pdeqx_timing_enable(int enabled) {
   g_timing.store(enabled ? 1 : 0);
 }
 
-extern "C" int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launches) {
+extern "C" int pdeqx_timing_read_ex(int32_t tag, double* total_ms, int64_t* launches, double* algorithmic_bytes) {
   using namespace pdeqx;
   PDEQX_CHECK_ARG(total_ms && launches, "null argument");
   std::lock_guard<std::mutex> lk(g_timing_mu);
-  double tot = 0.0;
+  double tot = 0.0, bytes = 0.0;
   int64_t n = 0;
   for (auto& r : g_timed) {
     if (r.tag != tag) continue;
@@ -69,11 +79,17 @@ extern "C" int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launche
     float ms = 0.f;
     PDEQX_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
     tot += ms;
+    bytes += r.bytes;
     ++n;
   }
   *total_ms = tot;
   *launches = n;
+  if (algorithmic_bytes) *algorithmic_bytes = bytes;
   return PDEQX_OK;
+}
+
+extern "C" int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launches) {
+  return pdeqx_timing_read_ex(tag, total_ms, launches, nullptr);
 }
 
 extern "C" const char* pdeqx_last_error(void) { return pdeqx::t_error; }

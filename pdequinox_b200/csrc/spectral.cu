@@ -234,6 +234,7 @@ static int stage_c2r(const pdeqx_spectral_plan* p, const float* z, const float* 
   a.M = rows; a.N = sD; a.K = 2 * mD;
   a.lda_m = 2 * mD; a.lda_k = 1; a.ldb = sD; a.ldc = sD;
   a.batch = 1; a.act = act;
+  timed_bytes(4.0 * (double)rows * (2.0 * mD + sD + (add ? sD : 0)));
   return sgemm_batched(a, s);
 }
 

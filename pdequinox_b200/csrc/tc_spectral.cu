@@ -1206,6 +1206,19 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
 #undef PDEQX_SLAB_LAUNCH_B
 #undef PDEQX_SLAB_LAUNCH
   PDEQX_LAUNCHED();
+  {
+    // algorithmic bytes of this launch: every tensor it reads or writes, once
+    const double n_pix = (double)lead * sD, B = (double)d.batch;
+    double bytes = 4.0 * B * c_out * (double)lead * 32;                       // z
+    if (bypass) bytes += 4.0 * B * c_in * n_pix + 4.0 * c_in * c_out;         // x slab (+ bypass weight)
+    if (mode == 1) bytes += 4.0 * B * c_out * n_pix;                          // cotangent tile
+    if (mode == 2 || mode == 3 || mode == 5) bytes += 4.0 * B * n_pix;        // single-channel cotangent factor / field
+    if (byp1) bytes += 4.0 * B * n_pix;                                       // single-channel field behind the lifting
+    if (mode == 4) bytes += 4.0 * B * n_pix;                                  // projected field
+    else if (mode != 3) bytes += 4.0 * B * c_out * n_pix;                     // output tile
+    bytes += 4.0 * 32 * sD + 4.0 * c_out;                                     // table + bias
+    timed_bytes(bytes);
+  }
   return PDEQX_OK;
 }
 
