@@ -117,7 +117,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-allreduce", action="store_true", help="bucketed all-reduce on a side stream during the reverse pass")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
+    ap.add_argument("--print-source-sha", action="store_true", help="print the kernel-source hash that keys profiles/slab_traffic.csv and exit")
     a = ap.parse_args()
+    if a.print_source_sha:
+        os.write(_RESULT_FD, (kernel_source_sha() + "\n").encode())
+        raise SystemExit(0)
     a.cfg = CONFIGS[a.config]
     if a.global_batch <= 0:
         a.global_batch = a.cfg["global_batch"]
