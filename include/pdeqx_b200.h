@@ -187,6 +187,39 @@ int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* plan, const float* x,
                                 float* gw_re, float* gw_im, float* g_bypass_w, float* g_bypass_b,
                                 float* scratch_full, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The VJP with every argument named (what the FFI handler fills from its operand list), plus CHAINING of two consecutive
+ * ClassicSpectralBlocks of a Sequential (pdequinox/_sequential.py:111-116: block k-1's output is block k's input):
+ *  - up_plan != NULL: the last kernel of this block's reverse pass does not store gx; in the same pass over the tiles it
+ *    multiplies the input-gradient tile by act'(pre) of the UPSTREAM block (pre recomputed from up_saved_z, up_x and the
+ *    upstream bypass, exactly as that block's own cotangent pass would) and stores up_gpre [B, C, *S], the cotangent of
+ *    the upstream block's pre-activation. Needs pdeqx_spectral_block_chain_ok(plan, up_plan, up_activation) == 1 (tcgen05
+ *    path, same batch / grid, all channel counts equal, 32 or 64) and gx == NULL. up_x == NULL: the upstream block's
+ *    input was a folded 1 -> C lifting of up_lift_u (see pdeqx_spectral_block_fwd_ex).
+ *  - gy_is_gpre != 0: `gy` already IS the cotangent of this block's pre-activation (the up_gpre of the chained call made
+ *    for the block behind it): the activation-derivative pass is skipped; saved_z / scratch_full are not needed for it.
+ * Every field not used must be zero (initialise the struct with {0}). */
+typedef struct pdeqx_spectral_bwd_args {
+  const float *x, *gy, *gy_w, *lift_u;
+  float *lift_gw, *lift_gb;
+  const float *lift_w, *lift_b;
+  float* proj_gw;
+  const float *w_re, *w_im, *bypass_w, *bypass_b;
+  int32_t activation;
+  const float *saved_xhat, *saved_z;
+  float *gx, *gw_re, *gw_im, *g_bypass_w, *g_bypass_b, *scratch_full;
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+  int32_t gy_is_gpre;
+  const pdeqx_spectral_plan* up_plan;
+  const float *up_x, *up_saved_z, *up_bypass_w, *up_bypass_b;
+  int32_t up_activation;
+  const float *up_lift_u, *up_lift_w, *up_lift_b;
+  float* up_gpre;
+} pdeqx_spectral_bwd_args;
+int pdeqx_spectral_block_bwd_args(const pdeqx_spectral_plan* plan, const pdeqx_spectral_bwd_args* args);
+int pdeqx_spectral_block_chain_ok(const pdeqx_spectral_plan* plan, const pdeqx_spectral_plan* up_plan, int32_t up_activation);
+
 /* ------------------------------------------------------------------------- *
  * PointwiseLinearConv (1x1 conv)
  *   replaces pdequinox/conv/_pointwise_linear_conv.py:6-53 (eqx.nn.Conv, k=1)

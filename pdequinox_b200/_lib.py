@@ -45,6 +45,17 @@ class ConvTDesc(C.Structure):
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 
+
+class SpectralBwdArgs(C.Structure):
+    """pdeqx_spectral_bwd_args (include/pdeqx_b200.h): every argument of the spectral block's VJP, named."""
+    _fields_ = [("x", _P), ("gy", _P), ("gy_w", _P), ("lift_u", _P), ("lift_gw", _P), ("lift_gb", _P), ("lift_w", _P),
+                ("lift_b", _P), ("proj_gw", _P), ("w_re", _P), ("w_im", _P), ("bypass_w", _P), ("bypass_b", _P),
+                ("activation", C.c_int32), ("saved_xhat", _P), ("saved_z", _P), ("gx", _P), ("gw_re", _P), ("gw_im", _P),
+                ("g_bypass_w", _P), ("g_bypass_b", _P), ("scratch_full", _P), ("workspace", _P),
+                ("workspace_bytes", C.c_size_t), ("stream", _P), ("gy_is_gpre", C.c_int32), ("up_plan", _P), ("up_x", _P),
+                ("up_saved_z", _P), ("up_bypass_w", _P), ("up_bypass_b", _P), ("up_activation", C.c_int32),
+                ("up_lift_u", _P), ("up_lift_w", _P), ("up_lift_b", _P), ("up_gpre", _P)]
+
 # name -> (restype, argtypes); every symbol include/pdeqx_b200.h declares
 PROTOTYPES = {
     "pdeqx_last_error": (C.c_char_p, []),
@@ -67,6 +78,8 @@ PROTOTYPES = {
     "pdeqx_spectral_block_rank1_ok": (C.c_int, [_P, _I32, _I32]),
     "pdeqx_spectral_block_bwd_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
                                               _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_spectral_block_bwd_args": (C.c_int, [_P, C.POINTER(SpectralBwdArgs)]),
+    "pdeqx_spectral_block_chain_ok": (C.c_int, [_P, _P, _I32]),
     "pdeqx_spectral_block_fwd_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_pointwise_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_pointwise_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P]),

@@ -8,6 +8,9 @@ from .conv import PointwiseLinearConv
 
 class Sequential(Module):
     _fields = ("lifting", "blocks", "projection")
+    # reverse pass: let consecutive spectral blocks share the kernel between them (ClassicSpectralBlock.chain_with);
+    # False = every block runs its own cotangent and data-gradient passes (tests compare the two)
+    chain_reverse = True
 
     def __init__(self, num_spatial_dims, in_channels, out_channels, *, hidden_channels, num_blocks, activation, key,
                  boundary_mode, lifting_factory=None, block_factory=None, projection_factory=None):
@@ -97,6 +100,7 @@ class Sequential(Module):
             else:
                 g = self.projection._bwd(gy, tape, True)
             hook("projection.")
+        gpre_ready = False  # True: `g` is the cotangent of the next block's pre-activation (chained reverse pass)
         for i in reversed(range(nb)):
             kw = {}
             if fold_proj and i == nb - 1:
@@ -112,6 +116,21 @@ class Sequential(Module):
                 kw["lift"] = (u, lw, lb)
                 if lifted_fwd:
                     kw["lifted"] = (self.lifting.weight, self.lifting.bias)
+            # two consecutive spectral blocks share the pass between them: block i's last kernel hands block i-1 the
+            # cotangent of its PRE-activation, so block i's input gradient is never written (ClassicSpectralBlock.chain_with)
+            if gpre_ready:
+                kw["gy_is_gpre"] = True
+            gpre_ready = False
+            if i > 0 and self.chain_reverse and hasattr(self.blocks[i], "chain_with"):
+                up_rec = tape.stack[-2]
+                up_lifted = isinstance(up_rec, tuple) and len(up_rec) == 2 and up_rec[0] is None
+                chain = self.blocks[i].chain_with(self.blocks[i - 1], tape.stack[-1], up_rec,
+                                                  lifting=self.lifting if up_lifted else None,
+                                                  u=tape.stack[-3] if up_lifted else None) \
+                    if isinstance(up_rec, tuple) and len(up_rec) == 2 and isinstance(up_rec[1], tuple) else None
+                if chain is not None:
+                    kw["chain"] = chain
+                    gpre_ready = True
             if kw:
                 g = self.blocks[i]._bwd_ex(g, tape, True, **kw)
             else:

@@ -65,14 +65,33 @@ class ClassicSpectralBlock(Block):
     def _fwd_lifted(self, u, lifting, tape):
         return self._fwd_ex(u, tape, lifting=lifting)
 
-    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None, lifted=None, proj_gw=None):
+    def _bwd_ex(self, gy, tape, need_gx=True, gy_w=None, lift=None, lifted=None, proj_gw=None, gy_is_gpre=False, chain=None):
         """gy_w: `gy` is the single-channel factor of a rank-one cotangent; lift = (u, gw, gb): accumulate the gradients of
         the 1 -> C lifting that produced this block's input from `u` instead of returning the input gradient; proj_gw: the
-        forward pass was projected (`_fwd_ex(proj=...)`): also accumulate the projection's weight gradient."""
+        forward pass was projected (`_fwd_ex(proj=...)`): also accumulate the projection's weight gradient; gy_is_gpre / chain:
+        see `chain_with` (two consecutive blocks share the pass between them)."""
         x, saved = tape.pop()
         return self.spectral_conv.apply_bwd(x, gy, saved, tape, bypass=self.by_pass_conv,
                                             act=nn.activation_code(self.activation), need_gx=need_gx, gy_w=gy_w, lift=lift,
-                                            lifted=lifted if x is None else None, proj_gw=proj_gw)
+                                            lifted=lifted if x is None else None, proj_gw=proj_gw, gy_is_gpre=gy_is_gpre,
+                                            chain=chain)
+
+    def chain_with(self, up, my_record, up_record, lifting=None, u=None):
+        """Description of the block `up` IN FRONT of this one (pdequinox/_sequential.py:111-116) for a chained reverse pass,
+        or None if the two do not qualify: this block's data-gradient kernel then also applies act'(pre) of `up`, so the
+        tensor between the two blocks' reverse passes is never written or read. `*_record` = what the blocks' forward passes
+        pushed on the tape; `lifting` / `u`: `up` ran with a folded lifting of the field `u` (its record holds x = None)."""
+        from .. import _lib
+        if not isinstance(up, ClassicSpectralBlock) or up.by_pass_conv is None or self.by_pass_conv is None:
+            return None
+        (_, (plan, _, _)), (up_x, up_saved) = my_record, up_record
+        act_up = nn.activation_code(up.activation)
+        if up_x is None and (lifting is None or u is None):
+            return None
+        if not _lib.lib().pdeqx_spectral_block_chain_ok(plan.handle, up_saved[0].handle, act_up):
+            return None
+        return dict(conv=up.spectral_conv, x=up_x, saved=up_saved, bypass=up.by_pass_conv, act=act_up, u=u,
+                    lifted=(lifting.weight, lifting.bias) if up_x is None else None)
 
 
 class ClassicSpectralBlockFactory(BlockFactory):

@@ -154,40 +154,55 @@ class SpectralConv(Module):
         return bool(L.pdeqx_spectral_block_rank1_ok(plan.handle, 1, act)) and (L.pdeqx_spectral_plan_tcgen05_stages(plan.handle) & 1) == 1
 
     def apply_bwd(self, x, gy, saved, tape, *, bypass=None, act=_lib.ACT_IDENTITY, need_gx=True, gy_w=None, lift=None,
-                  lifted=None, proj_gw=None):
-        """VJP. With `gy_w` the cotangent is rank one: gy_w[o] * gy[b, 0, *S] (what a C -> 1 pointwise projection sends
-        back); it is then formed inside the kernel instead of being materialised. With `lift = (u, gw, gb)` the input
-        gradient is not stored: the gradients gw, gb of the 1 -> C pointwise lifting that made x from the field u are
-        accumulated instead (pdeqx_spectral_block_bwd_ex). With `lifted = (lift_w, lift_b)` the forward pass was
-        `apply_lifted`: x is None and the reverse pass works from u alone. With `proj_gw` (needs `gy_w`) the forward pass was
-        `apply_ex(..., proj=...)`: the projection's weight gradient is accumulated into it from the recomputed activation."""
+                  lifted=None, proj_gw=None, gy_is_gpre=False, chain=None):
+        """VJP (pdeqx_spectral_block_bwd_args). With `gy_w` the cotangent is rank one: gy_w[o] * gy[b, 0, *S] (what a C -> 1
+        pointwise projection sends back); it is then formed inside the kernel instead of being materialised. With
+        `lift = (u, gw, gb)` the input gradient is not stored: the gradients gw, gb of the 1 -> C pointwise lifting that made
+        x from the field u are accumulated instead. With `lifted = (lift_w, lift_b)` the forward pass was `apply_lifted`: x is
+        None and the reverse pass works from u alone. With `proj_gw` (needs `gy_w`) the forward pass was
+        `apply_ex(..., proj=...)`: the projection's weight gradient is accumulated into it from the recomputed activation.
+        `gy_is_gpre`: gy already is the cotangent of this block's pre-activation (produced by the chained call of the block
+        behind it). `chain = dict(conv, x, saved, bypass, act, lifted, u)` describes the spectral block IN FRONT of this one:
+        instead of this block's input gradient, the cotangent of that block's pre-activation is formed in the same pass and
+        returned (it lives in that block's own `gpre` buffer)."""
         plan, xhat, z = saved
         ref = x if x is not None else lift[0]
-        gx = new_buf(tape, self, "gx", x.shape) if (need_gx and lift is None) else None
+        gx = new_buf(tape, self, "gx", x.shape) if (need_gx and lift is None and chain is None) else None
         full = (ref.shape[0], self.call_out_channels) + tuple(ref.shape[2:])
-        scratch = new_buf(tape, self, "gpre", full) if act != _lib.ACT_IDENTITY else None
-        bw = bypass.weight if bypass is not None else None
-        bb = bypass.bias if bypass is not None else None
-        gbw = bypass.grad("weight") if bypass is not None else None
-        gbb = bypass.grad("bias") if (bypass is not None and bypass.bias is not None) else None
-        if gy_w is not None or lift is not None:
-            u, lgw, lgb = lift if lift is not None else (None, None, None)
-            if lift is not None:
-                gx = None
-            lw, lb = lifted if lifted is not None else (None, None)
-            _lib.check(_lib.lib().pdeqx_spectral_block_bwd_ex(
-                plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(gy_w), _lib.ptr(u), _lib.ptr(lgw), _lib.ptr(lgb),
-                _lib.ptr(lw), _lib.ptr(lb), _lib.ptr(proj_gw), _lib.ptr(self.weights_real),
-                _lib.ptr(self.weights_imag), _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),
-                _lib.ptr(self.grad("weights_real")), _lib.ptr(self.grad("weights_imag")), _lib.ptr(gbw), _lib.ptr(gbb),
-                _lib.ptr(scratch), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))
-            return gx
-        _lib.check(_lib.lib().pdeqx_spectral_block_bwd(
-            plan.handle, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(self.weights_real), _lib.ptr(self.weights_imag),
-            _lib.ptr(bw), _lib.ptr(bb), act, _lib.ptr(xhat), _lib.ptr(z), _lib.ptr(gx),
-            _lib.ptr(self.grad("weights_real")), _lib.ptr(self.grad("weights_imag")), _lib.ptr(gbw), _lib.ptr(gbb),
-            _lib.ptr(scratch), _lib.ptr(plan.workspace), plan.ws_bytes, _lib.stream()))
-        return gx
+        scratch = new_buf(tape, self, "gpre", full) if (act != _lib.ACT_IDENTITY and not gy_is_gpre) else None
+        a = _lib.SpectralBwdArgs()
+        P = _lib.ptr
+        a.x, a.gy, a.gy_w, a.proj_gw = P(x), P(gy), P(gy_w), P(proj_gw)
+        if lift is not None:
+            a.lift_u, a.lift_gw, a.lift_gb = P(lift[0]), P(lift[1]), P(lift[2])
+        if lifted is not None:
+            a.lift_w, a.lift_b = P(lifted[0]), P(lifted[1])
+        a.w_re, a.w_im = P(self.weights_real), P(self.weights_imag)
+        if bypass is not None:
+            a.bypass_w, a.bypass_b = P(bypass.weight), P(bypass.bias)
+            a.g_bypass_w = P(bypass.grad("weight"))
+            a.g_bypass_b = P(bypass.grad("bias")) if bypass.bias is not None else None
+        a.activation = act
+        a.saved_xhat, a.saved_z, a.gx = P(xhat), P(z), P(gx)
+        a.gw_re, a.gw_im = P(self.grad("weights_real")), P(self.grad("weights_imag"))
+        a.scratch_full = P(scratch)
+        a.workspace, a.workspace_bytes, a.stream = P(plan.workspace), plan.ws_bytes, _lib.stream()
+        a.gy_is_gpre = 1 if gy_is_gpre else 0
+        out = gx
+        if chain is not None:
+            up = chain["conv"]
+            up_plan, _, up_z = chain["saved"]
+            up_ref = chain["x"] if chain["x"] is not None else chain["u"]
+            up_gpre = new_buf(tape, up, "gpre", (up_ref.shape[0], up.call_out_channels) + tuple(up_ref.shape[2:]))
+            a.up_plan, a.up_x, a.up_saved_z = up_plan.handle, P(chain["x"]), P(up_z)
+            a.up_bypass_w, a.up_bypass_b = P(chain["bypass"].weight), P(chain["bypass"].bias)
+            a.up_activation = chain["act"]
+            if chain["x"] is None:
+                a.up_lift_u, a.up_lift_w, a.up_lift_b = P(chain["u"]), P(chain["lifted"][0]), P(chain["lifted"][1])
+            a.up_gpre = P(up_gpre)
+            out = up_gpre
+        _lib.check(_lib.lib().pdeqx_spectral_block_bwd_args(plan.handle, C.byref(a)))
+        return out
 
     def _fwd(self, x, tape):
         y, saved = self.apply(x, tape, save=tape is not None)

@@ -506,13 +506,19 @@ extern "C" int pdeqx_spectral_block_fwd_ex(const pdeqx_spectral_plan* p, const f
 // lift_u != null: gx is not produced; the block's input came from the single-channel field lift_u through a 1 -> c_in
 // pointwise lifting, whose gradients lift_gw[i] = sum gx[b,i,pixel] lift_u[b,pixel], lift_gb[i] = sum gx[b,i,pixel] are
 // accumulated by the last kernel instead
-static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x, const float* gy, const float* gy_w,
-                                   const float* lift_u, float* lift_gw, float* lift_gb, const float* lift_w,
-                                   const float* lift_b, float* proj_gw, const float* w_re, const float* w_im, const float* bypass_w,
-                                   const float* bypass_b, int32_t act, const float* saved_xhat,
-                                   const float* saved_z, float* gx, float* gw_re, float* gw_im,
-                                   float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spectral_bwd_args& a) {
+  const float *x = a.x, *gy = a.gy, *gy_w = a.gy_w, *lift_u = a.lift_u, *lift_w = a.lift_w, *lift_b = a.lift_b;
+  float *lift_gw = a.lift_gw, *lift_gb = a.lift_gb, *proj_gw = a.proj_gw;
+  const float *w_re = a.w_re, *w_im = a.w_im, *bypass_w = a.bypass_w, *bypass_b = a.bypass_b;
+  const int32_t act = a.activation;
+  const float *saved_xhat = a.saved_xhat, *saved_z = a.saved_z;
+  float *gx = a.gx, *gw_re = a.gw_re, *gw_im = a.gw_im, *g_bypass_w = a.g_bypass_w, *g_bypass_b = a.g_bypass_b;
+  float* scratch_full = a.scratch_full;
+  void* workspace = a.workspace;
+  const size_t workspace_bytes = a.workspace_bytes;
+  void* stream = a.stream;
+  const bool chained = a.up_plan != nullptr;      // the data-gradient pass also forms the upstream block's pre-activation cotangent
+  const bool gy_is_gpre = a.gy_is_gpre != 0;      // the downstream block's chained pass already applied act'(pre) of THIS block
   PDEQX_CHECK_ARG(p && (x || (lift_u && lift_w)) && gy && w_re && w_im && saved_xhat && gw_re && gw_im, "null argument");
   PDEQX_CHECK_ARG(act >= 0 && act <= 2, "unknown activation %d", act);
   PDEQX_CHECK_ARG(!bypass_w || g_bypass_w, "g_bypass_w is required when bypass_w is given");
@@ -532,6 +538,14 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   const bool fast = tc_slab_available(p, bypass_w != nullptr);
   const float* gpre = gy;
   bool gx_has_bypass = false;
+  PDEQX_CHECK_ARG(!gy_is_gpre || (!gy_w && !proj_gw), "gy_is_gpre excludes the rank-one cotangent arguments");
+  if (chained) {
+    PDEQX_CHECK_ARG(!gx && !lift_u, "a chained reverse pass writes up_gpre instead of gx");
+    PDEQX_CHECK_ARG(fast && bypass_w && tc_chain_available(p, a.up_plan) && a.up_saved_z && a.up_gpre && a.up_bypass_w &&
+                        (a.up_x || (a.up_lift_u && a.up_lift_w && a.up_plan->lift_scratch)) &&
+                        (a.up_activation == PDEQX_ACT_RELU || a.up_activation == PDEQX_ACT_GELU_TANH),
+                    "the chained reverse pass does not qualify (pdeqx_spectral_block_chain_ok)");
+  }
   const bool fuse_bypass_gx = fast && bypass_w && gx;
   bool r2c_done = false;
   const int chunk = bwd_chunk_samples(p, n_pix);
@@ -541,7 +555,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   if (proj_gw) PDEQX_CUDA(cudaMemsetAsync(proj_gw, 0, sizeof(float) * (size_t)d.c_out, s));
   PDEQX_CHECK_ARG(!gy_w || (fast && act != PDEQX_ACT_IDENTITY),
                   "a rank-1 cotangent needs the tcgen05 slab kernel and a fused activation (pdeqx_spectral_block_rank1_ok)");
-  if (!gy_w && !lifted && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
+  if (!gy_is_gpre && !gy_w && !lifted && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
     // Steps 1-3a in sample chunks small enough for the 126 MB L2: the cotangent chunk written by the slab kernel is
     // still L2-resident when the bypass weight gradient and the first DFT stage read it back, and so is most of x.
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
@@ -570,7 +584,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
     r2c_done = true;
   } else {
   // 1. cotangent of the pre-activation (pre-activation recomputed from the saved z: nothing full-size is kept)
-  if (act != PDEQX_ACT_IDENTITY) {
+  if (act != PDEQX_ACT_IDENTITY && !gy_is_gpre) {
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
     if (lifted) {
       float* fa = p->lift_scratch;
@@ -632,7 +646,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   // 4. weight gradient (batch-reduced inside the kernel)
   PDEQX_TRY(mode_mix_dw(p, ghat, saved_xhat, gw_re, gw_im, s));
   PDEQX_CHECK_ARG(!lift_u || (fast && bypass_w), "the fused lifting gradients need the tcgen05 slab kernel (pdeqx_spectral_block_rank1_ok)");
-  if (!gx && !lift_u) return PDEQX_OK;
+  if (!gx && !lift_u && !chained) return PDEQX_OK;
   // 5. g_xhat = W^H g_yhat
   float* gxhat = r.mode[1];
   PDEQX_TRY(mode_mix(p, ghat, w_re, w_im, /*transposed_conj=*/true, gxhat, s));
@@ -644,6 +658,20 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
     gx1 = t;
   }
   // 7. last stage back to real space, plus the bypass contribution W^T gpre
+  if (chained) {
+    // ... and, in the same pass, times act'(pre) of the block in front of this one: this block's input gradient only ever
+    // exists as an accumulator tile; what is written is the upstream block's pre-activation cotangent
+    TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
+    if (!a.up_x) {
+      float* fa = a.up_plan->lift_scratch;
+      float* fc = a.up_plan->lift_scratch + 128;
+      lift_fold_bypass_kernel<<<(d.c_in + 127) / 128, 128, 0, s>>>(a.up_bypass_w, a.up_bypass_b, a.up_lift_w, a.up_lift_b, d.c_in,
+                                                                  a.up_plan->desc.c_in, fa, fc);
+      PDEQX_LAUNCHED();
+      return tc_chain(p, gpre, gx1, bypass_w, a.up_plan, nullptr, a.up_saved_z, nullptr, fc, a.up_activation, a.up_gpre, s, a.up_lift_u, fa);
+    }
+    return tc_chain(p, gpre, gx1, bypass_w, a.up_plan, a.up_x, a.up_saved_z, a.up_bypass_w, a.up_bypass_b, a.up_activation, a.up_gpre, s);
+  }
   if (fast && lift_u) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     PDEQX_CUDA(cudaMemsetAsync(lift_gw, 0, sizeof(float) * (size_t)d.c_in, s));
@@ -658,14 +686,28 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const float* x,
   return stage_c2r(p, gx1, p->t_c2r_bwd, rows_i, gx_has_bypass ? gx : nullptr, PDEQX_ACT_IDENTITY, gx, s);
 }
 
+extern "C" int pdeqx_spectral_block_bwd_args(const pdeqx_spectral_plan* p, const pdeqx_spectral_bwd_args* args) {
+  PDEQX_CHECK_ARG(args, "null argument");
+  PDEQX_CHECK_ARG(!args->lift_u || (args->lift_gw && !args->gx), "lift_u needs lift_gw and replaces gx");
+  return spectral_block_bwd_impl(p, *args);
+}
+
+extern "C" int pdeqx_spectral_block_chain_ok(const pdeqx_spectral_plan* p, const pdeqx_spectral_plan* up, int32_t up_activation) {
+  return (up_activation == PDEQX_ACT_RELU || up_activation == PDEQX_ACT_GELU_TANH) && tc_chain_available(p, up) ? 1 : 0;
+}
+
 extern "C" int pdeqx_spectral_block_bwd(const pdeqx_spectral_plan* p, const float* x, const float* gy,
                                         const float* w_re, const float* w_im, const float* bypass_w,
                                         const float* bypass_b, int32_t act, const float* saved_xhat,
                                         const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                         float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                         size_t workspace_bytes, void* stream) {
-  return spectral_block_bwd_impl(p, x, gy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, w_re, w_im, bypass_w, bypass_b, act, saved_xhat, saved_z, gx, gw_re, gw_im,
-                                 g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes, stream);
+  pdeqx_spectral_bwd_args a{};
+  a.x = x; a.gy = gy; a.w_re = w_re; a.w_im = w_im; a.bypass_w = bypass_w; a.bypass_b = bypass_b; a.activation = act;
+  a.saved_xhat = saved_xhat; a.saved_z = saved_z; a.gx = gx; a.gw_re = gw_re; a.gw_im = gw_im;
+  a.g_bypass_w = g_bypass_w; a.g_bypass_b = g_bypass_b; a.scratch_full = scratch_full;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = stream;
+  return spectral_block_bwd_impl(p, a);
 }
 
 extern "C" int pdeqx_spectral_block_rank1_ok(const pdeqx_spectral_plan* p, int32_t has_bypass, int32_t act) {
@@ -680,9 +722,12 @@ extern "C" int pdeqx_spectral_block_bwd_ex(const pdeqx_spectral_plan* p, const f
                                            const float* saved_z, float* gx, float* gw_re, float* gw_im,
                                            float* g_bypass_w, float* g_bypass_b, float* scratch_full, void* workspace,
                                            size_t workspace_bytes, void* stream) {
-  PDEQX_CHECK_ARG(!lift_u || (lift_gw && !gx), "lift_u needs lift_gw and replaces gx");
-  return spectral_block_bwd_impl(p, x, gy, gy_w, lift_u, lift_gw, lift_gb, lift_w, lift_b, proj_gw, w_re, w_im, bypass_w, bypass_b, act,
-                                 saved_xhat,
-                                 saved_z, gx, gw_re, gw_im, g_bypass_w, g_bypass_b, scratch_full, workspace, workspace_bytes,
-                                 stream);
+  pdeqx_spectral_bwd_args a{};
+  a.x = x; a.gy = gy; a.gy_w = gy_w; a.lift_u = lift_u; a.lift_gw = lift_gw; a.lift_gb = lift_gb; a.lift_w = lift_w;
+  a.lift_b = lift_b; a.proj_gw = proj_gw;
+  a.w_re = w_re; a.w_im = w_im; a.bypass_w = bypass_w; a.bypass_b = bypass_b; a.activation = act;
+  a.saved_xhat = saved_xhat; a.saved_z = saved_z; a.gx = gx; a.gw_re = gw_re; a.gw_im = gw_im;
+  a.g_bypass_w = g_bypass_w; a.g_bypass_b = g_bypass_b; a.scratch_full = scratch_full;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = stream;
+  return pdeqx_spectral_block_bwd_args(p, &a);
 }

@@ -67,6 +67,11 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
                float* y, cudaStream_t s, const float* aux_w = nullptr, float* red_w = nullptr, float* red_b = nullptr,
                const float* byp_u = nullptr, const float* byp_a = nullptr);
+// the data-gradient pass of block `p` fused with the pre-activation-cotangent pass of the block `up` in front of it
+bool tc_chain_available(const pdeqx_spectral_plan* p, const pdeqx_spectral_plan* up);
+int tc_chain(const pdeqx_spectral_plan* p, const float* g, const float* z1, const float* w_k, const pdeqx_spectral_plan* up,
+             const float* x_up, const float* z_up, const float* w_up, const float* bias_up, int act, float* out, cudaStream_t s,
+             const float* byp_u = nullptr, const float* byp_a = nullptr);
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);
 // gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller)
 int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb,

@@ -361,6 +361,7 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     // single-channel fields read per pixel (the rank-one factors): loaded ONE UNIT AHEAD -- this stage is latency bound and a
     // dependent global load at the top of every unit would sit on its critical path
     constexpr bool kUsesAux1 = MODE == 2 || MODE == 3 || MODE == 5;
+    constexpr bool kRoundOut = (MODE == 0 && ACT != PDEQX_ACT_IDENTITY) || MODE == 1 || MODE == 2 || MODE == 5;
     auto field_index = [&](const Coord& c) -> int64_t {
       return ((int64_t)c.b * p.lead + c.li * p.rpu + l_off) * p.W + pxw + lane;
     };
@@ -481,6 +482,10 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             else if (ACT == PDEQX_ACT_RELU) r = val > 0.f ? g[j] : 0.f;
             else r = g[j];
           }
+          // what this kernel stores is read next as a tcgen05 operand (the activated output by the next block's bypass and
+          // first-DFT-stage MMAs, the cotangent by the weight-gradient and data-gradient MMAs), and the tensor core TRUNCATES
+          // fp32 to tf32 (a bias of about -2^-12 per operand that adds up coherently through the layers): round to nearest here
+          if (kRoundOut) r = round_tf32(r);
           st_shared_f32(row0 + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
         }
       };
@@ -555,6 +560,283 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           if (p.red_b) atomicAdd(p.red_b + ch, vb);
         }
       }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ==========================================================================================
+// chain kernel: the data-gradient pass of block k FUSED with the pre-activation-cotangent pass of block k-1
+//
+//   gx_k[b,c,l,w]    = sum_kk Z'_k[b,c,l,kk] Tb[kk,w] + sum_o W_k[o,c] g_k[b,o,l,w]              (accumulator 1)
+//   pre_{k-1}[b,c,l,w] = sum_kk Z_{k-1}[b,c,l,kk] Ti[kk,w] + sum_i W_{k-1}[c,i] x_{k-1}[b,i,l,w] + bias (accumulator 2)
+//   g_{k-1}[b,c,l,w] = gx_k * act'(pre_{k-1})                                                     (epilogue, stored)
+//
+// gx_k (= the cotangent gy_{k-1} of the upstream block's output) is never written to HBM and never read back: per
+// block boundary one full-size tensor write and one read disappear (2 of the 7 tensor passes a block's reverse pass made).
+// Every operand layout is the slab kernel's: two load sub-stages per unit ([g_k slab | Z'_k] then [x_{k-1} slab | Z_{k-1}])
+// walk through one ring; both accumulators of a unit sit side by side in TMEM (2 x C columns, double buffered).
+// All four channel counts are equal (C <= 64). BYP1: the upstream block's input is the 1 -> C lifting of a single-channel
+// field (rank-one bypass in the epilogue, no x slab in its sub-stage).
+// ==========================================================================================
+struct ChainParams {
+  int lead, W, wt_per_row, C;
+  int rpu, stages;
+  int64_t units;
+  const float* bias;   // upstream block: bypass bias (BYP1: the folded constant part)
+  const float* byp_u;  // BYP1: single-channel field [B, lead, W]
+  const float* byp_a;  // BYP1: per-channel factor
+};
+
+struct ChainSmem {
+  uint32_t tab1_off, tab2_off, w1_off, w2_off, stage_off, stage_bytes, x_box_bytes, z_off_in_stage, epi_off, chunk_bytes, bar_off, total;
+};
+
+static ChainSmem chain_smem(int W, int C, int stages) {
+  ChainSmem s{};
+  uint32_t off = 0;
+  const uint32_t rpu = W >= 128 ? 1 : 128 / W;
+  s.tab1_off = off;
+  off += rpu * 128 * 128;
+  s.tab2_off = off;
+  off += rpu * 128 * 128;
+  const uint32_t wbytes = (uint32_t)((C + 31) / 32) * C * 128;
+  s.w1_off = off;
+  off += wbytes;
+  s.w2_off = off;
+  off += wbytes;
+  s.x_box_bytes = (uint32_t)C * 128;
+  s.z_off_in_stage = 4 * s.x_box_bytes;
+  s.stage_bytes = (s.z_off_in_stage + rpu * (uint32_t)C * 128 + 1023) & ~1023u;
+  s.stage_off = off;
+  off += s.stage_bytes * stages;
+  s.epi_off = off;  // ONE output tile [C x 128 w] as four SWIZZLE_128B chunks [C rows x 32 w]
+  s.chunk_bytes = (uint32_t)C * 128;
+  off += 4 * s.chunk_bytes;
+  s.bar_off = off;
+  off += 2048;
+  s.total = off + 1024;
+  return s;
+}
+
+template <int ACT, bool BYP1>
+__global__ void __launch_bounds__(kThreadsSlab, 1)
+chain_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_z1,
+             const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_z2,
+             const __grid_constant__ CUtensorMap tm_tab1, const __grid_constant__ CUtensorMap tm_tab2,
+             const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+             const __grid_constant__ CUtensorMap tm_y, ChainParams p, ChainSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* full = bars;          // [stages]
+  uint64_t* empty = bars + 8;     // [stages]
+  uint64_t* tfull = bars + 16;    // [2]
+  uint64_t* tempty = bars + 18;   // [2]
+  uint64_t* tabfull = bars + 20;  // [1]
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 22);
+  float* bias_s = (float*)(bars + 24);  // [C] (<= 64 floats)
+  float* bypa_s = bias_s + 64;          // [C]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const int C = p.C;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_z1);
+    tma_prefetch_desc(&tm_x2);
+    tma_prefetch_desc(&tm_z2);
+    tma_prefetch_desc(&tm_tab1);
+    tma_prefetch_desc(&tm_tab2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 16);
+    mbar_init(&tempty[1], 16);
+    mbar_init(tabfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 3) {
+    for (int i = lane; i < C; i += 32) {
+      bias_s[i] = p.bias ? p.bias[i] : 0.f;
+      bypa_s[i] = (BYP1 && p.byp_a) ? p.byp_a[i] : 0.f;
+    }
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_w1);
+      tma_prefetch_desc(&tm_w2);
+      tma_prefetch_desc(&tm_y);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int wchunks = (C + 31) / 32;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(tabfull, 2u * (uint32_t)p.rpu * 128 * 128 + (BYP1 ? 1u : 2u) * (uint32_t)wchunks * C * 128);
+      const int wt0 = (int)(first % p.wt_per_row);
+      for (int c = 0; c < p.rpu; ++c) {
+        tma_load_2d(smem + L.tab1_off + c * 128 * 128, &tm_tab1, tabfull, 0, (wt0 + c) * 128);
+        tma_load_2d(smem + L.tab2_off + c * 128 * 128, &tm_tab2, tabfull, 0, (wt0 + c) * 128);
+      }
+      for (int c = 0; c < wchunks; ++c) {
+        tma_load_2d(smem + L.w1_off + c * C * 128, &tm_w1, tabfull, c * 32, 0);
+        if (!BYP1) tma_load_2d(smem + L.w2_off + c * C * 128, &tm_w2, tabfull, c * 32, 0);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      const int lu = p.lead / p.rpu;
+      for (int64_t u = first; u < p.units; u += stride) {
+        const int wt = (int)(u % p.wt_per_row);
+        const int64_t bl = u / p.wt_per_row;
+        const int l = (int)(bl % lu) * p.rpu;
+        const int b = (int)(bl / lu);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const bool has_x = half == 0 || !BYP1;
+          mbar_wait_backoff(&empty[s], ph ^ 1);
+          uint8_t* st = smem + L.stage_off + (size_t)s * L.stage_bytes;
+          mbar_expect_tx(&full[s], (has_x ? 4 * L.x_box_bytes : 0) + (uint32_t)p.rpu * C * 128);
+          if (has_x)
+            for (int j = 0; j < 4; ++j) {
+              const int px = wt * 128 + j * 32;
+              tma_load_3d(st + j * L.x_box_bytes, half == 0 ? &tm_g : &tm_x2, &full[s], px % p.W, l + px / p.W, b * C);
+            }
+          for (int c = 0; c < p.rpu; ++c)
+            tma_load_3d(st + L.z_off_in_stage + c * C * 128, half == 0 ? &tm_z1 : &tm_z2, &full[s], 0, l + c, b * C);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_kk = idesc_tf32(128, C, false, false);
+      const uint32_t idesc_mk = idesc_tf32(128, C, true, false);
+      mbar_wait(tabfull, 0);
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      const uint64_t kk0 = smem_desc_sw128(0, 0, 1024);
+      const uint64_t mk0 = smem_desc_sw128_atom32(0, L.x_box_bytes, 512);
+      const uint32_t kk_hi = (uint32_t)(kk0 >> 32), kk_lo = (uint32_t)kk0, mk_hi = (uint32_t)(mk0 >> 32), mk_lo = (uint32_t)mk0;
+      const uint32_t tab_lo[2] = {kk_lo + (smem_u32(smem + L.tab1_off) >> 4), kk_lo + (smem_u32(smem + L.tab2_off) >> 4)};
+      const uint32_t w_lo[2] = {kk_lo + (smem_u32(smem + L.w1_off) >> 4), kk_lo + (smem_u32(smem + L.w2_off) >> 4)};
+      const uint32_t st16_0 = smem_u32(smem + L.stage_off) >> 4, stage16 = L.stage_bytes >> 4, z16 = L.z_off_in_stage >> 4;
+      const uint32_t cbox16 = (uint32_t)C * 128 >> 4;
+      const int ksteps = C / 8;
+      for (int64_t u = first; u < p.units; u += stride) {
+        mbar_wait(&tempty[a], aph ^ 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(a * 2 * C + half * C);
+          const uint32_t st16 = st16_0 + (uint32_t)s * stage16;
+          for (int c = 0; c < p.rpu; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_tf32_lohi(d, tab_lo[half] + (uint32_t)c * (128 * 128 >> 4) + k * 2, kk_hi,
+                            kk_lo + st16 + z16 + (uint32_t)c * cbox16 + k * 2, kk_hi, idesc_kk, (c | k) ? 1u : 0u);
+          if (half == 0 || !BYP1)
+            for (int k = 0; k < ksteps; ++k)
+              mma_tf32_lohi(d, mk_lo + st16 + (uint32_t)k * (1024 >> 4), mk_hi, w_lo[half] + (uint32_t)(k >> 2) * cbox16 + (k & 3) * 2,
+                            kk_hi, idesc_mk, 1u);
+          mma_commit(&empty[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        mma_commit(&tfull[a]);
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: two accumulators -> g = acc1 * act'(acc2 + bias) -> smem piece -> TMA store =====================
+    const int q = warp & 3;
+    const int part = (warp - 4) >> 2;
+    const int ncol = C / 4;  // 16 (C = 64) or 8 (C = 32)
+    const uint32_t bias_sa = smem_u32(bias_s), bypa_sa = smem_u32(bypa_s);
+    uint8_t* piece = smem + L.epi_off + (size_t)q * L.chunk_bytes + (size_t)part * ncol * 128;
+    const uint32_t col = smem_u32(piece);
+    int a = 0;
+    uint32_t aph = 0;
+    const int lu = p.lead / p.rpu;
+    const int px = (int)(first % p.wt_per_row) * 128 + q * 32;
+    const int pxw = px % p.W, l_off = px / p.W;
+    const int64_t dbl = stride / p.wt_per_row;
+    const int adv_b = (int)(dbl / lu), adv_l = (int)(dbl % lu);
+    int cli = (int)((first / p.wt_per_row) % lu), cb = (int)((first / p.wt_per_row) / lu);
+    int nli = cli + adv_l, nb = cb + adv_b;
+    if (nli >= lu) { nli -= lu; ++nb; }
+    float su_next = 0.f;
+    if (BYP1 && first < p.units) su_next = __ldg(p.byp_u + ((int64_t)cb * p.lead + cli * p.rpu + l_off) * p.W + pxw + lane);
+    const uint32_t lane_b = (uint32_t)lane * 4;
+    for (int64_t u = first; u < p.units; u += stride) {
+      const int l = cli * p.rpu + l_off;
+      const int b = cb;
+      const float su = su_next;
+      if (BYP1 && u + stride < p.units) su_next = __ldg(p.byp_u + ((int64_t)nb * p.lead + nli * p.rpu + l_off) * p.W + pxw + lane);
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+      if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has read the piece
+      __syncwarp();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 2 * C + part * ncol);
+      auto chunk = [&](auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;
+        float v1[16], v2[16];
+        tmem_ld16(t0, v1);
+        tmem_ld16(t0 + (uint32_t)C, v2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
+        const uint32_t cidx = (uint32_t)(part * ncol) * 4;
+        float bias_c[NC], bypa_c[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j += 4) {
+          ld_shared_const_v4(bias_sa + cidx + j * 4, bias_c + j);
+          if (BYP1) ld_shared_const_v4(bypa_sa + cidx + j * 4, bypa_c + j);
+        }
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          float pre = v2[j] + bias_c[j];
+          if (BYP1) pre = fmaf(bypa_c[j], su, pre);
+          float r;
+          if (ACT == PDEQX_ACT_GELU_TANH) r = v1[j] * gelu_grad_f<true>(pre);
+          else r = pre > 0.f ? v1[j] : 0.f;
+          r = round_tf32(r);  // read next as a tcgen05 operand (weight gradient, data gradient): round, do not let it truncate
+          st_shared_f32(col + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
+        }
+      };
+      if (ncol == 16) chunk(std::integral_constant<int, 16>{});
+      else chunk(std::integral_constant<int, 8>{});
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tm_y, piece, pxw, l, b * C + part * ncol);
+        tma_store_commit();
+      }
+      if (++a == 2) { a = 0; aph ^= 1; }
+      cli = nli;
+      cb = nb;
+      nli += adv_l;
+      nb += adv_b;
+      if (nli >= lu) { nli -= lu; ++nb; }
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -931,6 +1213,7 @@ struct TcPlan {
   float* tab_r2c[2] = {nullptr, nullptr};  // [32][s_D]  (n-major rows, K contiguous): forward / adjoint-of-inverse
   float* tab_c2r[2] = {nullptr, nullptr};  // [s_D][32]  (w rows, K contiguous): inverse / adjoint-of-forward
   float* w_prep = nullptr;                 // rounded (transposed) bypass weight
+  float* w_prep2 = nullptr;                // second one: the chain kernel holds the weights of two blocks
   CUtensorMap tm_tab_r2c[2], tm_tab_c2r[2];
   int slab_stages = 0;
 };
@@ -997,6 +1280,7 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
   }
   const int cmax = d.c_in > d.c_out ? d.c_in : d.c_out;
   if (rc == PDEQX_OK && cudaMalloc((void**)&t->w_prep, (size_t)cmax * cmax * 4) != cudaSuccess) rc = PDEQX_ERR_CUDA;
+  if (rc == PDEQX_OK && cudaMalloc((void**)&t->w_prep2, (size_t)cmax * cmax * 4) != cudaSuccess) rc = PDEQX_ERR_CUDA;
   if (rc != PDEQX_OK) {
     set_error("tcgen05 plan setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     p->tc = t;
@@ -1028,6 +1312,7 @@ void tc_plan_free(pdeqx_spectral_plan* p) {
     cudaFree(t->tab_c2r[v]);
   }
   cudaFree(t->w_prep);
+  cudaFree(t->w_prep2);
   delete t;
   p->tc = nullptr;
 }
@@ -1227,6 +1512,128 @@ int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int ta
   const pdeqx_spectral_desc& d = p->desc;
   const int c_in = bypass_transposed ? d.c_out : d.c_in, c_out = bypass_transposed ? d.c_in : d.c_out;
   return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+
+// ---- chain: data gradient of block `p` fused with the pre-activation cotangent of the block `up` in front of it ----
+static int chain_mode() {  // PDEQX_CHAIN=0 switches the fusion off (A/B measurements)
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PDEQX_CHAIN");
+    env = e ? atoi(e) : 1;
+  }
+  return env;
+}
+
+bool tc_chain_available(const pdeqx_spectral_plan* p, const pdeqx_spectral_plan* up) {
+  if (!p || !up || !chain_mode() || !tc_slab_available(p, true) || !tc_slab_available(up, true)) return false;
+  const pdeqx_spectral_desc &a = p->desc, &b = up->desc;
+  if (a.ndim != b.ndim || a.batch != b.batch || p->lead != up->lead) return false;
+  for (int i = 0; i < a.ndim; ++i)
+    if (a.spatial[i] != b.spatial[i]) return false;
+  const int C = a.c_in;
+  if (a.c_out != C || b.c_in != C || b.c_out != C || (C != 32 && C != 64)) return false;
+  return tc::chain_smem(a.spatial[a.ndim - 1], C, 2).total <= 227 * 1024;
+}
+
+// out[B, C, lead, W] = ( c2r_adj(z1) + w_k^T . g ) * act'( c2r_inv(z_up) + w_up . x_up + bias_up )
+//   byp_u / byp_a (x_up == null): the upstream block's bypass term is rank one, byp_a[c] * byp_u[b, pixel] (+ bias_up)
+int tc_chain(const pdeqx_spectral_plan* p, const float* g, const float* z1, const float* w_k, const pdeqx_spectral_plan* up,
+             const float* x_up, const float* z_up, const float* w_up, const float* bias_up, int act, float* out, cudaStream_t s,
+             const float* byp_u, const float* byp_a) {
+  TcPlan* t = tcp(p);
+  TcPlan* tu = tcp(up);
+  const pdeqx_spectral_desc& d = p->desc;
+  const int D = d.ndim, sD = d.spatial[D - 1], C = d.c_in;
+  const int64_t lead = p->lead;
+  const bool byp1 = x_up == nullptr;
+  PDEQX_CHECK_ARG(tc_chain_available(p, up), "tc_chain: the two blocks do not qualify for the fused pass");
+  PDEQX_CHECK_ARG(g && z1 && w_k && z_up && out && (byp1 ? (byp_u && byp_a) : (w_up != nullptr)), "tc_chain: null argument");
+  PDEQX_CHECK_ARG(act == PDEQX_ACT_RELU || act == PDEQX_ACT_GELU_TANH, "tc_chain: the upstream block needs an activation");
+  PDEQX_CHECK_ARG((((uintptr_t)g | (uintptr_t)z1 | (uintptr_t)z_up | (uintptr_t)out | (uintptr_t)x_up) & 15) == 0,
+                  "tc_chain: pointers must be 16-byte aligned");
+  CUtensorMap tm_g, tm_z1, tm_x2, tm_z2, tm_w1, tm_w2, tm_y;
+  {
+    uint64_t dims[3] = {32, (uint64_t)lead, (uint64_t)d.batch * C};
+    uint64_t str[2] = {32 * 4, (uint64_t)lead * 32 * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)C};
+    PDEQX_TRY(tc::make_tensor_map(&tm_z1, z1, 3, dims, str, box));
+    PDEQX_TRY(tc::make_tensor_map(&tm_z2, z_up, 3, dims, str, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)sD, (uint64_t)lead, (uint64_t)d.batch * C};
+    uint64_t str[2] = {(uint64_t)sD * 4, (uint64_t)lead * sD * 4};
+    uint32_t box[3] = {32, 1, (uint32_t)C};
+    PDEQX_TRY(tc::make_tensor_map(&tm_g, g, 3, dims, str, box, tc::TM_SW128_ATOM32));
+    if (!byp1) PDEQX_TRY(tc::make_tensor_map(&tm_x2, x_up, 3, dims, str, box, tc::TM_SW128_ATOM32));
+    else tm_x2 = tm_g;
+    uint32_t ybox[3] = {32, 1, (uint32_t)(C / 4)};
+    PDEQX_TRY(tc::make_tensor_map(&tm_y, out, 3, dims, str, ybox));
+  }
+  {
+    const int n = C * C;
+    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_k, t->w_prep, C, C, 1);  // w_k^T: [c_in rows][c_out]
+    PDEQX_LAUNCHED();
+    uint64_t wd[2] = {(uint64_t)C, (uint64_t)C};
+    uint64_t ws[1] = {(uint64_t)C * 4};
+    uint32_t wb[2] = {32, (uint32_t)C};
+    PDEQX_TRY(tc::make_tensor_map(&tm_w1, t->w_prep, 2, wd, ws, wb));
+    if (!byp1) {
+      tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_up, t->w_prep2, C, C, 0);
+      PDEQX_LAUNCHED();
+      PDEQX_TRY(tc::make_tensor_map(&tm_w2, t->w_prep2, 2, wd, ws, wb));
+    } else {
+      tm_w2 = tm_w1;
+    }
+  }
+  tc::ChainParams cp{};
+  cp.lead = (int)lead;
+  cp.W = sD;
+  cp.C = C;
+  cp.rpu = sD >= 128 ? 1 : 128 / sD;
+  cp.wt_per_row = sD >= 128 ? sD / 128 : 1;
+  cp.units = (int64_t)d.batch * (lead / cp.rpu) * cp.wt_per_row;
+  cp.bias = bias_up;
+  cp.byp_u = byp_u;
+  cp.byp_a = byp_a;
+  int stages = 0;
+  for (int st = 4; st >= 2; --st)
+    if (tc::chain_smem(sD, C, st).total <= 227 * 1024) { stages = st; break; }
+  PDEQX_CHECK_ARG(stages >= 2, "tc_chain: shared memory does not fit two load stages");
+  cp.stages = stages;
+  tc::ChainSmem L = tc::chain_smem(sD, C, stages);
+  int grid = (int)(cp.units < t->sms ? cp.units : t->sms);
+  grid = grid / cp.wt_per_row * cp.wt_per_row;
+  PDEQX_CHECK_ARG(grid >= cp.wt_per_row, "tc_chain: grid smaller than the number of w-tiles");
+#define PDEQX_CHAIN_LAUNCH(A, B1)                                                                                          \
+  do {                                                                                                                     \
+    static bool attr = false;                                                                                              \
+    if (!attr) {                                                                                                           \
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::chain_kernel<A, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
+      attr = true;                                                                                                         \
+    }                                                                                                                      \
+    tc::chain_kernel<A, B1><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_g, tm_z1, tm_x2, tm_z2, t->tm_tab_c2r[1],          \
+                                                                     tu->tm_tab_c2r[0], tm_w1, tm_w2, tm_y, cp, L);        \
+  } while (0)
+  if (act == PDEQX_ACT_GELU_TANH) {
+    if (byp1) PDEQX_CHAIN_LAUNCH(PDEQX_ACT_GELU_TANH, true);
+    else PDEQX_CHAIN_LAUNCH(PDEQX_ACT_GELU_TANH, false);
+  } else {
+    if (byp1) PDEQX_CHAIN_LAUNCH(PDEQX_ACT_RELU, true);
+    else PDEQX_CHAIN_LAUNCH(PDEQX_ACT_RELU, false);
+  }
+#undef PDEQX_CHAIN_LAUNCH
+  PDEQX_LAUNCHED();
+  {
+    const double n_pix = (double)lead * sD, B = (double)d.batch;
+    double bytes = 2 * 4.0 * B * C * (double)lead * 32;           // both z tensors
+    bytes += 4.0 * B * C * n_pix;                                 // g_k
+    bytes += byp1 ? 4.0 * B * n_pix : 4.0 * B * C * n_pix;        // upstream input (or the single-channel field behind it)
+    bytes += 4.0 * B * C * n_pix;                                 // g_{k-1}
+    bytes += 2 * 4.0 * 32 * sD + 2 * 4.0 * C * C + 4.0 * C;
+    timed_bytes(bytes);
+  }
+  return PDEQX_OK;
 }
 
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix) {

@@ -170,3 +170,41 @@ def test_tf32_folded_forward_equals_plain_forward(cuda, spatial, hidden, blocks,
         assert rel_l2(folded, ref) <= TOL
     finally:
         pdeqx.set_precision("fp32")
+
+
+@pytest.mark.parametrize("D,spatial,hidden,modes,blocks,fold", [
+    (2, (64, 128), 32, 16, 3, True),     # lifted first block (rank-one bypass in the chained pass), projected last block
+    (2, (32, 256), 64, 16, 3, False),    # plain chain: every block reads its stored input
+    (3, (32, 32, 64), 32, 12, 2, True),  # two image rows per unit
+])
+def test_tf32_chained_reverse_pass_equals_unchained(cuda, D, spatial, hidden, modes, blocks, fold):
+    """The chained reverse pass (data gradient of block k and pre-activation cotangent of block k-1 in ONE kernel: the tensor
+    between them is never written) gives the gradients of the block-by-block reverse pass; the only arithmetic difference is
+    that the input gradient stays in the fp32 accumulator instead of taking a round trip through HBM."""
+    from pdequinox_b200._module import Tape
+    from pdequinox_b200._sequential import Sequential
+    from pdequinox_b200 import _lib
+    pdeqx.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(17)
+        model = pdeqx.ClassicFNO(D, 1, 1, hidden_channels=hidden, num_modes=modes, num_blocks=blocks, key=6)
+        arena = ParameterArena(model)
+        x = dev(rng.standard_normal((2, 1) + spatial))
+        gy = dev(rng.standard_normal((2, 1) + spatial))
+        grads = {}
+        for chained in (False, True):
+            Sequential.chain_reverse = chained
+            tape = Tape()
+            tape.fold_lifting = fold
+            arena.grads.zero_()
+            before = _lib.lib().pdeqx_launch_count()
+            model._fwd(x, tape)
+            model._bwd(gy, tape, False)
+            torch.cuda.synchronize()
+            grads[chained] = ({k: host(v).copy() for k, v in arena.named_grads().items()}, _lib.lib().pdeqx_launch_count() - before)
+        assert grads[True][1] < grads[False][1], "the chained reverse pass did not run (same number of kernel launches)"
+        for k in grads[False][0]:
+            assert rel_l2(grads[True][0][k], grads[False][0][k]) <= 5e-4, k
+    finally:
+        Sequential.chain_reverse = True
+        pdeqx.set_precision("fp32")
