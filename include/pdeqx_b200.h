@@ -14,9 +14,15 @@
  *     void*): no synchronisation, no allocation; scratch memory is passed in;
  *   - return value 0 = ok, negative = error (PDEQX_ERR_*); the message of the
  *     last error on the calling thread is pdeqx_last_error();
- *   - the library keeps no mutable global state besides plan objects owned by
- *     the caller. Plans are immutable after creation and may be shared by
- *     threads/streams of the same device.
+ *   - the library keeps no mutable state between calls: plans are immutable after
+ *     creation (twiddle tables only) and may be shared by threads / streams of
+ *     their device; every scratch buffer, including the small per-call ones
+ *     (re-laid-out weights, partial sums), is carved from the workspace the
+ *     caller passes, so calls are re-entrant as long as concurrent calls bring
+ *     different workspaces. What IS process-wide: the per-device "kernel
+ *     attribute configured" / "cluster launch unsupported" capability caches,
+ *     the launch counter, the timing recorder (pdeqx_timing_enable) and the
+ *     test switch pdeqx_set_fast_paths -- none of them changes results.
  */
 #ifndef PDEQX_B200_H_
 #define PDEQX_B200_H_
@@ -249,14 +255,17 @@ typedef struct {
   int32_t dilation[PDEQX_MAX_DIMS];
   int32_t pad_lo[PDEQX_MAX_DIMS], pad_hi[PDEQX_MAX_DIMS];
   int32_t boundary; /* enum pdeqx_boundary */
+  int32_t precision; /* enum pdeqx_precision: PDEQX_PREC_FP32 (CUDA-core fp32, every shape) or PDEQX_PREC_TF32 (tcgen05
+                        implicit GEMM for the shapes that qualify: 2-D, k = 3, stride 1, W = 128, C = 64; fp32 otherwise) */
 } pdeqx_conv_desc;
 
-/* arithmetic of the convolution kernels for the calling process: PDEQX_PREC_FP32 (default; CUDA-core fp32) or
- * PDEQX_PREC_TF32 (tcgen05 implicit GEMM for the shapes that qualify: 2-D, k = 3, stride 1, W = 128, C = 32 / 64) */
-void pdeqx_set_conv_precision(int32_t precision);
-/* which passes of this convolution run on tcgen05 under the current settings
- * (bit 0: forward, bit 1: data gradient, bit 2: filter gradient); 0 = CUDA-core fp32 path */
+/* which passes of this convolution run on tcgen05 (bit 0: forward, bit 1: data gradient, bit 2: filter gradient);
+ * 0 = CUDA-core fp32 path */
 int pdeqx_conv_tcgen05_passes(const pdeqx_conv_desc* d);
+/* bytes of caller-provided scratch the three passes below need (re-laid-out filter + per-CTA partial filter gradients
+ * of the tcgen05 passes; 0 for the CUDA-core path, where `workspace` may be NULL). The calls keep nothing between
+ * launches: one workspace per stream makes them re-entrant. */
+size_t pdeqx_conv_workspace_bytes(const pdeqx_conv_desc* d);
 /* how many forward / data-gradient launches of this process took the CTA-pair kernel (tcgen05 cta_group::2: two CTAs of one
  * TPC share one N = 192 MMA, each holding half of the filter): the C = 64 shapes whose row chains split into equal segments.
  * A diagnostic for tests and profiles; the one-CTA kernel covers the rest. */
@@ -265,14 +274,15 @@ int64_t pdeqx_conv_pair_launches(void);
 int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]);
 /* y = act(corr(pad(x), w) + b + residual); w [c_out, c_in/groups, *k]; b [c_out]; b, residual may be NULL */
 int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b,
-                   const float* residual, int32_t activation, float* y, void* stream);
+                   const float* residual, int32_t activation, float* y, void* workspace, size_t workspace_bytes,
+                   void* stream);
 /* gx = adjoint-of-pad( corr^T(gy, w) ) + add, overwritten; add [B,c_in,*S] may be NULL (it carries
  * the cotangent of a residual connection into the same pass) */
 int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add,
-                        float* gx, void* stream);
+                        float* gx, void* workspace, size_t workspace_bytes, void* stream);
 /* gw[c_out,c_in/groups,*k] = sum_{b,p} gy . pad(x); gb[c_out] = sum gy (may be NULL); overwritten */
 int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, float* gw,
-                          float* gb, void* stream);
+                          float* gb, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * PhysicsConvTranspose / MorePaddingConvTranspose (ClassicUNet up-sampling)

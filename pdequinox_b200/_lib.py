@@ -31,7 +31,8 @@ class ConvDesc(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("batch", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32),
                 ("groups", C.c_int32), ("spatial", C.c_int32 * MAX_DIMS), ("kernel", C.c_int32 * MAX_DIMS),
                 ("stride", C.c_int32 * MAX_DIMS), ("dilation", C.c_int32 * MAX_DIMS),
-                ("pad_lo", C.c_int32 * MAX_DIMS), ("pad_hi", C.c_int32 * MAX_DIMS), ("boundary", C.c_int32)]
+                ("pad_lo", C.c_int32 * MAX_DIMS), ("pad_hi", C.c_int32 * MAX_DIMS), ("boundary", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 class ConvTDesc(C.Structure):
@@ -83,13 +84,13 @@ PROTOTYPES = {
     "pdeqx_spectral_block_fwd_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_pointwise_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _I32, _P, _P]),
     "pdeqx_pointwise_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P]),
-    "pdeqx_set_conv_precision": (None, [_I32]),
+    "pdeqx_conv_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
     "pdeqx_conv_tcgen05_passes": (C.c_int, [C.POINTER(ConvDesc)]),
     "pdeqx_conv_pair_launches": (C.c_int64, []),
     "pdeqx_conv_out_spatial": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
-    "pdeqx_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I32, _P, _P]),
-    "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
-    "pdeqx_conv_bwd_filter": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
+    "pdeqx_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I32, _P, _P, C.c_size_t, _P]),
+    "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_conv_bwd_filter": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_convT_out_spatial": (C.c_int, [C.POINTER(ConvTDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
     "pdeqx_convT_fwd": (C.c_int, [C.POINTER(ConvTDesc), _P, _P, _P, _P, _P]),
     "pdeqx_convT_bwd_data": (C.c_int, [C.POINTER(ConvTDesc), _P, _P, _P, _P]),

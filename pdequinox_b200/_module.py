@@ -24,8 +24,7 @@ def set_precision(mode: str):
     global _precision
     if mode not in _PRECISION:
         raise ValueError(f"precision must be one of {list(_PRECISION)}, got {mode}")
-    _precision = mode
-    _lib.lib().pdeqx_set_conv_precision(_PRECISION[mode])
+    _precision = mode  # read when a call builds its descriptor / plan: the library itself holds no precision state
 
 
 def get_precision() -> str:
@@ -67,6 +66,17 @@ class Tape:
 
     def pop(self):
         return self.stack.pop()
+
+
+_CONV_WORKSPACE_OWNER = object()  # every conv call of one tape (= one stream) shares one scratch buffer
+
+
+def conv_workspace(tape, nbytes):
+    """Scratch for the tcgen05 conv passes (pdeqx_conv_workspace_bytes): one persistent buffer per tape (a tape serves one
+    stream at a time, and the passes keep nothing in it between launches); a fresh one per call outside a tape."""
+    if nbytes == 0:
+        return None
+    return new_buf(tape, _CONV_WORKSPACE_OWNER, "conv_ws", ((nbytes + 3) // 4,))
 
 
 def new_buf(tape, owner, tag, shape):

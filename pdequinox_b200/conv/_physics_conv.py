@@ -10,7 +10,7 @@ import math
 import numpy as np
 
 from .. import _lib, random as jr
-from .._module import Module, new_buf, to_param
+from .._module import Module, conv_workspace, new_buf, precision_code, to_param
 
 
 def _ntuple(v, n, name):
@@ -79,6 +79,7 @@ class MorePaddingConv(Module):
         d.pad_lo = _lib.ivec([p[0] for p in self.padding], 0)
         d.pad_hi = _lib.ivec([p[1] for p in self.padding], 0)
         d.boundary = _PADDING_MODES[self.padding_mode]
+        d.precision = precision_code()
         out = (_lib.C.c_int32 * _lib.MAX_DIMS)()
         _lib.check(_lib.lib().pdeqx_conv_out_spatial(d, out))
         return d, tuple(out[a] for a in range(D))
@@ -86,21 +87,25 @@ class MorePaddingConv(Module):
     def apply(self, x, tape, *, residual=None, act=_lib.ACT_IDENTITY, tag="y"):
         d, out_sp = self._desc(x)
         y = new_buf(tape, self, tag, (x.shape[0], self.out_channels) + out_sp)
+        nws = _lib.lib().pdeqx_conv_workspace_bytes(d)
         _lib.check(_lib.lib().pdeqx_conv_fwd(d, _lib.ptr(x), _lib.ptr(self.weight), _lib.ptr(self.bias),
-                                             _lib.ptr(residual), act, _lib.ptr(y), _lib.stream()))
+                                             _lib.ptr(residual), act, _lib.ptr(y), _lib.ptr(conv_workspace(tape, nws)), nws,
+                                             _lib.stream()))
         return y
 
     def apply_bwd(self, x, gy, tape, need_gx=True, tag="gx", add=None):
         d, _ = self._desc(x)
         L = _lib.lib()
         gb = self.grad("bias") if self.bias is not None else None
+        nws = L.pdeqx_conv_workspace_bytes(d)
+        ws = _lib.ptr(conv_workspace(tape, nws))
         _lib.check(L.pdeqx_conv_bwd_filter(d, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(self.grad("weight")), _lib.ptr(gb),
-                                           _lib.stream()))
+                                           ws, nws, _lib.stream()))
         if not need_gx:
             return None
         gx = new_buf(tape, self, tag, x.shape)
         _lib.check(L.pdeqx_conv_bwd_data(d, _lib.ptr(gy), _lib.ptr(self.weight), _lib.ptr(add), _lib.ptr(gx),
-                                         _lib.stream()))
+                                         ws, nws, _lib.stream()))
         return gx
 
     def _fwd(self, x, tape):

@@ -69,6 +69,18 @@ void timed_bytes(double bytes);
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Function attributes (the 227 KB dynamic shared-memory opt-in) are per DEVICE: a launcher keeps one of these per kernel
+// and configures the kernel on the first launch on every device of the process.
+struct DeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool first_use() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const uint64_t bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+  }
+};
+
 // ---- activations (device) -------------------------------------------------
 // tanh via exp: |err| ~ 1e-7 (fp32 parity mode needs better than tanh.approx's 2^-11)
 __device__ __forceinline__ float tanh_accurate(float u) {

@@ -369,6 +369,7 @@ int conv_geometry(const pdeqx_conv_desc* d, ConvGeom* out) {
   PDEQX_CHECK_ARG(d->c_in % d->groups == 0, "`in_channels` (=%d) must be divisible by `groups` (=%d).", d->c_in, d->groups);
   PDEQX_CHECK_ARG(d->c_out % d->groups == 0, "out_channels (=%d) must be divisible by groups (=%d)", d->c_out, d->groups);
   PDEQX_CHECK_ARG(d->boundary >= PDEQX_PAD_ZEROS && d->boundary <= PDEQX_PAD_EDGE, "unknown boundary %d", d->boundary);
+  PDEQX_CHECK_ARG(d->precision == PDEQX_PREC_FP32 || d->precision == PDEQX_PREC_TF32, "unknown precision %d", d->precision);
   ConvGeom g{};
   g.ndim = d->ndim;
   g.batch = d->batch;
@@ -376,6 +377,7 @@ int conv_geometry(const pdeqx_conv_desc* d, ConvGeom* out) {
   g.c_out = d->c_out;
   g.groups = d->groups;
   g.boundary = d->boundary;
+  g.precision = d->precision;
   g.taps = 1;
   g.n_in = 1;
   g.n_out = 1;
@@ -435,10 +437,10 @@ static inline int grid_for(int64_t total) {
 int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w, float* gx, cudaStream_t s) {
   const size_t wbytes = sizeof(float) * ((size_t)g.taps * g.c_out * g.c_in + kMirWarps * kMirPairs * 64);
   if (g.ndim == 2 && g.groups == 1 && g.c_in == 64 && g.c_out == 64 && wbytes <= 220 * 1024) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;      
+    if (attr.first_use()) {
       PDEQX_CUDA(cudaFuncSetAttribute(conv_bwd_data_mirror2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr = true;
+                  
     }
     conv_bwd_data_mirror2d_kernel<<<148, kMirWarps * 32, wbytes, s>>>(g, gy, w, gx);
     PDEQX_LAUNCHED();
@@ -463,6 +465,12 @@ extern "C" int pdeqx_conv_tcgen05_passes(const pdeqx_conv_desc* d) {
   return (tc_conv_available(g) ? 1 : 0) | (tc_conv_bwd_data_available(g) ? 2 : 0) | (tc_conv_bwd_filter_available(g) ? 4 : 0);
 }
 
+extern "C" size_t pdeqx_conv_workspace_bytes(const pdeqx_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geometry(d, &g) != PDEQX_OK) return 0;
+  return tc_conv_workspace_bytes(g);
+}
+
 extern "C" int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_MAX_DIMS]) {
   ConvGeom g;
   PDEQX_TRY(conv_geometry(d, &g));
@@ -471,14 +479,15 @@ extern "C" int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spat
 }
 
 extern "C" int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b,
-                              const float* residual, int32_t activation, float* y, void* stream) {
+                              const float* residual, int32_t activation, float* y, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(x && w && y, "null argument");
   PDEQX_CHECK_ARG(activation >= 0 && activation <= 2, "unknown activation %d", activation);
   ConvGeom g;
   PDEQX_TRY(conv_geometry(d, &g));
   if (g.batch == 0) return PDEQX_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (tc_conv_available(g)) return tc_conv_fwd(g, x, w, b, residual, activation, y, s);
+  if (tc_conv_available(g)) return tc_conv_fwd(g, x, w, b, residual, activation, y, workspace, workspace_bytes, s);
   const int cog = g.c_out / g.groups;
   const int64_t total = (int64_t)g.batch * g.groups * ceil_div(cog, kOPT) * g.n_out;
   TimedScope timed(PDEQX_K_CONV_FWD, s);
@@ -488,7 +497,7 @@ extern "C" int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const fl
 }
 
 extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add, float* gx,
-                                   void* stream) {
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(gy && w && gx, "null argument");
   ConvGeom g;
   PDEQX_TRY(conv_geometry(d, &g));
@@ -498,7 +507,7 @@ extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, co
     return PDEQX_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (tc_conv_bwd_data_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, s);
+  if (tc_conv_bwd_data_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, workspace, workspace_bytes, s);
   const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
   conv_bwd_data_kernel<false><<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
   PDEQX_LAUNCHED();
@@ -506,7 +515,7 @@ extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, co
 }
 
 extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, float* gw, float* gb,
-                                     void* stream) {
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(x && gy && gw, "null argument");
   ConvGeom g;
   PDEQX_TRY(conv_geometry(d, &g));
@@ -515,7 +524,7 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
   if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
   if (g.batch == 0) return PDEQX_OK;
-  if (tc_conv_bwd_filter_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, s);
+  if (tc_conv_bwd_filter_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, workspace, workspace_bytes, s);
   const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
   const int64_t chunks = ceil_div(g.n_out, WF_P);
   const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;

@@ -6,7 +6,7 @@
 namespace pdeqx {
 
 struct ConvGeom {
-  int ndim, batch, c_in, c_out, groups, boundary, taps, max_pre;
+  int ndim, batch, c_in, c_out, groups, boundary, taps, max_pre, precision;
   int spatial[PDEQX_MAX_DIMS], out[PDEQX_MAX_DIMS];
   int kernel[PDEQX_MAX_DIMS], stride[PDEQX_MAX_DIMS], dilation[PDEQX_MAX_DIMS];
   int pad_lo[PDEQX_MAX_DIMS], pad_hi[PDEQX_MAX_DIMS];
@@ -23,9 +23,13 @@ int conv_bwd_data_mirror_part(const ConvGeom& g, const float* gy, const float* w
 bool tc_conv_available(const ConvGeom& g);
 bool tc_conv_bwd_data_available(const ConvGeom& g);
 bool tc_conv_bwd_filter_available(const ConvGeom& g);
+// scratch of the tcgen05 passes (0 when the geometry does not take them): re-laid-out filter + partial filter gradients
+size_t tc_conv_workspace_bytes(const ConvGeom& g);
 int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* residual, int act,
-                float* y, cudaStream_t s);
-int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, cudaStream_t s);
-int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, cudaStream_t s);
+                float* y, void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, void* ws, size_t ws_bytes,
+                     cudaStream_t s);
+int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws, size_t ws_bytes,
+                       cudaStream_t s);
 
 }  // namespace pdeqx

@@ -300,11 +300,11 @@ static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
 #define PDEQX_MODE_GEMM(RT_)                                                                                            \
   do {                                                                                                                 \
     const size_t smem = (size_t)(RT_ == 1 ? 4 : (RT_ == 2 ? 3 : 2)) * TM_KC * (8 * RT_ + nt) * PT * sizeof(float2);    \
-    static bool attr = false;                                                                                          \
-    if (!attr) {                                                                                                       \
+    static DeviceOnce attr;                                                                                                \
+    if (attr.first_use()) {                                                                                                       \
       cudaFuncSetAttribute(mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B>,                                \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                                    \
-      attr = true;                                                                                                     \
+                                                                                                                       \
     }                                                                                                                  \
     mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, smem, s>>>(t);                            \
   } while (0)

@@ -165,8 +165,10 @@ extern "C" int pdeqx_spectral_plan_create(const pdeqx_spectral_desc* desc, pdeqx
   for (int a = 0; a < D - 1; ++a) lead_max *= (desc->spatial[a] > p->n2[a] ? desc->spatial[a] : p->n2[a]);
   p->stage_floats = 2 * (int64_t)desc->batch * cmax * lead_max * mP;
   p->mode_floats = (2 * (int64_t)desc->batch * cmax * J + 63) / 64 * 64;
-  p->ws_bytes = (size_t)(2 * p->stage_floats + 2 * p->mode_floats) * sizeof(float) + 256;
-  if (cudaMalloc((void**)&p->lift_scratch, sizeof(float) * 4 * 128) != cudaSuccess) p->lift_scratch = nullptr;
+  // + the per-call scratch of the tcgen05 stages (two re-laid-out bypass weights, folded lifting factors): the plan itself
+  // stays immutable, so one plan can serve several streams as long as each call brings its own workspace
+  p->small_floats = 2 * cmax * cmax + 512;
+  p->ws_bytes = (size_t)(2 * p->stage_floats + 2 * p->mode_floats + p->small_floats) * sizeof(float) + 256;
   rc = tc_plan_init(p);  // builds the tcgen05-side operand tables when the shape qualifies
   if (rc == PDEQX_OK) rc = tc_c2c_plan_init(p);
   if (rc != PDEQX_OK) {
@@ -189,7 +191,6 @@ extern "C" void pdeqx_spectral_plan_destroy(pdeqx_spectral_plan* p) {
     cudaFree(p->t_inv_adj[a]);
     cudaFree(p->t_fwd_adj[a]);
   }
-  cudaFree(p->lift_scratch);
   tc_plan_free(p);
   tc_c2c_plan_free(p);
   delete p;
@@ -317,6 +318,8 @@ __global__ void lift_unfold_wgrad_kernel(const float* __restrict__ s1, const flo
 struct Regions {
   float* big[2];
   float* mode[2];
+  float* wprep[2];  // tf32-rounded (transposed) bypass weights of the tcgen05 stages
+  float* lift;      // 4 x 128 floats: folded factors / partial reductions of a pointwise lifting in front of the block
 };
 
 // x_hat[B, C, J] <- x[B, C, *S]. Intermediates live in r.big[]; src/dst must not alias them.
@@ -394,6 +397,10 @@ static Regions make_regions(const pdeqx_spectral_plan* p, void* ws) {
   r.big[1] = r.big[0] + p->stage_floats;
   r.mode[0] = r.big[1] + p->stage_floats;
   r.mode[1] = r.mode[0] + p->mode_floats;
+  const int64_t cmax = p->desc.c_in > p->desc.c_out ? p->desc.c_in : p->desc.c_out;
+  r.wprep[0] = r.mode[1] + p->mode_floats;
+  r.wprep[1] = r.wprep[0] + cmax * cmax;
+  r.lift = r.wprep[1] + cmax * cmax;
   return r;
 }
 
@@ -425,7 +432,7 @@ static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x,
   float* xhat = save_xhat ? save_xhat : r.mode[0];
   const bool lifted = lift_u != nullptr;
   if (lifted) {
-    PDEQX_CHECK_ARG(lift_w && bypass_w && D >= 2 && p->lift_scratch && d.c_in <= 128 && d.c_out <= 128 &&
+    PDEQX_CHECK_ARG(lift_w && bypass_w && D >= 2 && d.c_in <= 128 && d.c_out <= 128 &&
                         tc_slab_available(p, true) && tc_r2c_available(p) && p->mlast == 16,
                     "the lifted forward pass needs the tcgen05 path (pdeqx_spectral_block_rank1_ok) and a bypass");
     // first stage of the single-channel field, then its lifting (the DFT is linear; the bias only feeds column k = 0)
@@ -460,21 +467,21 @@ static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x,
     PDEQX_LAUNCHED();
   }
   if (lifted) {
-    float* fa = p->lift_scratch;       // a[o]: per-channel factor of the rank-one bypass
-    float* fc = p->lift_scratch + 128;  // c[o]: its constant part (+ bypass bias)
+    float* fa = r.lift;       // a[o]: per-channel factor of the rank-one bypass
+    float* fc = r.lift + 128;  // c[o]: its constant part (+ bypass bias)
     lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
     PDEQX_LAUNCHED();
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-    return tc_slab_ex(p, nullptr, z, /*table_sel=*/0, nullptr, false, fc, act, /*mode=*/projected ? 4 : 0, nullptr, d.c_in, d.c_out,
+    return tc_slab_ex(p, r.wprep[0], nullptr, z, /*table_sel=*/0, nullptr, false, fc, act, /*mode=*/projected ? 4 : 0, nullptr, d.c_in, d.c_out,
                       projected ? proj_out : y, s, projected ? proj_w : nullptr, nullptr, nullptr, lift_u, fa);
   }
   if (projected) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-    return tc_slab_ex(p, x, z, /*table_sel=*/0, bypass_w, false, bypass_b, act, /*mode=*/4, nullptr, d.c_in, d.c_out, proj_out, s, proj_w);
+    return tc_slab_ex(p, r.wprep[0], x, z, /*table_sel=*/0, bypass_w, false, bypass_b, act, /*mode=*/4, nullptr, d.c_in, d.c_out, proj_out, s, proj_w);
   }
   if (tc_slab_available(p, bypass_w != nullptr)) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-    return tc_slab(p, x, z, /*table_sel=*/0, bypass_w, /*bypass_transposed=*/false, bypass_b, act, y, s);
+    return tc_slab(p, r.wprep[0], x, z, /*table_sel=*/0, bypass_w, /*bypass_transposed=*/false, bypass_b, act, y, s);
   }
   if (!bypass_w) return stage_c2r(p, z, p->t_c2r_inv, rows, nullptr, act, y, s);
   PDEQX_TRY(stage_c2r(p, z, p->t_c2r_inv, rows, nullptr, PDEQX_ACT_IDENTITY, y, s));
@@ -542,14 +549,14 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
   if (chained) {
     PDEQX_CHECK_ARG(!gx && !lift_u, "a chained reverse pass writes up_gpre instead of gx");
     PDEQX_CHECK_ARG(fast && bypass_w && tc_chain_available(p, a.up_plan) && a.up_saved_z && a.up_gpre && a.up_bypass_w &&
-                        (a.up_x || (a.up_lift_u && a.up_lift_w && a.up_plan->lift_scratch)) &&
+                        (a.up_x || (a.up_lift_u && a.up_lift_w)) &&
                         (a.up_activation == PDEQX_ACT_RELU || a.up_activation == PDEQX_ACT_GELU_TANH),
                     "the chained reverse pass does not qualify (pdeqx_spectral_block_chain_ok)");
   }
   const bool fuse_bypass_gx = fast && bypass_w && gx;
   bool r2c_done = false;
   const int chunk = bwd_chunk_samples(p, n_pix);
-  PDEQX_CHECK_ARG(!lifted || (fast && act != PDEQX_ACT_IDENTITY && bypass_w && p->lift_scratch && lift_gw),
+  PDEQX_CHECK_ARG(!lifted || (fast && act != PDEQX_ACT_IDENTITY && bypass_w && lift_gw),
                   "the lifted reverse pass needs the tcgen05 slab kernel, a fused activation and a bypass");
   PDEQX_CHECK_ARG(!proj_gw || (gy_w && d.c_out <= 64), "proj_gw needs the rank-one cotangent (gy_w) and c_out <= 64");
   if (proj_gw) PDEQX_CUDA(cudaMemsetAsync(proj_gw, 0, sizeof(float) * (size_t)d.c_out, s));
@@ -571,7 +578,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
       const int64_t off_z = (int64_t)b0 * d.c_out * p->lead * 2 * mD;
       {
         TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-        PDEQX_TRY(tc_slab_ex(&pc, x + off_i, saved_z + off_z, 0, bypass_w, false, bypass_b, act, /*mode=*/1, gy + off_o,
+        PDEQX_TRY(tc_slab_ex(&pc, r.wprep[0], x + off_i, saved_z + off_z, 0, bypass_w, false, bypass_b, act, /*mode=*/1, gy + off_o,
                              d.c_in, d.c_out, scratch_full + off_o, s));
       }
       {
@@ -587,19 +594,19 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
   if (act != PDEQX_ACT_IDENTITY && !gy_is_gpre) {
     PDEQX_CHECK_ARG(saved_z && scratch_full, "saved_z and scratch_full are required when an activation is fused");
     if (lifted) {
-      float* fa = p->lift_scratch;
-      float* fc = p->lift_scratch + 128;
+      float* fa = r.lift;
+      float* fc = r.lift + 128;
       lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
       PDEQX_LAUNCHED();
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-      PDEQX_TRY(tc_slab_ex(p, nullptr, saved_z, 0, nullptr, false, fc, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
+      PDEQX_TRY(tc_slab_ex(p, r.wprep[0], nullptr, saved_z, 0, nullptr, false, fc, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
                            scratch_full, s, gy_w, proj_gw, nullptr, lift_u, fa));
     } else if (fast) {
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
       // mode 2: the cotangent tile is formed in the epilogue from its two factors instead of being read from HBM
       // mode 5: ... and the projection's weight gradient is accumulated from the recomputed activation (the block's output
       // was never stored by the projected forward pass)
-      PDEQX_TRY(tc_slab_ex(p, x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
+      PDEQX_TRY(tc_slab_ex(p, r.wprep[0], x, saved_z, 0, bypass_w, false, bypass_b, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
                            scratch_full, s, gy_w, proj_gw));
     } else {
       PDEQX_TRY(stage_c2r(p, saved_z, p->t_c2r_inv, rows_o, nullptr, PDEQX_ACT_IDENTITY, scratch_full, s));
@@ -613,8 +620,8 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
   // 2. bypass grads (and the bypass part of gx; on the tcgen05 path that part is fused into step 7)
   if (bypass_w && lifted) {
     // gW_byp[o,i] = sum g[o,p] x[i,p] with x = lift_w (x) u + lift_b: two reductions over g (one pass), then an outer product
-    float* s1 = p->lift_scratch + 256;
-    float* s0 = p->lift_scratch + 384;
+    float* s1 = r.lift + 256;
+    float* s0 = r.lift + 384;
     TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
     PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, 1, d.c_out, n_pix, lift_u, lift_w, gpre, nullptr, s1, s0, stream));
     lift_unfold_wgrad_kernel<<<(d.c_out * d.c_in + 255) / 256, 256, 0, s>>>(s1, s0, lift_w, lift_b, d.c_out, d.c_in, g_bypass_w,
@@ -663,25 +670,25 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     // exists as an accumulator tile; what is written is the upstream block's pre-activation cotangent
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     if (!a.up_x) {
-      float* fa = a.up_plan->lift_scratch;
-      float* fc = a.up_plan->lift_scratch + 128;
+      float* fa = r.lift;
+      float* fc = r.lift + 128;
       lift_fold_bypass_kernel<<<(d.c_in + 127) / 128, 128, 0, s>>>(a.up_bypass_w, a.up_bypass_b, a.up_lift_w, a.up_lift_b, d.c_in,
                                                                   a.up_plan->desc.c_in, fa, fc);
       PDEQX_LAUNCHED();
-      return tc_chain(p, gpre, gx1, bypass_w, a.up_plan, nullptr, a.up_saved_z, nullptr, fc, a.up_activation, a.up_gpre, s, a.up_lift_u, fa);
+      return tc_chain(p, r.wprep[0], r.wprep[1], gpre, gx1, bypass_w, a.up_plan, nullptr, a.up_saved_z, nullptr, fc, a.up_activation, a.up_gpre, s, a.up_lift_u, fa);
     }
-    return tc_chain(p, gpre, gx1, bypass_w, a.up_plan, a.up_x, a.up_saved_z, a.up_bypass_w, a.up_bypass_b, a.up_activation, a.up_gpre, s);
+    return tc_chain(p, r.wprep[0], r.wprep[1], gpre, gx1, bypass_w, a.up_plan, a.up_x, a.up_saved_z, a.up_bypass_w, a.up_bypass_b, a.up_activation, a.up_gpre, s);
   }
   if (fast && lift_u) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     PDEQX_CUDA(cudaMemsetAsync(lift_gw, 0, sizeof(float) * (size_t)d.c_in, s));
     if (lift_gb) PDEQX_CUDA(cudaMemsetAsync(lift_gb, 0, sizeof(float) * (size_t)d.c_in, s));
-    return tc_slab_ex(p, gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, /*mode=*/3,
+    return tc_slab_ex(p, r.wprep[0], gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, /*mode=*/3,
                       lift_u, d.c_out, d.c_in, nullptr, s, nullptr, lift_gw, lift_gb);
   }
   if (fast) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-    return tc_slab(p, gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, gx, s);
+    return tc_slab(p, r.wprep[0], gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, gx, s);
   }
   return stage_c2r(p, gx1, p->t_c2r_bwd, rows_i, gx_has_bypass ? gx : nullptr, PDEQX_ACT_IDENTITY, gx, s);
 }

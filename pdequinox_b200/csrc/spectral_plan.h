@@ -13,7 +13,7 @@ struct pdeqx_spectral_plan {
   int64_t stage_floats = 0;  // floats of one chain ping-pong buffer
   int64_t mode_floats = 0;   // floats of one mode-space buffer
   size_t ws_bytes = 0;
-  float* lift_scratch = nullptr;  // 4 x 128 floats: folded factors of a pointwise lifting in front of the block
+  int64_t small_floats = 0;  // per-call scratch of the tcgen05 stages inside the workspace (bypass weights, lifting factors)
   // last axis, real tables (fp32, generated in fp64)
   float* t_r2c_fwd = nullptr;  // [s_D, 2 m_D]  cos | -sin                (forward)
   float* t_c2r_inv = nullptr;  // [2 m_D, s_D]  c/s cos ; -c/s sin        (inverse, irfft weights c)
@@ -47,8 +47,8 @@ bool tc_r2c_available(const pdeqx_spectral_plan* p);
 int tc_stage_mask(const pdeqx_spectral_plan* p);
 int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int64_t rows, float* out, cudaStream_t s);
 bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass);
-// y = act( c2r(z) [table_sel: 0 = inverse, 1 = adjoint-of-forward] + W(.)x + b )
-int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+// y = act( c2r(z) [table_sel: 0 = inverse, 1 = adjoint-of-forward] + W(.)x + b ); w_prep: c_in * c_out floats of caller scratch
+int tc_slab(const pdeqx_spectral_plan* p, float* w_prep, const float* x, const float* z, int table_sel, const float* bypass_w,
             bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s);
 
 // leading-axis complex DFT stages on tcgen05 (tc_c2c.cu). kind: 0 forward, 1 inverse, 2 adjoint-of-inverse, 3 adjoint-of-forward
@@ -63,13 +63,13 @@ int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, fl
 // mode 2 = the same with a rank-1 cotangent aux_w[o] * aux[b, pixel] (behind a C -> 1 pointwise projection),
 // byp_u / byp_a (modes 0-2, bypass_w == null): rank-one bypass byp_a[o] * byp_u[b, pixel] added before the activation;
 // mode 3 = nothing stored: red_w[o] += sum result * aux[b, pixel], red_b[o] += sum result (in front of a 1 -> C lifting)
-int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+int tc_slab_ex(const pdeqx_spectral_plan* p, float* w_prep, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
                float* y, cudaStream_t s, const float* aux_w = nullptr, float* red_w = nullptr, float* red_b = nullptr,
                const float* byp_u = nullptr, const float* byp_a = nullptr);
 // the data-gradient pass of block `p` fused with the pre-activation-cotangent pass of the block `up` in front of it
 bool tc_chain_available(const pdeqx_spectral_plan* p, const pdeqx_spectral_plan* up);
-int tc_chain(const pdeqx_spectral_plan* p, const float* g, const float* z1, const float* w_k, const pdeqx_spectral_plan* up,
+int tc_chain(const pdeqx_spectral_plan* p, float* w_prep, float* w_prep2, const float* g, const float* z1, const float* w_k, const pdeqx_spectral_plan* up,
              const float* x_up, const float* z_up, const float* w_up, const float* bias_up, int act, float* out, cudaStream_t s,
              const float* byp_u = nullptr, const float* byp_a = nullptr);
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);

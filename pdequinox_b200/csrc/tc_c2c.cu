@@ -316,10 +316,10 @@ int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, fl
     PDEQX_TRY(tc::make_tensor_map(&tm_in, in, 3, dims, str, box, tc::TM_SW128_ATOM32));
   }
   const size_t smem = tab_bytes + (size_t)stages * stage_bytes + 1024 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;      
+  if (attr.first_use()) {
     PDEQX_CUDA(cudaFuncSetAttribute(tc::c2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+                
   }
   const int grid = (int)(cp.units < t->sms ? cp.units : t->sms);
   tc::c2c_kernel<<<grid, tc::kC2cThreads, smem, s>>>(tm_in, tb.map, cp);

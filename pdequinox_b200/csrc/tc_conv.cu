@@ -355,6 +355,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (p.has_residual) r += res[jx];
           if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
           else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
+          // the next consumer is a tcgen05 stage (conv / data gradient / filter gradient), which would TRUNCATE fp32 to
+          // tf32 (a coherent bias of about -2^-12 per layer): round to nearest here
+          r = round_tf32(r);
           st_shared_f32(piece + (uint32_t)jx * 128 + (lane_b ^ ((uint32_t)jx << 4)), r);
         }
         fence_proxy_async();
@@ -645,7 +648,7 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #if defined(PDEQX_CONV_DIAG) && PDEQX_CONV_DIAG == 3  // timing experiment: full epilogue arithmetic, no stores
             if (r == 123.456f) p.y[off0] = r;
 #else
-            p.y[off0 + (int64_t)jx * plane] = r;
+            p.y[off0 + (int64_t)jx * plane] = round_tf32(r);  // (read next by a tcgen05 stage: round, do not let it truncate)
 #endif
           }
           par ^= 1;
@@ -705,30 +708,9 @@ struct WgParams {
   int seg, segs_per_chain;
   int64_t items;  // batch * d * segs_per_chain
   float* scratch;  // [grid][3 tw][3 th][c i][c o]
-  int col_shift;   // TMA column shift of the two outer taps (0 when pre-shifted copies are used)
 };
 
-struct WgSmem {
-  uint32_t gy_off, gy_chunk_bytes, ring_off, slot_bytes, box_bytes, bar_off, total;
-};
 constexpr int kWgRing = 4;   // x rows resident (3 in use + 1 in flight)
-constexpr int kWgGyStages = 3;  // 32-column chunks of shifted gy copies in flight (4 chunks per row rotate through them)
-
-static WgSmem wg_smem(int c) {
-  WgSmem s{};
-  uint32_t off = 0;
-  s.box_bytes = (uint32_t)c * 128;          // [c rows][32 w]
-  s.gy_off = off;
-  s.gy_chunk_bytes = 3 * s.box_bytes;       // [shift tw=0][shift tw=2][centre]
-  off += kWgGyStages * s.gy_chunk_bytes + s.box_bytes;  // + tail so that the last centre box has a (don't-care) upper half
-  s.ring_off = off;
-  s.slot_bytes = 4 * s.box_bytes;
-  off += kWgRing * s.slot_bytes;
-  s.bar_off = off;
-  off += 1024;
-  s.total = off + 1024;
-  return s;
-}
 
 struct WgItem {
   int b, r0, j0, count;
@@ -745,203 +727,6 @@ __device__ __forceinline__ WgItem wg_item(const WgParams& p, int64_t item) {
   int c = len - it.j0;
   it.count = c < 0 ? 0 : (c > p.seg ? p.seg : c);
   return it;
-}
-
-__global__ void __launch_bounds__(256, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_gy0,
-                  const __grid_constant__ CUtensorMap tm_gy2, const __grid_constant__ CUtensorMap tm_x, WgParams p, WgSmem L) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
-  uint64_t* gyfull = bars;        // [kWgGyStages] chunk stages of shifted gy copies
-  uint64_t* gyempty = bars + 4;   // [kWgGyStages]
-  uint64_t* xfull = bars + 8;     // [kWgRing]
-  uint64_t* xempty = bars + 12;   // [kWgRing]
-  uint64_t* done = bars + 16;
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 17);
-  uint32_t* inited_s = (uint32_t*)(bars + 18);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = p.c;
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_gy);
-    tma_prefetch_desc(&tm_gy0);
-    tma_prefetch_desc(&tm_gy2);
-    tma_prefetch_desc(&tm_x);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&gyfull[i], 1);
-      mbar_init(&gyempty[i], 1);
-      mbar_init(&xfull[i], 1);
-      mbar_init(&xempty[i], 1);
-    }
-    mbar_init(done, 1);
-    *inited_s = 0;
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
-  // the don't-care upper half of the last centre box must at least be finite
-  for (uint32_t i = threadIdx.x; i < L.box_bytes / 4; i += blockDim.x)
-    ((float*)(smem + L.gy_off + kWgGyStages * L.gy_chunk_bytes))[i] = 0.f;
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const int64_t first = blockIdx.x, stride = gridDim.x;
-  const bool zeros = p.boundary == PDEQX_PAD_ZEROS;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t pe = 0, used = 0, gpe = 0, gused = 0;
-      int gs = 0;  // gy chunk stage of the next chunk (global rotation over all chunks of all units)
-      for (int64_t item = first; item < p.items; item += stride) {
-        const WgItem it = wg_item(p, item);
-        int v_next = it.j0 - 1;  // next chain row of x to fetch
-        for (int jj = 0; jj < it.count; ++jj) {
-          const int j = it.j0 + jj;
-          const int h = it.r0 + j * p.d;
-          // x rows up to v = j + 2 (one row ahead of what this unit needs)
-          const int v_hi = (j + 2 <= it.j0 + it.count) ? j + 2 : it.j0 + it.count;
-          for (; v_next <= v_hi; ++v_next) {
-            const int row = conv_map(it.r0 + v_next * p.d, p.H, p.boundary);
-            if (row < 0) continue;
-            const int s = (v_next + 1) & (kWgRing - 1);
-            if (used & (1u << s)) {
-              mbar_wait_backoff(&xempty[s], (pe >> s) & 1u);
-              pe ^= 1u << s;
-            }
-            used |= 1u << s;
-            uint8_t* dst = smem + L.ring_off + (size_t)s * L.slot_bytes;
-            mbar_expect_tx(&xfull[s], L.slot_bytes);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_x, &xfull[s], c * 32, row, it.b * C);
-          }
-          // the gy row of this unit: per 32-column chunk the two shifted copies and the centre copy
-          for (int c = 0; c < 4; ++c) {
-            if (gused & (1u << gs)) {
-              mbar_wait_backoff(&gyempty[gs], (gpe >> gs) & 1u);
-              gpe ^= 1u << gs;
-            }
-            gused |= 1u << gs;
-            uint8_t* dst = smem + L.gy_off + (size_t)gs * L.gy_chunk_bytes;
-            mbar_expect_tx(&gyfull[gs], L.gy_chunk_bytes);
-            // tap tw reads x column w + s, s = (tw - 1) d: substitute w' = w + s  =>  A_tw[o, w'] = gy[o, w' - s]
-            // (TMA needs 16-byte aligned box columns: for d % 4 != 0 the shifted copies come from pre-shifted tensors)
-            tma_load_3d(dst, &tm_gy0, &gyfull[gs], c * 32 + p.col_shift, h, it.b * C);                // tw = 0 (s = -d)
-            tma_load_3d(dst + L.box_bytes, &tm_gy2, &gyfull[gs], c * 32 - p.col_shift, h, it.b * C);  // tw = 2 (s = +d)
-            tma_load_3d(dst + 2 * L.box_bytes, &tm_gy, &gyfull[gs], c * 32, h, it.b * C);        // tw = 1
-            if (++gs == kWgGyStages) gs = 0;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
-    const uint32_t idesc = idesc_tf32(128, C, false, false);
-    const uint64_t adesc0 = smem_desc_sw128(smem_u32(smem + L.gy_off), 0, 1024);
-    const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.ring_off), 0, 1024);
-    const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
-    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0;
-    const uint32_t gchunk16 = L.gy_chunk_bytes >> 4, box16 = L.box_bytes >> 4, slot16 = L.slot_bytes >> 4;
-    uint32_t pf = 0, gpf = 0, inited = 0;
-    int gs = 0;
-    bool any = false;
-    for (int64_t item = first; item < p.items; item += stride) {
-      const WgItem it = wg_item(p, item);
-      for (int jj = 0; jj < it.count; ++jj) {
-        const int j = it.j0 + jj;
-        const bool last = jj == it.count - 1;
-        const int h = it.r0 + j * p.d;
-        bool valid[3];
-        valid[0] = !(zeros && h - p.d < 0);
-        valid[1] = true;
-        valid[2] = !(zeros && h + p.d >= p.H);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          if (!valid[t]) continue;
-          if (jj == 0 || t == 2) {  // first use of chain row v = j - 1 + t
-            const int s = (j + t) & (kWgRing - 1);
-            mbar_wait(&xfull[s], (pf >> s) & 1u);
-            pf ^= 1u << s;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          mbar_wait(&gyfull[gs], (gpf >> gs) & 1u);
-          gpf ^= 1u << gs;
-          tc_fence_after();
-          if (elect_one()) {
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              if (!valid[t]) continue;
-              const int s = (j + t) & (kWgRing - 1);
-              const uint32_t b_lo = b_lo0 + (uint32_t)s * slot16 + (uint32_t)c * box16;
-              const uint32_t a1 = a_lo0 + (uint32_t)gs * gchunk16;  // [shift tw=0 ; shift tw=2]
-              const uint32_t a2 = a1 + 2 * box16;                  // [centre ; don't-care]
-              const uint32_t d1 = tmem_base + (uint32_t)(t * C), d2 = tmem_base + (uint32_t)((3 + t) * C);
-              const uint32_t acc = (inited >> t) & 1u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                mma_tf32_lohi(d1, a1 + k * 2, a_hi, b_lo + k * 2, b_hi, idesc, (c | k) ? 1u : acc);
-                mma_tf32_lohi(d2, a2 + k * 2, a_hi, b_lo + k * 2, b_hi, idesc, (c | k) ? 1u : acc);
-              }
-            }
-            mma_commit(&gyempty[gs]);
-            if (c == 3) {  // rows: v = j-1 is never needed again; at a segment end nothing is
-#pragma unroll
-              for (int t = 0; t < 3; ++t)
-                if (valid[t] && (t == 0 || last)) mma_commit(&xempty[(j + t) & (kWgRing - 1)]);
-            }
-          }
-          __syncwarp();
-          if (++gs == kWgGyStages) gs = 0;
-        }
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-          if (valid[t]) inited |= 1u << t;
-        any = true;
-      }
-    }
-    if (elect_one()) {
-      *inited_s = inited;
-      mma_commit(done);
-    }
-    __syncwarp();
-    (void)any;
-  } else if (warp >= 4) {
-    // ===================== flush: TMEM -> scratch[cta][tw][th][i][o] =====================
-    const int q = warp & 3;
-    mbar_wait(done, 0);
-    tc_fence_after();
-    const uint32_t inited = *(volatile uint32_t*)inited_s;
-    float* out = p.scratch + (size_t)blockIdx.x * 9 * C * C;
-    // lanes 0..63 of group 1 = tap tw 0, lanes 64..127 = tap tw 2; lanes 0..63 of group 2 = tap tw 1
-    const int o = (q & 1) * 32 + lane;
-    for (int g = 0; g < 2; ++g) {
-      if (g == 1 && q >= 2) break;
-      const int tw = g == 0 ? (q < 2 ? 0 : 2) : 1;
-      for (int t = 0; t < 3; ++t) {
-        for (int c0 = 0; c0 < C; c0 += 16) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 3 + t) * C + c0), v);
-          tmem_ld_wait();
-          if (o < C) {
-#pragma unroll
-            for (int jx = 0; jx < 16; ++jx)
-              out[((size_t)(tw * 3 + t) * C + c0 + jx) * C + o] = ((inited >> t) & 1u) ? v[jx] : 0.f;
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1256,30 +1041,6 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
   }
 }
 
-// Column-shifted copies of gy for the two outer column taps when d is not a multiple of 4 (an unaligned TMA box column
-// faults): A_tw[.., w'] = sum over the output columns w whose tap reads x column w' = colmap(w + s), s = (tw - 1) d:
-//   the direct one, w = w' - s, plus -- periodic / neumann -- the columns that reach w' through the wrapped / mirrored halo.
-// With these operands the tensor-core pass is the complete filter gradient for every boundary mode (no edge pass).
-__global__ void __launch_bounds__(256)
-conv_shift_rows_kernel(const float* __restrict__ gy, float* __restrict__ out0, float* __restrict__ out2, int64_t rows, int W, int d,
-                       int boundary) {
-  const int64_t total = rows * W;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(idx % W);
-    const float* row = gy + (idx - w);
-    float a0 = (w + d < W) ? __ldg(row + w + d) : 0.f;   // tw = 0: s = -d, direct source column w + d
-    float a2 = (w - d >= 0) ? __ldg(row + w - d) : 0.f;  // tw = 2: s = +d, direct source column w - d
-    if (boundary != PDEQX_PAD_ZEROS && (w <= d || w >= W - 1 - d)) {
-      for (int e = 0; e < d; ++e) {
-        if (conv_map(e - d, W, boundary) == w) a0 += __ldg(row + e);                  // left halo of tap 0
-        if (conv_map(W - d + e + d, W, boundary) == w) a2 += __ldg(row + W - d + e);  // right halo of tap 2
-      }
-    }
-    out0[idx] = a0;
-    out2[idx] = a2;
-  }
-}
-
 // gw[o][i][th][tw] = sum_cta scratch[cta][tw][th][i][o]   (+ what the edge kernel adds afterwards)
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gw, int nslabs, int C) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [tw][th][i][o]
@@ -1300,50 +1061,6 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, floa
   r /= C;
   const int th = r % 3, tw = r / 3;
   gw[((o * C + i) * 3 + th) * 3 + tw] = acc;
-}
-
-// The wrapped (periodic) / mirrored (neumann) edge columns of the two outer column taps, which the zero-extended tensor-core
-// pass leaves out:  gW[o,i,th,tw] += sum_{b,h} sum_{w : w+s outside [0,W)} gy[b,o,h,w] x[b,i,rowmap(h+(th-1)d), colmap(w+s)].
-// grid (row blocks, 6 = 3 row taps x 2 sides); 256 threads, thread = (o, 16 input channels); d <= 8 columns per side.
-__global__ void __launch_bounds__(256)
-conv_wgrad_edge_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw, int B, int C, int H,
-                       int W, int d, int boundary) {
-  __shared__ float gs[64][kMaxDil + 1];
-  __shared__ float xs[64][kMaxDil + 1];
-  const int th = blockIdx.y % 3, side = blockIdx.y / 3;  // side 0: tap tw = 0 (s = -d, left edge), side 1: tw = 2
-  const int tw = side == 0 ? 0 : 2;
-  const int s = (tw - 1) * d;
-  const int tid = threadIdx.x;
-  const int o = tid & 63, ig = tid >> 6;  // 4 groups of 16 input channels
-  float acc[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  const int64_t rows = (int64_t)B * H;
-  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int b = (int)(r / H), h = (int)(r % H);
-    const int hr = conv_map(h + (th - 1) * d, H, boundary);
-    __syncthreads();
-    for (int idx = tid; idx < 64 * d; idx += 256) {
-      const int ch = idx / d, e = idx % d;
-      const int w = side == 0 ? e : W - d + e;  // the d output columns whose tap falls outside the row
-      const int wc = conv_map(w + s, W, boundary);
-      gs[ch][e] = ch < C ? __ldg(gy + (((int64_t)b * C + ch) * H + h) * W + w) : 0.f;
-      xs[ch][e] = (ch < C && hr >= 0 && wc >= 0) ? __ldg(x + (((int64_t)b * C + ch) * H + hr) * W + wc) : 0.f;
-    }
-    __syncthreads();
-    for (int e = 0; e < d; ++e) {
-      const float g = gs[o][e];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] = fmaf(g, xs[ig * 16 + k][e], acc[k]);
-    }
-  }
-  if (o < C) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int i = ig * 16 + k;
-      if (i < C) atomicAdd(gw + ((o * C + i) * 3 + th) * 3 + tw, acc[k]);
-    }
-  }
 }
 
 // gb[o] = sum_{b,h,w} gy[b,o,h,w]: one block per (b, o) plane chunk, atomics on C addresses
@@ -1372,8 +1089,6 @@ conv_bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ gb, int 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-static float* g_wprep[16] = {nullptr};  // per-device scratch for the re-laid-out weights (k*k*64*64 floats max)
-
 // rows per work item: a divisor of H (so that no item has a ragged tail), as close to 32 as possible
 static int conv_segment(int H) {
   if (H <= 64) return H;
@@ -1401,34 +1116,51 @@ static bool tc_conv_shape_ok(const ConvGeom& g) {
   return true;
 }
 
-extern std::atomic<int> g_precision_conv;
-std::atomic<int> g_precision_conv{PDEQX_PREC_FP32};
+// Caller-provided scratch of the tcgen05 passes (pdeqx_conv_workspace_bytes): [re-laid-out filter][partial filter gradients]
+constexpr size_t kWprepFloats = 64 * 64 * 9;
+constexpr size_t kWgSlabs = 160;  // one partial filter gradient [3 tw][3 th][64 i][64 o] per CTA of the filter-gradient kernel
+size_t tc_conv_workspace_bytes(const ConvGeom& g) {
+  if (!tc_conv_available(g)) return 0;
+  return sizeof(float) * (kWprepFloats + kWgSlabs * 9 * 64 * 64) + 256;
+}
+static float* ws_wprep(void* ws) { return (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255); }
+static float* ws_wgrad(void* ws) { return ws_wprep(ws) + kWprepFloats; }
 
 bool tc_conv_available(const ConvGeom& g) {
   if (!g_fast_paths.load(std::memory_order_relaxed)) return false;
-  if (g_precision_conv.load(std::memory_order_relaxed) != PDEQX_PREC_TF32) return false;
+  if (g.precision != PDEQX_PREC_TF32) return false;
   if (!tc_conv_shape_ok(g)) return false;
   if (!pdeqx_has_tcgen05() || !tc::encode_tiled_fn()) return false;
   return true;
 }
 
-static std::atomic<int64_t> g_pair_launches{0};
-static std::atomic<bool> g_pair_unavailable{false};
+static std::atomic<int64_t> g_pair_launches{0};  // diagnostic counter
+// devices (bit = ordinal) that rejected the two-CTA cluster launch once -- a cached capability, like the attribute flags
+static std::atomic<uint64_t> g_pair_unavailable{0};
 int64_t tc_conv_pair_launches() { return g_pair_launches.load(std::memory_order_relaxed); }
 
+static int check_conv_ws(const ConvGeom& g, void* ws, size_t ws_bytes) {
+  if (!ws || ws_bytes < tc_conv_workspace_bytes(g)) {
+    set_error("conv workspace too small: need %zu bytes (pdeqx_conv_workspace_bytes), got %zu", tc_conv_workspace_bytes(g), ws ? ws_bytes : (size_t)0);
+    return PDEQX_ERR_WORKSPACE;
+  }
+  return PDEQX_OK;
+}
+
 static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, bool flip, const float* bias,
-                            const float* residual, int act, float* y, cudaStream_t s) {
+                            const float* residual, int act, float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
   int dev = 0, sms = 148;
   PDEQX_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  PDEQX_CHECK_ARG(dev < 16, "device index too large");
+  PDEQX_TRY(check_conv_ws(g, ws, ws_bytes));
+  float* wprep = ws_wprep(ws);
+  const uint64_t dev_bit = 1ull << (dev & 63);
   const int c_in = flip ? g.c_out : g.c_in, c_out = flip ? g.c_in : g.c_out;
   const int k = g.kernel[0];
-  if (!g_wprep[dev]) PDEQX_CUDA(cudaMalloc((void**)&g_wprep[dev], sizeof(float) * 64 * 64 * 9));
   PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!residual || ((uintptr_t)residual & 15) == 0),
                   "tc_conv: tensors must be 16-byte aligned");
   const int total_w = c_out * c_in * k * k;
-  tc::conv_prep_weights_kernel<<<(total_w + 255) / 256, 256, 0, s>>>(w, g_wprep[dev], c_out, c_in, k, flip ? 1 : 0);
+  tc::conv_prep_weights_kernel<<<(total_w + 255) / 256, 256, 0, s>>>(w, wprep, c_out, c_in, k, flip ? 1 : 0);
   PDEQX_LAUNCHED();
   const int H = g.spatial[0], W = g.spatial[1];
   CUtensorMap tm_x, tm_w, tm_y, tm_res;
@@ -1443,7 +1175,7 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
     uint64_t dims[2] = {(uint64_t)c_in, (uint64_t)2 * k * N};
     uint64_t str[1] = {(uint64_t)c_in * 4};
     uint32_t box[2] = {32, N};
-    PDEQX_TRY(tc::make_tensor_map(&tm_w, g_wprep[dev], 2, dims, str, box, tc::TM_SW128));
+    PDEQX_TRY(tc::make_tensor_map(&tm_w, wprep, 2, dims, str, box, tc::TM_SW128));
   }
   {
     uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * c_out};
@@ -1473,7 +1205,7 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   // (both CTAs of a pair issue the same schedule) and an even number of items
   static const bool pair_enabled = [] { const char* e = getenv("PDEQX_CONV_PAIR"); return !(e && e[0] == '0'); }();
   const tc::ConvParams cp_one_cta = cp;
-  if (pair_enabled && !g_pair_unavailable.load(std::memory_order_relaxed) && c_in == 64 && c_out == 64 && H % cp.d == 0 && sms >= 2) {
+  if (pair_enabled && !(g_pair_unavailable.load(std::memory_order_relaxed) & dev_bit) && c_in == 64 && c_out == 64 && H % cp.d == 0 && sms >= 2) {
     const int chain = H / cp.d, pairs = sms / 2;
     int best_seg = 0;
     int64_t best_cost = 0;
@@ -1490,12 +1222,19 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
       cp.segs_per_image = chain / best_seg;
       cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image;
       int grid2 = (int)(cp.items < sms ? cp.items : sms) & ~1;
+      {  // an error pending from an earlier asynchronous failure must not be read as "cluster launch rejected" below
+        const cudaError_t stale = cudaPeekAtLastError();
+        if (stale != cudaSuccess) {
+          set_error("CUDA error pending before the conv launch: %s", cudaGetErrorString(stale));
+          return PDEQX_ERR_CUDA;
+        }
+      }
 #define PDEQX_CONV_PAIR_LAUNCH(A)                                                                                         \
   do {                                                                                                                    \
-    static bool attr = false;                                                                                             \
-    if (!attr) {                                                                                                          \
+    static DeviceOnce attr;                                                                                                   \
+    if (attr.first_use()) {                                                                                                          \
       PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_rows_pair_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                                        \
+                                                                                                                          \
     }                                                                                                                     \
     tc::conv_rows_pair_kernel<A><<<grid2, tc::kConvThreads, L.total, s>>>(tm_x, tm_w, tm_y, tm_res, cp, L);               \
   } while (0)
@@ -1505,13 +1244,13 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
 #undef PDEQX_CONV_PAIR_LAUNCH
       // A device that cannot co-schedule the two-CTA cluster with 227 KB each (a partitioned GPU, an odd SM count) rejects
       // the launch synchronously: remember that and take the one-CTA kernel from now on instead of failing the call.
-      const cudaError_t pair_err = cudaGetLastError();
+      const cudaError_t pair_err = cudaGetLastError();  // (an error left over from an earlier call was surfaced by that call's own check)
       if (pair_err == cudaSuccess) {
         ::pdeqx::g_launches.fetch_add(1, std::memory_order_relaxed);
         g_pair_launches.fetch_add(1, std::memory_order_relaxed);
         return PDEQX_OK;
       }
-      g_pair_unavailable.store(true, std::memory_order_relaxed);
+      g_pair_unavailable.fetch_or(dev_bit, std::memory_order_relaxed);
       cp = cp_one_cta;
     }
   }
@@ -1520,10 +1259,10 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   PDEQX_CHECK_ARG(grid >= 2, "tc_conv: grid too small");
 #define PDEQX_CONV_LAUNCH(A)                                                                                         \
   do {                                                                                                               \
-    static bool attr = false;                                                                                        \
-    if (!attr) {                                                                                                     \
+    static DeviceOnce attr;                                                                                              \
+    if (attr.first_use()) {                                                                                                     \
       PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_rows_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                                   \
+                                                                                                                     \
     }                                                                                                                \
     tc::conv_rows_kernel<A><<<grid, tc::kConvThreads, L.total, s>>>(tm_x, tm_w, tm_y, tm_res, cp, L);                 \
   } while (0)
@@ -1536,122 +1275,64 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
 }
 
 int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* residual, int act,
-                float* y, cudaStream_t s) {
+                float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
   TimedScope timed(PDEQX_K_CONV_FWD, s);
-  return conv_rows_launch(g, x, w, false, b, residual, act, y, s);
+  return conv_rows_launch(g, x, w, false, b, residual, act, y, ws, ws_bytes, s);
 }
 
 bool tc_conv_bwd_data_available(const ConvGeom& g) { return tc_conv_available(g); }
 
-int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, cudaStream_t s) {
+int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, void* ws, size_t ws_bytes,
+                     cudaStream_t s) {
   TimedScope timed(PDEQX_K_CONV_BWD_DATA, s);
-  if (g.boundary != PDEQX_PAD_REFLECT) return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, s);
+  if (g.boundary != PDEQX_PAD_REFLECT) return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, ws, ws_bytes, s);
   // neumann: the adjoint of a reflect pad is a FOLD, not a convolution. The zero-extended part is the same implicit GEMM
   // (dirichlet data gradient); what arrives through mirrored halo positions only touches a frame of width d and is added
   // by the CUDA-core gather.
   ConvGeom z = g;
   z.boundary = PDEQX_PAD_ZEROS;
-  PDEQX_TRY(conv_rows_launch(z, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, s));
+  PDEQX_TRY(conv_rows_launch(z, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, ws, ws_bytes, s));
   return conv_bwd_data_mirror_part(g, gy, w, gx, s);
 }
 
-static float* g_wg_scratch[16] = {nullptr};
-static float* g_wg_shift[16] = {nullptr};   // per-device pre-shifted gy copies (2 x activation size), grown on demand
-static size_t g_wg_shift_floats[16] = {0};  // per-device [148][9][64][64] partial filter gradients
-
 bool tc_conv_bwd_filter_available(const ConvGeom& g) { return tc_conv_available(g) && g.c_in == 64; }
 
-// gw, gb zeroed by the caller (conv.cu)
-int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, cudaStream_t s) {
+// gw, gb zeroed by the caller (conv.cu). The column-shifted operands (halo folded in) are built in shared memory by the
+// kernel itself: x and gy are read once. Every CTA flushes its partial sum to a slab of the workspace; a second kernel
+// reduces the slabs (deterministic, no atomics on the filter gradient).
+int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws, size_t ws_bytes,
+                       cudaStream_t s) {
   TimedScope timed(PDEQX_K_CONV_BWD_FILTER, s);
   int dev = 0, sms = 148;
   PDEQX_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  PDEQX_CHECK_ARG(dev < 16 && sms <= 160, "unexpected device");
+  PDEQX_CHECK_ARG(sms <= (int)kWgSlabs, "unexpected device (%d SMs)", sms);
+  PDEQX_TRY(check_conv_ws(g, ws, ws_bytes));
   const int C = g.c_in, H = g.spatial[0], W = g.spatial[1], d = g.dilation[0];
-  if (!g_wg_scratch[dev]) PDEQX_CUDA(cudaMalloc((void**)&g_wg_scratch[dev], sizeof(float) * 160 * 9 * 64 * 64));
   PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)gy & 15) == 0, "tc_conv: tensors must be 16-byte aligned");
-  CUtensorMap tm_gy, tm_gy0, tm_gy2, tm_x;
-  static const bool smem_shift = [] { const char* e = getenv("PDEQX_WG_SMEM_SHIFT"); return !(e && e[0] == '0'); }();
-  if (smem_shift && C == 64) {
-    // the shifted operands (halo folded in) are built in shared memory by the kernel itself: x and gy are read once
-    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * C};
-    uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)C};
-    PDEQX_TRY(tc::make_tensor_map(&tm_gy, gy, 3, dims, str, box, tc::TM_SW128));
-    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128));
-    tc::WgParams wp{};
-    wp.H = H; wp.W = W; wp.c = C; wp.d = d; wp.boundary = g.boundary;
-    const int max_chain = (int)ceil_div(H, d);
-    wp.seg = max_chain < 32 ? max_chain : 32;
-    wp.segs_per_chain = (int)ceil_div(max_chain, wp.seg);
-    wp.items = (int64_t)g.batch * d * wp.segs_per_chain;
-    wp.scratch = g_wg_scratch[dev];
-    tc::WgsSmem L = tc::wgs_smem(C);
-    PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
-    const int grid = (int)(wp.items < sms ? wp.items : sms);
-    static bool attr2 = false;
-    if (!attr2) {
-      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr2 = true;
-    }
-    tc::conv_wgrad_shift_kernel<<<grid, tc::kWgsThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
-    PDEQX_LAUNCHED();
-    tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C);
-    PDEQX_LAUNCHED();
-    if (gb) {
-      tc::conv_bias_grad_kernel<<<g.batch * C, 256, 0, s>>>(gy, gb, C, (int64_t)H * W);
-      PDEQX_LAUNCHED();
-    }
-    return PDEQX_OK;
-  }
-  const bool preshift = (d % 4) != 0;
-  const size_t n_act = (size_t)g.batch * C * H * W;
-  if (preshift) {  // TMA box columns must be 16-byte aligned: materialise the two shifted copies once
-    if (g_wg_shift_floats[dev] < 2 * n_act) {
-      if (g_wg_shift[dev]) PDEQX_CUDA(cudaFree(g_wg_shift[dev]));
-      g_wg_shift[dev] = nullptr;
-      g_wg_shift_floats[dev] = 0;
-      PDEQX_CUDA(cudaMalloc((void**)&g_wg_shift[dev], sizeof(float) * 2 * n_act));
-      g_wg_shift_floats[dev] = 2 * n_act;
-    }
-    tc::conv_shift_rows_kernel<<<148 * 16, 256, 0, s>>>(gy, g_wg_shift[dev], g_wg_shift[dev] + n_act, (int64_t)g.batch * C * H, W, d,
-                                                        g.boundary);
-    PDEQX_LAUNCHED();
-  }
-  {
-    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * C};
-    uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)C};
-    PDEQX_TRY(tc::make_tensor_map(&tm_gy, gy, 3, dims, str, box, tc::TM_SW128));
-    PDEQX_TRY(tc::make_tensor_map(&tm_gy0, preshift ? g_wg_shift[dev] : gy, 3, dims, str, box, tc::TM_SW128));
-    PDEQX_TRY(tc::make_tensor_map(&tm_gy2, preshift ? g_wg_shift[dev] + n_act : gy, 3, dims, str, box, tc::TM_SW128));
-    PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128));
-  }
+  CUtensorMap tm_gy, tm_x;
+  uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)g.batch * C};
+  uint64_t str[2] = {(uint64_t)W * 4, (uint64_t)H * W * 4};
+  uint32_t box[3] = {32, 1, (uint32_t)C};
+  PDEQX_TRY(tc::make_tensor_map(&tm_gy, gy, 3, dims, str, box, tc::TM_SW128));
+  PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 3, dims, str, box, tc::TM_SW128));
   tc::WgParams wp{};
   wp.H = H; wp.W = W; wp.c = C; wp.d = d; wp.boundary = g.boundary;
   const int max_chain = (int)ceil_div(H, d);
   wp.seg = max_chain < 32 ? max_chain : 32;
   wp.segs_per_chain = (int)ceil_div(max_chain, wp.seg);
   wp.items = (int64_t)g.batch * d * wp.segs_per_chain;
-  wp.scratch = g_wg_scratch[dev];
-  wp.col_shift = preshift ? 0 : d;
-  tc::WgSmem L = tc::wg_smem(C);
+  wp.scratch = ws_wgrad(ws);
+  tc::WgsSmem L = tc::wgs_smem(C);
   PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
   const int grid = (int)(wp.items < sms ? wp.items : sms);
-  static bool attr = false;
-  if (!attr) {
-    PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
-  tc::conv_wgrad_kernel<<<grid, 256, L.total, s>>>(tm_gy, tm_gy0, tm_gy2, tm_x, wp, L);
+  static DeviceOnce attr;
+  if (attr.first_use())
+    PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  tc::conv_wgrad_shift_kernel<<<grid, tc::kWgsThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
   PDEQX_LAUNCHED();
   tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C);
   PDEQX_LAUNCHED();
-  if (!preshift && (g.boundary == PDEQX_PAD_WRAP || g.boundary == PDEQX_PAD_REFLECT)) {  // (pre-shifted operands carry the halo)
-    tc::conv_wgrad_edge_kernel<<<dim3(148 * 2, 6), 256, 0, s>>>(x, gy, gw, g.batch, C, H, W, d, g.boundary);
-    PDEQX_LAUNCHED();
-  }
   if (gb) {
     tc::conv_bias_grad_kernel<<<g.batch * C, 256, 0, s>>>(gy, gb, C, (int64_t)H * W);
     PDEQX_LAUNCHED();
@@ -1661,4 +1342,3 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
 
 }  // namespace pdeqx
 
-extern "C" void pdeqx_set_conv_precision(int32_t precision) { pdeqx::g_precision_conv.store(precision); }

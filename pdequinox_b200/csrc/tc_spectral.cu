@@ -1212,8 +1212,6 @@ struct TcPlan {
   int sms = 148;
   float* tab_r2c[2] = {nullptr, nullptr};  // [32][s_D]  (n-major rows, K contiguous): forward / adjoint-of-inverse
   float* tab_c2r[2] = {nullptr, nullptr};  // [s_D][32]  (w rows, K contiguous): inverse / adjoint-of-forward
-  float* w_prep = nullptr;                 // rounded (transposed) bypass weight
-  float* w_prep2 = nullptr;                // second one: the chain kernel holds the weights of two blocks
   CUtensorMap tm_tab_r2c[2], tm_tab_c2r[2];
   int slab_stages = 0;
 };
@@ -1278,9 +1276,6 @@ int tc_plan_init(pdeqx_spectral_plan* p) {
       rc = tc::make_tensor_map(&t->tm_tab_c2r[v], t->tab_c2r[v], 2, dims, str, box);
     }
   }
-  const int cmax = d.c_in > d.c_out ? d.c_in : d.c_out;
-  if (rc == PDEQX_OK && cudaMalloc((void**)&t->w_prep, (size_t)cmax * cmax * 4) != cudaSuccess) rc = PDEQX_ERR_CUDA;
-  if (rc == PDEQX_OK && cudaMalloc((void**)&t->w_prep2, (size_t)cmax * cmax * 4) != cudaSuccess) rc = PDEQX_ERR_CUDA;
   if (rc != PDEQX_OK) {
     set_error("tcgen05 plan setup failed: %s", cudaGetErrorString(cudaGetLastError()));
     p->tc = t;
@@ -1311,8 +1306,6 @@ void tc_plan_free(pdeqx_spectral_plan* p) {
     cudaFree(t->tab_r2c[v]);
     cudaFree(t->tab_c2r[v]);
   }
-  cudaFree(t->w_prep);
-  cudaFree(t->w_prep2);
   delete t;
   p->tc = nullptr;
 }
@@ -1350,10 +1343,10 @@ int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int
   PDEQX_CHECK_ARG(stages >= 2, "tc_r2c: table does not leave room for the pipeline");
   rp.stages = stages;
   const size_t smem = tab_bytes + (size_t)stages * 16384 + 1024 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;      
+  if (attr.first_use()) {
     PDEQX_CUDA(cudaFuncSetAttribute(tc::r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+                
   }
   const int grid = (int)(rp.tiles < t->sms ? rp.tiles : t->sms);
   tc::r2c_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_x, t->tm_tab_r2c[adjoint_table ? 1 : 0], rp);
@@ -1368,7 +1361,7 @@ bool tc_slab_available(const pdeqx_spectral_plan* p, bool has_bypass) {
 
 // y[B, c_o, lead, W] = epi( c2r(z)[table_sel] + Wmat . x + bias ), Wmat = bypass_w (c_o x c_i) or its transpose
 // (bypass_transposed: bypass_w is [c_i_of_this_call... see spectral.cu) ; mode 1: y = aux * act'(.)
-int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+int tc_slab_ex(const pdeqx_spectral_plan* p, float* w_prep, const float* x, const float* z, int table_sel, const float* bypass_w,
                bool bypass_transposed, const float* bypass_b, int act, int mode, const float* aux, int c_in, int c_out,
                float* y, cudaStream_t s, const float* aux_w, float* red_w, float* red_b, const float* byp_u, const float* byp_a) {
   TcPlan* t = tcp(p);
@@ -1384,6 +1377,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   PDEQX_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!x || ((uintptr_t)x & 15) == 0),
                   "tc_slab: pointers must be 16-byte aligned");
   const bool bypass = bypass_w != nullptr;
+  PDEQX_CHECK_ARG(!bypass || w_prep, "tc_slab: the bypass needs c_in * c_out floats of scratch");
   CUtensorMap tm_x, tm_z, tm_w;
   {
     uint64_t dims[3] = {32, (uint64_t)lead, (uint64_t)d.batch * c_out};
@@ -1399,13 +1393,13 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
     // rounded copy of the weight as [c_out rows][c_in] (K contiguous)
     const int n = c_in * c_out;
     // bypass_w is stored [rows_w][cols_w]; not transposed: [c_out][c_in]; transposed: stored [c_in][c_out]
-    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(bypass_w, t->w_prep, bypass_transposed ? c_in : c_out,
+    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(bypass_w, w_prep, bypass_transposed ? c_in : c_out,
                                                           bypass_transposed ? c_out : c_in, bypass_transposed ? 1 : 0);
     PDEQX_LAUNCHED();
     uint64_t wd[2] = {(uint64_t)c_in, (uint64_t)c_out};
     uint64_t ws[1] = {(uint64_t)c_in * 4};
     uint32_t wb[2] = {32, (uint32_t)c_out};
-    PDEQX_TRY(tc::make_tensor_map(&tm_w, t->w_prep, 2, wd, ws, wb));
+    PDEQX_TRY(tc::make_tensor_map(&tm_w, w_prep, 2, wd, ws, wb));
   } else {
     tm_x = tm_z;
     tm_w = tm_z;
@@ -1463,10 +1457,10 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   PDEQX_CHECK_ARG(!byp1 || (byp_a && !bypass && mode != 3), "tc_slab: a rank-one bypass replaces the bypass weight");
 #define PDEQX_SLAB_LAUNCH_B(M, A, B1)                                                                                     \
   do {                                                                                                                    \
-    static bool attr = false;                                                                                             \
-    if (!attr) {                                                                                                          \
+    static DeviceOnce attr;                                                                                                   \
+    if (attr.first_use()) {                                                                                                          \
       PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<M, A, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                                        \
+                                                                                                                          \
     }                                                                                                                     \
     tc::slab_kernel<M, A, B1><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L);         \
   } while (0)
@@ -1507,11 +1501,11 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, const float* x, const float* z, int
   return PDEQX_OK;
 }
 
-int tc_slab(const pdeqx_spectral_plan* p, const float* x, const float* z, int table_sel, const float* bypass_w,
+int tc_slab(const pdeqx_spectral_plan* p, float* w_prep, const float* x, const float* z, int table_sel, const float* bypass_w,
             bool bypass_transposed, const float* bypass_b, int act, float* y, cudaStream_t s) {
   const pdeqx_spectral_desc& d = p->desc;
   const int c_in = bypass_transposed ? d.c_out : d.c_in, c_out = bypass_transposed ? d.c_in : d.c_out;
-  return tc_slab_ex(p, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return tc_slab_ex(p, w_prep, x, z, table_sel, bypass_w, bypass_transposed, bypass_b, act, 0, nullptr, c_in, c_out, y, s, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 
@@ -1538,7 +1532,7 @@ bool tc_chain_available(const pdeqx_spectral_plan* p, const pdeqx_spectral_plan*
 
 // out[B, C, lead, W] = ( c2r_adj(z1) + w_k^T . g ) * act'( c2r_inv(z_up) + w_up . x_up + bias_up )
 //   byp_u / byp_a (x_up == null): the upstream block's bypass term is rank one, byp_a[c] * byp_u[b, pixel] (+ bias_up)
-int tc_chain(const pdeqx_spectral_plan* p, const float* g, const float* z1, const float* w_k, const pdeqx_spectral_plan* up,
+int tc_chain(const pdeqx_spectral_plan* p, float* w_prep, float* w_prep2, const float* g, const float* z1, const float* w_k, const pdeqx_spectral_plan* up,
              const float* x_up, const float* z_up, const float* w_up, const float* bias_up, int act, float* out, cudaStream_t s,
              const float* byp_u, const float* byp_a) {
   TcPlan* t = tcp(p);
@@ -1572,16 +1566,16 @@ int tc_chain(const pdeqx_spectral_plan* p, const float* g, const float* z1, cons
   }
   {
     const int n = C * C;
-    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_k, t->w_prep, C, C, 1);  // w_k^T: [c_in rows][c_out]
+    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_k, w_prep, C, C, 1);  // w_k^T: [c_in rows][c_out]
     PDEQX_LAUNCHED();
     uint64_t wd[2] = {(uint64_t)C, (uint64_t)C};
     uint64_t ws[1] = {(uint64_t)C * 4};
     uint32_t wb[2] = {32, (uint32_t)C};
-    PDEQX_TRY(tc::make_tensor_map(&tm_w1, t->w_prep, 2, wd, ws, wb));
+    PDEQX_TRY(tc::make_tensor_map(&tm_w1, w_prep, 2, wd, ws, wb));
     if (!byp1) {
-      tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_up, t->w_prep2, C, C, 0);
+      tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_up, w_prep2, C, C, 0);
       PDEQX_LAUNCHED();
-      PDEQX_TRY(tc::make_tensor_map(&tm_w2, t->w_prep2, 2, wd, ws, wb));
+      PDEQX_TRY(tc::make_tensor_map(&tm_w2, w_prep2, 2, wd, ws, wb));
     } else {
       tm_w2 = tm_w1;
     }
@@ -1607,10 +1601,10 @@ int tc_chain(const pdeqx_spectral_plan* p, const float* g, const float* z1, cons
   PDEQX_CHECK_ARG(grid >= cp.wt_per_row, "tc_chain: grid smaller than the number of w-tiles");
 #define PDEQX_CHAIN_LAUNCH(A, B1)                                                                                          \
   do {                                                                                                                     \
-    static bool attr = false;                                                                                              \
-    if (!attr) {                                                                                                           \
+    static DeviceOnce attr;                                                                                                    \
+    if (attr.first_use()) {                                                                                                           \
       PDEQX_CUDA(cudaFuncSetAttribute(tc::chain_kernel<A, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
-      attr = true;                                                                                                         \
+                                                                                                                           \
     }                                                                                                                      \
     tc::chain_kernel<A, B1><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_g, tm_z1, tm_x2, tm_z2, t->tm_tab_c2r[1],          \
                                                                      tu->tm_tab_c2r[0], tm_w1, tm_w2, tm_y, cp, L);        \
@@ -1684,10 +1678,10 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   PDEQX_CHECK_ARG(stages >= 2, "tc_wgrad: shared memory does not fit two stages");
   wp.stages = stages;
   const size_t smem = tab_bytes + (size_t)stages * stage_bytes + 16384 + 1024 + 1024;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;      
+  if (attr.first_use()) {
     PDEQX_CUDA(cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+                
   }
   const int64_t wgroups = ceil_div(wp.rows, tc::kWgGroup);
   const int grid = (int)(wgroups < t->sms ? wgroups : t->sms);
