@@ -73,6 +73,9 @@ const char* pdeqx_version(void);
 uint64_t pdeqx_launch_count(void);
 /* 1 if the tcgen05/TMA fast paths can run on the current device (sm_100). */
 int pdeqx_has_tcgen05(void);
+/* ordinal of the calling thread's current CUDA device (-1 on error): lets a binding key per-device caches (plans)
+ * without linking the CUDA runtime itself. */
+int pdeqx_current_device(void);
 /* force-disable (0) / enable (1) the tcgen05 fast paths (tests compare both). */
 void pdeqx_set_fast_paths(int enabled);
 

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "pdeqx_version": (C.c_char_p, []),
     "pdeqx_launch_count": (C.c_uint64, []),
     "pdeqx_has_tcgen05": (C.c_int, []),
+    "pdeqx_current_device": (C.c_int, []),
     "pdeqx_set_fast_paths": (None, [C.c_int]),
     "pdeqx_timing_enable": (None, [C.c_int]),
     "pdeqx_timing_read": (C.c_int, [_I32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -104,4 +104,9 @@ extern "C" int pdeqx_has_tcgen05(void) {
   return major == 10 ? 1 : 0;
 }
 
+extern "C" int pdeqx_current_device(void) {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 extern "C" void pdeqx_set_fast_paths(int enabled) { pdeqx::g_fast_paths.store(enabled ? 1 : 0); }
