@@ -116,6 +116,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples (= host threads) per CPU-baseline step; 0 = all cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-allreduce", action="store_true", help="bucketed all-reduce on a side stream during the reverse pass")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "allreduce"],
+                    help="gradient exchange of the N > 1 runs: peer-memory kernel (default where available) or NCCL all-reduce")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--print-source-sha", action="store_true", help="print the kernel-source hash that keys profiles/slab_traffic.csv and exit")
     a = ap.parse_args()
@@ -324,7 +326,7 @@ def run_ours(args):
     D, GRID, HIDDEN, MODES, BLOCKS = cfg["ndim"], cfg["grid"], cfg["hidden"], cfg["modes"], cfg["blocks"]
     spatial = (GRID,) * D
     model = pdeqx.ClassicFNO(D, 1, 1, hidden_channels=HIDDEN, num_modes=MODES, num_blocks=BLOCKS, key=0)
-    step = TrainStep(model, lr=3e-4, overlap=args.overlap_allreduce)
+    step = TrainStep(model, lr=3e-4, overlap=args.overlap_allreduce, exchange=args.exchange)
     rng = np.random.default_rng(1234)  # same global batch on every rank, sharded by sample
     xg = rng.standard_normal((args.global_batch, 1) + spatial, dtype=np.float32)
     yg = rng.standard_normal((args.global_batch, 1) + spatial, dtype=np.float32)
@@ -409,6 +411,8 @@ def run_ours(args):
     _lib.check(L.pdeqx_timing_read_ex(_lib.K_SPECTRAL_SLAB, _lib.C.byref(slab_ms), _lib.C.byref(slab_n), _lib.C.byref(slab_bytes_total)))
     L.pdeqx_timing_enable(0)
 
+    if step.peer is not None:
+        step.peer.check()  # every rank arrived at every flag barrier of the exchange
     if rank != 0:
         shutdown(world, graphed)
         return
@@ -529,7 +533,11 @@ def run_ours(args):
         "data": "synthetic",
         "config": config_block(args),
         "details": {"per_gpu_batch": per,
-                   "parallelism": f"dp{world} (batch-sharded, one NCCL all-reduce of the %.1f MB gradient arena per step)" % (step.arena.size * 4 / 1e6),
+                   "parallelism": f"dp{world} (batch-sharded; exchange of the %.1f MB gradient arena per step: %s)" % (
+                       step.arena.size * 4 / 1e6,
+                       "none (one rank)" if world == 1 else
+                       "reduce-scatter + Adam on the rank's shard + all-gather in one kernel over NVLink peer memory" if step.peer is not None
+                       else "one NCCL all-reduce + replicated Adam"),
                    "launch": "one CUDA graph replay per step" if graphed is not None else "eager kernel launches",
                    "precision": args.precision,
                    "activation_tensor_mb_per_rank": per * HIDDEN * n_pix * 4 / 1e6},

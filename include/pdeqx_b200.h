@@ -364,6 +364,39 @@ int pdeqx_adam_step(int64_t n, float* param, const float* grad, float* mu, float
 int pdeqx_adam_step_dev(int64_t n, float* param, const float* grad, float* mu, float* nu, float lr,
                         float b1, float b2, float eps, float* state, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Data-parallel exchange over NVLink peer memory (one process per GPU, one node):
+ * reduce-scatter of the gradient arenas + Adam on the rank's 1/world shard + all-gather of the new parameters in ONE
+ * kernel, instead of an all-reduce followed by a replicated optimiser pass. The reference has no multi-device code
+ * (SURVEY.md 2.2); this is the exchange step of SURVEY.md 8(e).
+ *   - pdeqx_dp_alloc: cudaMalloc'ed (zeroed) buffer of its own -- exportable; hold the parameter arena, the gradient arena
+ *     and the signal pad (pdeqx_dp_pad_bytes) of every rank in such buffers;
+ *   - pdeqx_dp_export / _import: CUDA IPC handle of such a buffer / a pointer to a peer's buffer valid on this device
+ *     (the 64-byte handles travel through whatever the host uses for rendezvous, e.g. torch.distributed.all_gather_object);
+ *   - pdeqx_dp_adam_step: grads[r], params[r], pads[r] for r < world are every rank's buffers as seen from THIS device
+ *     (the rank's own ones included). mu_shard / nu_shard: pdeqx_dp_shard_floats(n, world) floats each (Adam moments of the
+ *     rank's shard only). state: 4 floats as pdeqx_adam_step_dev. loss_io (may be NULL): in = this rank's loss, out = mean
+ *     over the ranks. Enqueues only; ranks synchronise through flags in the signal pads, a wait longer than ~3 s sets an
+ *     error word that pdeqx_dp_check reports (it synchronises the stream).
+ * ------------------------------------------------------------------------- */
+#define PDEQX_MAX_RANKS 8
+typedef struct {
+  int32_t world, rank;
+  float* grads[PDEQX_MAX_RANKS];
+  float* params[PDEQX_MAX_RANKS];
+  uint32_t* pads[PDEQX_MAX_RANKS];
+} pdeqx_dp_peers;
+int pdeqx_dp_alloc(size_t bytes, void** out);
+int pdeqx_dp_free(void* p);
+int pdeqx_dp_export(const void* p, uint8_t handle[64]);
+int pdeqx_dp_import(const uint8_t handle[64], void** out);
+int pdeqx_dp_unimport(void* p);
+size_t pdeqx_dp_pad_bytes(void);
+int64_t pdeqx_dp_shard_floats(int64_t n, int32_t world);
+int pdeqx_dp_adam_step(const pdeqx_dp_peers* peers, int64_t n, float* mu_shard, float* nu_shard, float lr, float b1,
+                       float b2, float eps, float* state, float* loss_io, void* stream);
+int pdeqx_dp_check(const pdeqx_dp_peers* peers, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,26 @@ PROTOTYPES = {
     "pdeqx_adam_step_dev": (C.c_int, [_I64, _P, _P, _P, _P, _F, _F, _F, _F, _P, _F, _P]),
 }
 
+MAX_RANKS = 8
+
+
+class DpPeers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grads", _P * MAX_RANKS), ("params", _P * MAX_RANKS),
+                ("pads", _P * MAX_RANKS)]
+
+
+PROTOTYPES.update({
+    "pdeqx_dp_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "pdeqx_dp_free": (C.c_int, [_P]),
+    "pdeqx_dp_export": (C.c_int, [_P, C.c_char * 64]),
+    "pdeqx_dp_import": (C.c_int, [C.c_char * 64, C.POINTER(_P)]),
+    "pdeqx_dp_unimport": (C.c_int, [_P]),
+    "pdeqx_dp_pad_bytes": (C.c_size_t, []),
+    "pdeqx_dp_shard_floats": (C.c_int64, [_I64, _I32]),
+    "pdeqx_dp_adam_step": (C.c_int, [C.POINTER(DpPeers), _I64, _P, _P, _F, _F, _F, _F, _P, _P, _P]),
+    "pdeqx_dp_check": (C.c_int, [C.POINTER(DpPeers), _P]),
+})
+
 _lib = None
 
 

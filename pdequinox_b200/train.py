@@ -16,11 +16,30 @@ from . import _lib
 from ._module import Tape, _as_device, default_device
 
 
+class _DeviceBuffer:
+    """A float32 buffer from pdeqx_dp_alloc (a cudaMalloc allocation of its own, which CUDA IPC can export -- a slice of
+    torch's caching allocator cannot), wrapped as a torch tensor through __cuda_array_interface__."""
+
+    def __init__(self, n_floats):
+        import ctypes as C
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.lib().pdeqx_dp_alloc(max(int(n_floats), 1) * 4, C.byref(self.ptr)))
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (self.ptr.value, False), "version": 3}
+        self.tensor = torch.as_tensor(self, device=default_device())
+
+    def handle(self):
+        import ctypes as C
+        h = (C.c_char * 64)()
+        _lib.check(_lib.lib().pdeqx_dp_export(self.ptr, h))
+        return bytes(h.raw)
+
+
 class ParameterArena:
     """Re-homes every parameter of `model` into one flat buffer (16-byte aligned slices, pytree order)
-    and gives every parameter a gradient view in a second flat buffer."""
+    and gives every parameter a gradient view in a second flat buffer. `exportable`: hold both arenas in allocations that
+    CUDA IPC can export to the other ranks of the node (the peer-memory exchange of `PeerExchange`)."""
 
-    def __init__(self, model):
+    def __init__(self, model, exportable=False):
         self.model = model
         self.entries = []  # (path, owner, field, offset, numel, shape)
         off = 0
@@ -30,8 +49,13 @@ class ParameterArena:
             off += (t.numel() + 3) // 4 * 4
         self.size = off
         dev = default_device()
-        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.buffers = None
+        if exportable:
+            self.buffers = (_DeviceBuffer(off), _DeviceBuffer(off))
+            self.params, self.grads = self.buffers[0].tensor, self.buffers[1].tensor
+        else:
+            self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
         for path, owner, field, o, n, shape in self.entries:
             view = self.params[o:o + n].view(shape)
             view.copy_(getattr(owner, field))
@@ -66,15 +90,86 @@ def allreduce_gradients_(grads, loss, world, group=None):
     return grads, loss
 
 
-class TrainStep:
-    """One Adam step on mse(vmap(model)(x), y); `world` = a torch.distributed process group (or None)."""
+class PeerExchange:
+    """This rank's view of every rank's parameter arena, gradient arena and signal pad through CUDA IPC: what
+    pdeqx_dp_adam_step (reduce-scatter + Adam on the rank's shard + all-gather, one kernel over NVLink peer memory) needs.
+    The 64-byte IPC handles travel through torch.distributed (plumbing). `ok` is False -- on EVERY rank -- if any rank could
+    not map a peer's memory (ranks on different nodes, no peer access); the caller then keeps the NCCL all-reduce."""
 
-    def __init__(self, model, lr=3e-4, b1=0.9, b2=0.999, eps=1e-8, process_group=None, distributed=None, overlap=False):
+    def __init__(self, arena, group=None):
+        import ctypes as C
+        import socket
+        dist = torch.distributed
+        L = _lib.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.pad = _DeviceBuffer(L.pdeqx_dp_pad_bytes() // 4)
+        self.imported = []
+        mine = (socket.gethostname(), arena.buffers[0].handle(), arena.buffers[1].handle(), self.pad.handle())
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peers = _lib.DpPeers()
+        self.peers.world, self.peers.rank = self.world, self.rank
+        ok = self.world <= _lib.MAX_RANKS and all(e[0] == mine[0] for e in everyone)
+        if ok:
+            for r, (_, hp, hg, hs) in enumerate(everyone):
+                if r == self.rank:
+                    ptrs = (arena.buffers[0].ptr.value, arena.buffers[1].ptr.value, self.pad.ptr.value)
+                else:
+                    ptrs = []
+                    for h in (hp, hg, hs):
+                        out = C.c_void_p()
+                        if ok and L.pdeqx_dp_import((C.c_char * 64).from_buffer_copy(h), C.byref(out)) == 0:
+                            self.imported.append(out)
+                            ptrs.append(out.value)
+                        else:
+                            ok = False
+                            ptrs.append(None)
+                self.peers.params[r], self.peers.grads[r], self.peers.pads[r] = ptrs
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=default_device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.ok = bool(flag.item())
+        self.shard_floats = int(L.pdeqx_dp_shard_floats(arena.size, self.world))
+
+    def check(self):
+        """Raises if a peer rank did not arrive at one of the exchange's flag barriers (synchronises the stream)."""
+        import ctypes as C
+        _lib.check(_lib.lib().pdeqx_dp_check(C.byref(self.peers), _lib.stream()))
+
+    def close(self):
+        for p in self.imported:
+            _lib.lib().pdeqx_dp_unimport(p)
+        self.imported = []
+
+
+class TrainStep:
+    """One Adam step on mse(vmap(model)(x), y); `process_group` = a torch.distributed process group (or None = the default
+    one when initialised). exchange: how the ranks' gradients meet -- "peer": pdeqx_dp_adam_step over NVLink peer memory
+    (needs NCCL ranks of one node, one GPU each); "allreduce": one NCCL / gloo all-reduce of the gradient arena + a replicated
+    Adam pass; "auto" (default): "peer" where it is available."""
+
+    def __init__(self, model, lr=3e-4, b1=0.9, b2=0.999, eps=1e-8, process_group=None, distributed=None, overlap=False,
+                 exchange="auto"):
         self.model = model
-        self.arena = ParameterArena(model)
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        world = torch.distributed.get_world_size(process_group) if distributed else 1
+        want_peer = (distributed and world > 1 and exchange in ("auto", "peer") and not overlap and torch.cuda.is_available()
+                     and torch.distributed.get_backend(process_group) == "nccl")
+        if exchange == "peer" and not want_peer:
+            raise _lib.PdeqxError("exchange='peer' needs an initialised NCCL process group with more than one rank")
+        self.arena = ParameterArena(model, exportable=want_peer)
+        self.peer = None
+        if want_peer:
+            self.peer = PeerExchange(self.arena, process_group)
+            if not self.peer.ok:
+                if exchange == "peer":
+                    raise _lib.PdeqxError("exchange='peer': a rank could not map a peer's memory (different nodes / no peer access)")
+                self.peer.close()
+                self.peer = None
         dev = default_device()
-        self.mu = torch.zeros_like(self.arena.params)
-        self.nu = torch.zeros_like(self.arena.params)
+        n_moments = self.peer.shard_floats if self.peer is not None else self.arena.size
+        self.mu = torch.zeros(n_moments, dtype=torch.float32, device=dev)  # peer exchange: the rank's shard only
+        self.nu = torch.zeros(n_moments, dtype=torch.float32, device=dev)
         self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
         self.count = 0
         self.adam_state = torch.zeros(4, dtype=torch.float32, device=dev)  # device-side step counter + bias corrections
@@ -83,10 +178,8 @@ class TrainStep:
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.partials = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.pg = process_group
-        if distributed is None:
-            distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.distributed = distributed
-        self.world = torch.distributed.get_world_size(process_group) if distributed else 1
+        self.world = world
         # Bucketed exchange (overlap=True): a model that reports finished pytree prefixes during its reverse pass
         # (Sequential) gets each bucket's all-reduce enqueued on a side stream right away. Off by default: measured on
         # 2 x B200 it is SLOWER (6.14 vs 5.94 ms per step) -- the NCCL kernel occupies a few SMs, and the persistent
@@ -134,7 +227,15 @@ class TrainStep:
         return self.loss
 
     def apply_gradients(self):
-        """All-reduce (sum) the gradient arena over the data-parallel group, then Adam with grad/world."""
+        """All-reduce (sum) the gradient arena over the data-parallel group, then Adam with grad/world -- or, with the
+        peer-memory exchange, both in one kernel (reduce-scatter + Adam on this rank's shard + all-gather)."""
+        if self.peer is not None:
+            import ctypes as C
+            self.count += 1
+            _lib.check(_lib.lib().pdeqx_dp_adam_step(C.byref(self.peer.peers), self.arena.size, _lib.ptr(self.mu), _lib.ptr(self.nu),
+                                                     self.lr, self.b1, self.b2, self.eps, _lib.ptr(self.adam_state),
+                                                     _lib.ptr(self.loss), _lib.stream()))
+            return
         if self.distributed:
             covered = sum(hi - lo for lo, hi in self._reduced)
             if self.comm_stream is not None and covered == self.arena.size:

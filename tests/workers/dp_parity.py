@@ -42,21 +42,29 @@ ref = TrainStep(make(), lr=1e-2, distributed=False)  # single process, full batc
 for x, y in zip(xs, ys):
     ref(x, y)
 errs = {}
-for name, overlap in (("eager", False), ("eager+overlap", True)):
-    if overlap and backend != "nccl":
-        continue  # the side-stream bucket exchange is an NCCL-stream feature
-    dp = TrainStep(make(), lr=1e-2, overlap=overlap)
+# exchange paths: NCCL ranks default to the peer-memory kernel (reduce-scatter + Adam + all-gather over NVLink); the
+# all-reduce path (the only one gloo has) and its bucketed, overlapped variant are kept covered explicitly
+cases = [("allreduce", dict(exchange="allreduce"))]
+if backend == "nccl":
+    cases += [("peer", dict(exchange="peer")), ("allreduce+overlap", dict(overlap=True))]
+for name, kw in cases:
+    dp = TrainStep(make(), lr=1e-2, **kw)
+    assert (dp.peer is not None) == (name == "peer"), name
     for x, y in zip(xs, ys):
         loss = dp(shard_batch(x, rank, world), shard_batch(y, rank, world))
+    if dp.peer is not None:
+        dp.peer.check()
     errs[name] = rel(dp.arena.params, ref.arena.params)
     assert abs(loss.item() - ref.loss.item()) <= 10 * tol * abs(ref.loss.item()), (name, loss.item(), ref.loss.item())
-if backend == "nccl":  # graph capture of a step needs a capturable collective
+if backend == "nccl":  # graph capture of a step needs a capturable exchange: the peer-memory kernels (default) are plain kernels
     gp = TrainStep(make(), lr=1e-2)
+    assert gp.peer is not None
     g = GraphedTrainStep(gp, torch.from_numpy(shard_batch(xs[0], rank, world)), torch.from_numpy(shard_batch(ys[0], rank, world)),
                          warmup=1)
     for x, y in zip(xs, ys):
         g(torch.from_numpy(shard_batch(x, rank, world)).cuda(), torch.from_numpy(shard_batch(y, rank, world)).cuda())
-    errs["graph"] = rel(gp.arena.params, ref.arena.params)
+    gp.peer.check()
+    errs["graph+peer"] = rel(gp.arena.params, ref.arena.params)
     g.graph.reset()
 torch.cuda.synchronize()
 if rank == 0:
