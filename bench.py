@@ -409,6 +409,11 @@ def run_ours(args):
     ms_probe = timed(lambda: step(xd, yd), probe_steps)
     slab_ms, slab_n, slab_bytes_total = _lib.C.c_double(), _lib.C.c_int64(), _lib.C.c_double()
     _lib.check(L.pdeqx_timing_read_ex(_lib.K_SPECTRAL_SLAB, _lib.C.byref(slab_ms), _lib.C.byref(slab_n), _lib.C.byref(slab_bytes_total)))
+    exchange_us = None
+    if step.peer is not None:
+        ex_ms, ex_n = _lib.C.c_double(), _lib.C.c_int64()
+        _lib.check(L.pdeqx_timing_read(_lib.K_DP_EXCHANGE, _lib.C.byref(ex_ms), _lib.C.byref(ex_n)))
+        exchange_us = ex_ms.value * 1e3 / max(ex_n.value, 1)
     L.pdeqx_timing_enable(0)
 
     if step.peer is not None:
@@ -540,6 +545,7 @@ def run_ours(args):
                        else "one NCCL all-reduce + replicated Adam"),
                    "launch": "one CUDA graph replay per step" if graphed is not None else "eager kernel launches",
                    "precision": args.precision,
+                   "exchange_us_per_step_rank0": exchange_us,  # peer-memory exchange incl. the wait for the slowest rank (eager probe steps)
                    "activation_tensor_mb_per_rank": per * HIDDEN * n_pix * 4 / 1e6},
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4) * world, "d2h_bytes_per_step": 4 * world},

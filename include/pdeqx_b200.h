@@ -90,7 +90,8 @@ enum pdeqx_kernel_tag {
   PDEQX_K_CONV_FWD = 5,
   PDEQX_K_CONV_BWD_DATA = 6,
   PDEQX_K_CONV_BWD_FILTER = 7,
-  PDEQX_K_TAG_COUNT = 8
+  PDEQX_K_DP_EXCHANGE = 8,   /* pdeqx_dp_adam_step: reduce-scatter + Adam + all-gather (includes the wait for the slowest rank) */
+  PDEQX_K_TAG_COUNT = 9
 };
 void pdeqx_timing_enable(int enabled); /* also clears what was recorded */
 int pdeqx_timing_read(int32_t tag, double* total_ms, int64_t* launches);

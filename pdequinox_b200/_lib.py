@@ -13,7 +13,7 @@ MAX_DIMS = 3
 ACT_IDENTITY, ACT_RELU, ACT_GELU_TANH = 0, 1, 2
 PAD_ZEROS, PAD_WRAP, PAD_REFLECT, PAD_EDGE = 0, 1, 2, 3
 PREC_FP32, PREC_TF32 = 0, 1
-K_SPECTRAL_SLAB, K_SPECTRAL_R2C, K_SPECTRAL_MODES, K_POINTWISE_WGRAD, K_CONV_FWD, K_CONV_BWD_DATA, K_CONV_BWD_FILTER = range(1, 8)
+K_SPECTRAL_SLAB, K_SPECTRAL_R2C, K_SPECTRAL_MODES, K_POINTWISE_WGRAD, K_CONV_FWD, K_CONV_BWD_DATA, K_CONV_BWD_FILTER, K_DP_EXCHANGE = range(1, 9)
 
 LIB_PATH = os.environ.get("PDEQX_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpdeqx_b200.so")
 

@@ -75,10 +75,16 @@ dp_adam_kernel(pdeqx_dp_peers P, int64_t n, float* __restrict__ mu, float* __res
   const int64_t lo = (int64_t)P.rank * per, hi = lo + per < nv ? lo + per : nv;
   float4* const own = (float4*)P.params[P.rank];
   for (int64_t v = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += (int64_t)gridDim.x * blockDim.x) {
-    float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < P.world; ++r) {  // fixed order: every replica of the job computes bit-identical parameters
-      const float4 g = __ldcv((const float4*)P.grads[r] + v);  // peer memory, rewritten every step: never from a stale cache line
-      gs.x += g.x; gs.y += g.y; gs.z += g.z; gs.w += g.w;
+    // all N loads are issued before the first add (a peer load takes microseconds: serialised they would bound the kernel);
+    // peer memory is rewritten every step: ld.cv, never from a stale cache line
+    float4 g[PDEQX_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < PDEQX_MAX_RANKS; ++r)
+      g[r] = r < P.world ? __ldcv((const float4*)P.grads[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gs = g[0];
+#pragma unroll
+    for (int r = 1; r < PDEQX_MAX_RANKS; ++r) {  // fixed order: every replica of the job computes bit-identical parameters
+      gs.x += g[r].x; gs.y += g[r].y; gs.z += g[r].z; gs.w += g[r].w;
     }
     const float4 pv = own[v], mv = ((float4*)mu)[v - lo], vv = ((float4*)nu)[v - lo];
     float pe[4] = {pv.x, pv.y, pv.z, pv.w}, ge[4] = {gs.x, gs.y, gs.z, gs.w};
@@ -167,6 +173,8 @@ extern "C" int pdeqx_dp_adam_step(const pdeqx_dp_peers* peers, int64_t n, float*
                         ((uintptr_t)peers->params[r] & 15) == 0,
                     "peer %d: null or unaligned arena pointers", r);
   cudaStream_t s = (cudaStream_t)stream;
+  TimedScope timed(PDEQX_K_DP_EXCHANGE, s);
+  timed_bytes(4.0 * (double)n * (2.0 * (peers->world - 1) / peers->world + 4.0 / peers->world));  // NVLink in + out, local p / mu / nu
   dp_tick_kernel<<<1, 1, 0, s>>>(state, b1, b2);
   PDEQX_LAUNCHED();
   const int64_t per = pdeqx_dp_shard_floats(n, peers->world) / 4;

@@ -182,6 +182,11 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc,
   const int src_bytes = pred ? BYTES : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(gsrc), "n"(BYTES), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_zfill16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int src_bytes = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -225,12 +230,26 @@ mode_gemm_tiled_kernel(TiledArgs t) {
       const int q = idx % PT, n = (idx / PT) % NT, k = idx / (PT * NT);
       const bool ok = n0 + n < t.N && k0 + k < t.K;
       if (B_PLANAR) {
-        const int64_t off = ok ? (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + woff + q : 0;
-        cp_async_zfill<4>(&Bs[idx].x, t.br + off, ok);
-        cp_async_zfill<4>(&Bs[idx].y, t.bi + off, ok);
+        break;  // (staged below as two planes with 16-byte copies)
       } else {
         const float2* src = ok ? t.b2 + (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + p0 + q : t.b2;
         cp_async_zfill<8>(Bs + idx, src, ok);
+      }
+    }
+    if (B_PLANAR) {
+      // weights: re / im planes of the reference layout, PT consecutive modes = one contiguous run per (n, k): kept planar in
+      // shared memory ([KC][NT][PT] floats each) so that a run moves as 16-byte copies -- at a few samples per GPU this kernel
+      // is a pure stream over the weights and was bound by the number of 4-byte copy instructions
+      float* Bre = (float*)Bs;
+      float* Bim = Bre + B_ELEMS;
+      constexpr int P4 = PT / 4;
+      for (int idx = tid; idx < B_ELEMS / 4; idx += 256) {
+        const int q4 = idx % P4, n = (idx / P4) % NT, k = idx / (P4 * NT);
+        const bool ok = n0 + n < t.N && k0 + k < t.K;
+        const int64_t off = ok ? (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + woff + q4 * 4 : 0;
+        const int dst = (k * NT + n) * PT + q4 * 4;
+        cp_async_zfill16(Bre + dst, t.br + off, ok);
+        cp_async_zfill16(Bim + dst, t.bi + off, ok);
       }
     }
     cp_async_commit();
@@ -256,7 +275,12 @@ mode_gemm_tiled_kernel(TiledArgs t) {
       for (int r = 0; r < RT; ++r) a[r] = As[(k * TM_MT + mq + 8 * r) * PT + pm];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        b[cc] = Bs[(k * NT + nq * 4 + cc) * PT + pm];
+        if (B_PLANAR) {
+          const float* Bre = (const float*)Bs;
+          b[cc] = make_float2(Bre[(k * NT + nq * 4 + cc) * PT + pm], Bre[B_ELEMS + (k * NT + nq * 4 + cc) * PT + pm]);
+        } else {
+          b[cc] = Bs[(k * NT + nq * 4 + cc) * PT + pm];
+        }
         if (CONJ_B) b[cc].y = -b[cc].y;
       }
 #pragma unroll
@@ -356,7 +380,8 @@ int mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re, c
     t.b_sk = transposed_conj ? (int64_t)I * t.mm.mprod : t.mm.mprod;
     t.c2 = (float2*)out; t.c_sm = (int64_t)U * p->J; t.c_sn = p->J;
     t.M = d.batch; t.N = U; t.K = V; t.J = p->J; t.w_corner = (int64_t)O * I * t.mm.mprod;
-    const bool ok = transposed_conj ? launch_tiled<true, false, true>(t, s) : launch_tiled<true, false, false>(t, s);
+    const bool aligned = (((uintptr_t)w_re | (uintptr_t)w_im) & 15) == 0 && t.mm.mprod % 4 == 0;  // 16-byte weight copies
+    const bool ok = aligned && (transposed_conj ? launch_tiled<true, false, true>(t, s) : launch_tiled<true, false, false>(t, s));
     if (ok) { PDEQX_LAUNCHED(); return PDEQX_OK; }
   }
   dim3 grid((unsigned)ceil_div(p->J, 16), (unsigned)ceil_div(d.batch, 16), (unsigned)ceil_div(U, 16));
