@@ -280,10 +280,12 @@ int pdeqx_conv_out_spatial(const pdeqx_conv_desc* d, int32_t out_spatial[PDEQX_M
 int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b,
                    const float* residual, int32_t activation, float* y, void* workspace, size_t workspace_bytes,
                    void* stream);
-/* gx = adjoint-of-pad( corr^T(gy, w) ) + add, overwritten; add [B,c_in,*S] may be NULL (it carries
- * the cotangent of a residual connection into the same pass) */
+/* gx = ( adjoint-of-pad( corr^T(gy, w) ) + add ) * [relu_mask > 0], overwritten. add [B,c_in,*S] may be NULL (it carries
+ * the cotangent of a residual connection into the same pass). relu_mask [B,c_in,*S] may be NULL: the OUTPUT of the relu
+ * layer whose result this convolution read (pdequinox/blocks/_classic_res_block.py:112-121: conv_2(act(conv_1(x)))) --
+ * its derivative is applied where the cotangent is produced instead of in an elementwise pass of its own. */
 int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add,
-                        float* gx, void* workspace, size_t workspace_bytes, void* stream);
+                        const float* relu_mask, float* gx, void* workspace, size_t workspace_bytes, void* stream);
 /* gw[c_out,c_in/groups,*k] = sum_{b,p} gy . pad(x); gb[c_out] = sum gy (may be NULL); overwritten */
 int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, float* gw,
                           float* gb, void* workspace, size_t workspace_bytes, void* stream);

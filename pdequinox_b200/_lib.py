@@ -90,7 +90,7 @@ PROTOTYPES = {
     "pdeqx_conv_pair_launches": (C.c_int64, []),
     "pdeqx_conv_out_spatial": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
     "pdeqx_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _I32, _P, _P, C.c_size_t, _P]),
-    "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_conv_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_conv_bwd_filter": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pdeqx_convT_out_spatial": (C.c_int, [C.POINTER(ConvTDesc), C.POINTER(C.c_int32 * MAX_DIMS)]),
     "pdeqx_convT_fwd": (C.c_int, [C.POINTER(ConvTDesc), _P, _P, _P, _P, _P]),

@@ -101,6 +101,7 @@ class Sequential(Module):
                 g = self.projection._bwd(gy, tape, True)
             hook("projection.")
         gpre_ready = False  # True: `g` is the cotangent of the next block's pre-activation (chained reverse pass)
+        premasked = False   # True: `g` already carries the relu' of the next ResNet block's output
         for i in reversed(range(nb)):
             kw = {}
             if fold_proj and i == nb - 1:
@@ -131,8 +132,22 @@ class Sequential(Module):
                 if chain is not None:
                     kw["chain"] = chain
                     gpre_ready = True
+            # two consecutive relu ResNet blocks: block i forms its input gradient already multiplied by relu' of block i-1's
+            # output (its own input), so block i-1 skips that elementwise pass (ClassicResBlock._bwd)
+            res_kw = {}
+            if hasattr(self.blocks[i], "relu_output_saved"):
+                if premasked:
+                    res_kw["gy_premasked"] = True
+                premasked = False
+                if (i > 0 and self.chain_reverse and hasattr(self.blocks[i - 1], "relu_output_saved")
+                        and self.blocks[i].relu_output_saved(tape.stack[-1])
+                        and self.blocks[i - 1].relu_output_saved(tape.stack[-2])):
+                    res_kw["mask_gx"] = True
+                    premasked = True
             if kw:
                 g = self.blocks[i]._bwd_ex(g, tape, True, **kw)
+            elif res_kw:
+                g = self.blocks[i]._bwd(g, tape, True, **res_kw)
             else:
                 g = self.blocks[i]._bwd(g, tape, True)
             if projected_fwd and i == nb - 1:

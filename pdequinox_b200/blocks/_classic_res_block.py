@@ -67,19 +67,32 @@ class ClassicResBlock(Block):
             tape.push((x, h, p1, y, p2))
         return y
 
-    def _bwd(self, gy, tape, need_gx=True):
+    def _bwd(self, gy, tape, need_gx=True, gy_premasked=False, mask_gx=False):
+        """gy_premasked: `gy` already carries this block's output relu' (the block behind applied it while forming its input
+        gradient, see mask_gx). mask_gx: this block's input is the relu output of the block in front: its relu' is applied by
+        the kernel that forms the input gradient, which is then that block's pre-activation cotangent (no pass of its own)."""
         act = nn.activation_code(self.activation)
         if self.use_norm:
             return self._bwd_norm(gy, tape, need_gx, act)
         x, h, p1, y, p2 = tape.pop()
-        g2 = nn.activation_bwd(p2 if p2 is not None else y, gy, act, tape, self, "g2")
-        gh = self.conv_2.apply_bwd(h, g2, tape, True, tag="gh")
-        g1 = nn.activation_bwd(p1 if p1 is not None else h, gh, act, tape, self, "g1")
+        g2 = gy if gy_premasked else nn.activation_bwd(p2 if p2 is not None else y, gy, act, tape, self, "g2")
+        # relu' of the inner activation rides on the data-gradient kernel of conv_2 (relu'(p1) = [h > 0]); other activations
+        # keep their elementwise pass
+        inner_fused = act == _lib.ACT_RELU and p1 is None
+        gh = self.conv_2.apply_bwd(h, g2, tape, True, tag="gh", relu_mask=h if inner_fused else None)
+        g1 = gh if inner_fused else nn.activation_bwd(p1 if p1 is not None else h, gh, act, tape, self, "g1")
+        mask = x if (mask_gx and need_gx) else None
         identity_skip = isinstance(self.bypass_conv, Identity)
         if identity_skip:  # cotangent of the skip joins inside the data-gradient pass
-            return self.conv_1.apply_bwd(x, g1, tape, need_gx, tag="gx", add=g2)
+            return self.conv_1.apply_bwd(x, g1, tape, need_gx, tag="gx", add=g2, relu_mask=mask)
         gskip = self.bypass_conv.apply_bwd(x, g2, tape, need_gx, tag="gskip")
-        return self.conv_1.apply_bwd(x, g1, tape, need_gx, tag="gx", add=gskip)
+        return self.conv_1.apply_bwd(x, g1, tape, need_gx, tag="gx", add=gskip, relu_mask=mask)
+
+    def relu_output_saved(self, record):
+        """True if `record` (what this block's forward pass pushed) holds the block's relu OUTPUT, i.e. the block behind may
+        apply this block's relu' through `mask_gx`."""
+        return (not self.use_norm and nn.activation_code(self.activation) == _lib.ACT_RELU and isinstance(record, tuple)
+                and len(record) == 5 and record[4] is None)
 
     # ---- with GroupNorm (unfused ordering) ----
     def _fwd_norm(self, x, tape, act):

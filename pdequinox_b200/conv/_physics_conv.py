@@ -93,7 +93,10 @@ class MorePaddingConv(Module):
                                              _lib.stream()))
         return y
 
-    def apply_bwd(self, x, gy, tape, need_gx=True, tag="gx", add=None):
+    def apply_bwd(self, x, gy, tape, need_gx=True, tag="gx", add=None, relu_mask=None):
+        """Filter / bias gradients into the bound gradient buffers; returns the input gradient (+ `add`, the cotangent of a
+        residual connection joining here), zeroed where `relu_mask` <= 0 (the output of the relu layer that produced x: its
+        derivative is applied by the kernel that forms the cotangent)."""
         d, _ = self._desc(x)
         L = _lib.lib()
         gb = self.grad("bias") if self.bias is not None else None
@@ -104,7 +107,7 @@ class MorePaddingConv(Module):
         if not need_gx:
             return None
         gx = new_buf(tape, self, tag, x.shape)
-        _lib.check(L.pdeqx_conv_bwd_data(d, _lib.ptr(gy), _lib.ptr(self.weight), _lib.ptr(add), _lib.ptr(gx),
+        _lib.check(L.pdeqx_conv_bwd_data(d, _lib.ptr(gy), _lib.ptr(self.weight), _lib.ptr(add), _lib.ptr(relu_mask), _lib.ptr(gx),
                                          ws, nws, _lib.stream()))
         return gx
 

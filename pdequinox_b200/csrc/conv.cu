@@ -496,8 +496,8 @@ extern "C" int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const fl
   return PDEQX_OK;
 }
 
-extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add, float* gx,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* add,
+                                   const float* relu_mask, float* gx, void* workspace, size_t workspace_bytes, void* stream) {
   PDEQX_CHECK_ARG(gy && w && gx, "null argument");
   ConvGeom g;
   PDEQX_TRY(conv_geometry(d, &g));
@@ -507,10 +507,16 @@ extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, co
     return PDEQX_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (tc_conv_bwd_data_available(g)) return tc_conv_bwd_data(g, gy, w, add, gx, workspace, workspace_bytes, s);
   const int64_t total = (int64_t)g.batch * g.c_in * g.n_in;
-  conv_bwd_data_kernel<false><<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
-  PDEQX_LAUNCHED();
+  bool masked = false;  // the tcgen05 kernels zero the masked elements in their epilogue; every other path in a pass behind
+  if (tc_conv_bwd_data_available(g)) {
+    PDEQX_TRY(tc_conv_bwd_data(g, gy, w, add, relu_mask, gx, workspace, workspace_bytes, s));
+    masked = g.boundary != PDEQX_PAD_REFLECT;
+  } else {
+    conv_bwd_data_kernel<false><<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
+    PDEQX_LAUNCHED();
+  }
+  if (relu_mask && !masked) return pdeqx_activation_bwd(total, relu_mask, gx, PDEQX_ACT_RELU, gx, stream);
   return PDEQX_OK;
 }
 

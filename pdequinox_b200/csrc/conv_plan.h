@@ -27,8 +27,9 @@ bool tc_conv_bwd_filter_available(const ConvGeom& g);
 size_t tc_conv_workspace_bytes(const ConvGeom& g);
 int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* residual, int act,
                 float* y, void* ws, size_t ws_bytes, cudaStream_t s);
-int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, void* ws, size_t ws_bytes,
-                     cudaStream_t s);
+// relu_mask: applied in the kernel's epilogue except for the neumann boundary (two-pass data gradient: the caller masks)
+int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, const float* relu_mask, float* gx,
+                     void* ws, size_t ws_bytes, cudaStream_t s);
 int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws, size_t ws_bytes,
                        cudaStream_t s);
 

@@ -38,6 +38,8 @@ struct ConvParams {
   const float* bias;
   float* y;          // pair kernel: output / residual as plain pointers (its epilogue stores from registers)
   const float* res;
+  const float* mask;  // optional [B, c_out, H, W]: the result is zeroed where mask <= 0 (relu' of the layer in front, applied
+                      // in the data-gradient pass that produces its cotangent instead of in a pass of its own)
 };
 
 struct ConvSmem {
@@ -355,6 +357,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
           if (p.has_residual) r += res[jx];
           if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
           else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
+          if (p.mask && __ldg(p.mask + (((int64_t)ch0 + jx) * p.H + h) * p.W + wq) <= 0.f) r = 0.f;
           // the next consumer is a tcgen05 stage (conv / data gradient / filter gradient), which would TRUNCATE fp32 to
           // tf32 (a coherent bias of about -2^-12 per layer): round to nearest here
           r = round_tf32(r);
@@ -572,10 +575,14 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           // this lane's 8 output elements: pixel (h, wq) of 8 consecutive channel planes; a warp-wide store per channel is one
           // full 128-byte line, so the pass needs no staging tile, no async-proxy fence and no wait on an earlier TMA store
           const int64_t off0 = (((int64_t)chb + ps * ocnt) * p.H + h) * p.W + wq;
-          float res[ocnt];
+          float res[ocnt], msk[ocnt];
           if (p.has_residual) {
 #pragma unroll
             for (int jx = 0; jx < ocnt; ++jx) res[jx] = __ldg(p.res + off0 + (int64_t)jx * plane);
+          }
+          if (p.mask) {
+#pragma unroll
+            for (int jx = 0; jx < ocnt; ++jx) msk[jx] = __ldg(p.mask + off0 + (int64_t)jx * plane);
           }
           float v0[ocnt], v1[ocnt], v2[ocnt];
           tmem_ld8(t0, v0);
@@ -645,6 +652,7 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             float r = acc[jx] + (in0 ? s0[jx] : f0[jx]) + (in2 ? s2[jx] : f2[jx]);
             if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
             else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
+            if (p.mask && msk[jx] <= 0.f) r = 0.f;
 #if defined(PDEQX_CONV_DIAG) && PDEQX_CONV_DIAG == 3  // timing experiment: full epilogue arithmetic, no stores
             if (r == 123.456f) p.y[off0] = r;
 #else
@@ -1148,7 +1156,8 @@ static int check_conv_ws(const ConvGeom& g, void* ws, size_t ws_bytes) {
 }
 
 static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, bool flip, const float* bias,
-                            const float* residual, int act, float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
+                            const float* residual, int act, float* y, void* ws, size_t ws_bytes, cudaStream_t s,
+                            const float* mask = nullptr) {
   int dev = 0, sms = 148;
   PDEQX_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1198,6 +1207,7 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   cp.bias = bias;
   cp.y = y;
   cp.res = residual;
+  cp.mask = mask;
   cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image * 2;
   tc::ConvSmem L = tc::conv_smem(c_in, c_out, k);
   PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv: shared memory budget exceeded (%u bytes)", L.total);
@@ -1282,13 +1292,14 @@ int tc_conv_fwd(const ConvGeom& g, const float* x, const float* w, const float* 
 
 bool tc_conv_bwd_data_available(const ConvGeom& g) { return tc_conv_available(g); }
 
-int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, float* gx, void* ws, size_t ws_bytes,
-                     cudaStream_t s) {
+int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* add, const float* relu_mask, float* gx,
+                     void* ws, size_t ws_bytes, cudaStream_t s) {
   TimedScope timed(PDEQX_K_CONV_BWD_DATA, s);
-  if (g.boundary != PDEQX_PAD_REFLECT) return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, ws, ws_bytes, s);
+  if (g.boundary != PDEQX_PAD_REFLECT)
+    return conv_rows_launch(g, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, ws, ws_bytes, s, relu_mask);
   // neumann: the adjoint of a reflect pad is a FOLD, not a convolution. The zero-extended part is the same implicit GEMM
   // (dirichlet data gradient); what arrives through mirrored halo positions only touches a frame of width d and is added
-  // by the CUDA-core gather.
+  // by the CUDA-core gather (the relu mask, if any, is applied by the caller after that).
   ConvGeom z = g;
   z.boundary = PDEQX_PAD_ZEROS;
   PDEQX_TRY(conv_rows_launch(z, gy, w, true, nullptr, add, PDEQX_ACT_IDENTITY, gx, ws, ws_bytes, s));

@@ -15,7 +15,7 @@
 // Only the plain-C call-frame ABI (xla/ffi/api/c_api.h) is used -- no C++ template layer -- so the shim has no build
 // dependency beyond that one header. Build: `make xla_ffi` (Makefile): against jaxlib's header when `import jax.ffi`
 // works, else against the minimal restatement under stub/ (compile check + the call-frame tests of this repository).
-// The JAX side (registration, custom_vjp, custom_vmap) is pdequinox_b200/jax/.
+// The JAX side (registration, custom_vjp, custom_vmap) is pdequinox_b200/jax_ffi/.
 //
 // Contract of every handler: XLA owns all buffers; a handler only ENQUEUES on the stream XLA hands it, never
 // synchronises, never allocates device memory at execute time (scratch arrives as an extra result buffer; spectral
@@ -266,7 +266,7 @@ int64_t pixels(const XLA_FFI_Buffer* x) {  // product of the spatial dims of [B,
 }  // namespace
 
 // ==========================================================================================
-// trace-time helper (called through ctypes by pdequinox_b200/jax/_ffi.py to size the result buffers of the spectral ops):
+// trace-time helper (called through ctypes by pdequinox_b200/jax_ffi/_ffi.py to size the result buffers of the spectral ops):
 // sizes[0..2] = floats of x_hat, floats of z, BYTES of the workspace. Creates (and caches) the plan on the current device.
 // ==========================================================================================
 extern "C" int pdeqx_ffi_spectral_sizes(const pdeqx_spectral_desc* d, size_t sizes[3]) {
@@ -366,7 +366,7 @@ extern "C" XLA_FFI_Error* pdeqx_ffi_conv_bwd(XLA_FFI_CallFrame* call_frame) {
   if ((err = fr.status(pdeqx_conv_bwd_filter(&d, fr.in(0), fr.in(1), fr.out(1), fr.opt_out(2), fr.out(3), fr.out_bytes(3), stream),
                        "pdeqx_conv_bwd_filter")))
     return err;
-  return fr.status(pdeqx_conv_bwd_data(&d, fr.in(1), fr.in(2), fr.opt(3), fr.out(0), fr.out(3), fr.out_bytes(3), stream),
+  return fr.status(pdeqx_conv_bwd_data(&d, fr.in(1), fr.in(2), fr.opt(3), nullptr, fr.out(0), fr.out(3), fr.out_bytes(3), stream),
                    "pdeqx_conv_bwd_data");
 }
 

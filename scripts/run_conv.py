@@ -30,6 +30,6 @@ nws = L.pdeqx_conv_workspace_bytes(desc)
 ws = torch.empty(nws // 4 + 1, device="cuda")
 gb = 4 * B * 64 * 128 * 128 * 2 / 1e9
 tf = t(lambda: _lib.check(L.pdeqx_conv_fwd(desc, _lib.ptr(x), _lib.ptr(conv.weight), _lib.ptr(conv.bias), None, 1, _lib.ptr(y), _lib.ptr(ws), nws, _lib.stream())))
-td = t(lambda: _lib.check(L.pdeqx_conv_bwd_data(desc, _lib.ptr(gy), _lib.ptr(conv.weight), None, _lib.ptr(gx), _lib.ptr(ws), nws, _lib.stream())))
+td = t(lambda: _lib.check(L.pdeqx_conv_bwd_data(desc, _lib.ptr(gy), _lib.ptr(conv.weight), None, None, _lib.ptr(gx), _lib.ptr(ws), nws, _lib.stream())))
 tw = t(lambda: _lib.check(L.pdeqx_conv_bwd_filter(desc, _lib.ptr(x), _lib.ptr(gy), _lib.ptr(conv.grad("weight")), _lib.ptr(conv.grad("bias")), _lib.ptr(ws), nws, _lib.stream())), n=2)
 print(f"conv 3x3 64->64 B={B} d={d} {mode} {prec}: fwd {tf:.1f} us ({gb/tf*1e6:.0f} GB/s), bwd_data {td:.1f} us ({gb/td*1e6:.0f} GB/s), bwd_filter {tw:.1f} us ({gb/tw*1e6:.0f} GB/s)")
