@@ -515,10 +515,16 @@ def run_ours(args):
         reps = 100  # ~25 ms back to back: long enough for the clocks to settle under this kernel
         ms_c = timed(conv_fwd, reps) / reps
         conv_bytes = 4 * 128 * (64 + 64) * 128 * 128 + 4 * 64 * (64 * 9 + 1)
-        physics = {"bound": "hbm (at the TF32 ridge: 144 flop/B)", "kernel": "PhysicsConv 3x3 64->64 fwd + bias + relu, 128x128, batch 128, periodic",
+        tflops = 2 * 64 * 64 * 9 * 128 * 128 * 128 / (ms_c * 1e-3) / 1e12
+        # 144 flop per algorithmic byte puts this layer ON the TF32 ridge: the HBM fraction is the north star's target figure, the
+        # tensor fraction says what actually bounds the kernel (TF32 dense peak taken as half of the measured bf16 figure, the
+        # sustained one: the probe runs the kernel back to back)
+        tf32_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.6)) / 2.0
+        physics = {"bound": "tensor (tf32) -- at the ridge: 144 flop/B", "kernel": "PhysicsConv 3x3 64->64 fwd + bias + relu, 128x128, batch 128, periodic",
                    "achieved": conv_bytes / (ms_c * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                    "frac": conv_bytes / (ms_c * 1e-3) / 1e9 / hbm_peak, "avg_launch_us": ms_c * 1e3,
-                   "tflops": 2 * 64 * 64 * 9 * 128 * 128 * 128 / (ms_c * 1e-3) / 1e12,
+                   "tflops": tflops, "tensor_peak_tflops": tf32_peak, "tensor_frac": tflops / tf32_peak,
+                   "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (derived: tf32 runs at half the bf16 rate)" if peaks else "fallback",
                    "tcgen05_passes": int(L.pdeqx_conv_tcgen05_passes(desc))}
         del xc, yc
 

@@ -376,6 +376,7 @@ int pdeqx_adam_step_dev(int64_t n, float* param, const float* grad, float* mu, f
  *     and the signal pad (pdeqx_dp_pad_bytes) of every rank in such buffers;
  *   - pdeqx_dp_export / _import: CUDA IPC handle of such a buffer / a pointer to a peer's buffer valid on this device
  *     (the 64-byte handles travel through whatever the host uses for rendezvous, e.g. torch.distributed.all_gather_object);
+ *     any other way of obtaining peer-mapped (and multicast-mapped) pointers works as well, e.g. torch's symmetric memory;
  *   - pdeqx_dp_adam_step: grads[r], params[r], pads[r] for r < world are every rank's buffers as seen from THIS device
  *     (the rank's own ones included). mu_shard / nu_shard: pdeqx_dp_shard_floats(n, world) floats each (Adam moments of the
  *     rank's shard only). state: 4 floats as pdeqx_adam_step_dev. loss_io (may be NULL): in = this rank's loss, out = mean
@@ -388,6 +389,12 @@ typedef struct {
   float* grads[PDEQX_MAX_RANKS];
   float* params[PDEQX_MAX_RANKS];
   uint32_t* pads[PDEQX_MAX_RANKS];
+  /* optional NVSwitch multicast (NVLS) addresses of the SAME gradient / parameter arenas (one multicast object bound to
+   * every rank's buffer; NULL = not available): the kernel then sums the N gradient slices with ONE multimem.ld_reduce
+   * per 16 bytes (the switch reduces: 1/N of the arena crosses this GPU's links instead of (N-1)/N) and publishes the
+   * new parameters with ONE multimem.st (the switch replicates). */
+  float* mc_grads;
+  float* mc_params;
 } pdeqx_dp_peers;
 int pdeqx_dp_alloc(size_t bytes, void** out);
 int pdeqx_dp_free(void* p);

@@ -114,7 +114,7 @@ MAX_RANKS = 8
 
 class DpPeers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grads", _P * MAX_RANKS), ("params", _P * MAX_RANKS),
-                ("pads", _P * MAX_RANKS)]
+                ("pads", _P * MAX_RANKS), ("mc_grads", _P), ("mc_params", _P)]
 
 
 PROTOTYPES.update({

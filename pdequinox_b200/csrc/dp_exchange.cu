@@ -33,6 +33,21 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// NVSwitch multicast (NVLS): one load that returns the SUM over every device bound to the multicast object / one store that
+// the switch replicates to all of them
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 // spin until *flag >= epoch (wrap-safe); false on timeout
 __device__ __forceinline__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
   const long long t0 = clock64();
@@ -77,14 +92,19 @@ dp_adam_kernel(pdeqx_dp_peers P, int64_t n, float* __restrict__ mu, float* __res
   for (int64_t v = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < hi; v += (int64_t)gridDim.x * blockDim.x) {
     // all N loads are issued before the first add (a peer load takes microseconds: serialised they would bound the kernel);
     // peer memory is rewritten every step: ld.cv, never from a stale cache line
-    float4 g[PDEQX_MAX_RANKS];
+    float4 gs;
+    if (P.mc_grads) {
+      gs = multimem_ld_reduce_add((const float4*)P.mc_grads + v);  // summed inside the switch
+    } else {
+      float4 g[PDEQX_MAX_RANKS];
 #pragma unroll
-    for (int r = 0; r < PDEQX_MAX_RANKS; ++r)
-      g[r] = r < P.world ? __ldcv((const float4*)P.grads[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 gs = g[0];
+      for (int r = 0; r < PDEQX_MAX_RANKS; ++r)
+        g[r] = r < P.world ? __ldcv((const float4*)P.grads[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gs = g[0];
 #pragma unroll
-    for (int r = 1; r < PDEQX_MAX_RANKS; ++r) {  // fixed order: every replica of the job computes bit-identical parameters
-      gs.x += g[r].x; gs.y += g[r].y; gs.z += g[r].z; gs.w += g[r].w;
+      for (int r = 1; r < PDEQX_MAX_RANKS; ++r) {  // fixed order: every replica of the job computes bit-identical parameters
+        gs.x += g[r].x; gs.y += g[r].y; gs.z += g[r].z; gs.w += g[r].w;
+      }
     }
     const float4 pv = own[v], mv = ((float4*)mu)[v - lo], vv = ((float4*)nu)[v - lo];
     float pe[4] = {pv.x, pv.y, pv.z, pv.w}, ge[4] = {gs.x, gs.y, gs.z, gs.w};
@@ -99,7 +119,11 @@ dp_adam_kernel(pdeqx_dp_peers P, int64_t n, float* __restrict__ mu, float* __res
     ((float4*)mu)[v - lo] = make_float4(me[0], me[1], me[2], me[3]);
     ((float4*)nu)[v - lo] = make_float4(ve[0], ve[1], ve[2], ve[3]);
     const float4 pn = make_float4(pe[0], pe[1], pe[2], pe[3]);
-    for (int r = 0; r < P.world; ++r) ((float4*)P.params[r])[v] = pn;
+    if (P.mc_params) {
+      multimem_st((float4*)P.mc_params + v, pn);  // replicated by the switch into every rank's arena (this one included)
+    } else {
+      for (int r = 0; r < P.world; ++r) ((float4*)P.params[r])[v] = pn;
+    }
   }
 }
 
@@ -174,7 +198,8 @@ extern "C" int pdeqx_dp_adam_step(const pdeqx_dp_peers* peers, int64_t n, float*
                     "peer %d: null or unaligned arena pointers", r);
   cudaStream_t s = (cudaStream_t)stream;
   TimedScope timed(PDEQX_K_DP_EXCHANGE, s);
-  timed_bytes(4.0 * (double)n * (2.0 * (peers->world - 1) / peers->world + 4.0 / peers->world));  // NVLink in + out, local p / mu / nu
+  // bytes over this GPU's links (in + out) + the local p / mu / nu traffic of the shard
+  timed_bytes(4.0 * (double)n * ((peers->mc_grads ? 2.0 : 2.0 * (peers->world - 1)) / peers->world + 4.0 / peers->world));
   dp_tick_kernel<<<1, 1, 0, s>>>(state, b1, b2);
   PDEQX_LAUNCHED();
   const int64_t per = pdeqx_dp_shard_floats(n, peers->world) / 4;

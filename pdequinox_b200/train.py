@@ -10,6 +10,8 @@ and the 1/world_size scaling is fused into the Adam kernel.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -39,8 +41,9 @@ class ParameterArena:
     and gives every parameter a gradient view in a second flat buffer. `exportable`: hold both arenas in allocations that
     CUDA IPC can export to the other ranks of the node (the peer-memory exchange of `PeerExchange`)."""
 
-    def __init__(self, model, exportable=False):
+    def __init__(self, model, exportable=False, group=None):
         self.model = model
+        self.symmetric = None  # (params handle, grads handle) of torch symmetric memory
         self.entries = []  # (path, owner, field, offset, numel, shape)
         off = 0
         for path, owner, field in model.named_leaves():
@@ -50,7 +53,14 @@ class ParameterArena:
         self.size = off
         dev = default_device()
         self.buffers = None
-        if exportable:
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st in the exchange kernel) needs torch's symmetric memory for the
+        # mapping; opt-in (PDEQX_DP_MULTICAST=1): measured SLOWER than plain peer loads / stores at 2 ranks (222 vs 145 us per
+        # exchange), where the switch has nothing to reduce
+        sym = _symmetric_arenas(off, group) if (exportable and os.environ.get("PDEQX_DP_MULTICAST", "0") == "1") else None
+        if sym is not None:
+            self.params, self.grads = sym[0], sym[1]
+            self.symmetric = tuple(sym[2])
+        elif exportable:
             self.buffers = (_DeviceBuffer(off), _DeviceBuffer(off))
             self.params, self.grads = self.buffers[0].tensor, self.buffers[1].tensor
         else:
@@ -90,11 +100,40 @@ def allreduce_gradients_(grads, loss, world, group=None):
     return grads, loss
 
 
+def _symmetric_arenas(n_floats, group):
+    """(params, grads, handles) as torch symmetric-memory tensors (peer-mapped AND, on an NVSwitch fabric, multicast-mapped
+    on every rank), or None -- on EVERY rank -- if this torch build / fabric cannot provide them on some rank. Plumbing only:
+    the kernels just get pointers."""
+    dist = torch.distributed
+    group = group if group is not None else dist.group.WORLD
+    dev = default_device()
+    tensors, why = None, ""
+    try:
+        import torch.distributed._symmetric_memory as symm
+        tensors = [symm.empty(int(n_floats), dtype=torch.float32, device=dev) for _ in range(2)]
+        for t in tensors:
+            t.zero_()
+    except Exception as exc:  # noqa: BLE001 - any failure means "not available": the IPC path needs nothing of this
+        why = f"{type(exc).__name__}: {exc}"
+    flag = torch.tensor([1 if tensors is not None else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # the rendezvous below is collective: all ranks or none
+    if not bool(flag.item()):
+        if why:
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({why}); the peer exchange uses CUDA IPC without multicast")
+        return None
+    handles = [symm.rendezvous(t, group) for t in tensors]
+    return tensors[0], tensors[1], handles
+
+
 class PeerExchange:
-    """This rank's view of every rank's parameter arena, gradient arena and signal pad through CUDA IPC: what
-    pdeqx_dp_adam_step (reduce-scatter + Adam on the rank's shard + all-gather, one kernel over NVLink peer memory) needs.
-    The 64-byte IPC handles travel through torch.distributed (plumbing). `ok` is False -- on EVERY rank -- if any rank could
-    not map a peer's memory (ranks on different nodes, no peer access); the caller then keeps the NCCL all-reduce."""
+    """This rank's view of every rank's parameter arena, gradient arena and signal pad: what pdeqx_dp_adam_step
+    (reduce-scatter + Adam on the rank's shard + all-gather, one kernel over NVLink peer memory) needs. The arenas are
+    either torch symmetric-memory tensors (`ParameterArena(exportable="symmetric")`: peer pointers and, on NVSwitch, the
+    multicast addresses that let the switch do the reduction and the broadcast) or pdeqx_dp_alloc buffers exchanged as CUDA
+    IPC handles through torch.distributed. The signal pads always travel as IPC handles. `ok` is False -- on EVERY rank --
+    if any rank could not map a peer's memory (ranks on different nodes, no peer access); the caller then keeps the NCCL
+    all-reduce."""
 
     def __init__(self, arena, group=None):
         import ctypes as C
@@ -104,19 +143,23 @@ class PeerExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.pad = _DeviceBuffer(L.pdeqx_dp_pad_bytes() // 4)
         self.imported = []
-        mine = (socket.gethostname(), arena.buffers[0].handle(), arena.buffers[1].handle(), self.pad.handle())
+        symmetric = arena.symmetric is not None
+        mine = (socket.gethostname(), None if symmetric else arena.buffers[0].handle(),
+                None if symmetric else arena.buffers[1].handle(), self.pad.handle())
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self.peers = _lib.DpPeers()
         self.peers.world, self.peers.rank = self.world, self.rank
         ok = self.world <= _lib.MAX_RANKS and all(e[0] == mine[0] for e in everyone)
+        self.multicast = False
         if ok:
             for r, (_, hp, hg, hs) in enumerate(everyone):
+                handles = (hs,) if symmetric else (hp, hg, hs)
                 if r == self.rank:
-                    ptrs = (arena.buffers[0].ptr.value, arena.buffers[1].ptr.value, self.pad.ptr.value)
+                    ptrs = [self.pad.ptr.value] if symmetric else [arena.buffers[0].ptr.value, arena.buffers[1].ptr.value, self.pad.ptr.value]
                 else:
                     ptrs = []
-                    for h in (hp, hg, hs):
+                    for h in handles:
                         out = C.c_void_p()
                         if ok and L.pdeqx_dp_import((C.c_char * 64).from_buffer_copy(h), C.byref(out)) == 0:
                             self.imported.append(out)
@@ -124,10 +167,22 @@ class PeerExchange:
                         else:
                             ok = False
                             ptrs.append(None)
-                self.peers.params[r], self.peers.grads[r], self.peers.pads[r] = ptrs
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=default_device())
+                if symmetric:
+                    hp_, hg_ = arena.symmetric
+                    self.peers.params[r], self.peers.grads[r], self.peers.pads[r] = hp_.buffer_ptrs[r], hg_.buffer_ptrs[r], ptrs[0]
+                else:
+                    self.peers.params[r], self.peers.grads[r], self.peers.pads[r] = ptrs
+            if symmetric:
+                hp_, hg_ = arena.symmetric
+                if hp_.multicast_ptr and hg_.multicast_ptr:
+                    self.peers.mc_params, self.peers.mc_grads = hp_.multicast_ptr, hg_.multicast_ptr
+                    self.multicast = True
+        flag = torch.tensor([1 if ok else 0, 1 if self.multicast else 0], dtype=torch.int32, device=default_device())
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        self.ok = bool(flag.item())
+        self.ok = bool(flag[0].item())
+        if self.multicast and not bool(flag[1].item()):  # all ranks or none
+            self.peers.mc_params = self.peers.mc_grads = None
+            self.multicast = False
         self.shard_floats = int(L.pdeqx_dp_shard_floats(arena.size, self.world))
 
     def check(self):
@@ -157,7 +212,7 @@ class TrainStep:
                      and torch.distributed.get_backend(process_group) == "nccl")
         if exchange == "peer" and not want_peer:
             raise _lib.PdeqxError("exchange='peer' needs an initialised NCCL process group with more than one rank")
-        self.arena = ParameterArena(model, exportable=want_peer)
+        self.arena = ParameterArena(model, exportable=want_peer, group=process_group)
         self.peer = None
         if want_peer:
             self.peer = PeerExchange(self.arena, process_group)
