@@ -124,6 +124,31 @@ __device__ __forceinline__ void gelu_both_f(float x, float& y, float& dy) {
   dy = fmaf(hx * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }
 
+// gelu / gelu' of two values at once on packed fp32 (same formulas, same per-lane rounding as gelu_f / gelu_grad_f<true>)
+__device__ __forceinline__ f32x2 gelu2(f32x2 x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const f32x2 x2 = mul2(x, x);
+  const f32x2 u = mul2(x, fma2(x2, pk2(k01, k01), pk2(k0, k0)));
+  float u0, u1;
+  upk2(u, u0, u1);
+  const f32x2 t = pk2(tanh_fast(u0), tanh_fast(u1));
+  const f32x2 hx = mul2(x, pk2(0.5f, 0.5f));
+  return fma2(hx, t, hx);
+}
+__device__ __forceinline__ f32x2 gelu_grad2(f32x2 x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const f32x2 x2 = mul2(x, x);
+  const f32x2 u = mul2(x, fma2(x2, pk2(k01, k01), pk2(k0, k0)));
+  float u0, u1;
+  upk2(u, u0, u1);
+  const f32x2 t = pk2(tanh_fast(u0), tanh_fast(u1));
+  const f32x2 du = fma2(x2, pk2(3.0f * k01, 3.0f * k01), pk2(k0, k0));
+  const f32x2 hx = mul2(x, pk2(0.5f, 0.5f));
+  const f32x2 omt2 = fma2(mul2(t, t), pk2(-1.0f, -1.0f), pk2(1.0f, 1.0f));  // 1 - t^2
+  const f32x2 half = pk2(0.5f, 0.5f);
+  return fma2(mul2(hx, du), omt2, fma2(half, t, half));  // 0.5 (1 + t) + 0.5 x (1 - t^2) du
+}
+
 // ==========================================================================================
 // slab kernel
 // ==========================================================================================
@@ -455,6 +480,30 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         } else if (MODE == 2 || MODE == 5) {
 #pragma unroll
           for (int j = 0; j < NC; ++j) g[j] = auxw_c[j] * sv;
+        }
+        if (ACT == PDEQX_ACT_GELU_TANH && (MODE == 0 || MODE == 4 || MODE == 1 || MODE == 2)) {
+          // packed path: two channels per instruction (bias add, rank-one bypass, gelu / gelu')
+          const f32x2 su2 = pk2(su, su);
+#pragma unroll
+          for (int j = 0; j < NC; j += 2) {
+            f32x2 val = add2(pk2(v[j], v[j + 1]), pk2(bias_c[j], bias_c[j + 1]));
+            if (BYP1) val = fma2(pk2(bypa_c[j], bypa_c[j + 1]), su2, val);
+            float r0, r1;
+            if (MODE == 0 || MODE == 4) {
+              upk2(gelu2(val), r0, r1);
+              if (MODE == 4) {
+                pacc = fmaf(auxw_c[j], r0, pacc);
+                pacc = fmaf(auxw_c[j + 1], r1, pacc);
+                continue;
+              }
+            } else {
+              upk2(mul2(pk2(g[j], g[j + 1]), gelu_grad2(val)), r0, r1);
+            }
+            if (kRoundOut) { r0 = round_tf32(r0); r1 = round_tf32(r1); }
+            st_shared_f32(row0 + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r0);
+            st_shared_f32(row0 + (uint32_t)(j + 1) * 128 + (lane_b ^ ((uint32_t)((j + 1) & 7) << 4)), r1);
+          }
+          return;
         }
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
@@ -812,15 +861,26 @@ chain_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
           ld_shared_const_v4(bias_sa + cidx + j * 4, bias_c + j);
           if (BYP1) ld_shared_const_v4(bypa_sa + cidx + j * 4, bypa_c + j);
         }
+        if (ACT == PDEQX_ACT_GELU_TANH) {  // packed fp32: two channels per instruction
+          const f32x2 su2 = pk2(su, su);
 #pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          float pre = v2[j] + bias_c[j];
-          if (BYP1) pre = fmaf(bypa_c[j], su, pre);
-          float r;
-          if (ACT == PDEQX_ACT_GELU_TANH) r = v1[j] * gelu_grad_f<true>(pre);
-          else r = pre > 0.f ? v1[j] : 0.f;
-          r = round_tf32(r);  // read next as a tcgen05 operand (weight gradient, data gradient): round, do not let it truncate
-          st_shared_f32(col + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
+          for (int j = 0; j < NC; j += 2) {
+            f32x2 pre = add2(pk2(v2[j], v2[j + 1]), pk2(bias_c[j], bias_c[j + 1]));
+            if (BYP1) pre = fma2(pk2(bypa_c[j], bypa_c[j + 1]), su2, pre);
+            float r0, r1;
+            upk2(mul2(pk2(v1[j], v1[j + 1]), gelu_grad2(pre)), r0, r1);
+            // read next as a tcgen05 operand (weight gradient, data gradient): round, do not let it truncate
+            st_shared_f32(col + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), round_tf32(r0));
+            st_shared_f32(col + (uint32_t)(j + 1) * 128 + (lane_b ^ ((uint32_t)((j + 1) & 7) << 4)), round_tf32(r1));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            float pre = v2[j] + bias_c[j];
+            if (BYP1) pre = fmaf(bypa_c[j], su, pre);
+            const float r = round_tf32(pre > 0.f ? v1[j] : 0.f);
+            st_shared_f32(col + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r);
+          }
         }
       };
       if (ncol == 16) chunk(std::integral_constant<int, 16>{});
