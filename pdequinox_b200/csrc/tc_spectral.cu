@@ -1047,6 +1047,8 @@ struct WgradParams {
   // fused first stage of the adjoint-of-inverse DFT of g (optional): x1[(b * c_out + o) * lead + l][0:32] = sum_w g[b,o,l,w] T[w,:]
   float* x1;
   int round_x1;  // x1 feeds a tcgen05 c2c stage (D >= 2): round to tf32 here
+  int m64;       // c_out <= 64: M = 64 MMAs (A = the g rows only: half the A operand bytes; accumulator row r sits in TMEM lane
+                 // 32 * (r / 16) + r % 16, i.e. 16 rows per lane quarter)
 };
 
 constexpr int kWgGroup = 4;  // image rows whose first-DFT-stage results share one accumulator tile (one drain per group)
@@ -1081,13 +1083,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], p.x1 != nullptr ? 2 : 1);  // fused: two issuing warps read every stage
     }
     mbar_init(done, 1);
     mbar_init(tabfull, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&x1full[i], 1);
-      mbar_init(&x1empty[i], 2);
+      mbar_init(&x1empty[i], p.m64 ? 4 : 2);
     }
     fence_barrier_init();
   }
@@ -1134,28 +1136,24 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(128, N, false, false);
-      const uint32_t idesc2 = idesc_tf32(128, 32, false, false);
+      const uint32_t idesc = idesc_tf32(p.m64 ? 64 : 128, N, false, false);
+      const uint32_t idesc2 = idesc_tf32(p.m64 ? 64 : 128, 32, false, false);
       // The issuing thread is the critical resource of this kernel (8 MMAs per 16 KB stage): descriptors are built once,
       // per MMA only the 14-bit start-address field moves (>> 4 units: +2 per 32-byte K step)
       const uint64_t d0 = smem_desc_sw128(smem_u32(stage0), 0, 1024);
       const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
       const uint32_t stage16 = stage_bytes >> 4, g16 = g_bytes >> 4;
       const uint32_t tab_lo0 = (uint32_t)smem_desc_sw128(smem_u32(smem), 0, 1024);
-      if (fused) mbar_wait(tabfull, 0);
-      int s = 0, it = 0;
+      (void)idesc2;
+      (void)tab_lo0;
+      // weight-gradient MMAs only: the first-DFT-stage MMAs of the same stages are issued by warp 3 (the single issuing
+      // thread was the critical resource: 8 MMAs + barrier polling per 16 KB stage)
+      int s = 0;
       uint32_t ph = 0;
       uint32_t acc = 0;
-      for (int64_t gi = first; gi < groups; gi += stride, ++it) {
-        const int a2 = it & 1;
-        if (fused) {
-          mbar_wait(&x1empty[a2], (((uint32_t)it >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
+      for (int64_t gi = first; gi < groups; gi += stride) {
        for (int rr = 0; rr < kWgGroup; ++rr) {
         if (gi * kWgGroup + rr >= p.rows) break;
-        // the rows of a group land in consecutive 32-column slices of one accumulator tile: ONE drain per group
-        const uint32_t d2 = tmem_base + 128u + (uint32_t)(a2 * kWgGroup * 32 + rr * 32);
         for (int c = 0; c < p.chunks_per_row; ++c) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -1166,26 +1164,54 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
             mma_tf32_lohi(tmem_base, a_lo + k * 2, hi, b_lo + k * 2, hi, idesc, acc);
             acc = 1;
           }
-          if (fused) {
-            // same A rows (g rows 0..c_out-1 are the ones kept), B = table chunk [32 k x 32 w] of this pixel chunk
-            const uint32_t t_lo = tab_lo0 + (uint32_t)c * (4096 >> 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_tf32_lohi(d2, a_lo + k * 2, hi, t_lo + k * 2, hi, idesc2, (c | k) ? 1u : 0u);
-          }
           mma_commit(&empty[s]);
           if (++s == S) { s = 0; ph ^= 1; }
         }
        }
-        if (fused) mma_commit(&x1full[a2]);
       }
       mma_commit(done);
     }
+  } else if (warp == 3) {
+    // second MMA issuer (fused only): X1[(b, o, l), 0:32] += g rows . table chunk, per image row its own accumulator slice
+    if (lane == 0 && fused) {
+      const uint32_t idesc2 = idesc_tf32(p.m64 ? 64 : 128, 32, false, false);
+      const uint64_t d0 = smem_desc_sw128(smem_u32(stage0), 0, 1024);
+      const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+      const uint32_t stage16 = stage_bytes >> 4;
+      const uint32_t tab_lo0 = (uint32_t)smem_desc_sw128(smem_u32(smem), 0, 1024);
+      mbar_wait(tabfull, 0);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int64_t gi = first; gi < groups; gi += stride, ++it) {
+        const int a2 = it & 1;
+        mbar_wait(&x1empty[a2], (((uint32_t)it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int rr = 0; rr < kWgGroup; ++rr) {
+          if (gi * kWgGroup + rr >= p.rows) break;
+          // the rows of a group land in consecutive 32-column slices of one accumulator tile: ONE drain per group
+          const uint32_t d2 = tmem_base + 128u + (uint32_t)(a2 * kWgGroup * 32 + rr * 32);
+          for (int c = 0; c < p.chunks_per_row; ++c) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_lo = lo0 + (uint32_t)s * stage16;
+            // same A rows (g rows 0..c_out-1 are the ones kept), B = table chunk [32 k x 32 w] of this pixel chunk
+            const uint32_t t_lo = tab_lo0 + (uint32_t)c * (4096 >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_tf32_lohi(d2, a_lo + k * 2, hi, t_lo + k * 2, hi, idesc2, (c | k) ? 1u : 0u);
+            mma_commit(&empty[s]);
+            if (++s == S) { s = 0; ph ^= 1; }
+          }
+        }
+        mma_commit(&x1full[a2]);
+      }
+    }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    if (fused && q < 2) {
-      // drain the r2c accumulator of every row: TMEM lane = A row = output channel o (q < 2: rows 0..63 hold g)
+    if (fused && (q < 2 || p.m64)) {
+      // drain the r2c accumulator of every row: TMEM lane = A row = output channel o (M = 128: lanes 0..63 hold the g rows;
+      // M = 64: 16 rows in the first 16 lanes of every lane quarter)
       int it = 0;
-      const int o = q * 32 + lane;
+      const int o = p.m64 ? (lane < 16 ? q * 16 + lane : 1 << 20) : q * 32 + lane;
       for (int64_t gi = first; gi < groups; gi += stride, ++it) {
         const int a2 = it & 1;
         mbar_wait(&x1full[a2], ((uint32_t)it >> 1) & 1);
@@ -1220,7 +1246,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
     if (first < groups) {
       mbar_wait(done, 0);
       tc_fence_after();
-      const int o = q * 32 + lane;
+      const int o = p.m64 ? (lane < 16 ? q * 16 + lane : 1 << 20) : q * 32 + lane;
       const bool vec_ok = (p.c_in & 3) == 0 && ((uintptr_t)p.gw & 15) == 0;
       for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
@@ -1731,6 +1757,8 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   wp.gb = gb;
   wp.x1 = x1_out;
   wp.round_x1 = d.ndim >= 2 ? 1 : 0;
+  static const bool m64_on = [] { const char* e = getenv("PDEQX_WG_M64"); return !(e && e[0] == '0'); }();  // (0: M = 128, A = [g ; x])
+  wp.m64 = (m64_on && d.c_out <= 64) ? 1 : 0;
   const uint32_t tab_bytes = x1_out ? (uint32_t)wp.chunks_per_row * 4096 : 0;
   const uint32_t stage_bytes = (uint32_t)(d.c_out + d.c_in) * 128 + 2048;
   int stages = (int)((227 * 1024 - 16384 - 2048 - (int)tab_bytes) / (int)stage_bytes);
