@@ -798,15 +798,15 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&rawfull[i], 1);
-      mbar_init(&rawempty[i], 1);
+      mbar_init(&rawempty[i], 2);  // both MMA issuers
       mbar_init(&shfull[i], kWgsShifters);
       mbar_init(&shempty[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&xfull[i], 1);
-      mbar_init(&xempty[i], 1);
+      mbar_init(&xempty[i], 2);  // both MMA issuers read every x row
     }
-    mbar_init(done, 1);
+    mbar_init(done, 2);
     *inited_s = 0;
     fence_barrier_init();
   }
@@ -863,11 +863,14 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers (whole warp convergent, one elected lane issues) =====================
     // Per k-step and A group: one MMA of N = 2C over the two row taps whose ring slots are neighbours + one of N = C for the
-    // third -- 4 MMAs instead of 6, 28 KB of operands instead of 36 KB (the time of these MMAs is their operand fetch).
-    // Accumulator columns are [group][row tap][C], so either pairing -- taps (0,1) or (1,2) -- lands on consistent columns.
+    // third -- 4 MMAs instead of 6. Accumulator columns are [group][row tap][C], so either pairing -- taps (0,1) or (1,2) --
+    // lands on consistent columns. The two A groups are issued by TWO warps (warp 1: the shifted copies, warp 2 -- free after
+    // the TMEM allocation -- the centre tap straight from the raw row): with one issuing thread the kernel was bound by that
+    // thread's instruction stream (16 MMAs + barrier polling per 32-column chunk), not by the tensor pipe or HBM.
+    const int grp = warp - 1;
     const uint32_t idesc1 = idesc_tf32(128, C, false, false), idesc2 = idesc_tf32(128, 2 * C, false, false);
     const uint64_t adesc0 = smem_desc_sw128(smem_u32(smem + L.sh_off), 0, 1024);
     const uint64_t rdesc0 = smem_desc_sw128(smem_u32(smem + L.raw_off), 0, 1024);
@@ -890,8 +893,10 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
             pf ^= 1u << s;
           }
         }
-        mbar_wait(&rawfull[rb], (rpf >> rb) & 1u);
-        rpf ^= 1u << rb;
+        if (grp == 1) {  // the centre tap reads the raw row itself
+          mbar_wait(&rawfull[rb], (rpf >> rb) & 1u);
+          rpf ^= 1u << rb;
+        }
         // taps t = 0, 1, 2 sit in slots s0, s0 + 1, s0 + 2 (mod 4): the pair that does not wrap around the ring is merged
         const int s0 = j & (kWgRing - 1);
         const int pair_t = s0 == kWgRing - 1 ? 1 : 0;      // first tap of the merged pair
@@ -899,27 +904,28 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
         const int pair_s = (j + pair_t) & (kWgRing - 1), single_s = (j + single_t) & (kWgRing - 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          mbar_wait(&shfull[st], (spf >> st) & 1u);
-          spf ^= 1u << st;
+          if (grp == 0) {  // the shifted copies of this chunk are in the operand stage
+            mbar_wait(&shfull[st], (spf >> st) & 1u);
+            spf ^= 1u << st;
+          }
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a1 = a_lo0 + (uint32_t)st * 2 * box16;        // [shift tw=0 ; shift tw=2]
-            const uint32_t a2 = r_lo0 + (uint32_t)(rb * 4 + c) * box16;  // [centre ; don't-care]
+            // group 0: A = [shift tw=0 ; shift tw=2] (operand stage); group 1: A = [centre ; don't-care] (raw row)
+            const uint32_t a_lo = grp == 0 ? a_lo0 + (uint32_t)st * 2 * box16 : r_lo0 + (uint32_t)(rb * 4 + c) * box16;
             const uint32_t bp = b_lo0 + (uint32_t)c * slot16 + (uint32_t)pair_s * box16;
             const uint32_t bs = b_lo0 + (uint32_t)c * slot16 + (uint32_t)single_s * box16;
-            const uint32_t dp1 = tmem_base + (uint32_t)(pair_t * C), dp2 = tmem_base + (uint32_t)((3 + pair_t) * C);
-            const uint32_t ds1 = tmem_base + (uint32_t)(single_t * C), ds2 = tmem_base + (uint32_t)((3 + single_t) * C);
+            const uint32_t dp = tmem_base + (uint32_t)((3 * grp + pair_t) * C), ds = tmem_base + (uint32_t)((3 * grp + single_t) * C);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t acc = (c | k) ? 1u : started;
-              mma_tf32_lohi(dp1, a1 + k * 2, a_hi, bp + k * 2, b_hi, idesc2, acc);
-              mma_tf32_lohi(dp2, a2 + k * 2, a_hi, bp + k * 2, b_hi, idesc2, acc);
-              mma_tf32_lohi(ds1, a1 + k * 2, a_hi, bs + k * 2, b_hi, idesc1, acc);
-              mma_tf32_lohi(ds2, a2 + k * 2, a_hi, bs + k * 2, b_hi, idesc1, acc);
+              mma_tf32_lohi(dp, a_lo + k * 2, a_hi, bp + k * 2, b_hi, idesc2, acc);
+              mma_tf32_lohi(ds, a_lo + k * 2, a_hi, bs + k * 2, b_hi, idesc1, acc);
             }
-            mma_commit(&shempty[st]);
+            if (grp == 0) mma_commit(&shempty[st]);
             if (c == 3) {
-              mma_commit(&rawempty[rb]);  // (the shifters are done with a raw row before its last chunk can be consumed)
+              // raw row: group 1 has read it; group 0's commit stands for the shifters (they are done with a raw row before
+              // its last chunk can be consumed) -- two arrivals free the buffer
+              mma_commit(&rawempty[rb]);
 #pragma unroll
               for (int t = 0; t < 3; ++t)
                 if (t == 0 || last) mma_commit(&xempty[(j + t) & (kWgRing - 1)]);
@@ -933,7 +939,7 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
       }
     }
     if (elect_one()) {
-      *inited_s = started ? 7u : 0u;
+      if (grp == 0) *inited_s = started ? 7u : 0u;
       mma_commit(done);
     }
     __syncwarp();
