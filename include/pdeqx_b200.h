@@ -338,9 +338,11 @@ size_t pdeqx_groupnorm_workspace_bytes(int32_t batch, int32_t channels);
 int pdeqx_groupnorm_fwd(int32_t batch, int32_t channels, int32_t groups, int64_t n, const float* x,
                         const float* weight, const float* bias, float eps, float* y, float* stats,
                         void* workspace, void* stream);
-/* gx, gweight[C], gbias[C] (overwritten; the last two may be NULL); scratch: 2*B*C floats */
+/* gx, gweight[C], gbias[C] (overwritten; the last two may be NULL); scratch: 2*B*C floats. relu_mask [B,C,n] may be NULL:
+ * gx is zeroed where relu_mask <= 0 -- the relu' of the layer whose OUTPUT this norm read (norm -> conv -> act chains,
+ * pdequinox/blocks/_dilated_res_block.py:141-151), applied here instead of in an elementwise pass of its own. */
 int pdeqx_groupnorm_bwd(int32_t batch, int32_t channels, int32_t groups, int64_t n, const float* x,
-                        const float* weight, const float* stats, const float* gy, float* gx,
+                        const float* weight, const float* stats, const float* gy, const float* relu_mask, float* gx,
                         float* gweight, float* gbias, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------- *

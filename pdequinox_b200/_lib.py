@@ -100,7 +100,7 @@ PROTOTYPES = {
     "pdeqx_split_channels": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P]),
     "pdeqx_groupnorm_workspace_bytes": (C.c_size_t, [_I32, _I32]),
     "pdeqx_groupnorm_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _F, _P, _P, _P, _P]),
-    "pdeqx_groupnorm_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pdeqx_groupnorm_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pdeqx_activation_fwd": (C.c_int, [_I64, _P, _I32, _P, _P]),
     "pdeqx_add": (C.c_int, [_I64, _P, _P, _P, _P]),
     "pdeqx_activation_bwd": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),

@@ -75,19 +75,27 @@ class DilatedResBlock(Block):
         saved = tape.pop()
         identity_skip = isinstance(self.bypass_conv, Identity)
         g = gy
+        premasked = False  # True: `g` already carries relu' of layer j's output (applied by the GroupNorm reverse pass behind it)
         for j in reversed(range(len(self.conv_layers))):
             hn, out, pre = saved[j]
             conv, norm = self.conv_layers[j], self.norm_layers[j]
-            ga = nn.activation_bwd(pre if pre is not None else out, g, act, tape, conv, "ga")
+            ga = g if premasked else nn.activation_bwd(pre if pre is not None else out, g, act, tape, conv, "ga")
+            premasked = False
             first = j == 0
             no_norm = isinstance(norm, Identity)
             # a GroupNorm in front of the conv has parameters of its own: their gradients need the conv's input gradient
             # even when the caller does not want the block's (and the norm's tape record must be popped either way)
             want = need_gx or not first or not no_norm
             add = gy if (first and identity_skip and no_norm) else None
-            g = conv.apply_bwd(hn, ga, tape, want, tag="gx", add=add)
+            # without a norm in between, the conv's input IS the relu output of layer j-1: its relu' rides on this data gradient
+            cmask = saved[j - 1][1] if (no_norm and j > 0 and act == _lib.ACT_RELU and saved[j - 1][2] is None) else None
+            g = conv.apply_bwd(hn, ga, tape, want, tag="gx", add=add, relu_mask=cmask)
+            premasked = cmask is not None
             if want and not no_norm:
-                g = norm._bwd(g, tape)
+                # the norm's input is the relu output of layer j-1: that layer's relu' rides on this norm's reverse pass
+                mask = saved[j - 1][1] if (j > 0 and act == _lib.ACT_RELU and saved[j - 1][2] is None) else None
+                g = norm._bwd(g, tape, relu_mask=mask)
+                premasked = mask is not None
                 if first and identity_skip:
                     g = nn.add(g, gy, tape, self, "gx")
         if not identity_skip:

@@ -126,8 +126,8 @@ gn_bwd_channel_kernel(const float* __restrict__ x, const float* __restrict__ gy,
 // gx = rstd * (w gy - s1 - xhat s2), s1 = mean_group(w gy), s2 = mean_group(w gy xhat). grid (B*C, chunks)
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ stats,
-                    const float* __restrict__ w, const float* __restrict__ scratch, float* __restrict__ gx, int C,
-                    int cpg, int G, int64_t n) {
+                    const float* __restrict__ w, const float* __restrict__ scratch, const float* __restrict__ mask,
+                    float* __restrict__ gx, int C, int cpg, int G, int64_t n) {
   const int bc = blockIdx.x, b = bc / C, c = bc % C, g = c / cpg;
   const float mean = stats[2 * (b * G + g)], rstd = stats[2 * (b * G + g) + 1];
   // group sums of the per-channel partials: the block's threads split the group's channels (a serial loop per thread over
@@ -163,9 +163,12 @@ gn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ gy, c
   const float* xc = x + (int64_t)bc * n;
   const float* gc = gy + (int64_t)bc * n;
   float* oc = gx + (int64_t)bc * n;
+  const float* mc = mask ? mask + (int64_t)bc * n : nullptr;
   for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
     float xh = (__ldg(xc + i) - mean) * rstd;
-    oc[i] = rstd * (wv * __ldg(gc + i) - s1 - xh * s2);
+    float v = rstd * (wv * __ldg(gc + i) - s1 - xh * s2);
+    if (mc && __ldg(mc + i) <= 0.f) v = 0.f;  // relu' of the layer that produced x (its output IS x when mask == x)
+    oc[i] = v;
   }
 }
 
@@ -219,8 +222,8 @@ extern "C" int pdeqx_groupnorm_fwd(int32_t batch, int32_t channels, int32_t grou
 }
 
 extern "C" int pdeqx_groupnorm_bwd(int32_t batch, int32_t channels, int32_t groups, int64_t n, const float* x,
-                                   const float* weight, const float* stats, const float* gy, float* gx, float* gweight,
-                                   float* gbias, float* scratch, void* stream) {
+                                   const float* weight, const float* stats, const float* gy, const float* relu_mask,
+                                   float* gx, float* gweight, float* gbias, float* scratch, void* stream) {
   PDEQX_CHECK_ARG(x && stats && gy && gx && scratch, "null argument");
   PDEQX_CHECK_ARG(batch >= 0 && channels >= 1 && groups >= 1 && n >= 1 && channels % groups == 0, "bad sizes");
   if (batch == 0) return PDEQX_OK;
@@ -228,7 +231,7 @@ extern "C" int pdeqx_groupnorm_bwd(int32_t batch, int32_t channels, int32_t grou
   const int BC = batch * channels, cpg = channels / groups;
   gn_bwd_channel_kernel<<<BC, 256, 0, s>>>(x, gy, stats, scratch, channels, cpg, groups, n);
   PDEQX_LAUNCHED();
-  gn_bwd_apply_kernel<<<dim3(BC, chunks_for(n, BC)), 256, 0, s>>>(x, gy, stats, weight, scratch, gx, channels, cpg, groups, n);
+  gn_bwd_apply_kernel<<<dim3(BC, chunks_for(n, BC)), 256, 0, s>>>(x, gy, stats, weight, scratch, relu_mask, gx, channels, cpg, groups, n);
   PDEQX_LAUNCHED();
   if (gweight || gbias) {
     gn_bwd_param_kernel<<<(int)ceil_div(channels, 128), 128, 0, s>>>(scratch, gweight, gbias, batch, channels);

@@ -453,7 +453,7 @@ extern "C" XLA_FFI_Error* pdeqx_ffi_groupnorm_bwd(XLA_FFI_CallFrame* call_frame)
     return fr.fail(XLA_FFI_Error_Code_RESOURCE_EXHAUSTED, "%s: scratch result must hold 2 * B * C floats", "pdeqx_groupnorm_bwd");
   if (!execute) return nullptr;
   return fr.status(pdeqx_groupnorm_bwd((int32_t)x->dims[0], (int32_t)x->dims[1], (int32_t)groups, pixels(x), fr.in(0), fr.opt(1), fr.in(2),
-                                       fr.in(3), fr.out(0), fr.opt_out(1), fr.opt_out(2), fr.out(3), stream),
+                                       fr.in(3), nullptr, fr.out(0), fr.opt_out(1), fr.opt_out(2), fr.out(3), stream),
                    "pdeqx_groupnorm_bwd");
 }
 

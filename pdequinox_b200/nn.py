@@ -108,7 +108,8 @@ class GroupNorm(Module):
             tape.push((x, stats))
         return y
 
-    def _bwd(self, gy, tape, need_gx=True):
+    def _bwd(self, gy, tape, need_gx=True, relu_mask=None):
+        """relu_mask: the input gradient is zeroed where it is <= 0 (relu' of the layer whose output this norm read)."""
         x, stats = tape.pop()
         B, Cc = x.shape[:2]
         n = x[0, 0].numel()
@@ -117,6 +118,6 @@ class GroupNorm(Module):
         gw = self.grad("weight") if self.weight is not None else None
         gb = self.grad("bias") if self.bias is not None else None
         _lib.check(_lib.lib().pdeqx_groupnorm_bwd(B, Cc, self.groups, n, _lib.ptr(x), _lib.ptr(self.weight),
-                                                  _lib.ptr(stats), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(gw),
+                                                  _lib.ptr(stats), _lib.ptr(gy), _lib.ptr(relu_mask), _lib.ptr(gx), _lib.ptr(gw),
                                                   _lib.ptr(gb), _lib.ptr(scratch), _lib.stream()))
         return gx
