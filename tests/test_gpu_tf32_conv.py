@@ -94,3 +94,38 @@ def test_tf32_resnet_train_step(cuda):
     g = {k: host(v) for k, v in step.arena.named_grads().items()}
     for k in g_ref:
         assert rel_l2(g[k], g_ref[k]) <= TOL, k
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+@pytest.mark.parametrize("mode,d,H", [("periodic", 1, 32), ("dirichlet", 2, 24), ("neumann", 1, 32), ("periodic", 3, 37)])
+def test_conv_data_gradient_applies_the_relu_mask(precision, mode, d, H):
+    """pdeqx_conv_bwd_data(relu_mask): (conv^T(gy) + add) * [mask > 0] in ONE pass equals the unmasked data gradient followed by
+    the mask -- on the CTA-pair kernel, the one-CTA kernel (H % d != 0), the two-pass neumann path and the fp32 kernels."""
+    pdeqx.set_precision(precision)
+    rng = np.random.default_rng(31)
+    conv = pdeqx.PhysicsConv(2, 64, 64, 3, dilation=d, key=0, boundary_mode=mode)
+    ParameterArena(conv)
+    x = dev(rng.standard_normal((2, 64, H, 128)))
+    gy = dev(rng.standard_normal((2, 64, H, 128)))
+    add = dev(rng.standard_normal((2, 64, H, 128)))
+    mask = dev(rng.standard_normal((2, 64, H, 128)))
+    plain = host(conv.apply_bwd(x, gy, None, True, add=add))
+    masked = host(conv.apply_bwd(x, gy, None, True, add=add, relu_mask=mask))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(masked, plain * (host(mask) > 0))
+
+
+def test_groupnorm_reverse_pass_applies_the_relu_mask(cuda):
+    from pdequinox_b200 import nn as pnn
+    from pdequinox_b200._module import Tape
+    rng = np.random.default_rng(32)
+    norm = pnn.GroupNorm(groups=2, channels=8)
+    ParameterArena(norm)
+    x = dev(rng.standard_normal((3, 8, 10, 12)))
+    gy = dev(rng.standard_normal((3, 8, 10, 12)))
+    out = {}
+    for masked in (False, True):
+        tape = Tape()
+        norm._fwd(x, tape)
+        out[masked] = host(norm._bwd(gy, tape, relu_mask=x if masked else None)).copy()
+    np.testing.assert_array_equal(out[True], out[False] * (host(x) > 0))
