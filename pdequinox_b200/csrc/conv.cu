@@ -101,6 +101,83 @@ conv_fwd_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict
   }
 }
 
+// Deep-channel / few-points regime (the inner levels of ClassicUNet 1D: 256 channels on 4 points): one thread per output
+// would loop serially over c_in/groups x taps = 768 dependent loads (~50 us per launch on KB-sized tensors). Here ONE WARP
+// owns an output quad and its lanes split the input channels; a shuffle reduction finishes. Everything is cache resident, so
+// the lane-strided x reads do not matter.
+__global__ void __launch_bounds__(256)
+conv_fwd_warp_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     const float* __restrict__ residual, float* __restrict__ y, int act) {
+  const int64_t n_out = g.n_out;
+  const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
+  const int ochunks = (cog + kOPT - 1) / kOPT;
+  const int64_t total = (int64_t)g.batch * g.groups * ochunks * n_out;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < total; idx += warps) {
+    int64_t p = idx % n_out;
+    int64_t r = idx / n_out;
+    const int oc = (int)(r % ochunks);
+    r /= ochunks;
+    const int grp = (int)(r % g.groups);
+    const int b = (int)(r / g.groups);
+    int po[PDEQX_MAX_DIMS];
+    {
+      int64_t pp = p;
+      for (int a = g.ndim - 1; a >= 0; --a) {
+        po[a] = (int)(pp % g.out[a]);
+        pp /= g.out[a];
+      }
+    }
+    const int o0 = grp * cog + oc * kOPT;
+    const int no = min(kOPT, cog - oc * kOPT);
+    float acc[kOPT];
+#pragma unroll
+    for (int j = 0; j < kOPT; ++j) acc[j] = 0.f;
+    const float* xb = x + ((int64_t)b * g.c_in + (int64_t)grp * cig) * g.n_in;
+    for (int t = 0; t < g.taps; ++t) {
+      int tt = t;
+      int64_t src = 0;
+      bool valid = true;
+      for (int a = g.ndim - 1; a >= 0; --a) {
+        int ta = tt % g.kernel[a];
+        tt /= g.kernel[a];
+        int q = po[a] * g.stride[a] + ta * g.dilation[a] - g.pad_lo[a];
+        int m = boundary_map(q, g.spatial[a], g.boundary);
+        valid = valid && (m >= 0);
+        src += (int64_t)m * g.in_stride[a];
+      }
+      if (!valid) continue;
+      for (int i = lane; i < cig; i += 32) {
+        const float xv = __ldg(xb + (int64_t)i * g.n_in + src);
+#pragma unroll
+        for (int j = 0; j < kOPT; ++j)
+          if (j < no) acc[j] = fmaf(__ldg(w + ((int64_t)(o0 + j) * cig + i) * g.taps + t), xv, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kOPT; ++j)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    if (lane < no) {
+      float v = acc[0];
+#pragma unroll
+      for (int j = 1; j < kOPT; ++j)
+        if (lane == j) v = acc[j];
+      const int64_t off = ((int64_t)b * g.c_out + o0 + lane) * n_out + p;
+      v += bias ? __ldg(bias + o0 + lane) : 0.f;
+      if (residual) v += __ldg(residual + off);
+      y[off] = apply_act_rt(v, act);
+    }
+  }
+}
+
+// true when the warp-cooperative kernels pay: enough reduction work per output to fill a warp, tensors small enough to be
+// cache resident (lanes read channel-strided)
+static inline bool conv_small_deep(const ConvGeom& g, int red_channels) {
+  return red_channels >= 32 && g.n_in <= 1024 && g.n_out <= 1024;
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward data: gather over the pre-images of each input position under the boundary map
 // ---------------------------------------------------------------------------------------------
@@ -157,7 +234,8 @@ __device__ __forceinline__ int64_t frame2d_point(const ConvGeom& g, const Frame2
   return (int64_t)(f.band_h + r) * W + wcol;
 }
 
-template <bool MIRROR_ONLY>
+// WARP: one warp per input point, lanes split the output channels (deep-channel / few-points regime, see conv_fwd_warp_kernel)
+template <bool MIRROR_ONLY, bool WARP = false>
 __global__ void __launch_bounds__(256)
 conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __restrict__ w, const float* __restrict__ add,
                      float* __restrict__ gx) {
@@ -167,7 +245,10 @@ conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __re
   if (framed) fr = frame2d(g);
   const int64_t per_plane = framed ? fr.count : g.n_in;
   const int64_t total = (int64_t)g.batch * g.c_in * per_plane;
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = WARP ? (int)(threadIdx.x & 31) : 0, lanes = WARP ? 32 : 1;
+  const int64_t it0 = WARP ? (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t it_step = WARP ? (((int64_t)gridDim.x * blockDim.x) >> 5) : (int64_t)gridDim.x * blockDim.x;
+  for (int64_t it = it0; it < total; it += it_step) {
     int64_t n = it % per_plane;
     int64_t r = it / per_plane;
     if (framed) n = frame2d_point(g, fr, n);
@@ -209,10 +290,15 @@ conv_bwd_data_kernel(ConvGeom g, const float* __restrict__ gy, const float* __re
             }
             if (!valid) continue;
 #pragma unroll 8
-            for (int o = 0; o < cog; ++o)
+            for (int o = lane; o < cog; o += lanes)
               acc = fmaf(__ldg(wg + (int64_t)o * cig * g.taps + t), __ldg(gyb + (int64_t)o * g.n_out + dst), acc);
           }
         }
+    if (WARP) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane != 0) continue;
+    }
     if (MIRROR_ONLY) gx[idx] += acc;
     else gx[idx] = acc + (add ? __ldg(add + idx) : 0.f);
   }
@@ -322,15 +408,18 @@ conv_bwd_filter_kernel(ConvGeom g, const float* __restrict__ x, const float* __r
     }
   }
   float acc = 0.f, bsum = 0.f;
-  const int64_t total_chunks = (int64_t)g.batch * chunks;
-  for (int64_t c = blockIdx.y; c < total_chunks; c += gridDim.y) {
-    const int b = (int)(c / chunks);
-    const int64_t p0 = (c % chunks) * WF_P;
+  // the reduction runs over the flattened (sample, pixel) index in chunks of WF_P: with a handful of points per sample (the
+  // inner UNet levels) a per-sample chunk would be almost all padding
+  const int64_t red = (int64_t)g.batch * g.n_out;
+  (void)chunks;
+  for (int64_t c = blockIdx.y; c * WF_P < red; c += gridDim.y) {
     for (int idx = tid; idx < 16 * WF_P; idx += 256) {
       const int ch = idx / WF_P, pl = idx % WF_P;
-      const int64_t p = p0 + pl;
+      const int64_t rp = c * WF_P + pl;
+      const int b = (int)(rp / g.n_out);
+      const int64_t p = rp % g.n_out;
       float gv = 0.f, xv = 0.f;
-      if (p < g.n_out) {
+      if (rp < red) {
         const int o = ot * 16 + ch, i = it * 16 + ch;
         if (o < cog) gv = __ldg(gy + ((int64_t)b * g.c_out + grp * cog + o) * g.n_out + p);
         if (i < cig) {
@@ -491,7 +580,8 @@ extern "C" int pdeqx_conv_fwd(const pdeqx_conv_desc* d, const float* x, const fl
   const int cog = g.c_out / g.groups;
   const int64_t total = (int64_t)g.batch * g.groups * ceil_div(cog, kOPT) * g.n_out;
   TimedScope timed(PDEQX_K_CONV_FWD, s);
-  conv_fwd_kernel<<<grid_for(total), 256, 0, s>>>(g, x, w, b, residual, y, activation);
+  if (conv_small_deep(g, g.c_in / g.groups)) conv_fwd_warp_kernel<<<grid_for(total * 32), 256, 0, s>>>(g, x, w, b, residual, y, activation);
+  else conv_fwd_kernel<<<grid_for(total), 256, 0, s>>>(g, x, w, b, residual, y, activation);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
@@ -513,7 +603,8 @@ extern "C" int pdeqx_conv_bwd_data(const pdeqx_conv_desc* d, const float* gy, co
     PDEQX_TRY(tc_conv_bwd_data(g, gy, w, add, relu_mask, gx, workspace, workspace_bytes, s));
     masked = g.boundary != PDEQX_PAD_REFLECT;
   } else {
-    conv_bwd_data_kernel<false><<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
+    if (conv_small_deep(g, g.c_out / g.groups)) conv_bwd_data_kernel<false, true><<<grid_for(total * 32), 256, 0, s>>>(g, gy, w, add, gx);
+    else conv_bwd_data_kernel<false><<<grid_for(total), 256, 0, s>>>(g, gy, w, add, gx);
     PDEQX_LAUNCHED();
   }
   if (relu_mask && !masked) return pdeqx_activation_bwd(total, relu_mask, gx, PDEQX_ACT_RELU, gx, stream);
@@ -536,7 +627,8 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;
   PDEQX_CHECK_ARG(gx_blocks < (1ll << 31), "conv_bwd_filter: grid too large");
   int64_t split = ceil_div(148 * 8, gx_blocks);
-  if (split > (int64_t)g.batch * chunks) split = (int64_t)g.batch * chunks;
+  const int64_t red_chunks = ceil_div((int64_t)g.batch * g.n_out, WF_P);  // chunks of the flattened (sample, pixel) reduction
+  if (split > red_chunks) split = red_chunks;
   if (split > 65535) split = 65535;
   if (split < 1) split = 1;
   conv_bwd_filter_kernel<<<dim3((unsigned)gx_blocks, (unsigned)split), 256, 0, s>>>(g, x, gy, gw, gb, o_tiles, i_tiles, chunks);

@@ -53,10 +53,12 @@ class ParameterArena:
         self.size = off
         dev = default_device()
         self.buffers = None
-        # NVSwitch multicast (multimem.ld_reduce / multimem.st in the exchange kernel) needs torch's symmetric memory for the
-        # mapping; opt-in (PDEQX_DP_MULTICAST=1): measured SLOWER than plain peer loads / stores at 2 ranks (222 vs 145 us per
-        # exchange), where the switch has nothing to reduce
-        sym = _symmetric_arenas(off, group) if (exportable and os.environ.get("PDEQX_DP_MULTICAST", "0") == "1") else None
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st in the exchange kernel; torch's symmetric memory provides the
+        # mapping). Measured per exchange: 222 vs 145 us at 2 ranks (nothing for the switch to reduce), 208 vs 196 us at 4,
+        # 203 vs 253 us at 8 -> on from 8 ranks (PDEQX_DP_MULTICAST=0 / 1 forces it off / on)
+        mc = os.environ.get("PDEQX_DP_MULTICAST", "auto")
+        world = torch.distributed.get_world_size(group) if exportable else 1
+        sym = _symmetric_arenas(off, group) if (exportable and (mc == "1" or (mc == "auto" and world >= 8))) else None
         if sym is not None:
             self.params, self.grads = sym[0], sym[1]
             self.symmetric = tuple(sym[2])
