@@ -53,13 +53,19 @@ __device__ __forceinline__ int ct_source(const ConvTGeom& g, int a, int po, int 
 
 constexpr int kCtOPT = 4;
 
+// WARP: one warp per output quad, lanes split the input channels, shuffle reduction (the deep-channel / few-points levels of
+// ClassicUNet 1D: one thread per output would loop serially over c_in x taps dependent loads -- 70 us on KB-sized tensors)
+template <bool WARP>
 __global__ void __launch_bounds__(256)
 convT_fwd_kernel(ConvTGeom g, const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ y) {
   const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
   const int ochunks = (cog + kCtOPT - 1) / kCtOPT;
   const int64_t total = (int64_t)g.batch * g.groups * ochunks * g.n_out;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = WARP ? (int)(threadIdx.x & 31) : 0, lanes = WARP ? 32 : 1;
+  const int64_t idx0 = WARP ? (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx_step = WARP ? (((int64_t)gridDim.x * blockDim.x) >> 5) : (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = idx0; idx < total; idx += idx_step) {
     const int64_t p = idx % g.n_out;
     int64_t r = idx / g.n_out;
     const int oc = (int)(r % ochunks);
@@ -93,12 +99,19 @@ convT_fwd_kernel(ConvTGeom g, const float* __restrict__ x, const float* __restri
       }
       if (!valid) continue;
 #pragma unroll 8
-      for (int i = 0; i < cig; ++i) {  // independent loads in flight: the small-tensor regime is latency bound
+      for (int i = lane; i < cig; i += lanes) {  // independent loads in flight: the small-tensor regime is latency bound
         const float xv = __ldg(xb + (int64_t)i * g.n_in + src);
 #pragma unroll
         for (int j = 0; j < kCtOPT; ++j)
           if (j < no) acc[j] = fmaf(__ldg(w + ((int64_t)(o0 + j) * cig + i) * g.taps + t), xv, acc[j]);
       }
+    }
+    if (WARP) {
+#pragma unroll
+      for (int j = 0; j < kCtOPT; ++j)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+      if (lane != 0) continue;
     }
 #pragma unroll
     for (int j = 0; j < kCtOPT; ++j) {
@@ -198,15 +211,17 @@ convT_bwd_filter_kernel(ConvTGeom g, const float* __restrict__ x, const float* _
     }
   }
   float acc = 0.f, bsum = 0.f;
-  const int64_t total_chunks = (int64_t)g.batch * chunks;
-  for (int64_t c = blockIdx.y; c < total_chunks; c += gridDim.y) {
-    const int b = (int)(c / chunks);
-    const int64_t p0 = (c % chunks) * CT_WF_P;
+  // the reduction runs over the flattened (sample, output point) index (see conv_bwd_filter_kernel)
+  const int64_t red = (int64_t)g.batch * g.n_out;
+  (void)chunks;
+  for (int64_t c = blockIdx.y; c * CT_WF_P < red; c += gridDim.y) {
     for (int idx = tid; idx < 16 * CT_WF_P; idx += 256) {
       const int ch = idx / CT_WF_P, pl = idx % CT_WF_P;
-      const int64_t p = p0 + pl;
+      const int64_t rp = c * CT_WF_P + pl;
+      const int b = (int)(rp / g.n_out);
+      const int64_t p = rp % g.n_out;
       float gv = 0.f, xv = 0.f;
-      if (p < g.n_out) {
+      if (rp < red) {
         const int o = ot * 16 + ch, i = it * 16 + ch;
         if (o < cog) gv = __ldg(gy + ((int64_t)b * g.c_out + grp * cog + o) * g.n_out + p);
         if (i < cig) {
@@ -323,7 +338,10 @@ extern "C" int pdeqx_convT_fwd(const pdeqx_convT_desc* d, const float* x, const 
   if (g.batch == 0) return PDEQX_OK;
   const int cog = g.c_out / g.groups;
   const int64_t total = (int64_t)g.batch * g.groups * ceil_div(cog, kCtOPT) * g.n_out;
-  convT_fwd_kernel<<<ct_grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, x, w, b, y);
+  if (g.c_in / g.groups >= 32 && g.n_in <= 1024 && g.n_out <= 2048)
+    convT_fwd_kernel<true><<<ct_grid_for(total * 32), 256, 0, (cudaStream_t)stream>>>(g, x, w, b, y);
+  else
+    convT_fwd_kernel<false><<<ct_grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, x, w, b, y);
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
@@ -365,7 +383,7 @@ extern "C" int pdeqx_convT_bwd_filter(const pdeqx_convT_desc* d, const float* x,
   const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;
   PDEQX_CHECK_ARG(gx_blocks < (1ll << 31), "convT_bwd_filter: grid too large");
   int64_t split = ceil_div(148 * 8, gx_blocks);
-  if (split > (int64_t)g.batch * chunks) split = (int64_t)g.batch * chunks;
+  if (split > ceil_div((int64_t)g.batch * g.n_out, CT_WF_P)) split = ceil_div((int64_t)g.batch * g.n_out, CT_WF_P);
   if (split > 65535) split = 65535;
   if (split < 1) split = 1;
   convT_bwd_filter_kernel<<<dim3((unsigned)gx_blocks, (unsigned)split), 256, 0, s>>>(g, x, gy, gw, gb, o_tiles, i_tiles, chunks);
