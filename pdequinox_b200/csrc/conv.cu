@@ -610,10 +610,11 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   PDEQX_TRY(conv_geometry(d, &g));
   cudaStream_t s = (cudaStream_t)stream;
   const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
+  // (the tcgen05 pass overwrites every element of gw / gb: no memset nodes in front of it)
+  if (g.batch > 0 && tc_conv_bwd_filter_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, workspace, workspace_bytes, s);
   PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
   if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
   if (g.batch == 0) return PDEQX_OK;
-  if (tc_conv_bwd_filter_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, workspace, workspace_bytes, s);
   const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
   const int64_t chunks = ceil_div(g.n_out, WF_P);
   const int64_t gx_blocks = (int64_t)g.groups * o_tiles * i_tiles * g.taps;

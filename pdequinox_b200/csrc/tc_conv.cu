@@ -716,6 +716,7 @@ struct WgParams {
   int seg, segs_per_chain;
   int64_t items;  // batch * d * segs_per_chain
   float* scratch;  // [grid][3 tw][3 th][c i][c o]
+  float* bias_part;  // [grid][c o] per-CTA sums of gy (TMEM-operand kernel; nullptr: no bias gradient wanted)
 };
 
 constexpr int kWgRing = 4;   // x rows resident (3 in use + 1 in flight)
@@ -1055,11 +1056,355 @@ conv_wgrad_shift_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_
   }
 }
 
-// gw[o][i][th][tw] = sum_cta scratch[cta][tw][th][i][o]   (+ what the edge kernel adds afterwards)
-__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gw, int nslabs, int C) {
+// ------------------------------------------------------------------------------------------
+// Filter gradient with the column-shifted operands in TENSOR MEMORY (tcgen05.mma, A operand from TMEM).
+// ------------------------------------------------------------------------------------------
+// The kernel above is bound by the shared-memory operand fetch of its MMAs: every tcgen05.mma re-reads its 128-row A tile
+// (4 KB per k-step) next to B, 28 KB per k-step over the four MMAs, and the shifter warps write 64 KB of shifted copies per
+// row through the same pipe. Here the shifted copies never exist in shared memory: the shifter warps read the raw gy row
+// (ld.shared.v4), shift in REGISTERS (a compile-time register offset per dilation residue) and write the A tile straight
+// into tensor memory (tcgen05.st, lane = (column tap, o), column = w); the MMAs take A from TMEM and fetch only B -- the x
+// rows of the ring, 6 KB per k-step and group -- so an M = 128, N = 128 + 64 pair runs at its 96-cycle math floor.
+//   TMEM: columns 0..383 the six accumulators [group][row tap][C] as before; 384..447 A of group 0 ([shift tw=0 ; shift
+//   tw=2], two 32-column stages), 448..511 A of group 1 ([centre ; zeros], two stages).
+//   Shifter warps 4..15 = (role r, lane quarter q): r = 0 / 1 build group 0 for the even / odd 32-column chunks of a row,
+//   r = 2 (q < 2) copies the centre tap and, having every gy element of its channel in registers once, sums the BIAS
+//   gradient on the way (per-CTA partial sums, reduced with the filter-gradient slabs: no separate pass over gy).
+//   The 32 KB of shifted-operand stages the other kernel keeps in shared memory hold a third raw gy row in flight here.
+struct WgtSmem {
+  uint32_t raw_off, ring_off, slot_bytes, box_bytes, bar_off, total;
+};
+constexpr int kWgtThreads = 512;
+constexpr int kWgtRaw = 3;      // raw gy rows in flight
+constexpr int kWgtACol = 384;   // first TMEM column of the A stages
+
+static WgtSmem wgt_smem(int c) {
+  WgtSmem s{};
+  uint32_t off = 0;
+  s.box_bytes = (uint32_t)c * 128;  // [c rows][32 w]
+  s.raw_off = off;
+  off += kWgtRaw * 4 * s.box_bytes;
+  s.ring_off = off;
+  s.slot_bytes = 4 * s.box_bytes;
+  off += kWgRing * s.slot_bytes;
+  s.bar_off = off;
+  off += 1024;
+  s.total = off + 1024;
+  return s;
+}
+
+__global__ void __launch_bounds__(kWgtThreads, 1)
+conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_x, WgParams p, WgtSmem L) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + L.bar_off);
+  uint64_t* rawfull = bars;       // [kWgtRaw] raw gy rows
+  uint64_t* rawempty = bars + 4;  // [kWgtRaw] (one arrive per reading shifter warp)
+  uint64_t* afull = bars + 8;     // [2 groups][2 stages] A chunk is in TMEM
+  uint64_t* aempty = bars + 12;   // [2 groups][2 stages] the MMAs that read it have completed
+  uint64_t* xfull = bars + 16;    // [kWgRing]
+  uint64_t* xempty = bars + 20;   // [kWgRing]
+  uint64_t* done = bars + 24;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 25);
+  uint32_t* inited_s = (uint32_t*)(bars + 26);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.c, W = p.W, d = p.d;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_gy);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kWgtRaw; ++i) {
+      mbar_init(&rawfull[i], 1);
+      mbar_init(&rawempty[i], 10);  // 4 + 4 group-0 warps, 2 centre warps
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&afull[i], 4);      // group 0: the four lane-quarter warps of the stage's role
+      mbar_init(&afull[2 + i], 2);  // group 1: lanes 0..63
+      mbar_init(&aempty[i], 1);
+      mbar_init(&aempty[2 + i], 1);
+    }
+    for (int i = 0; i < kWgRing; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 2);  // both MMA issuers read every x row
+    }
+    mbar_init(done, 2);
+    *inited_s = 0;
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 14 || warp == 15) {
+    // the don't-care upper half (lanes 64..127) of group 1's A stages: zeros once, so that nothing undefined is multiplied
+    float z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0.f;
+    tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kWgtACol + 64), z);
+    tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kWgtACol + 96), z);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const bool zeros = p.boundary == PDEQX_PAD_ZEROS;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    // x ring laid out [32-column chunk c][slot][C rows] as in the kernel above (two row taps in neighbouring slots are one
+    // K-major B operand of N = 2C); dropped (dirichlet) rows are loaded as zeros.
+    if (lane == 0) {
+      uint32_t pe = 0, used = 0, rpe = 0, rused = 0;
+      int rb = 0;
+      for (int64_t item = first; item < p.items; item += stride) {
+        const WgItem it = wg_item(p, item);
+        int v_next = it.j0 - 1;  // next chain row of x to fetch
+        for (int jj = 0; jj < it.count; ++jj) {
+          const int j = it.j0 + jj;
+          const int h = it.r0 + j * p.d;
+          const int v_hi = (j + 2 <= it.j0 + it.count) ? j + 2 : it.j0 + it.count;
+          for (; v_next <= v_hi; ++v_next) {
+            const int row = conv_map(it.r0 + v_next * p.d, p.H, p.boundary);  // -1: a row of zeros
+            const int s = (v_next + 1) & (kWgRing - 1);
+            if (used & (1u << s)) {
+              mbar_wait_backoff(&xempty[s], (pe >> s) & 1u);
+              pe ^= 1u << s;
+            }
+            used |= 1u << s;
+            uint8_t* dst = smem + L.ring_off + (size_t)s * L.box_bytes;
+            mbar_expect_tx(&xfull[s], L.slot_bytes);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.slot_bytes, &tm_x, &xfull[s], c * 32, row, it.b * C);
+          }
+          // the raw gy row of this unit
+          if (rused & (1u << rb)) {
+            mbar_wait_backoff(&rawempty[rb], (rpe >> rb) & 1u);
+            rpe ^= 1u << rb;
+          }
+          rused |= 1u << rb;
+          uint8_t* dst = smem + L.raw_off + (size_t)rb * 4 * L.box_bytes;
+          mbar_expect_tx(&rawfull[rb], 4 * L.box_bytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_gy, &rawfull[rb], c * 32, h, it.b * C);
+          rb = rb == kWgtRaw - 1 ? 0 : rb + 1;
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers (whole warp convergent, one elected lane issues) =====================
+    // warp 1: group 0 (A = [shift tw=0 ; shift tw=2]), warp 2: group 1 (A = [centre ; zeros]). Per 32-column chunk and group:
+    // 4 k-steps x (one MMA of N = 2C over the two row taps in neighbouring ring slots + one of N = C for the third).
+    const int grp = warp - 1;
+    const uint32_t idesc1 = idesc_tf32(128, C, false, false), idesc2 = idesc_tf32(128, 2 * C, false, false);
+    const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem + L.ring_off), 0, 1024);
+    const uint32_t b_hi = (uint32_t)(bdesc0 >> 32), b_lo0 = (uint32_t)bdesc0;
+    const uint32_t box16 = L.box_bytes >> 4, slot16 = L.slot_bytes >> 4;
+    const uint32_t a_col0 = tmem_base + (uint32_t)(kWgtACol + grp * 64);
+    uint32_t pf = 0, apf = 0, started = 0;
+    int st = 0;
+    for (int64_t item = first; item < p.items; item += stride) {
+      const WgItem it = wg_item(p, item);
+      for (int jj = 0; jj < it.count; ++jj) {
+        const int j = it.j0 + jj;
+        const bool last = jj == it.count - 1;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          if (jj == 0 || t == 2) {  // first use of chain row v = j - 1 + t
+            const int s = (j + t) & (kWgRing - 1);
+            mbar_wait(&xfull[s], (pf >> s) & 1u);
+            pf ^= 1u << s;
+          }
+        }
+        // taps t = 0, 1, 2 sit in slots s0, s0 + 1, s0 + 2 (mod 4): the pair that does not wrap around the ring is merged
+        const int s0 = j & (kWgRing - 1);
+        const int pair_t = s0 == kWgRing - 1 ? 1 : 0;  // first tap of the merged pair
+        const int single_t = pair_t == 0 ? 2 : 0;
+        const int pair_s = (j + pair_t) & (kWgRing - 1), single_s = (j + single_t) & (kWgRing - 1);
+        const uint32_t dp = tmem_base + (uint32_t)((3 * grp + pair_t) * C), ds = tmem_base + (uint32_t)((3 * grp + single_t) * C);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(&afull[grp * 2 + st], (apf >> st) & 1u);
+          apf ^= 1u << st;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_t = a_col0 + (uint32_t)(st * 32);
+            const uint32_t bp = b_lo0 + (uint32_t)c * slot16 + (uint32_t)pair_s * box16;
+            const uint32_t bs = b_lo0 + (uint32_t)c * slot16 + (uint32_t)single_s * box16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (c | k) ? 1u : started;
+              mma_tf32_ts(dp, a_t + k * 8, bp + k * 2, b_hi, idesc2, acc);
+              mma_tf32_ts(ds, a_t + k * 8, bs + k * 2, b_hi, idesc1, acc);
+            }
+            mma_commit(&aempty[grp * 2 + st]);
+            if (c == 3) {
+#pragma unroll
+              for (int t = 0; t < 3; ++t)
+                if (t == 0 || last) mma_commit(&xempty[(j + t) & (kWgRing - 1)]);
+            }
+          }
+          __syncwarp();
+          st ^= 1;
+        }
+        started = 1;
+      }
+    }
+    if (elect_one()) {
+      if (grp == 0) *inited_s = started ? 7u : 0u;
+      mma_commit(done);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== shifters: raw gy row (shared memory) -> A chunks (tensor memory) =====================
+    //   group 0, lane (tap, o):  tap 0 (tw = 0): A[o, w'] = gy[o, w' + d];  tap 1 (tw = 2): A[o, w'] = gy[o, w' - d]
+    //   (+ the wrapped / mirrored halo columns that reach x column w' through the boundary map, as in the kernel above).
+    // One thread = one channel row of one 32-column chunk: nine 128-bit loads cover the 32 source columns, which sit at a
+    // warp-uniform register offset 0..3; the chunks whose sources leave the row (dirichlet / neumann edges) go element-wise.
+    const int q = warp & 3, r = (warp - 4) >> 2;
+    const uint32_t raw0 = smem_u32(smem + L.raw_off);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool wrap = p.boundary == PDEQX_PAD_WRAP;
+    const int tap = q >> 1;
+    const int o = (q & 1) * 32 + lane;  // group 0: channel of this lane; group 1 (q < 2): q * 32 + lane, the same number
+    const int dm = d & 3;
+    const int sh = tap == 0 ? d : -d;
+    const int off = tap == 0 ? dm : ((4 - dm) & 3);
+    uint32_t rpf = 0, eph = 0;
+    int rb = 0;
+    float bsum = 0.f;
+    if (r < 2 || q < 2) {
+      for (int64_t item = first; item < p.items; item += stride) {
+        const WgItem it = wg_item(p, item);
+        for (int jj = 0; jj < it.count; ++jj) {
+          mbar_wait(&rawfull[rb], (rpf >> rb) & 1u);
+          rpf ^= 1u << rb;
+          const uint32_t rbase = raw0 + (uint32_t)rb * 4 * L.box_bytes;
+          if (r < 2) {
+            // group 0, chunks c = r and r + 2: always stage r
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = 2 * cc + r;
+              const int w0 = c * 32, src0 = w0 + sh;
+              float in[36];
+              const bool interior = wrap || (src0 >= 0 && src0 + 31 < W && (zeros || (w0 > d && w0 + 31 < W - 1 - d)));
+              if (interior) {
+                const int ub = ((src0 - off) >> 2) & 31;  // first of the nine 16-byte units (circular in the row)
+#pragma unroll
+                for (int u = 0; u < 9; ++u) ld_shared_v4(wgs_elem_addr(rbase, L.box_bytes, o, ((ub + u) & 31) * 4), in + 4 * u);
+                if (off == 1) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) in[i] = in[i + 1];
+                } else if (off == 2) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) in[i] = in[i + 2];
+                } else if (off == 3) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) in[i] = in[i + 3];
+                }
+              } else {
+                // zero-extended direct source + (neumann) the one mirrored halo column that maps onto x column w:
+                //   tap 0: conv_map(e - d) = d - e = w  ->  gy[d - w] for 1 <= w <= d;   tap 2: conv_map(W + e) = W - 2 - e = w  ->
+                //   gy[2W - 2 - d - w] for W - 1 - d <= w <= W - 2
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const int w = w0 + i, src = w + sh;
+                  float a = (src >= 0 && src < W) ? ld_shared_f32(wgs_elem_addr(rbase, L.box_bytes, o, src)) : 0.f;
+                  if (!zeros) {
+                    const int hs = tap == 0 ? d - w : 2 * W - 2 - d - w;
+                    const bool has = tap == 0 ? (w >= 1 && w <= d) : (w >= W - 1 - d && w <= W - 2);
+                    if (has) a += ld_shared_f32(wgs_elem_addr(rbase, L.box_bytes, o, hs));
+                  }
+                  in[i] = a;
+                }
+              }
+              mbar_wait(&aempty[r], (eph & 1u) ^ 1u);  // the MMAs on this stage's previous chunk have completed
+              eph ^= 1u;
+              tc_fence_after();
+              tmem_st32(lane_base + (uint32_t)(kWgtACol + r * 32), in);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&afull[r]);
+            }
+          } else {
+            // group 1: the centre tap is the raw row itself; its running sum is the bias gradient
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              const int st = c & 1;
+              float in[32];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) ld_shared_v4(wgs_elem_addr(rbase, L.box_bytes, o, c * 32 + u * 4), in + 4 * u);
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int i = 0; i < 32; ++i) s4[i & 3] += in[i];
+              bsum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              mbar_wait(&aempty[2 + st], ((eph >> st) & 1u) ^ 1u);
+              eph ^= 1u << st;
+              tc_fence_after();
+              tmem_st32(lane_base + (uint32_t)(kWgtACol + 64 + st * 32), in);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&afull[2 + st]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rawempty[rb]);  // this warp's loads of the row have all landed in registers
+          rb = rb == kWgtRaw - 1 ? 0 : rb + 1;
+        }
+      }
+    }
+    if (r == 2 && q < 2 && p.bias_part) p.bias_part[(size_t)blockIdx.x * C + o] = bsum;
+    if (r == 0) {
+      // ===================== flush: TMEM -> scratch[cta][tw][th][i][o] =====================
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const uint32_t inited = *(volatile uint32_t*)inited_s;
+      float* out = p.scratch + (size_t)blockIdx.x * 9 * C * C;
+      for (int g = 0; g < 2; ++g) {
+        if (g == 1 && q >= 2) break;
+        const int tw = g == 0 ? (q < 2 ? 0 : 2) : 1;
+        for (int t = 0; t < 3; ++t) {
+          for (int c0 = 0; c0 < C; c0 += 16) {
+            float v[16];
+            tmem_ld16(lane_base + (uint32_t)((g * 3 + t) * C + c0), v);
+            tmem_ld_wait();
+            if (o < C) {
+#pragma unroll
+              for (int jx = 0; jx < 16; ++jx)
+                out[((size_t)(tw * 3 + t) * C + c0 + jx) * C + o] = ((inited >> t) & 1u) ? v[jx] : 0.f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// gw[o][i][th][tw] = sum_cta scratch[cta][tw][th][i][o]   (+ what the edge kernel adds afterwards);
+// gb[o] = sum_cta bias_part[cta][o] when the filter-gradient kernel summed gy on the way (bias_part != nullptr)
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gw, int nslabs, int C,
+                                         const float* __restrict__ bias_part, float* __restrict__ gb) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [tw][th][i][o]
   const int total = 9 * C * C;
-  if (idx >= total) return;
+  if (idx >= total) {
+    if (bias_part && idx < total + C) {
+      const int o = idx - total;
+      float acc = 0.f;
+      for (int s = 0; s < nslabs; ++s) acc += __ldg(bias_part + (size_t)s * C + o);
+      gb[o] = acc;
+    }
+    return;
+  }
   // eight independent partial sums: the 148 slab reads of a thread are otherwise one latency-bound dependent chain
   float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int s = 0;
@@ -1135,10 +1480,11 @@ constexpr size_t kWprepFloats = 64 * 64 * 9;
 constexpr size_t kWgSlabs = 160;  // one partial filter gradient [3 tw][3 th][64 i][64 o] per CTA of the filter-gradient kernel
 size_t tc_conv_workspace_bytes(const ConvGeom& g) {
   if (!tc_conv_available(g)) return 0;
-  return sizeof(float) * (kWprepFloats + kWgSlabs * 9 * 64 * 64) + 256;
+  return sizeof(float) * (kWprepFloats + kWgSlabs * (9 * 64 * 64 + 64)) + 256;
 }
 static float* ws_wprep(void* ws) { return (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255); }
 static float* ws_wgrad(void* ws) { return ws_wprep(ws) + kWprepFloats; }
+static float* ws_bias_part(void* ws) { return ws_wgrad(ws) + kWgSlabs * 9 * 64 * 64; }  // [slab][64] per-CTA sums of gy
 
 bool tc_conv_available(const ConvGeom& g) {
   if (!g_fast_paths.load(std::memory_order_relaxed)) return false;
@@ -1340,17 +1686,51 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
   wp.segs_per_chain = (int)ceil_div(max_chain, wp.seg);
   wp.items = (int64_t)g.batch * d * wp.segs_per_chain;
   wp.scratch = ws_wgrad(ws);
+  // Work items: chain segments of `seg` rows (+ one halo row at either end). A divisor of the chain length that balances
+  // the CTAs: cost = rounds of the busiest CTA x (seg + 1).
+  {
+    const int chain = max_chain;
+    int best = 0;
+    int64_t best_cost = 0;
+    for (int seg = 4; seg <= 64 && seg <= chain; ++seg) {
+      if (chain % seg) continue;
+      const int64_t items = (int64_t)g.batch * d * (chain / seg);
+      const int64_t cost = ceil_div(items, (int64_t)sms) * (seg + 1);
+      if (!best || cost < best_cost) { best = seg; best_cost = cost; }
+    }
+    if (best && H % d == 0) {
+      wp.seg = best;
+      wp.segs_per_chain = chain / best;
+      wp.items = (int64_t)g.batch * d * wp.segs_per_chain;
+    }
+  }
+  const int grid = (int)(wp.items < sms ? wp.items : sms);
+  // A operand from tensor memory (default) / shifted copies in shared memory (PDEQX_WG_TMEM=0: the round-1 kernel)
+  static const bool tmem_a = [] { const char* e = getenv("PDEQX_WG_TMEM"); return !(e && e[0] == '0'); }();
+  if (tmem_a) {
+    tc::WgtSmem L = tc::wgt_smem(C);
+    PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
+    wp.bias_part = gb ? ws_bias_part(ws) : nullptr;
+    static DeviceOnce attr;
+    if (attr.first_use())
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    tc::conv_wgrad_tmem_kernel<<<grid, tc::kWgtThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
+    PDEQX_LAUNCHED();
+    tc::conv_wgrad_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, wp.bias_part, gb);
+    PDEQX_LAUNCHED();
+    return PDEQX_OK;
+  }
   tc::WgsSmem L = tc::wgs_smem(C);
   PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
-  const int grid = (int)(wp.items < sms ? wp.items : sms);
   static DeviceOnce attr;
   if (attr.first_use())
     PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   tc::conv_wgrad_shift_kernel<<<grid, tc::kWgsThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
   PDEQX_LAUNCHED();
-  tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C);
+  tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, nullptr, nullptr);
   PDEQX_LAUNCHED();
   if (gb) {
+    PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)C, s));
     tc::conv_bias_grad_kernel<<<g.batch * C, 256, 0, s>>>(gy, gb, C, (int64_t)H * W);
     PDEQX_LAUNCHED();
   }
