@@ -1075,38 +1075,39 @@ struct WgtSmem {
   uint32_t raw_off, ring_off, slot_bytes, box_bytes, bar_off, total;
 };
 constexpr int kWgtThreads = 512;
-constexpr int kWgtRaw = 3;      // raw gy rows in flight
 constexpr int kWgtACol = 384;   // first TMEM column of the A stages
 
-static WgtSmem wgt_smem(int c) {
+static WgtSmem wgt_smem(int c, int ring, int raw) {
   WgtSmem s{};
   uint32_t off = 0;
   s.box_bytes = (uint32_t)c * 128;  // [c rows][32 w]
   s.raw_off = off;
-  off += kWgtRaw * 4 * s.box_bytes;
+  off += (uint32_t)raw * 4 * s.box_bytes;
   s.ring_off = off;
-  s.slot_bytes = 4 * s.box_bytes;
-  off += kWgRing * s.slot_bytes;
+  s.slot_bytes = (uint32_t)ring * s.box_bytes;  // stride between the 32-column chunks of the ring: [chunk][slot][c rows]
+  off += 4 * s.slot_bytes;
   s.bar_off = off;
   off += 1024;
   s.total = off + 1024;
   return s;
 }
 
+// RING = x rows resident (3 in use + RING - 3 in flight), RAW = raw gy rows in flight: (4, 3) or (5, 2) fill the 227 KB
+template <int RING, int RAW>
 __global__ void __launch_bounds__(kWgtThreads, 1)
 conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_constant__ CUtensorMap tm_x, WgParams p, WgtSmem L) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + L.bar_off);
-  uint64_t* rawfull = bars;       // [kWgtRaw] raw gy rows
-  uint64_t* rawempty = bars + 4;  // [kWgtRaw] (one arrive per reading shifter warp)
+  uint64_t* rawfull = bars;       // [RAW] raw gy rows
+  uint64_t* rawempty = bars + 4;  // [RAW] (one arrive per reading shifter warp)
   uint64_t* afull = bars + 8;     // [2 groups][2 stages] A chunk is in TMEM
   uint64_t* aempty = bars + 12;   // [2 groups][2 stages] the MMAs that read it have completed
-  uint64_t* xfull = bars + 16;    // [kWgRing]
-  uint64_t* xempty = bars + 20;   // [kWgRing]
-  uint64_t* done = bars + 24;
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 25);
-  uint32_t* inited_s = (uint32_t*)(bars + 26);
+  uint64_t* xfull = bars + 16;    // [RING]
+  uint64_t* xempty = bars + 24;   // [RING]
+  uint64_t* done = bars + 32;
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 33);
+  uint32_t* inited_s = (uint32_t*)(bars + 34);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.c, W = p.W, d = p.d;
   if (warp == 0 && lane == 0) {
@@ -1114,7 +1115,7 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
     tma_prefetch_desc(&tm_x);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kWgtRaw; ++i) {
+    for (int i = 0; i < RAW; ++i) {
       mbar_init(&rawfull[i], 1);
       mbar_init(&rawempty[i], 10);  // 4 + 4 group-0 warps, 2 centre warps
     }
@@ -1124,7 +1125,7 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
       mbar_init(&aempty[i], 1);
       mbar_init(&aempty[2 + i], 1);
     }
-    for (int i = 0; i < kWgRing; ++i) {
+    for (int i = 0; i < RING; ++i) {
       mbar_init(&xfull[i], 1);
       mbar_init(&xempty[i], 2);  // both MMA issuers read every x row
     }
@@ -1157,29 +1158,42 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
     // x ring laid out [32-column chunk c][slot][C rows] as in the kernel above (two row taps in neighbouring slots are one
     // K-major B operand of N = 2C); dropped (dirichlet) rows are loaded as zeros.
     if (lane == 0) {
-      uint32_t pe = 0, used = 0, rpe = 0, rused = 0;
-      int rb = 0;
+      uint32_t pe = 0, used = 0;
       for (int64_t item = first; item < p.items; item += stride) {
         const WgItem it = wg_item(p, item);
         int v_next = it.j0 - 1;  // next chain row of x to fetch
         for (int jj = 0; jj < it.count; ++jj) {
           const int j = it.j0 + jj;
-          const int h = it.r0 + j * p.d;
-          const int v_hi = (j + 2 <= it.j0 + it.count) ? j + 2 : it.j0 + it.count;
+          const int v_hi = (j + RING - 2 <= it.j0 + it.count) ? j + RING - 2 : it.j0 + it.count;
           for (; v_next <= v_hi; ++v_next) {
             const int row = conv_map(it.r0 + v_next * p.d, p.H, p.boundary);  // -1: a row of zeros
-            const int s = (v_next + 1) & (kWgRing - 1);
+            const int s = (v_next + 1) % RING;
             if (used & (1u << s)) {
               mbar_wait_backoff(&xempty[s], (pe >> s) & 1u);
               pe ^= 1u << s;
             }
             used |= 1u << s;
             uint8_t* dst = smem + L.ring_off + (size_t)s * L.box_bytes;
-            mbar_expect_tx(&xfull[s], L.slot_bytes);
+            mbar_expect_tx(&xfull[s], 4 * L.box_bytes);
 #pragma unroll
             for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.slot_bytes, &tm_x, &xfull[s], c * 32, row, it.b * C);
           }
-          // the raw gy row of this unit
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA producer of the raw gy rows =====================
+    // A thread of its own: the x producer above blocks on a ring slot that the MMAs of the previous unit still read, and a gy
+    // row requested only behind that wait arrives one full DRAM latency late in EVERY unit (ncu: the shifter warps' wait for
+    // the raw row was the top stall, the tensor pipe 50 % idle). This thread waits for nothing but a free raw buffer, so
+    // RAW rows are in flight.
+    if (lane == 0) {
+      uint32_t rpe = 0, rused = 0;
+      int rb = 0;
+      for (int64_t item = first; item < p.items; item += stride) {
+        const WgItem it = wg_item(p, item);
+        for (int jj = 0; jj < it.count; ++jj) {
+          const int h = it.r0 + (it.j0 + jj) * p.d;
           if (rused & (1u << rb)) {
             mbar_wait_backoff(&rawempty[rb], (rpe >> rb) & 1u);
             rpe ^= 1u << rb;
@@ -1189,7 +1203,7 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
           mbar_expect_tx(&rawfull[rb], 4 * L.box_bytes);
 #pragma unroll
           for (int c = 0; c < 4; ++c) tma_load_3d(dst + c * L.box_bytes, &tm_gy, &rawfull[rb], c * 32, h, it.b * C);
-          rb = rb == kWgtRaw - 1 ? 0 : rb + 1;
+          rb = rb == RAW - 1 ? 0 : rb + 1;
         }
       }
     }
@@ -1213,16 +1227,16 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
           if (jj == 0 || t == 2) {  // first use of chain row v = j - 1 + t
-            const int s = (j + t) & (kWgRing - 1);
+            const int s = (j + t) % RING;
             mbar_wait(&xfull[s], (pf >> s) & 1u);
             pf ^= 1u << s;
           }
         }
         // taps t = 0, 1, 2 sit in slots s0, s0 + 1, s0 + 2 (mod 4): the pair that does not wrap around the ring is merged
-        const int s0 = j & (kWgRing - 1);
-        const int pair_t = s0 == kWgRing - 1 ? 1 : 0;  // first tap of the merged pair
+        const int s0 = j % RING;
+        const int pair_t = s0 == RING - 1 ? 1 : 0;  // first tap of the merged pair
         const int single_t = pair_t == 0 ? 2 : 0;
-        const int pair_s = (j + pair_t) & (kWgRing - 1), single_s = (j + single_t) & (kWgRing - 1);
+        const int pair_s = (j + pair_t) % RING, single_s = (j + single_t) % RING;
         const uint32_t dp = tmem_base + (uint32_t)((3 * grp + pair_t) * C), ds = tmem_base + (uint32_t)((3 * grp + single_t) * C);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -1243,7 +1257,7 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
             if (c == 3) {
 #pragma unroll
               for (int t = 0; t < 3; ++t)
-                if (t == 0 || last) mma_commit(&xempty[(j + t) & (kWgRing - 1)]);
+                if (t == 0 || last) mma_commit(&xempty[(j + t) % RING]);
             }
           }
           __syncwarp();
@@ -1353,7 +1367,7 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&rawempty[rb]);  // this warp's loads of the row have all landed in registers
-          rb = rb == kWgtRaw - 1 ? 0 : rb + 1;
+          rb = rb == RAW - 1 ? 0 : rb + 1;
         }
       }
     }
@@ -1708,13 +1722,17 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
   // A operand from tensor memory (default) / shifted copies in shared memory (PDEQX_WG_TMEM=0: the round-1 kernel)
   static const bool tmem_a = [] { const char* e = getenv("PDEQX_WG_TMEM"); return !(e && e[0] == '0'); }();
   if (tmem_a) {
-    tc::WgtSmem L = tc::wgt_smem(C);
+    static const bool ring5 = [] { const char* e = getenv("PDEQX_WG_RING5"); return e && e[0] == '1'; }();
+    tc::WgtSmem L = ring5 ? tc::wgt_smem(C, 5, 2) : tc::wgt_smem(C, 4, 3);
     PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
     wp.bias_part = gb ? ws_bias_part(ws) : nullptr;
     static DeviceOnce attr;
-    if (attr.first_use())
-      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc::conv_wgrad_tmem_kernel<<<grid, tc::kWgtThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
+    if (attr.first_use()) {
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_tmem_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_tmem_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    if (ring5) tc::conv_wgrad_tmem_kernel<5, 2><<<grid, tc::kWgtThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
+    else tc::conv_wgrad_tmem_kernel<4, 3><<<grid, tc::kWgtThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
     PDEQX_LAUNCHED();
     tc::conv_wgrad_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, wp.bias_part, gb);
     PDEQX_LAUNCHED();
