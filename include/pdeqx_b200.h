@@ -346,6 +346,54 @@ int pdeqx_groupnorm_bwd(int32_t batch, int32_t channels, int32_t groups, int64_t
                         float* gweight, float* gbias, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * GroupNorm folded into the convolutions around it ("stats in the producer's epilogue, normalise on load")
+ *   replaces the norm -> conv -> act chain of pdequinox/blocks/_dilated_res_block.py:141-151 (eqx.nn.GroupNorm with
+ *   groups = 1 in front of a periodic PhysicsConv) without the normalised tensor ever being written or read:
+ *     forward   conv(gamma (h - mu_b) rstd_b + beta) = rstd_b conv(h; W gamma) + const[b, o]: gamma rides in the prepared
+ *               filter, rstd_b and the constant in the epilogue, which also sums y, y^2 per sample for the NEXT norm;
+ *     filter    gradient against the virtual normalised input: the cotangent operand is scaled by rstd_b on its way into
+ *               tensor memory, gamma / beta / mu enter as a rank-one correction when the per-CTA partial sums are reduced;
+ *     data      v = corr^T(gy, w) with sum gamma v and sum gamma v h per sample from the epilogue, then ONE elementwise
+ *               pass (pdeqx_groupnorm_bwd_fused) forms the norm's input gradient, relu' of the layer in front and the
+ *               norm's parameter gradients.
+ *   Accepted shapes: pdeqx_conv_gn_fusable(d) != 0 (the tcgen05 CTA-pair shapes -- 2-D, k = 3, stride 1, W = 128,
+ *   C = 64, H % dilation == 0, TF32 precision -- with periodic boundary: only there is the norm's shift a per-sample
+ *   constant). Everything else takes pdeqx_groupnorm_fwd/bwd + pdeqx_conv_*.
+ *   parts: [B][slots][2] fp32 partial sums, slots = pdeqx_conv_gn_slots(d) for the buffers the convolution passes write.
+ * ------------------------------------------------------------------------- */
+int pdeqx_conv_gn_fusable(const pdeqx_conv_desc* d);
+int pdeqx_conv_gn_slots(const pdeqx_conv_desc* d);
+/* y = act(corr(pad(gn(x)), w) + b), gn = GroupNorm(groups = 1) with statistics gn_stats [B][2] = (mean, rstd) of x and
+ * affine gn_weight / gn_bias [c_in] (NULL: 1 / 0). out_parts (may be NULL): per-sample partial sums (y, y^2). */
+int pdeqx_conv_gn_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b, const float* gn_stats,
+                      const float* gn_weight, const float* gn_bias, int32_t activation, float* y, float* out_parts,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* gw = sum gy . pad(gn(x)), gb = sum gy (may be NULL); x is the norm's INPUT */
+int pdeqx_conv_gn_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, const float* gn_stats,
+                             const float* gn_weight, const float* gn_bias, float* gw, float* gb, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* v = adjoint-of-pad(corr^T(gy, w)) (the cotangent of gn(h)); parts [B][slots][2] = per-sample partial sums
+ * (gamma_c v, gamma_c v h) */
+int pdeqx_conv_gn_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* gn_weight, const float* h,
+                           float* v, float* parts, void* workspace, size_t workspace_bytes, void* stream);
+/* statistics only: stats [B,groups,2] = (mean, rstd); workspace: pdeqx_groupnorm_workspace_bytes */
+int pdeqx_groupnorm_stats(int32_t batch, int32_t channels, int32_t groups, int64_t n, const float* x, float eps,
+                          float* stats, void* workspace, void* stream);
+/* groups = 1: stats [B][2] from per-sample partial sums (x, x^2) over `count` elements per sample */
+int pdeqx_groupnorm_stats_from_parts(int32_t batch, int32_t slots, int64_t count, const float* parts, float eps,
+                                     float* stats, void* stream);
+/* out = a + b (the residual join of a block, [B][per_sample]) + per-sample partial sums (out, out^2) in parts [B][slots][2];
+ * per_sample % (4 slots) == 0 */
+int pdeqx_add_parts(int32_t batch, int64_t per_sample, int32_t slots, const float* a, const float* b, float* out,
+                    float* parts, void* stream);
+/* gx = rstd_b (gamma_c v - s1_b - xhat s2_b) [* (h > 0) if relu_mask_h] [+ add], gweight, gbias (may be NULL; overwritten);
+ * parts / slots as written by pdeqx_conv_gn_bwd_data; scratch: 2*B*C floats; n % 4 == 0 */
+int pdeqx_groupnorm_bwd_fused(int32_t batch, int32_t channels, int64_t n, const float* h, const float* v,
+                              const float* weight, const float* stats, const float* parts, int32_t slots,
+                              int32_t relu_mask_h, const float* add, float* gx, float* gweight, float* gbias,
+                              float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Elementwise pieces of the block / training step
  * ------------------------------------------------------------------------- */
 /* gx = gy * act'(pre) (gelu'/relu' evaluated on the PRE-activation) */

@@ -102,6 +102,15 @@ PROTOTYPES = {
     "pdeqx_groupnorm_fwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _F, _P, _P, _P, _P]),
     "pdeqx_groupnorm_bwd": (C.c_int, [_I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pdeqx_activation_fwd": (C.c_int, [_I64, _P, _I32, _P, _P]),
+    "pdeqx_conv_gn_fusable": (C.c_int, [C.POINTER(ConvDesc)]),
+    "pdeqx_conv_gn_slots": (C.c_int, [C.POINTER(ConvDesc)]),
+    "pdeqx_conv_gn_fwd": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_conv_gn_bwd_filter": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_conv_gn_bwd_data": (C.c_int, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "pdeqx_groupnorm_stats": (C.c_int, [_I32, _I32, _I32, _I64, _P, _F, _P, _P, _P]),
+    "pdeqx_groupnorm_stats_from_parts": (C.c_int, [_I32, _I32, _I64, _P, _F, _P, _P]),
+    "pdeqx_add_parts": (C.c_int, [_I32, _I64, _I32, _P, _P, _P, _P, _P]),
+    "pdeqx_groupnorm_bwd_fused": (C.c_int, [_I32, _I32, _I64, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "pdeqx_add": (C.c_int, [_I64, _P, _P, _P, _P]),
     "pdeqx_activation_bwd": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),
     "pdeqx_mse_loss": (C.c_int, [_I64, _P, _P, _F, _P, _P, _P, _P]),

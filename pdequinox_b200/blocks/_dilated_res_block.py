@@ -1,5 +1,7 @@
 """DilatedResBlock: per dilation rate norm -> conv -> act, then + bypass
 (reference: pdequinox/blocks/_dilated_res_block.py:18-158)."""
+import os
+
 from .. import _lib, nn, random as jr
 from ..conv import PhysicsConv, PointwiseLinearConv
 from ..nn import Identity
@@ -47,8 +49,52 @@ class DilatedResBlock(Block):
         from .._utils import sum_receptive_fields
         return sum_receptive_fields(tuple(c.receptive_field for c in self.conv_layers))
 
+    # ---- GroupNorm folded into the convolutions (statistics in the producer's epilogue, normalise on
+    # load): every norm is groups = 1, every conv a periodic tcgen05 CTA-pair shape, the skip is the identity ----
+    def _gn_folded(self, x, act):
+        if os.environ.get("PDEQX_GN_FOLD", "1") == "0":  # experiment knob: separate GroupNorm passes
+            return False
+        if act not in (_lib.ACT_RELU, _lib.ACT_IDENTITY) or not isinstance(self.bypass_conv, Identity):
+            return False
+        if not all(isinstance(n, nn.GroupNorm) and n.groups == 1 for n in self.norm_layers):
+            return False
+        return all(c.gn_fusable(x) for c in self.conv_layers)
+
+    def _fwd_folded(self, x, tape, act):
+        B, count = x.shape[0], x[0].numel()
+        h, parts, slots = x, *getattr(x, "_pdeqx_parts", (None, 0))
+        saved, stats_all = [], []
+        last = len(self.conv_layers) - 1
+        for j, (norm, conv) in enumerate(zip(self.norm_layers, self.conv_layers)):
+            stats = norm.stats_of(h, tape) if parts is None else norm.stats_from_parts(parts, slots, B, count, tape)
+            out, parts, slots = conv.apply_gn(h, norm, stats, tape, act=act, tag="a", want_parts=j < last)
+            saved.append((h, out, None))
+            stats_all.append(stats)
+            h = out
+        y, yparts, yslots = nn.add_parts(h, x, tape, self, "y")
+        y._pdeqx_parts = (yparts, yslots)  # the next block's first norm reads its statistics from these
+        if tape is not None:
+            tape.push({"dilated_folded": stats_all})
+            tape.push(saved)
+        return y
+
+    def _bwd_folded(self, gy, tape, saved, stats_all, act):
+        last = len(self.conv_layers) - 1
+        g = gy
+        for j in reversed(range(len(self.conv_layers))):
+            h, out, _ = saved[j]
+            conv, norm = self.conv_layers[j], self.norm_layers[j]
+            # below the last layer `g` already carries relu' of this layer's output (applied by the norm pass behind it)
+            ga = nn.activation_bwd(out, g, act, tape, conv, "ga") if j == last else g
+            v, parts, slots = conv.apply_bwd_gn(h, ga, norm, stats_all[j], tape)
+            g = norm.bwd_fused(h, v, stats_all[j], parts, slots, tape, mask_h=(j > 0 and act == _lib.ACT_RELU),
+                               add=gy if j == 0 else None)
+        return g
+
     def _fwd(self, x, tape):
         act = nn.activation_code(self.activation)
+        if self._gn_folded(x, act):
+            return self._fwd_folded(x, tape, act)
         fuse = act in (_lib.ACT_RELU, _lib.ACT_IDENTITY)
         identity_skip = isinstance(self.bypass_conv, Identity)
         skip = x if identity_skip else self.bypass_conv._fwd(self.bypass_norm._fwd(x, tape), tape)
@@ -66,13 +112,20 @@ class DilatedResBlock(Block):
                 saved.append((hn, out, pre))
             h = out
         y = nn.add(h, skip, tape, self, "y")
+        if hasattr(y, "_pdeqx_parts"):  # (a persistent buffer that an earlier, folded pass annotated)
+            del y._pdeqx_parts
         if tape is not None:
+            tape.push({"dilated_folded": None})
             tape.push(saved)
         return y
 
     def _bwd(self, gy, tape, need_gx=True):
         act = nn.activation_code(self.activation)
         saved = tape.pop()
+        stats_all = tape.pop()["dilated_folded"]
+        if stats_all is not None:
+            g = self._bwd_folded(gy, tape, saved, stats_all, act)
+            return g if need_gx else None
         identity_skip = isinstance(self.bypass_conv, Identity)
         g = gy
         premasked = False  # True: `g` already carries relu' of layer j's output (applied by the GroupNorm reverse pass behind it)

@@ -111,6 +111,45 @@ class MorePaddingConv(Module):
                                          ws, nws, _lib.stream()))
         return gx
 
+    # ---- GroupNorm (groups = 1) in front of this convolution folded into its passes (pdeqx_conv_gn_*) ----
+    def gn_fusable(self, x):
+        """True when the norm -> conv -> act chain of _dilated_res_block.py:141-151 runs without the normalised tensor:
+        the tcgen05 CTA-pair shapes with periodic boundary, TF32 mode."""
+        d, _ = self._desc(x)
+        return bool(_lib.lib().pdeqx_conv_gn_fusable(d))
+
+    def apply_gn(self, x, norm, stats, tape, *, act=_lib.ACT_IDENTITY, tag="y", want_parts=True):
+        """act(conv(norm(x)) + bias) from x itself; returns (y, parts, slots): per-sample partial sums (y, y^2) for the norm
+        behind this layer."""
+        d, out_sp = self._desc(x)
+        L = _lib.lib()
+        y = new_buf(tape, self, tag, (x.shape[0], self.out_channels) + out_sp)
+        slots = L.pdeqx_conv_gn_slots(d)
+        parts = new_buf(tape, self, "gn_parts", (x.shape[0] * slots * 2,)) if want_parts else None
+        nws = L.pdeqx_conv_workspace_bytes(d)
+        _lib.check(L.pdeqx_conv_gn_fwd(d, _lib.ptr(x), _lib.ptr(self.weight), _lib.ptr(self.bias), _lib.ptr(stats),
+                                       _lib.ptr(norm.weight), _lib.ptr(norm.bias), act, _lib.ptr(y), _lib.ptr(parts),
+                                       _lib.ptr(conv_workspace(tape, nws)), nws, _lib.stream()))
+        return y, parts, slots
+
+    def apply_bwd_gn(self, h, gy, norm, stats, tape, tag="gv"):
+        """Filter / bias gradients against the (virtual) normalised input, and v = the cotangent of norm(h) with its
+        per-sample sums (gamma v, gamma v h) for pdeqx_groupnorm_bwd_fused; returns (v, parts, slots)."""
+        d, _ = self._desc(h)
+        L = _lib.lib()
+        gb = self.grad("bias") if self.bias is not None else None
+        nws = L.pdeqx_conv_workspace_bytes(d)
+        ws = _lib.ptr(conv_workspace(tape, nws))
+        _lib.check(L.pdeqx_conv_gn_bwd_filter(d, _lib.ptr(h), _lib.ptr(gy), _lib.ptr(stats), _lib.ptr(norm.weight),
+                                              _lib.ptr(norm.bias), _lib.ptr(self.grad("weight")), _lib.ptr(gb), ws, nws,
+                                              _lib.stream()))
+        slots = L.pdeqx_conv_gn_slots(d)
+        v = new_buf(tape, self, tag, h.shape)
+        parts = new_buf(tape, self, "gn_bparts", (h.shape[0] * slots * 2,))
+        _lib.check(L.pdeqx_conv_gn_bwd_data(d, _lib.ptr(gy), _lib.ptr(self.weight), _lib.ptr(norm.weight), _lib.ptr(h),
+                                            _lib.ptr(v), _lib.ptr(parts), ws, nws, _lib.stream()))
+        return v, parts, slots
+
     def _fwd(self, x, tape):
         y = self.apply(x, tape)
         if tape is not None:

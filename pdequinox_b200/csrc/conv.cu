@@ -628,3 +628,59 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm (groups = 1) -> PhysicsConv -> activation, the norm folded into the convolution's passes (tc_conv.cu)
+// ------------------------------------------------------------------------------------------
+extern "C" int pdeqx_conv_gn_fusable(const pdeqx_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geometry(d, &g) != PDEQX_OK) return 0;
+  return tc_conv_gn_fusable(g) ? 1 : 0;
+}
+
+extern "C" int pdeqx_conv_gn_slots(const pdeqx_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geometry(d, &g) != PDEQX_OK || !tc_conv_gn_fusable(g)) return 0;
+  return tc_conv_gn_slots(g);
+}
+
+static int gn_geometry(const pdeqx_conv_desc* d, ConvGeom* g) {
+  PDEQX_TRY(conv_geometry(d, g));
+  if (!tc_conv_gn_fusable(*g)) {
+    set_error("this convolution does not take the fused GroupNorm passes (pdeqx_conv_gn_fusable)");
+    return PDEQX_ERR_UNSUPPORTED;
+  }
+  return PDEQX_OK;
+}
+
+extern "C" int pdeqx_conv_gn_fwd(const pdeqx_conv_desc* d, const float* x, const float* w, const float* b, const float* gn_stats,
+                                 const float* gn_weight, const float* gn_bias, int32_t activation, float* y, float* out_parts,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(x && w && y && gn_stats, "null argument");
+  PDEQX_CHECK_ARG(activation >= 0 && activation <= 2, "unknown activation %d", activation);
+  ConvGeom g;
+  PDEQX_TRY(gn_geometry(d, &g));
+  if (g.batch == 0) return PDEQX_OK;
+  return tc_conv_gn_fwd(g, x, w, b, gn_stats, gn_weight, gn_bias, activation, y, out_parts, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int pdeqx_conv_gn_bwd_filter(const pdeqx_conv_desc* d, const float* x, const float* gy, const float* gn_stats,
+                                        const float* gn_weight, const float* gn_bias, float* gw, float* gb, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  PDEQX_CHECK_ARG(x && gy && gw && gn_stats, "null argument");
+  ConvGeom g;
+  PDEQX_TRY(gn_geometry(d, &g));
+  if (g.batch == 0) return PDEQX_OK;
+  return tc_conv_gn_bwd_filter(g, x, gy, gn_stats, gn_weight, gn_bias, gw, gb, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int pdeqx_conv_gn_bwd_data(const pdeqx_conv_desc* d, const float* gy, const float* w, const float* gn_weight,
+                                      const float* h, float* v, float* parts, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  PDEQX_CHECK_ARG(gy && w && h && v && parts, "null argument");
+  ConvGeom g;
+  PDEQX_TRY(gn_geometry(d, &g));
+  if (g.batch == 0) return PDEQX_OK;
+  return tc_conv_gn_bwd_data(g, gy, w, gn_weight, h, v, parts, workspace, workspace_bytes, (cudaStream_t)stream);
+}

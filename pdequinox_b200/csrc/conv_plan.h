@@ -33,4 +33,14 @@ int tc_conv_bwd_data(const ConvGeom& g, const float* gy, const float* w, const f
 int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws, size_t ws_bytes,
                        cudaStream_t s);
 
+// GroupNorm (groups = 1) folded into the three passes of a periodic tcgen05 convolution (tc_conv.cu)
+bool tc_conv_gn_fusable(const ConvGeom& g);
+int tc_conv_gn_slots(const ConvGeom& g);
+int tc_conv_gn_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* stats, const float* gamma,
+                   const float* beta, int act, float* y, float* out_parts, void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_conv_gn_bwd_filter(const ConvGeom& g, const float* x, const float* gy, const float* stats, const float* gamma,
+                          const float* beta, float* gw, float* gb, void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_conv_gn_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* gamma, const float* h, float* v,
+                        float* parts, void* ws, size_t ws_bytes, cudaStream_t s);
+
 }  // namespace pdeqx

@@ -40,6 +40,12 @@ struct ConvParams {
   const float* res;
   const float* mask;  // optional [B, c_out, H, W]: the result is zeroed where mask <= 0 (relu' of the layer in front, applied
                       // in the data-gradient pass that produces its cotangent instead of in a pass of its own)
+  // GroupNorm (groups = 1) folded into the pair kernel (template parameter GN, see conv_rows_pair_kernel):
+  const float* gn_stats;  // GN 1: [B][2] (mean, rstd) of the conv input -- the accumulator is scaled by rstd_b in the epilogue
+  const float* bias_b;    // GN 1: [B][c_out] per-sample epilogue constant (bias + what the norm's shift contributes)
+  float* parts;           // GN 1: [B][slots][2] partial sums (y, y^2) of the output = the NEXT norm's statistics (may be NULL);
+                          // GN 2: [B][slots][2] partial sums (gamma v, gamma v h) of the data gradient v (the norm's reverse pass)
+  int slots;              // partial sums per sample: items per sample x 16 epilogue warps
 };
 
 struct ConvSmem {
@@ -406,7 +412,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 //     different rows and must issue the same instruction stream.
 constexpr int kAcc2 = 2;  // accumulator stages: 2 x 192 columns
 
-template <int ACT>
+// GN = 0: plain. GN = 1: forward pass with a GroupNorm (groups = 1) in front folded in -- the filter carries gamma (prepared
+// weights), the epilogue computes act(rstd_b * D + bias_b[b, o]) and sums y, y^2 per sample for the norm BEHIND this layer.
+// GN = 2: data gradient whose result v feeds that norm's reverse pass -- bias_s holds gamma, p.mask the norm's input h (read,
+// not applied): the epilogue sums gamma v and gamma v h per sample (pdequinox/blocks/_dilated_res_block.py:141-151).
+template <int ACT, int GN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res, ConvParams p, ConvSmem L) {
@@ -447,7 +457,7 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   }
   if (warp == 2) tmem_alloc_pair<kConvTmemCols>(tmem_ptr);
   if (warp == 3) {
-    for (int i = lane; i < p.c_out; i += 32) bias_s[i] = p.has_bias ? p.bias[i] : 0.f;
+    for (int i = lane; i < p.c_out; i += 32) bias_s[i] = p.has_bias ? p.bias[i] : (GN == 2 ? 1.f : 0.f);  // (GN 2: gamma)
     if (lane < 16) ((float*)(smem + L.xbuf_off + 2 * 16 * 8 * kMaxDil * 4))[lane] = 0.f;
   }
   tc_fence_before();
@@ -564,6 +574,8 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     for (int64_t item = first; item < p.items; item += stride) {
       const ConvItem it = conv_item(p, item * 2);
       const int chb = it.b * p.c_out + og * 2 * ocnt;  // first of this warp's 16 channels
+      float rstd = 1.f, sum_a = 0.f, sum_b = 0.f;
+      if (GN == 1) rstd = __ldg(p.gn_stats + 2 * it.b + 1);
       for (int jj = 0; jj < it.count; ++jj) {
         const int h = it.r0 + (it.j0 + jj) * p.d;
         mbar_wait(&tfull[a], aph);
@@ -622,13 +634,22 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&xbar[og * 2 + (int)par]);
           float bias_r[ocnt], acc[ocnt], s0[ocnt], s2[ocnt];
-          ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4), bias_r);
-          ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4) + 16, bias_r + 4);
+          if (GN == 1) {  // per-sample constants: 8 consecutive floats of bias_b[b], the same address in every lane
+            const float4 b0 = __ldg((const float4*)(p.bias_b + (size_t)it.b * p.c_out + cg * ocnt));
+            const float4 b1 = __ldg((const float4*)(p.bias_b + (size_t)it.b * p.c_out + cg * ocnt) + 1);
+            bias_r[0] = b0.x; bias_r[1] = b0.y; bias_r[2] = b0.z; bias_r[3] = b0.w;
+            bias_r[4] = b1.x; bias_r[5] = b1.y; bias_r[6] = b1.z; bias_r[7] = b1.w;
+          } else {
+            ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4), bias_r);
+            ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4) + 16, bias_r + 4);
+          }
 #pragma unroll
           for (int jx = 0; jx < ocnt; ++jx) {
             s0[jx] = __shfl_sync(0xffffffffu, v0[jx], l0);
             s2[jx] = __shfl_sync(0xffffffffu, v2[jx], l2);
-            acc[jx] = v1[jx] + bias_r[jx];
+            if (GN == 1) acc[jx] = fmaf(v1[jx], rstd, bias_r[jx]);
+            else if (GN == 2) acc[jx] = v1[jx];
+            else acc[jx] = v1[jx] + bias_r[jx];
             if (p.has_residual) acc[jx] += res[jx];
           }
           mbar_wait(&xbar[og * 2 + (int)par], (xph >> par) & 1u);
@@ -649,19 +670,46 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           if (!dbuf) named_bar_sync(1 + og, 128);
 #pragma unroll
           for (int jx = 0; jx < ocnt; ++jx) {
-            float r = acc[jx] + (in0 ? s0[jx] : f0[jx]) + (in2 ? s2[jx] : f2[jx]);
+            float r;
+            if (GN == 1) r = fmaf((in0 ? s0[jx] : f0[jx]) + (in2 ? s2[jx] : f2[jx]), rstd, acc[jx]);
+            else r = acc[jx] + (in0 ? s0[jx] : f0[jx]) + (in2 ? s2[jx] : f2[jx]);
             if (ACT == PDEQX_ACT_RELU) r = fmaxf(r, 0.f);
             else if (ACT == PDEQX_ACT_GELU_TANH) r = gelu_tanh(r);
+            if (GN == 2) {  // v stays fp32 (an elementwise pass reads it); msk = the norm's input h, bias_r = gamma
+              const float t = bias_r[jx] * r;
+              sum_a += t;
+              sum_b = fmaf(t, msk[jx], sum_b);
+              p.y[off0 + (int64_t)jx * plane] = r;
+              continue;
+            }
             if (p.mask && msk[jx] <= 0.f) r = 0.f;
 #if defined(PDEQX_CONV_DIAG) && PDEQX_CONV_DIAG == 3  // timing experiment: full epilogue arithmetic, no stores
             if (r == 123.456f) p.y[off0] = r;
 #else
-            p.y[off0 + (int64_t)jx * plane] = round_tf32(r);  // (read next by a tcgen05 stage: round, do not let it truncate)
+            r = round_tf32(r);  // (read next by a tcgen05 stage: round, do not let it truncate)
+            p.y[off0 + (int64_t)jx * plane] = r;
 #endif
+            if (GN == 1) {
+              sum_a += r;
+              sum_b = fmaf(r, r, sum_b);
+            }
           }
           par ^= 1;
         }
         if (++a == kAcc2) { a = 0; aph ^= 1; }
+      }
+      if (GN != 0 && p.parts) {  // this warp's partial sums of the item (one sample): a slot of its own, reduced later
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          sum_a += __shfl_xor_sync(0xffffffffu, sum_a, off);
+          sum_b += __shfl_xor_sync(0xffffffffu, sum_b, off);
+        }
+        if (lane == 0) {
+          const int64_t local = item - (int64_t)it.b * (p.d * p.segs_per_image);
+          float* dst = p.parts + (((int64_t)it.b * p.slots) + local * 16 + wid) * 2;
+          dst[0] = sum_a;
+          dst[1] = sum_b;
+        }
       }
     }
   }
@@ -676,8 +724,9 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
 // weights -> [half][th][n = tw * NOH + o_local][i], tf32-rounded. flip: data-gradient weights
 // W'[i_as_out][o_as_in][th][tw] = W[o][i][k-1-th][k-1-tw]
+// in_scale [c_in] (may be NULL): gamma of a GroupNorm in front of the convolution, folded into the filter (forward only)
 __global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int c_out, int c_in, int k,
-                                         int flip) {
+                                         int flip, const float* __restrict__ in_scale) {
   // (c_out, c_in) are the channel counts of THIS call (after the swap for the data gradient)
   const int NOH = c_out / 2;
   const int total = c_out * c_in * k * k;
@@ -694,8 +743,43 @@ __global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __r
     float v;
     if (!flip) v = w[((o * c_in + i) * k + th) * k + tw];
     else v = w[((i * c_out + o) * k + (k - 1 - th)) * k + (k - 1 - tw)];  // stored [c_in_call = orig out][c_out_call = orig in]
+    if (in_scale) v *= __ldg(in_scale + i);
     out[idx] = round_tf32(v);
   }
+}
+
+// GroupNorm (groups = 1) in front of a periodic convolution, folded: conv(gamma_c (x - mu_b) rstd_b + beta_c) =
+//   rstd_b conv(x; W gamma) + [ bias_o + sum_{c,t} W[o,c,t] beta_c - mu_b rstd_b sum_{c,t} W[o,c,t] gamma_c ]
+// (every tap of a periodic -- or mirrored -- halo reads a real, normalised pixel, so the shift's contribution is a constant
+// per sample and output channel). out[b][o] = the bracket. One block per o.
+__global__ void __launch_bounds__(128)
+conv_gn_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ stats, float* __restrict__ out, int c_out,
+                    int c_in, int taps, int batch) {
+  __shared__ float red_a[4], red_b[4];
+  const int o = blockIdx.x;
+  float sb = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < c_in * taps; i += blockDim.x) {
+    const int c = i / taps;
+    const float wv = __ldg(w + (size_t)o * c_in * taps + i);
+    sb = fmaf(wv, beta ? __ldg(beta + c) : 0.f, sb);
+    sg += round_tf32(wv * (gamma ? __ldg(gamma + c) : 1.f));  // the filter as the tensor core reads it: the mean cancels exactly
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    sg += __shfl_xor_sync(0xffffffffu, sg, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_a[threadIdx.x >> 5] = sb;
+    red_b[threadIdx.x >> 5] = sg;
+  }
+  __syncthreads();
+  sb = (red_a[0] + red_a[1]) + (red_a[2] + red_a[3]);
+  sg = (red_b[0] + red_b[1]) + (red_b[2] + red_b[3]);
+  const float b0 = (bias ? __ldg(bias + o) : 0.f) + sb;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x)
+    out[(size_t)b * c_out + o] = b0 - __ldg(stats + 2 * b) * __ldg(stats + 2 * b + 1) * sg;
 }
 
 // ==========================================================================================
@@ -717,6 +801,11 @@ struct WgParams {
   int64_t items;  // batch * d * segs_per_chain
   float* scratch;  // [grid][3 tw][3 th][c i][c o]
   float* bias_part;  // [grid][c o] per-CTA sums of gy (TMEM-operand kernel; nullptr: no bias gradient wanted)
+  // GroupNorm (groups = 1) in front of the convolution folded in: x is the norm's INPUT h, the gradient is taken against
+  // gamma_c (h - mu_b) rstd_b + beta_c without that tensor existing -- the A operand is scaled by rstd_b on its way into
+  // tensor memory, the rest is a rank-one correction in the reduce kernel (needs sum gy and sum mu_b rstd_b gy per o)
+  const float* gn_stats;  // [B][2] mean, rstd (nullptr: plain filter gradient)
+  float* m_part;          // [grid][c o] per-CTA sums of mu_b * (rstd_b gy as the tensor core reads it: tf32-rounded)
 };
 
 constexpr int kWgRing = 4;   // x rows resident (3 in use + 1 in flight)
@@ -1288,10 +1377,12 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
     const int off = tap == 0 ? dm : ((4 - dm) & 3);
     uint32_t rpf = 0, eph = 0;
     int rb = 0;
-    float bsum = 0.f;
+    float bsum = 0.f, msum = 0.f;
     if (r < 2 || q < 2) {
       for (int64_t item = first; item < p.items; item += stride) {
         const WgItem it = wg_item(p, item);
+        float rstd = 1.f;  // GroupNorm fold: the sample's 1/sigma
+        if (p.gn_stats) rstd = __ldg(p.gn_stats + 2 * it.b + 1);
         for (int jj = 0; jj < it.count; ++jj) {
           mbar_wait(&rawfull[rb], (rpf >> rb) & 1u);
           rpf ^= 1u << rb;
@@ -1334,6 +1425,10 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
                   in[i] = a;
                 }
               }
+              if (p.gn_stats) {  // rounded, not left to the tensor core's truncation: exactly the values the centre warps sum
+#pragma unroll
+                for (int i = 0; i < 32; ++i) in[i] = round_tf32(in[i] * rstd);
+              }
               mbar_wait(&aempty[r], (eph & 1u) ^ 1u);  // the MMAs on this stage's previous chunk have completed
               eph ^= 1u;
               tc_fence_after();
@@ -1354,7 +1449,18 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
               float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int i = 0; i < 32; ++i) s4[i & 3] += in[i];
-              bsum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              const float rowsum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              bsum += rowsum;
+              if (p.gn_stats) {
+                // M must cancel the mean part of what the tensor core accumulates EXACTLY: sum the operand values themselves
+                float r4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  in[i] = round_tf32(in[i] * rstd);
+                  r4[i & 3] += in[i];
+                }
+                msum = fmaf(__ldg(p.gn_stats + 2 * it.b), (r4[0] + r4[1]) + (r4[2] + r4[3]), msum);
+              }
               mbar_wait(&aempty[2 + st], ((eph >> st) & 1u) ^ 1u);
               eph ^= 1u << st;
               tc_fence_after();
@@ -1372,6 +1478,7 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
       }
     }
     if (r == 2 && q < 2 && p.bias_part) p.bias_part[(size_t)blockIdx.x * C + o] = bsum;
+    if (r == 2 && q < 2 && p.m_part) p.m_part[(size_t)blockIdx.x * C + o] = msum;
     if (r == 0) {
       // ===================== flush: TMEM -> scratch[cta][tw][th][i][o] =====================
       mbar_wait(done, 0);
@@ -1406,10 +1513,30 @@ conv_wgrad_tmem_kernel(const __grid_constant__ CUtensorMap tm_gy, const __grid_c
 
 // gw[o][i][th][tw] = sum_cta scratch[cta][tw][th][i][o]   (+ what the edge kernel adds afterwards);
 // gb[o] = sum_cta bias_part[cta][o] when the filter-gradient kernel summed gy on the way (bias_part != nullptr)
+// GroupNorm fold (m_part != nullptr; C = 64, blockDim = 256 so that a block covers all o for four i):
+//   gw[o][i][t] = gamma_i acc + beta_i G[o] - gamma_i M[o],  G[o] = sum gy (the bias gradient), M[o] = sum mu_b rstd_b gy
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ gw, int nslabs, int C,
-                                         const float* __restrict__ bias_part, float* __restrict__ gb) {
+                                         const float* __restrict__ bias_part, float* __restrict__ gb,
+                                         const float* __restrict__ m_part, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [tw][th][i][o]
   const int total = 9 * C * C;
+  __shared__ float gm_s[2][64];
+  if (m_part) {  // (block-uniform) every block sums G and M itself: nslabs coalesced 256-byte rows each
+    if (threadIdx.x < 128) {
+      const int o = threadIdx.x & 63;
+      const float* src = (threadIdx.x < 64 ? bias_part : m_part) + o;
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+      int s = 0;
+      for (; s + 4 <= nslabs; s += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part[j] += __ldg(src + (size_t)(s + j) * C);
+      }
+      for (; s < nslabs; ++s) part[0] += __ldg(src + (size_t)s * C);
+      gm_s[threadIdx.x >> 6][o] = (part[0] + part[1]) + (part[2] + part[3]);
+    }
+    __syncthreads();
+  }
   if (idx >= total) {
     if (bias_part && idx < total + C) {
       const int o = idx - total;
@@ -1433,7 +1560,12 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ scratch, floa
   const int i = r % C;
   r /= C;
   const int th = r % 3, tw = r / 3;
-  gw[((o * C + i) * 3 + th) * 3 + tw] = acc;
+  float v = acc;
+  if (m_part) {
+    const float ga = gamma ? __ldg(gamma + i) : 1.f, be = beta ? __ldg(beta + i) : 0.f;
+    v = ga * (acc - gm_s[1][o]) + be * gm_s[0][o];
+  }
+  gw[((o * C + i) * 3 + th) * 3 + tw] = v;
 }
 
 // gb[o] = sum_{b,h,w} gy[b,o,h,w]: one block per (b, o) plane chunk, atomics on C addresses
@@ -1494,11 +1626,13 @@ constexpr size_t kWprepFloats = 64 * 64 * 9;
 constexpr size_t kWgSlabs = 160;  // one partial filter gradient [3 tw][3 th][64 i][64 o] per CTA of the filter-gradient kernel
 size_t tc_conv_workspace_bytes(const ConvGeom& g) {
   if (!tc_conv_available(g)) return 0;
-  return sizeof(float) * (kWprepFloats + kWgSlabs * (9 * 64 * 64 + 64)) + 256;
+  return sizeof(float) * (kWprepFloats + kWgSlabs * (9 * 64 * 64 + 2 * 64) + (size_t)g.batch * 64) + 256;
 }
 static float* ws_wprep(void* ws) { return (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255); }
 static float* ws_wgrad(void* ws) { return ws_wprep(ws) + kWprepFloats; }
 static float* ws_bias_part(void* ws) { return ws_wgrad(ws) + kWgSlabs * 9 * 64 * 64; }  // [slab][64] per-CTA sums of gy
+static float* ws_m_part(void* ws) { return ws_bias_part(ws) + kWgSlabs * 64; }  // [slab][64] per-CTA sums of mu_b rstd_b gy (GroupNorm fold)
+static float* ws_bias_b(void* ws) { return ws_m_part(ws) + kWgSlabs * 64; }     // [batch][64] per-sample epilogue constants (GroupNorm fold)
 
 bool tc_conv_available(const ConvGeom& g) {
   if (!g_fast_paths.load(std::memory_order_relaxed)) return false;
@@ -1521,9 +1655,38 @@ static int check_conv_ws(const ConvGeom& g, void* ws, size_t ws_bytes) {
   return PDEQX_OK;
 }
 
+// GroupNorm fold of the pair kernel (mode 1: forward, mode 2: data gradient; see conv_rows_pair_kernel)
+struct GnFold {
+  int mode = 0;
+  const float* stats = nullptr;  // [B][2] mean, rstd of the norm's input
+  const float* gamma = nullptr;  // [C] (NULL: ones)
+  const float* beta = nullptr;   // [C] (NULL: zeros)
+  const float* h = nullptr;      // mode 2: the norm's input
+  float* parts = nullptr;        // partial sums out, [B][slots][2]
+};
+
+// The CTA-pair kernel's work split: chains of equal length cut into equal segments (both CTAs of a pair issue the same
+// schedule) and an even number of items. Returns the segment length (0: the shape does not take the pair kernel).
+static int conv_pair_segment(const ConvGeom& g, int c_in, int c_out, int sms) {
+  const int H = g.spatial[0], d = g.dilation[0];
+  if (!(c_in == 64 && c_out == 64 && H % d == 0 && sms >= 2)) return 0;
+  const int chain = H / d, pairs = sms / 2;
+  int best_seg = 0;
+  int64_t best_cost = 0;
+  for (int seg = 4; seg <= 64 && seg <= chain; ++seg) {
+    if (chain % seg) continue;
+    const int64_t items2 = (int64_t)g.batch * d * (chain / seg);
+    if (items2 & 1) continue;
+    const int64_t rounds = ceil_div(items2 / 2, (int64_t)pairs);
+    const int64_t cost = rounds * (seg + 2);  // rows a CTA walks, the two halo rows of every segment included
+    if (!best_seg || cost < best_cost) { best_seg = seg; best_cost = cost; }
+  }
+  return best_seg;
+}
+
 static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, bool flip, const float* bias,
                             const float* residual, int act, float* y, void* ws, size_t ws_bytes, cudaStream_t s,
-                            const float* mask = nullptr) {
+                            const float* mask = nullptr, const GnFold* gn = nullptr) {
   int dev = 0, sms = 148;
   PDEQX_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1535,8 +1698,14 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   PDEQX_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && (!residual || ((uintptr_t)residual & 15) == 0),
                   "tc_conv: tensors must be 16-byte aligned");
   const int total_w = c_out * c_in * k * k;
-  tc::conv_prep_weights_kernel<<<(total_w + 255) / 256, 256, 0, s>>>(w, wprep, c_out, c_in, k, flip ? 1 : 0);
+  const int gn_mode = gn ? gn->mode : 0;
+  tc::conv_prep_weights_kernel<<<(total_w + 255) / 256, 256, 0, s>>>(w, wprep, c_out, c_in, k, flip ? 1 : 0,
+                                                                     gn_mode == 1 ? gn->gamma : nullptr);
   PDEQX_LAUNCHED();
+  if (gn_mode == 1) {
+    tc::conv_gn_bias_kernel<<<c_out, 128, 0, s>>>(w, bias, gn->gamma, gn->beta, gn->stats, ws_bias_b(ws), c_out, c_in, k * k, g.batch);
+    PDEQX_LAUNCHED();
+  }
   const int H = g.spatial[0], W = g.spatial[1];
   CUtensorMap tm_x, tm_w, tm_y, tm_res;
   {
@@ -1574,6 +1743,16 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   cp.y = y;
   cp.res = residual;
   cp.mask = mask;
+  if (gn_mode == 1) {
+    cp.gn_stats = gn->stats;
+    cp.bias_b = ws_bias_b(ws);
+    cp.has_bias = 0;
+  } else if (gn_mode == 2) {
+    cp.bias = gn->gamma;  // bias_s carries gamma (ones when the norm has no affine part: has_bias = 0 would zero it)
+    cp.has_bias = gn->gamma ? 1 : 0;
+    cp.mask = gn->h;
+  }
+  if (gn_mode) cp.parts = gn->parts;
   cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image * 2;
   tc::ConvSmem L = tc::conv_smem(c_in, c_out, k);
   PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv: shared memory budget exceeded (%u bytes)", L.total);
@@ -1581,22 +1760,14 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
   // (both CTAs of a pair issue the same schedule) and an even number of items
   static const bool pair_enabled = [] { const char* e = getenv("PDEQX_CONV_PAIR"); return !(e && e[0] == '0'); }();
   const tc::ConvParams cp_one_cta = cp;
-  if (pair_enabled && !(g_pair_unavailable.load(std::memory_order_relaxed) & dev_bit) && c_in == 64 && c_out == 64 && H % cp.d == 0 && sms >= 2) {
-    const int chain = H / cp.d, pairs = sms / 2;
-    int best_seg = 0;
-    int64_t best_cost = 0;
-    for (int seg = 4; seg <= 64 && seg <= chain; ++seg) {
-      if (chain % seg) continue;
-      const int64_t items2 = (int64_t)g.batch * cp.d * (chain / seg);
-      if (items2 & 1) continue;
-      const int64_t rounds = ceil_div(items2 / 2, (int64_t)pairs);
-      const int64_t cost = rounds * (seg + 2);  // rows a CTA walks, the two halo rows of every segment included
-      if (!best_seg || cost < best_cost) { best_seg = seg; best_cost = cost; }
-    }
+  if ((pair_enabled || gn_mode) && !(g_pair_unavailable.load(std::memory_order_relaxed) & dev_bit)) {
+    const int chain = H / cp.d;
+    const int best_seg = conv_pair_segment(g, c_in, c_out, sms);
     if (best_seg) {
       cp.seg = best_seg;
       cp.segs_per_image = chain / best_seg;
       cp.items = (int64_t)g.batch * cp.d * cp.segs_per_image;
+      cp.slots = cp.d * cp.segs_per_image * 16;
       int grid2 = (int)(cp.items < sms ? cp.items : sms) & ~1;
       {  // an error pending from an earlier asynchronous failure must not be read as "cluster launch rejected" below
         const cudaError_t stale = cudaPeekAtLastError();
@@ -1605,18 +1776,22 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
           return PDEQX_ERR_CUDA;
         }
       }
-#define PDEQX_CONV_PAIR_LAUNCH(A)                                                                                         \
+#define PDEQX_CONV_PAIR_LAUNCH(A, G)                                                                                      \
   do {                                                                                                                    \
-    static DeviceOnce attr;                                                                                                   \
-    if (attr.first_use()) {                                                                                                          \
-      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_rows_pair_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-                                                                                                                          \
+    static DeviceOnce attr;                                                                                               \
+    if (attr.first_use()) {                                                                                               \
+      PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_rows_pair_kernel<A, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
     }                                                                                                                     \
-    tc::conv_rows_pair_kernel<A><<<grid2, tc::kConvThreads, L.total, s>>>(tm_x, tm_w, tm_y, tm_res, cp, L);               \
+    tc::conv_rows_pair_kernel<A, G><<<grid2, tc::kConvThreads, L.total, s>>>(tm_x, tm_w, tm_y, tm_res, cp, L);            \
   } while (0)
-      if (act == PDEQX_ACT_RELU) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_RELU);
-      else if (act == PDEQX_ACT_GELU_TANH) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_GELU_TANH);
-      else PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_IDENTITY);
+      if (gn_mode == 2) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_IDENTITY, 2);
+      else if (gn_mode == 1) {
+        if (act == PDEQX_ACT_RELU) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_RELU, 1);
+        else if (act == PDEQX_ACT_GELU_TANH) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_GELU_TANH, 1);
+        else PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_IDENTITY, 1);
+      } else if (act == PDEQX_ACT_RELU) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_RELU, 0);
+      else if (act == PDEQX_ACT_GELU_TANH) PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_GELU_TANH, 0);
+      else PDEQX_CONV_PAIR_LAUNCH(PDEQX_ACT_IDENTITY, 0);
 #undef PDEQX_CONV_PAIR_LAUNCH
       // A device that cannot co-schedule the two-CTA cluster with 227 KB each (a partitioned GPU, an odd SM count) rejects
       // the launch synchronously: remember that and take the one-CTA kernel from now on instead of failing the call.
@@ -1629,6 +1804,10 @@ static int conv_rows_launch(const ConvGeom& g, const float* x, const float* w, b
       g_pair_unavailable.fetch_or(dev_bit, std::memory_order_relaxed);
       cp = cp_one_cta;
     }
+  }
+  if (gn_mode) {
+    set_error("the GroupNorm fold needs the CTA-pair convolution kernel, which this shape / device does not take (pdeqx_conv_gn_fusable)");
+    return PDEQX_ERR_UNSUPPORTED;
   }
   int grid = (int)(cp.items < sms ? cp.items : sms);
   grid &= ~1;  // even: a CTA keeps one channel half (its weights stay resident)
@@ -1677,8 +1856,8 @@ bool tc_conv_bwd_filter_available(const ConvGeom& g) { return tc_conv_available(
 // gw, gb zeroed by the caller (conv.cu). The column-shifted operands (halo folded in) are built in shared memory by the
 // kernel itself: x and gy are read once. Every CTA flushes its partial sum to a slab of the workspace; a second kernel
 // reduces the slabs (deterministic, no atomics on the filter gradient).
-int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws, size_t ws_bytes,
-                       cudaStream_t s) {
+static int conv_bwd_filter_launch(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws,
+                                  size_t ws_bytes, cudaStream_t s, const GnFold* gn) {
   TimedScope timed(PDEQX_K_CONV_BWD_FILTER, s);
   int dev = 0, sms = 148;
   PDEQX_CUDA(cudaGetDevice(&dev));
@@ -1725,7 +1904,11 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
     static const bool ring5 = [] { const char* e = getenv("PDEQX_WG_RING5"); return e && e[0] == '1'; }();
     tc::WgtSmem L = ring5 ? tc::wgt_smem(C, 5, 2) : tc::wgt_smem(C, 4, 3);
     PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
-    wp.bias_part = gb ? ws_bias_part(ws) : nullptr;
+    wp.bias_part = (gb || gn) ? ws_bias_part(ws) : nullptr;
+    if (gn) {
+      wp.gn_stats = gn->stats;
+      wp.m_part = ws_m_part(ws);
+    }
     static DeviceOnce attr;
     if (attr.first_use()) {
       PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_tmem_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1734,9 +1917,14 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
     if (ring5) tc::conv_wgrad_tmem_kernel<5, 2><<<grid, tc::kWgtThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
     else tc::conv_wgrad_tmem_kernel<4, 3><<<grid, tc::kWgtThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
     PDEQX_LAUNCHED();
-    tc::conv_wgrad_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, wp.bias_part, gb);
+    tc::conv_wgrad_reduce_kernel<<<(9 * C * C + C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, gb ? wp.bias_part : nullptr, gb,
+                                                                             wp.m_part, gn ? gn->gamma : nullptr, gn ? gn->beta : nullptr);
     PDEQX_LAUNCHED();
     return PDEQX_OK;
+  }
+  if (gn) {
+    set_error("the GroupNorm fold needs the tensor-memory filter-gradient kernel (PDEQX_WG_TMEM=0 is set)");
+    return PDEQX_ERR_UNSUPPORTED;
   }
   tc::WgsSmem L = tc::wgs_smem(C);
   PDEQX_CHECK_ARG(L.total <= 227 * 1024, "tc_conv_bwd_filter: shared memory budget exceeded (%u bytes)", L.total);
@@ -1745,7 +1933,7 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
     PDEQX_CUDA(cudaFuncSetAttribute(tc::conv_wgrad_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   tc::conv_wgrad_shift_kernel<<<grid, tc::kWgsThreads, L.total, s>>>(tm_gy, tm_x, wp, L);
   PDEQX_LAUNCHED();
-  tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, nullptr, nullptr);
+  tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, nullptr, nullptr, nullptr, nullptr, nullptr);
   PDEQX_LAUNCHED();
   if (gb) {
     PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)C, s));
@@ -1753,6 +1941,61 @@ int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float
     PDEQX_LAUNCHED();
   }
   return PDEQX_OK;
+}
+
+int tc_conv_bwd_filter(const ConvGeom& g, const float* x, const float* gy, float* gw, float* gb, void* ws, size_t ws_bytes,
+                       cudaStream_t s) {
+  return conv_bwd_filter_launch(g, x, gy, gw, gb, ws, ws_bytes, s, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm (groups = 1) -> PhysicsConv -> activation with the norm folded into the convolution's three passes
+// (pdequinox/blocks/_dilated_res_block.py:141-151). The normalised tensor is never written or read.
+// ------------------------------------------------------------------------------------------
+static int device_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+bool tc_conv_gn_fusable(const ConvGeom& g) {
+  if (!tc_conv_available(g) || !tc_conv_bwd_filter_available(g)) return false;
+  if (g.boundary != PDEQX_PAD_WRAP) return false;  // the norm's shift is a per-sample constant only if every tap reads a real pixel
+  static const bool tmem_a = [] { const char* e = getenv("PDEQX_WG_TMEM"); return !(e && e[0] == '0'); }();
+  if (!tmem_a) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (g_pair_unavailable.load(std::memory_order_relaxed) & (1ull << (dev & 63))) return false;
+  return conv_pair_segment(g, g.c_in, g.c_out, device_sms()) != 0;
+}
+
+int tc_conv_gn_slots(const ConvGeom& g) {
+  const int seg = conv_pair_segment(g, g.c_in, g.c_out, device_sms());
+  if (!seg) return 0;
+  return g.dilation[0] * (g.spatial[0] / g.dilation[0] / seg) * 16;
+}
+
+int tc_conv_gn_fwd(const ConvGeom& g, const float* x, const float* w, const float* b, const float* stats, const float* gamma,
+                   const float* beta, int act, float* y, float* out_parts, void* ws, size_t ws_bytes, cudaStream_t s) {
+  TimedScope timed(PDEQX_K_CONV_FWD, s);
+  GnFold gn;
+  gn.mode = 1; gn.stats = stats; gn.gamma = gamma; gn.beta = beta; gn.parts = out_parts;
+  return conv_rows_launch(g, x, w, false, b, nullptr, act, y, ws, ws_bytes, s, nullptr, &gn);
+}
+
+int tc_conv_gn_bwd_filter(const ConvGeom& g, const float* x, const float* gy, const float* stats, const float* gamma,
+                          const float* beta, float* gw, float* gb, void* ws, size_t ws_bytes, cudaStream_t s) {
+  GnFold gn;
+  gn.mode = 1; gn.stats = stats; gn.gamma = gamma; gn.beta = beta;
+  return conv_bwd_filter_launch(g, x, gy, gw, gb, ws, ws_bytes, s, &gn);
+}
+
+int tc_conv_gn_bwd_data(const ConvGeom& g, const float* gy, const float* w, const float* gamma, const float* h, float* v,
+                        float* parts, void* ws, size_t ws_bytes, cudaStream_t s) {
+  TimedScope timed(PDEQX_K_CONV_BWD_DATA, s);
+  GnFold gn;
+  gn.mode = 2; gn.gamma = gamma; gn.h = h; gn.parts = parts;
+  return conv_rows_launch(g, gy, w, true, nullptr, nullptr, PDEQX_ACT_IDENTITY, v, ws, ws_bytes, s, nullptr, &gn);
 }
 
 }  // namespace pdeqx

@@ -75,6 +75,22 @@ def activation_bwd(pre, gy, act, tape, owner, tag):
     return gx
 
 
+ADD_PARTS_SLOTS = 64
+
+
+def add_parts(a, b, tape, owner, tag):
+    """a + b with per-sample partial sums (sum, sum of squares) of the result: (out, parts, slots) or (out, None, 0) when the
+    per-sample size does not split evenly."""
+    per_sample = a[0].numel()
+    if per_sample % (4 * ADD_PARTS_SLOTS) != 0:
+        return add(a, b, tape, owner, tag), None, 0
+    out = new_buf(tape, owner, tag, a.shape)
+    parts = new_buf(tape, owner, tag + "_parts", (a.shape[0] * ADD_PARTS_SLOTS * 2,))
+    _lib.check(_lib.lib().pdeqx_add_parts(a.shape[0], per_sample, ADD_PARTS_SLOTS, _lib.ptr(a), _lib.ptr(b), _lib.ptr(out),
+                                          _lib.ptr(parts), _lib.stream()))
+    return out, parts, ADD_PARTS_SLOTS
+
+
 def add(a, b, tape, owner, tag):
     out = new_buf(tape, owner, tag, a.shape)
     _lib.check(_lib.lib().pdeqx_add(a.numel(), _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), _lib.stream()))
@@ -107,6 +123,37 @@ class GroupNorm(Module):
         if tape is not None:
             tape.push((x, stats))
         return y
+
+    # ---- the pieces left of a norm that is folded into the convolution behind it (groups = 1; pdeqx_conv_gn_*) ----
+    def stats_of(self, x, tape, tag="stats"):
+        """(mean, rstd) per sample and group in a pass of its own -- for an input whose producer did not sum it."""
+        B, Cc = x.shape[:2]
+        stats = new_buf(tape, self, tag, (B * self.groups * 2,))
+        ws = new_buf(tape, self, "ws", (B * Cc * 4,))
+        _lib.check(_lib.lib().pdeqx_groupnorm_stats(B, Cc, self.groups, x[0, 0].numel(), _lib.ptr(x), self.eps,
+                                                    _lib.ptr(stats), _lib.ptr(ws), _lib.stream()))
+        return stats
+
+    def stats_from_parts(self, parts, slots, batch, count, tape, tag="stats"):
+        """(mean, rstd) per sample from the partial sums (x, x^2) its producer wrote in its epilogue."""
+        stats = new_buf(tape, self, tag, (batch * 2,))
+        _lib.check(_lib.lib().pdeqx_groupnorm_stats_from_parts(batch, slots, count, _lib.ptr(parts), self.eps,
+                                                               _lib.ptr(stats), _lib.stream()))
+        return stats
+
+    def bwd_fused(self, h, v, stats, parts, slots, tape, *, mask_h=False, add=None):
+        """Input gradient of the folded norm from v = cotangent of norm(h) (+ relu' of the layer whose output h is, + the
+        cotangent `add` of a residual connection joining here) and the norm's parameter gradients, in one pass."""
+        B, Cc = h.shape[:2]
+        gx = new_buf(tape, self, "gx", h.shape)
+        scratch = new_buf(tape, self, "scr", (B * Cc * 2,))
+        gw = self.grad("weight") if self.weight is not None else None
+        gb = self.grad("bias") if self.bias is not None else None
+        _lib.check(_lib.lib().pdeqx_groupnorm_bwd_fused(B, Cc, h[0, 0].numel(), _lib.ptr(h), _lib.ptr(v), _lib.ptr(self.weight),
+                                                        _lib.ptr(stats), _lib.ptr(parts), slots, 1 if mask_h else 0,
+                                                        _lib.ptr(add), _lib.ptr(gx), _lib.ptr(gw), _lib.ptr(gb),
+                                                        _lib.ptr(scratch), _lib.stream()))
+        return gx
 
     def _bwd(self, gy, tape, need_gx=True, relu_mask=None):
         """relu_mask: the input gradient is zeroed where it is <= 0 (relu' of the layer whose output this norm read)."""

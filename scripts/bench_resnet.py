@@ -11,15 +11,18 @@ prec = os.environ.get("PREC", "tf32")
 B = int(os.environ.get("B", "128"))
 pdeqx.set_precision(prec)
 out = {}
+want = os.environ.get("MODELS", "ClassicResNet,DilatedResNet").split(",")
+n_warm, n = int(os.environ.get("WARM", "3")), int(os.environ.get("N", "5"))
 for name, ctor in [("ClassicResNet", lambda: pdeqx.ClassicResNet(2, 1, 1, hidden_channels=64, boundary_mode="periodic", key=0)),
                    ("DilatedResNet", lambda: pdeqx.DilatedResNet(2, 1, 1, hidden_channels=64, boundary_mode="periodic", key=0))]:
+    if name not in want:
+        continue
     model = ctor()
     step = TrainStep(model)
     x = torch.randn(B, 1, 128, 128, device="cuda"); y = torch.randn(B, 1, 128, 128, device="cuda")
-    for _ in range(3): step(x, y)
+    for _ in range(n_warm): step(x, y)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 5
     l0 = _lib.lib().pdeqx_launch_count()
     e0.record()
     for _ in range(n): step(x, y)
