@@ -570,14 +570,32 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const uint32_t xo_b = dbuf ? (kMaxDil / 2) * (ocnt * 4) : 0u;  // byte offset of the second exchange buffer half
     const uint32_t xo0_b = use0 ? xo_b : 0u, xo2_b = use2 ? xo_b : 0u;  // (the zero slot has no second half)
     const uint32_t bias_sa = smem_u32(bias_s);
+    const uint32_t bias_w = smem_u32(smem + L.tile_off) + (uint32_t)wid * 64;  // GN 1: this warp's per-sample constants
     uint32_t xph = 0;
     for (int64_t item = first; item < p.items; item += stride) {
       const ConvItem it = conv_item(p, item * 2);
       const int chb = it.b * p.c_out + og * 2 * ocnt;  // first of this warp's 16 channels
       float rstd = 1.f, sum_a = 0.f, sum_b = 0.f;
-      if (GN == 1) rstd = __ldg(p.gn_stats + 2 * it.b + 1);
+      if (GN == 1) {
+        // the sample's epilogue constants of this warp's 16 channels: fetched once per item into the warp's own 64 bytes of
+        // the (otherwise unused) output-tile region, read per pass like the shared bias of the plain kernel
+        rstd = __ldg(p.gn_stats + 2 * it.b + 1);
+        __syncwarp();
+        if (lane < 2 * ocnt) st_shared_f32(bias_w + (uint32_t)lane * 4, __ldg(p.bias_b + (size_t)it.b * p.c_out + og * 2 * ocnt + lane));
+        __syncwarp();
+      }
       for (int jj = 0; jj < it.count; ++jj) {
         const int h = it.r0 + (it.j0 + jj) * p.d;
+        // GN 2: the norm's input at this lane's 16 output elements is requested BEFORE the wait for the accumulator, so the
+        // global-load latency overlaps the unit's MMAs instead of sitting on the epilogue's chain of two passes
+        float pre_m[2][ocnt];
+        if (GN == 2) {
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps)
+#pragma unroll
+            for (int jx = 0; jx < ocnt; ++jx)
+              pre_m[ps][jx] = __ldg(p.mask + (((int64_t)chb + ps * ocnt + jx) * p.H + h) * p.W + wq);
+        }
         mbar_wait(&tfull[a], aph);
         tc_fence_after();
 #pragma unroll
@@ -592,7 +610,10 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
             for (int jx = 0; jx < ocnt; ++jx) res[jx] = __ldg(p.res + off0 + (int64_t)jx * plane);
           }
-          if (p.mask) {
+          if (GN == 2) {
+#pragma unroll
+            for (int jx = 0; jx < ocnt; ++jx) msk[jx] = pre_m[ps][jx];
+          } else if (p.mask) {
 #pragma unroll
             for (int jx = 0; jx < ocnt; ++jx) msk[jx] = __ldg(p.mask + off0 + (int64_t)jx * plane);
           }
@@ -634,11 +655,9 @@ conv_rows_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&xbar[og * 2 + (int)par]);
           float bias_r[ocnt], acc[ocnt], s0[ocnt], s2[ocnt];
-          if (GN == 1) {  // per-sample constants: 8 consecutive floats of bias_b[b], the same address in every lane
-            const float4 b0 = __ldg((const float4*)(p.bias_b + (size_t)it.b * p.c_out + cg * ocnt));
-            const float4 b1 = __ldg((const float4*)(p.bias_b + (size_t)it.b * p.c_out + cg * ocnt) + 1);
-            bias_r[0] = b0.x; bias_r[1] = b0.y; bias_r[2] = b0.z; bias_r[3] = b0.w;
-            bias_r[4] = b1.x; bias_r[5] = b1.y; bias_r[6] = b1.z; bias_r[7] = b1.w;
+          if (GN == 1) {
+            ld_shared_v4(bias_w + (uint32_t)ps * (ocnt * 4), bias_r);
+            ld_shared_v4(bias_w + (uint32_t)ps * (ocnt * 4) + 16, bias_r + 4);
           } else {
             ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4), bias_r);
             ld_shared_const_v4(bias_sa + (uint32_t)cg * (ocnt * 4) + 16, bias_r + 4);

@@ -458,6 +458,82 @@ extern "C" XLA_FFI_Error* pdeqx_ffi_groupnorm_bwd(XLA_FFI_CallFrame* call_frame)
 }
 
 // ==========================================================================================
+// GroupNorm (groups = 1) -> PhysicsConv -> activation as ONE op, the norm folded into the convolution's passes
+// (pdequinox/blocks/_dilated_res_block.py:141-151; accepted shapes: pdeqx_conv_gn_fusable)
+//   fwd operands: x [B,C,*S], gn_weight [C] or (0,), gn_bias [C] or (0,), w [Co,C,*k], b [Co,1..] or (0,),
+//                 in_parts [B,slots_in,2] or (0,): per-sample sums (x, x^2) its producer wrote (absent: a statistics pass)
+//       attrs   : the conv's + activation, eps
+//       results : y, stats [B,2] (saved), out_parts [B, pdeqx_conv_gn_slots, 2] (sums of y, y^2 for the next norm),
+//                 workspace (max of pdeqx_conv_workspace_bytes and pdeqx_groupnorm_workspace_bytes)
+//   bwd operands: x, stats, gn_weight or (0,), gn_bias or (0,), w, ga [B,Co,*S] (cotangent of the PRE-activation),
+//                 add [B,C,*S] or (0,)                                   attrs: the conv's + relu_mask_x (0 / 1)
+//       results : gx, g_gn_weight or (0,), g_gn_bias or (0,), gw, gb or (0,), v [B,C,*S] (scratch: cotangent of the
+//                 normalised tensor), parts [B, pdeqx_conv_gn_slots, 2], scratch [2*B*C], workspace
+// ==========================================================================================
+extern "C" XLA_FFI_Error* pdeqx_ffi_norm_conv_fwd(XLA_FFI_CallFrame* call_frame) {
+  PDEQX_FFI_PROLOGUE("pdeqx_norm_conv_fwd", 6, 4);
+  PDEQX_FFI_NUMBER(activation, "activation", "pdeqx_norm_conv_fwd");
+  PDEQX_FFI_NUMBER(eps, "eps", "pdeqx_norm_conv_fwd");
+  pdeqx_conv_desc d;
+  const XLA_FFI_Buffer* x = fr.arg(0);
+  if (!conv_desc(fr, x, fr.arg(3), &d))
+    return fr.fail(XLA_FFI_Error_Code_INVALID_ARGUMENT, "%s: bad operand ranks or missing static attributes", "pdeqx_norm_conv_fwd");
+  const int slots = pdeqx_conv_gn_slots(&d);
+  if (slots == 0)
+    return fr.fail(XLA_FFI_Error_Code_UNIMPLEMENTED, "%s: this convolution does not take the folded GroupNorm passes (pdeqx_conv_gn_fusable)", "pdeqx_norm_conv_fwd");
+  if (Frame::count(fr.ret(1)) < 2 * x->dims[0] || Frame::count(fr.ret(2)) < 2 * (int64_t)slots * x->dims[0])
+    return fr.fail(XLA_FFI_Error_Code_RESOURCE_EXHAUSTED, "%s: stats / out_parts results are too small", "pdeqx_norm_conv_fwd");
+  size_t need = pdeqx_conv_workspace_bytes(&d);
+  const size_t gn_ws = pdeqx_groupnorm_workspace_bytes(d.batch, d.c_in);
+  if (gn_ws > need) need = gn_ws;
+  if (fr.out_bytes(3) < need)
+    return fr.fail(XLA_FFI_Error_Code_RESOURCE_EXHAUSTED, "%s: workspace result is too small", "pdeqx_norm_conv_fwd");
+  if (!execute) return nullptr;
+  const XLA_FFI_Buffer* in_parts = fr.arg(5);
+  if (Frame::count(in_parts) == 0) {
+    if ((err = fr.status(pdeqx_groupnorm_stats(d.batch, d.c_in, 1, pixels(x), fr.in(0), (float)eps, fr.out(1), fr.out(3), stream),
+                         "pdeqx_groupnorm_stats")))
+      return err;
+  } else {
+    if (in_parts->rank != 3 || in_parts->dims[0] != x->dims[0] || in_parts->dims[2] != 2)
+      return fr.fail(XLA_FFI_Error_Code_INVALID_ARGUMENT, "%s: in_parts must be [B, slots, 2]", "pdeqx_norm_conv_fwd");
+    if ((err = fr.status(pdeqx_groupnorm_stats_from_parts(d.batch, (int32_t)in_parts->dims[1], (int64_t)d.c_in * pixels(x), fr.in(5),
+                                                          (float)eps, fr.out(1), stream),
+                         "pdeqx_groupnorm_stats_from_parts")))
+      return err;
+  }
+  return fr.status(pdeqx_conv_gn_fwd(&d, fr.in(0), fr.in(3), fr.opt(4), fr.out(1), fr.opt(1), fr.opt(2), (int32_t)activation, fr.out(0),
+                                     fr.out(2), fr.out(3), fr.out_bytes(3), stream),
+                   "pdeqx_conv_gn_fwd");
+}
+
+extern "C" XLA_FFI_Error* pdeqx_ffi_norm_conv_bwd(XLA_FFI_CallFrame* call_frame) {
+  PDEQX_FFI_PROLOGUE("pdeqx_norm_conv_bwd", 7, 9);
+  PDEQX_FFI_NUMBER(relu_mask_x, "relu_mask_x", "pdeqx_norm_conv_bwd");
+  pdeqx_conv_desc d;
+  const XLA_FFI_Buffer* x = fr.arg(0);
+  if (!conv_desc(fr, x, fr.arg(4), &d))
+    return fr.fail(XLA_FFI_Error_Code_INVALID_ARGUMENT, "%s: bad operand ranks or missing static attributes", "pdeqx_norm_conv_bwd");
+  const int slots = pdeqx_conv_gn_slots(&d);
+  if (slots == 0)
+    return fr.fail(XLA_FFI_Error_Code_UNIMPLEMENTED, "%s: this convolution does not take the folded GroupNorm passes (pdeqx_conv_gn_fusable)", "pdeqx_norm_conv_bwd");
+  if (Frame::count(fr.ret(5)) < Frame::count(x) || Frame::count(fr.ret(6)) < 2 * (int64_t)slots * x->dims[0] ||
+      Frame::count(fr.ret(7)) < 2 * x->dims[0] * x->dims[1] || fr.out_bytes(8) < pdeqx_conv_workspace_bytes(&d))
+    return fr.fail(XLA_FFI_Error_Code_RESOURCE_EXHAUSTED, "%s: a scratch result (v, parts, scratch, workspace) is too small", "pdeqx_norm_conv_bwd");
+  if (!execute) return nullptr;
+  if ((err = fr.status(pdeqx_conv_gn_bwd_filter(&d, fr.in(0), fr.in(5), fr.in(1), fr.opt(2), fr.opt(3), fr.out(3), fr.opt_out(4), fr.out(8),
+                                                fr.out_bytes(8), stream),
+                       "pdeqx_conv_gn_bwd_filter")))
+    return err;
+  if ((err = fr.status(pdeqx_conv_gn_bwd_data(&d, fr.in(5), fr.in(4), fr.opt(2), fr.in(0), fr.out(5), fr.out(6), fr.out(8), fr.out_bytes(8), stream),
+                       "pdeqx_conv_gn_bwd_data")))
+    return err;
+  return fr.status(pdeqx_groupnorm_bwd_fused(d.batch, d.c_in, pixels(x), fr.in(0), fr.out(5), fr.opt(2), fr.in(1), fr.out(6), slots,
+                                             relu_mask_x != 0 ? 1 : 0, fr.opt(6), fr.out(0), fr.opt_out(1), fr.opt_out(2), fr.out(7), stream),
+                   "pdeqx_groupnorm_bwd_fused");
+}
+
+// ==========================================================================================
 // Adam (optax.adam + eqx.apply_updates on one flat leaf), IN PLACE:
 //   operands: param, grad, mu, nu, state [4] (state[0] = update count, int32 bit pattern, starts at 0)
 //   attrs   : lr, b1, b2, eps, grad_scale (1 / number of data-parallel ranks)
@@ -486,7 +562,8 @@ extern "C" const char* const* pdeqx_ffi_handler_names(int* count) {
   static const char* const names[] = {"pdeqx_ffi_spectral_block_fwd", "pdeqx_ffi_spectral_block_bwd", "pdeqx_ffi_conv_fwd",
                                       "pdeqx_ffi_conv_bwd",           "pdeqx_ffi_convT_fwd",          "pdeqx_ffi_convT_bwd",
                                       "pdeqx_ffi_pointwise_fwd",      "pdeqx_ffi_pointwise_bwd",      "pdeqx_ffi_groupnorm_fwd",
-                                      "pdeqx_ffi_groupnorm_bwd",      "pdeqx_ffi_adam"};
+                                      "pdeqx_ffi_groupnorm_bwd",      "pdeqx_ffi_adam",               "pdeqx_ffi_norm_conv_fwd",
+                                      "pdeqx_ffi_norm_conv_bwd"};
   if (count) *count = (int)(sizeof(names) / sizeof(names[0]));
   return names;
 }

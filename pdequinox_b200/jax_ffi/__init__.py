@@ -24,6 +24,6 @@ except ImportError as exc:  # pragma: no cover - exercised only where JAX is abs
         "pdequinox_b200 itself have no such dependency") from exc
 
 from ._ffi import register, set_precision, get_precision  # noqa: E402,F401
-from ._ops import physics_conv, pointwise_conv, spectral_block  # noqa: E402,F401
+from ._ops import norm_conv_act, physics_conv, pointwise_conv, spectral_block  # noqa: E402,F401
 from ._modules import ClassicSpectralBlock, PhysicsConv, PointwiseLinearConv, SpectralConv, convert  # noqa: E402,F401
 from ._train import data_parallel_step  # noqa: E402,F401

@@ -23,6 +23,7 @@ from typing import NamedTuple
 
 import jax
 import jax.numpy as jnp
+import numpy as np
 from jax.custom_batching import custom_vmap
 
 from . import _ffi
@@ -233,6 +234,113 @@ def physics_conv(x, weight, bias, *, stride, dilation, padding, padding_mode, gr
     cfg = ConvCfg(tuple(stride), tuple(dilation), tuple(p[0] for p in padding), tuple(p[1] for p in padding),
                   _ffi.BOUNDARY[padding_mode], int(groups), _ffi.get_precision())
     return _physics_conv(x, weight, _opt(bias), cfg)
+
+
+# ------------------------------------------------------------------------------------------
+# GroupNorm(1, C) -> PhysicsConv -> activation as one op   (pdequinox/blocks/_dilated_res_block.py:141-151)
+#   the norm is folded into the convolution's passes (pdeqx_conv_gn_*): the normalised tensor never exists. Accepted shapes:
+#   pdeqx_conv_gn_fusable (periodic, the tcgen05 CTA-pair shapes, TF32 precision); callers fall back to
+#   group_norm + physics_conv elsewhere (`norm_conv_act_fusable`).
+# ------------------------------------------------------------------------------------------
+def norm_conv_act_fusable(batch, c_in, c_out, spatial, kernel, cfg):
+    return bool(_ffi._core.lib().pdeqx_conv_gn_fusable(_ffi.conv_desc(batch, c_in, c_out, spatial, kernel, cfg)))
+
+
+def _norm_conv_sizes(x, w, cfg):
+    B, ci, *S = x.shape
+    d = _ffi.conv_desc(B, ci, w.shape[0], S, w.shape[2:], cfg)
+    L = _ffi._core.lib()
+    slots = L.pdeqx_conv_gn_slots(d)
+    if slots == 0:
+        raise NotImplementedError("norm_conv_act: this convolution does not take the folded GroupNorm passes "
+                                  "(pdeqx_conv_gn_fusable): use group_norm + physics_conv")
+    nws = max(L.pdeqx_conv_workspace_bytes(d), L.pdeqx_groupnorm_workspace_bytes(B, ci)) // 4 + 1
+    return slots, nws
+
+
+def _norm_conv_fwd_batched(x, gn_w, gn_b, w, b, cfg, activation, eps):
+    _ffi.register()
+    B = x.shape[0]
+    slots, nws = _norm_conv_sizes(x, w, cfg)
+    y, stats, _, _ = jax.ffi.ffi_call("pdeqx_norm_conv_fwd", (_sds((B, w.shape[0], *x.shape[2:])), _sds((B, 2)), _sds((B, slots, 2)),
+                                                              _sds((nws,))))(
+        x, gn_w, gn_b, w, b, _absent(), eps=np.float32(eps), **_conv_attrs(cfg, activation))
+    return y, stats
+
+
+def _norm_conv_bwd_batched(x, stats, gn_w, gn_b, w, b, ga, cfg):
+    _ffi.register()
+    B, ci = x.shape[:2]
+    slots, nws = _norm_conv_sizes(x, w, cfg)
+    gx, ggw, ggb, gw, gb, *_ = jax.ffi.ffi_call(
+        "pdeqx_norm_conv_bwd", (_sds(x.shape), _sds(gn_w.shape), _sds(gn_b.shape), _sds(w.shape), _sds(b.shape), _sds(x.shape),
+                                _sds((B, slots, 2)), _sds((2 * B * ci,)), _sds((nws,))))(
+        x, stats, gn_w, gn_b, w, ga, _absent(), relu_mask_x=_ffi.i32(0), **_conv_attrs(cfg))
+    return gx, ggw, ggb, gw, gb
+
+
+@functools.lru_cache(maxsize=None)
+def _norm_conv_fwd_call(cfg, activation, eps):
+    @custom_vmap
+    def call(x, gn_w, gn_b, w, b):
+        y, stats = _norm_conv_fwd_batched(x[None], gn_w, gn_b, w, b, cfg, activation, eps)
+        return y[0], stats[0]
+
+    @call.def_vmap
+    def rule(axis_size, in_batched, x, gn_w, gn_b, w, b):
+        _require_params_unbatched(in_batched, 1, "norm_conv_act")
+        return _norm_conv_fwd_batched(_lead(x, in_batched[0], axis_size), gn_w, gn_b, w, b, cfg, activation, eps), (True, True)
+
+    return call
+
+
+@functools.lru_cache(maxsize=None)
+def _norm_conv_bwd_call(cfg):
+    @custom_vmap
+    def call(x, stats, ga, gn_w, gn_b, w, b):
+        gx, *gp = _norm_conv_bwd_batched(x[None], stats[None], gn_w, gn_b, w, b, ga[None], cfg)
+        return (gx[0], *gp)
+
+    @call.def_vmap
+    def rule(axis_size, in_batched, x, stats, ga, gn_w, gn_b, w, b):
+        _require_params_unbatched(in_batched, 3, "norm_conv_act (reverse pass)")
+        out = _norm_conv_bwd_batched(_lead(x, in_batched[0], axis_size), _lead(stats, in_batched[1], axis_size), gn_w, gn_b, w, b,
+                                     _lead(ga, in_batched[2], axis_size), cfg)
+        return out, (True, False, False, False, False)
+
+    return call
+
+
+@functools.partial(jax.custom_vjp, nondiff_argnums=(5, 6, 7))
+def _norm_conv_act(x, gn_w, gn_b, w, b, cfg, activation, eps):
+    return _norm_conv_fwd_call(cfg, activation, eps)(x, gn_w, gn_b, w, b)[0]
+
+
+def _norm_conv_act_fwd(x, gn_w, gn_b, w, b, cfg, activation, eps):
+    y, stats = _norm_conv_fwd_call(cfg, activation, eps)(x, gn_w, gn_b, w, b)
+    return y, (x, stats, y, gn_w, gn_b, w, b)
+
+
+def _norm_conv_act_bwd(cfg, activation, eps, res, gy):
+    x, stats, y, gn_w, gn_b, w, b = res
+    ga = jnp.where(y > 0, gy, 0) if activation == _ffi.ACT["relu"] else gy  # cotangent of the pre-activation
+    return _norm_conv_bwd_call(cfg)(x, stats, ga, gn_w, gn_b, w, b)
+
+
+_norm_conv_act.defvjp(_norm_conv_act_fwd, _norm_conv_act_bwd)
+
+
+def norm_conv_act(x, norm_weight, norm_bias, weight, bias, *, stride, dilation, padding, padding_mode, activation="relu",
+                  eps=1e-5):
+    """activation(corr(pad(group_norm_1(x)), weight) + bias) for ONE sample x: (C, *S) -- the layer of DilatedResBlock
+    (norm -> conv -> act) as one custom call each way. activation: relu or identity (the reverse pass needs act' from the
+    output alone). In this functional binding every layer takes its statistics in a pass of its own; the torch host side
+    (pdequinox_b200/blocks/_dilated_res_block.py) additionally chains the producer's partial sums from layer to layer."""
+    if activation not in ("relu", "identity"):
+        raise NotImplementedError("norm_conv_act: relu or identity")
+    cfg = ConvCfg(tuple(stride), tuple(dilation), tuple(p[0] for p in padding), tuple(p[1] for p in padding),
+                  _ffi.BOUNDARY[padding_mode], 1, _ffi.get_precision())
+    return _norm_conv_act(x, norm_weight, norm_bias, weight, _opt(bias), cfg, _ffi.ACT[activation], float(eps))
 
 
 # ------------------------------------------------------------------------------------------

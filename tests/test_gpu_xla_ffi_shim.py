@@ -184,3 +184,57 @@ def test_convT_pointwise_groupnorm_adam_handlers(ffi):
         ref_p, st = onn.adam_step(ref_p, {"w": g}, st)
     torch.cuda.synchronize()
     assert rel_l2(host(P), ref_p["w"]) <= 1e-6
+
+
+@pytest.mark.parametrize("with_parts", [False, True])
+def test_folded_norm_conv_handlers(ffi, with_parts):
+    """pdeqx_ffi_norm_conv_fwd / _bwd: GroupNorm(1, C) -> periodic PhysicsConv -> relu as one op (the layer of
+    pdequinox/blocks/_dilated_res_block.py:141-151), statistics from a pass of their own or from the producer's partial sums."""
+    lib, h, call = ffi
+    rng = np.random.default_rng(9)
+    Bn, C_, H, W, dil = 2, 64, 16, 128, 2
+    x = (0.5 + 1.5 * rng.standard_normal((Bn, C_, H, W))).astype(np.float32).astype(np.float64)
+    gamma, beta = 1 + 0.3 * rng.standard_normal(C_), 0.3 * rng.standard_normal(C_)
+    w = rng.standard_normal((C_, C_, 3, 3)) / np.sqrt(9 * C_)
+    b = rng.standard_normal((C_, 1, 1))
+    attrs = {"activation": 1, "eps": 1e-5, "groups": 1, "boundary": 1, "precision": 1, "stride": [1, 1], "dilation": [dil, dil],
+             "pad_lo": [dil, dil], "pad_hi": [dil, dil]}
+    d = _lib.ConvDesc()
+    d.ndim, d.batch, d.c_in, d.c_out, d.groups = 2, Bn, C_, C_, 1
+    d.spatial, d.kernel = _lib.ivec((H, W), 1), _lib.ivec((3, 3), 1)
+    d.stride, d.dilation = _lib.ivec((1, 1), 1), _lib.ivec((dil, dil), 1)
+    d.pad_lo, d.pad_hi = _lib.ivec((dil, dil), 0), _lib.ivec((dil, dil), 0)
+    d.boundary, d.precision = 1, 1
+    L = _lib.lib()
+    assert L.pdeqx_conv_gn_fusable(d) == 1
+    slots = L.pdeqx_conv_gn_slots(d)
+    nws = max(L.pdeqx_conv_workspace_bytes(d), L.pdeqx_groupnorm_workspace_bytes(Bn, C_))
+    X, G_, Be, Wd, Bd = dev(x), dev(gamma), dev(beta), dev(w), dev(b)
+    y, stats = torch.empty_like(X), torch.empty(Bn, 2, device="cuda")
+    parts, ws = torch.empty(Bn, slots, 2, device="cuda"), torch.empty(nws // 4 + 1, device="cuda")
+    in_parts = None
+    if with_parts:  # what a producing layer's epilogue would have written: here 4 slots per sample
+        xs = x.reshape(Bn, 4, -1)
+        in_parts = dev(np.stack([xs.sum(-1), (xs ** 2).sum(-1)], axis=-1))
+    call(h["pdeqx_ffi_norm_conv_fwd"], [B(X), B(G_), B(Be), B(Wd), B(Bd), B(in_parts)], [B(y), B(stats), B(parts), B(ws)], attrs)
+    torch.cuda.synchronize()
+    hn = onn.group_norm(host(X).astype(np.float64), host(G_), host(Be), 1, 2)
+    ref = np.maximum(oconv.physics_conv(hn, host(Wd), host(Bd), boundary_mode="periodic", dilation=dil), 0)
+    assert rel_l2(host(y), ref) <= 2e-3
+    p = host(parts).astype(np.float64).sum(1)
+    np.testing.assert_allclose(p[:, 0], host(y).astype(np.float64).reshape(Bn, -1).sum(1), rtol=1e-4)
+    # reverse pass: cotangent of the pre-activation in, everything else out
+    ga = rng.standard_normal(ref.shape) * (host(y) > 0)
+    ghn, gw_r, gb_r = oconv.physics_conv_vjp(hn, host(Wd).astype(np.float64), ga, boundary_mode="periodic", dilation=dil)
+    gx_r, gg_r, gbe_r = onn.group_norm_vjp(host(X).astype(np.float64), host(G_).astype(np.float64), 1, 2, ghn)
+    add = rng.standard_normal(x.shape)
+    gx, gg, gbe, gw, gb = torch.empty_like(X), torch.empty_like(G_), torch.empty_like(Be), torch.empty_like(Wd), torch.empty_like(Bd)
+    v, bparts, scr = torch.empty_like(X), torch.empty(Bn, slots, 2, device="cuda"), torch.empty(2 * Bn * C_, device="cuda")
+    battrs = dict(attrs, relu_mask_x=1)
+    GA, ADD = dev(ga), dev(add)  # (kept alive: a call frame holds raw device pointers)
+    call(h["pdeqx_ffi_norm_conv_bwd"], [B(X), B(stats), B(G_), B(Be), B(Wd), B(GA), B(ADD)],
+         [B(gx), B(gg), B(gbe), B(gw), B(gb), B(v), B(bparts), B(scr), B(ws)], battrs)
+    torch.cuda.synchronize()
+    assert rel_l2(host(gx), gx_r * (host(X) > 0) + add) <= 2e-3
+    assert rel_l2(host(gw), gw_r) <= 2e-3 and rel_l2(host(gb).ravel(), gb_r.ravel()) <= 2e-3
+    assert rel_l2(host(gg), gg_r) <= 2e-3 and rel_l2(host(gbe), gbe_r) <= 2e-3

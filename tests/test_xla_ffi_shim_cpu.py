@@ -10,7 +10,8 @@ import xla_ffi_frame as xf
 
 EXPECTED = ["pdeqx_ffi_spectral_block_fwd", "pdeqx_ffi_spectral_block_bwd", "pdeqx_ffi_conv_fwd", "pdeqx_ffi_conv_bwd",
             "pdeqx_ffi_convT_fwd", "pdeqx_ffi_convT_bwd", "pdeqx_ffi_pointwise_fwd", "pdeqx_ffi_pointwise_bwd",
-            "pdeqx_ffi_groupnorm_fwd", "pdeqx_ffi_groupnorm_bwd", "pdeqx_ffi_adam"]
+            "pdeqx_ffi_groupnorm_fwd", "pdeqx_ffi_groupnorm_bwd", "pdeqx_ffi_adam", "pdeqx_ffi_norm_conv_fwd",
+            "pdeqx_ffi_norm_conv_bwd"]
 
 
 @pytest.fixture(scope="module")
