@@ -533,7 +533,26 @@ def run_ours(args):
                    "tflops": tflops, "tensor_peak_tflops": tf32_peak, "tensor_frac": tflops / tf32_peak,
                    "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (derived: tf32 runs at half the bf16 rate)" if peaks else "fallback",
                    "tcgen05_passes": int(L.pdeqx_conv_tcgen05_passes(desc))}
-        del xc, yc
+        # the two reverse passes of the same layer (same algorithmic bytes: two activation-sized tensors each; same flops)
+        gxc = torch.empty_like(xc)
+        gwc, gbc = torch.empty_like(conv.weight), torch.empty_like(conv.bias)
+
+        def conv_bwd_data():
+            _lib.check(L.pdeqx_conv_bwd_data(desc, _lib.ptr(yc), _lib.ptr(conv.weight), None, None, _lib.ptr(gxc), _lib.ptr(ws), nws,
+                                             _lib.stream()))
+
+        def conv_bwd_filter():
+            _lib.check(L.pdeqx_conv_bwd_filter(desc, _lib.ptr(xc), _lib.ptr(yc), _lib.ptr(gwc), _lib.ptr(gbc), _lib.ptr(ws), nws,
+                                               _lib.stream()))
+        for name, fn in (("bwd_data", conv_bwd_data), ("bwd_filter", conv_bwd_filter)):
+            for _ in range(3):
+                fn()
+            ms_r = timed(fn, 50) / 50
+            physics[name] = {"avg_us": ms_r * 1e3, "frac": conv_bytes / (ms_r * 1e-3) / 1e9 / hbm_peak,
+                             "tensor_frac": 2 * 64 * 64 * 9 * 128 * 128 * 128 / (ms_r * 1e-3) / 1e12 / tf32_peak}
+        physics["bwd_filter"]["note"] = ("filter + bias gradient: tcgen05 with the column-shifted cotangent operand in tensor memory, "
+                                         "partial sums of every CTA reduced by a second kernel (inside the bracket)")
+        del xc, yc, gxc
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
