@@ -12,7 +12,7 @@ import sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "pdequinox_b200/libpdeqx_b200.so"
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(["cu++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
-PAT = [("UTCHMMA", r"\bUTCHMMA"), ("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCQMMA/UTCOMMA", r"\bUTC[QO]MMA"), ("LDTM", r"\bLDTM"),
+PAT = [("UTCHMMA", r"\bUTCHMMA"), ("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCQMMA/UTCOMMA", r"\bUTC[QO]MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"),
        ("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"), ("UTCBAR", r"\bUTCBAR"), ("SYNCS", r"\bSYNCS"), ("FFMA", r"\bFFMA\b"),
        ("FFMA2/FMUL2/FADD2", r"\bF(FMA|MUL|ADD)2\b"),
        ("HMMA/IMMA (legacy mma.sync)", r"\b[HI]MMA\b")]
