@@ -40,6 +40,13 @@ int mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re, c
 int mode_mix_dw(const pdeqx_spectral_plan* p, const float* ghat, const float* xhat, float* gw_re, float* gw_im,
                 cudaStream_t s);
 
+// the same two on tcgen05 (tc_modemix.cu; TF32 precision)
+bool tc_mode_gemm_available(const pdeqx_spectral_plan* p);
+int tc_mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re, const float* w_im, bool transposed_conj,
+                float* out, cudaStream_t s);
+int tc_mode_mix_dw(const pdeqx_spectral_plan* p, const float* ghat, const float* xhat, float* gw_re, float* gw_im,
+                   cudaStream_t s);
+
 // tcgen05 stages
 int tc_plan_init(pdeqx_spectral_plan* p);
 void tc_plan_free(pdeqx_spectral_plan* p);
