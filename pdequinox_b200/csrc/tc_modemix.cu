@@ -72,7 +72,7 @@ struct MxRegs {
 };
 
 template <int NT, int NS, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
-__global__ void __launch_bounds__(MX_PROD + 32, NT == 32 ? 2 : 1)
+__global__ void __launch_bounds__(MX_PROD + 32, 1)
 mode_gemm_tc_kernel(MixArgs t) {
   constexpr uint32_t TILE_B = mx_tile_b<NT>();
   constexpr uint32_t STAGE = mx_stage_bytes<NT>();
@@ -80,6 +80,7 @@ mode_gemm_tc_kernel(MixArgs t) {
   constexpr int TCOLS = MX_PT * NT;               // 256 or 512 accumulator columns
   constexpr int NBP = NT * MX_KC * 2 / MX_PROD;   // planar B: 16-byte loads per thread and plane
   constexpr int NBI = NT * MX_KC * 4 / MX_PROD;   // interleaved B: 16-byte loads per thread
+  constexpr int P = NS;                           // chunks per load group (one register set and one operand stage each)
   extern __shared__ __align__(128) uint8_t mx_smem[];
   __shared__ uint64_t full[NS], empty[NS], done;
   __shared__ uint32_t tmem_slot;
@@ -108,7 +109,7 @@ mode_gemm_tc_kernel(MixArgs t) {
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
-      mbar_init(&full[i], MX_PROD);
+      mbar_init(&full[i], MX_PROD / 32);
       mbar_init(&empty[i], 1);
     }
     mbar_init(&done, 1);
@@ -163,6 +164,7 @@ mode_gemm_tc_kernel(MixArgs t) {
       for (int it = 0; it < 4; ++it) {
         const int idx = it * MX_PROD + tid;
         const int j = idx & 3, k = (idx >> 2) & 3, m = mx_row(idx >> 4);
+        if (m0 + m >= t.M) continue;  // D row r depends on A' row r only, and rows past M are never read back
         // rows 2m (re) and 2m + 1 (im) of the A' tiles of modes 2j and 2j + 1
         const uint32_t o = sa + (uint32_t)(2 * j) * MX_TILE_A + (uint32_t)(m >> 2) * MX_SBO + (uint32_t)((2 * m) & 7) * 16 + (uint32_t)k * 4;
         const float re0 = round_tf32(r.a[it].x), im0 = round_tf32(r.a[it].y);
@@ -181,6 +183,7 @@ mode_gemm_tc_kernel(MixArgs t) {
         for (int it = 0; it < NBP; ++it) {
           const int idx = it * MX_PROD + tid;
           const int h = idx & 1, k = (idx >> 1) & 3, n = idx >> 3;
+          if (n0 + n >= t.N) continue;  // (likewise D column n and B' row n)
           const uint32_t o = sb + (uint32_t)(4 * h) * TILE_B + (uint32_t)(n >> 3) * MX_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)k * 4;
           const float4 vr = r.b[2 * it], vi = r.b[2 * it + 1];
           st_shared_f32(o, round_tf32(vr.x));
@@ -197,6 +200,7 @@ mode_gemm_tc_kernel(MixArgs t) {
         for (int it = 0; it < NBI; ++it) {
           const int idx = it * MX_PROD + tid;
           const int j = idx & 3, k = (idx >> 2) & 3, n = idx >> 4;
+          if (n0 + n >= t.N) continue;
           const uint32_t o = sb + (uint32_t)(2 * j) * TILE_B + (uint32_t)(n >> 3) * MX_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)k * 4;
           st_shared_f32(o, round_tf32(r.b[it].x));
           st_shared_f32(o + MX_LBO, round_tf32(r.b[it].y));
@@ -205,18 +209,21 @@ mode_gemm_tc_kernel(MixArgs t) {
         }
       }
       fence_proxy_async();  // the tensor core reads what this thread wrote through the async proxy
-      mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);  // one arrive per warp: 256 arrives per chunk serialise on the barrier word
     };
-    // two register sets: the loads of chunk c + 1 are in flight while chunk c is transposed into shared memory
-    MxRegs r0, r1;
-    load(0, r0);
-    for (int c = 0; c < nch; c += 2) {
-      if (c + 1 < nch) load(c + 1, r1);
-      store(c, r0);
-      if (c + 1 < nch) {
-        if (c + 2 < nch) load(c + 2, r0);
-        store(c + 1, r1);
-      }
+    // Groups of P chunks: all loads of a group are issued, then its chunks are transposed one by one (one register set and one
+    // operand stage per chunk). What bounds the kernel is the L1TEX wavefront count, not bytes: a mode-contiguous operand
+    // gives a warp-wide 16-byte load only 32 - 64 useful bytes per 128-byte line (8 - 16 lines per instruction at ~2 cycles per
+    // line), the transposing stores are one wavefront each, and the output runs are 64 bytes (profiles/r2_modemix.md)
+    MxRegs r[P];
+    for (int c = 0; c < nch; c += P) {
+#pragma unroll
+      for (int u = 0; u < P; ++u)
+        if (c + u < nch) load(c + u, r[u]);
+#pragma unroll
+      for (int u = 0; u < P; ++u)
+        if (c + u < nch) store(c + u, r[u]);
     }
 
     // ===================== epilogue: TMEM -> registers -> 32-byte runs along the mode axis =====================
@@ -236,25 +243,35 @@ mode_gemm_tc_kernel(MixArgs t) {
         const int n = n0 + nb + nn;
         const bool ok = m < t.M && n < t.N;
         if (C_PLANAR) {
-          float* dst = (part ? t.ci : t.cr) + (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + woff;
-          if (ok) {
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0][nn], v[1][nn], v[2][nn], v[3][nn]);
-            if (gv1) *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4][nn], v[5][nn], v[6][nn], v[7][nn]);
+          // per store instruction a lane pair fills one whole 32-byte sector of ONE plane: the re lane writes modes 0..3 of both
+          // planes, the im lane modes 4..7; each sends the partner the four values it needs
+          float o[4], r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            o[q] = part ? v[4 + q][nn] : v[q][nn];
+            r[q] = __shfl_xor_sync(0xffffffffu, part ? v[q][nn] : v[4 + q][nn], 1);
+          }
+          const int64_t off = (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + woff + 4 * part;
+          if (ok && (part == 0 || gv1)) {
+            *reinterpret_cast<float4*>(t.cr + off) = part ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(t.ci + off) = part ? make_float4(o[0], o[1], o[2], o[3]) : make_float4(r[0], r[1], r[2], r[3]);
           }
         } else {
-          // the re lane writes modes 0..3, the im lane modes 4..7: each sends the partner the four values it needs
+          // per store instruction a lane pair fills one whole 32-byte sector: the re lane writes modes 0,1 / 4,5, the im lane
+          // modes 2,3 / 6,7; each sends the partner the four values it needs
           float x[4], y[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float send = part ? v[q][nn] : v[4 + q][nn];
+            const int qm = (q & 1) + 4 * (q >> 1);  // 0, 1, 4, 5: the re lane's modes; the im lane's are qm + 2
+            const float send = part ? v[qm][nn] : v[qm + 2][nn];
             const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            x[q] = round_tf32(part ? recv : v[q][nn]);
-            y[q] = round_tf32(part ? v[4 + q][nn] : recv);
+            x[q] = round_tf32(part ? recv : v[qm][nn]);
+            y[q] = round_tf32(part ? v[qm + 2][nn] : recv);
           }
           if (ok) {
-            float4* dst = reinterpret_cast<float4*>(t.c2 + (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + p0 + 4 * part);
+            float4* dst = reinterpret_cast<float4*>(t.c2 + (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + p0 + 2 * part);
             dst[0] = make_float4(x[0], y[0], x[1], y[1]);
-            dst[1] = make_float4(x[2], y[2], x[3], y[3]);
+            dst[2] = make_float4(x[2], y[2], x[3], y[3]);
           }
         }
       }
@@ -291,7 +308,7 @@ mode_gemm_tc_kernel(MixArgs t) {
 
 template <int NT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 static void launch_nt(const MixArgs& t, int64_t J, cudaStream_t s) {
-  constexpr int NS = NT == 32 ? 2 : 4;
+  constexpr int NS = 4;
   constexpr size_t smem = (size_t)NS * mx_stage_bytes<NT>();
   static DeviceOnce attr;
   if (attr.first_use())
@@ -303,7 +320,7 @@ static void launch_nt(const MixArgs& t, int64_t J, cudaStream_t s) {
 
 template <bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 static void launch(const MixArgs& t, int64_t J, cudaStream_t s) {
-  // 32-column tiles (two CTAs per SM) unless 64-column tiles already fill the GPU
+  // 32-column tiles unless 64-column tiles already fill the GPU
   const int64_t tiles64 = (J / MX_PT) * ceil_div(t.N, 64) * ceil_div(t.M, 64);
   if (t.N <= 32 || tiles64 < 148) launch_nt<32, B_PLANAR, C_PLANAR, CONJ_B>(t, J, s);
   else launch_nt<64, B_PLANAR, C_PLANAR, CONJ_B>(t, J, s);
@@ -319,6 +336,10 @@ bool tc_mode_gemm_available(const pdeqx_spectral_plan* p) {
   const int D = p->desc.ndim;
   int64_t mprod = 1;
   for (int a = 0; a < D; ++a) mprod *= p->desc.modes[a];
+  // measured (B200, profiles/r2_modemix.md): ahead of the CUDA-core kernel from 32 samples per GPU and 64 channels on (26 vs 45 us
+  // at B = 64, C = 64); behind it where that kernel is a pure stream over the weights (B = 8: 17 vs 13 us) and on the padded
+  // 32-channel mode space of configs[4]
+  if (p->desc.batch < 32 || p->desc.c_in < 64 || p->desc.c_out < 64) return false;
   // 8-mode tiles must not straddle a row of the data layout; 16-byte weight runs start on 4-mode boundaries
   return p->mlast % 8 == 0 && p->desc.modes[D - 1] % 4 == 0 && mprod % 4 == 0 && p->J % 8 == 0 && p->J / 8 < (1ll << 31) &&
          ceil_div(p->desc.batch, 64) <= 65535;
