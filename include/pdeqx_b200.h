@@ -129,7 +129,9 @@ size_t pdeqx_spectral_workspace_bytes(const pdeqx_spectral_plan* plan);
 size_t pdeqx_spectral_xhat_floats(const pdeqx_spectral_plan* plan);
 size_t pdeqx_spectral_z_floats(const pdeqx_spectral_plan* plan);
 /* which stages of this plan run on tcgen05 (bit 0: first-stage r2c DFT, bit 1: last-stage slab kernel,
- * bit 2: bypass weight gradient); 0 in fp32 precision or when the shape does not qualify */
+ * bit 2: bypass weight gradient, bit 3: per-mode channel mix and its two adjoints -- from 16 samples per call and
+ * 64 channels on; below that the CUDA-core kernel is the faster one); 0 in fp32 precision or when the shape does not
+ * qualify */
 int pdeqx_spectral_plan_tcgen05_stages(const pdeqx_spectral_plan* plan);
 
 /* y[B,c_out,*S] = act( irfftn(mix(rfftn(x))) + (bypass_w . x + bypass_b) )

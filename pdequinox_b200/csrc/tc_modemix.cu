@@ -5,10 +5,11 @@
 //
 // Per retained mode p the op is a small complex GEMM  C[m,n] = sum_k A(m,k) * B(n,k)^(conj)  (M, N, K = batch / channels).
 // The reference keeps the MODE index contiguous in every operand (mode space [B, C, J] complex-interleaved, weights
-// (G, o, i, *m) planar), so no operand has 16 contiguous bytes along K or M/N of a mode's matrix and TMA cannot stage them.
-// Instead a CTA owns 8 consecutive modes (32-byte runs of a weight plane, 64-byte runs of mode space) and its producer
-// warps TRANSPOSE on the way: coalesced 16-byte global loads along the mode axis -> registers -> the K-major no-swizzle
-// UMMA layout (8-row x 16-byte core matrices) of eight per-mode operand tiles in shared memory. The complex product runs
+// (G, o, i, *m) planar), so no operand has 16 contiguous bytes along K or M/N of a mode's matrix: TMA cannot deliver a UMMA
+// tile. A CTA owns 8 consecutive modes (32-byte runs of a weight plane, 64-byte runs of mode space); one thread streams RAW
+// chunks of 4 K indices with TMA (boxes with the mode axis innermost, zero-filled past the batch / channel counts, 3 - 5
+// chunks in flight), and 16 warps TRANSPOSE them: 16-byte shared loads -> registers -> scalar stores into the K-major
+// no-swizzle UMMA layout (8-row x 16-byte core matrices) of eight per-mode operand tiles. The complex product runs
 // as ONE real MMA per mode and K step with the parts stacked along M and K:
 //   A' row 2m   = [ Re A(m, k..k+3) | s1 Im A(m, k..k+3) ]      B' row n = [ Re B(n, k..k+3) | Im B(n, k..k+3) ]
 //   A' row 2m+1 = [ Im A(m, k..k+3) | s2 Re A(m, k..k+3) ]      (s1, s2) = (-1, +1), conj(B): (+1, -1)
@@ -37,12 +38,14 @@ struct MixArgs {
   int64_t c_sm, c_sn;
   int M, N, K;
   int64_t w_corner;  // O * I * mprod: weight floats per corner
+  uint32_t a_rm, a_rk, b_rn, b_rk;  // byte strides of (row, k) inside a raw chunk (set by the launcher)
+  int a_k_inner, b_k_inner;         // k is the faster of the two box dimensions
   ModeMap mm;
 };
 
 constexpr int MX_PT = 8;        // modes per CTA
 constexpr int MX_KC = 4;        // complex K per chunk = 8 real K = one MMA per mode
-constexpr int MX_PROD = 256;    // producer threads (8 warps; they also run the epilogue)
+constexpr int MX_PROD = 512;    // transposer threads (16 warps; they also run the epilogue)
 constexpr uint32_t MX_LBO = 128;           // bytes between the two core matrices of one K step
 constexpr uint32_t MX_SBO = 2 * 128 + 16;  // bytes between 8-row groups (+16: row groups 4 banks apart)
 constexpr uint32_t MX_TILE_A = 16 * MX_SBO + 16;  // one mode's A' tile (128 rows), +16: tiles 4 banks apart
@@ -66,23 +69,34 @@ __device__ __forceinline__ uint64_t smem_desc_none(uint32_t smem_addr, uint32_t 
 // the next mode pair's tile already sits)
 __device__ __forceinline__ int mx_row(int mi) { return ((mi & 1) << 2) + ((mi >> 1) & 3) + ((mi >> 3) << 3); }
 
-struct MxRegs {
-  float4 a[4];   // A: 4 x (2 modes complex)
-  float4 b[4];   // B planar: [re, im] x up to 2; B interleaved: up to 4
-};
+// round-to-nearest for a value the tensor core will TRUNCATE to tf32: add half a tf32 ulp (one integer add; the low 13 bits
+// that remain are ignored by the MMA). Finite inputs only.
+__device__ __forceinline__ float mx_round(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
 
-template <int NT, int NS, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
-__global__ void __launch_bounds__(MX_PROD + 32, 1)
-mode_gemm_tc_kernel(MixArgs t) {
+// the same with the low bits cleared: for values that go back to global memory (any consumer may read them)
+__device__ __forceinline__ float mx_round_store(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+
+// raw operand chunk as TMA leaves it: A 64 rows x 4 k x 64 B (8 modes complex), B NT rows x 4 k x 64 B (interleaved) or two
+// planes of NT x 4 x 32 B (planar); which of (row, k) is the faster box dimension depends on the operand (byte strides
+// a_rm / a_rk / b_rn / b_rk in MixArgs)
+constexpr uint32_t MX_RAW_A = 64 * MX_KC * 64;
+template <int NT>
+__host__ __device__ constexpr uint32_t mx_raw_bytes() { return MX_RAW_A + NT * MX_KC * 64; }
+
+template <int NT, int NS, int R, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
+__global__ void __launch_bounds__(MX_PROD + 64, 1)
+mode_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b0,
+                    const __grid_constant__ CUtensorMap tm_b1, MixArgs t) {
   constexpr uint32_t TILE_B = mx_tile_b<NT>();
   constexpr uint32_t STAGE = mx_stage_bytes<NT>();
   constexpr uint32_t B_OFF = MX_PT * MX_TILE_A;  // B' tiles follow the A' tiles inside a stage
+  constexpr uint32_t RAW = mx_raw_bytes<NT>();
+  constexpr uint32_t RAW_OFF = NS * STAGE;        // raw chunks follow the operand stages
   constexpr int TCOLS = MX_PT * NT;               // 256 or 512 accumulator columns
-  constexpr int NBP = NT * MX_KC * 2 / MX_PROD;   // planar B: 16-byte loads per thread and plane
-  constexpr int NBI = NT * MX_KC * 4 / MX_PROD;   // interleaved B: 16-byte loads per thread
-  constexpr int P = NS;                           // chunks per load group (one register set and one operand stage each)
-  extern __shared__ __align__(128) uint8_t mx_smem[];
-  __shared__ uint64_t full[NS], empty[NS], done;
+  constexpr int NBP = (NT * MX_KC * 2 + MX_PROD - 1) / MX_PROD;  // planar B: 16-byte pieces per thread and plane
+  constexpr int NBI = NT * MX_KC * 4 / MX_PROD;   // interleaved B: 16-byte pieces per thread
+  extern __shared__ __align__(1024) uint8_t mx_smem[];
+  __shared__ uint64_t full[NS], empty[NS], rawfull[R], rawempty[R], done;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t p0 = (int64_t)blockIdx.x * MX_PT;
@@ -98,7 +112,7 @@ mode_gemm_tc_kernel(MixArgs t) {
     // padding tile: zeros out (interleaved), nothing to write (planar)
     if (!C_PLANAR) {
       const int rows = min(64, t.M - m0), cols = min(NT, t.N - n0);
-      for (int idx = tid; idx < rows * cols * 4; idx += MX_PROD + 32) {
+      for (int idx = tid; idx < rows * cols * 4; idx += MX_PROD + 64) {
         const int q = idx & 3, n = (idx >> 2) % cols, m = (idx >> 2) / cols;
         reinterpret_cast<float4*>(t.c2 + (int64_t)(m0 + m) * t.c_sm + (int64_t)(n0 + n) * t.c_sn + p0)[q] =
             make_float4(0.f, 0.f, 0.f, 0.f);
@@ -112,10 +126,19 @@ mode_gemm_tc_kernel(MixArgs t) {
       mbar_init(&full[i], MX_PROD / 32);
       mbar_init(&empty[i], 1);
     }
+    for (int i = 0; i < R; ++i) {
+      mbar_init(&rawfull[i], 1);
+      mbar_init(&rawempty[i], MX_PROD / 32);
+    }
     mbar_init(&done, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc<TCOLS>(&tmem_slot);
+  if (warp == MX_PROD / 32 + 1 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b0);
+    if (B_PLANAR) tma_prefetch_desc(&tm_b1);
+  }
+  if (warp == MX_PROD / 32) tmem_alloc<TCOLS>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,52 +146,45 @@ mode_gemm_tc_kernel(MixArgs t) {
   const int nch = (t.K + MX_KC - 1) / MX_KC;
   const uint32_t smem0 = smem_u32(mx_smem);
 
-  if (warp < 8) {
-    // ===================== producers: global (mode axis contiguous) -> registers -> UMMA K-major tiles =====================
-    auto load = [&](int c, MxRegs& r) {
-      const int k0 = c * MX_KC;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int idx = it * MX_PROD + tid;
-        const int j = idx & 3, k = (idx >> 2) & 3, m = mx_row(idx >> 4);
-        const bool ok = m0 + m < t.M && k0 + k < t.K && (j < 2 ? true : gv1);
-        r.a[it] = ok ? __ldg(reinterpret_cast<const float4*>(t.a + (int64_t)(m0 + m) * t.a_sm + (int64_t)(k0 + k) * t.a_sk + p0) + j)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (B_PLANAR) {
-#pragma unroll
-        for (int it = 0; it < NBP; ++it) {
-          const int idx = it * MX_PROD + tid;
-          const int h = idx & 1, k = (idx >> 1) & 3, n = idx >> 3;
-          const bool ok = n0 + n < t.N && k0 + k < t.K && (h == 0 || gv1);
-          const int64_t off = (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + woff + 4 * h;
-          r.b[2 * it] = ok ? __ldg(reinterpret_cast<const float4*>(t.br + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          r.b[2 * it + 1] = ok ? __ldg(reinterpret_cast<const float4*>(t.bi + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-#pragma unroll
-        for (int it = 0; it < NBI; ++it) {
-          const int idx = it * MX_PROD + tid;
-          const int j = idx & 3, k = (idx >> 2) & 3, n = idx >> 4;
-          const bool ok = n0 + n < t.N && k0 + k < t.K && (j < 2 ? true : gv1);
-          r.b[it] = ok ? __ldg(reinterpret_cast<const float4*>(t.b2 + (int64_t)(n0 + n) * t.b_sn + (int64_t)(k0 + k) * t.b_sk + p0) + j)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == MX_PROD / 32 + 1) {
+    // ===================== TMA producer: raw chunks, the mode axis innermost (32 / 64-byte box rows) =====================
+    if (lane == 0) {
+      for (int c = 0; c < nch; ++c) {
+        const int rs = c % R, k0 = c * MX_KC;
+        if (c >= R) mbar_wait_backoff(&rawempty[rs], (uint32_t)((c / R - 1) & 1));
+        uint8_t* dst = mx_smem + RAW_OFF + (size_t)rs * RAW;
+        mbar_expect_tx(&rawfull[rs], RAW);
+        if (t.a_k_inner) tma_load_3d(dst, &tm_a, &rawfull[rs], (int)(2 * p0), k0, m0);
+        else tma_load_3d(dst, &tm_a, &rawfull[rs], (int)(2 * p0), m0, k0);
+        if (B_PLANAR) {
+          const int c1 = t.b_k_inner ? k0 : n0, c2 = t.b_k_inner ? n0 : k0;
+          tma_load_4d(dst + MX_RAW_A, &tm_b0, &rawfull[rs], (int)loc0, c1, c2, g0);
+          tma_load_4d(dst + MX_RAW_A + NT * MX_KC * 32, &tm_b1, &rawfull[rs], (int)loc0, c1, c2, g0);
+        } else {
+          tma_load_3d(dst + MX_RAW_A, &tm_b0, &rawfull[rs], (int)(2 * p0), n0, k0);
         }
       }
-    };
-    auto store = [&](int c, const MxRegs& r) {
-      const int s = c % NS;
+    }
+  } else if (warp < MX_PROD / 32) {
+    // ===================== transposers: raw chunk -> UMMA K-major tiles (tf32-rounded, re / im stacked) =====================
+    for (int c = 0; c < nch; ++c) {
+      const int rs = c % R, s = c % NS;
+      mbar_wait(&rawfull[rs], (uint32_t)((c / R) & 1));
       if (c >= NS) mbar_wait(&empty[s], (uint32_t)((c / NS - 1) & 1));
+      const uint32_t ra = smem0 + RAW_OFF + (uint32_t)rs * RAW, rb = ra + MX_RAW_A;
       const uint32_t sa = smem0 + (uint32_t)s * STAGE, sb = sa + B_OFF;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < 64 * MX_KC * 4 / MX_PROD; ++it) {
         const int idx = it * MX_PROD + tid;
         const int j = idx & 3, k = (idx >> 2) & 3, m = mx_row(idx >> 4);
         if (m0 + m >= t.M) continue;  // D row r depends on A' row r only, and rows past M are never read back
+        float v[4];
+        ld_shared_v4(ra + (uint32_t)m * t.a_rm + (uint32_t)k * t.a_rk + (uint32_t)j * 16, v);
+        if (j >= 2 && !gv1) v[0] = v[1] = v[2] = v[3] = 0.f;  // padding modes: exact zeros whatever the other operand holds
         // rows 2m (re) and 2m + 1 (im) of the A' tiles of modes 2j and 2j + 1
         const uint32_t o = sa + (uint32_t)(2 * j) * MX_TILE_A + (uint32_t)(m >> 2) * MX_SBO + (uint32_t)((2 * m) & 7) * 16 + (uint32_t)k * 4;
-        const float re0 = round_tf32(r.a[it].x), im0 = round_tf32(r.a[it].y);
-        const float re1 = round_tf32(r.a[it].z), im1 = round_tf32(r.a[it].w);
+        const float re0 = mx_round(v[0]), im0 = mx_round(v[1]);
+        const float re1 = mx_round(v[2]), im1 = mx_round(v[3]);
         st_shared_f32(o, re0);
         st_shared_f32(o + MX_LBO, CONJ_B ? im0 : -im0);
         st_shared_f32(o + 16, im0);
@@ -182,18 +198,23 @@ mode_gemm_tc_kernel(MixArgs t) {
 #pragma unroll
         for (int it = 0; it < NBP; ++it) {
           const int idx = it * MX_PROD + tid;
-          const int h = idx & 1, k = (idx >> 1) & 3, n = idx >> 3;
+          if (NT * MX_KC * 2 < MX_PROD && idx >= NT * MX_KC * 2) continue;  // (NT = 32: half the threads have no piece)
+          // a quarter warp reads 128 contiguous bytes of the raw chunk whichever of (n, k) is its faster dimension; the
+          // transposing stores hit 32 distinct banks under either assignment of the lane bits
+          const int h = idx & 1;
+          const int k = t.b_k_inner ? (idx >> 1) & 3 : (idx >> 3) & 3;
+          const int n = t.b_k_inner ? idx >> 3 : ((idx >> 1) & 3) | ((idx >> 5) << 2);
           if (n0 + n >= t.N) continue;  // (likewise D column n and B' row n)
+          float vr[4], vi[4];
+          const uint32_t r = rb + (uint32_t)n * t.b_rn + (uint32_t)k * t.b_rk + (uint32_t)h * 16;
+          ld_shared_v4(r, vr);
+          ld_shared_v4(r + NT * MX_KC * 32, vi);
           const uint32_t o = sb + (uint32_t)(4 * h) * TILE_B + (uint32_t)(n >> 3) * MX_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)k * 4;
-          const float4 vr = r.b[2 * it], vi = r.b[2 * it + 1];
-          st_shared_f32(o, round_tf32(vr.x));
-          st_shared_f32(o + MX_LBO, round_tf32(vi.x));
-          st_shared_f32(o + TILE_B, round_tf32(vr.y));
-          st_shared_f32(o + TILE_B + MX_LBO, round_tf32(vi.y));
-          st_shared_f32(o + 2 * TILE_B, round_tf32(vr.z));
-          st_shared_f32(o + 2 * TILE_B + MX_LBO, round_tf32(vi.z));
-          st_shared_f32(o + 3 * TILE_B, round_tf32(vr.w));
-          st_shared_f32(o + 3 * TILE_B + MX_LBO, round_tf32(vi.w));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            st_shared_f32(o + (uint32_t)q * TILE_B, mx_round(vr[q]));
+            st_shared_f32(o + (uint32_t)q * TILE_B + MX_LBO, mx_round(vi[q]));
+          }
         }
       } else {
 #pragma unroll
@@ -201,39 +222,31 @@ mode_gemm_tc_kernel(MixArgs t) {
           const int idx = it * MX_PROD + tid;
           const int j = idx & 3, k = (idx >> 2) & 3, n = idx >> 4;
           if (n0 + n >= t.N) continue;
+          float v[4];
+          ld_shared_v4(rb + (uint32_t)n * t.b_rn + (uint32_t)k * t.b_rk + (uint32_t)j * 16, v);
           const uint32_t o = sb + (uint32_t)(2 * j) * TILE_B + (uint32_t)(n >> 3) * MX_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)k * 4;
-          st_shared_f32(o, round_tf32(r.b[it].x));
-          st_shared_f32(o + MX_LBO, round_tf32(r.b[it].y));
-          st_shared_f32(o + TILE_B, round_tf32(r.b[it].z));
-          st_shared_f32(o + TILE_B + MX_LBO, round_tf32(r.b[it].w));
+          st_shared_f32(o, mx_round(v[0]));
+          st_shared_f32(o + MX_LBO, mx_round(v[1]));
+          st_shared_f32(o + TILE_B, mx_round(v[2]));
+          st_shared_f32(o + TILE_B + MX_LBO, mx_round(v[3]));
         }
       }
       fence_proxy_async();  // the tensor core reads what this thread wrote through the async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);  // one arrive per warp: 256 arrives per chunk serialise on the barrier word
-    };
-    // Groups of P chunks: all loads of a group are issued, then its chunks are transposed one by one (one register set and one
-    // operand stage per chunk). What bounds the kernel is the L1TEX wavefront count, not bytes: a mode-contiguous operand
-    // gives a warp-wide 16-byte load only 32 - 64 useful bytes per 128-byte line (8 - 16 lines per instruction at ~2 cycles per
-    // line), the transposing stores are one wavefront each, and the output runs are 64 bytes (profiles/r2_modemix.md)
-    MxRegs r[P];
-    for (int c = 0; c < nch; c += P) {
-#pragma unroll
-      for (int u = 0; u < P; ++u)
-        if (c + u < nch) load(c + u, r[u]);
-#pragma unroll
-      for (int u = 0; u < P; ++u)
-        if (c + u < nch) store(c + u, r[u]);
+      if (lane == 0) {
+        mbar_arrive(&full[s]);      // one arrive per warp
+        mbar_arrive(&rawempty[rs]);
+      }
     }
 
     // ===================== epilogue: TMEM -> registers -> 32-byte runs along the mode axis =====================
     mbar_wait(&done, 0);
     tc_fence_after();
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, half = warp >> 2;  // TMEM lane quarter, column quarter
     const int m = m0 + 16 * quad + (lane >> 1);
     const int part = lane & 1;  // 0: this lane holds Re C(m, :), 1: Im C(m, :)
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int nb = half * (NT / 2); nb < (half + 1) * (NT / 2); nb += 8) {
+    for (int nb = half * (NT / 4); nb < (half + 1) * (NT / 4); nb += 8) {
       float v[MX_PT][8];
 #pragma unroll
       for (int q = 0; q < MX_PT; ++q) tmem_ld8(trow + (uint32_t)(q * NT + nb), v[q]);
@@ -265,8 +278,8 @@ mode_gemm_tc_kernel(MixArgs t) {
             const int qm = (q & 1) + 4 * (q >> 1);  // 0, 1, 4, 5: the re lane's modes; the im lane's are qm + 2
             const float send = part ? v[qm][nn] : v[qm + 2][nn];
             const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            x[q] = round_tf32(part ? recv : v[qm][nn]);
-            y[q] = round_tf32(part ? v[qm + 2][nn] : recv);
+            x[q] = mx_round_store(part ? recv : v[qm][nn]);
+            y[q] = mx_round_store(part ? v[qm + 2][nn] : recv);
           }
           if (ok) {
             float4* dst = reinterpret_cast<float4*>(t.c2 + (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + p0 + 2 * part);
@@ -276,7 +289,7 @@ mode_gemm_tc_kernel(MixArgs t) {
         }
       }
     }
-  } else {
+  } else if (warp == MX_PROD / 32) {
     // ===================== MMA issuer (warp convergent, one elected lane issues) =====================
     const uint32_t idesc = idesc_tf32(128, NT, /*a_mn_major=*/false, /*b_mn_major=*/false);
     const uint64_t adesc0 = smem_desc_none(smem0, MX_LBO, MX_SBO);
@@ -300,30 +313,74 @@ mode_gemm_tc_kernel(MixArgs t) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MX_PROD / 32) {
     tc_fence_after();
     tmem_dealloc<TCOLS>(tmem_base);
   }
 }
 
+struct MixMaps {
+  CUtensorMap a, b0, b1;
+};
+
 template <int NT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
-static void launch_nt(const MixArgs& t, int64_t J, cudaStream_t s) {
-  constexpr int NS = 4;
-  constexpr size_t smem = (size_t)NS * mx_stage_bytes<NT>();
+static int launch_nt(MixArgs t, int64_t J, cudaStream_t s) {
+  constexpr int NS = 2;
+  constexpr int R = NT == 32 ? 5 : 3;
+  constexpr size_t smem = (size_t)NS * mx_stage_bytes<NT>() + (size_t)R * mx_raw_bytes<NT>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static DeviceOnce attr;
   if (attr.first_use())
-    cudaFuncSetAttribute(mode_gemm_tc_kernel<NT, NS, B_PLANAR, C_PLANAR, CONJ_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(mode_gemm_tc_kernel<NT, NS, R, B_PLANAR, C_PLANAR, CONJ_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
+  // tensor maps: the mode axis is the contiguous one of every operand; (row, k) ordered by their strides
+  MixMaps mp;
+  {
+    t.a_k_inner = t.a_sk < t.a_sm ? 1 : 0;
+    const uint64_t dims[3] = {(uint64_t)(2 * J), (uint64_t)(t.a_k_inner ? t.K : t.M), (uint64_t)(t.a_k_inner ? t.M : t.K)};
+    const uint64_t str[2] = {(uint64_t)(t.a_k_inner ? t.a_sk : t.a_sm) * 8, (uint64_t)(t.a_k_inner ? t.a_sm : t.a_sk) * 8};
+    const uint32_t box[3] = {16, (uint32_t)(t.a_k_inner ? MX_KC : 64), (uint32_t)(t.a_k_inner ? 64 : MX_KC)};
+    PDEQX_TRY(make_tensor_map(&mp.a, t.a, 3, dims, str, box, TM_NONE));
+    t.a_rk = t.a_k_inner ? 64 : 64 * 64;
+    t.a_rm = t.a_k_inner ? 64 * MX_KC : 64;
+  }
+  if (B_PLANAR) {
+    // weights (G, o, i, *m): n = o, k = i (mix) or n = i, k = o (adjoint mix)
+    t.b_k_inner = t.b_sk < t.b_sn ? 1 : 0;
+    const int64_t mprod = t.mm.mprod;
+    const int64_t d1 = (t.b_k_inner ? t.b_sn : t.b_sk) / mprod;  // = I
+    const int64_t d2 = t.w_corner / (d1 * mprod);                // = O
+    int G = 1;
+    for (int a = 0; a < t.mm.D - 1; ++a) G *= 2;
+    const uint64_t dims[4] = {(uint64_t)mprod, (uint64_t)d1, (uint64_t)d2, (uint64_t)G};
+    const uint64_t str[3] = {(uint64_t)mprod * 4, (uint64_t)d1 * mprod * 4, (uint64_t)t.w_corner * 4};
+    const uint32_t box[4] = {8, (uint32_t)(t.b_k_inner ? MX_KC : NT), (uint32_t)(t.b_k_inner ? NT : MX_KC), 1};
+    PDEQX_TRY(make_tensor_map(&mp.b0, t.br, 4, dims, str, box, TM_NONE));
+    PDEQX_TRY(make_tensor_map(&mp.b1, t.bi, 4, dims, str, box, TM_NONE));
+    t.b_rk = t.b_k_inner ? 32 : NT * 32;
+    t.b_rn = t.b_k_inner ? 32 * MX_KC : 32;
+  } else {
+    // interleaved B (dW): x_hat [b = k, i = n, J]
+    t.b_k_inner = 0;
+    const uint64_t dims[3] = {(uint64_t)(2 * J), (uint64_t)t.N, (uint64_t)t.K};
+    const uint64_t str[2] = {(uint64_t)t.b_sn * 8, (uint64_t)t.b_sk * 8};
+    const uint32_t box[3] = {16, (uint32_t)NT, (uint32_t)MX_KC};
+    PDEQX_TRY(make_tensor_map(&mp.b0, t.b2, 3, dims, str, box, TM_NONE));
+    mp.b1 = mp.b0;
+    t.b_rk = NT * 64;
+    t.b_rn = 64;
+  }
   dim3 grid((unsigned)(J / MX_PT), (unsigned)ceil_div(t.N, NT), (unsigned)ceil_div(t.M, 64));
-  mode_gemm_tc_kernel<NT, NS, B_PLANAR, C_PLANAR, CONJ_B><<<grid, MX_PROD + 32, smem, s>>>(t);
+  mode_gemm_tc_kernel<NT, NS, R, B_PLANAR, C_PLANAR, CONJ_B><<<grid, MX_PROD + 64, smem, s>>>(mp.a, mp.b0, mp.b1, t);
+  return PDEQX_OK;
 }
 
 template <bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
-static void launch(const MixArgs& t, int64_t J, cudaStream_t s) {
+static int launch(const MixArgs& t, int64_t J, cudaStream_t s) {
   // 32-column tiles unless 64-column tiles already fill the GPU
   const int64_t tiles64 = (J / MX_PT) * ceil_div(t.N, 64) * ceil_div(t.M, 64);
-  if (t.N <= 32 || tiles64 < 148) launch_nt<32, B_PLANAR, C_PLANAR, CONJ_B>(t, J, s);
-  else launch_nt<64, B_PLANAR, C_PLANAR, CONJ_B>(t, J, s);
+  if (t.N <= 32 || tiles64 < 148) return launch_nt<32, B_PLANAR, C_PLANAR, CONJ_B>(t, J, s);
+  return launch_nt<64, B_PLANAR, C_PLANAR, CONJ_B>(t, J, s);
 }
 
 }  // namespace tc
@@ -331,15 +388,16 @@ static void launch(const MixArgs& t, int64_t J, cudaStream_t s) {
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 bool tc_mode_gemm_available(const pdeqx_spectral_plan* p) {
-  static const bool off = getenv("PDEQX_TC_MODEMIX") && atoi(getenv("PDEQX_TC_MODEMIX")) == 0;  // experiment knob
-  if (off || p->desc.precision != PDEQX_PREC_TF32 || !g_fast_paths.load(std::memory_order_relaxed) || !p->tc) return false;
+  // experiment knob: PDEQX_TC_MODEMIX=0 keeps the CUDA-core kernel, =2 takes this one whenever the shape allows it
+  static const int knob = getenv("PDEQX_TC_MODEMIX") ? atoi(getenv("PDEQX_TC_MODEMIX")) : 1;
+  if (knob == 0 || p->desc.precision != PDEQX_PREC_TF32 || !g_fast_paths.load(std::memory_order_relaxed) || !p->tc) return false;
+  // measured (B200, profiles/r2_modemix.md): ahead of the CUDA-core kernel from 16 samples per GPU and 64 channels on; level with
+  // it where that kernel is a pure stream over the weights (8 samples per GPU), behind it on the padded 32-channel mode space
+  // of configs[4]
+  if (knob != 2 && (p->desc.batch < 16 || p->desc.c_in < 64 || p->desc.c_out < 64)) return false;
   const int D = p->desc.ndim;
   int64_t mprod = 1;
   for (int a = 0; a < D; ++a) mprod *= p->desc.modes[a];
-  // measured (B200, profiles/r2_modemix.md): ahead of the CUDA-core kernel from 32 samples per GPU and 64 channels on (26 vs 45 us
-  // at B = 64, C = 64); behind it where that kernel is a pure stream over the weights (B = 8: 17 vs 13 us) and on the padded
-  // 32-channel mode space of configs[4]
-  if (p->desc.batch < 32 || p->desc.c_in < 64 || p->desc.c_out < 64) return false;
   // 8-mode tiles must not straddle a row of the data layout; 16-byte weight runs start on 4-mode boundaries
   return p->mlast % 8 == 0 && p->desc.modes[D - 1] % 4 == 0 && mprod % 4 == 0 && p->J % 8 == 0 && p->J / 8 < (1ll << 31) &&
          ceil_div(p->desc.batch, 64) <= 65535;
@@ -360,8 +418,8 @@ int tc_mode_mix(const pdeqx_spectral_plan* p, const float* in, const float* w_re
   t.b_sk = transposed_conj ? (int64_t)I * t.mm.mprod : t.mm.mprod;
   t.c2 = (float2*)out; t.c_sm = (int64_t)U * p->J; t.c_sn = p->J;
   t.M = d.batch; t.N = U; t.K = V; t.w_corner = (int64_t)O * I * t.mm.mprod;
-  if (transposed_conj) tc::launch<true, false, true>(t, p->J, s);
-  else tc::launch<true, false, false>(t, p->J, s);
+  if (transposed_conj) PDEQX_TRY((tc::launch<true, false, true>(t, p->J, s)));
+  else PDEQX_TRY((tc::launch<true, false, false>(t, p->J, s)));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
@@ -377,7 +435,7 @@ int tc_mode_mix_dw(const pdeqx_spectral_plan* p, const float* ghat, const float*
   t.b2 = (const float2*)xhat; t.b_sn = p->J; t.b_sk = (int64_t)d.c_in * p->J;
   t.cr = gw_re; t.ci = gw_im; t.c_sm = (int64_t)d.c_in * t.mm.mprod; t.c_sn = t.mm.mprod;
   t.M = d.c_out; t.N = d.c_in; t.K = d.batch; t.w_corner = (int64_t)d.c_out * d.c_in * t.mm.mprod;
-  tc::launch<false, true, true>(t, p->J, s);
+  PDEQX_TRY((tc::launch<false, true, true>(t, p->J, s)));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }

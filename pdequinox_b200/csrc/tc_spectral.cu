@@ -1399,7 +1399,7 @@ void tc_plan_free(pdeqx_spectral_plan* p) {
 int tc_stage_mask(const pdeqx_spectral_plan* p) {
   TcPlan* t = tcp(p);
   if (!t || !g_fast_paths.load(std::memory_order_relaxed)) return 0;
-  return (t->r2c_ok ? 1 : 0) | (t->slab_ok ? 2 : 0) | (t->wgrad_ok ? 4 : 0);
+  return (t->r2c_ok ? 1 : 0) | (t->slab_ok ? 2 : 0) | (t->wgrad_ok ? 4 : 0) | (tc_mode_gemm_available(p) ? 8 : 0);
 }
 
 bool tc_r2c_available(const pdeqx_spectral_plan* p) {

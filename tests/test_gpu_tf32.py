@@ -40,6 +40,12 @@ CASES = [
     (2, 2, 32, 32, (64, 64), (12, 12)),
     (2, 2, 64, 64, (64, 128), (8, 12)),
     (2, 3, 32, 32, (32, 32), (4, 8)),            # W = 32: four rows per unit
+    # >= 16 samples and >= 64 channels: the per-mode channel mix and its two adjoints run on tcgen05 (tc_modemix.cu)
+    (2, 16, 64, 64, (16, 128), (4, 16)),
+    (2, 40, 64, 64, (8, 128), (4, 12)),          # ragged batch tile, a half-valid 8-mode tile (12 modes in a row of 16)
+    (2, 72, 64, 64, (8, 128), (4, 8)),           # two batch tiles (the second one ragged), 18 K chunks in the weight gradient
+    (1, 32, 64, 64, (128,), (16,)),
+    (3, 32, 64, 64, (4, 6, 128), (2, 3, 16)),
 ]
 
 
@@ -64,7 +70,8 @@ def test_tf32_spectral_block(cuda, D, B, ci, co, spatial, modes, act):
 
         plan = get_plan(D, B, ci, co, spatial, modes)
         mask = _lib.lib().pdeqx_spectral_plan_tcgen05_stages(plan.handle)
-        assert mask == 7, f"tcgen05 stages not enabled for this shape (mask {mask})"
+        assert mask & 7 == 7, f"tcgen05 stages not enabled for this shape (mask {mask})"
+        assert bool(mask & 8) == (B >= 16 and min(ci, co) >= 64), f"channel mix on the wrong path (mask {mask})"
 
         blk = pdeqx.ClassicSpectralBlock(D, ci, co, activation=getattr(pdeqx.nn, act), num_modes=modes, key=0)
         blk.spectral_conv.weights_real, blk.spectral_conv.weights_imag = dev(wr), dev(wi)
