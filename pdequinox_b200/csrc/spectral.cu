@@ -623,7 +623,16 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     float* s1 = r.lift + 256;
     float* s0 = r.lift + 384;
     TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
-    PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, 1, d.c_out, n_pix, lift_u, lift_w, gpre, nullptr, s1, s0, stream));
+    if (fast && tc_wgrad_available(p, n_pix) && fuse_r2c_mode() == 1 && tc_wgrad_r2c_available(p)) {
+      // the two reductions are the bypass weight gradient against a ONE-channel input: the tcgen05 weight-gradient kernel
+      // takes the field as its x operand, and its pass over gpre also applies the first DFT stage (no second read of gpre)
+      PDEQX_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)d.c_out, s));
+      PDEQX_CUDA(cudaMemsetAsync(s0, 0, sizeof(float) * (size_t)d.c_out, s));
+      PDEQX_TRY(tc_wgrad(p, gpre, lift_u, n_pix, s1, s0, s, (D == 1) ? r.mode[0] : r.big[0], /*rank1=*/true));
+      r2c_done = true;
+    } else {
+      PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, 1, d.c_out, n_pix, lift_u, lift_w, gpre, nullptr, s1, s0, stream));
+    }
     lift_unfold_wgrad_kernel<<<(d.c_out * d.c_in + 255) / 256, 256, 0, s>>>(s1, s0, lift_w, lift_b, d.c_out, d.c_in, g_bypass_w,
                                                                          bypass_b ? g_bypass_b : nullptr);
     PDEQX_LAUNCHED();

@@ -80,9 +80,10 @@ int tc_chain(const pdeqx_spectral_plan* p, float* w_prep, float* w_prep2, const 
              const float* x_up, const float* z_up, const float* w_up, const float* bias_up, int act, float* out, cudaStream_t s,
              const float* byp_u = nullptr, const float* byp_a = nullptr);
 bool tc_wgrad_available(const pdeqx_spectral_plan* p, int64_t n_pix);
-// gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller)
+// gw[c_out,c_in] += sum g x^T, gb[c_out] += sum g (outputs zeroed by the caller); rank1: x is a single-channel field
+// [B, 1, pixels] (the input of a 1 -> C lifting that was folded into the block) and gw is [c_out]
 int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb,
-             cudaStream_t s, float* x1_out = nullptr);
+             cudaStream_t s, float* x1_out = nullptr, bool rank1 = false);
 bool tc_wgrad_r2c_available(const pdeqx_spectral_plan* p);
 
 }  // namespace pdeqx

@@ -69,13 +69,6 @@ __device__ __forceinline__ uint64_t smem_desc_none(uint32_t smem_addr, uint32_t 
 // the next mode pair's tile already sits)
 __device__ __forceinline__ int mx_row(int mi) { return ((mi & 1) << 2) + ((mi >> 1) & 3) + ((mi >> 3) << 3); }
 
-// round-to-nearest for a value the tensor core will TRUNCATE to tf32: add half a tf32 ulp (one integer add; the low 13 bits
-// that remain are ignored by the MMA). Finite inputs only.
-__device__ __forceinline__ float mx_round(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
-
-// the same with the low bits cleared: for values that go back to global memory (any consumer may read them)
-__device__ __forceinline__ float mx_round_store(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
-
 // raw operand chunk as TMA leaves it: A 64 rows x 4 k x 64 B (8 modes complex), B NT rows x 4 k x 64 B (interleaved) or two
 // planes of NT x 4 x 32 B (planar); which of (row, k) is the faster box dimension depends on the operand (byte strides
 // a_rm / a_rk / b_rn / b_rk in MixArgs)
@@ -183,8 +176,8 @@ mode_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (j >= 2 && !gv1) v[0] = v[1] = v[2] = v[3] = 0.f;  // padding modes: exact zeros whatever the other operand holds
         // rows 2m (re) and 2m + 1 (im) of the A' tiles of modes 2j and 2j + 1
         const uint32_t o = sa + (uint32_t)(2 * j) * MX_TILE_A + (uint32_t)(m >> 2) * MX_SBO + (uint32_t)((2 * m) & 7) * 16 + (uint32_t)k * 4;
-        const float re0 = mx_round(v[0]), im0 = mx_round(v[1]);
-        const float re1 = mx_round(v[2]), im1 = mx_round(v[3]);
+        const float re0 = round_tf32(v[0]), im0 = round_tf32(v[1]);
+        const float re1 = round_tf32(v[2]), im1 = round_tf32(v[3]);
         st_shared_f32(o, re0);
         st_shared_f32(o + MX_LBO, CONJ_B ? im0 : -im0);
         st_shared_f32(o + 16, im0);
@@ -212,8 +205,8 @@ mode_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           const uint32_t o = sb + (uint32_t)(4 * h) * TILE_B + (uint32_t)(n >> 3) * MX_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)k * 4;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            st_shared_f32(o + (uint32_t)q * TILE_B, mx_round(vr[q]));
-            st_shared_f32(o + (uint32_t)q * TILE_B + MX_LBO, mx_round(vi[q]));
+            st_shared_f32(o + (uint32_t)q * TILE_B, round_tf32(vr[q]));
+            st_shared_f32(o + (uint32_t)q * TILE_B + MX_LBO, round_tf32(vi[q]));
           }
         }
       } else {
@@ -225,10 +218,10 @@ mode_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
           float v[4];
           ld_shared_v4(rb + (uint32_t)n * t.b_rn + (uint32_t)k * t.b_rk + (uint32_t)j * 16, v);
           const uint32_t o = sb + (uint32_t)(2 * j) * TILE_B + (uint32_t)(n >> 3) * MX_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)k * 4;
-          st_shared_f32(o, mx_round(v[0]));
-          st_shared_f32(o + MX_LBO, mx_round(v[1]));
-          st_shared_f32(o + TILE_B, mx_round(v[2]));
-          st_shared_f32(o + TILE_B + MX_LBO, mx_round(v[3]));
+          st_shared_f32(o, round_tf32(v[0]));
+          st_shared_f32(o + MX_LBO, round_tf32(v[1]));
+          st_shared_f32(o + TILE_B, round_tf32(v[2]));
+          st_shared_f32(o + TILE_B + MX_LBO, round_tf32(v[3]));
         }
       }
       fence_proxy_async();  // the tensor core reads what this thread wrote through the async proxy
@@ -278,8 +271,8 @@ mode_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int qm = (q & 1) + 4 * (q >> 1);  // 0, 1, 4, 5: the re lane's modes; the im lane's are qm + 2
             const float send = part ? v[qm][nn] : v[qm + 2][nn];
             const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            x[q] = mx_round_store(part ? recv : v[qm][nn]);
-            y[q] = mx_round_store(part ? v[qm + 2][nn] : recv);
+            x[q] = round_tf32(part ? recv : v[qm][nn]);
+            y[q] = round_tf32(part ? v[qm + 2][nn] : recv);
           }
           if (ok) {
             float4* dst = reinterpret_cast<float4*>(t.c2 + (int64_t)m * t.c_sm + (int64_t)n * t.c_sn + p0 + 2 * part);

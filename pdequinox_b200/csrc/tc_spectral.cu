@@ -1041,6 +1041,9 @@ r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
 // ==========================================================================================
 struct WgradParams {
   int c_out, c_in, chunks_per_row, lead, stages;
+  int c_in_pad;  // rows of the x box (>= c_in, a multiple of 8): a single-channel x (the field in front of a 1 -> C lifting)
+                 // is loaded as a 16-row box whose other rows (the next samples' fields) only feed accumulator columns
+                 // that are never read back
   int64_t rows;  // batch * lead image rows; a unit = one row = chunks_per_row stages of 32 pixels
   float* gw;
   float* gb;
@@ -1063,7 +1066,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   const bool fused = p.x1 != nullptr;
   const uint32_t tab_bytes = fused ? (uint32_t)p.chunks_per_row * 4096 : 0;
   uint8_t* stage0 = smem + tab_bytes;
-  const uint32_t g_bytes = (uint32_t)p.c_out * 128, x_bytes = (uint32_t)p.c_in * 128;
+  const uint32_t g_bytes = (uint32_t)p.c_out * 128, x_bytes = (uint32_t)p.c_in_pad * 128;
   const uint32_t stage_bytes = g_bytes + x_bytes + 2048;
   uint64_t* bars = (uint64_t*)(stage0 + (size_t)p.stages * stage_bytes + 16384);  // 16 KB slack: A tile of the last stage
   uint64_t* full = bars;
@@ -1106,7 +1109,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
   const int64_t first = blockIdx.x, stride = gridDim.x;
   const int64_t groups = (p.rows + kWgGroup - 1) / kWgGroup;  // a CTA walks groups of kWgGroup consecutive image rows
-  const int N = p.c_in + 16;
+  const int N = p.c_in_pad + 16;
   const int W = p.chunks_per_row * 32;
 
   if (warp == 0) {
@@ -1263,7 +1266,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
             for (int j = 0; j < 16; ++j) {
               const int i = c0 + j;
               if (i < p.c_in) atomicAdd(p.gw + (int64_t)o * p.c_in + i, v[j]);
-              else if (i == p.c_in && p.gb) atomicAdd(p.gb + o, v[j]);
+              else if (i == p.c_in_pad && p.gb) atomicAdd(p.gb + o, v[j]);
             }
           }
         }
@@ -1728,7 +1731,7 @@ bool tc_wgrad_r2c_available(const pdeqx_spectral_plan* p) {
 // gw [c_out, c_in] and gb [c_out] must be zeroed by the caller. x1_out (optional): the first stage of the
 // adjoint-of-inverse DFT of g, [B * c_out * lead][32] -- the same pass over g that feeds the weight gradient
 int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64_t n_pix, float* gw, float* gb, cudaStream_t s,
-             float* x1_out) {
+             float* x1_out, bool rank1) {
   TcPlan* t = tcp(p);
   const pdeqx_spectral_desc& d = p->desc;
   const int sD = d.spatial[d.ndim - 1];
@@ -1741,15 +1744,18 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
     uint32_t box[2] = {32, (uint32_t)d.c_out};
     PDEQX_TRY(tc::make_tensor_map(&tm_g, g, 2, dims, str, box));
   }
+  // rank1: x is the single-channel field [B, 1, pixels] in front of a 1 -> C lifting; gw is [c_out] (one column)
+  const int c_in = rank1 ? 1 : d.c_in, c_in_pad = rank1 ? 16 : d.c_in;
   {
-    uint64_t dims[2] = {(uint64_t)n_pix, (uint64_t)d.batch * d.c_in};
+    uint64_t dims[2] = {(uint64_t)n_pix, (uint64_t)d.batch * c_in};
     uint64_t str[1] = {(uint64_t)n_pix * 4};
-    uint32_t box[2] = {32, (uint32_t)d.c_in};
+    uint32_t box[2] = {32, (uint32_t)c_in_pad};
     PDEQX_TRY(tc::make_tensor_map(&tm_x, x, 2, dims, str, box));
   }
   tc::WgradParams wp{};
   wp.c_out = d.c_out;
-  wp.c_in = d.c_in;
+  wp.c_in = c_in;
+  wp.c_in_pad = c_in_pad;
   wp.chunks_per_row = sD / 32;
   wp.lead = (int)p->lead;
   wp.rows = (int64_t)d.batch * p->lead;
@@ -1760,7 +1766,7 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   static const bool m64_on = [] { const char* e = getenv("PDEQX_WG_M64"); return !(e && e[0] == '0'); }();  // (0: M = 128, A = [g ; x])
   wp.m64 = (m64_on && d.c_out <= 64) ? 1 : 0;
   const uint32_t tab_bytes = x1_out ? (uint32_t)wp.chunks_per_row * 4096 : 0;
-  const uint32_t stage_bytes = (uint32_t)(d.c_out + d.c_in) * 128 + 2048;
+  const uint32_t stage_bytes = (uint32_t)(d.c_out + c_in_pad) * 128 + 2048;
   int stages = (int)((227 * 1024 - 16384 - 2048 - (int)tab_bytes) / (int)stage_bytes);
   if (stages > 12) stages = 12;
   PDEQX_CHECK_ARG(stages >= 2, "tc_wgrad: shared memory does not fit two stages");
