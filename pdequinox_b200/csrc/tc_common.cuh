@@ -380,6 +380,16 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   return r;
 }
 
+// round both lanes to tf32 precision (11 significant bits, to nearest) with three packed instructions: Veltkamp's split
+// hi = p + (v - p), p = (2^13 + 1) v. cvt.rna.tf32.f32 is not a native instruction on sm_100a (FSETP + predicated IADD + LOP3
+// per value), and the epilogues that store tensor-core operands are bound by their instruction count. Ties go to even instead
+// of away from zero; NaN stays NaN; |v| > 4e34 overflows to NaN (such a value has already diverged).
+__device__ __forceinline__ f32x2 round_tf32x2(f32x2 v) {
+  const f32x2 c = pk2(8193.0f, 8193.0f), m1 = pk2(-1.0f, -1.0f);
+  const f32x2 p = mul2(v, c);
+  return add2(p, fma2(p, m1, v));
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

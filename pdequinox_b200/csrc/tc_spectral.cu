@@ -489,17 +489,15 @@ slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             f32x2 val = add2(pk2(v[j], v[j + 1]), pk2(bias_c[j], bias_c[j + 1]));
             if (BYP1) val = fma2(pk2(bypa_c[j], bypa_c[j + 1]), su2, val);
             float r0, r1;
-            if (MODE == 0 || MODE == 4) {
+            if (MODE == 4) {
               upk2(gelu2(val), r0, r1);
-              if (MODE == 4) {
-                pacc = fmaf(auxw_c[j], r0, pacc);
-                pacc = fmaf(auxw_c[j + 1], r1, pacc);
-                continue;
-              }
-            } else {
-              upk2(mul2(pk2(g[j], g[j + 1]), gelu_grad2(val)), r0, r1);
+              pacc = fmaf(auxw_c[j], r0, pacc);
+              pacc = fmaf(auxw_c[j + 1], r1, pacc);
+              continue;
             }
-            if (kRoundOut) { r0 = round_tf32(r0); r1 = round_tf32(r1); }
+            f32x2 out = MODE == 0 ? gelu2(val) : mul2(pk2(g[j], g[j + 1]), gelu_grad2(val));
+            if (kRoundOut) out = round_tf32x2(out);
+            upk2(out, r0, r1);
             st_shared_f32(row0 + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r0);
             st_shared_f32(row0 + (uint32_t)(j + 1) * 128 + (lane_b ^ ((uint32_t)((j + 1) & 7) << 4)), r1);
           }
@@ -868,10 +866,10 @@ chain_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
             f32x2 pre = add2(pk2(v2[j], v2[j + 1]), pk2(bias_c[j], bias_c[j + 1]));
             if (BYP1) pre = fma2(pk2(bypa_c[j], bypa_c[j + 1]), su2, pre);
             float r0, r1;
-            upk2(mul2(pk2(v1[j], v1[j + 1]), gelu_grad2(pre)), r0, r1);
             // read next as a tcgen05 operand (weight gradient, data gradient): round, do not let it truncate
-            st_shared_f32(col + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), round_tf32(r0));
-            st_shared_f32(col + (uint32_t)(j + 1) * 128 + (lane_b ^ ((uint32_t)((j + 1) & 7) << 4)), round_tf32(r1));
+            upk2(round_tf32x2(mul2(pk2(v1[j], v1[j + 1]), gelu_grad2(pre))), r0, r1);
+            st_shared_f32(col + (uint32_t)j * 128 + (lane_b ^ ((uint32_t)(j & 7) << 4)), r0);
+            st_shared_f32(col + (uint32_t)(j + 1) * 128 + (lane_b ^ ((uint32_t)((j + 1) & 7) << 4)), r1);
           }
         } else {
 #pragma unroll
