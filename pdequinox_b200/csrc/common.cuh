@@ -15,6 +15,8 @@ namespace pdeqx {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_fast_paths;
+// a[0:na] = b[0:nb] = 0 by one small kernel (either pointer may be null): see core.cu
+int zero_small(float* a, int64_t na, float* b, int64_t nb, cudaStream_t s);
 
 #define PDEQX_CHECK_ARG(cond, ...)                 \
   do {                                             \

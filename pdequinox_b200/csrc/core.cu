@@ -12,6 +12,26 @@ static thread_local char t_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_fast_paths{1};
 
+// ---- small accumulators zeroed by a KERNEL node -------------------------------------------------
+// Inside a replayed CUDA graph a memset node costs ~3 us of idle time on top of its own 1.5 us (CUPTI timeline of the train step,
+// profiles/r2_graph_timeline_b8.txt), a kernel node none: the per-block gradient accumulators (a few KB each, 13 per step) are
+// cleared by this kernel, two buffers per launch.
+__global__ void zero2_kernel(float* __restrict__ a, int64_t na, float* __restrict__ b, int64_t nb) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < na) a[i] = 0.f;
+    else b[i - na] = 0.f;
+  }
+}
+int zero_small(float* a, int64_t na, float* b, int64_t nb, cudaStream_t s) {
+  if (!a) na = 0;
+  if (!b) nb = 0;
+  if (na + nb == 0) return PDEQX_OK;
+  const int64_t blocks = (na + nb + 255) / 256;
+  zero2_kernel<<<(int)(blocks < 64 ? blocks : 64), 256, 0, s>>>(a, na, b, nb);
+  PDEQX_LAUNCHED();
+  return PDEQX_OK;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

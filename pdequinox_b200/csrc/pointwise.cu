@@ -421,8 +421,7 @@ extern "C" int pdeqx_pointwise_bwd(int32_t batch, int32_t c_in, int32_t c_out, i
   cudaStream_t s = (cudaStream_t)stream;
   if (gx)  // gx[b,i,n] = sum_o w[o,i] gy[b,o,n]: the forward op with W' = w^T (roles of c_in/c_out swapped)
     PDEQX_TRY(pointwise_apply(batch, c_out, c_in, n_pixels, gy, w, 1, c_in, nullptr, nullptr, PDEQX_ACT_IDENTITY, gx, s));
-  PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)c_in * c_out, s));
-  if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)c_out, s));
+  PDEQX_TRY(zero_small(gw, (int64_t)c_in * c_out, gb, c_out, s));
   if (batch == 0 || n_pixels == 0) return PDEQX_OK;
   const int nbig = c_out >= c_in ? c_out : c_in, nsmall = c_out >= c_in ? c_in : c_out;
   if (nsmall == 1 && n_pixels % 1024 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)gy % 16 == 0) {

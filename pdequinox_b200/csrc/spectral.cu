@@ -559,7 +559,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
   PDEQX_CHECK_ARG(!lifted || (fast && act != PDEQX_ACT_IDENTITY && bypass_w && lift_gw),
                   "the lifted reverse pass needs the tcgen05 slab kernel, a fused activation and a bypass");
   PDEQX_CHECK_ARG(!proj_gw || (gy_w && d.c_out <= 64), "proj_gw needs the rank-one cotangent (gy_w) and c_out <= 64");
-  if (proj_gw) PDEQX_CUDA(cudaMemsetAsync(proj_gw, 0, sizeof(float) * (size_t)d.c_out, s));
+  if (proj_gw) PDEQX_TRY(zero_small(proj_gw, d.c_out, nullptr, 0, s));
   PDEQX_CHECK_ARG(!gy_w || (fast && act != PDEQX_ACT_IDENTITY),
                   "a rank-1 cotangent needs the tcgen05 slab kernel and a fused activation (pdeqx_spectral_block_rank1_ok)");
   if (!gy_is_gpre && !gy_w && !lifted && fast && chunk > 0 && act != PDEQX_ACT_IDENTITY && bypass_w && tc_wgrad_available(p, n_pix) && tc_r2c_available(p)) {
@@ -569,8 +569,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     const int mD = p->mlast;
     float* x1 = (D == 1) ? r.mode[0] : r.big[0];
     float* gb = bypass_b ? g_bypass_b : nullptr;
-    PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));
-    if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)d.c_out, s));
+    PDEQX_TRY(zero_small(g_bypass_w, (int64_t)d.c_in * d.c_out, gb, d.c_out, s));
     for (int b0 = 0; b0 < d.batch; b0 += chunk) {
       pdeqx_spectral_plan pc = *p;  // shallow copy: same tables, fewer samples
       pc.desc.batch = d.batch - b0 < chunk ? d.batch - b0 : chunk;
@@ -626,8 +625,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     if (fast && tc_wgrad_available(p, n_pix) && fuse_r2c_mode() == 1 && tc_wgrad_r2c_available(p)) {
       // the two reductions are the bypass weight gradient against a ONE-channel input: the tcgen05 weight-gradient kernel
       // takes the field as its x operand, and its pass over gpre also applies the first DFT stage (no second read of gpre)
-      PDEQX_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * (size_t)d.c_out, s));
-      PDEQX_CUDA(cudaMemsetAsync(s0, 0, sizeof(float) * (size_t)d.c_out, s));
+      PDEQX_TRY(zero_small(s1, d.c_out, s0, d.c_out, s));
       PDEQX_TRY(tc_wgrad(p, gpre, lift_u, n_pix, s1, s0, s, (D == 1) ? r.mode[0] : r.big[0], /*rank1=*/true));
       r2c_done = true;
     } else {
@@ -639,9 +637,8 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
   } else if (bypass_w) {
     if (fast && tc_wgrad_available(p, n_pix)) {
       TimedScope timed(PDEQX_K_POINTWISE_WGRAD, s);
-      PDEQX_CUDA(cudaMemsetAsync(g_bypass_w, 0, sizeof(float) * (size_t)d.c_in * d.c_out, s));
       float* gb = bypass_b ? g_bypass_b : nullptr;
-      if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)d.c_out, s));
+      PDEQX_TRY(zero_small(g_bypass_w, (int64_t)d.c_in * d.c_out, gb, d.c_out, s));
       // step 3a rides along: the kernel that streams gpre for the weight gradient also applies the first DFT stage
       float* x1 = nullptr;
       if (fuse_r2c_mode() == 1 && tc_wgrad_r2c_available(p)) {
@@ -690,8 +687,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
   }
   if (fast && lift_u) {
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
-    PDEQX_CUDA(cudaMemsetAsync(lift_gw, 0, sizeof(float) * (size_t)d.c_in, s));
-    if (lift_gb) PDEQX_CUDA(cudaMemsetAsync(lift_gb, 0, sizeof(float) * (size_t)d.c_in, s));
+    PDEQX_TRY(zero_small(lift_gw, d.c_in, lift_gb, d.c_in, s));
     return tc_slab_ex(p, r.wprep[0], gpre, gx1, /*table_sel=*/1, bypass_w, /*bypass_transposed=*/true, nullptr, PDEQX_ACT_IDENTITY, /*mode=*/3,
                       lift_u, d.c_out, d.c_in, nullptr, s, nullptr, lift_gw, lift_gb);
   }

@@ -1096,9 +1096,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);  // 128 (gW | gb) + 2 x kWgGroup x 32 (first-DFT-stage tiles)
   // ones rows (bias-gradient columns) and a defined value everywhere an A/B descriptor can reach
-  for (uint32_t i = threadIdx.x; i < ((uint32_t)S * stage_bytes + 16384) / 4; i += blockDim.x) {
-    const uint32_t in_stage = (i * 4) % stage_bytes;
-    ((float*)stage0)[i] = (i * 4 < (uint32_t)S * stage_bytes && in_stage >= g_bytes + x_bytes) ? 1.0f : 0.0f;
+  if (p.m64) {
+    // M = 64: A is exactly the g box and B the x box + the ones rows -- TMA rewrites both boxes before every use, so only the
+    // ones rows need a value (the full fill below is ~200 KB of shared-memory stores per CTA: 3-4 us of a 60 us launch at 8
+    // samples per GPU)
+    for (uint32_t i = threadIdx.x; i < (uint32_t)S * 512; i += blockDim.x)
+      ((float*)(stage0 + (size_t)(i >> 9) * stage_bytes + g_bytes + x_bytes))[i & 511] = 1.0f;
+  } else {
+    for (uint32_t i = threadIdx.x; i < ((uint32_t)S * stage_bytes + 16384) / 4; i += blockDim.x) {
+      const uint32_t in_stage = (i * 4) % stage_bytes;
+      ((float*)stage0)[i] = (i * 4 < (uint32_t)S * stage_bytes && in_stage >= g_bytes + x_bytes) ? 1.0f : 0.0f;
+    }
   }
   fence_proxy_async();
   tc_fence_before();
