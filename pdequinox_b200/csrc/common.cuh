@@ -1,5 +1,6 @@
 // Shared helpers for libpdeqx_b200 (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -15,6 +16,34 @@ namespace pdeqx {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 extern std::atomic<int> g_fast_paths;
+// ---- programmatic dependent launch (experiment, PDEQX_PDL=1 switches it on; see pdl_enabled() in core.cu) ------
+// With the switch on every kernel of the spectral train step is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts
+// with pdl_enter(): griddepcontrol.launch_dependents (the NEXT kernel's CTAs may be scheduled as soon as every CTA of this
+// grid has started) followed by griddepcontrol.wait (nothing of global memory is touched, and no exclusive SM resource such
+// as tensor memory is taken, before the previous grid has completed and flushed). What overlaps is the launch latency and
+// the CTA ramp-up of kernel N + 1 with the tail of kernel N -- a replayed step is ~70 kernels, a dozen of them 2 - 8 us long.
+bool pdl_enabled();
+template <typename... Params, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 // a[0:na] = b[0:nb] = 0 by one small kernel (either pointer may be null): see core.cu
 int zero_small(float* a, int64_t na, float* b, int64_t nb, cudaStream_t s);
 

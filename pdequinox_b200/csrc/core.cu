@@ -17,17 +17,26 @@ std::atomic<int> g_fast_paths{1};
 // profiles/r2_graph_timeline_b8.txt), a kernel node none: the per-block gradient accumulators (a few KB each, 13 per step) are
 // cleared by this kernel, two buffers per launch.
 __global__ void zero2_kernel(float* __restrict__ a, int64_t na, float* __restrict__ b, int64_t nb) {
+  pdl_enter();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
     if (i < na) a[i] = 0.f;
     else b[i - na] = 0.f;
   }
 }
+bool pdl_enabled() {
+  // off unless PDEQX_PDL=1: measured SLOWER on B200 (configs[3] step 6.269 -> 6.365 ms, 1.199 -> 1.228 ms at 8 samples per GPU):
+  // the CUPTI timeline of the replayed graph shows no idle time between kernel nodes to win back, and the early-scheduled CTAs
+  // of kernel N + 1 hold SM slots while they wait
+  static const bool on = [] { const char* e = getenv("PDEQX_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
+
 int zero_small(float* a, int64_t na, float* b, int64_t nb, cudaStream_t s) {
   if (!a) na = 0;
   if (!b) nb = 0;
   if (na + nb == 0) return PDEQX_OK;
   const int64_t blocks = (na + nb + 255) / 256;
-  zero2_kernel<<<(int)(blocks < 64 ? blocks : 64), 256, 0, s>>>(a, na, b, nb);
+  PDEQX_CUDA(launch_pdl(zero2_kernel, dim3((unsigned)(blocks < 64 ? blocks : 64)), dim3(256), 0, s, a, na, b, nb));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }

@@ -52,6 +52,7 @@ constexpr int kMsePartials = 1024;
 __global__ void __launch_bounds__(256)
 mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ gpred,
                    float* __restrict__ partials, int64_t n, float gscale) {
+  pdl_enter();
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float d = pred[i] - target[i];
@@ -71,6 +72,7 @@ mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tar
 
 __global__ void __launch_bounds__(256)
 mse_final_kernel(const float* __restrict__ partials, int nparts, double inv_n, float* __restrict__ loss) {
+  pdl_enter();
   double acc = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += (double)partials[i];
   __shared__ double red[256];
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu,
             int64_t n, float lr, float b1, float b2, float eps, float inv_c1, float inv_c2, float gscale,
             const float* __restrict__ corr) {
+  pdl_enter();
   if (corr) {  // bias corrections of the device-side step counter (CUDA-graph replays)
     inv_c1 = corr[1];
     inv_c2 = corr[2];
@@ -158,9 +161,9 @@ extern "C" int pdeqx_mse_loss(int64_t n, const float* pred, const float* target,
   PDEQX_CHECK_ARG(n > 0 && pred && target && loss && partials, "bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   int blocks = (int)(ceil_div(n, 256 * 8) < kMsePartials ? ceil_div(n, 256 * 8) : kMsePartials);
-  mse_partial_kernel<<<blocks, 256, 0, s>>>(pred, target, gpred, partials, n, grad_scale * 2.0f / (float)n);
+  PDEQX_CUDA(launch_pdl(mse_partial_kernel, dim3(blocks), dim3(256), 0, s, pred, target, gpred, partials, n, grad_scale * 2.0f / (float)n));
   PDEQX_LAUNCHED();
-  mse_final_kernel<<<1, 256, 0, s>>>(partials, blocks, 1.0 / (double)n, loss);
+  PDEQX_CUDA(launch_pdl(mse_final_kernel, dim3(1), dim3(256), 0, s, partials, blocks, 1.0 / (double)n, loss));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
@@ -181,6 +184,7 @@ extern "C" int pdeqx_adam_step(int64_t n, float* param, const float* grad, float
 
 // state[0] = update count (int32 bits), state[1] = 1 / (1 - b1^t), state[2] = 1 / (1 - b2^t)
 __global__ void adam_tick_kernel(float* state, float b1, float b2) {
+  pdl_enter();
   const int t = __float_as_int(state[0]) + 1;
   state[0] = __int_as_float(t);
   state[1] = (float)(1.0 / (1.0 - pow((double)b1, (double)t)));
@@ -193,10 +197,11 @@ extern "C" int pdeqx_adam_step_dev(int64_t n, float* param, const float* grad, f
   PDEQX_CHECK_ARG(aligned16(param) && aligned16(grad) && aligned16(mu) && aligned16(nu),
                   "arena pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  adam_tick_kernel<<<1, 1, 0, s>>>(state, b1, b2);
+  PDEQX_CUDA(launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, s, state, b1, b2));
   PDEQX_LAUNCHED();
   if (n == 0) return PDEQX_OK;
-  adam_kernel<<<stream_blocks(n / 4 + 1), 256, 0, s>>>(param, grad, mu, nu, n, lr, b1, b2, eps, 1.f, 1.f, grad_scale, state);
+  PDEQX_CUDA(launch_pdl(adam_kernel, dim3(stream_blocks(n / 4 + 1)), dim3(256), 0, s, param, grad, mu, nu, n, lr, b1, b2, eps, 1.f, 1.f, grad_scale,
+                        (const float*)state));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }

@@ -168,6 +168,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int PT, int RT, bool B_PLANAR, bool C_PLANAR, bool CONJ_B, int NS = (RT == 1 ? 4 : (RT == 2 ? 3 : 2))>
 __global__ void __launch_bounds__(256, 2)
 mode_gemm_tiled_kernel(TiledArgs t) {
+  pdl_enter();
   constexpr int NQ = 32 / PT;   // n-quads per warp-row group ... threads = PT * 8 * NQ
   constexpr int NT = 4 * NQ;    // columns per CTA
   constexpr int TM_MT = 8 * RT; // rows per CTA
@@ -302,7 +303,7 @@ static bool launch_tiled_pt(const TiledArgs& t, cudaStream_t s) {
                            cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                                    \
                                                                                                                        \
     }                                                                                                                  \
-    mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B><<<grid, 256, smem, s>>>(t);                            \
+    if (launch_pdl(mode_gemm_tiled_kernel<PT, RT_, B_PLANAR, C_PLANAR, CONJ_B>, grid, dim3(256), smem, s, t) != cudaSuccess) return false;                            \
   } while (0)
   switch (rt) {
     case 1: PDEQX_MODE_GEMM(1); break;

@@ -352,6 +352,7 @@ template <bool BIG_IS_GY>
 __global__ void __launch_bounds__(256, 2)
 pw_wgrad_c1_kernel(const float* __restrict__ big, const float* __restrict__ small_, float* __restrict__ gw,
                    float* __restrict__ gb, int batch, int nbig, int64_t n) {
+  pdl_enter();
   __shared__ float red[8][2 * WC_CG + 1];
   const int c0 = blockIdx.y * WC_CG;
   const int64_t chunks = n / 1024;  // the launcher guarantees n % 1024 == 0
@@ -431,8 +432,8 @@ extern "C" int pdeqx_pointwise_bwd(int32_t batch, int32_t c_in, int32_t c_out, i
     int per_group = (148 * 2 + groups - 1) / groups;  // 2 resident CTAs per SM over all channel groups
     if (per_group > units) per_group = (int)units;
     dim3 grid(per_group, groups);
-    if (big_is_gy) pw_wgrad_c1_kernel<true><<<grid, 256, 0, s>>>(gy, x, gw, gb, batch, nbig, n_pixels);
-    else pw_wgrad_c1_kernel<false><<<grid, 256, 0, s>>>(x, gy, gw, gb, batch, nbig, n_pixels);
+    if (big_is_gy) PDEQX_CUDA(launch_pdl(pw_wgrad_c1_kernel<true>, grid, dim3(256), 0, s, gy, x, gw, gb, batch, nbig, n_pixels));
+    else PDEQX_CUDA(launch_pdl(pw_wgrad_c1_kernel<false>, grid, dim3(256), 0, s, x, gy, gw, gb, batch, nbig, n_pixels));
     PDEQX_LAUNCHED();
     return PDEQX_OK;
   }

@@ -259,6 +259,7 @@ __device__ __forceinline__ float to_tf32(float v) {  // round to nearest, as the
 }
 
 __global__ void fill_kernel(float* __restrict__ out, int64_t n, const float* __restrict__ value) {
+  pdl_enter();
   const float v = value ? value[0] : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
 }
@@ -267,6 +268,7 @@ __global__ void fill_kernel(float* __restrict__ out, int64_t n, const float* __r
 // a[o] = sum_i Wb[o,i] wl[i];  c[o] = sum_i Wb[o,i] bl[i] + bb[o]: the bypass of the lifted input is a[o] u[pixel] + c[o]
 __global__ void lift_fold_bypass_kernel(const float* __restrict__ wb, const float* __restrict__ bb, const float* __restrict__ wl,
                                         const float* __restrict__ bl, int co, int ci, float* __restrict__ a, float* __restrict__ c) {
+  pdl_enter();
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= co) return;
   float sa = 0.f, sc = bb ? bb[o] : 0.f;
@@ -283,6 +285,7 @@ __global__ void lift_fold_bypass_kernel(const float* __restrict__ wb, const floa
 __global__ void __launch_bounds__(256)
 lift_x1_kernel(const float4* __restrict__ u1, const float* __restrict__ wl, const float* __restrict__ bl, float sD, int C, int64_t lead,
                int64_t total4, int round, float4* __restrict__ x1) {
+  pdl_enter();
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (int64_t)gridDim.x * blockDim.x) {
     const int k4 = (int)(idx & 7);          // float4 index inside the 32-float row
     const int64_t row = idx >> 3;            // (b C + o) lead + l
@@ -306,6 +309,7 @@ lift_x1_kernel(const float4* __restrict__ u1, const float* __restrict__ wl, cons
 // bypass gradients from the two reductions s1[o] = sum g u, s0[o] = sum g:  gW[o,i] = s1[o] wl[i] + s0[o] bl[i];  gb[o] = s0[o]
 __global__ void lift_unfold_wgrad_kernel(const float* __restrict__ s1, const float* __restrict__ s0, const float* __restrict__ wl,
                                          const float* __restrict__ bl, int co, int ci, float* __restrict__ gw, float* __restrict__ gb) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= co * ci) return;
   const int o = idx / ci, i = idx % ci;
@@ -440,7 +444,7 @@ static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x,
     PDEQX_TRY(stage_r2c(p, lift_u, p->t_r2c_fwd, (int64_t)d.batch * p->lead, u1, s));
     const int64_t total4 = (int64_t)d.batch * d.c_in * p->lead * 8;
     const int blocks = (int)(ceil_div(total4, 256) < 148 * 16 ? ceil_div(total4, 256) : 148 * 16);
-    lift_x1_kernel<<<blocks, 256, 0, s>>>((const float4*)u1, lift_w, lift_b, (float)sD, d.c_in, p->lead, total4, 1, (float4*)r.big[0]);
+    PDEQX_CUDA(launch_pdl(lift_x1_kernel, dim3((unsigned)(blocks)), dim3(256), 0, s, (const float4*)u1, lift_w, lift_b, (float)sD, d.c_in, p->lead, total4, 1, (float4*)r.big[0]));
     PDEQX_LAUNCHED();
     PDEQX_TRY(forward_chain(p, nullptr, d.c_in, false, xhat, r, s, /*r2c_done=*/true));
   } else {
@@ -463,13 +467,13 @@ static int spectral_block_fwd_impl(const pdeqx_spectral_plan* p, const float* x,
     PDEQX_CHECK_ARG(proj_w && bypass_w && tc_slab_available(p, true),
                     "the projected forward pass needs the tcgen05 path (pdeqx_spectral_block_rank1_ok) and a bypass");
     const int64_t n1 = (int64_t)d.batch * n_pix;
-    fill_kernel<<<(int)(ceil_div(n1, 1024) < 148 * 8 ? ceil_div(n1, 1024) : 148 * 8), 256, 0, s>>>(proj_out, n1, proj_b);
+    PDEQX_CUDA(launch_pdl(fill_kernel, dim3((unsigned)((int)(ceil_div(n1, 1024) < 148 * 8 ? ceil_div(n1, 1024) : 148 * 8))), dim3(256), 0, s, proj_out, n1, proj_b));
     PDEQX_LAUNCHED();
   }
   if (lifted) {
     float* fa = r.lift;       // a[o]: per-channel factor of the rank-one bypass
     float* fc = r.lift + 128;  // c[o]: its constant part (+ bypass bias)
-    lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
+    PDEQX_CUDA(launch_pdl(lift_fold_bypass_kernel, dim3((unsigned)((d.c_out + 127) / 128)), dim3(128), 0, s, bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc));
     PDEQX_LAUNCHED();
     TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
     return tc_slab_ex(p, r.wprep[0], nullptr, z, /*table_sel=*/0, nullptr, false, fc, act, /*mode=*/projected ? 4 : 0, nullptr, d.c_in, d.c_out,
@@ -595,7 +599,7 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     if (lifted) {
       float* fa = r.lift;
       float* fc = r.lift + 128;
-      lift_fold_bypass_kernel<<<(d.c_out + 127) / 128, 128, 0, s>>>(bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc);
+      PDEQX_CUDA(launch_pdl(lift_fold_bypass_kernel, dim3((unsigned)((d.c_out + 127) / 128)), dim3(128), 0, s, bypass_w, bypass_b, lift_w, lift_b, d.c_out, d.c_in, fa, fc));
       PDEQX_LAUNCHED();
       TimedScope timed(PDEQX_K_SPECTRAL_SLAB, s);
       PDEQX_TRY(tc_slab_ex(p, r.wprep[0], nullptr, saved_z, 0, nullptr, false, fc, act, /*mode=*/gy_w ? (proj_gw ? 5 : 2) : 1, gy, d.c_in, d.c_out,
@@ -631,8 +635,8 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     } else {
       PDEQX_TRY(pdeqx_pointwise_bwd(d.batch, 1, d.c_out, n_pix, lift_u, lift_w, gpre, nullptr, s1, s0, stream));
     }
-    lift_unfold_wgrad_kernel<<<(d.c_out * d.c_in + 255) / 256, 256, 0, s>>>(s1, s0, lift_w, lift_b, d.c_out, d.c_in, g_bypass_w,
-                                                                         bypass_b ? g_bypass_b : nullptr);
+    PDEQX_CUDA(launch_pdl(lift_unfold_wgrad_kernel, dim3((unsigned)((d.c_out * d.c_in + 255) / 256)), dim3(256), 0, s, s1, s0, lift_w, lift_b, d.c_out, d.c_in, g_bypass_w,
+                                                                         bypass_b ? g_bypass_b : nullptr));
     PDEQX_LAUNCHED();
   } else if (bypass_w) {
     if (fast && tc_wgrad_available(p, n_pix)) {
@@ -678,8 +682,8 @@ static int spectral_block_bwd_impl(const pdeqx_spectral_plan* p, const pdeqx_spe
     if (!a.up_x) {
       float* fa = r.lift;
       float* fc = r.lift + 128;
-      lift_fold_bypass_kernel<<<(d.c_in + 127) / 128, 128, 0, s>>>(a.up_bypass_w, a.up_bypass_b, a.up_lift_w, a.up_lift_b, d.c_in,
-                                                                  a.up_plan->desc.c_in, fa, fc);
+      PDEQX_CUDA(launch_pdl(lift_fold_bypass_kernel, dim3((unsigned)((d.c_in + 127) / 128)), dim3(128), 0, s, a.up_bypass_w, a.up_bypass_b, a.up_lift_w, a.up_lift_b, d.c_in,
+                                                                  a.up_plan->desc.c_in, fa, fc));
       PDEQX_LAUNCHED();
       return tc_chain(p, r.wprep[0], r.wprep[1], gpre, gx1, bypass_w, a.up_plan, nullptr, a.up_saved_z, nullptr, fc, a.up_activation, a.up_gpre, s, a.up_lift_u, fa);
     }

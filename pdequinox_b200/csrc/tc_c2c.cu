@@ -38,6 +38,7 @@ constexpr int kC2cThreads = 384;  // warps 0-2 roles, 4-11 epilogue (two warps p
 
 __global__ void __launch_bounds__(kC2cThreads, 1)
 c2c_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_tab, C2cParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t tab_chunk_bytes = (uint32_t)(2 * p.n_out) * 128;     // [2 n_out rows][32 k]
@@ -322,7 +323,7 @@ int tc_c2c(const pdeqx_spectral_plan* p, int axis, int kind, const float* in, fl
                 
   }
   const int grid = (int)(cp.units < t->sms ? cp.units : t->sms);
-  tc::c2c_kernel<<<grid, tc::kC2cThreads, smem, s>>>(tm_in, tb.map, cp);
+  PDEQX_CUDA(launch_pdl(tc::c2c_kernel, dim3(grid), dim3(tc::kC2cThreads), smem, s, tm_in, tb.map, cp));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }

@@ -80,6 +80,7 @@ template <int NT, int NS, int R, bool B_PLANAR, bool C_PLANAR, bool CONJ_B>
 __global__ void __launch_bounds__(MX_PROD + 64, 1)
 mode_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b0,
                     const __grid_constant__ CUtensorMap tm_b1, MixArgs t) {
+  pdl_enter();
   constexpr uint32_t TILE_B = mx_tile_b<NT>();
   constexpr uint32_t STAGE = mx_stage_bytes<NT>();
   constexpr uint32_t B_OFF = MX_PT * MX_TILE_A;  // B' tiles follow the A' tiles inside a stage
@@ -364,7 +365,7 @@ static int launch_nt(MixArgs t, int64_t J, cudaStream_t s) {
     t.b_rn = 64;
   }
   dim3 grid((unsigned)(J / MX_PT), (unsigned)ceil_div(t.N, NT), (unsigned)ceil_div(t.M, 64));
-  mode_gemm_tc_kernel<NT, NS, R, B_PLANAR, C_PLANAR, CONJ_B><<<grid, MX_PROD + 64, smem, s>>>(mp.a, mp.b0, mp.b1, t);
+  PDEQX_CUDA(launch_pdl(mode_gemm_tc_kernel<NT, NS, R, B_PLANAR, C_PLANAR, CONJ_B>, grid, dim3(MX_PROD + 64), smem, s, mp.a, mp.b0, mp.b1, t));
   return PDEQX_OK;
 }
 

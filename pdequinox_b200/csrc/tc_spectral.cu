@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1)
 slab_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_z,
             const __grid_constant__ CUtensorMap tm_tab, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_aux, SlabParams p, SlabSmem L) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + L.bar_off);
@@ -679,6 +680,7 @@ chain_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tm_tab1, const __grid_constant__ CUtensorMap tm_tab2,
              const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
              const __grid_constant__ CUtensorMap tm_y, ChainParams p, ChainSmem L) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + L.bar_off);
@@ -917,6 +919,7 @@ struct R2cParams {
 
 __global__ void __launch_bounds__(kThreadsR2c, 1)
 r2c_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_tab, R2cParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // [table: kchunks x 4 KB][stages x 16 KB][barriers]
@@ -1057,6 +1060,7 @@ constexpr int kWgGroup = 4;  // image rows whose first-DFT-stage results share o
 __global__ void __launch_bounds__(kThreadsR2c, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
              const __grid_constant__ CUtensorMap tm_tab, WgradParams p) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // [r2c table: chunks_per_row x 4 KB (fused only)] [stages] ; stage = [g box: c_out x 128 B][x box: c_in x 128 B][ones: 16 x 128 B];
@@ -1289,6 +1293,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ C
 
 // small prep kernel: rounded (and optionally transposed) copy of the bypass weight
 __global__ void prep_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int co, int ci, int transpose) {
+  pdl_enter();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= co * ci) return;
   int o = idx / ci, i = idx % ci;
@@ -1444,7 +1449,7 @@ int tc_r2c(const pdeqx_spectral_plan* p, const float* x, bool adjoint_table, int
                 
   }
   const int grid = (int)(rp.tiles < t->sms ? rp.tiles : t->sms);
-  tc::r2c_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_x, t->tm_tab_r2c[adjoint_table ? 1 : 0], rp);
+  PDEQX_CUDA(launch_pdl(tc::r2c_kernel, dim3(grid), dim3(tc::kThreadsR2c), smem, s, tm_x, t->tm_tab_r2c[adjoint_table ? 1 : 0], rp));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
@@ -1488,8 +1493,8 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, float* w_prep, const float* x, cons
     // rounded copy of the weight as [c_out rows][c_in] (K contiguous)
     const int n = c_in * c_out;
     // bypass_w is stored [rows_w][cols_w]; not transposed: [c_out][c_in]; transposed: stored [c_in][c_out]
-    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(bypass_w, w_prep, bypass_transposed ? c_in : c_out,
-                                                          bypass_transposed ? c_out : c_in, bypass_transposed ? 1 : 0);
+    PDEQX_CUDA(launch_pdl(tc::prep_weight_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, bypass_w, w_prep, bypass_transposed ? c_in : c_out,
+                                                          bypass_transposed ? c_out : c_in, bypass_transposed ? 1 : 0));
     PDEQX_LAUNCHED();
     uint64_t wd[2] = {(uint64_t)c_in, (uint64_t)c_out};
     uint64_t ws[1] = {(uint64_t)c_in * 4};
@@ -1557,7 +1562,7 @@ int tc_slab_ex(const pdeqx_spectral_plan* p, float* w_prep, const float* x, cons
       PDEQX_CUDA(cudaFuncSetAttribute(tc::slab_kernel<M, A, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
                                                                                                                           \
     }                                                                                                                     \
-    tc::slab_kernel<M, A, B1><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L);         \
+    PDEQX_CUDA(launch_pdl(tc::slab_kernel<M, A, B1>, dim3(grid), dim3(tc::kThreadsSlab), L.total, s, tm_x, tm_z, tab, tm_w, tm_y, tm_aux, sp, L)); \
   } while (0)
 #define PDEQX_SLAB_LAUNCH(M, A)                 \
   do {                                          \
@@ -1661,14 +1666,14 @@ int tc_chain(const pdeqx_spectral_plan* p, float* w_prep, float* w_prep2, const 
   }
   {
     const int n = C * C;
-    tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_k, w_prep, C, C, 1);  // w_k^T: [c_in rows][c_out]
+    PDEQX_CUDA(launch_pdl(tc::prep_weight_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, w_k, w_prep, C, C, 1));  // w_k^T: [c_in rows][c_out]
     PDEQX_LAUNCHED();
     uint64_t wd[2] = {(uint64_t)C, (uint64_t)C};
     uint64_t ws[1] = {(uint64_t)C * 4};
     uint32_t wb[2] = {32, (uint32_t)C};
     PDEQX_TRY(tc::make_tensor_map(&tm_w1, w_prep, 2, wd, ws, wb));
     if (!byp1) {
-      tc::prep_weight_kernel<<<(n + 255) / 256, 256, 0, s>>>(w_up, w_prep2, C, C, 0);
+      PDEQX_CUDA(launch_pdl(tc::prep_weight_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, w_up, w_prep2, C, C, 0));
       PDEQX_LAUNCHED();
       PDEQX_TRY(tc::make_tensor_map(&tm_w2, w_prep2, 2, wd, ws, wb));
     } else {
@@ -1701,8 +1706,8 @@ int tc_chain(const pdeqx_spectral_plan* p, float* w_prep, float* w_prep2, const 
       PDEQX_CUDA(cudaFuncSetAttribute(tc::chain_kernel<A, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
                                                                                                                            \
     }                                                                                                                      \
-    tc::chain_kernel<A, B1><<<grid, tc::kThreadsSlab, L.total, s>>>(tm_g, tm_z1, tm_x2, tm_z2, t->tm_tab_c2r[1],          \
-                                                                     tu->tm_tab_c2r[0], tm_w1, tm_w2, tm_y, cp, L);        \
+    PDEQX_CUDA(launch_pdl(tc::chain_kernel<A, B1>, dim3(grid), dim3(tc::kThreadsSlab), L.total, s, tm_g, tm_z1, tm_x2, tm_z2, t->tm_tab_c2r[1], \
+                          tu->tm_tab_c2r[0], tm_w1, tm_w2, tm_y, cp, L));                                                    \
   } while (0)
   if (act == PDEQX_ACT_GELU_TANH) {
     if (byp1) PDEQX_CHAIN_LAUNCH(PDEQX_ACT_GELU_TANH, true);
@@ -1785,7 +1790,7 @@ int tc_wgrad(const pdeqx_spectral_plan* p, const float* g, const float* x, int64
   }
   const int64_t wgroups = ceil_div(wp.rows, tc::kWgGroup);
   const int grid = (int)(wgroups < t->sms ? wgroups : t->sms);
-  tc::wgrad_kernel<<<grid, tc::kThreadsR2c, smem, s>>>(tm_g, tm_x, t->tm_tab_r2c[1], wp);
+  PDEQX_CUDA(launch_pdl(tc::wgrad_kernel, dim3(grid), dim3(tc::kThreadsR2c), smem, s, tm_g, tm_x, t->tm_tab_r2c[1], wp));
   PDEQX_LAUNCHED();
   return PDEQX_OK;
 }
