@@ -372,6 +372,12 @@ def run_ours(args):
     # W warm-up steps above are too short to reach it (20 steps of 7 ms measured 3 % slower when they came first than the same
     # steps half a second later). Replay untimed steps for ~0.4 s so that the timed region sees the sustained clocks.
     # (the number of steps is agreed between the ranks: they synchronise inside every step)
+    # The clock sampler starts BEFORE the settling steps: launching nvidia-smi (NVML initialisation) next to running kernels
+    # slowed the first tenths of a second of them by ~3 % (device-timed value 6.45 ms/step against 6.26 ms in the end-to-end
+    # arm of the same run, which started after the sampler had stopped); its samples cover the settling load and the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     settle_steps = max(2, min(400, int(400.0 / max(timed(run_step, 3) / 3.0, 0.05))))
     for _ in range(settle_steps):
         run_step()
@@ -379,9 +385,6 @@ def run_ours(args):
     settle_steps += 3
 
     # ---- device-resident arm ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms = timed(run_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = launches_per_step * args.steps
