@@ -612,8 +612,8 @@ extern "C" int pdeqx_conv_bwd_filter(const pdeqx_conv_desc* d, const float* x, c
   const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
   // (the tcgen05 pass overwrites every element of gw / gb: no memset nodes in front of it)
   if (g.batch > 0 && tc_conv_bwd_filter_available(g)) return tc_conv_bwd_filter(g, x, gy, gw, gb, workspace, workspace_bytes, s);
-  PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
-  if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
+  // (a kernel node, not two memset nodes: inside a replayed graph a memset node costs ~3 us of idle time, see core.cu)
+  PDEQX_TRY(zero_small(gw, (int64_t)g.c_out * cig * g.taps, gb, g.c_out, s));
   if (g.batch == 0) return PDEQX_OK;
   const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
   const int64_t chunks = ceil_div(g.n_out, WF_P);

@@ -375,8 +375,8 @@ extern "C" int pdeqx_convT_bwd_filter(const pdeqx_convT_desc* d, const float* x,
   PDEQX_TRY(convT_geometry(d, &g));
   cudaStream_t s = (cudaStream_t)stream;
   const int cog = g.c_out / g.groups, cig = g.c_in / g.groups;
-  PDEQX_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)g.c_out * cig * g.taps, s));
-  if (gb) PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)g.c_out, s));
+  // (a kernel node, not two memset nodes: inside a replayed graph a memset node costs ~3 us of idle time, see core.cu)
+  PDEQX_TRY(zero_small(gw, (int64_t)g.c_out * cig * g.taps, gb, g.c_out, s));
   if (g.batch == 0) return PDEQX_OK;
   const int o_tiles = (int)ceil_div(cog, 16), i_tiles = (int)ceil_div(cig, 16);
   const int64_t chunks = ceil_div(g.n_out, CT_WF_P);

@@ -1955,7 +1955,7 @@ static int conv_bwd_filter_launch(const ConvGeom& g, const float* x, const float
   tc::conv_wgrad_reduce_kernel<<<(9 * C * C + 255) / 256, 256, 0, s>>>(wp.scratch, gw, grid, C, nullptr, nullptr, nullptr, nullptr, nullptr);
   PDEQX_LAUNCHED();
   if (gb) {
-    PDEQX_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)C, s));
+    PDEQX_TRY(zero_small(gb, C, nullptr, 0, s));
     tc::conv_bias_grad_kernel<<<g.batch * C, 256, 0, s>>>(gy, gb, C, (int64_t)H * W);
     PDEQX_LAUNCHED();
   }
